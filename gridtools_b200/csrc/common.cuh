@@ -1,0 +1,210 @@
+// common.cuh -- shared host/device helpers of libgtb200 (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/gtb200.h"
+
+#define GTB_API extern "C" __attribute__((visibility("default")))
+
+namespace gtb {
+
+    // ---------------------------------------------------------------- errors (thread local, never throws)
+    void set_error(const char *fmt, ...);
+    int fail(gtb_status st, const char *fmt, ...);
+    int cuda_fail(cudaError_t e, const char *what);
+
+#define GTB_CUDA(call)                                   \
+    do {                                                 \
+        cudaError_t e__ = (call);                        \
+        if (e__ != cudaSuccess)                          \
+            return ::gtb::cuda_fail(e__, #call);         \
+    } while (0)
+
+    // ---------------------------------------------------------------- options
+    struct options {
+        int hd_variant = 0;   // 0 auto, 1 cp.async staged, 2 TMA staged
+        int hd_stages = 0;    // 0 auto
+        int hd_ctas_per_sm = 0;
+        int va_variant = 0;   // 0 auto, 1 register-prefetch LDG
+        int va_threads = 0;   // threads per CTA (multiple of 32)
+        int va_unroll = 0;    // k levels prefetched ahead
+        int va_scratch = 0;   // 0 auto, 1 global (L2) scratch, 2 shared memory
+        int va_hints = 1;     // L2 eviction-priority hints on/off
+        int copy_vec = 1;     // vectorised copy on/off
+    };
+    options &opts();
+
+    // ---------------------------------------------------------------- device info / scratch
+    struct device_state {
+        int device = -1;
+        int sm_count = 0;
+        int64_t l2_bytes = 0;
+        int64_t hbm_bytes = 0;
+        int max_smem_optin = 0;
+    };
+    // Lazily initialised state of the current device; nullptr + error set if there is no usable device.
+    device_state *dev();
+
+    // Cached scratch (temporaries): one growing slab per device, reused by every call on that device.  Stencil
+    // calls on different streams that both need scratch must not overlap (same rule as the reference's
+    // thread-local cached allocator).
+    void *scratch(size_t bytes);
+
+    extern std::atomic<int64_t> g_launches;
+    inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+    inline cudaStream_t as_stream(void *s) { return static_cast<cudaStream_t>(s); }
+
+    inline int check_launch(const char *what) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess)
+            return cuda_fail(e, what);
+        return GTB_OK;
+    }
+
+    inline bool field_ok(const gtb_field *f) { return f && f->ptr; }
+
+    // TMA descriptor encoder, resolved from the driver at run time (no link-time dependency on libcuda).
+    typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+        const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    encode_tiled_fn tensor_map_encoder();
+
+    constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+} // namespace gtb
+
+// ---------------------------------------------------------------------- device-side PTX wrappers
+namespace gtb {
+    namespace ptx {
+#ifdef __CUDACC__
+        __device__ __forceinline__ uint32_t smem_addr(const void *p) {
+            return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+        }
+        __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+        }
+        __device__ __forceinline__ void fence_barrier_init() {
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+        __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+                         : "memory");
+        }
+        __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+        }
+        __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+            uint32_t ok;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok)
+                : "r"(smem_addr(bar)), "r"(parity)
+                : "memory");
+            return ok != 0;
+        }
+        __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+            while (!mbar_try_wait(bar, parity)) {
+            }
+        }
+        // 3-D tiled TMA load global -> shared, completion on an mbarrier.
+        __device__ __forceinline__ void tma_load_3d(
+            void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+                " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_addr(dst)),
+                "l"(reinterpret_cast<uint64_t>(map)),
+                "r"(smem_addr(bar)),
+                "r"(c0),
+                "r"(c1),
+                "r"(c2)
+                : "memory");
+        }
+        __device__ __forceinline__ void tma_load_3d_hint(
+            void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, uint64_t policy) {
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+                " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_addr(dst)),
+                "l"(reinterpret_cast<uint64_t>(map)),
+                "r"(smem_addr(bar)),
+                "r"(c0),
+                "r"(c1),
+                "r"(c2),
+                "l"(policy)
+                : "memory");
+        }
+        __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *map) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+        }
+        __device__ __forceinline__ uint64_t policy_evict_first() {
+            uint64_t p;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+            return p;
+        }
+        __device__ __forceinline__ uint64_t policy_evict_last() {
+            uint64_t p;
+            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+            return p;
+        }
+        // cp.async (LDGSTS) with zero fill when !pred.
+        template <int Bytes>
+        __device__ __forceinline__ void cp_async(void *dst, const void *src, bool pred) {
+            static_assert(Bytes == 4 || Bytes == 8 || Bytes == 16, "cp.async size");
+            int n = pred ? Bytes : 0;
+            if constexpr (Bytes == 16)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr(dst)), "l"(src), "r"(n)
+                             : "memory");
+            else
+                asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(smem_addr(dst)),
+                             "l"(src),
+                             "n"(Bytes),
+                             "r"(n)
+                             : "memory");
+        }
+        __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+        template <int N>
+        __device__ __forceinline__ void cp_async_wait() {
+            asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+        }
+
+        // Streaming global accesses with an L2 eviction policy.
+        template <class T>
+        __device__ __forceinline__ T ld_hint(const T *p, uint64_t policy) {
+            T v;
+            if constexpr (sizeof(T) == 8) {
+                uint64_t r;
+                asm volatile("ld.global.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(r) : "l"(p), "l"(policy));
+                memcpy(&v, &r, 8);
+            } else {
+                uint32_t r;
+                asm volatile("ld.global.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(policy));
+                memcpy(&v, &r, 4);
+            }
+            return v;
+        }
+        template <class T>
+        __device__ __forceinline__ void st_hint(T *p, T v, uint64_t policy) {
+            if constexpr (sizeof(T) == 8) {
+                uint64_t r;
+                memcpy(&r, &v, 8);
+                asm volatile("st.global.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(p), "l"(r), "l"(policy) : "memory");
+            } else {
+                uint32_t r;
+                memcpy(&r, &v, 4);
+                asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(p), "r"(r), "l"(policy) : "memory");
+            }
+        }
+#endif
+    } // namespace ptx
+} // namespace gtb

@@ -1,0 +1,208 @@
+// runtime.cu -- error state, options, device state, cached scratch and the TMA descriptor encoder of libgtb200.
+#include "common.cuh"
+
+#include <mutex>
+#include <string>
+
+namespace gtb {
+
+    namespace {
+        thread_local char t_error[512] = "";
+        std::mutex g_mutex;
+        constexpr int max_devices = 64;
+        device_state g_dev[max_devices];
+        struct slab {
+            void *ptr = nullptr;
+            size_t bytes = 0;
+        } g_scratch[max_devices];
+        options g_opts;
+    } // namespace
+
+    std::atomic<int64_t> g_launches{0};
+
+    void set_error(const char *fmt, ...) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(t_error, sizeof(t_error), fmt, ap);
+        va_end(ap);
+    }
+
+    int fail(gtb_status st, const char *fmt, ...) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(t_error, sizeof(t_error), fmt, ap);
+        va_end(ap);
+        return st;
+    }
+
+    int cuda_fail(cudaError_t e, const char *what) {
+        snprintf(t_error, sizeof(t_error), "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+        return GTB_ERR_CUDA;
+    }
+
+    options &opts() { return g_opts; }
+
+    device_state *dev() {
+        int d = -1;
+        cudaError_t e = cudaGetDevice(&d);
+        if (e != cudaSuccess || d < 0 || d >= max_devices) {
+            cuda_fail(e, "cudaGetDevice (libgtb200 has no CPU fallback: a CUDA device is required)");
+            return nullptr;
+        }
+        device_state &s = g_dev[d];
+        if (s.device == d)
+            return &s;
+        std::lock_guard<std::mutex> lock(g_mutex);
+        if (s.device == d)
+            return &s;
+        cudaDeviceProp p;
+        e = cudaGetDeviceProperties(&p, d);
+        if (e != cudaSuccess) {
+            cuda_fail(e, "cudaGetDeviceProperties");
+            return nullptr;
+        }
+        if (p.major != 10) {
+            set_error("libgtb200 is built for sm_100a only; device %d is sm_%d%d", d, p.major, p.minor);
+            return nullptr;
+        }
+        s.sm_count = p.multiProcessorCount;
+        s.l2_bytes = p.l2CacheSize;
+        s.hbm_bytes = (int64_t)p.totalGlobalMem;
+        s.max_smem_optin = (int)p.sharedMemPerBlockOptin;
+        s.device = d;
+        return &s;
+    }
+
+    void *scratch(size_t bytes) {
+        device_state *s = dev();
+        if (!s)
+            return nullptr;
+        std::lock_guard<std::mutex> lock(g_mutex);
+        slab &sl = g_scratch[s->device];
+        if (sl.bytes >= bytes && sl.ptr)
+            return sl.ptr;
+        if (sl.ptr) {
+            cudaDeviceSynchronize(); // earlier kernels may still use the old slab
+            cudaFree(sl.ptr);
+            sl = slab{};
+        }
+        size_t want = bytes + bytes / 4; // head room so slightly larger domains do not reallocate
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            want = bytes;
+            e = cudaMalloc(&p, want);
+        }
+        if (e != cudaSuccess) {
+            cuda_fail(e, "cudaMalloc(scratch)");
+            return nullptr;
+        }
+        sl.ptr = p;
+        sl.bytes = want;
+        return p;
+    }
+
+    encode_tiled_fn tensor_map_encoder() {
+        static encode_tiled_fn fn = [] {
+            void *p = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+            if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+                p = nullptr;
+            return reinterpret_cast<encode_tiled_fn>(p);
+        }();
+        return fn;
+    }
+
+} // namespace gtb
+
+using namespace gtb;
+
+GTB_API int gtb_version(void) { return GTB_VERSION; }
+
+GTB_API const char *gtb_last_error(void) { return t_error; }
+
+GTB_API int gtb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+GTB_API int gtb_init(int device) {
+    GTB_CUDA(cudaSetDevice(device));
+    if (!dev())
+        return GTB_ERR_CUDA;
+    return GTB_OK;
+}
+
+GTB_API int gtb_device_info(int *sm_count, int64_t *l2_bytes, int64_t *hbm_bytes) {
+    device_state *s = dev();
+    if (!s)
+        return GTB_ERR_CUDA;
+    if (sm_count)
+        *sm_count = s->sm_count;
+    if (l2_bytes)
+        *l2_bytes = s->l2_bytes;
+    if (hbm_bytes)
+        *hbm_bytes = s->hbm_bytes;
+    return GTB_OK;
+}
+
+namespace {
+    int *find_option(const char *key) {
+        if (!key)
+            return nullptr;
+        options &o = opts();
+        struct {
+            const char *name;
+            int *ptr;
+        } table[] = {{"hd.variant", &o.hd_variant},
+            {"hd.stages", &o.hd_stages},
+            {"hd.ctas_per_sm", &o.hd_ctas_per_sm},
+            {"va.variant", &o.va_variant},
+            {"va.threads", &o.va_threads},
+            {"va.unroll", &o.va_unroll},
+            {"va.scratch", &o.va_scratch},
+            {"va.hints", &o.va_hints},
+            {"copy.vec", &o.copy_vec}};
+        for (auto &t : table)
+            if (strcmp(t.name, key) == 0)
+                return t.ptr;
+        return nullptr;
+    }
+} // namespace
+
+GTB_API int gtb_set_option(const char *key, int value) {
+    int *p = find_option(key);
+    if (!p)
+        return fail(GTB_ERR_ARG, "unknown option '%s'", key ? key : "(null)");
+    *p = value;
+    return GTB_OK;
+}
+
+GTB_API int gtb_get_option(const char *key, int *value) {
+    int *p = find_option(key);
+    if (!p || !value)
+        return fail(GTB_ERR_ARG, "unknown option '%s'", key ? key : "(null)");
+    *value = *p;
+    return GTB_OK;
+}
+
+GTB_API int gtb_release_scratch(void) {
+    device_state *s = dev();
+    if (!s)
+        return GTB_ERR_CUDA;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    slab &sl = g_scratch[s->device];
+    if (sl.ptr) {
+        cudaDeviceSynchronize();
+        cudaFree(sl.ptr);
+        sl = slab{};
+    }
+    return GTB_OK;
+}
+
+GTB_API int64_t gtb_launch_count(void) { return g_launches.load(); }

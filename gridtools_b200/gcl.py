@@ -1,0 +1,403 @@
+"""Host side of the halo exchange: a mirror of `gcl::halo_exchange_dynamic_ut` (gcl/halo_exchange.hpp:163-306) and of
+the Cartesian process grid `MPI_3D_process_grid_t` (gcl/low_level/proc_grids_3D.hpp:34-245) for ranks that live on
+one NVLink/NVSwitch box, one process per GPU.
+
+Layers
+  ProcGrid      pure host logic: coordinates, neighbour lookup with periodicity (proc_grids_3D.hpp:179-211)
+  HaloPlan      pure host logic: which storage region goes to / comes from which neighbour, message sizes
+                (common/halo_descriptor.hpp:90-201, gcl/high_level/empty_field_base.hpp:170-176)
+  transports    "p2p"  : fused pack + NVLink store into the neighbour's receive buffer, flag handshake on the device
+                         (libgtb200: gtb_halo_pack_send / wait / unpack) -- the product path on a B200 box
+                "nccl" : pack -> torch.distributed send/recv of the staging buffers -> unpack (NCCL point-to-point;
+                         also runs with gloo + an injected host codec, which is how the CPU tests exercise the
+                         choreography without a GPU)
+`torch.distributed` is plumbing only: it carries the 512-byte connection blobs and, for the "nccl" transport, the
+packed messages.
+"""
+import ctypes as C
+import itertools
+
+import numpy as np
+
+from . import _lib
+
+DIRECTIONS = [e for e in itertools.product((-1, 0, 1), repeat=3)]  # (e2, e1, e0) order, see dir_index
+
+
+def dir_index(e0, e1, e2):
+    """n = (e0+1) + 3*(e1+1) + 9*(e2+1), e_d = offset along storage dimension d (include/gtb200.h)."""
+    return (e0 + 1) + 3 * (e1 + 1) + 9 * (e2 + 1)
+
+
+def dir_of(n):
+    return (n % 3 - 1, (n // 3) % 3 - 1, n // 9 - 1)
+
+
+class ProcGrid:
+    """3-d Cartesian process grid, row-major ranks like MPI_Cart_create (proc_grids_3D.hpp:34-245)."""
+
+    def __init__(self, dims, periodic, rank):
+        self.dims = tuple(int(d) for d in dims)
+        self.periodic = tuple(bool(p) for p in periodic)
+        self.size = self.dims[0] * self.dims[1] * self.dims[2]
+        if not 0 <= rank < self.size:
+            raise ValueError("rank %d outside a %s process grid" % (rank, self.dims))
+        self.rank = int(rank)
+        self.coords = (rank // (self.dims[1] * self.dims[2]), (rank // self.dims[2]) % self.dims[1],
+                       rank % self.dims[2])
+
+    def proc(self, di, dj, dk):
+        """Rank of the neighbour at offset (di, dj, dk) in process-grid coordinates, -1 if outside
+        (proc_grids_3D.hpp:179-211)."""
+        c = [self.coords[0] + di, self.coords[1] + dj, self.coords[2] + dk]
+        for d in range(3):
+            if self.periodic[d]:
+                c[d] %= self.dims[d]
+            elif c[d] < 0 or c[d] >= self.dims[d]:
+                return -1
+        return (c[0] * self.dims[1] + c[1]) * self.dims[2] + c[2]
+
+    @staticmethod
+    def dims_create(nranks, ndims=2):
+        """Balanced factorisation like MPI_Dims_create; the trailing (3 - ndims) dimensions are 1.  J is split
+        first (i is the contiguous axis: J faces are contiguous slabs, I faces are strided strips)."""
+        dims = [1, 1, 1]
+        n, f, factors = nranks, 2, []
+        while n > 1:
+            while n % f == 0:
+                factors.append(f)
+                n //= f
+            f += 1
+        for f in sorted(factors, reverse=True):
+            d = min(range(ndims), key=lambda x: (dims[x], -x))
+            dims[d] *= f
+        dims[:ndims] = sorted(dims[:ndims])  # larger factor on the later (j) dimension
+        return tuple(dims)
+
+
+class HaloPlan:
+    """Regions and message sizes of one rank.  `halos[d]` = (minus, plus, begin, end, total) for USER dimension d;
+    `layout[d]` = position of user dimension d in increasing-stride order (0 = unit stride); `proc_layout[d]` =
+    process-grid dimension user dimension d is distributed over."""
+
+    def __init__(self, halos, grid: ProcGrid, layout=(0, 1, 2), proc_layout=(0, 1, 2)):
+        if sorted(layout) != [0, 1, 2] or sorted(proc_layout) != [0, 1, 2]:
+            raise ValueError("layout and proc_layout must be permutations of (0, 1, 2)")
+        self.grid = grid
+        self.layout, self.proc_layout = tuple(layout), tuple(proc_layout)
+        self.halos_user = [tuple(int(x) for x in h) for h in halos]
+        self.halos = [None, None, None]  # storage order
+        for d in range(3):
+            self.halos[layout[d]] = self.halos_user[d]
+        for m, p, b, e, t in self.halos:
+            if m < 0 or p < 0 or b < m or e < b or e + p >= t:
+                raise ValueError("inconsistent halo descriptor (%d, %d, %d, %d, %d)" % (m, p, b, e, t))
+        self.neighbour = [-1] * 27
+        for n in range(27):
+            if n == 13:
+                continue
+            es = dir_of(n)  # storage-order direction
+            off = [0, 0, 0]
+            for d in range(3):
+                off[proc_layout[d]] = es[layout[d]]
+            self.neighbour[n] = grid.proc(*off)
+
+    # common/halo_descriptor.hpp:90-201
+    @staticmethod
+    def _inside(h, e):
+        m, p, b, en, _ = h
+        return (en - m + 1 if e == 1 else b), (b + p - 1 if e == -1 else en)
+
+    @staticmethod
+    def _outside(h, e):
+        m, p, b, en, _ = h
+        if e == 0:
+            return b, en
+        return (en + 1, en + p) if e == 1 else (b - m, b - 1)
+
+    def send_region(self, n):
+        """[(lo, hi)] * 3 in storage order (inclusive) of what goes to neighbour n."""
+        return [self._inside(self.halos[d], e) for d, e in enumerate(dir_of(n))]
+
+    def recv_region(self, n):
+        return [self._outside(self.halos[d], e) for d, e in enumerate(dir_of(n))]
+
+    @staticmethod
+    def _count(region):
+        c = 1
+        for lo, hi in region:
+            c *= max(0, hi - lo + 1)
+        return c
+
+    def send_count(self, n):
+        return 0 if n == 13 or self.neighbour[n] < 0 else self._count(self.send_region(n))
+
+    def recv_count(self, n):
+        return 0 if n == 13 or self.neighbour[n] < 0 else self._count(self.recv_region(n))
+
+    def storage_shape(self):
+        """numpy shape (slowest first) of a field."""
+        return tuple(self.halos[d][4] for d in (2, 1, 0))
+
+    # host codec used by the gloo tests (numpy, dimension 0 fastest == last numpy axis)
+    def pack_numpy(self, n, fields):
+        (a0, b0), (a1, b1), (a2, b2) = self.send_region(n)
+        return np.concatenate([np.ascontiguousarray(f[a2:b2 + 1, a1:b1 + 1, a0:b0 + 1]).ravel() for f in fields])
+
+    def unpack_numpy(self, n, fields, msg):
+        (a0, b0), (a1, b1), (a2, b2) = self.recv_region(n)
+        shape = (b2 - a2 + 1, b1 - a1 + 1, b0 - a0 + 1)
+        cnt = shape[0] * shape[1] * shape[2]
+        for i, f in enumerate(fields):
+            f[a2:b2 + 1, a1:b1 + 1, a0:b0 + 1] = msg[i * cnt:(i + 1) * cnt].reshape(shape)
+
+
+def message_tag(n):
+    """Tag of the message SENT towards direction n; the receiver posts the matching receive for direction 26 - n
+    with the same tag (the reference derives its MPI tag from the direction too, Halo_Exchange_3D.hpp:217-219)."""
+    return n
+
+
+class TorchComm:
+    """torch.distributed as the out-of-band channel (blobs) and, for transport='nccl', the message transport."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.size = dist.get_world_size(group)
+
+    def all_gather_bytes(self, data: bytes):
+        out = [None] * self.size
+        self.dist.all_gather_object(out, data, group=self.group)
+        return out
+
+    def exchange(self, sends, recvs):
+        """sends / recvs: lists of (peer_rank, tag, tensor).  Posts all receives, then all sends, then waits --
+        the order of Halo_Exchange_3D::exchange (:792-931).  Messages between the same pair are matched by posting
+        order, so both lists must be sorted by tag on the two sides."""
+        ops = [self.dist.P2POp(self.dist.irecv, t, peer, group=self.group) for peer, _, t in recvs]
+        ops += [self.dist.P2POp(self.dist.isend, t, peer, group=self.group) for peer, _, t in sends]
+        if ops:
+            for w in self.dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def barrier(self):
+        self.dist.barrier(group=self.group)
+
+
+class halo_exchange_dynamic_ut:
+    """gcl::halo_exchange_dynamic_ut<DataLayout, ProcLayout, T, Arch> (gcl/halo_exchange.hpp:163-306).
+
+        he = halo_exchange_dynamic_ut(periodicity, grid, dtype, layout=(0,1,2), proc_layout=(0,1,2), comm=...)
+        he.add_halo(0, minus, plus, begin, end, total); he.add_halo(1, ...); he.add_halo(2, ...)
+        he.setup(max_fields)
+        he.pack(f0, f1); he.exchange(); he.unpack(f0, f1)
+
+    Fields are DataStore objects (or anything with raw_ptr()) or raw device pointers (ints) to storage element
+    (0,0,0) including the halo -- the `T*` of the reference.
+    """
+
+    def __init__(self, periodicity, grid: ProcGrid, dtype, layout=(0, 1, 2), proc_layout=(0, 1, 2), comm=None,
+                 transport="p2p", codec=None):
+        self.grid = grid
+        self.dtype = np.dtype(dtype)
+        self.layout, self.proc_layout = tuple(layout), tuple(proc_layout)
+        per = [False] * 3
+        for d in range(3):
+            per[proc_layout[d]] = bool(periodicity[d])  # c.permute<layout2proc_map_abs>() (:202)
+        if tuple(per) != grid.periodic:
+            raise ValueError("periodicity %s does not match the process grid's %s" % (per, grid.periodic))
+        if transport not in ("p2p", "nccl", "host"):
+            raise ValueError("transport must be 'p2p', 'nccl' or 'host'")
+        self.comm, self.transport, self.codec = comm, transport, codec
+        self._halos = [None, None, None]
+        self.plan = None
+        self._h = None
+        self._packed = None
+
+    def comm_grid(self):
+        """comm() of the reference (:306): the process grid."""
+        return self.grid
+
+    def add_halo(self, dim, minus, plus=None, begin=None, end=None, total=None):
+        """add_halo<D>(minus, plus, begin, end, total) or add_halo<D>(halo_descriptor) (:235,:240)."""
+        if plus is None:
+            minus, plus, begin, end, total = minus
+        self._halos[dim] = (minus, plus, begin, end, total)
+
+    def setup(self, max_fields):
+        """setup(max_fields) (:216): builds the plan, allocates buffers, connects the neighbours."""
+        if any(h is None for h in self._halos):
+            raise RuntimeError("setup() called before add_halo() for all three dimensions")
+        self.max_fields = int(max_fields)
+        self.plan = HaloPlan(self._halos, self.grid, self.layout, self.proc_layout)
+        if self.transport == "host":
+            return
+        self._export()
+        if self.transport == "p2p" and self.comm is not None:  # comm=None: several ranks in one process,
+            blobs = self.comm.all_gather_bytes(self.blob)      # the caller finishes with connect_local()
+            self._connect(blobs)
+
+    def _export(self):
+        L = _lib.lib()
+        desc = (_lib.HaloDesc * 3)(*[_lib.HaloDesc(*h) for h in self.plan.halos])
+        nbr = (C.c_int * 27)(*self.plan.neighbour)
+        h = C.c_void_p()
+        _lib.check(L.gtb_halo_create(desc, nbr, self.grid.rank, self.max_fields, self.dtype.itemsize, C.byref(h)))
+        self._h = h
+        buf = C.create_string_buffer(_lib.HALO_BLOB_BYTES)
+        _lib.check(L.gtb_halo_export(self._h, buf))
+        self.blob = buf.raw
+
+    def _connect(self, blobs_by_rank):
+        keep = [C.create_string_buffer(blobs_by_rank[r], _lib.HALO_BLOB_BYTES) if r >= 0 else None
+                for r in self.plan.neighbour]
+        arr = (C.c_void_p * 27)(*[C.cast(b, C.c_void_p) if b is not None else None for b in keep])
+        _lib.check(_lib.lib().gtb_halo_connect(self._h, arr))
+
+    # ------------------------------------------------------------------ the three phases
+    def _ptrs(self, fields):
+        if len(fields) == 1 and isinstance(fields[0], (list, tuple)):
+            fields = fields[0]  # pack(vector<T*>) overload (:250)
+        if len(fields) > self.max_fields:
+            raise ValueError("%d fields passed, setup() was told at most %d" % (len(fields), self.max_fields))
+        ptrs = [f.raw_ptr() if hasattr(f, "raw_ptr") else int(f) for f in fields]
+        return (C.c_void_p * max(1, len(ptrs)))(*ptrs), len(ptrs)
+
+    @staticmethod
+    def _stream():
+        import torch
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def pack(self, *fields):
+        if self.transport == "host":
+            f = fields[0] if len(fields) == 1 and isinstance(fields[0], (list, tuple)) else fields
+            self._packed = {n: self.codec.pack(self.plan, n, f) for n in range(27) if self.plan.send_count(n)}
+            self._nf = len(f)
+            return
+        arr, n = self._ptrs(fields)
+        self._nf = n
+        fn = _lib.lib().gtb_halo_pack_send if self.transport == "p2p" else _lib.lib().gtb_halo_pack
+        _lib.check(fn(self._h, arr, n, self._stream()))
+
+    def exchange(self):
+        """exchange() = start_exchange() + wait() (:284-304)."""
+        self.start_exchange()
+        self.wait()
+
+    def post_receives(self):
+        pass  # receives are implicit: NVLink stores land in the exported arena / batch_isend_irecv posts them
+
+    def do_sends(self):
+        self.start_exchange()
+
+    def start_exchange(self):
+        if self.transport == "p2p":
+            return  # pack() already pushed the messages and raised the neighbours' flags
+        sends, recvs = [], []
+        if self.transport == "nccl":
+            import torch
+            torch.cuda.current_stream().synchronize()  # the reference syncs the device before MPI too (:486)
+        for n in range(27):
+            peer = self.plan.neighbour[n]
+            if n == 13 or peer < 0:
+                continue
+            if peer == self.grid.rank:  # periodic dimension of extent 1: the message stays on this rank
+                if self.plan.recv_count(n):
+                    self._recv_tensor(n).copy_(self._send_tensor(26 - n))
+                continue
+            if self.plan.send_count(n):
+                sends.append((peer, message_tag(n), self._send_tensor(n)))
+            if self.plan.recv_count(n):
+                recvs.append((peer, message_tag(26 - n), self._recv_tensor(n)))
+        sends.sort(key=lambda x: x[1])
+        recvs.sort(key=lambda x: x[1])
+        if sends or recvs:
+            self.comm.exchange(sends, recvs)
+
+    def wait(self):
+        if self.transport == "p2p":
+            _lib.check(_lib.lib().gtb_halo_wait(self._h, self._stream()))
+
+    def unpack(self, *fields):
+        if self.transport == "host":
+            f = fields[0] if len(fields) == 1 and isinstance(fields[0], (list, tuple)) else fields
+            for n, msg in self._received.items():
+                self.codec.unpack(self.plan, n, f, msg)
+            return
+        arr, n = self._ptrs(fields)
+        _lib.check(_lib.lib().gtb_halo_unpack(self._h, arr, n, self._stream()))
+        _lib.check(_lib.lib().gtb_halo_next_epoch(self._h))
+
+    def check(self):
+        """0 if every wait so far completed; 1 + direction of a message that never arrived otherwise."""
+        code = C.c_int()
+        _lib.check(_lib.lib().gtb_halo_error(self._h, C.byref(code)))
+        return code.value
+
+    # ------------------------------------------------------------------ staging buffers as tensors
+    def _send_tensor(self, n):
+        if self.transport == "host":
+            import torch
+            return torch.from_numpy(np.ascontiguousarray(self._packed[n]))
+        nbytes = _lib.lib().gtb_halo_send_bytes(self._h, n, self._nf)
+        return _device_tensor(_lib.lib().gtb_halo_send_buffer(self._h, n), nbytes)
+
+    def _recv_tensor(self, n):
+        if self.transport == "host":
+            import torch
+            if not hasattr(self, "_received"):
+                self._received = {}
+            t = torch.empty(self.plan.recv_count(n) * self._nf,
+                            dtype=torch.float64 if self.dtype.itemsize == 8 else torch.float32)
+            self._received[n] = t.numpy()
+            return t
+        nbytes = _lib.lib().gtb_halo_recv_bytes(self._h, n, self._nf)
+        return _device_tensor(_lib.lib().gtb_halo_recv_buffer(self._h, n), nbytes)
+
+    def close(self):
+        if self._h is not None:
+            _lib.lib().gtb_halo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _CudaBuffer:
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def _device_tensor(ptr, nbytes):
+    import torch
+    return torch.as_tensor(_CudaBuffer(ptr, nbytes), device="cuda")
+
+
+class NumpyCodec:
+    """Host pack/unpack for transport='host' (tests of the choreography on CPU with gloo)."""
+
+    @staticmethod
+    def pack(plan, n, fields):
+        return plan.pack_numpy(n, fields)
+
+    @staticmethod
+    def unpack(plan, n, fields, msg):
+        plan.unpack_numpy(n, fields, msg)
+
+
+def connect_local(exchangers):
+    """Several ranks inside ONE process (tests on a single GPU): export all, then connect all."""
+    for he in exchangers:
+        if any(h is None for h in he._halos):
+            raise RuntimeError("add_halo() missing")
+    blobs = {he.grid.rank: he.blob for he in exchangers}
+    size = exchangers[0].grid.size
+    table = [blobs.get(r, b"") for r in range(size)]
+    for he in exchangers:
+        he._connect(table)

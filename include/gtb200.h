@@ -1,0 +1,181 @@
+/*
+ * gtb200.h -- C ABI of libgtb200.so, the B200 (sm_100a) stencil execution + halo-exchange library that sits
+ * behind the GridTools backend-tag / gcl interfaces.
+ *
+ * Every entry point replaces a piece of the reference's `stencil::gpu` / `gcl::gpu` path; the reference
+ * interface each one stands in for is cited as file:line (paths relative to the GridTools v2.4.0 tree).
+ *
+ * Conventions
+ *  - Plain C: pointers, sizes, ints.  No C++/torch types.  All functions return a gtb_status (0 == OK) and
+ *    never throw; gtb_last_error() gives the message of the last failure on the calling thread
+ *    (the reference throws std::runtime_error from GT_CUDA_CHECK, common/cuda_util.hpp:20-35 -- the C++
+ *    header include/gtb200/stencil/b200.hpp turns a non-zero status back into that exception).
+ *  - A field is {pointer to element (0,0,0) of the COMPUTE DOMAIN, element strides}.  This is exactly what a
+ *    backend receives from the frontend: origin-shifted SIDs (stencil/core/backend.hpp:29-34) whose
+ *    sid::get_origin / sid::get_strides give pointer and strides.  Halo points are addressed with negative or
+ *    >= n indices and must be valid device memory within the stencil's extent (frontend/run.hpp:215-232).
+ *  - Fields are borrowed for the duration of the call (frontend/run.hpp:214).  Kernels are enqueued on `stream`
+ *    (a cudaStream_t passed as void*, NULL = legacy default stream like the reference,
+ *    stencil/gpu/launch_kernel.hpp:161) and the call returns without synchronising, like
+ *    common/cuda_util.hpp:79-96 in release mode.
+ *  - There is no CPU fallback anywhere in this library: without a CUDA device every compute entry point
+ *    returns GTB_ERR_CUDA.
+ */
+#ifndef GTB200_H
+#define GTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GTB_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+    GTB_OK = 0,
+    GTB_ERR_ARG = 1,    /* null pointer, negative size, unsupported element size */
+    GTB_ERR_LAYOUT = 2, /* layout the kernel cannot address (stride_i != 1 for the tiled kernels) */
+    GTB_ERR_CUDA = 3,   /* CUDA runtime / driver error, see gtb_last_error() */
+    GTB_ERR_ALLOC = 4,  /* scratch allocation failed */
+    GTB_ERR_STATE = 5   /* halo object used out of order (e.g. exchange before connect) */
+} gtb_status;
+
+typedef struct {
+    void *ptr;                            /* element (0,0,0) of the compute domain (device memory) */
+    int64_t stride_i, stride_j, stride_k; /* element strides */
+} gtb_field;
+
+/* ------------------------------------------------------------------------------------------- runtime */
+
+/* Library version (GTB_VERSION). */
+int gtb_version(void);
+/* Message of the last error on this thread ("" if none).  Replaces the what() of the std::runtime_error thrown by
+ * GT_CUDA_CHECK (common/cuda_util.hpp:20-35). */
+const char *gtb_last_error(void);
+/* Number of visible CUDA devices (0 if none / no driver).  Never fails. */
+int gtb_device_count(void);
+/* Selects `device` for the calling thread and warms the kernels' function attributes (the reference calls
+ * cudaFuncSetAttribute on every launch, common/cuda_util.hpp:84-88; here it happens once). */
+int gtb_init(int device);
+/* SM count and L2 size of the current device (used by the host side to size persistent grids / report). */
+int gtb_device_info(int *sm_count, int64_t *l2_bytes, int64_t *hbm_bytes);
+/* Tuning knob: kernels pick a variant from integer options, e.g. ("hd.variant", 0=auto 1=cp.async 2=tma),
+ * ("va.threads", 32..256), ("va.unroll", 1..8), ("va.scratch", 0=auto 1=global 2=smem).  Unknown keys return
+ * GTB_ERR_ARG.  The reference's only knobs are the compile-time block sizes of gpu<IBlock,JBlock,KBlock>
+ * (stencil/gpu/entry_point.hpp:147-150). */
+int gtb_set_option(const char *key, int value);
+int gtb_get_option(const char *key, int *value);
+/* Releases the cached scratch (temporaries) of the calling device; the reference keeps them in a thread-local
+ * sid::device::cached_allocator (sid/allocator.hpp:65-95, stencil/gpu/entry_point.hpp:155-175). */
+int gtb_release_scratch(void);
+/* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
+int64_t gtb_launch_count(void);
+
+/* --------------------------------------------------------------------------------- named stencil kernels
+ * Each is the fused B200 kernel for one spec of the reference's regression/perf suite; together they are what
+ * `run(spec, gpu<>{}, grid, fields...)` (frontend/run.hpp:242-250 -> stencil/gpu/entry_point.hpp:254-260)
+ * executes for that spec.  ni,nj,nk = compute-domain size (grid.i_size(), j_size(), k_size()). */
+
+/* copy_stencil.cpp:24-36 : out = in (bit exact).  elem_size in {4,8}.  Any strides. */
+int gtb_copy(const gtb_field *in, const gtb_field *out, int ni, int nj, int nk, int elem_size, void *stream);
+
+/* horizontal_diffusion.cpp:35-106 : execute_parallel, ij_cached(lap, flx, fly), 4 stages fused into one kernel.
+ * Reads `in` on [-2, n+2) in i and j.  stride_i must be 1.  `out` must not alias `in`/`coeff`. */
+int gtb_hori_diff_f64(const gtb_field *in, const gtb_field *coeff, const gtb_field *out, int ni, int nj, int nk,
+    void *stream);
+int gtb_hori_diff_f32(const gtb_field *in, const gtb_field *coeff, const gtb_field *out, int ni, int nj, int nk,
+    void *stream);
+
+/* vertical_advection_dycore.cpp:32-149 : forward sweep (k_cached ccol/dcol flush, u_stage fill) + backward sweep
+ * (k_cached data_col) fused into one kernel; utens_stage is updated in place.  Reads wcon at i+1 and k+1.
+ * nk >= 2.  stride_i must be 1. */
+int gtb_vert_adv_f64(const gtb_field *utens_stage, const gtb_field *u_stage, const gtb_field *wcon,
+    const gtb_field *u_pos, const gtb_field *utens, double dtr_stage, int ni, int nj, int nk, void *stream);
+int gtb_vert_adv_f32(const gtb_field *utens_stage, const gtb_field *u_stage, const gtb_field *wcon,
+    const gtb_field *u_pos, const gtb_field *utens, float dtr_stage, int ni, int nj, int nk, void *stream);
+
+/* tridiagonal.cpp:39-97 : Thomas solve, forward + backward in one kernel.  sup and rhs are overwritten by the
+ * forward sweep exactly like in the reference (they are inout fields there). */
+int gtb_tridiagonal_f64(const gtb_field *inf, const gtb_field *diag, const gtb_field *sup, const gtb_field *rhs,
+    const gtb_field *out, int ni, int nj, int nk, void *stream);
+
+/* advection_pdbott_prepare_tracers.cpp:23-34 run through expandable_run<2> (frontend/expandable_run.hpp:144-184):
+ * out[t] = rho * in[t] for all n_tracers in ONE launch (the reference needs ceil(n/2) launches). */
+int gtb_prepare_tracers_f64(const gtb_field *out, const gtb_field *in, int n_tracers, const gtb_field *rho, int ni,
+    int nj, int nk, void *stream);
+
+/* ------------------------------------------------------------------------------------------ gcl halo exchange
+ * Replaces hndlr_dynamic_ut<..., gpu> (gcl/high_level/descriptors_manual_gpu.hpp:83-515), the 24 pack/unpack
+ * kernels gcl/high_level/m_{pack,unpack}{X,Y,Z}{L,U}.hpp and the MPI choreography of
+ * gcl/low_level/Halo_Exchange_3D.hpp:145-931 for ranks that live on one NVLink/NVSwitch box.
+ *
+ * One gtb_halo object per rank (process, one GPU each).  Dimension d of a descriptor is the d-th STORAGE
+ * dimension in increasing-stride order (d = 0 is the unit-stride axis); halo descriptors have the meaning of
+ * common/halo_descriptor.hpp:44-227 (minus, plus, begin, end inclusive, total length).
+ * Neighbours are indexed n = (e0+1) + 3*(e1+1) + 9*(e2+1) with e_d in {-1,0,1} the offset along storage
+ * dimension d; n = 13 is the rank itself (unused).
+ *
+ * Life cycle (mirrors halo_exchange_dynamic_ut, gcl/halo_exchange.hpp:163-306):
+ *   gtb_halo_create            <- ctor + add_halo<D>() x3 + setup(max_fields)            (:202,:235,:216)
+ *   gtb_halo_export/connect    <- buffer registration of Halo_Exchange_3D (:270-287 of descriptors_manual_gpu.hpp);
+ *                                 the blobs travel through whatever out-of-band channel the host has
+ *                                 (torch.distributed, MPI, a file)
+ *   gtb_halo_pack              <- pack(vector<T*>)                                        (:250,:269)
+ *   gtb_halo_exchange          <- exchange() = start_exchange() + wait()                  (:284-304)
+ *   gtb_halo_unpack            <- unpack(vector<T*>)                                      (:260,:276)
+ *   gtb_halo_destroy           <- dtor
+ */
+typedef struct {
+    int minus, plus, begin, end, total;
+} gtb_halo_desc;
+
+typedef struct gtb_halo gtb_halo;
+
+#define GTB_HALO_BLOB_BYTES 512
+
+/* neighbour_rank[27]: rank of the neighbour in direction n or -1 (non-periodic border,
+ * gcl/low_level/proc_grids_3D.hpp:179-211); entry 13 is ignored.  The handle owns 26 send + 26 recv device buffers
+ * sized like descriptors_manual_gpu.hpp:255-300: prod_d s_length(e_d) * max_fields * elem_size. */
+int gtb_halo_create(const gtb_halo_desc desc[3], const int neighbour_rank[27], int my_rank, int max_fields,
+    int elem_size, gtb_halo **out);
+int gtb_halo_destroy(gtb_halo *h);
+
+/* Bytes of the message towards / from neighbour n for n_fields fields (0 if there is no such neighbour). */
+int64_t gtb_halo_send_bytes(const gtb_halo *h, int n, int n_fields);
+int64_t gtb_halo_recv_bytes(const gtb_halo *h, int n, int n_fields);
+/* Device pointers of the staging buffers, for hosts that move the messages themselves (NCCL / MPI transport). */
+void *gtb_halo_send_buffer(const gtb_halo *h, int n);
+void *gtb_halo_recv_buffer(const gtb_halo *h, int n);
+
+/* Peer-to-peer transport over NVLink: export this rank's receive arena (cudaIpcMemHandle + layout) as an opaque
+ * blob of GTB_HALO_BLOB_BYTES, hand every neighbour's blob to connect (blobs[n] = blob of neighbour_rank[n], NULL
+ * where there is none; a neighbour that is this very process -- periodic grid of extent 1 or 2 ranks in one
+ * process -- is detected and not re-opened). */
+int gtb_halo_export(gtb_halo *h, void *blob);
+int gtb_halo_connect(gtb_halo *h, const void *const blobs[27]);
+
+/* One fused launch: gathers the send regions of all fields for all existing neighbours into the send buffers.
+ * fields[f] points at storage element (0,0,0) INCLUDING the halo (like the raw T* the reference takes). */
+int gtb_halo_pack(gtb_halo *h, void *const *fields, int n_fields, void *stream);
+/* Fused pack + NVLink store: writes every message straight into the neighbour's receive buffer and raises its
+ * arrival flag (needs connect).  Equivalent to pack() + the do_sends() half of exchange(). */
+int gtb_halo_pack_send(gtb_halo *h, void *const *fields, int n_fields, void *stream);
+/* Pushes the packed send buffers into the neighbours' receive buffers and raises their flags (needs connect). */
+int gtb_halo_send(gtb_halo *h, int n_fields, void *stream);
+/* Device-side wait until all expected messages of the current epoch have arrived (enqueued on stream). */
+int gtb_halo_wait(gtb_halo *h, void *stream);
+/* One fused launch: scatters every received message into the halo regions of all fields. */
+int gtb_halo_unpack(gtb_halo *h, void *const *fields, int n_fields, void *stream);
+/* Synchronises the device and reports whether a wait timed out: *code = 0 if not, else 1 + direction that never
+ * arrived.  (Halo_Exchange_3D has no error path: a lost MPI peer hangs in MPI_Wait.) */
+int gtb_halo_error(gtb_halo *h, int *code);
+/* Advances the epoch after unpack (double-buffered arenas: a neighbour may already send epoch e+1 while this rank
+ * still unpacks epoch e). */
+int gtb_halo_next_epoch(gtb_halo *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GTB200_H */
