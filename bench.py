@@ -1,0 +1,432 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of BASELINE.json on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--stencil vert_adv|hori_diff]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (config.workload): vertical_advection_dycore 256x256x80 fp64 per GPU (BASELINE.json configs[1]), the
+reference's own perftest (tests/regression/vertical_advection_dycore.cpp:128-152, `perftests 256 256 80`).
+A step = one application of the stencil to one set of synthetic fields (the reference repository's analytic
+fields); the 5 input fields of a set are 228 MB > L2 (126 MB) and the sets are rotated, so no step finds its inputs
+in L2.  At N > 1 the global domain is decomposed in IJ (weak scaling: 256x256x80 per GPU) and every step first
+exchanges the halo of wcon with the neighbours (gcl pack -> NVLink stores -> unpack), which is the exchange step a
+real dycore has between two stencils.
+
+One JSON line on stdout (rank 0).  `value` = whole-job Mpts/s with inputs resident in HBM; `e2e` = the same metric
+through the public API with HOST buffers (pinned host -> device copies of the step's five input fields and the
+device -> host copy of the result inside the timed region); `roofline` = algorithmic bytes (48 B/point, SURVEY.md
+section 8d) / CUDA-event kernel time against the measured HBM peak; `cpu_baseline` = the reference's own cpu_ifirst /
+cpu_kfirst backends (oracle/_ref/libgtref.so, built from the unmodified reference headers) timed on this host.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NI = NJ = 256
+NK = 80
+ALGO_BYTES = {"vert_adv": 48, "hori_diff": 24}  # per interior point, fp64
+P100_MPTS = {"vert_adv": 5117.0, "hori_diff": 10300.0}  # reference stencil::gpu on P100
+HALO = {"vert_adv": 3, "hori_diff": 2}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--stencil", default="vert_adv", choices=["vert_adv", "hori_diff"])
+    ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / secondary stencil")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------- synthetic fields
+def repo_vert_adv(ni, nj, nk, i_off=0, j_off=0, gi=None, gj=None):
+    """vertical_advection_repository.hpp:70-93 on the (nk, nj+6, ni+6) box; global indices for multi-GPU like
+    copy_stencil_parallel.cpp:102-107."""
+    d0, d1 = (gi or ni) + 6, (gj or nj) + 6
+    k, j, i = np.meshgrid(np.arange(nk), np.arange(nj + 6) + j_off, np.arange(ni + 6) + i_off, indexing="ij",
+                          sparse=True)
+    x, y, z = i / d0, j / d1, k / nk
+    pi = np.pi
+    t = x + y + 0 * z
+    u_stage = 7.0 + np.cos(pi * t) + np.sin(2 * pi * t) + 0 * z
+    u_pos = u_stage.copy()
+    wcon = 2e-4 * (-1.07 + (2. + np.cos(pi * (x + z)) + np.cos(pi * y)) / 2.)
+    utens = 3e-6 * (-1.0235 + (2. + np.cos(pi * (x + y)) + np.cos(pi * y * z)) / 2.)
+    utens_stage = 7.0 + 1.25 * (2. + np.cos(pi * (x + y)) + np.sin(2 * pi * (x + y))) + 0.1 * k
+    shape = (nk, nj + 6, ni + 6)
+    return [np.ascontiguousarray(np.broadcast_to(a, shape)) for a in (utens_stage, u_stage, wcon, u_pos, utens)], 3. / 20.
+
+
+def repo_hori_diff(ni, nj, nk, i_off=0, j_off=0, gi=None, gj=None):
+    """horizontal_diffusion_repository.hpp:32-42 on the (nk, nj+4, ni+4) box."""
+    d0, d1 = (gi or ni) + 4, (gj or nj) + 4
+    k, j, i = np.meshgrid(np.arange(nk), np.arange(nj + 4) + j_off, np.arange(ni + 4) + i_off, indexing="ij",
+                          sparse=True)
+    x, y = i / d0, j / d1
+    inp = 5. + 8 * (2. + np.cos(np.pi * (x + 1.5 * y)) + np.sin(2 * np.pi * (x + 1.5 * y))) / 4. + 0. * k
+    shape = (nk, nj + 4, ni + 4)
+    return np.ascontiguousarray(np.broadcast_to(inp, shape)), np.full(shape, 0.025)
+
+
+# --------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------- reference arm (CPU)
+def time_reference(stencil, steps, warmup):
+    """The UNMODIFIED reference (its headers compiled into oracle/_ref/libgtref.so by oracle/Makefile) running its own
+    cpu_ifirst / cpu_kfirst OpenMP backends on this host's cores.  Returns (best_backend, seconds per step list)."""
+    from oracle import pyoracle as o
+    if not o.have_ref():
+        raise RuntimeError("oracle/_ref/libgtref.so missing (built in the build container by __graft_entry__.build)")
+    best = None
+    for backend in ("cpu_ifirst", "cpu_kfirst"):
+        if stencil == "vert_adv":
+            arrs, dtr = repo_vert_adv(NI, NJ, NK)
+            res = np.zeros_like(arrs[0])
+            o.ref_run(o.VERT_ADV, backend, arrs, [res], NI, NJ, NK, scalar=dtr, nrep=warmup, flush=True)
+            times = o.ref_run(o.VERT_ADV, backend, arrs, [res], NI, NJ, NK, scalar=dtr, nrep=steps, flush=True)
+        else:
+            inp, coeff = repo_hori_diff(NI, NJ, NK)
+            res = np.zeros_like(inp)
+            o.ref_run(o.HORI_DIFF, backend, [inp, coeff], [res], NI, NJ, NK, nrep=warmup, flush=True)
+            times = o.ref_run(o.HORI_DIFF, backend, [inp, coeff], [res], NI, NJ, NK, nrep=steps, flush=True)
+        if best is None or statistics.median(times) < statistics.median(best[1]):
+            best = (backend, times)
+    return best[0], best[1], o.ref_num_threads()
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = min(args.steps, 50)  # bounded sample: each step is one full 256x256x80 application (~5-15 ms)
+    backend, times, cores = time_reference(args.stencil, steps, min(args.warmup, 5))
+    sec = statistics.median(times)
+    mpts = NI * NJ * NK / sec / 1e6
+    sample = "%d timed applications of %s %dx%dx%d fp64 on stencil::%s, cache flush before each, median" % (
+        steps, args.stencil, NI, NJ, NK, backend)
+    line = {
+        "impl": "reference", "metric": "Mpts/s %s %dx%dx%d fp64" % (args.stencil, NI, NJ, NK), "value": mpts,
+        "unit": "Mpts/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 5),
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (reference repository's analytic fields)",
+        "config": {"workload": "%s %dx%dx%d fp64, reference CPU backend %s" % (args.stencil, NI, NJ, NK, backend)},
+        "cpu_baseline": {"value": mpts, "unit": "Mpts/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": mpts, "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------- B200 arm
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            for key in ("hbm_gbs", "hbm_gb_s", "hbm_copy_gbs"):
+                if key in d:
+                    return float(d[key]), "measured (MEASURED_PEAKS.json %s)" % key
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def traffic_from_profile(stencil):
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(stencil)
+        except Exception:
+            return None
+    return None
+
+
+def b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    from gridtools_b200 import _lib, gcl, stencil, storage
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    _lib.check(_lib.lib().gtb_init(local))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_gpus = world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- fields: two rotating sets per rank
+    dims = gcl.ProcGrid.dims_create(world)
+    grid = gcl.ProcGrid(dims, (False, False, False), rank)
+    i_off, j_off = grid.coords[0] * NI, grid.coords[1] * NJ
+    name = args.stencil
+    H = HALO[name]
+    sets = []
+    n_sets = 2 if name == "vert_adv" else 3
+    for s in range(n_sets):
+        if name == "vert_adv":
+            arrs, dtr = repo_vert_adv(NI, NJ, NK, i_off, j_off, NI * dims[0], NJ * dims[1])
+            sets.append([storage.from_numpy(a, (H, H, 0)) for a in arrs])
+        else:
+            inp, coeff = repo_hori_diff(NI, NJ, NK, i_off, j_off, NI * dims[0], NJ * dims[1])
+            sets.append([storage.from_numpy(inp, (H, H, 0)), storage.from_numpy(coeff, (H, H, 0)),
+                         storage.from_numpy(np.zeros_like(inp), (H, H, 0))])
+    for st in sets:
+        for f in st:
+            f.const_target_tensor()  # upload now
+
+    # ---- halo exchange object (N > 1): the field with an IJ extent (wcon resp. in), one per set
+    he = None
+    if world > 1:
+        he = gcl.halo_exchange_dynamic_ut((False, False, False), grid, np.float64, comm=gcl.TorchComm(),
+                                          transport="p2p")
+        f0 = sets[0][0]
+        p0, d1, d2 = f0.padded_lengths
+        he.add_halo(0, H, H, H, H + NI - 1, p0)
+        he.add_halo(1, H, H, H, H + NJ - 1, d1)
+        he.add_halo(2, 0, 0, 0, NK - 1, d2)
+        he.setup(1)
+
+    exch_index = 2 if name == "vert_adv" else 0
+
+    def step(s):
+        st = sets[s % n_sets]
+        if he is not None:
+            f = st[exch_index]
+            he.pack(f)
+            he.exchange()
+            he.unpack(f)
+        if name == "vert_adv":
+            stencil.vertical_advection_dycore(*st, dtr)
+        else:
+            stencil.horizontal_diffusion(*st)
+
+    sampler = ClockSampler(local)
+    for s in range(max(args.warmup, 3)):
+        step(s)
+    barrier()
+    sampler.start()
+    launches0 = _lib.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for s in range(args.steps):
+        step(s)
+        ev[s + 1].record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_step = [ev[s].elapsed_time(ev[s + 1]) for s in range(args.steps)]
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    pts = NI * NJ * NK
+    value = n_gpus * pts / (ms_per_step * 1e-3) / 1e6
+
+    # ---- kernel-only duration for the roofline (CUDA events around the stencil launch alone, same stream)
+    kern_ms = []
+    for s in range(min(args.steps, 100)):
+        st = sets[s % n_sets]
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        if name == "vert_adv":
+            stencil.vertical_advection_dycore(*st, dtr)
+        else:
+            stencil.horizontal_diffusion(*st)
+        b.record()
+        kern_ms.append((a, b))
+    torch.cuda.synchronize()
+    kern_ms = statistics.mean(a.elapsed_time(b) for a, b in kern_ms)
+    clocks = sampler.stop()
+    peak, peak_src = measured_peak()
+    achieved = ALGO_BYTES[name] * pts / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic_from_profile(name), "peak_source": peak_src,
+                "kernel": "va_kernel" if name == "vert_adv" else "hd_tma_kernel", "kernel_ms": kern_ms,
+                "algorithmic_bytes_per_launch": ALGO_BYTES[name] * pts}
+
+    line = {
+        "metric": "Mpts/s %s %dx%dx%d fp64" % (name, NI, NJ, NK), "value": value, "unit": "Mpts/s",
+        "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": value / n_gpus / P100_MPTS[name] if n_gpus == 1
+        else None, "dtype": "f64", "data": "synthetic (reference repository's analytic fields)",
+        "config": {"workload": "%s %dx%dx%d fp64 per GPU (BASELINE.json configs[1] family)" % (name, NI, NJ, NK),
+                   "decomposition": "%dx%dx1 IJ process grid, halo exchange of %s every step" % (
+                       dims[0], dims[1], "wcon" if name == "vert_adv" else "in") if world > 1 else "single GPU",
+                   "l2": "inputs of one step (%d MB) exceed L2 and %d field sets are rotated" % (
+                       sum(f.nbytes_host for f in sets[0]) // 2**20, n_sets),
+                   "vs_baseline_ref": "reference stencil::gpu on P100, BASELINE.md section 1"},
+        "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
+        "step_ms_median": statistics.median(per_step),
+    }
+
+    if rank == 0 and not args.no_extras:
+        line["e2e"] = e2e(torch, stencil, storage, name, sets, dtr if name == "vert_adv" else None, args, n_gpus)
+        try:
+            backend, times, cores = time_reference(name, 20, 2)
+            sec = statistics.median(times)
+            line["cpu_baseline"] = {
+                "value": pts / sec / 1e6, "unit": "Mpts/s", "cores": cores, "kind": "reference",
+                "sample": "20 timed applications of %s %dx%dx%d fp64 on the reference's stencil::%s (best of "
+                          "cpu_ifirst/cpu_kfirst), cache flush before each, median" % (name, NI, NJ, NK, backend)}
+        except Exception as e:  # the checker library is not part of the product
+            line["cpu_baseline"] = {"value": None, "unit": "Mpts/s", "cores": 0, "kind": "reference",
+                                    "sample": "unavailable: %s" % e}
+        if world == 1:
+            line["also"] = secondary(torch, stencil, storage, "hori_diff" if name == "vert_adv" else "vert_adv", peak)
+    elif world > 1 and not args.no_extras:
+        pass
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def e2e(torch, stencil, storage, name, sets, dtr, args, n_gpus):
+    """Same metric through the public API with host buffers: every step copies the step's input fields from pinned
+    host memory to the device, runs the stencil and copies the result back to the host."""
+    st = sets[0]
+    steps = max(3, min(args.steps, 20))
+    n_in = 5 if name == "vert_adv" else 2
+    out = st[0] if name == "vert_adv" else st[2]
+    h2d = sum(f.nbytes_host for f in st[:n_in])
+    d2h = out.nbytes_host
+    for f in st:
+        f.const_host_view()
+
+    def one():
+        for f in st[:n_in]:
+            f.update_target_async()
+        if name == "vert_adv":
+            stencil.vertical_advection_dycore(*st, dtr)
+        else:
+            stencil.horizontal_diffusion(*st)
+        out.update_host_async()
+
+    for _ in range(3):
+        one()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    a.record()
+    for _ in range(steps):
+        one()
+    b.record()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / steps
+    ms = max(a.elapsed_time(b) / steps, wall * 1e3)
+    return {"value": n_gpus * NI * NJ * NK / (ms * 1e-3) / 1e6, "unit": "Mpts/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "ms_per_step": ms, "steps": steps}
+
+
+def secondary(torch, stencil, storage, name, peak):
+    """The other stencil of the metric, kernel-only, same hygiene (reported beside the headline)."""
+    H = HALO[name]
+    sets = []
+    if name == "hori_diff":
+        for _ in range(3):
+            inp, coeff = repo_hori_diff(NI, NJ, NK)
+            sets.append([storage.from_numpy(inp, (H, H, 0)), storage.from_numpy(coeff, (H, H, 0)),
+                         storage.from_numpy(np.zeros_like(inp), (H, H, 0))])
+        run = lambda st: stencil.horizontal_diffusion(*st)  # noqa: E731
+    else:
+        for _ in range(2):
+            arrs, dtr = repo_vert_adv(NI, NJ, NK)
+            sets.append([storage.from_numpy(a, (H, H, 0)) for a in arrs])
+        run = lambda st: stencil.vertical_advection_dycore(*st, 0.15)  # noqa: E731
+    for st in sets:
+        for f in st:
+            f.const_target_tensor()
+    for s in range(10):
+        run(sets[s % len(sets)])
+    torch.cuda.synchronize()
+    evs = []
+    for s in range(100):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        run(sets[s % len(sets)])
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
+    pts = NI * NJ * NK
+    gbs = ALGO_BYTES[name] * pts / (ms * 1e-3) / 1e9
+    return {"metric": "Mpts/s %s %dx%dx%d fp64" % (name, NI, NJ, NK), "value": pts / (ms * 1e-3) / 1e6,
+            "unit": "Mpts/s", "kernel_ms": ms, "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak,
+                                                            "unit": "GB/s", "frac": gbs / peak,
+                                                            "traffic": traffic_from_profile(name)}}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        b200_arm(a)

@@ -1,0 +1,119 @@
+"""Halo exchange kernels on one GPU: several ranks of a process grid live in this process (each with its own
+gtb_halo object and arena), messages travel through the peer-to-peer path (same code as over NVLink, the "peer"
+pointer simply is local), results are compared bit-for-bit with the oracle's restatement of gcl's
+pack -> exchange -> unpack (test pattern of regression/gcl/test_halo_exchange_3D.cpp:66-123)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HALOS = [(2, 3, 2, 9, 14), (1, 2, 1, 6, 10), (0, 1, 0, 4, 6)]
+HALOS_IJ = [(2, 2, 2, 33, 36), (2, 2, 2, 17, 20), (0, 0, 0, 4, 5)]  # hori_diff-like: halo 2 in i/j, none in k
+
+
+@pytest.fixture(scope="module")
+def gt():
+    import torch
+    from gridtools_b200 import _lib, gcl, storage
+    _lib.check(_lib.lib().gtb_init(0))
+
+    class NS:
+        pass
+    ns = NS()
+    ns.lib, ns.gcl, ns.storage, ns.torch = _lib, gcl, storage, torch
+    return ns
+
+
+def stamp(plan, grid, field_id, dtype):
+    shape = plan.storage_shape()
+    a = -np.ones(shape, dtype)
+    (m0, p0, b0, e0, t0), (m1, p1, b1, e1, t1), (m2, p2, b2, e2, t2) = plan.halos
+    n0, n1, n2 = e0 - b0 + 1, e1 - b1 + 1, e2 - b2 + 1
+    k, j, i = np.meshgrid(np.arange(n2), np.arange(n1), np.arange(n0), indexing="ij")
+    gi, gj, gk = i + n0 * grid.coords[0], j + n1 * grid.coords[1], k + n2 * grid.coords[2]
+    a[b2:e2 + 1, b1:e1 + 1, b0:e0 + 1] = field_id * 1e5 + gi * 1e3 + gj * 10 + gk
+    return a
+
+
+def exchange_in_process(gt, halos, dims, periodic, n_fields, dtype, fused, epochs=1):
+    size = dims[0] * dims[1] * dims[2]
+    hes, fields, dev = [], [], []
+    for r in range(size):
+        grid = gt.gcl.ProcGrid(dims, periodic, r)
+        he = gt.gcl.halo_exchange_dynamic_ut(periodic, grid, dtype, comm=None, transport="p2p")
+        for d in range(3):
+            he.add_halo(d, *halos[d])
+        he.setup(n_fields)
+        hes.append(he)
+        fields.append([stamp(he.plan, grid, f, dtype) for f in range(n_fields)])
+        dev.append([gt.torch.from_numpy(a.copy()).cuda() for a in fields[-1]])
+    gt.gcl.connect_local(hes)
+    L = gt.lib.lib()
+    import ctypes as C
+    stream = C.c_void_p(gt.torch.cuda.current_stream().cuda_stream)
+    for _ in range(epochs):
+        ptrs = [[t.data_ptr() for t in d] for d in dev]
+        # all ranks send first, then all wait: the ranks share one stream in this test
+        for he, p in zip(hes, ptrs):
+            if fused:
+                he.pack(p)
+            else:
+                arr = (C.c_void_p * n_fields)(*p)
+                gt.lib.check(L.gtb_halo_pack(he._h, arr, n_fields, stream))
+                gt.lib.check(L.gtb_halo_send(he._h, n_fields, stream))
+        for he, p in zip(hes, ptrs):
+            he.wait()
+            he.unpack(p)
+    gt.torch.cuda.synchronize()
+    for he in hes:
+        assert he.check() == 0
+    got = [[t.cpu().numpy() for t in d] for d in dev]
+    for he in hes:
+        he.close()
+    return fields, got
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("dims,periodic", [((1, 1, 1), (1, 1, 1)), ((2, 1, 1), (0, 0, 0)), ((2, 2, 1), (1, 0, 1)),
+                                           ((2, 2, 2), (0, 1, 0)), ((3, 2, 1), (1, 1, 1))])
+def test_exchange_matches_oracle(gt, oracle, dims, periodic, dtype, fused):
+    n_fields = 3
+    fields, got = exchange_in_process(gt, HALOS, dims, periodic, n_fields, dtype, fused)
+    oracle.halo_exchange_all(HALOS, dims, periodic, fields, np.dtype(dtype).itemsize)
+    for r, (want, have) in enumerate(zip(fields, got)):
+        for f in range(n_fields):
+            assert np.array_equal(want[f], have[f]), "rank %d field %d" % (r, f)
+
+
+def test_many_fields_and_epochs(gt, oracle):
+    """More fields than one launch carries (16) and three back-to-back epochs (double-buffered arenas)."""
+    dims, periodic, n_fields = (2, 2, 1), (1, 1, 0), 19
+    fields, got = exchange_in_process(gt, HALOS_IJ, dims, periodic, n_fields, np.float64, True, epochs=3)
+    for _ in range(3):
+        oracle.halo_exchange_all(HALOS_IJ, dims, periodic, fields, 8)
+    for want, have in zip(fields, got):
+        for f in range(n_fields):
+            assert np.array_equal(want[f], have[f])
+
+
+def test_non_periodic_border_untouched(gt, oracle):
+    fields, got = exchange_in_process(gt, HALOS_IJ, (1, 2, 1), (0, 0, 0), 1, np.float64, True)
+    assert (got[0][0] == -1).any() and (got[1][0] == -1).any()
+    oracle.halo_exchange_all(HALOS_IJ, (1, 2, 1), (0, 0, 0), fields, 8)
+    assert np.array_equal(fields[0][0], got[0][0]) and np.array_equal(fields[1][0], got[1][0])
+
+
+def test_too_many_fields_is_an_error(gt):
+    grid = gt.gcl.ProcGrid((1, 1, 1), (1, 1, 1), 0)
+    he = gt.gcl.halo_exchange_dynamic_ut((1, 1, 1), grid, np.float64, comm=None, transport="p2p")
+    for d in range(3):
+        he.add_halo(d, *HALOS[d])
+    he.setup(1)
+    with pytest.raises(ValueError):
+        he.pack([1, 2])
+    import ctypes as C
+    arr = (C.c_void_p * 2)(8, 16)
+    assert gt.lib.lib().gtb_halo_pack(he._h, arr, 2, None) == gt.lib.GTB_ERR_ARG
+    assert gt.lib.lib().gtb_halo_pack_send(he._h, arr, 1, None) == gt.lib.GTB_ERR_STATE  # not connected yet
+    he.close()

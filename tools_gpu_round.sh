@@ -1,0 +1,30 @@
+#!/bin/bash
+# One gpurun call: GPU tests, variant sweep, bench, ncu launch list and full captures.  Everything lands in gpurun_out/.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,power.limit,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
+nproc >> gpurun_out/gpu.txt
+STEP=${1:-all}
+if [ "$STEP" = all ] || [ "$STEP" = test ]; then
+  timeout 900 python -m pytest tests -m gpu -q --maxfail=30 -p no:cacheprovider --timeout=300 > gpurun_out/pytest_gpu.log 2>&1
+  echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+  tail -5 gpurun_out/pytest_gpu.log
+fi
+if [ "$STEP" = all ] || [ "$STEP" = tune ]; then
+  timeout 600 python tools_tune.py > gpurun_out/tune.txt 2>&1
+  tail -3 gpurun_out/tune.txt
+fi
+if [ "$STEP" = all ] || [ "$STEP" = bench ]; then
+  timeout 600 python bench.py --steps 200 --warmup 20 > gpurun_out/bench.json 2> gpurun_out/bench.err
+  cat gpurun_out/bench.json
+  timeout 300 python bench.py --stencil hori_diff --steps 200 --warmup 20 --no-extras > gpurun_out/bench_hd.json 2>> gpurun_out/bench.err
+  timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err
+fi
+if [ "$STEP" = all ] || [ "$STEP" = ncu ]; then
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
+      python bench.py --steps 5 --warmup 3 --no-extras > gpurun_out/ncu_launches.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:va_kernel -s 3 -c 2 -f -o gpurun_out/prof_va \
+      python bench.py --steps 5 --warmup 3 --no-extras > gpurun_out/ncu_va.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:hd_ -s 3 -c 2 -f -o gpurun_out/prof_hd \
+      python bench.py --stencil hori_diff --steps 5 --warmup 3 --no-extras > gpurun_out/ncu_hd.log 2>&1
+  ls -la gpurun_out
+fi

@@ -1,0 +1,100 @@
+"""Sweeps the kernel variants on the GPU box and prints a table (used to pick the defaults in csrc/*.cu).
+
+    python tools_tune.py > gpurun_out/tune.txt
+"""
+import itertools
+import statistics
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+import bench  # noqa: E402
+from gridtools_b200 import _lib, stencil, storage  # noqa: E402
+
+NI = NJ = 256
+NK = 80
+
+
+def timeit(run, sets, n=60):
+    for s in range(6):
+        run(sets[s % len(sets)])
+    torch.cuda.synchronize()
+    evs = []
+    for s in range(n):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        run(sets[s % len(sets)])
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    t = [a.elapsed_time(b) for a, b in evs]
+    return statistics.median(t), min(t)
+
+
+def main():
+    torch.cuda.set_device(0)
+    _lib.check(_lib.lib().gtb_init(0))
+    print("device", _lib.device_info())
+    # ---- copy as a bandwidth yardstick
+    a = np.zeros((NK, NJ + 4, NI + 4))
+    cs = [[storage.from_numpy(a, (2, 2, 0)), storage.from_numpy(a, (2, 2, 0))] for _ in range(4)]
+    for st in cs:
+        for f in st:
+            f.const_target_tensor()
+    med, mn = timeit(lambda st: stencil.copy(*st), cs)
+    print("copy 256x256x80 f64: median %.2f us min %.2f us -> %.0f GB/s" % (med * 1e3, mn * 1e3, 16 * NI * NJ * NK / med / 1e6))
+    # ---- hori_diff
+    for dtype, n in ((np.float64, 256), (np.float32, 256), (np.float64, 512)):
+        sets = []
+        for _ in range(3):
+            inp, coeff = bench.repo_hori_diff(n, n, NK)
+            inp, coeff = inp.astype(dtype), coeff.astype(dtype)
+            sets.append([storage.from_numpy(inp, (2, 2, 0)), storage.from_numpy(coeff, (2, 2, 0)),
+                         storage.from_numpy(np.zeros_like(inp), (2, 2, 0))])
+        for st in sets:
+            for f in st:
+                f.const_target_tensor()
+        for variant, stages, ctas in itertools.product((1, 2), (2, 3, 4, 5), (1, 2)):
+            if stages == 5 and ctas == 2 and dtype == np.float64:
+                continue
+            for k, v in (("hd.variant", variant), ("hd.stages", stages), ("hd.ctas_per_sm", ctas)):
+                _lib.set_option(k, v)
+            try:
+                med, mn = timeit(lambda st: stencil.horizontal_diffusion(*st), sets)
+            except Exception as e:
+                print("hd", dtype.__name__, n, variant, stages, ctas, "FAILED", e)
+                continue
+            b = 3 * np.dtype(dtype).itemsize * n * n * NK
+            print("hd %s %d variant=%d stages=%d ctas=%d: median %.2f us min %.2f us -> %.0f GB/s" % (
+                dtype.__name__, n, variant, stages, ctas, med * 1e3, mn * 1e3, b / med / 1e6))
+        del sets
+    # ---- vert_adv
+    for dtype in (np.float64, np.float32):
+        sets = []
+        for _ in range(2):
+            arrs, dtr = bench.repo_vert_adv(NI, NJ, NK)
+            sets.append([storage.from_numpy(x.astype(dtype), (3, 3, 0)) for x in arrs])
+        for st in sets:
+            for f in st:
+                f.const_target_tensor()
+        for scratch, threads, unroll, hints in itertools.product((1, 2), (32, 64, 128, 256), (1, 2, 4, 8), (0, 1)):
+            if scratch == 2 and 2 * NK * threads * np.dtype(dtype).itemsize > 227 * 1024:
+                continue
+            if dtype == np.float32 and (hints == 0 or threads == 256):
+                continue
+            for k, v in (("va.scratch", scratch), ("va.threads", threads), ("va.unroll", unroll), ("va.hints", hints)):
+                _lib.set_option(k, v)
+            try:
+                med, mn = timeit(lambda st: stencil.vertical_advection_dycore(*st, 0.15), sets, n=30)
+            except Exception as e:
+                print("va", dtype.__name__, scratch, threads, unroll, hints, "FAILED", e)
+                continue
+            b = 6 * np.dtype(dtype).itemsize * NI * NJ * NK
+            print("va %s scratch=%d threads=%d unroll=%d hints=%d: median %.2f us min %.2f us -> %.0f GB/s" % (
+                dtype.__name__, scratch, threads, unroll, hints, med * 1e3, mn * 1e3, b / med / 1e6))
+
+
+if __name__ == "__main__":
+    main()
