@@ -30,7 +30,7 @@ namespace gtb {
 
     // ---------------------------------------------------------------- options
     struct options {
-        int hd_variant = 0;   // 0 auto, 1 cp.async staged, 2 TMA staged
+        int hd_variant = 0;   // 0 auto, 1 cp.async staged, 2 TMA + block barrier, 3 TMA warp specialised
         int hd_stages = 0;    // 0 auto
         int hd_ctas_per_sm = 0;
         int va_variant = 0;   // 0 auto, 1 register-prefetch LDG
@@ -38,6 +38,8 @@ namespace gtb {
         int va_unroll = 0;    // k levels prefetched ahead
         int va_scratch = 0;   // 0 auto, 1 global (L2) scratch, 2 shared memory
         int va_hints = 1;     // L2 eviction-priority hints on/off
+        int va_ctas_per_sm = 0; // > 0: persistent grid of that many CTAs per SM with per-thread scratch slots
+        int va_save_upos = 0; // keep u_pos(k) next to ccol/dcol instead of re-reading it in the backward sweep
         int copy_vec = 1;     // vectorised copy on/off
     };
     options &opts();

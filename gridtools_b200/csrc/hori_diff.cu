@@ -16,7 +16,7 @@
 //    three block-wide barriers of the reference and leaves exactly one __syncthreads per item (ring hand-over);
 //  * `out` is stored straight from registers, 256 B (fp64) per warp instruction.
 // A second variant stages the same tiles with cp.async (LDGSTS) element by element; it is used when the layout
-// does not satisfy TMA's 16-byte stride/alignment rules, and serves as an A/B baseline ("hd.variant" option).
+// does not satisfy TMA's 16-byte stride/alignment rules, and serves as an A/B baseline ("hd.variant" option: 1 cp.async, 2 TMA + block barrier, 3 TMA warp specialised = default).
 //
 // Arithmetic follows the functor bodies operation by operation (no FMA contraction: the file is compiled with
 // -fmad=false), so results are bit-identical to oracle/gt_oracle.c compiled with -ffp-contract=off.
@@ -29,13 +29,17 @@ namespace {
     constexpr int BI = 64;  // tile extent along i (one warp row = 32 consecutive i)
     constexpr int BJ = 16;  // tile extent along j
     constexpr int R = 4;    // outputs per thread (consecutive j)
-    constexpr int THREADS = BI * (BJ / R);
-    constexpr int IN_W = BI + 4;
+    constexpr int THREADS = BI * (BJ / R); // compute threads
+    constexpr int WARPS = THREADS / 32;
     constexpr int IN_H = BJ + 4;
 
     template <class T>
     struct layout {
-        static constexpr int in_bytes = IN_W * IN_H * (int)sizeof(T);
+        // The staged `in` tile starts LEAD elements before the tile so that every TMA box starts on a 16-byte
+        // boundary (the innermost box coordinate must be 16-byte aligned): 2 doubles or 4 floats; only 2 are used.
+        static constexpr int lead = 16 / (int)sizeof(T);
+        static constexpr int in_w = BI + 2 * lead;
+        static constexpr int in_bytes = in_w * IN_H * (int)sizeof(T);
         static constexpr int co_bytes = BI * BJ * (int)sizeof(T);
         static constexpr int in_alloc = (in_bytes + 127) / 128 * 128;
         static constexpr int co_alloc = (co_bytes + 127) / 128 * 128;
@@ -50,48 +54,62 @@ namespace {
         int64_t in_sj, in_sk, co_sj, co_sk, out_sj, out_sk;
         int ni, nj, nk;
         int tiles_i, tiles_j;
-        int64_t items;
+        int step_i, step_j, step_k; // gridDim.x decomposed in (tile_i, tile_j, k) digits
     };
 
-    struct item_pos {
-        int i0, j0, k;
+    // Position of a CTA in the flat item list (i fastest, then j, then k: CTAs that run side by side work on
+    // neighbouring tiles of the same level, so the halo rows they share are still in L2).  Advancing by gridDim.x
+    // items is three adds with carry instead of 64-bit divisions.
+    struct item_iter {
+        int ti, tj, k;
+        template <class P>
+        __device__ __forceinline__ void start(const P &p, int w) {
+            ti = w % p.tiles_i;
+            int r = w / p.tiles_i;
+            tj = r % p.tiles_j;
+            k = r / p.tiles_j;
+        }
+        template <class P>
+        __device__ __forceinline__ void next(const P &p) {
+            ti += p.step_i;
+            int c = ti >= p.tiles_i;
+            ti -= c * p.tiles_i;
+            tj += p.step_j + c;
+            c = tj >= p.tiles_j;
+            tj -= c * p.tiles_j;
+            k += p.step_k + c;
+        }
+        __device__ __forceinline__ int i0() const { return ti * BI; }
+        __device__ __forceinline__ int j0() const { return tj * BJ; }
     };
 
-    template <class T>
-    __device__ __forceinline__ item_pos decode(const hd_params<T> &p, int64_t w) {
-        // i fastest, then j, then k: CTAs that run side by side work on neighbouring tiles of the same level, so
-        // the halo rows they share are still in L2.
-        int ti = (int)(w % p.tiles_i);
-        int64_t r = w / p.tiles_i;
-        int tj = (int)(r % p.tiles_j);
-        int k = (int)(r / p.tiles_j);
-        return {ti * BI, tj * BJ, k};
-    }
-
-    // The four stages for one thread: column i = tx, rows j0+ty*R .. +R-1, reading the staged tiles.
-    template <class T>
-    __device__ __forceinline__ void compute_item(
-        const hd_params<T> &p, const T *__restrict__ sin, const T *__restrict__ sco, item_pos it, int tx, int ty) {
+    // The four stages for one thread: column i = tx, rows j0+ty*R .. +R-1, reading the staged tiles.  `release` is
+    // called once the thread's shared-memory reads are done (the stage can be refilled while the math runs).
+    template <class T, class Release>
+    __device__ __forceinline__ void compute_item(const hd_params<T> &p, const T *__restrict__ sin,
+        const T *__restrict__ sco, const item_iter &it, int tx, int ty, Release &&release) {
+        constexpr int W = layout<T>::in_w;
         const int jl = ty * R;
-        const T *c = sin + (jl + 2) * IN_W + tx + 2; // in(i, j0+jl)
+        const T *c = sin + (jl + 2) * W + tx + layout<T>::lead; // in(i, j0+jl)
         T c0[R + 4], cp1[R + 2], cm1[R + 2], cp2[R], cm2[R];
 #pragma unroll
         for (int d = 0; d < R + 4; ++d)
-            c0[d] = c[(d - 2) * IN_W];
+            c0[d] = c[(d - 2) * W];
 #pragma unroll
         for (int d = 0; d < R + 2; ++d) {
-            cp1[d] = c[(d - 1) * IN_W + 1];
-            cm1[d] = c[(d - 1) * IN_W - 1];
+            cp1[d] = c[(d - 1) * W + 1];
+            cm1[d] = c[(d - 1) * W - 1];
         }
 #pragma unroll
         for (int d = 0; d < R; ++d) {
-            cp2[d] = c[d * IN_W + 2];
-            cm2[d] = c[d * IN_W - 2];
+            cp2[d] = c[d * W + 2];
+            cm2[d] = c[d * W - 2];
         }
         T co[R];
 #pragma unroll
         for (int d = 0; d < R; ++d)
             co[d] = sco[(jl + d) * BI + tx];
+        release();
 
         // lap_function (horizontal_diffusion.cpp:35-47): 4*in - (in(1,0) + in(0,1) + in(-1,0) + in(0,-1))
         T lap_c[R + 2]; // lap(i, j) for j = -1 .. R
@@ -111,8 +129,8 @@ namespace {
             T res = lap_c[d + 1] - lap_c[d];
             fly[d] = res * (c0[d + 2] - c0[d + 1]) > T(0) ? T(0) : res;
         }
-        const int i = it.i0 + tx;
-        const int j = it.j0 + jl;
+        const int i = it.i0() + tx;
+        const int j = it.j0() + jl;
         T *o = p.out + i + (int64_t)j * p.out_sj + (int64_t)it.k * p.out_sk;
 #pragma unroll
         for (int d = 0; d < R; ++d) {
@@ -128,16 +146,76 @@ namespace {
         }
     }
 
-    // ------------------------------------------------------------------------------------------ TMA variant
+    template <class T>
+    __device__ __forceinline__ void tma_issue(const CUtensorMap *map_in, const CUtensorMap *map_co, unsigned char *base,
+        uint64_t *bar, const item_iter &it) {
+        using L = layout<T>;
+        ptx::mbar_expect_tx(bar, L::in_bytes + L::co_bytes);
+        // tensor coordinate 0 of map_in is element (-lead, -2); of map_co element (0, 0)
+        ptx::tma_load_3d(base, map_in, bar, it.i0(), it.j0(), it.k);
+        ptx::tma_load_3d(base + L::in_alloc, map_co, bar, it.i0(), it.j0(), it.k);
+    }
+
+    // ------------------------------------------------ TMA variant, warp specialised (hd.variant = 3, the default)
+    // WARPS compute warps + 1 producer warp.  full[s]: TMA landed stage s.  empty[s]: all compute warps have read it.
+    // No block-wide barrier in the loop: compute warps drift apart and keep the fp64 pipe and the LSU busy while
+    // other warps wait for data.
+    template <class T, int STAGES>
+    __global__ void __launch_bounds__(THREADS + 32, 2) hd_tma_ws_kernel(const __grid_constant__ CUtensorMap map_in,
+        const __grid_constant__ CUtensorMap map_co, const hd_params<T> p) {
+        using L = layout<T>;
+        extern __shared__ __align__(128) unsigned char smem[];
+        uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * L::stage_bytes);
+        uint64_t *empty = full + STAGES;
+        const int tid = threadIdx.x;
+        const int warp = tid >> 5, lane = tid & 31;
+        if (tid == 0) {
+            ptx::prefetch_tensormap(&map_in);
+            ptx::prefetch_tensormap(&map_co);
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s) {
+                ptx::mbar_init(&full[s], 1);
+                ptx::mbar_init(&empty[s], WARPS);
+            }
+            ptx::fence_barrier_init();
+        }
+        __syncthreads();
+        item_iter it;
+        it.start(p, (int)blockIdx.x);
+        if (warp == WARPS) {
+            if (lane == 0) {
+                for (int n = 0; it.k < p.nk; ++n, it.next(p)) {
+                    const int s = n % STAGES;
+                    if (n >= STAGES)
+                        ptx::mbar_wait(&empty[s], (uint32_t)((n / STAGES - 1) & 1));
+                    tma_issue<T>(&map_in, &map_co, smem + s * L::stage_bytes, &full[s], it);
+                }
+            }
+            return;
+        }
+        const int tx = tid % BI, ty = tid / BI;
+        for (int n = 0; it.k < p.nk; ++n, it.next(p)) {
+            const int s = n % STAGES;
+            ptx::mbar_wait(&full[s], (uint32_t)((n / STAGES) & 1));
+            const unsigned char *base = smem + s * L::stage_bytes;
+            compute_item<T>(p, reinterpret_cast<const T *>(base), reinterpret_cast<const T *>(base + L::in_alloc), it,
+                tx, ty, [&] {
+                    __syncwarp();
+                    if (lane == 0)
+                        ptx::mbar_arrive(&empty[s]);
+                });
+        }
+    }
+
+    // ------------------------------------------------ TMA variant with a block barrier per item (hd.variant = 2)
     template <class T, int STAGES>
     __global__ void __launch_bounds__(THREADS, 2) hd_tma_kernel(const __grid_constant__ CUtensorMap map_in,
-        const __grid_constant__ CUtensorMap map_co, const hd_params<T> p, int pad_in, int pad_co) {
+        const __grid_constant__ CUtensorMap map_co, const hd_params<T> p) {
         using L = layout<T>;
         extern __shared__ __align__(128) unsigned char smem[];
         uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * L::stage_bytes);
         const int tid = threadIdx.x;
         const int tx = tid % BI, ty = tid / BI;
-
         if (tid == 0) {
             ptx::prefetch_tensormap(&map_in);
             ptx::prefetch_tensormap(&map_co);
@@ -147,90 +225,78 @@ namespace {
             ptx::fence_barrier_init();
         }
         __syncthreads();
-
-        const int64_t first = blockIdx.x, step = gridDim.x;
-        const int64_t n_my = first < p.items ? (p.items - first + step - 1) / step : 0;
-
-        auto issue = [&](int s, int64_t w) {
-            item_pos it = decode(p, w);
-            unsigned char *base = smem + s * L::stage_bytes;
-            ptx::mbar_expect_tx(&full[s], L::in_bytes + L::co_bytes);
-            ptx::tma_load_3d(base, &map_in, &full[s], it.i0 + pad_in, it.j0, it.k);
-            ptx::tma_load_3d(base + L::in_alloc, &map_co, &full[s], it.i0 + pad_co, it.j0, it.k);
-        };
-
+        item_iter it, ahead;
+        it.start(p, (int)blockIdx.x);
+        ahead = it;
         if (tid == 0) {
-            for (int s = 0; s < STAGES && s < n_my; ++s)
-                issue(s, first + s * step);
+            for (int s = 0; s < STAGES && ahead.k < p.nk; ++s, ahead.next(p))
+                tma_issue<T>(&map_in, &map_co, smem + s * L::stage_bytes, &full[s], ahead);
         }
-        for (int64_t n = 0; n < n_my; ++n) {
-            const int s = (int)(n % STAGES);
-            const uint32_t parity = (uint32_t)((n / STAGES) & 1);
-            ptx::mbar_wait(&full[s], parity);
+        for (int n = 0; it.k < p.nk; ++n, it.next(p)) {
+            const int s = n % STAGES;
+            ptx::mbar_wait(&full[s], (uint32_t)((n / STAGES) & 1));
             const unsigned char *base = smem + s * L::stage_bytes;
-            compute_item<T>(p,
-                reinterpret_cast<const T *>(base),
-                reinterpret_cast<const T *>(base + L::in_alloc),
-                decode(p, first + n * step),
-                tx,
-                ty);
+            compute_item<T>(p, reinterpret_cast<const T *>(base), reinterpret_cast<const T *>(base + L::in_alloc), it,
+                tx, ty, [] {});
             __syncthreads(); // every thread has consumed stage s: hand it back to the TMA unit
-            if (tid == 0 && n + STAGES < n_my)
-                issue(s, first + (n + STAGES) * step);
+            if (tid == 0 && ahead.k < p.nk) {
+                tma_issue<T>(&map_in, &map_co, smem + s * L::stage_bytes, &full[s], ahead);
+                ahead.next(p);
+            }
         }
     }
 
-    // ------------------------------------------------------------------------------- cp.async (LDGSTS) variant
+    // ------------------------------------------------ cp.async (LDGSTS) variant (hd.variant = 1, any alignment)
     template <class T, int STAGES>
     __global__ void __launch_bounds__(THREADS, 2) hd_cpasync_kernel(const hd_params<T> p) {
         using L = layout<T>;
         extern __shared__ __align__(128) unsigned char smem[];
         const int tid = threadIdx.x;
         const int tx = tid % BI, ty = tid / BI;
-        const int64_t first = blockIdx.x, step = gridDim.x;
-        const int64_t n_my = first < p.items ? (p.items - first + step - 1) / step : 0;
 
-        auto issue = [&](int s, int64_t w) {
-            item_pos it = decode(p, w);
+        auto issue = [&](int s, const item_iter &w) {
             T *sin = reinterpret_cast<T *>(smem + s * L::stage_bytes);
             T *sco = reinterpret_cast<T *>(smem + s * L::stage_bytes + L::in_alloc);
-            const T *gin = p.in + (int64_t)it.k * p.in_sk;
-            for (int e = tid; e < IN_W * IN_H; e += THREADS) {
-                int r = e / IN_W, c = e - r * IN_W;
-                int i = it.i0 + c - 2, j = it.j0 + r - 2;
-                bool ok = i < p.ni + 2 && j < p.nj + 2; // i, j >= -2 always
+            const T *gin = p.in + (int64_t)w.k * p.in_sk;
+            for (int e = tid; e < L::in_w * IN_H; e += THREADS) {
+                int r = e / L::in_w, c = e - r * L::in_w;
+                int i = w.i0() + c - L::lead, j = w.j0() + r - 2;
+                bool ok = i >= -2 && i < p.ni + 2 && j < p.nj + 2; // j >= -2 always
                 const T *src = ok ? gin + i + (int64_t)j * p.in_sj : p.in;
                 ptx::cp_async<sizeof(T)>(sin + e, src, ok);
             }
-            const T *gco = p.coeff + (int64_t)it.k * p.co_sk;
+            const T *gco = p.coeff + (int64_t)w.k * p.co_sk;
             for (int e = tid; e < BI * BJ; e += THREADS) {
                 int r = e / BI, c = e - r * BI;
-                int i = it.i0 + c, j = it.j0 + r;
+                int i = w.i0() + c, j = w.j0() + r;
                 bool ok = i < p.ni && j < p.nj;
                 const T *src = ok ? gco + i + (int64_t)j * p.co_sj : p.coeff;
                 ptx::cp_async<sizeof(T)>(sco + e, src, ok);
             }
         };
 
+        item_iter it, ahead;
+        it.start(p, (int)blockIdx.x);
+        ahead = it;
         for (int s = 0; s < STAGES - 1; ++s) {
-            if (s < n_my)
-                issue(s, first + s * step);
+            if (ahead.k < p.nk) {
+                issue(s, ahead);
+                ahead.next(p);
+            }
             ptx::cp_async_commit();
         }
-        for (int64_t n = 0; n < n_my; ++n) {
-            const int s = (int)(n % STAGES);
+        for (int n = 0; it.k < p.nk; ++n, it.next(p)) {
+            const int s = n % STAGES;
             ptx::cp_async_wait<STAGES - 2>(); // this thread's copies for item n have landed
             __syncthreads();                  // ... everybody's have, and stage (n-1)%STAGES is free again
-            if (n + STAGES - 1 < n_my)
-                issue((int)((n + STAGES - 1) % STAGES), first + (n + STAGES - 1) * step);
+            if (ahead.k < p.nk) {
+                issue((n + STAGES - 1) % STAGES, ahead);
+                ahead.next(p);
+            }
             ptx::cp_async_commit();
             const unsigned char *base = smem + s * L::stage_bytes;
-            compute_item<T>(p,
-                reinterpret_cast<const T *>(base),
-                reinterpret_cast<const T *>(base + L::in_alloc),
-                decode(p, first + n * step),
-                tx,
-                ty);
+            compute_item<T>(p, reinterpret_cast<const T *>(base), reinterpret_cast<const T *>(base + L::in_alloc), it,
+                tx, ty, [] {});
         }
         ptx::cp_async_wait<0>();
     }
@@ -247,11 +313,12 @@ namespace {
         return CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     }
 
-    // Tensor map over a field whose coordinate 0 sits `lead_i` (+pad for 16-byte alignment) elements before the
-    // origin in i and `lead_j` rows before it in j.  Returns false when the layout is not TMA-addressable.
+    // Tensor map whose coordinate 0 is element (-lead_i, -lead_j, 0) of the field and that covers len_i x len_j x
+    // len_k elements from there.  Returns false when the layout is not TMA-addressable (base or strides not 16-byte
+    // aligned): the caller then uses the cp.async variant.
     template <class T>
-    bool make_map(CUtensorMap *map, int *pad, const T *origin, int64_t sj, int64_t sk, int lead_i, int lead_j,
-        int64_t len_i, int64_t len_j, int64_t len_k, int box_i, int box_j) {
+    bool make_map(CUtensorMap *map, const T *origin, int64_t sj, int64_t sk, int lead_i, int lead_j, int64_t len_i,
+        int64_t len_j, int64_t len_k, int box_i, int box_j) {
         auto enc = tensor_map_encoder();
         if (!enc)
             return false;
@@ -259,18 +326,10 @@ namespace {
         if ((sj * es) % 16 != 0 || (sk * es) % 16 != 0 || sj <= 0 || sk <= 0)
             return false;
         uintptr_t a = reinterpret_cast<uintptr_t>(origin - lead_i - (int64_t)lead_j * sj);
-        int extra = (int)((a % 16) / es); // move the base down to the previous 16-byte boundary
-        a -= (uintptr_t)extra * es;
         if (a % 16 != 0)
             return false;
-        // keep the descriptor self-consistent: a row of the tensor must fit inside the row pitch
-        if ((len_i + extra) > sj || len_j * sj > sk)
-            return false;
-        *pad = extra;
-        cuuint64_t dims[3] = {(cuuint64_t)(len_i + extra), (cuuint64_t)len_j, (cuuint64_t)len_k};
+        cuuint64_t dims[3] = {(cuuint64_t)len_i, (cuuint64_t)len_j, (cuuint64_t)len_k};
         cuuint64_t strides[2] = {(cuuint64_t)(sj * es), (cuuint64_t)(sk * es)};
-        // a single k level is addressed with a k stride that may be smaller than sj * len_j for padded layouts;
-        // TMA only needs the strides to be multiples of 16 bytes
         cuuint32_t box[3] = {(cuuint32_t)box_i, (cuuint32_t)box_j, 1};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = enc(map,
@@ -304,36 +363,52 @@ namespace {
     }
 
     template <class T, int STAGES>
-    int launch(const hd_params<T> &p, int variant, int ctas_per_sm, cudaStream_t stream) {
+    int launch(hd_params<T> &p, int variant, int ctas_per_sm, cudaStream_t stream) {
         using L = layout<T>;
         device_state *d = dev();
-        const int smem = STAGES * L::stage_bytes + 8 * STAGES;
-        int64_t grid = (int64_t)d->sm_count * ctas_per_sm;
-        if (grid > p.items)
-            grid = p.items;
+        const int smem = STAGES * L::stage_bytes + 16 * STAGES;
+        const int64_t items = (int64_t)p.tiles_i * p.tiles_j * p.nk;
+        if (items >= (int64_t)1 << 31)
+            return fail(GTB_ERR_ARG, "gtb_hori_diff: domain too large (%lld tile-levels)", (long long)items);
+        int grid = d->sm_count * ctas_per_sm;
+        if (grid > items)
+            grid = (int)items;
+        p.step_i = grid % p.tiles_i;
+        p.step_j = (grid / p.tiles_i) % p.tiles_j;
+        p.step_k = (grid / p.tiles_i) / p.tiles_j;
         if (variant != 1) {
             CUtensorMap map_in, map_co;
-            int pad_in = 0, pad_co = 0;
-            bool ok = make_map<T>(&map_in, &pad_in, p.in, p.in_sj, p.in_sk, 2, 2, p.ni + 4, p.nj + 4, p.nk, IN_W, IN_H) &&
-                      make_map<T>(&map_co, &pad_co, p.coeff, p.co_sj, p.co_sk, 0, 0, p.ni, p.nj, p.nk, BI, BJ);
-            if (ok) {
+            bool ok = make_map<T>(&map_in, p.in, p.in_sj, p.in_sk, L::lead, 2, (int64_t)L::lead + p.ni + 2, p.nj + 4,
+                          p.nk, L::in_w, IN_H) &&
+                      make_map<T>(&map_co, p.coeff, p.co_sj, p.co_sk, 0, 0, p.ni, p.nj, p.nk, BI, BJ);
+            if (ok && variant == 2) {
                 auto kernel = hd_tma_kernel<T, STAGES>;
                 int st = prepare_kernel(kernel, smem);
                 if (st)
                     return st;
-                kernel<<<(unsigned)grid, THREADS, smem, stream>>>(map_in, map_co, p, pad_in, pad_co);
+                kernel<<<grid, THREADS, smem, stream>>>(map_in, map_co, p);
                 count_launch();
                 return check_launch("hd_tma_kernel");
             }
-            if (variant == 2)
+            if (ok) {
+                auto kernel = hd_tma_ws_kernel<T, STAGES>;
+                int st = prepare_kernel(kernel, smem);
+                if (st)
+                    return st;
+                kernel<<<grid, THREADS + 32, smem, stream>>>(map_in, map_co, p);
+                count_launch();
+                return check_launch("hd_tma_ws_kernel");
+            }
+            if (variant != 0)
                 return fail(GTB_ERR_LAYOUT,
-                    "gtb_hori_diff: hd.variant=2 (TMA) needs stride_j/stride_k that are multiples of 16 bytes");
+                    "gtb_hori_diff: hd.variant=%d (TMA) needs 16-byte aligned origins and stride_j/stride_k that "
+                    "are multiples of 16 bytes", variant);
         }
         auto kernel = hd_cpasync_kernel<T, STAGES>;
         int st = prepare_kernel(kernel, smem);
         if (st)
             return st;
-        kernel<<<(unsigned)grid, THREADS, smem, stream>>>(p);
+        kernel<<<grid, THREADS, smem, stream>>>(p);
         count_launch();
         return check_launch("hd_cpasync_kernel");
     }
@@ -362,7 +437,6 @@ namespace {
         p.out_sj = out->stride_j, p.out_sk = out->stride_k;
         p.ni = ni, p.nj = nj, p.nk = nk;
         p.tiles_i = ceil_div(ni, BI), p.tiles_j = ceil_div(nj, BJ);
-        p.items = (int64_t)p.tiles_i * p.tiles_j * nk;
         const options &o = opts();
         int stages = o.hd_stages ? o.hd_stages : 4;
         int ctas = o.hd_ctas_per_sm ? o.hd_ctas_per_sm : 2;

@@ -167,6 +167,8 @@ namespace {
             {"va.unroll", &o.va_unroll},
             {"va.scratch", &o.va_scratch},
             {"va.hints", &o.va_hints},
+            {"va.ctas_per_sm", &o.va_ctas_per_sm},
+            {"va.save_upos", &o.va_save_upos},
             {"copy.vec", &o.copy_vec}};
         for (auto &t : table)
             if (strcmp(t.name, key) == 0)

@@ -40,8 +40,10 @@ namespace {
         T dtr;
         int ni, nj, nk;
         int tiles_i;
-        T *scratch; // [2*nk][ncols] when the global scratch is used
-        int64_t ncols;
+        int items;      // column blocks of 32 x (threads/32) columns
+        T *scratch;     // [NS*nk][slots] when the global scratch is used
+        int64_t slots;  // columns (one slot per column) or resident threads (persistent grid: one slot per thread)
+        int persistent; // slots are per thread and CTAs loop over the items
     };
 
     template <class T, bool Hints>
@@ -57,13 +59,15 @@ namespace {
         T us, un, w0, w1, up, ut; // utens_stage(k), u_stage(k+1), wcon(i,k+1), wcon(i+1,k+1), u_pos(k), utens(k)
     };
 
-    // SMEM: ccol/dcol live in dynamic shared memory [2*nk][THREADS]; else in p.scratch [2*nk][ncols].
-    template <class T, int UNROLL, bool SMEM, bool Hints>
-    __global__ void va_kernel(const va_params<T> p) {
-        extern __shared__ __align__(16) unsigned char smem_raw[];
+    // SMEM: ccol/dcol live in dynamic shared memory [NS*nk][THREADS]; else in p.scratch [NS*nk][slots].
+    // SAVE_UPOS: u_pos(k) is kept next to ccol/dcol (NS = 3) so that the backward sweep does not read it from HBM a
+    // second time.
+    template <class T, int UNROLL, bool SMEM, bool Hints, bool SAVE_UPOS>
+    __device__ __forceinline__ void va_columns(const va_params<T> &p, int item, unsigned char *smem_raw) {
+        constexpr int NS = SAVE_UPOS ? 3 : 2;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const int tj_threads = blockDim.x >> 5;
-        const int ti = blockIdx.x % p.tiles_i, tj = blockIdx.x / p.tiles_i;
+        const int ti = item % p.tiles_i, tj = item / p.tiles_i;
         const int i = ti * 32 + lane, j = tj * tj_threads + warp;
         if (i >= p.ni || j >= p.nj)
             return;
@@ -84,31 +88,39 @@ namespace {
         const int64_t us_sk = p.utens_stage.sk, un_sk = p.u_stage.sk, wc_sk = p.wcon.sk, up_sk = p.u_pos.sk,
                       ut_sk = p.utens.sk;
 
-        T *sc;            // ccol(k) at sc[(2*k) * sc_stride], dcol(k) at sc[(2*k+1) * sc_stride]
+        T *sc;            // ccol(k) at sc[(NS*k) * sc_stride], dcol(k) at sc[(NS*k+1) * sc_stride], u_pos(k) at +2
         int64_t sc_stride;
         if constexpr (SMEM) {
             sc = reinterpret_cast<T *>(smem_raw) + threadIdx.x;
             sc_stride = blockDim.x;
         } else {
-            sc = p.scratch + (int64_t)j * p.ni + i;
-            sc_stride = p.ncols;
+            sc = p.scratch + (p.persistent ? (int64_t)blockIdx.x * blockDim.x + threadIdx.x : (int64_t)j * p.ni + i);
+            sc_stride = p.slots;
         }
-        auto sc_store = [&](int k, T cc, T dc) {
+        auto sc_store = [&](int k, T cc, T dc, T up) {
             if constexpr (SMEM || !Hints) {
-                sc[(2 * k) * sc_stride] = cc;
-                sc[(2 * k + 1) * sc_stride] = dc;
+                sc[(NS * k) * sc_stride] = cc;
+                sc[(NS * k + 1) * sc_stride] = dc;
+                if constexpr (SAVE_UPOS)
+                    sc[(NS * k + 2) * sc_stride] = up;
             } else {
-                ptx::st_hint(sc + (2 * k) * sc_stride, cc, pol_keep);
-                ptx::st_hint(sc + (2 * k + 1) * sc_stride, dc, pol_keep);
+                ptx::st_hint(sc + (NS * k) * sc_stride, cc, pol_keep);
+                ptx::st_hint(sc + (NS * k + 1) * sc_stride, dc, pol_keep);
+                if constexpr (SAVE_UPOS)
+                    ptx::st_hint(sc + (NS * k + 2) * sc_stride, up, pol_keep);
             }
         };
-        auto sc_load = [&](int k, T &cc, T &dc) {
+        auto sc_load = [&](int k, T &cc, T &dc, T &up) {
             if constexpr (SMEM || !Hints) {
-                cc = sc[(2 * k) * sc_stride];
-                dc = sc[(2 * k + 1) * sc_stride];
+                cc = sc[(NS * k) * sc_stride];
+                dc = sc[(NS * k + 1) * sc_stride];
+                if constexpr (SAVE_UPOS)
+                    up = sc[(NS * k + 2) * sc_stride];
             } else {
-                cc = ptx::ld_hint(sc + (2 * k) * sc_stride, pol_keep);
-                dc = ptx::ld_hint(sc + (2 * k + 1) * sc_stride, pol_keep);
+                cc = ptx::ld_hint(sc + (NS * k) * sc_stride, pol_keep);
+                dc = ptx::ld_hint(sc + (NS * k + 1) * sc_stride, pol_keep);
+                if constexpr (SAVE_UPOS)
+                    up = ptx::ld_hint(sc + (NS * k + 2) * sc_stride, pol_keep);
             }
         };
 
@@ -188,7 +200,7 @@ namespace {
                         up_last = v.up;
                     }
                     if (k < nk - 1)
-                        sc_store(k, cc, dc);
+                        sc_store(k, cc, dc, v.up);
                     cc_prev = cc;
                     dc_prev = dc;
                     u_km1 = u_k;
@@ -209,8 +221,9 @@ namespace {
         };
         auto load_back = [&](int k, back_level &v) {
             if (k >= 0) {
-                sc_load(k, v.cc, v.dc);
-                v.up = ldg_stream<T, Hints>(up_p + k * up_sk, pol_stream);
+                sc_load(k, v.cc, v.dc, v.up);
+                if constexpr (!SAVE_UPOS)
+                    v.up = ldg_stream<T, Hints>(up_p + k * up_sk, pol_stream);
             }
         };
         back_level bcur[UNROLL];
@@ -233,6 +246,19 @@ namespace {
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u)
                 bcur[u] = bnxt[u];
+        }
+    }
+
+    template <class T, int UNROLL, bool SMEM, bool Hints, bool SAVE_UPOS>
+    __global__ void va_kernel(const va_params<T> p) {
+        extern __shared__ __align__(16) unsigned char smem_raw[];
+        if (p.persistent) {
+            // resident CTAs walk the column blocks; a thread re-uses its scratch slot for every block it handles,
+            // so the scratch footprint is (resident threads) x nk instead of (all columns) x nk and stays in L2
+            for (int item = blockIdx.x; item < p.items; item += gridDim.x)
+                va_columns<T, UNROLL, SMEM, Hints, SAVE_UPOS>(p, item, smem_raw);
+        } else {
+            va_columns<T, UNROLL, SMEM, Hints, SAVE_UPOS>(p, blockIdx.x, smem_raw);
         }
     }
 
@@ -340,9 +366,9 @@ namespace {
     }
 
     // ------------------------------------------------------------------------------------------ host side
-    template <class T, int UNROLL, bool SMEM, bool Hints>
-    int launch_va(const va_params<T> &p, int threads, int smem, cudaStream_t stream) {
-        auto kernel = va_kernel<T, UNROLL, SMEM, Hints>;
+    template <class T, int UNROLL, bool SMEM, bool Hints, bool SAVE_UPOS>
+    int launch_va(const va_params<T> &p, int threads, int smem, int grid, cudaStream_t stream) {
+        auto kernel = va_kernel<T, UNROLL, SMEM, Hints, SAVE_UPOS>;
         if (smem > 48 * 1024) {
             static thread_local int done_smem = 0, done_dev = -1;
             if (done_smem < smem || done_dev != dev()->device) {
@@ -351,27 +377,35 @@ namespace {
                 done_dev = dev()->device;
             }
         }
-        const int tj = threads / 32;
-        const int64_t blocks = (int64_t)p.tiles_i * ceil_div(p.nj, tj);
-        kernel<<<(unsigned)blocks, threads, smem, stream>>>(p);
+        kernel<<<grid, threads, smem, stream>>>(p);
         count_launch();
         return check_launch("va_kernel");
     }
 
-    template <class T, bool SMEM, bool Hints>
-    int dispatch_unroll(const va_params<T> &p, int unroll, int threads, int smem, cudaStream_t stream) {
+    template <class T, bool SMEM, bool Hints, bool SAVE_UPOS>
+    int dispatch_unroll(const va_params<T> &p, int unroll, int threads, int smem, int grid, cudaStream_t stream) {
         switch (unroll) {
         case 1:
-            return launch_va<T, 1, SMEM, Hints>(p, threads, smem, stream);
+            return launch_va<T, 1, SMEM, Hints, SAVE_UPOS>(p, threads, smem, grid, stream);
         case 2:
-            return launch_va<T, 2, SMEM, Hints>(p, threads, smem, stream);
+            return launch_va<T, 2, SMEM, Hints, SAVE_UPOS>(p, threads, smem, grid, stream);
         case 4:
-            return launch_va<T, 4, SMEM, Hints>(p, threads, smem, stream);
+            return launch_va<T, 4, SMEM, Hints, SAVE_UPOS>(p, threads, smem, grid, stream);
         case 8:
-            return launch_va<T, 8, SMEM, Hints>(p, threads, smem, stream);
+            return launch_va<T, 8, SMEM, Hints, SAVE_UPOS>(p, threads, smem, grid, stream);
         default:
             return fail(GTB_ERR_ARG, "gtb_vert_adv: va.unroll must be 1, 2, 4 or 8");
         }
+    }
+
+    template <class T, bool SMEM>
+    int dispatch_flags(const va_params<T> &p, bool hints, bool save_upos, int unroll, int threads, int smem, int grid,
+        cudaStream_t stream) {
+        if (hints)
+            return save_upos ? dispatch_unroll<T, SMEM, true, true>(p, unroll, threads, smem, grid, stream)
+                             : dispatch_unroll<T, SMEM, true, false>(p, unroll, threads, smem, grid, stream);
+        return save_upos ? dispatch_unroll<T, SMEM, false, true>(p, unroll, threads, smem, grid, stream)
+                         : dispatch_unroll<T, SMEM, false, false>(p, unroll, threads, smem, grid, stream);
     }
 
     template <class T>
@@ -412,9 +446,23 @@ namespace {
         p.dtr = dtr_stage;
         p.ni = ni, p.nj = nj, p.nk = nk;
         p.tiles_i = ceil_div(ni, 32);
-        p.ncols = (int64_t)ni * nj;
+        const int64_t items = (int64_t)p.tiles_i * ceil_div(nj, threads / 32);
+        if (items >= (int64_t)1 << 31)
+            return fail(GTB_ERR_ARG, "gtb_vert_adv: domain too large");
+        p.items = (int)items;
         p.scratch = nullptr;
-        const int64_t smem_need = (int64_t)2 * nk * threads * (int64_t)sizeof(T);
+        const bool save_upos = o.va_save_upos != 0;
+        const int ns = save_upos ? 3 : 2;
+        int grid = p.items;
+        p.persistent = 0;
+        // va.ctas_per_sm > 0: that many resident CTAs per SM; < 0: an absolute grid size (used by the tests to
+        // exercise the persistent path on small domains)
+        const int64_t want = o.va_ctas_per_sm > 0 ? (int64_t)o.va_ctas_per_sm * d->sm_count : -(int64_t)o.va_ctas_per_sm;
+        if (want > 0 && want < items) {
+            grid = (int)want;
+            p.persistent = 1;
+        }
+        const int64_t smem_need = (int64_t)ns * nk * threads * (int64_t)sizeof(T);
         int mode = o.va_scratch;
         if (mode == 0)
             mode = 1;
@@ -422,15 +470,13 @@ namespace {
             return fail(GTB_ERR_ARG, "gtb_vert_adv: va.scratch=2 needs %lld bytes of shared memory per CTA (max %d)",
                 (long long)smem_need, d->max_smem_optin);
         cudaStream_t s = as_stream(stream);
-        if (mode == 2) {
-            return o.va_hints ? dispatch_unroll<T, true, true>(p, unroll, threads, (int)smem_need, s)
-                              : dispatch_unroll<T, true, false>(p, unroll, threads, (int)smem_need, s);
-        }
-        p.scratch = static_cast<T *>(scratch((size_t)2 * nk * p.ncols * sizeof(T)));
+        if (mode == 2)
+            return dispatch_flags<T, true>(p, o.va_hints != 0, save_upos, unroll, threads, (int)smem_need, grid, s);
+        p.slots = p.persistent ? (int64_t)grid * threads : (int64_t)ni * nj;
+        p.scratch = static_cast<T *>(scratch((size_t)ns * nk * p.slots * sizeof(T)));
         if (!p.scratch)
             return GTB_ERR_ALLOC;
-        return o.va_hints ? dispatch_unroll<T, false, true>(p, unroll, threads, 0, s)
-                          : dispatch_unroll<T, false, false>(p, unroll, threads, 0, s);
+        return dispatch_flags<T, false>(p, o.va_hints != 0, save_upos, unroll, threads, 0, grid, s);
     }
 
 } // namespace

@@ -36,7 +36,8 @@ def gt():
 @pytest.fixture(autouse=True)
 def reset_options(gt):
     yield
-    for k in ("hd.variant", "hd.stages", "hd.ctas_per_sm", "va.variant", "va.threads", "va.unroll", "va.scratch"):
+    for k in ("hd.variant", "hd.stages", "hd.ctas_per_sm", "va.variant", "va.threads", "va.unroll", "va.scratch",
+              "va.ctas_per_sm", "va.save_upos"):
         gt.lib.set_option(k, 0)
     gt.lib.set_option("va.hints", 1)
     gt.lib.set_option("copy.vec", 1)
@@ -85,7 +86,7 @@ def test_copy_scalar_path(gt, oracle):
 
 
 # ------------------------------------------------------------------------------------- horizontal diffusion
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("name", ["hori_diff_12x33x6.npz", "hori_diff_70x19x3.npz"])
 def test_hori_diff_golden(gt, oracle, golden, name, variant):
     g = golden(name)
@@ -102,19 +103,22 @@ def test_hori_diff_golden(gt, oracle, golden, name, variant):
     assert np.all(out[halo_mask] == -7.0), "the kernel wrote outside the compute domain"
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("size,alignment", [((1, 1, 1), 128), ((5, 3, 2), 1), ((64, 16, 3), 128), ((65, 17, 2), 128),
                                             ((129, 47, 5), 1), ((200, 40, 7), 128), ((23, 11, 43), 128)])
 def test_hori_diff_random_bit_exact(gt, oracle, variant, dtype, size, alignment):
     ni, nj, nk = size
-    if variant == 2 and alignment == 1 and ((ni + 4) * np.dtype(dtype).itemsize) % 16:
-        pytest.skip("layout is not TMA addressable; covered by test_hori_diff_tma_refuses_bad_layout")
     rng = np.random.default_rng(ni * 131 + nj * 7 + nk)
     inp = rng.standard_normal((nk, nj + 4, ni + 4)).astype(dtype)
     coeff = rng.uniform(0, 0.05, inp.shape).astype(dtype)
     gt.lib.set_option("hd.variant", variant)
-    out = run_hd(gt, inp, coeff, alignment)
+    try:
+        out = run_hd(gt, inp, coeff, alignment)
+    except gt.lib.GtbError as e:
+        # an explicitly requested TMA variant refuses layouts TMA cannot address (variant 0 falls back to cp.async)
+        assert variant in (2, 3) and alignment == 1 and e.status == gt.lib.GTB_ERR_LAYOUT
+        pytest.skip("layout is not TMA addressable")
     inner = (slice(None), slice(2, -2), slice(2, -2))
     assert np.array_equal(out[inner], oracle.hori_diff(inp, coeff)[inner])
 
@@ -134,7 +138,7 @@ def test_hori_diff_pipeline_depths(gt, oracle, stages, ctas):
     coeff = rng.uniform(0, 0.05, inp.shape)
     ref = oracle.hori_diff(inp, coeff)
     inner = (slice(None), slice(2, -2), slice(2, -2))
-    for variant in (1, 2):
+    for variant in (1, 2, 3):
         gt.lib.set_option("hd.variant", variant)
         gt.lib.set_option("hd.stages", stages)
         gt.lib.set_option("hd.ctas_per_sm", ctas)
@@ -173,7 +177,9 @@ def test_hori_diff_linearity(gt):
 # ------------------------------------------------------------------------------------- vertical advection
 VA_CONFIGS = [dict(), dict(threads=32, unroll=1), dict(threads=128, unroll=2), dict(threads=64, unroll=8),
               dict(scratch=2, threads=32, unroll=4), dict(scratch=2, threads=64, unroll=2, hints=0),
-              dict(hints=0, unroll=4)]
+              dict(hints=0, unroll=4), dict(ctas_per_sm=-3, threads=32, unroll=2),
+              dict(ctas_per_sm=-2, threads=32, save_upos=1), dict(scratch=2, threads=32, save_upos=1, ctas_per_sm=-1),
+              dict(save_upos=1, hints=0, unroll=8)]
 
 
 def set_va(gt, cfg):
@@ -211,7 +217,7 @@ def test_vert_adv_random_bit_exact(gt, oracle, size, alignment):
     shape = (nk, nj + 6, ni + 6)
     arrs = [rng.uniform(5, 9, shape), rng.uniform(5, 9, shape), rng.uniform(-3e-4, 3e-4, shape),
             rng.uniform(5, 9, shape), rng.uniform(-1e-5, 1e-5, shape)]
-    for cfg in (dict(), dict(scratch=2, threads=32)):
+    for cfg in (dict(), dict(scratch=2, threads=32), dict(ctas_per_sm=-2, threads=32, save_upos=1)):
         set_va(gt, cfg)
         out, _ = run_va(gt, arrs, 0.15, alignment)
         inner = (slice(None), slice(3, -3), slice(3, -3))

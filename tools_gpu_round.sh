@@ -5,9 +5,16 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,power.limit,memor
 nproc >> gpurun_out/gpu.txt
 STEP=${1:-all}
 if [ "$STEP" = all ] || [ "$STEP" = test ]; then
-  timeout 900 python -m pytest tests -m gpu -q --maxfail=30 -p no:cacheprovider --timeout=300 > gpurun_out/pytest_gpu.log 2>&1
-  echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-  tail -5 gpurun_out/pytest_gpu.log
+  : > gpurun_out/pytest_gpu.log
+  for f in tests/test_stencils_gpu.py tests/test_halo_gpu.py; do   # one process per file: a fault cannot cascade
+    timeout 900 python -m pytest $f -m gpu -q --maxfail=10 -p no:cacheprovider --timeout=300 >> gpurun_out/pytest_gpu.log 2>&1
+    echo "pytest $f exit $?" >> gpurun_out/pytest_gpu.log
+  done
+  grep -E "passed|failed|exit" gpurun_out/pytest_gpu.log | tail -6
+fi
+if [ "$STEP" = sanitize ]; then
+  timeout 900 compute-sanitizer --tool memcheck python tools_sanitize.py > gpurun_out/sanitize.log 2>&1
+  tail -15 gpurun_out/sanitize.log
 fi
 if [ "$STEP" = all ] || [ "$STEP" = tune ]; then
   timeout 600 python tools_tune.py > gpurun_out/tune.txt 2>&1
