@@ -33,13 +33,13 @@ namespace gtb {
         int hd_variant = 0;   // 0 auto, 1 cp.async staged, 2 TMA + block barrier, 3 TMA warp specialised
         int hd_stages = 0;    // 0 auto
         int hd_ctas_per_sm = 0;
-        int va_variant = 0;   // 0 auto, 1 register-prefetch LDG
+        int va_variant = 0;   // 0 auto, 1 register-prefetch LDG, 2 TMA-streamed persistent warps
         int va_threads = 0;   // threads per CTA (multiple of 32)
         int va_unroll = 0;    // k levels prefetched ahead
         int va_scratch = 0;   // 0 auto, 1 global (L2) scratch, 2 shared memory
         int va_hints = 1;     // L2 eviction-priority hints on/off
         int va_ctas_per_sm = 0; // > 0: persistent grid of that many CTAs per SM with per-thread scratch slots
-        int va_save_upos = 0; // keep u_pos(k) next to ccol/dcol instead of re-reading it in the backward sweep
+        int va_save_upos = 0; // u_pos(k) kept next to ccol/dcol instead of re-read in the backward sweep: 0 auto, 1 on, 2 off
         int copy_vec = 1;     // vectorised copy on/off
     };
     options &opts();

@@ -22,6 +22,7 @@
 // Arithmetic follows the functor bodies operation by operation (-fmad=false, IEEE division), so results are
 // bit-identical to oracle/gt_oracle.c compiled with -ffp-contract=off.
 #include "common.cuh"
+#include "tma.cuh"
 
 using namespace gtb;
 
@@ -44,6 +45,7 @@ namespace {
         T *scratch;     // [NS*nk][slots] when the global scratch is used
         int64_t slots;  // columns (one slot per column) or resident threads (persistent grid: one slot per thread)
         int persistent; // slots are per thread and CTAs loop over the items
+        int kc;         // levels per TMA stage (TMA variant)
     };
 
     template <class T, bool Hints>
@@ -59,6 +61,64 @@ namespace {
         T us, un, w0, w1, up, ut; // utens_stage(k), u_stage(k+1), wcon(i,k+1), wcon(i+1,k+1), u_pos(k), utens(k)
     };
 
+    // Rotating k_caches of one column (registers): u_stage(k-1), u_stage(k), wcon(i+1,k)+wcon(i,k), ccol/dcol(k-1).
+    template <class T>
+    struct va_state {
+        T u_k, u_km1, wsum_k, cc_prev, dc_prev, up_last;
+    };
+
+    // One level of u_forward_function for one column.  us = utens_stage(k), un = u_stage(k+1), w0/w1 = wcon(i,k+1) /
+    // wcon(i+1,k+1), up = u_pos(k), ut = utens(k).  Returns ccol(k), dcol(k) and slides the k_caches.
+    template <class T>
+    __device__ __forceinline__ void va_forward_level(
+        int k, int nk, T dtr, T us, T un, T w0, T w1, T up, T ut, va_state<T> &s, T &cc, T &dc) {
+        const T bet_m = T(0.5), bet_p = T(0.5); // vertical_advection_defs.hpp
+        T dd = dtr * up + ut + us;                // dtr_stage * u_pos + utens + utens_stage
+        if (k == 0) {                             // first_level, vertical_advection_dycore.cpp:85-98
+            T wsum_n = w1 + w0;
+            T gcv = T(.25) * wsum_n;
+            T cs = gcv * bet_m;
+            T c = gcv * bet_p;
+            T b = dtr - c;
+            T correction = -cs * (un - s.u_k);
+            T d = dd + correction;
+            T divided = T(1) / b;
+            cc = c * divided;
+            dc = d * divided;
+            s.wsum_k = wsum_n;
+        } else if (k < nk - 1) { // body, :50-68
+            T wsum_n = w1 + w0;
+            T gav = -T(.25) * s.wsum_k;
+            T gcv = T(.25) * wsum_n;
+            T as = gav * bet_m;
+            T cs = gcv * bet_m;
+            T a = gav * bet_p;
+            T c = gcv * bet_p;
+            T b = dtr - a - c;
+            T correction = -as * (s.u_km1 - s.u_k) - cs * (un - s.u_k);
+            T d = dd + correction;
+            T divided = T(1) / (b - s.cc_prev * a);
+            cc = c * divided;
+            dc = (d - s.dc_prev * a) * divided;
+            s.wsum_k = wsum_n;
+        } else { // last_level, :70-83
+            T gav = -T(.25) * s.wsum_k;
+            T as = gav * bet_m;
+            T a = gav * bet_p;
+            T b = dtr - a;
+            T correction = -as * (s.u_km1 - s.u_k);
+            T d = dd + correction;
+            T divided = T(1) / (b - s.cc_prev * a);
+            cc = s.cc_prev; // ccol is not written on the last level
+            dc = (d - s.dc_prev * a) * divided;
+            s.up_last = up;
+        }
+        s.cc_prev = cc;
+        s.dc_prev = dc;
+        s.u_km1 = s.u_k;
+        s.u_k = un;
+    }
+
     // SMEM: ccol/dcol live in dynamic shared memory [NS*nk][THREADS]; else in p.scratch [NS*nk][slots].
     // SAVE_UPOS: u_pos(k) is kept next to ccol/dcol (NS = 3) so that the backward sweep does not read it from HBM a
     // second time.
@@ -73,7 +133,6 @@ namespace {
             return;
         const int nk = p.nk;
         const T dtr = p.dtr;
-        const T bet_m = T(0.5), bet_p = T(0.5); // vertical_advection_defs.hpp
         uint64_t pol_stream = 0, pol_keep = 0;
         if constexpr (Hints) {
             pol_stream = ptx::policy_evict_first();
@@ -142,11 +201,9 @@ namespace {
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
             load_level(u, cur[u]);
-        T u_k = ldg_stream<T, Hints>(un_p, pol_stream); // u_stage(k), starts at k = 0
-        T u_km1 = T(0);
-        T wsum_k = T(0); // wcon(i+1,k) + wcon(i,k)
-        T cc_prev = T(0), dc_prev = T(0);
-        T up_last = T(0);
+        va_state<T> st;
+        st.u_k = ldg_stream<T, Hints>(un_p, pol_stream); // u_stage(k), starts at k = 0
+        st.u_km1 = st.wsum_k = st.cc_prev = st.dc_prev = st.up_last = T(0);
 
         for (int k0 = 0; k0 < nk; k0 += UNROLL) {
             va_level<T> nxt[UNROLL];
@@ -158,53 +215,10 @@ namespace {
                 const int k = k0 + u;
                 if (k < nk) {
                     const va_level<T> &v = cur[u];
-                    T dd = dtr * v.up + v.ut + v.us; // dtr_stage * u_pos + utens + utens_stage
                     T cc, dc;
-                    if (k == 0) { // first_level, vertical_advection_dycore.cpp:85-98
-                        T wsum_n = v.w1 + v.w0;
-                        T gcv = T(.25) * wsum_n;
-                        T cs = gcv * bet_m;
-                        T c = gcv * bet_p;
-                        T b = dtr - c;
-                        T correction = -cs * (v.un - u_k);
-                        T d = dd + correction;
-                        T divided = T(1) / b;
-                        cc = c * divided;
-                        dc = d * divided;
-                        wsum_k = wsum_n;
-                    } else if (k < nk - 1) { // body, :50-68
-                        T wsum_n = v.w1 + v.w0;
-                        T gav = -T(.25) * wsum_k;
-                        T gcv = T(.25) * wsum_n;
-                        T as = gav * bet_m;
-                        T cs = gcv * bet_m;
-                        T a = gav * bet_p;
-                        T c = gcv * bet_p;
-                        T b = dtr - a - c;
-                        T correction = -as * (u_km1 - u_k) - cs * (v.un - u_k);
-                        T d = dd + correction;
-                        T divided = T(1) / (b - cc_prev * a);
-                        cc = c * divided;
-                        dc = (d - dc_prev * a) * divided;
-                        wsum_k = wsum_n;
-                    } else { // last_level, :70-83
-                        T gav = -T(.25) * wsum_k;
-                        T as = gav * bet_m;
-                        T a = gav * bet_p;
-                        T b = dtr - a;
-                        T correction = -as * (u_km1 - u_k);
-                        T d = dd + correction;
-                        T divided = T(1) / (b - cc_prev * a);
-                        cc = cc_prev; // ccol is not written on the last level
-                        dc = (d - dc_prev * a) * divided;
-                        up_last = v.up;
-                    }
+                    va_forward_level<T>(k, nk, dtr, v.us, v.un, v.w0, v.w1, v.up, v.ut, st, cc, dc);
                     if (k < nk - 1)
                         sc_store(k, cc, dc, v.up);
-                    cc_prev = cc;
-                    dc_prev = dc;
-                    u_km1 = u_k;
-                    u_k = v.un;
                 }
             }
 #pragma unroll
@@ -214,8 +228,8 @@ namespace {
 
         // ------------------------------------------------------------------ backward sweep (u_backward_function)
         // last_level :118-121
-        T data = dc_prev;
-        us_p[(int64_t)(nk - 1) * us_sk] = dtr * (data - up_last);
+        T data = st.dc_prev;
+        us_p[(int64_t)(nk - 1) * us_sk] = dtr * (data - st.up_last);
         struct back_level {
             T cc, dc, up;
         };
@@ -259,6 +273,159 @@ namespace {
                 va_columns<T, UNROLL, SMEM, Hints, SAVE_UPOS>(p, item, smem_raw);
         } else {
             va_columns<T, UNROLL, SMEM, Hints, SAVE_UPOS>(p, blockIdx.x, smem_raw);
+        }
+    }
+
+    // ------------------------------------------------------------------ TMA-streamed variant (va.variant = 2)
+    // One warp = one strip of 32 columns, persistent over the strips.  The warp is its own producer: lane 0 keeps a
+    // private ring of S stages in shared memory filled by TMA, each stage holding KC levels of the five fields for
+    // the strip ({32,1,KC} boxes; wcon one 16-byte chunk wider for the i+1 neighbour; u_stage and wcon shifted one
+    // level up because the functor reads them at k+1).  Nothing but the warp itself touches the ring, so there is no
+    // block barrier anywhere; (S-1)*KC levels of HBM traffic stay in flight per warp without using registers, which
+    // is what a sequential sweep needs to be bandwidth- instead of latency-bound.  ccol/dcol/u_pos go to a per-warp
+    // slab [k][3][32] that is re-used for every strip of the warp: with 7 warps per SM the slabs total ~64 MB and
+    // stay in L2 (evict_last), so the flush/fill traffic of the reference's k_caches never reaches HBM.
+    template <class T>
+    struct va_tma_layout {
+        static constexpr int es = (int)sizeof(T);
+        static constexpr int ww = 32 + 16 / es; // wcon box width (needs i0 .. i0+32)
+        template <int KC>
+        static constexpr int stage_bytes() {
+            return (KC * (4 * 32 + ww) * es + 127) / 128 * 128;
+        }
+    };
+
+    struct va_maps {
+        CUtensorMap us, up, ut, un, wc;
+    };
+
+    template <class T, int KC, int S, int WARPS>
+    __global__ void __launch_bounds__(WARPS * 32) va_tma_kernel(const __grid_constant__ va_maps maps,
+        const va_params<T> p) {
+        using L = va_tma_layout<T>;
+        constexpr int stage_bytes = L::template stage_bytes<KC>();
+        constexpr int NS = 3;
+        extern __shared__ __align__(128) unsigned char smem_all[];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        unsigned char *ring = smem_all + warp * (S * stage_bytes);
+        uint64_t *full = reinterpret_cast<uint64_t *>(smem_all + WARPS * S * stage_bytes) + warp * S;
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+                ptx::mbar_init(&full[s], 1);
+            ptx::fence_barrier_init();
+            if (threadIdx.x == 0) {
+                ptx::prefetch_tensormap(&maps.us);
+                ptx::prefetch_tensormap(&maps.up);
+                ptx::prefetch_tensormap(&maps.ut);
+                ptx::prefetch_tensormap(&maps.un);
+                ptx::prefetch_tensormap(&maps.wc);
+            }
+        }
+        __syncwarp();
+        const int nk = p.nk;
+        const T dtr = p.dtr;
+        const uint64_t pol_keep = ptx::policy_evict_last();
+        const int gw = blockIdx.x * WARPS + warp, total = gridDim.x * WARPS;
+        T *slab = p.scratch + (int64_t)gw * 32 + lane; // [k][NS][slots]
+        const int64_t sstride = p.slots;
+        const int nchunks = (nk + KC - 1) / KC;
+        uint32_t n_issued = 0, n_waited = 0; // ring uses so far (stage = n % S, parity = (n / S) & 1)
+
+        for (int item = gw; item < p.items; item += total) {
+            const int ti = item % p.tiles_i, j = item / p.tiles_i;
+            const int i0 = ti * 32, i = i0 + lane;
+            const bool active = i < p.ni;
+            auto issue = [&](int c) { // lane 0 only
+                const int s = n_issued % S;
+                unsigned char *dst = ring + s * stage_bytes;
+                const int k0 = c * KC;
+                ptx::mbar_expect_tx(&full[s], KC * (4 * 32 + L::ww) * L::es);
+                ptx::tma_load_3d(dst, &maps.us, &full[s], i0, j, k0);
+                ptx::tma_load_3d(dst + 1 * KC * 32 * L::es, &maps.up, &full[s], i0, j, k0);
+                ptx::tma_load_3d(dst + 2 * KC * 32 * L::es, &maps.ut, &full[s], i0, j, k0);
+                ptx::tma_load_3d(dst + 3 * KC * 32 * L::es, &maps.un, &full[s], i0, j, k0 + 1);
+                ptx::tma_load_3d(dst + 4 * KC * 32 * L::es, &maps.wc, &full[s], i0, j, k0 + 1);
+            };
+            // prologue: S-1 chunks in flight
+            for (int c = 0; c < S - 1 && c < nchunks; ++c) {
+                if (lane == 0)
+                    issue(c);
+                ++n_issued;
+            }
+            va_state<T> st;
+            st.u_k = active ? __ldg(p.u_stage.ptr + i + (int64_t)j * p.u_stage.sj) : T(0);
+            st.u_km1 = st.wsum_k = st.cc_prev = st.dc_prev = st.up_last = T(0);
+            for (int c = 0; c < nchunks; ++c) {
+                if (c + S - 1 < nchunks) { // refill the stage consumed in the previous iteration
+                    if (lane == 0)
+                        issue(c + S - 1);
+                    ++n_issued;
+                }
+                const int s = n_waited % S;
+                ptx::mbar_wait(&full[s], (n_waited / S) & 1);
+                ++n_waited;
+                const T *sd = reinterpret_cast<const T *>(ring + s * stage_bytes);
+                const T *wc = sd + 4 * KC * 32;
+#pragma unroll
+                for (int u = 0; u < KC; ++u) {
+                    const int k = c * KC + u;
+                    if (k < nk) {
+                        T us = sd[u * 32 + lane], up = sd[(KC + u) * 32 + lane], ut = sd[(2 * KC + u) * 32 + lane];
+                        T un = sd[(3 * KC + u) * 32 + lane];
+                        T w0 = wc[u * L::ww + lane], w1 = wc[u * L::ww + lane + 1];
+                        T cc, dc;
+                        va_forward_level<T>(k, nk, dtr, us, un, w0, w1, up, ut, st, cc, dc);
+                        if (k < nk - 1) {
+                            T *q = slab + (int64_t)k * NS * sstride;
+                            ptx::st_hint(q, cc, pol_keep);
+                            ptx::st_hint(q + sstride, dc, pol_keep);
+                            ptx::st_hint(q + 2 * sstride, up, pol_keep);
+                        }
+                    }
+                }
+                __syncwarp(); // all lanes are done with stage s before lane 0 refills it
+            }
+            // ---------------------------------------------------------------- backward sweep (u_backward_function)
+            T *us_p = p.utens_stage.ptr + i + (int64_t)j * p.utens_stage.sj;
+            const int64_t us_sk = p.utens_stage.sk;
+            T data = st.dc_prev;
+            if (active)
+                us_p[(int64_t)(nk - 1) * us_sk] = dtr * (data - st.up_last);
+            constexpr int BU = 8;
+            struct back_level {
+                T cc, dc, up;
+            };
+            auto load_back = [&](int k, back_level &v) {
+                if (k >= 0) {
+                    const T *q = slab + (int64_t)k * NS * sstride;
+                    v.cc = ptx::ld_hint(q, pol_keep);
+                    v.dc = ptx::ld_hint(q + sstride, pol_keep);
+                    v.up = ptx::ld_hint(q + 2 * sstride, pol_keep);
+                }
+            };
+            back_level bcur[BU];
+#pragma unroll
+            for (int u = 0; u < BU; ++u)
+                load_back(nk - 2 - u, bcur[u]);
+            for (int k0 = nk - 2; k0 >= 0; k0 -= BU) {
+                back_level bnxt[BU];
+#pragma unroll
+                for (int u = 0; u < BU; ++u)
+                    load_back(k0 - BU - u, bnxt[u]);
+#pragma unroll
+                for (int u = 0; u < BU; ++u) {
+                    const int k = k0 - u;
+                    if (k >= 0) { // body :111-116
+                        data = bcur[u].dc - bcur[u].cc * data;
+                        if (active)
+                            us_p[(int64_t)k * us_sk] = dtr * (data - bcur[u].up);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < BU; ++u)
+                    bcur[u] = bnxt[u];
+            }
         }
     }
 
@@ -408,6 +575,68 @@ namespace {
                          : dispatch_unroll<T, SMEM, false, false>(p, unroll, threads, smem, grid, stream);
     }
 
+    template <class T, int KC, int S, int WARPS>
+    int launch_va_tma(const va_maps &maps, const va_params<T> &p, int grid, cudaStream_t stream) {
+        using L = va_tma_layout<T>;
+        auto kernel = va_tma_kernel<T, KC, S, WARPS>;
+        const int smem = WARPS * (S * L::template stage_bytes<KC>() + S * 8);
+        static thread_local int done_dev = -1;
+        if (done_dev != dev()->device) {
+            GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            done_dev = dev()->device;
+        }
+        kernel<<<grid, WARPS * 32, smem, stream>>>(maps, p);
+        count_launch();
+        return check_launch("va_tma_kernel");
+    }
+
+    // Builds the five tensor maps; false if any field is not TMA-addressable.
+    template <class T>
+    bool make_va_maps(va_maps &m, const va_params<T> &p) {
+        using L = va_tma_layout<T>;
+        const int ni = p.ni, nj = p.nj, nk = p.nk;
+        auto one = [&](CUtensorMap *map, const T *ptr, int64_t sj, int64_t sk, int len_i, int box_i, int kc) {
+            return make_map<T>(map, ptr, sj, sk, 0, 0, len_i, nj, nk, box_i, 1, kc);
+        };
+        const int kc = p.kc;
+        return one(&m.us, p.utens_stage.ptr, p.utens_stage.sj, p.utens_stage.sk, ni, 32, kc) &&
+               one(&m.up, p.u_pos.ptr, p.u_pos.sj, p.u_pos.sk, ni, 32, kc) &&
+               one(&m.ut, p.utens.ptr, p.utens.sj, p.utens.sk, ni, 32, kc) &&
+               one(&m.un, p.u_stage.ptr, p.u_stage.sj, p.u_stage.sk, ni, 32, kc) &&
+               one(&m.wc, p.wcon.ptr, p.wcon.sj, p.wcon.sk, ni + 1, L::ww, kc);
+    }
+
+    template <class T>
+    int vert_adv_tma(va_params<T> &p, const options &o, device_state *d, cudaStream_t stream, bool *done) {
+        *done = false;
+        const int kc = o.va_unroll == 8 ? 8 : (o.va_unroll == 2 ? 2 : 4);
+        p.kc = kc;
+        va_maps maps;
+        if (!make_va_maps<T>(maps, p))
+            return GTB_OK; // not addressable: the caller falls back to the register-prefetch kernel
+        const int wps = o.va_ctas_per_sm > 0 ? o.va_ctas_per_sm : 7; // warps per SM
+        const int64_t strips = (int64_t)p.tiles_i * p.nj;
+        p.items = (int)strips;
+        int grid = o.va_ctas_per_sm < 0 ? -o.va_ctas_per_sm : wps * d->sm_count;
+        if (grid > strips)
+            grid = (int)strips;
+        p.slots = (int64_t)grid * 32;
+        p.scratch = static_cast<T *>(scratch((size_t)3 * p.nk * p.slots * sizeof(T)));
+        if (!p.scratch)
+            return GTB_ERR_ALLOC;
+        p.persistent = 1;
+        *done = true;
+        switch (kc) {
+        case 2:
+            return launch_va_tma<T, 2, 6, 1>(maps, p, grid, stream);
+        case 8:
+            return launch_va_tma<T, 8, 3, 1>(maps, p, grid, stream);
+        default:
+            return launch_va_tma<T, 4, 4, 1>(maps, p, grid, stream);
+        }
+    }
+
     template <class T>
     col_field<T> make_col(const gtb_field *f) {
         return {static_cast<T *>(f->ptr), f->stride_j, f->stride_k};
@@ -436,7 +665,7 @@ namespace {
         int threads = o.va_threads ? o.va_threads : 64;
         if (threads % 32 != 0 || threads < 32 || threads > 1024)
             return fail(GTB_ERR_ARG, "gtb_vert_adv: va.threads must be a multiple of 32 in 32..1024");
-        int unroll = o.va_unroll ? o.va_unroll : 4;
+        int unroll = o.va_unroll ? o.va_unroll : 8;
         va_params<T> p;
         p.utens_stage = make_col<T>(utens_stage);
         p.u_stage = make_col<const T>(u_stage);
@@ -446,12 +675,24 @@ namespace {
         p.dtr = dtr_stage;
         p.ni = ni, p.nj = nj, p.nk = nk;
         p.tiles_i = ceil_div(ni, 32);
+        if ((int64_t)p.tiles_i * nj >= (int64_t)1 << 31)
+            return fail(GTB_ERR_ARG, "gtb_vert_adv: domain too large");
+        if (o.va_variant != 1) { // 0 auto / 2: TMA-streamed persistent warps
+            bool done = false;
+            int st = vert_adv_tma<T>(p, o, d, as_stream(stream), &done);
+            if (st || done)
+                return st;
+            if (o.va_variant == 2)
+                return fail(GTB_ERR_LAYOUT,
+                    "gtb_vert_adv: va.variant=2 (TMA) needs 16-byte aligned origins and stride_j/stride_k that are "
+                    "multiples of 16 bytes");
+        }
         const int64_t items = (int64_t)p.tiles_i * ceil_div(nj, threads / 32);
         if (items >= (int64_t)1 << 31)
             return fail(GTB_ERR_ARG, "gtb_vert_adv: domain too large");
         p.items = (int)items;
         p.scratch = nullptr;
-        const bool save_upos = o.va_save_upos != 0;
+        const bool save_upos = o.va_save_upos != 2; // 0 auto (on), 1 on, 2 off
         const int ns = save_upos ? 3 : 2;
         int grid = p.items;
         p.persistent = 0;

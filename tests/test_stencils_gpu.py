@@ -175,11 +175,12 @@ def test_hori_diff_linearity(gt):
 
 
 # ------------------------------------------------------------------------------------- vertical advection
-VA_CONFIGS = [dict(), dict(threads=32, unroll=1), dict(threads=128, unroll=2), dict(threads=64, unroll=8),
-              dict(scratch=2, threads=32, unroll=4), dict(scratch=2, threads=64, unroll=2, hints=0),
-              dict(hints=0, unroll=4), dict(ctas_per_sm=-3, threads=32, unroll=2),
-              dict(ctas_per_sm=-2, threads=32, save_upos=1), dict(scratch=2, threads=32, save_upos=1, ctas_per_sm=-1),
-              dict(save_upos=1, hints=0, unroll=8)]
+VA_CONFIGS = [dict(), dict(variant=2, unroll=8), dict(variant=2, unroll=2, ctas_per_sm=-2), dict(variant=2, ctas_per_sm=-1),
+              dict(variant=1), dict(variant=1, threads=32, unroll=1), dict(variant=1, threads=128, unroll=2),
+              dict(variant=1, threads=64, unroll=8, save_upos=2), dict(variant=1, scratch=2, threads=32, unroll=4),
+              dict(variant=1, scratch=2, threads=64, unroll=2, hints=0, save_upos=2), dict(variant=1, hints=0, unroll=4),
+              dict(variant=1, ctas_per_sm=-3, threads=32, unroll=2), dict(variant=1, ctas_per_sm=-2, threads=32),
+              dict(variant=1, scratch=2, threads=32, ctas_per_sm=-1), dict(variant=1, hints=0, unroll=8)]
 
 
 def set_va(gt, cfg):
@@ -217,7 +218,10 @@ def test_vert_adv_random_bit_exact(gt, oracle, size, alignment):
     shape = (nk, nj + 6, ni + 6)
     arrs = [rng.uniform(5, 9, shape), rng.uniform(5, 9, shape), rng.uniform(-3e-4, 3e-4, shape),
             rng.uniform(5, 9, shape), rng.uniform(-1e-5, 1e-5, shape)]
-    for cfg in (dict(), dict(scratch=2, threads=32), dict(ctas_per_sm=-2, threads=32, save_upos=1)):
+    for cfg in (dict(), dict(variant=2, ctas_per_sm=-2), dict(variant=1), dict(variant=1, scratch=2, threads=32),
+                dict(variant=1, ctas_per_sm=-2, threads=32)):
+        for k in ("variant", "threads", "unroll", "scratch", "ctas_per_sm", "save_upos"):
+            gt.lib.set_option("va." + k, 0)
         set_va(gt, cfg)
         out, _ = run_va(gt, arrs, 0.15, alignment)
         inner = (slice(None), slice(3, -3), slice(3, -3))

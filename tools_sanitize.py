@@ -19,8 +19,9 @@ for dtype in (np.float64, np.float32):
         stencil.horizontal_diffusion(*st)
         torch.cuda.synchronize()
         print("hd", dtype.__name__, variant, "ok", flush=True)
-    for cfg in (dict(), dict(scratch=2, threads=32), dict(ctas_per_sm=-2, threads=32, save_upos=1)):
-        for k in ("scratch", "threads", "ctas_per_sm", "save_upos"):
+    for cfg in (dict(), dict(variant=2, ctas_per_sm=-2, unroll=2), dict(variant=1, scratch=2, threads=32),
+                dict(variant=1, ctas_per_sm=-2, threads=32)):
+        for k in ("variant", "scratch", "threads", "ctas_per_sm", "save_upos", "unroll"):
             _lib.set_option("va." + k, cfg.get(k, 0))
         arrs = [rng.uniform(5, 9, (12, 11, 41)).astype(dtype) for _ in range(5)]
         st = [storage.from_numpy(a, (3, 3, 0)) for a in arrs]

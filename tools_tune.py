@@ -80,32 +80,26 @@ def main():
             for f in st:
                 f.const_target_tensor()
         combos = []
+        for kc, wps in itertools.product((2, 4, 8), (4, 5, 6, 7, 8, 10, 12, 14)):
+            combos.append((2, 1, 32, kc, 1, wps, 1))
         for scratch, threads, unroll, hints, ctas, save in itertools.product(
-                (1, 2), (32, 64, 128, 256), (2, 4, 8), (0, 1), (0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14), (0, 1)):
-            isz = np.dtype(dtype).itemsize
-            warps = ctas * threads // 32
-            if ctas and warps not in (4, 5, 6, 7, 8, 10, 12, 14):
+                (1,), (32, 64, 128), (4, 8), (1,), (0, 7), (1, 2)):
+            if dtype == np.float32 and threads != 64:
                 continue
-            if scratch == 2 and (2 + save) * NK * threads * isz * max(ctas, 1) > 227 * 1024:
-                continue
-            if scratch == 2 and ctas == 0 and threads > 64:
-                continue
-            if dtype == np.float32 and (hints == 0 or threads > 64 or unroll == 2):
-                continue
-            combos.append((scratch, threads, unroll, hints, ctas, save))
+            combos.append((1, scratch, threads, unroll, hints, ctas, save))
         results = []
-        for scratch, threads, unroll, hints, ctas, save in combos:
-            for k, v in (("va.scratch", scratch), ("va.threads", threads), ("va.unroll", unroll), ("va.hints", hints),
+        for variant, scratch, threads, unroll, hints, ctas, save in combos:
+            for k, v in (("va.variant", variant), ("va.scratch", scratch), ("va.threads", threads), ("va.unroll", unroll), ("va.hints", hints),
                          ("va.ctas_per_sm", ctas), ("va.save_upos", save)):
                 _lib.set_option(k, v)
             try:
                 med, mn = timeit(lambda st: stencil.vertical_advection_dycore(*st, 0.15), sets, n=20)
             except Exception as e:
-                print("va", dtype.__name__, scratch, threads, unroll, hints, ctas, save, "FAILED", e)
+                print("va", dtype.__name__, variant, scratch, threads, unroll, hints, ctas, save, "FAILED", e)
                 continue
             b = 6 * np.dtype(dtype).itemsize * NI * NJ * NK
-            results.append((med, "va %s scratch=%d threads=%d unroll=%d hints=%d ctas=%d save_upos=%d: median %.2f us "
-                            "min %.2f us -> %.0f GB/s" % (dtype.__name__, scratch, threads, unroll, hints, ctas, save,
+            results.append((med, "va %s variant=%d scratch=%d threads=%d unroll=%d hints=%d ctas=%d save_upos=%d: median %.2f us "
+                            "min %.2f us -> %.0f GB/s" % (dtype.__name__, variant, scratch, threads, unroll, hints, ctas, save,
                                                            med * 1e3, mn * 1e3, b / med / 1e6)))
         for _, line in sorted(results):
             print(line)
