@@ -223,7 +223,12 @@ def test_vert_adv_random_bit_exact(gt, oracle, size, alignment):
         for k in ("variant", "threads", "unroll", "scratch", "ctas_per_sm", "save_upos"):
             gt.lib.set_option("va." + k, 0)
         set_va(gt, cfg)
-        out, _ = run_va(gt, arrs, 0.15, alignment)
+        try:
+            out, _ = run_va(gt, arrs, 0.15, alignment)
+        except gt.lib.GtbError as e:
+            # an explicitly requested TMA variant refuses layouts TMA cannot address (auto falls back)
+            assert cfg.get("variant") == 2 and alignment == 1 and e.status == gt.lib.GTB_ERR_LAYOUT
+            continue
         inner = (slice(None), slice(3, -3), slice(3, -3))
         assert np.array_equal(out[inner], oracle.vert_adv(*arrs, 0.15)[inner])
 

@@ -29,7 +29,7 @@ fi
 if [ "$STEP" = all ] || [ "$STEP" = ncu ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 5 --warmup 3 --no-extras > gpurun_out/ncu_launches.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:va_kernel -s 3 -c 2 -f -o gpurun_out/prof_va \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:va_ -s 3 -c 2 -f -o gpurun_out/prof_va \
       python bench.py --steps 5 --warmup 3 --no-extras > gpurun_out/ncu_va.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:hd_ -s 3 -c 2 -f -o gpurun_out/prof_hd \
       python bench.py --stencil hori_diff --steps 5 --warmup 3 --no-extras > gpurun_out/ncu_hd.log 2>&1
