@@ -40,7 +40,10 @@ namespace gtb {
         int va_hints = 1;     // L2 eviction-priority hints on/off
         int va_ctas_per_sm = 0; // > 0: persistent grid of that many CTAs per SM with per-thread scratch slots
         int va_save_upos = 0; // u_pos(k) kept next to ccol/dcol instead of re-read in the backward sweep: 0 auto, 1 on, 2 off
+        int va_debug = 0;     // diagnosis only, see va_params::debug
+        int va_stages = 0;    // TMA ring depth (0 auto)
         int copy_vec = 1;     // vectorised copy on/off
+        int l2_persist_mb = -1; // L2 set-aside for the k-cache slabs in MB: -1 auto (slab size), 0 off
     };
     options &opts();
 
@@ -51,6 +54,8 @@ namespace gtb {
         int64_t l2_bytes = 0;
         int64_t hbm_bytes = 0;
         int max_smem_optin = 0;
+        int64_t persisting_l2_max = 0;
+        int64_t persisting_l2_set = -1;
     };
     // Lazily initialised state of the current device; nullptr + error set if there is no usable device.
     device_state *dev();
@@ -59,6 +64,7 @@ namespace gtb {
     // calls on different streams that both need scratch must not overlap (same rule as the reference's
     // thread-local cached allocator).
     void *scratch(size_t bytes);
+    int set_l2_persist(int64_t bytes);
 
     extern std::atomic<int64_t> g_launches;
     inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }

@@ -165,6 +165,8 @@ namespace {
     __global__ void wait_kernel(const __grid_constant__ wait_args a) {
         const int n = threadIdx.x;
         if (n < 27 && a.flag[n]) {
+            if (*reinterpret_cast<volatile int *>(a.error))
+                return; // an earlier wait already timed out: do not stall every following exchange as well
             const long long t0 = clock64();
             for (;;) {
                 uint64_t v;
@@ -522,7 +524,7 @@ GTB_API int gtb_halo_wait(gtb_halo *h, void *stream) {
         return GTB_OK;
     w.epoch = h->epoch;
     w.error = h->d_error;
-    w.timeout_cycles = 20000000000ll; // ~10 s at 2 GHz: a lost neighbour must not hang the GPU
+    w.timeout_cycles = 6000000000ll; // ~3 s at 2 GHz: a lost neighbour must not hang the GPU
     wait_kernel<<<1, 32, 0, as_stream(stream)>>>(w);
     count_launch();
     return check_launch("halo wait");

@@ -69,6 +69,7 @@ namespace gtb {
         s.l2_bytes = p.l2CacheSize;
         s.hbm_bytes = (int64_t)p.totalGlobalMem;
         s.max_smem_optin = (int)p.sharedMemPerBlockOptin;
+        s.persisting_l2_max = (int64_t)p.persistingL2CacheMaxSize;
         s.device = d;
         return &s;
     }
@@ -169,6 +170,9 @@ namespace {
             {"va.hints", &o.va_hints},
             {"va.ctas_per_sm", &o.va_ctas_per_sm},
             {"va.save_upos", &o.va_save_upos},
+            {"l2.persist_mb", &o.l2_persist_mb},
+            {"va.debug", &o.va_debug},
+            {"va.stages", &o.va_stages},
             {"copy.vec", &o.copy_vec}};
         for (auto &t : table)
             if (strcmp(t.name, key) == 0)
@@ -192,6 +196,24 @@ GTB_API int gtb_get_option(const char *key, int *value) {
     *value = *p;
     return GTB_OK;
 }
+
+namespace gtb {
+    // L2 set-aside for persisting (evict_last) accesses: the k-cache slabs of the vertical sweeps live there.
+    int set_l2_persist(int64_t bytes) {
+        device_state *s = dev();
+        if (!s)
+            return GTB_ERR_CUDA;
+        if (bytes > s->persisting_l2_max)
+            bytes = s->persisting_l2_max;
+        if (bytes < 0)
+            bytes = 0;
+        if (s->persisting_l2_set == bytes)
+            return GTB_OK;
+        GTB_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)bytes));
+        s->persisting_l2_set = bytes;
+        return GTB_OK;
+    }
+} // namespace gtb
 
 GTB_API int gtb_release_scratch(void) {
     device_state *s = dev();

@@ -46,6 +46,7 @@ namespace {
         int64_t slots;  // columns (one slot per column) or resident threads (persistent grid: one slot per thread)
         int persistent; // slots are per thread and CTAs loop over the items
         int kc;         // levels per TMA stage (TMA variant)
+        int debug;      // diagnosis only (va.debug): 1 skip backward sweep, 2 skip forward math, 4 skip scratch stores
     };
 
     template <class T, bool Hints>
@@ -299,12 +300,11 @@ namespace {
         CUtensorMap us, up, ut, un, wc;
     };
 
-    template <class T, int KC, int S, int WARPS>
+    template <class T, int KC, int S, int WARPS, int NS>
     __global__ void __launch_bounds__(WARPS * 32) va_tma_kernel(const __grid_constant__ va_maps maps,
         const va_params<T> p) {
         using L = va_tma_layout<T>;
         constexpr int stage_bytes = L::template stage_bytes<KC>();
-        constexpr int NS = 3;
         extern __shared__ __align__(128) unsigned char smem_all[];
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         unsigned char *ring = smem_all + warp * (S * stage_bytes);
@@ -375,12 +375,19 @@ namespace {
                         T un = sd[(3 * KC + u) * 32 + lane];
                         T w0 = wc[u * L::ww + lane], w1 = wc[u * L::ww + lane + 1];
                         T cc, dc;
-                        va_forward_level<T>(k, nk, dtr, us, un, w0, w1, up, ut, st, cc, dc);
-                        if (k < nk - 1) {
+                        if (p.debug & 2) {
+                            cc = us + un + w0 + w1;
+                            dc = up + ut;
+                            st.dc_prev = dc;
+                        } else {
+                            va_forward_level<T>(k, nk, dtr, us, un, w0, w1, up, ut, st, cc, dc);
+                        }
+                        if (k < nk - 1 && !(p.debug & 4)) {
                             T *q = slab + (int64_t)k * NS * sstride;
                             ptx::st_hint(q, cc, pol_keep);
                             ptx::st_hint(q + sstride, dc, pol_keep);
-                            ptx::st_hint(q + 2 * sstride, up, pol_keep);
+                            if constexpr (NS == 3)
+                                ptx::st_hint(q + 2 * sstride, up, pol_keep);
                         }
                     }
                 }
@@ -388,7 +395,8 @@ namespace {
             }
             // ---------------------------------------------------------------- backward sweep (u_backward_function)
             T *us_p = p.utens_stage.ptr + i + (int64_t)j * p.utens_stage.sj;
-            const int64_t us_sk = p.utens_stage.sk;
+            const T *up_p = p.u_pos.ptr + (active ? i : 0) + (int64_t)j * p.u_pos.sj;
+            const int64_t us_sk = p.utens_stage.sk, up_sk = p.u_pos.sk;
             T data = st.dc_prev;
             if (active)
                 us_p[(int64_t)(nk - 1) * us_sk] = dtr * (data - st.up_last);
@@ -401,10 +409,15 @@ namespace {
                     const T *q = slab + (int64_t)k * NS * sstride;
                     v.cc = ptx::ld_hint(q, pol_keep);
                     v.dc = ptx::ld_hint(q + sstride, pol_keep);
-                    v.up = ptx::ld_hint(q + 2 * sstride, pol_keep);
+                    if constexpr (NS == 3)
+                        v.up = ptx::ld_hint(q + 2 * sstride, pol_keep);
+                    else
+                        v.up = __ldg(up_p + k * up_sk);
                 }
             };
             back_level bcur[BU];
+            if (p.debug & 1)
+                continue;
 #pragma unroll
             for (int u = 0; u < BU; ++u)
                 load_back(nk - 2 - u, bcur[u]);
@@ -575,10 +588,10 @@ namespace {
                          : dispatch_unroll<T, SMEM, false, false>(p, unroll, threads, smem, grid, stream);
     }
 
-    template <class T, int KC, int S, int WARPS>
+    template <class T, int KC, int S, int WARPS, int NS>
     int launch_va_tma(const va_maps &maps, const va_params<T> &p, int grid, cudaStream_t stream) {
         using L = va_tma_layout<T>;
-        auto kernel = va_tma_kernel<T, KC, S, WARPS>;
+        auto kernel = va_tma_kernel<T, KC, S, WARPS, NS>;
         const int smem = WARPS * (S * L::template stage_bytes<KC>() + S * 8);
         static thread_local int done_dev = -1;
         if (done_dev != dev()->device) {
@@ -612,6 +625,7 @@ namespace {
         *done = false;
         const int kc = o.va_unroll == 8 ? 8 : (o.va_unroll == 2 ? 2 : 4);
         p.kc = kc;
+        p.debug = o.va_debug;
         va_maps maps;
         if (!make_va_maps<T>(maps, p))
             return GTB_OK; // not addressable: the caller falls back to the register-prefetch kernel
@@ -622,18 +636,36 @@ namespace {
         if (grid > strips)
             grid = (int)strips;
         p.slots = (int64_t)grid * 32;
-        p.scratch = static_cast<T *>(scratch((size_t)3 * p.nk * p.slots * sizeof(T)));
+        const bool save_upos = o.va_save_upos != 2;
+        p.scratch = static_cast<T *>(scratch((size_t)(save_upos ? 3 : 2) * p.nk * p.slots * sizeof(T)));
         if (!p.scratch)
             return GTB_ERR_ALLOC;
         p.persistent = 1;
         *done = true;
+        {
+            const int64_t slab = (int64_t)(save_upos ? 3 : 2) * p.nk * p.slots * (int64_t)sizeof(T);
+            int st = set_l2_persist(o.l2_persist_mb < 0 ? slab : (int64_t)o.l2_persist_mb << 20);
+            if (st)
+                return st;
+        }
+        if (save_upos) {
+            switch (kc) {
+            case 2:
+                return launch_va_tma<T, 2, 6, 1, 3>(maps, p, grid, stream);
+            case 8:
+                return launch_va_tma<T, 8, 3, 1, 3>(maps, p, grid, stream);
+            default:
+                return o.va_stages == 6 ? launch_va_tma<T, 4, 6, 1, 3>(maps, p, grid, stream)
+                                        : launch_va_tma<T, 4, 4, 1, 3>(maps, p, grid, stream);
+            }
+        }
         switch (kc) {
         case 2:
-            return launch_va_tma<T, 2, 6, 1>(maps, p, grid, stream);
+            return launch_va_tma<T, 2, 6, 1, 2>(maps, p, grid, stream);
         case 8:
-            return launch_va_tma<T, 8, 3, 1>(maps, p, grid, stream);
+            return launch_va_tma<T, 8, 3, 1, 2>(maps, p, grid, stream);
         default:
-            return launch_va_tma<T, 4, 4, 1>(maps, p, grid, stream);
+            return launch_va_tma<T, 4, 4, 1, 2>(maps, p, grid, stream);
         }
     }
 

@@ -34,6 +34,7 @@ def timeit(run, sets, n=60):
 
 
 def main():
+    only = sys.argv[1] if len(sys.argv) > 1 else "all"
     torch.cuda.set_device(0)
     _lib.check(_lib.lib().gtb_init(0))
     print("device", _lib.device_info())
@@ -46,7 +47,7 @@ def main():
     med, mn = timeit(lambda st: stencil.copy(*st), cs)
     print("copy 256x256x80 f64: median %.2f us min %.2f us -> %.0f GB/s" % (med * 1e3, mn * 1e3, 16 * NI * NJ * NK / med / 1e6))
     # ---- hori_diff
-    for dtype, n in ((np.float64, 256), (np.float32, 256), (np.float64, 512)):
+    for dtype, n in ((np.float64, 256), (np.float32, 256), (np.float64, 512)) if only in ("all", "hd") else ():
         sets = []
         for _ in range(3):
             inp, coeff = bench.repo_hori_diff(n, n, NK)
@@ -71,7 +72,7 @@ def main():
                 dtype.__name__, n, variant, stages, ctas, med * 1e3, mn * 1e3, b / med / 1e6))
         del sets
     # ---- vert_adv
-    for dtype in (np.float64, np.float32):
+    for dtype in (np.float64, np.float32) if only in ("all", "va") else ():
         sets = []
         for _ in range(2):
             arrs, dtr = bench.repo_vert_adv(NI, NJ, NK)
@@ -80,27 +81,24 @@ def main():
             for f in st:
                 f.const_target_tensor()
         combos = []
-        for kc, wps in itertools.product((2, 4, 8), (4, 5, 6, 7, 8, 10, 12, 14)):
-            combos.append((2, 1, 32, kc, 1, wps, 1))
-        for scratch, threads, unroll, hints, ctas, save in itertools.product(
-                (1,), (32, 64, 128), (4, 8), (1,), (0, 7), (1, 2)):
-            if dtype == np.float32 and threads != 64:
-                continue
-            combos.append((1, scratch, threads, unroll, hints, ctas, save))
+        for kc, wps, save, persist in itertools.product((4, 8), (5, 6, 7, 8, 10, 14), (1, 2), (-1, 0)):
+            combos.append(dict(variant=2, unroll=kc, ctas_per_sm=wps, save_upos=save, persist=persist))
+        for threads, unroll, ctas, save in itertools.product((64,), (8,), (0, 7), (1, 2)):
+            combos.append(dict(variant=1, scratch=1, threads=threads, unroll=unroll, ctas_per_sm=ctas, save_upos=save,
+                               persist=-1))
         results = []
-        for variant, scratch, threads, unroll, hints, ctas, save in combos:
-            for k, v in (("va.variant", variant), ("va.scratch", scratch), ("va.threads", threads), ("va.unroll", unroll), ("va.hints", hints),
-                         ("va.ctas_per_sm", ctas), ("va.save_upos", save)):
-                _lib.set_option(k, v)
+        for cfg in combos:
+            for k in ("variant", "scratch", "threads", "unroll", "ctas_per_sm", "save_upos"):
+                _lib.set_option("va." + k, cfg.get(k, 0))
+            _lib.set_option("l2.persist_mb", cfg["persist"])
             try:
                 med, mn = timeit(lambda st: stencil.vertical_advection_dycore(*st, 0.15), sets, n=20)
             except Exception as e:
-                print("va", dtype.__name__, variant, scratch, threads, unroll, hints, ctas, save, "FAILED", e)
+                print("va", dtype.__name__, cfg, "FAILED", e)
                 continue
             b = 6 * np.dtype(dtype).itemsize * NI * NJ * NK
-            results.append((med, "va %s variant=%d scratch=%d threads=%d unroll=%d hints=%d ctas=%d save_upos=%d: median %.2f us "
-                            "min %.2f us -> %.0f GB/s" % (dtype.__name__, variant, scratch, threads, unroll, hints, ctas, save,
-                                                           med * 1e3, mn * 1e3, b / med / 1e6)))
+            results.append((med, "va %s %s: median %.2f us min %.2f us -> %.0f GB/s" % (
+                dtype.__name__, " ".join("%s=%d" % kv for kv in cfg.items()), med * 1e3, mn * 1e3, b / med / 1e6)))
         for _, line in sorted(results):
             print(line)
 
