@@ -1,0 +1,331 @@
+/*
+ * gtb200/stencil/b200.hpp -- the B200 backend tag for GridTools' `stencil::run` / `run_single_stage`.
+ *
+ *     #include <gridtools/stencil/cartesian.hpp>
+ *     #include <gtb200/stencil/b200.hpp>
+ *     gridtools::stencil::run(spec, gridtools::stencil::b200<>(), grid, fields...);
+ *
+ * A GridTools backend is a tag type plus one ADL-visible function template
+ * `gridtools_backend_entry_point(tag, be_spec, grid, data_stores)` (stencil/core/backend.hpp:48, stencil/README.md);
+ * this header provides exactly that and nothing above it: frontend, extent analysis, interval splitting and the
+ * be_api (stencil/be_api.hpp) are consumed unchanged.  It replaces stencil/gpu/entry_point.hpp:254-260.
+ *
+ * Two execution paths behind the tag:
+ *
+ *  1. NAMED KERNELS.  If the ordered list of user functors of the spec has been registered with
+ *     GTB200_REGISTER_SPEC(kernel, functors...), the whole spec (all stages, all multi-stages) is executed by ONE
+ *     hand-written sm_100a kernel of libgtb200.so through the C ABI of include/gtb200.h (TMA-staged fused
+ *     horizontal diffusion, TMA-streamed forward/backward vertical advection, ...).  The fields passed to `run`
+ *     must be in the order of the corresponding C-ABI function, which is the order the reference's own specs use
+ *     (horizontal_diffusion.cpp:98-106, vertical_advection_dycore.cpp:140-149, tridiagonal.cpp:83-97,
+ *     copy_stencil.cpp:42-47).  User functors are compile-time types a shared library cannot see, hence the one-line
+ *     registration next to the functor definitions.
+ *
+ *  2. GENERIC PATH (needs nvcc: the user functors are instantiated inside a __global__ template in the user's
+ *     translation unit).  Any other spec runs stage by stage: be_api::make_split_view, one launch per stage over
+ *     the extent-extended IJ domain, k levels in parallel for execute_parallel and swept by one thread per column
+ *     for execute_forward/backward, temporaries in device memory.  This is the semantics of the reference's `naive`
+ *     backend (stencil/naive.hpp:32-78) executed on the GPU; ij/k caches are honoured as what they are
+ *     semantically -- plain temporaries.
+ *
+ * Errors: a non-zero status of the C ABI becomes the std::runtime_error the reference throws from GT_CUDA_CHECK
+ * (common/cuda_util.hpp:20-35).  Launches go to the legacy default stream and do not synchronise, like the
+ * reference (stencil/gpu/launch_kernel.hpp:161, common/cuda_util.hpp:79-96); `b200<stream_getter>` may supply
+ * another stream.
+ */
+#pragma once
+
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <utility>
+
+#include <gridtools/common/hymap.hpp>
+#include <gridtools/common/integral_constant.hpp>
+#include <gridtools/common/tuple_util.hpp>
+#include <gridtools/meta.hpp>
+#include <gridtools/sid/allocator.hpp>
+#include <gridtools/sid/composite.hpp>
+#include <gridtools/sid/concept.hpp>
+#include <gridtools/sid/contiguous.hpp>
+#include <gridtools/sid/sid_shift_origin.hpp>
+#include <gridtools/stencil/be_api.hpp>
+#include <gridtools/stencil/common/dim.hpp>
+#include <gridtools/stencil/core/functor_metafunctions.hpp>
+#include <gridtools/stencil/frontend/cartesian/stage.hpp>
+
+#ifdef __CUDACC__
+#include <gridtools/common/cuda_util.hpp>
+#endif
+
+#include "../../gtb200.h"
+
+namespace gtb200 {
+
+    /// Kernels of libgtb200.so a whole spec can be bound to.
+    enum class kernel { none, copy, hori_diff, vert_adv, tridiagonal };
+
+    /// Primary template: a spec made of these user functors (in stage order, duplicates removed) has no named kernel.
+    template <class FunctorList>
+    struct named_spec : std::integral_constant<kernel, kernel::none> {};
+
+    struct default_stream {
+        void *operator()() const { return nullptr; } // legacy default stream, like the reference
+    };
+
+    inline void check(int status, const char *what) {
+        if (status != GTB_OK)
+            throw std::runtime_error(std::string(what) + ": " + gtb_last_error());
+    }
+} // namespace gtb200
+
+/// Binds a spec -- identified by its user functors in stage order -- to a named kernel.  Use at global scope, after
+/// the functor definitions:
+///     GTB200_REGISTER_SPEC(gtb200::kernel::hori_diff, lap_function, flx_function, fly_function, out_function)
+#define GTB200_REGISTER_SPEC(KERNEL, ...)                                                     \
+    template <>                                                                               \
+    struct gtb200::named_spec<::gridtools::meta::list<__VA_ARGS__>>                           \
+        : std::integral_constant<::gtb200::kernel, KERNEL> {}
+
+namespace gridtools {
+    namespace stencil {
+        namespace b200_backend {
+            namespace gt = ::gridtools;
+
+            // ---------------------------------------------------------------- which user functors make up the spec
+            template <class F>
+            struct strip_bound {
+                using type = F;
+            };
+            template <class F, class Param>
+            struct strip_bound<core::bound_functor<F, Param>> {
+                using type = F;
+            };
+            template <class Stage>
+            struct stage_functor;
+            template <class F, class PlhMap>
+            struct stage_functor<cartesian::stage_impl_::stage<F, PlhMap>> {
+                using type = typename strip_bound<F>::type;
+            };
+            template <class Stage>
+            using stage_functor_t = typename stage_functor<Stage>::type;
+            template <class Cell>
+            using cell_functors = meta::transform<stage_functor_t, typename Cell::funs_t>;
+
+            // Spec = list of multi-stage matrices; a matrix = list of stage rows; a row = list of cells (one per
+            // elementary k interval).
+            template <class Spec>
+            using spec_functors = meta::dedup<
+                meta::flatten<meta::transform<cell_functors, meta::flatten<meta::flatten<meta::rename<meta::list, Spec>>>>>>;
+
+            // ---------------------------------------------------------------- raw views of the data stores
+            template <class Sid>
+            gtb_field as_field(Sid &sid_) {
+                auto strides = sid::get_strides(sid_);
+                gtb_field f;
+                f.ptr = const_cast<void *>(static_cast<const void *>(sid::get_origin(sid_)()));
+                f.stride_i = sid::get_stride<dim::i>(strides);
+                f.stride_j = sid::get_stride<dim::j>(strides);
+                f.stride_k = sid::get_stride<dim::k>(strides);
+                return f;
+            }
+            template <class Sid>
+            using element_of = std::remove_cv_t<std::remove_pointer_t<decltype(sid::get_origin(std::declval<Sid &>())())>>;
+
+            using ::gtb200::kernel;
+            template <kernel K>
+            using kernel_c = std::integral_constant<kernel, K>;
+
+            // copy_stencil.cpp:42-47 : run_single_stage(copy_functor(), backend, grid, in, out)
+            template <class Grid, class DataStores>
+            void run_named(kernel_c<kernel::copy>, Grid const &grid, DataStores &ds, void *stream) {
+                static_assert(tuple_util::size<DataStores>::value == 2, "copy takes (in, out)");
+                auto in = as_field(tuple_util::get<0>(ds)), out = as_field(tuple_util::get<1>(ds));
+                using T = element_of<std::decay_t<decltype(tuple_util::get<1>(ds))>>;
+                gtb200::check(
+                    gtb_copy(&in, &out, grid.i_size(), grid.j_size(), grid.k_size(), (int)sizeof(T), stream), "gtb_copy");
+            }
+
+            // horizontal_diffusion.cpp:98-106 : run(spec, backend, grid, in, coeff, out)
+            template <class Grid, class DataStores>
+            void run_named(kernel_c<kernel::hori_diff>, Grid const &grid, DataStores &ds, void *stream) {
+                static_assert(tuple_util::size<DataStores>::value == 3, "hori_diff takes (in, coeff, out)");
+                auto in = as_field(tuple_util::get<0>(ds)), coeff = as_field(tuple_util::get<1>(ds)),
+                     out = as_field(tuple_util::get<2>(ds));
+                using T = element_of<std::decay_t<decltype(tuple_util::get<2>(ds))>>;
+                static_assert(std::is_same<T, double>::value || std::is_same<T, float>::value, "float or double");
+                int st = std::is_same<T, double>::value
+                             ? gtb_hori_diff_f64(&in, &coeff, &out, grid.i_size(), grid.j_size(), grid.k_size(), stream)
+                             : gtb_hori_diff_f32(&in, &coeff, &out, grid.i_size(), grid.j_size(), grid.k_size(), stream);
+                gtb200::check(st, "gtb_hori_diff");
+            }
+
+            // vertical_advection_dycore.cpp:140-149 : run(spec, backend, grid, utens_stage, u_stage, wcon, u_pos, utens,
+            // dtr_stage) with dtr_stage a global_parameter
+            template <class Grid, class DataStores>
+            void run_named(kernel_c<kernel::vert_adv>, Grid const &grid, DataStores &ds, void *stream) {
+                static_assert(tuple_util::size<DataStores>::value == 6,
+                    "vert_adv takes (utens_stage, u_stage, wcon, u_pos, utens, dtr_stage)");
+                gtb_field f[5] = {as_field(tuple_util::get<0>(ds)),
+                    as_field(tuple_util::get<1>(ds)),
+                    as_field(tuple_util::get<2>(ds)),
+                    as_field(tuple_util::get<3>(ds)),
+                    as_field(tuple_util::get<4>(ds))};
+                using T = element_of<std::decay_t<decltype(tuple_util::get<0>(ds))>>;
+                static_assert(std::is_same<T, double>::value || std::is_same<T, float>::value, "float or double");
+                const T dtr = *sid::get_origin(tuple_util::get<5>(ds))();
+                int st;
+                if (std::is_same<T, double>::value)
+                    st = gtb_vert_adv_f64(
+                        &f[0], &f[1], &f[2], &f[3], &f[4], (double)dtr, grid.i_size(), grid.j_size(), grid.k_size(), stream);
+                else
+                    st = gtb_vert_adv_f32(
+                        &f[0], &f[1], &f[2], &f[3], &f[4], (float)dtr, grid.i_size(), grid.j_size(), grid.k_size(), stream);
+                gtb200::check(st, "gtb_vert_adv");
+            }
+
+            // tridiagonal.cpp:83-97 : run(spec, backend, grid, inf, diag, sup, rhs, out)
+            template <class Grid, class DataStores>
+            void run_named(kernel_c<kernel::tridiagonal>, Grid const &grid, DataStores &ds, void *stream) {
+                static_assert(tuple_util::size<DataStores>::value == 5, "tridiagonal takes (inf, diag, sup, rhs, out)");
+                gtb_field f[5] = {as_field(tuple_util::get<0>(ds)),
+                    as_field(tuple_util::get<1>(ds)),
+                    as_field(tuple_util::get<2>(ds)),
+                    as_field(tuple_util::get<3>(ds)),
+                    as_field(tuple_util::get<4>(ds))};
+                gtb200::check(gtb_tridiagonal_f64(
+                                  &f[0], &f[1], &f[2], &f[3], &f[4], grid.i_size(), grid.j_size(), grid.k_size(), stream),
+                    "gtb_tridiagonal_f64");
+            }
+
+#ifdef __CUDACC__
+            // ---------------------------------------------------------------- generic path (stage by stage)
+            constexpr int generic_block_i = 32, generic_block_j = 8;
+
+            // One launch = one stage on the extent-extended IJ domain.  Parallel stages: blockIdx.z is the level
+            // (the cell that owns it is found by walking the intervals).  Sweeps: one thread per column walks all
+            // intervals in execution order.
+            template <class Stage, class PtrHolder, class Strides, class KSizes>
+            __global__ void generic_stage_kernel(
+                PtrHolder holder, Strides strides, KSizes k_sizes, int_t i_size, int_t j_size) {
+                const int_t i = blockIdx.x * generic_block_i + threadIdx.x;
+                const int_t j = blockIdx.y * generic_block_j + threadIdx.y;
+                if (i >= i_size || j >= j_size)
+                    return;
+                auto ptr = holder();
+                sid::shift(ptr, sid::get_stride<dim::i>(strides), i);
+                sid::shift(ptr, sid::get_stride<dim::j>(strides), j);
+                if (be_api::is_parallel<typename Stage::execution_t>::value) {
+                    int_t k = blockIdx.z;
+                    bool done = false;
+                    tuple_util::device::for_each(
+                        [&](auto cell, int_t size) {
+                            if (done)
+                                return;
+                            if (k < size) {
+                                sid::shift(ptr, sid::get_stride<dim::k>(strides), k);
+                                cell(ptr, strides);
+                                done = true;
+                            } else {
+                                k -= size;
+                                sid::shift(ptr, sid::get_stride<dim::k>(strides), size);
+                            }
+                        },
+                        Stage::cells(),
+                        k_sizes);
+                } else {
+                    tuple_util::device::for_each(
+                        [&](auto cell, int_t size) {
+                            for (int_t k = 0; k < size; ++k) {
+                                cell(ptr, strides);
+                                cell.inc_k(ptr, strides);
+                            }
+                        },
+                        Stage::cells(),
+                        k_sizes);
+                }
+            }
+
+            template <class Stage, class Grid, class DataStores>
+            void launch_generic_stage(Stage, Grid const &grid, DataStores &data_stores, cudaStream_t stream) {
+                using extent_t = typename Stage::extent_t;
+                using plh_map_t = typename Stage::plh_map_t;
+                using keys_t = meta::rename<sid::composite::keys, meta::transform<meta::first, plh_map_t>>;
+                auto composite = tuple_util::convert_to<keys_t::template values>(tuple_util::transform(
+                    [&](auto info) { return sid::add_const(info.is_const(), at_key<decltype(info.plh())>(data_stores)); },
+                    Stage::plh_map()));
+                using ptr_diff_t = sid::ptr_diff_type<decltype(composite)>;
+                auto strides = sid::get_strides(composite);
+                ptr_diff_t offset{};
+                sid::shift(offset, sid::get_stride<dim::i>(strides), extent_t::minus(dim::i()));
+                sid::shift(offset, sid::get_stride<dim::j>(strides), extent_t::minus(dim::j()));
+                sid::shift(offset, sid::get_stride<dim::k>(strides), grid.k_start(Stage::interval(), Stage::execution()));
+                auto k_sizes = tuple_util::transform([&](auto cell) { return grid.k_size(cell.interval()); }, Stage::cells());
+                const int_t i_size = grid.i_size(extent_t()), j_size = grid.j_size(extent_t());
+                int_t k_total = 0;
+                tuple_util::for_each([&](int_t n) { k_total += n; }, k_sizes);
+                if (i_size <= 0 || j_size <= 0 || k_total <= 0)
+                    return;
+                const bool parallel = be_api::is_parallel<typename Stage::execution_t>::value;
+                dim3 block(generic_block_i, generic_block_j);
+                dim3 blocks((i_size + generic_block_i - 1) / generic_block_i,
+                    (j_size + generic_block_j - 1) / generic_block_j,
+                    parallel ? k_total : 1);
+                auto holder = sid::get_origin(composite) + offset;
+                generic_stage_kernel<Stage><<<blocks, block, 0, stream>>>(holder, strides, k_sizes, i_size, j_size);
+                GT_CUDA_CHECK(cudaGetLastError());
+            }
+
+            template <class Spec, class Grid, class DataStores>
+            void run_generic(Spec, Grid const &grid, DataStores external, void *stream) {
+                using stages_t = be_api::make_split_view<Spec>;
+                using tmp_plh_map_t = be_api::remove_caches_from_plh_map<typename stages_t::tmp_plh_map_t>;
+                auto alloc = sid::device::cached_allocator(&cuda_util::cuda_malloc<char[]>);
+                // temporaries: whole (extent-extended) domain in device memory, origin at the first compute point
+                auto temporaries = be_api::make_data_stores(tmp_plh_map_t(), [&](auto info) {
+                    auto extent = info.extent();
+                    auto interval = stages_t::interval();
+                    auto num_colors = info.num_colors();
+                    auto offsets = hymap::keys<dim::i, dim::j, dim::k>::make_values(
+                        -extent.minus(dim::i()), -extent.minus(dim::j()), -grid.k_start(interval) - extent.minus(dim::k()));
+                    auto sizes = hymap::keys<dim::c, dim::k, dim::j, dim::i>::make_values(
+                        num_colors, grid.k_size(interval, extent), grid.j_size(extent), grid.i_size(extent));
+                    using stride_kind = meta::list<decltype(extent), decltype(num_colors)>;
+                    return sid::shift_sid_origin(
+                        sid::make_contiguous<decltype(info.data()), ptrdiff_t, stride_kind>(alloc, sizes), offsets);
+                });
+                auto data_stores = hymap::concat(std::move(external), std::move(temporaries));
+                for_each<stages_t>(
+                    [&](auto stage) { launch_generic_stage(stage, grid, data_stores, static_cast<cudaStream_t>(stream)); });
+            }
+#endif
+
+            // ---------------------------------------------------------------- the tag
+            template <class StreamGetter = ::gtb200::default_stream>
+            struct b200 {
+                template <class Spec, class Grid, class DataStores>
+                static void dispatch(std::true_type /*named*/, Spec, Grid const &grid, DataStores &data_stores) {
+                    run_named(kernel_c<::gtb200::named_spec<spec_functors<Spec>>::value>(), grid, data_stores,
+                        StreamGetter()());
+                }
+                template <class Spec, class Grid, class DataStores>
+                static void dispatch(std::false_type, Spec spec, Grid const &grid, DataStores &data_stores) {
+#ifdef __CUDACC__
+                    run_generic(spec, grid, std::move(data_stores), StreamGetter()());
+#else
+                    static_assert(sizeof(Spec) == 0,
+                        "stencil::b200: this spec is not bound to a named kernel (GTB200_REGISTER_SPEC); the generic "
+                        "path instantiates the user functors in a CUDA kernel and needs this file to be compiled by nvcc");
+#endif
+                }
+
+                template <class Spec, class Grid, class DataStores>
+                friend void gridtools_backend_entry_point(b200, Spec spec, Grid const &grid, DataStores data_stores) {
+                    constexpr bool named = ::gtb200::named_spec<spec_functors<Spec>>::value != ::gtb200::kernel::none;
+                    b200::dispatch(std::integral_constant<bool, named>(), spec, grid, data_stores);
+                }
+            };
+        } // namespace b200_backend
+        using b200_backend::b200;
+    } // namespace stencil
+} // namespace gridtools
