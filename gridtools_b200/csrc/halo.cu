@@ -71,6 +71,7 @@ struct gtb_halo {
     bool connected;
     uint64_t epoch; // starts at 1
     int *d_error;   // device flag set by a wait that timed out
+    unsigned *d_counters; // per-direction block counters of the fused pack + signal launch
 };
 
 namespace {
@@ -81,47 +82,98 @@ namespace {
     int lo_outside(const gtb_halo_desc &h, int e) { return e == 0 ? h.begin : (e == 1 ? h.end + 1 : h.begin - h.minus); }
     int hi_outside(const gtb_halo_desc &h, int e) { return e == 0 ? h.end : (e == 1 ? h.end + h.plus : h.begin - 1); }
 
+    // Fused synchronisation of a transfer launch.  mode 1 (pack towards peers): the last block of every direction
+    // raises the neighbour's flag once all blocks of that direction have made their stores visible system-wide.
+    // mode 2 (unpack): every block first acquires its direction's flag.
+    struct sync_args {
+        uint64_t *flag[27];
+        uint64_t epoch;
+        unsigned *counters;      // [27], zero between launches
+        unsigned blocks_per_dir; // gridDim.x * gridDim.z
+        int *error;
+        long long timeout_cycles;
+        int mode; // 0 none, 1 signal after pack, 2 wait before unpack
+    };
+
     struct xfer_args {
         region r[27];
         char *buf[27]; // message buffer per direction (local or NVLink-mapped)
         char *fields[kMaxFields];
         int64_t s1, s2; // element strides of storage dimensions 1 and 2
         int n_fields;
+        sync_args sync;
     };
+
+    __device__ __forceinline__ void wait_flag(const uint64_t *flag, uint64_t epoch, int *error, long long timeout, int n) {
+        if (*reinterpret_cast<volatile int *>(error))
+            return; // an earlier wait already timed out: do not stall every following exchange as well
+        const long long t0 = clock64();
+        for (;;) {
+            uint64_t v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+            if (v >= epoch)
+                break;
+            if (clock64() - t0 > timeout) {
+                atomicExch(error, 1 + n);
+                break;
+            }
+            __nanosleep(100);
+        }
+    }
 
     // PACK: field -> buffer; else buffer -> field.
     template <class E, bool PACK>
     __global__ void __launch_bounds__(kThreads) xfer_kernel(const __grid_constant__ xfer_args a) {
         const int n = blockIdx.y, f = blockIdx.z;
         const region &r = a.r[n];
-        const int64_t base = (int64_t)blockIdx.x * (kThreads * kItems) + threadIdx.x;
-        if (base >= r.count)
+        if (r.count == 0)
             return;
-        E *buf = reinterpret_cast<E *>(a.buf[n]) + (int64_t)f * r.count;
-        E *fld = reinterpret_cast<E *>(a.fields[f]);
-        const int l0 = r.len[0], l1 = r.len[1];
-        int64_t idx[kItems];
-        E v[kItems];
+        if (!PACK && a.sync.mode == 2 && a.sync.flag[n]) {
+            if (threadIdx.x == 0)
+                wait_flag(a.sync.flag[n], a.sync.epoch, a.sync.error, a.sync.timeout_cycles, n);
+            __syncthreads();
+        }
+        const int64_t base = (int64_t)blockIdx.x * (kThreads * kItems) + threadIdx.x;
+        if (base < r.count) {
+            E *buf = reinterpret_cast<E *>(a.buf[n]) + (int64_t)f * r.count;
+            E *fld = reinterpret_cast<E *>(a.fields[f]);
+            const int l0 = r.len[0], l1 = r.len[1];
+            int64_t idx[kItems];
+            E v[kItems];
 #pragma unroll
-        for (int t = 0; t < kItems; ++t) {
-            int64_t e = base + (int64_t)t * kThreads;
-            if (e < r.count) {
-                int64_t q = e / l0;
-                int i0 = (int)(e - q * l0);
-                int64_t q2 = q / l1;
-                int i1 = (int)(q - q2 * l1);
-                idx[t] = (r.lo[0] + i0) + (r.lo[1] + i1) * a.s1 + (r.lo[2] + q2) * a.s2;
-                v[t] = PACK ? fld[idx[t]] : buf[e];
+            for (int t = 0; t < kItems; ++t) {
+                int64_t e = base + (int64_t)t * kThreads;
+                if (e < r.count) {
+                    int64_t q = e / l0;
+                    int i0 = (int)(e - q * l0);
+                    int64_t q2 = q / l1;
+                    int i1 = (int)(q - q2 * l1);
+                    idx[t] = (r.lo[0] + i0) + (r.lo[1] + i1) * a.s1 + (r.lo[2] + q2) * a.s2;
+                    v[t] = PACK ? fld[idx[t]] : buf[e];
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < kItems; ++t) {
+                int64_t e = base + (int64_t)t * kThreads;
+                if (e < r.count) {
+                    if (PACK)
+                        buf[e] = v[t];
+                    else
+                        fld[idx[t]] = v[t];
+                }
             }
         }
-#pragma unroll
-        for (int t = 0; t < kItems; ++t) {
-            int64_t e = base + (int64_t)t * kThreads;
-            if (e < r.count) {
-                if (PACK)
-                    buf[e] = v[t];
-                else
-                    fld[idx[t]] = v[t];
+        if (PACK && a.sync.mode == 1 && a.sync.flag[n]) {
+            __threadfence_system(); // this thread's payload stores are visible to the peer before the block is counted
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned done = atomicAdd(&a.sync.counters[n], 1u) + 1u;
+                if (done == a.sync.blocks_per_dir) {
+                    a.sync.counters[n] = 0;
+                    __threadfence_system();
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.sync.flag[n]), "l"(a.sync.epoch)
+                                 : "memory");
+                }
             }
         }
     }
@@ -164,32 +216,29 @@ namespace {
 
     __global__ void wait_kernel(const __grid_constant__ wait_args a) {
         const int n = threadIdx.x;
-        if (n < 27 && a.flag[n]) {
-            if (*reinterpret_cast<volatile int *>(a.error))
-                return; // an earlier wait already timed out: do not stall every following exchange as well
-            const long long t0 = clock64();
-            for (;;) {
-                uint64_t v;
-                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.flag[n]) : "memory");
-                if (v >= a.epoch)
-                    break;
-                if (clock64() - t0 > a.timeout_cycles) {
-                    atomicExch(a.error, 1 + n);
-                    break;
-                }
-                __nanosleep(200);
-            }
-        }
+        if (n < 27 && a.flag[n])
+            wait_flag(a.flag[n], a.epoch, a.error, a.timeout_cycles, n);
     }
 
     int n_of(int e0, int e1, int e2) { return (e0 + 1) + 3 * (e1 + 1) + 9 * (e2 + 1); }
 
     int64_t align_up(int64_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 
+    constexpr long long kTimeoutCycles = 6000000000ll; // ~3 s at 2 GHz: a lost neighbour must not hang the GPU
+
+    // sync_mode 0: plain copy; 1: raise the neighbours' flags when done (pack); 2: wait for the own flags first (unpack)
     template <bool PACK>
-    int run_xfer(gtb_halo *h, void *const *fields, int n_fields, char *const bufs[27], cudaStream_t stream) {
+    int run_xfer(gtb_halo *h, void *const *fields, int n_fields, char *const bufs[27], cudaStream_t stream,
+        int sync_mode = 0) {
         int64_t max_count = 0;
         xfer_args a;
+        a.sync.mode = 0;
+        a.sync.epoch = h->epoch;
+        a.sync.counters = h->d_counters;
+        a.sync.error = h->d_error;
+        a.sync.timeout_cycles = kTimeoutCycles;
+        for (int n = 0; n < 27; ++n)
+            a.sync.flag[n] = nullptr;
         const region *regs = PACK ? h->send : h->recv;
         for (int n = 0; n < 27; ++n) {
             a.r[n] = regs[n];
@@ -213,6 +262,20 @@ namespace {
                 if (b.buf[n])
                     b.buf[n] += (int64_t)f0 * b.r[n].count * h->es;
             dim3 grid((unsigned)((max_count + kThreads * kItems - 1) / (kThreads * kItems)), 27, nf);
+            const bool first = f0 == 0, last = f0 + nf >= n_fields;
+            if ((sync_mode == 1 && last) || (sync_mode == 2 && first)) {
+                b.sync.mode = sync_mode;
+                b.sync.blocks_per_dir = grid.x * grid.z;
+                for (int n = 0; n < 27; ++n) {
+                    if (n == 13 || h->nbr[n] < 0 || b.r[n].count == 0)
+                        continue;
+                    if (sync_mode == 1) // the neighbour sees this rank in direction 26 - n
+                        b.sync.flag[n] =
+                            reinterpret_cast<uint64_t *>(h->peer_arena[n]) + (h->epoch & 1) * 32 + (26 - n);
+                    else
+                        b.sync.flag[n] = reinterpret_cast<uint64_t *>(h->arena) + (h->epoch & 1) * 32 + n;
+                }
+            }
             if (h->es == 8)
                 xfer_kernel<uint64_t, PACK><<<grid, kThreads, 0, stream>>>(b);
             else
@@ -323,11 +386,16 @@ GTB_API int gtb_halo_create(const gtb_halo_desc desc[3], const int neighbour_ran
     h->send_arena = nullptr;
     h->arena = nullptr;
     h->d_error = nullptr;
+    h->d_counters = nullptr;
     cudaError_t e = cudaMalloc(&h->send_arena, (size_t)(h->send_total + kAlign));
     if (e == cudaSuccess)
         e = cudaMalloc(&h->arena, (size_t)h->arena_bytes);
     if (e == cudaSuccess)
         e = cudaMalloc(&h->d_error, sizeof(int));
+    if (e == cudaSuccess)
+        e = cudaMalloc(&h->d_counters, 32 * sizeof(unsigned));
+    if (e == cudaSuccess)
+        e = cudaMemset(h->d_counters, 0, 32 * sizeof(unsigned));
     if (e == cudaSuccess)
         e = cudaMemset(h->arena, 0, (size_t)h->arena_bytes);
     if (e == cudaSuccess)
@@ -335,7 +403,7 @@ GTB_API int gtb_halo_create(const gtb_halo_desc desc[3], const int neighbour_ran
     if (e == cudaSuccess)
         e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
-        cudaFree(h->send_arena), cudaFree(h->arena), cudaFree(h->d_error);
+        cudaFree(h->send_arena), cudaFree(h->arena), cudaFree(h->d_error), cudaFree(h->d_counters);
         delete h;
         cuda_fail(e, "gtb_halo_create: buffer allocation");
         return GTB_ERR_ALLOC;
@@ -359,6 +427,7 @@ GTB_API int gtb_halo_destroy(gtb_halo *h) {
     cudaFree(h->send_arena);
     cudaFree(h->arena);
     cudaFree(h->d_error);
+    cudaFree(h->d_counters);
     delete h;
     return GTB_OK;
 }
@@ -466,10 +535,9 @@ GTB_API int gtb_halo_pack_send(gtb_halo *h, void *const *fields, int n_fields, v
     char *bufs[27];
     for (int n = 0; n < 27; ++n)
         bufs[n] = h->send[n].count ? peer_slot(h, n, h->epoch) : nullptr;
-    st = run_xfer<true>(h, fields, n_fields, bufs, as_stream(stream));
-    if (st)
-        return st;
-    return signal(h, as_stream(stream));
+    if (n_fields == 0)
+        return signal(h, as_stream(stream));
+    return run_xfer<true>(h, fields, n_fields, bufs, as_stream(stream), 1);
 }
 
 GTB_API int gtb_halo_send(gtb_halo *h, int n_fields, void *stream) {
@@ -524,7 +592,7 @@ GTB_API int gtb_halo_wait(gtb_halo *h, void *stream) {
         return GTB_OK;
     w.epoch = h->epoch;
     w.error = h->d_error;
-    w.timeout_cycles = 6000000000ll; // ~3 s at 2 GHz: a lost neighbour must not hang the GPU
+    w.timeout_cycles = kTimeoutCycles;
     wait_kernel<<<1, 32, 0, as_stream(stream)>>>(w);
     count_launch();
     return check_launch("halo wait");
@@ -538,6 +606,20 @@ GTB_API int gtb_halo_unpack(gtb_halo *h, void *const *fields, int n_fields, void
     for (int n = 0; n < 27; ++n)
         bufs[n] = h->recv[n].count ? recv_slot(h, n, h->epoch) : nullptr;
     return run_xfer<false>(h, fields, n_fields, bufs, as_stream(stream));
+}
+
+GTB_API int gtb_halo_wait_unpack(gtb_halo *h, void *const *fields, int n_fields, void *stream) {
+    int st = check_fields(h, fields, n_fields, "gtb_halo_wait_unpack");
+    if (st)
+        return st;
+    if (!h->connected)
+        return fail(GTB_ERR_STATE, "gtb_halo_wait_unpack: gtb_halo_connect has not been called");
+    if (n_fields == 0)
+        return gtb_halo_wait(h, stream);
+    char *bufs[27];
+    for (int n = 0; n < 27; ++n)
+        bufs[n] = h->recv[n].count ? recv_slot(h, n, h->epoch) : nullptr;
+    return run_xfer<false>(h, fields, n_fields, bufs, as_stream(stream), 2);
 }
 
 GTB_API int gtb_halo_error(gtb_halo *h, int *code) {

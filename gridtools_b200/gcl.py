@@ -318,8 +318,7 @@ class halo_exchange_dynamic_ut:
             self.comm.exchange(sends, recvs)
 
     def wait(self):
-        if self.transport == "p2p":
-            _lib.check(_lib.lib().gtb_halo_wait(self._h, self._stream()))
+        pass  # p2p: the arrival flags are acquired inside the unpack launch (gtb_halo_wait_unpack)
 
     def unpack(self, *fields):
         if self.transport == "host":
@@ -328,7 +327,8 @@ class halo_exchange_dynamic_ut:
                 self.codec.unpack(self.plan, n, f, msg)
             return
         arr, n = self._ptrs(fields)
-        _lib.check(_lib.lib().gtb_halo_unpack(self._h, arr, n, self._stream()))
+        fn = _lib.lib().gtb_halo_wait_unpack if self.transport == "p2p" else _lib.lib().gtb_halo_unpack
+        _lib.check(fn(self._h, arr, n, self._stream()))
         _lib.check(_lib.lib().gtb_halo_next_epoch(self._h))
 
     def check(self):

@@ -159,8 +159,9 @@ int gtb_halo_connect(gtb_halo *h, const void *const blobs[27]);
 /* One fused launch: gathers the send regions of all fields for all existing neighbours into the send buffers.
  * fields[f] points at storage element (0,0,0) INCLUDING the halo (like the raw T* the reference takes). */
 int gtb_halo_pack(gtb_halo *h, void *const *fields, int n_fields, void *stream);
-/* Fused pack + NVLink store: writes every message straight into the neighbour's receive buffer and raises its
- * arrival flag (needs connect).  Equivalent to pack() + the do_sends() half of exchange(). */
+/* Fused pack + NVLink store + signal in ONE launch: writes every message straight into the neighbour's receive
+ * buffer; the last block of each direction raises the neighbour's arrival flag (needs connect).  Equivalent to
+ * pack() + the do_sends() half of exchange(). */
 int gtb_halo_pack_send(gtb_halo *h, void *const *fields, int n_fields, void *stream);
 /* Pushes the packed send buffers into the neighbours' receive buffers and raises their flags (needs connect). */
 int gtb_halo_send(gtb_halo *h, int n_fields, void *stream);
@@ -168,6 +169,10 @@ int gtb_halo_send(gtb_halo *h, int n_fields, void *stream);
 int gtb_halo_wait(gtb_halo *h, void *stream);
 /* One fused launch: scatters every received message into the halo regions of all fields. */
 int gtb_halo_unpack(gtb_halo *h, void *const *fields, int n_fields, void *stream);
+/* wait + unpack in ONE launch: every block acquires the arrival flag of its direction before it scatters that
+ * message (needs connect).  Together with gtb_halo_pack_send an exchange is two launches and no host synchronisation,
+ * against up to 12 x n_fields launches, a cudaDeviceSynchronize and 2 x 26 MPI calls in the reference. */
+int gtb_halo_wait_unpack(gtb_halo *h, void *const *fields, int n_fields, void *stream);
 /* Synchronises the device and reports whether a wait timed out: *code = 0 if not, else 1 + direction that never
  * arrived.  (Halo_Exchange_3D has no error path: a lost MPI peer hangs in MPI_Wait.) */
 int gtb_halo_error(gtb_halo *h, int *code);

@@ -58,7 +58,7 @@ namespace {
                     double x = va(i, j, k), y = vb(i, j, k);
                     double d = std::fabs(x - y), s = std::fmax(std::fabs(x), std::fabs(y));
                     double rel = s > 0 ? d / s : 0;
-                    if (!(d < tol || rel < tol))
+                    if (tol == 0 ? x != y : !(d < tol || rel < tol))
                         ++bad;
                     if (rel > worst && d >= tol)
                         worst = rel;
