@@ -357,7 +357,8 @@ def b200_arm(args):
                        sum(f.nbytes_host for f in sets[0]) // 2**20, n_sets),
                    "vs_baseline_ref": "reference stencil::gpu on P100, BASELINE.md section 1"},
         "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
-        "step_ms_median": statistics.median(per_step),
+        "step_ms_median": statistics.median(per_step), "step_ms_p90": sorted(per_step)[int(0.9 * len(per_step))],
+        "step_ms_max": max(per_step),
     }
 
     if not args.no_extras:  # every rank moves its own sub-domain over its own PCIe link; max over ranks

@@ -201,6 +201,21 @@ namespace gtb {
             }
             return v;
         }
+        // Same, bypassing L1 (ld.global.cg): for data another warp of the SM has just rewritten through L2.
+        template <class T>
+        __device__ __forceinline__ T ld_cg_hint(const T *p, uint64_t policy) {
+            T v;
+            if constexpr (sizeof(T) == 8) {
+                uint64_t r;
+                asm volatile("ld.global.cg.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(r) : "l"(p), "l"(policy) : "memory");
+                memcpy(&v, &r, 8);
+            } else {
+                uint32_t r;
+                asm volatile("ld.global.cg.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(policy) : "memory");
+                memcpy(&v, &r, 4);
+            }
+            return v;
+        }
         template <class T>
         __device__ __forceinline__ void st_hint(T *p, T v, uint64_t policy) {
             if constexpr (sizeof(T) == 8) {

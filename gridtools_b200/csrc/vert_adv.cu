@@ -442,6 +442,177 @@ namespace {
         }
     }
 
+    // ------------------------------------------------------- forward/backward warp-specialised variant (va.variant = 3)
+    // A CTA is a pair of warps working on the same sequence of 32-column strips: warp 0 runs the forward sweeps
+    // (TMA ring exactly as above), warp 1 runs the backward sweeps one strip behind.  The k-cache slab is double
+    // buffered between them and handed over through two shared-memory mbarriers per buffer (ready: forward done,
+    // free: backward done).  With one warp doing both sweeps all warps of the chip alternate in lock-step between an
+    // HBM-bound phase (forward) and an L2-bound phase (backward); here the two phases of neighbouring strips overlap,
+    // so HBM streams continuously while the backward sweeps drain the slabs out of L2.
+    template <class T, int KC, int S, int NS>
+    __global__ void __launch_bounds__(64) va_fb_kernel(const __grid_constant__ va_maps maps, const va_params<T> p) {
+        using L = va_tma_layout<T>;
+        constexpr int stage_bytes = L::template stage_bytes<KC>();
+        extern __shared__ __align__(128) unsigned char smem_all[];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        unsigned char *ring = smem_all;
+        uint64_t *full = reinterpret_cast<uint64_t *>(smem_all + S * stage_bytes);
+        uint64_t *ready = full + S; // [2]
+        uint64_t *freeb = ready + 2; // [2]
+        T *tail = reinterpret_cast<T *>(freeb + 2); // [2 buffers][2 values][32 lanes]: dcol(nk-1), u_pos(nk-1)
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+                ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&ready[0], 1);
+            ptx::mbar_init(&ready[1], 1);
+            ptx::mbar_init(&freeb[0], 1);
+            ptx::mbar_init(&freeb[1], 1);
+            ptx::fence_barrier_init();
+            ptx::prefetch_tensormap(&maps.us);
+            ptx::prefetch_tensormap(&maps.up);
+            ptx::prefetch_tensormap(&maps.ut);
+            ptx::prefetch_tensormap(&maps.un);
+            ptx::prefetch_tensormap(&maps.wc);
+        }
+        __syncthreads();
+        const int nk = p.nk;
+        const T dtr = p.dtr;
+        const uint64_t pol_keep = ptx::policy_evict_last();
+        const int64_t sstride = p.slots; // slots = gridDim.x * 2 buffers * 32 lanes
+        T *slab0 = p.scratch + ((int64_t)blockIdx.x * 2) * 32 + lane;
+
+        if (warp == 0) {
+            // ------------------------------------------------------------ forward warp
+            const int nchunks = (nk + KC - 1) / KC;
+            uint32_t n_issued = 0, n_waited = 0;
+            int n = 0;
+            for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+                const int b = n & 1;
+                const int ti = item % p.tiles_i, j = item / p.tiles_i;
+                const int i0 = ti * 32, i = i0 + lane;
+                const bool active = i < p.ni;
+                auto issue = [&](int c) { // lane 0 only
+                    const int s = n_issued % S;
+                    unsigned char *dst = ring + s * stage_bytes;
+                    const int k0 = c * KC;
+                    ptx::mbar_expect_tx(&full[s], KC * (4 * 32 + L::ww) * L::es);
+                    ptx::tma_load_3d(dst, &maps.us, &full[s], i0, j, k0);
+                    ptx::tma_load_3d(dst + 1 * KC * 32 * L::es, &maps.up, &full[s], i0, j, k0);
+                    ptx::tma_load_3d(dst + 2 * KC * 32 * L::es, &maps.ut, &full[s], i0, j, k0);
+                    ptx::tma_load_3d(dst + 3 * KC * 32 * L::es, &maps.un, &full[s], i0, j, k0 + 1);
+                    ptx::tma_load_3d(dst + 4 * KC * 32 * L::es, &maps.wc, &full[s], i0, j, k0 + 1);
+                };
+                for (int c = 0; c < S - 1 && c < nchunks; ++c) {
+                    if (lane == 0)
+                        issue(c);
+                    ++n_issued;
+                }
+                if (n >= 2) // the backward warp must have drained this buffer (strip n-2)
+                    ptx::mbar_wait(&freeb[b], (uint32_t)((n / 2 - 1) & 1));
+                T *slab = slab0 + b * 32;
+                va_state<T> st;
+                st.u_k = active ? __ldg(p.u_stage.ptr + i + (int64_t)j * p.u_stage.sj) : T(0);
+                st.u_km1 = st.wsum_k = st.cc_prev = st.dc_prev = st.up_last = T(0);
+                for (int c = 0; c < nchunks; ++c) {
+                    if (c + S - 1 < nchunks) {
+                        if (lane == 0)
+                            issue(c + S - 1);
+                        ++n_issued;
+                    }
+                    const int s = n_waited % S;
+                    ptx::mbar_wait(&full[s], (n_waited / S) & 1);
+                    ++n_waited;
+                    const T *sd = reinterpret_cast<const T *>(ring + s * stage_bytes);
+                    const T *wc = sd + 4 * KC * 32;
+#pragma unroll
+                    for (int u = 0; u < KC; ++u) {
+                        const int k = c * KC + u;
+                        if (k < nk) {
+                            T us = sd[u * 32 + lane], up = sd[(KC + u) * 32 + lane], ut = sd[(2 * KC + u) * 32 + lane];
+                            T un = sd[(3 * KC + u) * 32 + lane];
+                            T w0 = wc[u * L::ww + lane], w1 = wc[u * L::ww + lane + 1];
+                            T cc, dc;
+                            va_forward_level<T>(k, nk, dtr, us, un, w0, w1, up, ut, st, cc, dc);
+                            if (k < nk - 1) {
+                                T *q = slab + (int64_t)k * NS * sstride;
+                                ptx::st_hint(q, cc, pol_keep);
+                                ptx::st_hint(q + sstride, dc, pol_keep);
+                                if constexpr (NS == 3)
+                                    ptx::st_hint(q + 2 * sstride, up, pol_keep);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+                tail[(b * 2 + 0) * 32 + lane] = st.dc_prev;
+                tail[(b * 2 + 1) * 32 + lane] = st.up_last;
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0)
+                    ptx::mbar_arrive(&ready[b]); // release: slab buffer b and its tail are complete
+            }
+        } else {
+            // ------------------------------------------------------------ backward warp
+            int n = 0;
+            for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+                const int b = n & 1;
+                const int ti = item % p.tiles_i, j = item / p.tiles_i;
+                const int i = ti * 32 + lane;
+                const bool active = i < p.ni;
+                ptx::mbar_wait(&ready[b], (uint32_t)((n / 2) & 1));
+                const T *slab = slab0 + b * 32;
+                T *us_p = p.utens_stage.ptr + i + (int64_t)j * p.utens_stage.sj;
+                const T *up_p = p.u_pos.ptr + (active ? i : 0) + (int64_t)j * p.u_pos.sj;
+                const int64_t us_sk = p.utens_stage.sk, up_sk = p.u_pos.sk;
+                T data = tail[(b * 2 + 0) * 32 + lane];
+                const T up_last = tail[(b * 2 + 1) * 32 + lane];
+                if (active)
+                    us_p[(int64_t)(nk - 1) * us_sk] = dtr * (data - up_last);
+                constexpr int BU = 8;
+                struct back_level {
+                    T cc, dc, up;
+                };
+                auto load_back = [&](int k, back_level &v) {
+                    if (k >= 0) {
+                        const T *q = slab + (int64_t)k * NS * sstride;
+                        v.cc = ptx::ld_cg_hint(q, pol_keep);
+                        v.dc = ptx::ld_cg_hint(q + sstride, pol_keep);
+                        if constexpr (NS == 3)
+                            v.up = ptx::ld_cg_hint(q + 2 * sstride, pol_keep);
+                        else
+                            v.up = __ldg(up_p + k * up_sk);
+                    }
+                };
+                back_level bcur[BU];
+#pragma unroll
+                for (int u = 0; u < BU; ++u)
+                    load_back(nk - 2 - u, bcur[u]);
+                for (int k0 = nk - 2; k0 >= 0; k0 -= BU) {
+                    back_level bnxt[BU];
+#pragma unroll
+                    for (int u = 0; u < BU; ++u)
+                        load_back(k0 - BU - u, bnxt[u]);
+#pragma unroll
+                    for (int u = 0; u < BU; ++u) {
+                        const int k = k0 - u;
+                        if (k >= 0) { // body :111-116
+                            data = bcur[u].dc - bcur[u].cc * data;
+                            if (active)
+                                us_p[(int64_t)k * us_sk] = dtr * (data - bcur[u].up);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < BU; ++u)
+                        bcur[u] = bnxt[u];
+                }
+                __syncwarp();
+                if (lane == 0)
+                    ptx::mbar_arrive(&freeb[b]);
+            }
+        }
+    }
+
     // ------------------------------------------------------------------------------ Thomas solve (tridiagonal.cpp)
     template <class T>
     struct td_params {
@@ -604,6 +775,22 @@ namespace {
         return check_launch("va_tma_kernel");
     }
 
+    template <class T, int KC, int S, int NS>
+    int launch_va_fb(const va_maps &maps, const va_params<T> &p, int grid, cudaStream_t stream) {
+        using L = va_tma_layout<T>;
+        auto kernel = va_fb_kernel<T, KC, S, NS>;
+        const int smem = S * L::template stage_bytes<KC>() + (S + 4) * 8 + 2 * 2 * 32 * (int)sizeof(T);
+        static thread_local int done_dev = -1;
+        if (done_dev != dev()->device) {
+            GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            done_dev = dev()->device;
+        }
+        kernel<<<grid, 64, smem, stream>>>(maps, p);
+        count_launch();
+        return check_launch("va_fb_kernel");
+    }
+
     // Builds the five tensor maps; false if any field is not TMA-addressable.
     template <class T>
     bool make_va_maps(va_maps &m, const va_params<T> &p) {
@@ -629,13 +816,14 @@ namespace {
         va_maps maps;
         if (!make_va_maps<T>(maps, p))
             return GTB_OK; // not addressable: the caller falls back to the register-prefetch kernel
-        const int wps = o.va_ctas_per_sm > 0 ? o.va_ctas_per_sm : 7; // warps per SM
+        const bool fb = o.va_variant == 3; // forward/backward warp pairs
+        const int wps = o.va_ctas_per_sm > 0 ? o.va_ctas_per_sm : (fb ? 4 : 7); // (forward) warps per SM
         const int64_t strips = (int64_t)p.tiles_i * p.nj;
         p.items = (int)strips;
         int grid = o.va_ctas_per_sm < 0 ? -o.va_ctas_per_sm : wps * d->sm_count;
         if (grid > strips)
             grid = (int)strips;
-        p.slots = (int64_t)grid * 32;
+        p.slots = (int64_t)grid * 32 * (fb ? 2 : 1);
         const bool save_upos = o.va_save_upos != 2;
         p.scratch = static_cast<T *>(scratch((size_t)(save_upos ? 3 : 2) * p.nk * p.slots * sizeof(T)));
         if (!p.scratch)
@@ -648,6 +836,9 @@ namespace {
             if (st)
                 return st;
         }
+        if (fb)
+            return save_upos ? launch_va_fb<T, 4, 4, 3>(maps, p, grid, stream)
+                             : launch_va_fb<T, 4, 4, 2>(maps, p, grid, stream);
         if (save_upos) {
             switch (kc) {
             case 2:
@@ -714,9 +905,9 @@ namespace {
             int st = vert_adv_tma<T>(p, o, d, as_stream(stream), &done);
             if (st || done)
                 return st;
-            if (o.va_variant == 2)
+            if (o.va_variant >= 2)
                 return fail(GTB_ERR_LAYOUT,
-                    "gtb_vert_adv: va.variant=2 (TMA) needs 16-byte aligned origins and stride_j/stride_k that are "
+                    "gtb_vert_adv: va.variant=2/3 (TMA) needs 16-byte aligned origins and stride_j/stride_k that are "
                     "multiples of 16 bytes");
         }
         const int64_t items = (int64_t)p.tiles_i * ceil_div(nj, threads / 32);

@@ -19,7 +19,7 @@ for dtype in (np.float64, np.float32):
         stencil.horizontal_diffusion(*st)
         torch.cuda.synchronize()
         print("hd", dtype.__name__, variant, "ok", flush=True)
-    for cfg in (dict(), dict(variant=2, ctas_per_sm=-2, unroll=2), dict(variant=1, scratch=2, threads=32),
+    for cfg in (dict(), dict(variant=3, ctas_per_sm=-2), dict(variant=2, ctas_per_sm=-2, unroll=2), dict(variant=1, scratch=2, threads=32),
                 dict(variant=1, ctas_per_sm=-2, threads=32)):
         for k in ("variant", "scratch", "threads", "ctas_per_sm", "save_upos", "unroll"):
             _lib.set_option("va." + k, cfg.get(k, 0))

@@ -81,7 +81,9 @@ def main():
             for f in st:
                 f.const_target_tensor()
         combos = []
-        for kc, wps, save, persist in itertools.product((4, 8), (5, 6, 7, 8, 10, 14), (1, 2), (-1, 0)):
+        for wps, save, persist in itertools.product((2, 3, 4, 5, 6, 7), (1, 2), (-1, 0)):
+            combos.append(dict(variant=3, unroll=4, ctas_per_sm=wps, save_upos=save, persist=persist))
+        for kc, wps, save, persist in itertools.product((4,), (6, 7, 8), (1, 2), (-1,)):
             combos.append(dict(variant=2, unroll=kc, ctas_per_sm=wps, save_upos=save, persist=persist))
         for threads, unroll, ctas, save in itertools.product((64,), (8,), (0, 7), (1, 2)):
             combos.append(dict(variant=1, scratch=1, threads=threads, unroll=unroll, ctas_per_sm=ctas, save_upos=save,
