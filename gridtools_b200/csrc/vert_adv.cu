@@ -336,21 +336,21 @@ namespace {
             const int ti = item % p.tiles_i, j = item / p.tiles_i;
             const int i0 = ti * 32, i = i0 + lane;
             const bool active = i < p.ni;
-            auto issue = [&](int c) { // lane 0 only
+            // Whole warp: lane 0 arms the barrier, then lanes 0..4 issue the five box loads with ONE predicated
+            // instruction (a TMA issue costs ~150 cycles of the issuing thread; five in a row by one lane made the
+            // ring refill as expensive as the forward math of the chunk).
+            auto issue = [&](int c) {
                 const int s = n_issued % S;
-                unsigned char *dst = ring + s * stage_bytes;
-                const int k0 = c * KC;
-                ptx::mbar_expect_tx(&full[s], KC * (4 * 32 + L::ww) * L::es);
-                ptx::tma_load_3d(dst, &maps.us, &full[s], i0, j, k0);
-                ptx::tma_load_3d(dst + 1 * KC * 32 * L::es, &maps.up, &full[s], i0, j, k0);
-                ptx::tma_load_3d(dst + 2 * KC * 32 * L::es, &maps.ut, &full[s], i0, j, k0);
-                ptx::tma_load_3d(dst + 3 * KC * 32 * L::es, &maps.un, &full[s], i0, j, k0 + 1);
-                ptx::tma_load_3d(dst + 4 * KC * 32 * L::es, &maps.wc, &full[s], i0, j, k0 + 1);
+                if (lane == 0)
+                    ptx::mbar_expect_tx(&full[s], KC * (4 * 32 + L::ww) * L::es);
+                __syncwarp();
+                if (lane < 5)
+                    ptx::tma_load_3d(ring + s * stage_bytes + lane * (KC * 32 * L::es), &maps.us + lane, &full[s], i0, j,
+                        c * KC + (lane >= 3 ? 1 : 0)); // u_stage and wcon are read one level up
             };
             // prologue: S-1 chunks in flight
             for (int c = 0; c < S - 1 && c < nchunks; ++c) {
-                if (lane == 0)
-                    issue(c);
+                issue(c);
                 ++n_issued;
             }
             va_state<T> st;
@@ -358,8 +358,7 @@ namespace {
             st.u_km1 = st.wsum_k = st.cc_prev = st.dc_prev = st.up_last = T(0);
             for (int c = 0; c < nchunks; ++c) {
                 if (c + S - 1 < nchunks) { // refill the stage consumed in the previous iteration
-                    if (lane == 0)
-                        issue(c + S - 1);
+                    issue(c + S - 1);
                     ++n_issued;
                 }
                 const int s = n_waited % S;
@@ -492,20 +491,17 @@ namespace {
                 const int ti = item % p.tiles_i, j = item / p.tiles_i;
                 const int i0 = ti * 32, i = i0 + lane;
                 const bool active = i < p.ni;
-                auto issue = [&](int c) { // lane 0 only
+                auto issue = [&](int c) { // whole warp, see va_tma_kernel
                     const int s = n_issued % S;
-                    unsigned char *dst = ring + s * stage_bytes;
-                    const int k0 = c * KC;
-                    ptx::mbar_expect_tx(&full[s], KC * (4 * 32 + L::ww) * L::es);
-                    ptx::tma_load_3d(dst, &maps.us, &full[s], i0, j, k0);
-                    ptx::tma_load_3d(dst + 1 * KC * 32 * L::es, &maps.up, &full[s], i0, j, k0);
-                    ptx::tma_load_3d(dst + 2 * KC * 32 * L::es, &maps.ut, &full[s], i0, j, k0);
-                    ptx::tma_load_3d(dst + 3 * KC * 32 * L::es, &maps.un, &full[s], i0, j, k0 + 1);
-                    ptx::tma_load_3d(dst + 4 * KC * 32 * L::es, &maps.wc, &full[s], i0, j, k0 + 1);
+                    if (lane == 0)
+                        ptx::mbar_expect_tx(&full[s], KC * (4 * 32 + L::ww) * L::es);
+                    __syncwarp();
+                    if (lane < 5)
+                        ptx::tma_load_3d(ring + s * stage_bytes + lane * (KC * 32 * L::es), &maps.us + lane, &full[s],
+                            i0, j, c * KC + (lane >= 3 ? 1 : 0));
                 };
                 for (int c = 0; c < S - 1 && c < nchunks; ++c) {
-                    if (lane == 0)
-                        issue(c);
+                    issue(c);
                     ++n_issued;
                 }
                 if (n >= 2) // the backward warp must have drained this buffer (strip n-2)
@@ -516,8 +512,7 @@ namespace {
                 st.u_km1 = st.wsum_k = st.cc_prev = st.dc_prev = st.up_last = T(0);
                 for (int c = 0; c < nchunks; ++c) {
                     if (c + S - 1 < nchunks) {
-                        if (lane == 0)
-                            issue(c + S - 1);
+                        issue(c + S - 1);
                         ++n_issued;
                     }
                     const int s = n_waited % S;
@@ -609,6 +604,148 @@ namespace {
                 __syncwarp();
                 if (lane == 0)
                     ptx::mbar_arrive(&freeb[b]);
+            }
+        }
+    }
+
+    // ------------------------------------------------------- producer/consumer warp pair variant (va.variant = 4)
+    // Same ring and slab as va_tma_kernel, but the TMA issue is moved to a second warp of the CTA: issuing a box load
+    // blocks the issuing warp for several hundred cycles, which the self-feeding warp of va_tma_kernel pays in series
+    // with its recurrence (measured: 9.8 us of 25 us per strip).  The producer warp only waits for a free stage
+    // (empty mbarrier, arrived by the consumer after its last read of the stage) and issues; the consumer warp only
+    // computes.
+    template <class T, int KC, int S, int NS>
+    __global__ void __launch_bounds__(64) va_pc_kernel(const __grid_constant__ va_maps maps, const va_params<T> p) {
+        using L = va_tma_layout<T>;
+        constexpr int stage_bytes = L::template stage_bytes<KC>();
+        extern __shared__ __align__(128) unsigned char smem_all[];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        unsigned char *ring = smem_all;
+        uint64_t *full = reinterpret_cast<uint64_t *>(smem_all + S * stage_bytes);
+        uint64_t *empty = full + S;
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                ptx::mbar_init(&full[s], 1);
+                ptx::mbar_init(&empty[s], 1);
+            }
+            ptx::fence_barrier_init();
+            ptx::prefetch_tensormap(&maps.us);
+            ptx::prefetch_tensormap(&maps.up);
+            ptx::prefetch_tensormap(&maps.ut);
+            ptx::prefetch_tensormap(&maps.un);
+            ptx::prefetch_tensormap(&maps.wc);
+        }
+        __syncthreads();
+        const int nk = p.nk;
+        const int nchunks = (nk + KC - 1) / KC;
+        if (warp == 1) {
+            // ------------------------------------------------------------ producer: lanes 0..4 issue one box each
+            uint32_t n = 0;
+            for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+                const int ti = item % p.tiles_i, j = item / p.tiles_i;
+                const int i0 = ti * 32;
+                for (int c = 0; c < nchunks; ++c, ++n) {
+                    const int s = n % S;
+                    if (n >= S)
+                        ptx::mbar_wait(&empty[s], (n / S - 1) & 1);
+                    if (lane == 0)
+                        ptx::mbar_expect_tx(&full[s], KC * (4 * 32 + L::ww) * L::es);
+                    __syncwarp();
+                    if (lane < 5)
+                        ptx::tma_load_3d(ring + s * stage_bytes + lane * (KC * 32 * L::es), &maps.us + lane, &full[s],
+                            i0, j, c * KC + (lane >= 3 ? 1 : 0));
+                }
+            }
+            return;
+        }
+        // ---------------------------------------------------------------- consumer: both sweeps of the strip
+        const T dtr = p.dtr;
+        const uint64_t pol_keep = ptx::policy_evict_last();
+        T *slab = p.scratch + (int64_t)blockIdx.x * 32 + lane; // [k][NS][slots]
+        const int64_t sstride = p.slots;
+        uint32_t n = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+            const int ti = item % p.tiles_i, j = item / p.tiles_i;
+            const int i = ti * 32 + lane;
+            const bool active = i < p.ni;
+            va_state<T> st;
+            st.u_k = active ? __ldg(p.u_stage.ptr + i + (int64_t)j * p.u_stage.sj) : T(0);
+            st.u_km1 = st.wsum_k = st.cc_prev = st.dc_prev = st.up_last = T(0);
+            for (int c = 0; c < nchunks; ++c, ++n) {
+                const int s = n % S;
+                ptx::mbar_wait(&full[s], (n / S) & 1);
+                const T *sd = reinterpret_cast<const T *>(ring + s * stage_bytes);
+                const T *wc = sd + 4 * KC * 32;
+                T us[KC], up[KC], ut[KC], un[KC], w0[KC], w1[KC];
+#pragma unroll
+                for (int u = 0; u < KC; ++u) {
+                    us[u] = sd[u * 32 + lane], up[u] = sd[(KC + u) * 32 + lane], ut[u] = sd[(2 * KC + u) * 32 + lane];
+                    un[u] = sd[(3 * KC + u) * 32 + lane];
+                    w0[u] = wc[u * L::ww + lane], w1[u] = wc[u * L::ww + lane + 1];
+                }
+                __syncwarp();
+                if (lane == 0)
+                    ptx::mbar_arrive(&empty[s]); // the stage is in registers: hand it back before the math
+#pragma unroll
+                for (int u = 0; u < KC; ++u) {
+                    const int k = c * KC + u;
+                    if (k < nk) {
+                        T cc, dc;
+                        va_forward_level<T>(k, nk, dtr, us[u], un[u], w0[u], w1[u], up[u], ut[u], st, cc, dc);
+                        if (k < nk - 1) {
+                            T *q = slab + (int64_t)k * NS * sstride;
+                            ptx::st_hint(q, cc, pol_keep);
+                            ptx::st_hint(q + sstride, dc, pol_keep);
+                            if constexpr (NS == 3)
+                                ptx::st_hint(q + 2 * sstride, up[u], pol_keep);
+                        }
+                    }
+                }
+            }
+            // backward sweep (u_backward_function)
+            T *us_p = p.utens_stage.ptr + i + (int64_t)j * p.utens_stage.sj;
+            const T *up_p = p.u_pos.ptr + (active ? i : 0) + (int64_t)j * p.u_pos.sj;
+            const int64_t us_sk = p.utens_stage.sk, up_sk = p.u_pos.sk;
+            T data = st.dc_prev;
+            if (active)
+                us_p[(int64_t)(nk - 1) * us_sk] = dtr * (data - st.up_last);
+            constexpr int BU = 8;
+            struct back_level {
+                T cc, dc, up;
+            };
+            auto load_back = [&](int k, back_level &v) {
+                if (k >= 0) {
+                    const T *q = slab + (int64_t)k * NS * sstride;
+                    v.cc = ptx::ld_hint(q, pol_keep);
+                    v.dc = ptx::ld_hint(q + sstride, pol_keep);
+                    if constexpr (NS == 3)
+                        v.up = ptx::ld_hint(q + 2 * sstride, pol_keep);
+                    else
+                        v.up = __ldg(up_p + k * up_sk);
+                }
+            };
+            back_level bcur[BU];
+#pragma unroll
+            for (int u = 0; u < BU; ++u)
+                load_back(nk - 2 - u, bcur[u]);
+            for (int k0 = nk - 2; k0 >= 0; k0 -= BU) {
+                back_level bnxt[BU];
+#pragma unroll
+                for (int u = 0; u < BU; ++u)
+                    load_back(k0 - BU - u, bnxt[u]);
+#pragma unroll
+                for (int u = 0; u < BU; ++u) {
+                    const int k = k0 - u;
+                    if (k >= 0) { // body :111-116
+                        data = bcur[u].dc - bcur[u].cc * data;
+                        if (active)
+                            us_p[(int64_t)k * us_sk] = dtr * (data - bcur[u].up);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < BU; ++u)
+                    bcur[u] = bnxt[u];
             }
         }
     }
@@ -791,6 +928,22 @@ namespace {
         return check_launch("va_fb_kernel");
     }
 
+    template <class T, int KC, int S, int NS>
+    int launch_va_pc(const va_maps &maps, const va_params<T> &p, int grid, cudaStream_t stream) {
+        using L = va_tma_layout<T>;
+        auto kernel = va_pc_kernel<T, KC, S, NS>;
+        const int smem = S * L::template stage_bytes<KC>() + 2 * S * 8;
+        static thread_local int done_dev = -1;
+        if (done_dev != dev()->device) {
+            GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            done_dev = dev()->device;
+        }
+        kernel<<<grid, 64, smem, stream>>>(maps, p);
+        count_launch();
+        return check_launch("va_pc_kernel");
+    }
+
     // Builds the five tensor maps; false if any field is not TMA-addressable.
     template <class T>
     bool make_va_maps(va_maps &m, const va_params<T> &p) {
@@ -839,6 +992,13 @@ namespace {
         if (fb)
             return save_upos ? launch_va_fb<T, 4, 4, 3>(maps, p, grid, stream)
                              : launch_va_fb<T, 4, 4, 2>(maps, p, grid, stream);
+        if (o.va_variant == 4) {
+            if (kc == 8)
+                return save_upos ? launch_va_pc<T, 8, 3, 3>(maps, p, grid, stream)
+                                 : launch_va_pc<T, 8, 3, 2>(maps, p, grid, stream);
+            return save_upos ? launch_va_pc<T, 4, 4, 3>(maps, p, grid, stream)
+                             : launch_va_pc<T, 4, 4, 2>(maps, p, grid, stream);
+        }
         if (save_upos) {
             switch (kc) {
             case 2:

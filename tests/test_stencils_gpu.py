@@ -175,7 +175,8 @@ def test_hori_diff_linearity(gt):
 
 
 # ------------------------------------------------------------------------------------- vertical advection
-VA_CONFIGS = [dict(), dict(variant=3), dict(variant=3, ctas_per_sm=-2), dict(variant=3, ctas_per_sm=-1, save_upos=2),
+VA_CONFIGS = [dict(), dict(variant=4), dict(variant=4, ctas_per_sm=-2, unroll=8), dict(variant=4, ctas_per_sm=-1, save_upos=2),
+              dict(variant=3), dict(variant=3, ctas_per_sm=-2), dict(variant=3, ctas_per_sm=-1, save_upos=2),
               dict(variant=2, unroll=8), dict(variant=2, unroll=2, ctas_per_sm=-2), dict(variant=2, ctas_per_sm=-1),
               dict(variant=1), dict(variant=1, threads=32, unroll=1), dict(variant=1, threads=128, unroll=2),
               dict(variant=1, threads=64, unroll=8, save_upos=2), dict(variant=1, scratch=2, threads=32, unroll=4),
@@ -219,7 +220,7 @@ def test_vert_adv_random_bit_exact(gt, oracle, size, alignment):
     shape = (nk, nj + 6, ni + 6)
     arrs = [rng.uniform(5, 9, shape), rng.uniform(5, 9, shape), rng.uniform(-3e-4, 3e-4, shape),
             rng.uniform(5, 9, shape), rng.uniform(-1e-5, 1e-5, shape)]
-    for cfg in (dict(), dict(variant=2, ctas_per_sm=-2), dict(variant=3, ctas_per_sm=-3), dict(variant=1), dict(variant=1, scratch=2, threads=32),
+    for cfg in (dict(), dict(variant=2, ctas_per_sm=-2), dict(variant=3, ctas_per_sm=-3), dict(variant=4, ctas_per_sm=-3), dict(variant=1), dict(variant=1, scratch=2, threads=32),
                 dict(variant=1, ctas_per_sm=-2, threads=32)):
         for k in ("variant", "threads", "unroll", "scratch", "ctas_per_sm", "save_upos"):
             gt.lib.set_option("va." + k, 0)
@@ -228,7 +229,7 @@ def test_vert_adv_random_bit_exact(gt, oracle, size, alignment):
             out, _ = run_va(gt, arrs, 0.15, alignment)
         except gt.lib.GtbError as e:
             # an explicitly requested TMA variant refuses layouts TMA cannot address (auto falls back)
-            assert cfg.get("variant") in (2, 3) and alignment == 1 and e.status == gt.lib.GTB_ERR_LAYOUT
+            assert cfg.get("variant") in (2, 3, 4) and alignment == 1 and e.status == gt.lib.GTB_ERR_LAYOUT
             continue
         inner = (slice(None), slice(3, -3), slice(3, -3))
         assert np.array_equal(out[inner], oracle.vert_adv(*arrs, 0.15)[inner])

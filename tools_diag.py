@@ -16,13 +16,12 @@ for st in sets:
     for f in st:
         f.const_target_tensor()
 _lib.set_option("va.variant", 2)
-for wps in (7, 14):
-    for stages in (0, 6):
-        for dbg in (0, 1, 2, 3, 4, 5, 6, 7):
-            _lib.set_option("va.ctas_per_sm", wps)
-            _lib.set_option("va.stages", stages)
-            _lib.set_option("va.debug", dbg)
-            med, mn = timeit(lambda st: stencil.vertical_advection_dycore(*st, 0.15), sets, n=20)
-            print("wps=%d stages=%d debug=%d (skip: %s%s%s): median %.2f us min %.2f" % (
-                wps, stages, dbg, "bwd " if dbg & 1 else "", "fwdmath " if dbg & 2 else "", "stores" if dbg & 4 else "",
-                med * 1e3, mn * 1e3), flush=True)
+_lib.set_option("va.variant", 4)
+for kc in (4, 8):
+    for wps in (1, 4, 6, 7, 8, 10):
+        _lib.set_option("va.unroll", kc)
+        _lib.set_option("va.ctas_per_sm", wps)
+        med, mn = timeit(lambda st: stencil.vertical_advection_dycore(*st, 0.15), sets, n=10)
+        strips = 2048 / (148 * wps)
+        print("variant 4 kc=%d wps=%d: median %.2f us min %.2f -> %.2f us per strip" % (kc, wps, med * 1e3, mn * 1e3,
+                                                                                   med * 1e3 / strips), flush=True)
