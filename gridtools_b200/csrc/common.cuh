@@ -152,6 +152,21 @@ namespace gtb {
                 "l"(policy)
                 : "memory");
         }
+        // 1-D bulk copy global -> shared (contiguous, 16-byte aligned address and size), completion on an mbarrier.
+        __device__ __forceinline__ void bulk_load_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar,
+            uint64_t policy) {
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+                    "r"(smem_addr(dst)),
+                "l"(src),
+                "r"(bytes),
+                "r"(smem_addr(bar)),
+                "l"(policy)
+                : "memory");
+        }
+        // Orders this thread's earlier generic-proxy accesses (all state spaces) before later async-proxy accesses
+        // (TMA / bulk copies): needed when data written with ordinary stores is re-read by a bulk copy.
+        __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
         __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *map) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
         }

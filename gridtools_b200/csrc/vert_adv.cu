@@ -7,17 +7,18 @@
 // by the backward sweep; no prefetching ("no unrolling", make_kernel_fun.hpp:62-64), so every level waits for its
 // own loads.
 //
-// What this kernel does instead:
-//  * one thread per column, a warp covers 32 consecutive i (256 B per fp64 load instruction), CTAs are small
-//    (default 64 threads) so that 256x256 columns spread evenly over 148 SMs;
-//  * the k_caches are plain registers rotated by the sweep: u_stage(k-1,k,k+1), wcon(i,k)+wcon(i+1,k) (the sum is
-//    what both gav of level k and gcv of level k-1 need), ccol/dcol(k-1), data_col(k+1);
-//  * loads are software-pipelined UNROLL levels ahead through a register ring (all loads of the next UNROLL levels
-//    are issued before the current UNROLL levels are computed), which is what hides HBM latency when only ~450
-//    columns live on an SM;
-//  * ccol/dcol, which the reference flushes to HBM, go either to shared memory (k-major, conflict free) when
-//    2*nk*threads elements fit, or to a column-interleaved global scratch accessed with an L2 evict_last policy
-//    while the streamed fields use evict_first, so the flush/read-back stays on chip as far as L2 allows.
+// What this file does instead (four kernels, "va.variant" option; 0 = auto = 3 when the layout is TMA-addressable,
+// else 1; measured numbers in profiles/README.md):
+//  1  va_kernel          one thread per column, loads software-pipelined UNROLL levels ahead through registers
+//                        (plain LDG, any alignment), ccol/dcol in shared memory or a column-interleaved global scratch;
+//  2  va_tma_kernel      first TMA version: persistent one-warp CTAs, per-warp TMA ring, per-thread slab loads;
+//  3  va_stream_kernel   the default: same decomposition as 2 with half the instructions per level, a contiguous
+//                        per-warp L2 slab and a 32-level register ring for the backward sweep;
+//  4  va_resident_kernel ccol/dcol never leave the SM: the upper 48 levels of a column in registers, the rest in
+//                        shared memory (no L2 slab at all; as fast as 3 at nk = 80, refused when nk is too tall).
+// Common to all: a warp covers 32 consecutive i (256 B per fp64 row), the k_caches of the reference are registers
+// rotated by the sweep (u_stage(k-1,k,k+1), wcon(i,k)+wcon(i+1,k), ccol/dcol(k-1), data_col(k+1)), and the
+// temporaries ccol/dcol that the reference flushes to HBM stay in L2 (evict_last, persisting set-aside) or on the SM.
 //
 // Arithmetic follows the functor bodies operation by operation (-fmad=false, IEEE division), so results are
 // bit-identical to oracle/gt_oracle.c compiled with -ffp-contract=off.
@@ -46,6 +47,7 @@ namespace {
         int64_t slots;  // columns (one slot per column) or resident threads (persistent grid: one slot per thread)
         int persistent; // slots are per thread and CTAs loop over the items
         int kc;         // levels per TMA stage (TMA variant)
+        int k_split;    // resident variant: levels [0, k_split) keep ccol/dcol in shared memory, the rest in registers
         int debug;      // diagnosis only (va.debug): 1 skip backward sweep, 2 skip forward math, 4 skip scratch stores
     };
 
@@ -118,6 +120,54 @@ namespace {
         s.dc_prev = dc;
         s.u_km1 = s.u_k;
         s.u_k = un;
+    }
+
+    // KC consecutive BODY levels (:50-68) in two phases: first everything that does not depend on the previous level's
+    // ccol/dcol (the tridiagonal coefficients a, b, c and the right-hand side d of all KC levels: independent
+    // instruction streams the scheduler can interleave), then the recurrence itself, which is the only serial part
+    // (multiply, subtract, reciprocal, multiply per level).  Same operations on the same operands as
+    // va_forward_level, hence bit-identical results; only the order of independent instructions differs.
+    // lv(u, us, un, w0, w1, up, ut) loads level u of the chunk, out(u, cc, dc, up) stores its results.
+    template <class T, int KC, class Load, class Store>
+    __device__ __forceinline__ void va_forward_body_chunk(T dtr, va_state<T> &s, Load &&lv, Store &&out) {
+        const T bet_m = T(0.5), bet_p = T(0.5); // vertical_advection_defs.hpp
+        T a[KC], b[KC], c[KC], d[KC], upv[KC];
+        T wsum = s.wsum_k, u_km1 = s.u_km1, u_k = s.u_k;
+#pragma unroll
+        for (int u = 0; u < KC; ++u) {
+            T us, un, w0, w1, up, ut;
+            lv(u, us, un, w0, w1, up, ut);
+            T dd = dtr * up + ut + us;
+            T wsum_n = w1 + w0;
+            T gav = -T(.25) * wsum;
+            T gcv = T(.25) * wsum_n;
+            T as = gav * bet_m;
+            T cs = gcv * bet_m;
+            a[u] = gav * bet_p;
+            c[u] = gcv * bet_p;
+            b[u] = dtr - a[u] - c[u];
+            T correction = -as * (u_km1 - u_k) - cs * (un - u_k);
+            d[u] = dd + correction;
+            upv[u] = up;
+            wsum = wsum_n;
+            u_km1 = u_k;
+            u_k = un;
+        }
+        T cc_prev = s.cc_prev, dc_prev = s.dc_prev;
+#pragma unroll
+        for (int u = 0; u < KC; ++u) {
+            T divided = T(1) / (b[u] - cc_prev * a[u]);
+            T cc = c[u] * divided;
+            T dc = (d[u] - dc_prev * a[u]) * divided;
+            out(u, cc, dc, upv[u]);
+            cc_prev = cc;
+            dc_prev = dc;
+        }
+        s.cc_prev = cc_prev;
+        s.dc_prev = dc_prev;
+        s.wsum_k = wsum;
+        s.u_km1 = u_km1;
+        s.u_k = u_k;
     }
 
     // SMEM: ccol/dcol live in dynamic shared memory [NS*nk][THREADS]; else in p.scratch [NS*nk][slots].
@@ -441,32 +491,42 @@ namespace {
         }
     }
 
-    // ------------------------------------------------------- forward/backward warp-specialised variant (va.variant = 3)
-    // A CTA is a pair of warps working on the same sequence of 32-column strips: warp 0 runs the forward sweeps
-    // (TMA ring exactly as above), warp 1 runs the backward sweeps one strip behind.  The k-cache slab is double
-    // buffered between them and handed over through two shared-memory mbarriers per buffer (ready: forward done,
-    // free: backward done).  With one warp doing both sweeps all warps of the chip alternate in lock-step between an
-    // HBM-bound phase (forward) and an L2-bound phase (backward); here the two phases of neighbouring strips overlap,
-    // so HBM streams continuously while the backward sweeps drain the slabs out of L2.
-    template <class T, int KC, int S, int NS>
-    __global__ void __launch_bounds__(64) va_fb_kernel(const __grid_constant__ va_maps maps, const va_params<T> p) {
+    // ------------------------------------------------------------------ streaming variant (va.variant = 3, default)
+    // Same decomposition as variant 2 (one warp = one 32-column strip, persistent over the strips, the warp is its
+    // own TMA producer), rebuilt around what the profile of variant 2 showed (profiles/README.md):
+    //  * 152 warp instructions per level of which 36 are fp64 -- the rest was 64-bit address arithmetic, the
+    //    three-way first/body/last branch in every level and register shuffling -- so a warp advanced one level every
+    //    ~700 cycles.  Here the k-cache slab of a warp is CONTIGUOUS, [level][ccol, dcol, u_pos][32 lanes] (all stores
+    //    of a level are one running pointer plus compile-time offsets), chunks that hold neither the first nor the
+    //    last level run a branch-free body, and one lane issues the five TMA boxes of a stage back to back;
+    //  * the backward sweep took 20 of 71 us although it is 4 flops per level: all warps of the chip run forward and
+    //    backward in lock-step, and a backward sweep that prefetches 8 levels ahead makes 10 dependent L2 round trips
+    //    of ~1 us while HBM idles.  With 7 warps per SM a thread may use ~290 registers, so the backward sweep here
+    //    keeps NB*8 levels (24 KB per warp at NB = 4) in flight in a statically indexed register ring;
+    //  * the forward ring of the NEXT strip is primed before the backward sweep of the current one starts, so HBM
+    //    streams while the warp drains its slab out of L2.
+    // NS = 3: u_pos(k) travels through the slab next to ccol/dcol (no second HBM read); NS = 2: re-read from HBM.
+    template <class T, int KC, int S>
+    constexpr int va_stream_smem() {
+        return S * va_tma_layout<T>::template stage_bytes<KC>() + S * 8;
+    }
+
+    template <class T, int KC, int S, int NB, int NS>
+    __global__ void __launch_bounds__(32) va_stream_kernel(const __grid_constant__ va_maps maps, const va_params<T> p) {
         using L = va_tma_layout<T>;
-        constexpr int stage_bytes = L::template stage_bytes<KC>();
+        constexpr int es = L::es;
+        constexpr int fstage = L::template stage_bytes<KC>();
+        constexpr uint32_t ftx = KC * (4 * 32 + L::ww) * es;
+        constexpr int G = 8;       // levels per register block of the backward sweep
+        constexpr int D = NB * G;  // levels in flight
         extern __shared__ __align__(128) unsigned char smem_all[];
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        unsigned char *ring = smem_all;
-        uint64_t *full = reinterpret_cast<uint64_t *>(smem_all + S * stage_bytes);
-        uint64_t *ready = full + S; // [2]
-        uint64_t *freeb = ready + 2; // [2]
-        T *tail = reinterpret_cast<T *>(freeb + 2); // [2 buffers][2 values][32 lanes]: dcol(nk-1), u_pos(nk-1)
-        if (threadIdx.x == 0) {
+        unsigned char *fring = smem_all;
+        uint64_t *ffull = reinterpret_cast<uint64_t *>(smem_all + S * fstage);
+        const int lane = threadIdx.x;
+        if (lane == 0) {
 #pragma unroll
             for (int s = 0; s < S; ++s)
-                ptx::mbar_init(&full[s], 1);
-            ptx::mbar_init(&ready[0], 1);
-            ptx::mbar_init(&ready[1], 1);
-            ptx::mbar_init(&freeb[0], 1);
-            ptx::mbar_init(&freeb[1], 1);
+                ptx::mbar_init(&ffull[s], 1);
             ptx::fence_barrier_init();
             ptx::prefetch_tensormap(&maps.us);
             ptx::prefetch_tensormap(&maps.up);
@@ -474,52 +534,79 @@ namespace {
             ptx::prefetch_tensormap(&maps.un);
             ptx::prefetch_tensormap(&maps.wc);
         }
-        __syncthreads();
+        __syncwarp();
         const int nk = p.nk;
         const T dtr = p.dtr;
+        const int dbg = p.debug; // diagnosis only (va.debug): 1 skip backward, 2 skip forward math, 4 skip slab stores, 8 skip output stores
         const uint64_t pol_keep = ptx::policy_evict_last();
-        const int64_t sstride = p.slots; // slots = gridDim.x * 2 buffers * 32 lanes
-        T *slab0 = p.scratch + ((int64_t)blockIdx.x * 2) * 32 + lane;
+        const int gw = blockIdx.x, total = gridDim.x;
+        T *const slab = p.scratch + (int64_t)gw * p.slots + lane; // p.slots = elements per warp slab: nk*NS*32
+        const int nchunks = (nk + KC - 1) / KC;
+        const int c_tail = (nk - 1) / KC; // first forward chunk that needs per-level checks (holds level nk-1)
+        uint32_t fi = 0, fw = 0;          // ring uses so far (stage = n % S, parity = (n / S) & 1)
 
-        if (warp == 0) {
-            // ------------------------------------------------------------ forward warp
-            const int nchunks = (nk + KC - 1) / KC;
-            uint32_t n_issued = 0, n_waited = 0;
-            int n = 0;
-            for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
-                const int b = n & 1;
-                const int ti = item % p.tiles_i, j = item / p.tiles_i;
-                const int i0 = ti * 32, i = i0 + lane;
-                const bool active = i < p.ni;
-                auto issue = [&](int c) { // whole warp, see va_tma_kernel
-                    const int s = n_issued % S;
-                    if (lane == 0)
-                        ptx::mbar_expect_tx(&full[s], KC * (4 * 32 + L::ww) * L::es);
-                    __syncwarp();
-                    if (lane < 5)
-                        ptx::tma_load_3d(ring + s * stage_bytes + lane * (KC * 32 * L::es), &maps.us + lane, &full[s],
-                            i0, j, c * KC + (lane >= 3 ? 1 : 0));
-                };
-                for (int c = 0; c < S - 1 && c < nchunks; ++c) {
-                    issue(c);
-                    ++n_issued;
-                }
-                if (n >= 2) // the backward warp must have drained this buffer (strip n-2)
-                    ptx::mbar_wait(&freeb[b], (uint32_t)((n / 2 - 1) & 1));
-                T *slab = slab0 + b * 32;
-                va_state<T> st;
-                st.u_k = active ? __ldg(p.u_stage.ptr + i + (int64_t)j * p.u_stage.sj) : T(0);
-                st.u_km1 = st.wsum_k = st.cc_prev = st.dc_prev = st.up_last = T(0);
-                for (int c = 0; c < nchunks; ++c) {
-                    if (c + S - 1 < nchunks) {
-                        issue(c + S - 1);
-                        ++n_issued;
-                    }
-                    const int s = n_waited % S;
-                    ptx::mbar_wait(&full[s], (n_waited / S) & 1);
-                    ++n_waited;
-                    const T *sd = reinterpret_cast<const T *>(ring + s * stage_bytes);
-                    const T *wc = sd + 4 * KC * 32;
+        // One lane issues the five boxes of a forward stage back to back (UTMALDG takes uniform operands: letting
+        // five lanes issue one box each only makes the compiler serialise them in an election loop).
+        auto issue_f = [&](int i0, int j, int c) {
+            const int s = fi % S;
+            if (lane == 0) {
+                unsigned char *st = fring + s * fstage;
+                uint64_t *bar = &ffull[s];
+                ptx::mbar_expect_tx(bar, ftx);
+                ptx::tma_load_3d(st, &maps.us, bar, i0, j, c * KC);
+                ptx::tma_load_3d(st + KC * 32 * es, &maps.up, bar, i0, j, c * KC);
+                ptx::tma_load_3d(st + 2 * KC * 32 * es, &maps.ut, bar, i0, j, c * KC);
+                ptx::tma_load_3d(st + 3 * KC * 32 * es, &maps.un, bar, i0, j, c * KC + 1); // read one level up
+                ptx::tma_load_3d(st + 4 * KC * 32 * es, &maps.wc, bar, i0, j, c * KC + 1);
+            }
+            ++fi;
+        };
+        auto prime = [&](int item, T &u0) { // first S-1 forward chunks of a strip + u_stage(k = 0)
+            const int ti = item % p.tiles_i, j = item / p.tiles_i;
+            const int i0 = ti * 32;
+            for (int c = 0; c < S - 1 && c < nchunks; ++c)
+                issue_f(i0, j, c);
+            u0 = i0 + lane < p.ni ? __ldg(p.u_stage.ptr + i0 + lane + (int64_t)j * p.u_stage.sj) : T(0);
+        };
+
+        int item = gw;
+        T u0 = T(0);
+        if (item < p.items)
+            prime(item, u0);
+        for (; item < p.items; item += total) {
+            const int ti = item % p.tiles_i, j = item / p.tiles_i;
+            const int i0 = ti * 32, i = i0 + lane;
+            const bool active = i < p.ni;
+            va_state<T> st;
+            st.u_k = u0;
+            st.u_km1 = st.wsum_k = st.cc_prev = st.dc_prev = st.up_last = T(0);
+            T *q = slab;
+            // ---------------------------------------------------------------- forward sweep (u_forward_function)
+            for (int c = 0; c < nchunks; ++c) {
+                if (c + S - 1 < nchunks) // refill the stage consumed in the previous iteration
+                    issue_f(i0, j, c + S - 1);
+                const int s = fw % S;
+                ptx::mbar_wait(&ffull[s], (fw / S) & 1);
+                ++fw;
+                const T *sd = reinterpret_cast<const T *>(fring + s * fstage);
+                const T *wc = sd + 4 * KC * 32;
+                if (c != 0 && c < c_tail) {
+                    va_forward_body_chunk<T, KC>(
+                        dtr, st,
+                        [&](int u, T &us, T &un, T &w0, T &w1, T &up, T &ut) {
+                            us = sd[u * 32 + lane], up = sd[(KC + u) * 32 + lane], ut = sd[(2 * KC + u) * 32 + lane];
+                            un = sd[(3 * KC + u) * 32 + lane];
+                            w0 = wc[u * L::ww + lane], w1 = wc[u * L::ww + lane + 1];
+                        },
+                        [&](int u, T cc, T dc, T up) {
+                            if (!(dbg & 4)) {
+                                ptx::st_hint(q + (u * NS) * 32, cc, pol_keep);
+                                ptx::st_hint(q + (u * NS + 1) * 32, dc, pol_keep);
+                                if constexpr (NS == 3)
+                                    ptx::st_hint(q + (u * NS + 2) * 32, up, pol_keep);
+                            }
+                        });
+                } else {
 #pragma unroll
                     for (int u = 0; u < KC; ++u) {
                         const int k = c * KC + u;
@@ -530,105 +617,174 @@ namespace {
                             T cc, dc;
                             va_forward_level<T>(k, nk, dtr, us, un, w0, w1, up, ut, st, cc, dc);
                             if (k < nk - 1) {
-                                T *q = slab + (int64_t)k * NS * sstride;
-                                ptx::st_hint(q, cc, pol_keep);
-                                ptx::st_hint(q + sstride, dc, pol_keep);
+                                ptx::st_hint(q + (u * NS) * 32, cc, pol_keep);
+                                ptx::st_hint(q + (u * NS + 1) * 32, dc, pol_keep);
                                 if constexpr (NS == 3)
-                                    ptx::st_hint(q + 2 * sstride, up, pol_keep);
+                                    ptx::st_hint(q + (u * NS + 2) * 32, up, pol_keep);
                             }
                         }
                     }
-                    __syncwarp();
                 }
-                tail[(b * 2 + 0) * 32 + lane] = st.dc_prev;
-                tail[(b * 2 + 1) * 32 + lane] = st.up_last;
-                __threadfence_block();
-                __syncwarp();
-                if (lane == 0)
-                    ptx::mbar_arrive(&ready[b]); // release: slab buffer b and its tail are complete
+                q += KC * NS * 32;
+                __syncwarp(); // all lanes are done with stage s before lane 0 refills it
             }
-        } else {
-            // ------------------------------------------------------------ backward warp
-            int n = 0;
-            for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
-                const int b = n & 1;
-                const int ti = item % p.tiles_i, j = item / p.tiles_i;
-                const int i = ti * 32 + lane;
-                const bool active = i < p.ni;
-                ptx::mbar_wait(&ready[b], (uint32_t)((n / 2) & 1));
-                const T *slab = slab0 + b * 32;
-                T *us_p = p.utens_stage.ptr + i + (int64_t)j * p.utens_stage.sj;
-                const T *up_p = p.u_pos.ptr + (active ? i : 0) + (int64_t)j * p.u_pos.sj;
-                const int64_t us_sk = p.utens_stage.sk, up_sk = p.u_pos.sk;
-                T data = tail[(b * 2 + 0) * 32 + lane];
-                const T up_last = tail[(b * 2 + 1) * 32 + lane];
+            // ---------------------------------------------------------------- backward sweep (u_backward_function)
+            // Register ring: block b holds levels kb - b*G - g (g = 0..G-1) of the current window of D levels.
+            if (dbg & 1) {
+                if (item + total < p.items)
+                    prime(item + total, u0);
                 if (active)
-                    us_p[(int64_t)(nk - 1) * us_sk] = dtr * (data - up_last);
-                constexpr int BU = 8;
-                struct back_level {
-                    T cc, dc, up;
-                };
-                auto load_back = [&](int k, back_level &v) {
-                    if (k >= 0) {
-                        const T *q = slab + (int64_t)k * NS * sstride;
-                        v.cc = ptx::ld_cg_hint(q, pol_keep);
-                        v.dc = ptx::ld_cg_hint(q + sstride, pol_keep);
+                    p.utens_stage.ptr[i + (int64_t)j * p.utens_stage.sj] = st.dc_prev;
+                continue;
+            }
+            T bc[NB][G], bd[NB][G], bu[NB][G];
+            const int64_t us_sk = p.utens_stage.sk, up_sk = p.u_pos.sk;
+            T *o = p.utens_stage.ptr + i + (int64_t)j * p.utens_stage.sj + (int64_t)(nk - 1) * us_sk;
+            const T *upp = p.u_pos.ptr + (active ? i : 0) + (int64_t)j * p.u_pos.sj; // NS == 2 only
+            auto load_block = [&](int b, int ktop) { // levels ktop .. ktop-G+1
+                const T *r = slab + (int64_t)ktop * (NS * 32);
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    if (ktop - g >= 0) {
+                        bc[b][g] = ptx::ld_hint(r - g * (NS * 32), pol_keep);
+                        bd[b][g] = ptx::ld_hint(r - g * (NS * 32) + 32, pol_keep);
                         if constexpr (NS == 3)
-                            v.up = ptx::ld_cg_hint(q + 2 * sstride, pol_keep);
+                            bu[b][g] = ptx::ld_hint(r - g * (NS * 32) + 64, pol_keep);
                         else
-                            v.up = __ldg(up_p + k * up_sk);
+                            bu[b][g] = __ldg(upp + (int64_t)(ktop - g) * up_sk);
                     }
-                };
-                back_level bcur[BU];
+                }
+            };
 #pragma unroll
-                for (int u = 0; u < BU; ++u)
-                    load_back(nk - 2 - u, bcur[u]);
-                for (int k0 = nk - 2; k0 >= 0; k0 -= BU) {
-                    back_level bnxt[BU];
+            for (int b = 0; b < NB; ++b)
+                load_block(b, nk - 2 - b * G);
+            if (item + total < p.items) // HBM keeps streaming while this warp drains its slab
+                prime(item + total, u0);
+            T data = st.dc_prev; // last_level :118-121
+            if (active)
+                *o = dtr * (data - st.up_last);
+            for (int kb = nk - 2; kb >= 0; kb -= D) {
 #pragma unroll
-                    for (int u = 0; u < BU; ++u)
-                        load_back(k0 - BU - u, bnxt[u]);
+                for (int b = 0; b < NB; ++b) {
+                    const int ktop = kb - b * G;
 #pragma unroll
-                    for (int u = 0; u < BU; ++u) {
-                        const int k = k0 - u;
-                        if (k >= 0) { // body :111-116
-                            data = bcur[u].dc - bcur[u].cc * data;
-                            if (active)
-                                us_p[(int64_t)k * us_sk] = dtr * (data - bcur[u].up);
+                    for (int g = 0; g < G; ++g) { // body :111-116
+                        if (ktop - g >= 0) {
+                            data = bd[b][g] - bc[b][g] * data;
+                            o -= us_sk;
+                            if (active && !(dbg & 8))
+                                *o = dtr * (data - bu[b][g]);
                         }
                     }
-#pragma unroll
-                    for (int u = 0; u < BU; ++u)
-                        bcur[u] = bnxt[u];
+                    load_block(b, ktop - D);
                 }
-                __syncwarp();
-                if (lane == 0)
-                    ptx::mbar_arrive(&freeb[b]);
             }
         }
     }
 
-    // ------------------------------------------------------- producer/consumer warp pair variant (va.variant = 4)
-    // Same ring and slab as va_tma_kernel, but the TMA issue is moved to a second warp of the CTA: issuing a box load
-    // blocks the issuing warp for several hundred cycles, which the self-feeding warp of va_tma_kernel pays in series
-    // with its recurrence (measured: 9.8 us of 25 us per strip).  The producer warp only waits for a free stage
-    // (empty mbarrier, arrived by the consumer after its last read of the stage) and issues; the consumer warp only
-    // computes.
-    template <class T, int KC, int S, int NS>
-    __global__ void __launch_bounds__(64) va_pc_kernel(const __grid_constant__ va_maps maps, const va_params<T> p) {
-        using L = va_tma_layout<T>;
-        constexpr int stage_bytes = L::template stage_bytes<KC>();
-        extern __shared__ __align__(128) unsigned char smem_all[];
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        unsigned char *ring = smem_all;
-        uint64_t *full = reinterpret_cast<uint64_t *>(smem_all + S * stage_bytes);
-        uint64_t *empty = full + S;
-        if (threadIdx.x == 0) {
+    // ------------------------------------------------------------------ resident variant (va.variant = 4, default)
+    // The L2 slab of variants 2 and 3 is not free: every byte written to and read back from it crosses the L2 slices,
+    // and the L2 slices of this chip move ~8 TB/s in total, HBM misses included (measured: 504 MB of L2 traffic in
+    // 62 us for variant 3, whatever the prefetch depth or the number of warps).  With ccol/dcol/u_pos in L2 the sweep
+    // moves 96 B per point through L2 against 48 B from HBM and is L2-bound at ~60 us.  Here ccol and dcol never
+    // leave the SM:
+    //  * the last RMAX levels of a column live in REGISTERS (statically indexed arrays, forward and backward sweeps
+    //    over that range are fully unrolled): at 7 warps per SM a thread may own 255 registers, and the register file
+    //    (256 KB per SM) is the largest on-chip memory there is;
+    //  * the levels below (k < k_split = nk - 1 - RMAX rounded up to a chunk) live in a per-warp SHARED-MEMORY slab
+    //    [k][ccol, dcol][32 lanes] (conflict free);
+    //  * u_pos, needed again by the backward sweep, is re-read through a small second TMA ring; the forward loads of
+    //    u_pos carry an L2 evict_last hint and everything else evict_first, so the second read is an L2 hit.
+    // L2 traffic drops to 56 B per point, HBM traffic stays at the compulsory 48 B.  A strip whose shared-memory slab
+    // would not leave room for 7 warps per SM (large nk) is run by variant 3 instead.
+    // Statically indexed access to the register-resident k-cache: chunk number -> KC array elements, through a switch
+    // (a jump table in SASS) so that the arrays never get a dynamic index and stay in registers.
+    template <class T, int KC, int NCR>
+    struct reg_tier {
+        template <int C>
+        static __device__ __forceinline__ void put_case(T *rc, T *rd, const T *ccv, const T *dcv) {
+            asm volatile("" ::: "memory"); // keeps the case a real branch target (the compiler would otherwise turn the
+                                           // switch into one select per array element and case)
 #pragma unroll
-            for (int s = 0; s < S; ++s) {
-                ptx::mbar_init(&full[s], 1);
-                ptx::mbar_init(&empty[s], 1);
+            for (int u = 0; u < KC; ++u) {
+                rc[C * KC + u] = ccv[u];
+                rd[C * KC + u] = dcv[u];
             }
+        }
+        template <int C>
+        static __device__ __forceinline__ void get_case(const T *rc, const T *rd, T *ccv, T *dcv) {
+            asm volatile("" ::: "memory");
+#pragma unroll
+            for (int u = 0; u < KC; ++u) {
+                ccv[u] = rc[C * KC + u];
+                dcv[u] = rd[C * KC + u];
+            }
+        }
+#define GTB_RT_CASES(F)                                                                                               \
+    F(0) F(1) F(2) F(3) F(4) F(5) F(6) F(7) F(8) F(9) F(10) F(11) F(12) F(13) F(14) F(15) F(16) F(17) F(18) F(19) F(20)   \
+        F(21) F(22) F(23) F(24) F(25) F(26) F(27) F(28) F(29) F(30) F(31) F(32) F(33) F(34) F(35) F(36) F(37) F(38) F(39) \
+            F(40) F(41)
+        static_assert(NCR <= 42, "extend GTB_RT_CASES");
+        static __device__ __forceinline__ void put(int c, T *rc, T *rd, const T *ccv, const T *dcv) {
+            switch (c) {
+#define GTB_RT_PUT(C)                          \
+    case C:                                    \
+        if constexpr (C < NCR)                 \
+            put_case<C>(rc, rd, ccv, dcv);     \
+        break;
+                GTB_RT_CASES(GTB_RT_PUT)
+#undef GTB_RT_PUT
+            default:
+                break;
+            }
+        }
+        static __device__ __forceinline__ void get(int c, const T *rc, const T *rd, T *ccv, T *dcv) {
+#pragma unroll
+            for (int u = 0; u < KC; ++u)
+                ccv[u] = dcv[u] = T(0);
+            switch (c) {
+#define GTB_RT_GET(C)                          \
+    case C:                                    \
+        if constexpr (C < NCR)                 \
+            get_case<C>(rc, rd, ccv, dcv);     \
+        break;
+                GTB_RT_CASES(GTB_RT_GET)
+#undef GTB_RT_GET
+            default:
+                break;
+            }
+        }
+#undef GTB_RT_CASES
+    };
+
+    template <class T, int KC>
+    constexpr int va_bstage_bytes() {
+        return (KC * 32 * (int)sizeof(T) + 127) / 128 * 128;
+    }
+
+    template <class T, int KC, int S, int SB, int RMAX>
+    __global__ void __launch_bounds__(32) va_resident_kernel(const __grid_constant__ va_maps maps, const va_params<T> p) {
+        using L = va_tma_layout<T>;
+        constexpr int es = L::es;
+        constexpr int fstage = L::template stage_bytes<KC>();
+        constexpr int bstage = va_bstage_bytes<T, KC>();
+        constexpr uint32_t ftx = KC * (4 * 32 + L::ww) * es;
+        constexpr uint32_t btx = KC * 32 * es;
+        constexpr int NCR = (RMAX + KC - 1) / KC + 1; // chunks of the register tier (+1: the chunk of level nk-1)
+        extern __shared__ __align__(128) unsigned char smem_all[];
+        unsigned char *fring = smem_all;
+        unsigned char *bring = smem_all + S * fstage;
+        uint64_t *ffull = reinterpret_cast<uint64_t *>(smem_all + S * fstage + SB * bstage);
+        uint64_t *bfull = ffull + S;
+        const int lane = threadIdx.x;
+        T *const ss = reinterpret_cast<T *>(smem_all + S * fstage + SB * bstage + 128) + lane; // [k][2][32]
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+                ptx::mbar_init(&ffull[s], 1);
+#pragma unroll
+            for (int s = 0; s < SB; ++s)
+                ptx::mbar_init(&bfull[s], 1);
             ptx::fence_barrier_init();
             ptx::prefetch_tensormap(&maps.us);
             ptx::prefetch_tensormap(&maps.up);
@@ -636,116 +792,184 @@ namespace {
             ptx::prefetch_tensormap(&maps.un);
             ptx::prefetch_tensormap(&maps.wc);
         }
-        __syncthreads();
+        __syncwarp();
         const int nk = p.nk;
-        const int nchunks = (nk + KC - 1) / KC;
-        if (warp == 1) {
-            // ------------------------------------------------------------ producer: lanes 0..4 issue one box each
-            uint32_t n = 0;
-            for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-                const int ti = item % p.tiles_i, j = item / p.tiles_i;
-                const int i0 = ti * 32;
-                for (int c = 0; c < nchunks; ++c, ++n) {
-                    const int s = n % S;
-                    if (n >= S)
-                        ptx::mbar_wait(&empty[s], (n / S - 1) & 1);
-                    if (lane == 0)
-                        ptx::mbar_expect_tx(&full[s], KC * (4 * 32 + L::ww) * L::es);
-                    __syncwarp();
-                    if (lane < 5)
-                        ptx::tma_load_3d(ring + s * stage_bytes + lane * (KC * 32 * L::es), &maps.us + lane, &full[s],
-                            i0, j, c * KC + (lane >= 3 ? 1 : 0));
-                }
-            }
-            return;
-        }
-        // ---------------------------------------------------------------- consumer: both sweeps of the strip
         const T dtr = p.dtr;
-        const uint64_t pol_keep = ptx::policy_evict_last();
-        T *slab = p.scratch + (int64_t)blockIdx.x * 32 + lane; // [k][NS][slots]
-        const int64_t sstride = p.slots;
-        uint32_t n = 0;
-        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const uint64_t pol_keep = ptx::policy_evict_last(), pol_stream = ptx::policy_evict_first();
+        const int gw = blockIdx.x, total = gridDim.x;
+        const int nchunks = (nk + KC - 1) / KC;
+        const int k_split = p.k_split, c_split = k_split / KC;
+        const int cb_top = (nk - 2) / KC; // backward chunk that holds level nk-2
+        uint32_t fi = 0, fw = 0, bi = 0, bw = 0; // ring uses so far (stage = n % depth, parity = (n / depth) & 1)
+
+        auto issue_f = [&](int i0, int j, int c) {
+            const int s = fi % S;
+            if (lane == 0) {
+                unsigned char *st = fring + s * fstage;
+                uint64_t *bar = &ffull[s];
+                ptx::mbar_expect_tx(bar, ftx);
+                ptx::tma_load_3d_hint(st, &maps.us, bar, i0, j, c * KC, pol_stream);
+                ptx::tma_load_3d_hint(st + KC * 32 * es, &maps.up, bar, i0, j, c * KC, pol_keep); // read again below
+                ptx::tma_load_3d_hint(st + 2 * KC * 32 * es, &maps.ut, bar, i0, j, c * KC, pol_stream);
+                ptx::tma_load_3d_hint(st + 3 * KC * 32 * es, &maps.un, bar, i0, j, c * KC + 1, pol_stream);
+                ptx::tma_load_3d_hint(st + 4 * KC * 32 * es, &maps.wc, bar, i0, j, c * KC + 1, pol_stream);
+            }
+            ++fi;
+        };
+        auto issue_b = [&](int i0, int j, int cb) {
+            const int s = bi % SB;
+            if (lane == 0) {
+                ptx::mbar_expect_tx(&bfull[s], btx);
+                ptx::tma_load_3d_hint(bring + s * bstage, &maps.up, &bfull[s], i0, j, cb * KC, pol_stream);
+            }
+            ++bi;
+        };
+        auto prime = [&](int item, T &u0) { // first S-1 forward chunks of a strip + u_stage(k = 0)
             const int ti = item % p.tiles_i, j = item / p.tiles_i;
-            const int i = ti * 32 + lane;
+            const int i0 = ti * 32;
+            for (int c = 0; c < S - 1 && c < nchunks; ++c)
+                issue_f(i0, j, c);
+            u0 = i0 + lane < p.ni ? __ldg(p.u_stage.ptr + i0 + lane + (int64_t)j * p.u_stage.sj) : T(0);
+        };
+        struct lvl {
+            T us, un, w0, w1, up, ut;
+        };
+        auto read_level = [&](const T *sd, int u) {
+            lvl v;
+            v.us = sd[u * 32 + lane], v.up = sd[(KC + u) * 32 + lane], v.ut = sd[(2 * KC + u) * 32 + lane];
+            v.un = sd[(3 * KC + u) * 32 + lane];
+            const T *wc = sd + 4 * KC * 32;
+            v.w0 = wc[u * L::ww + lane], v.w1 = wc[u * L::ww + lane + 1];
+            return v;
+        };
+
+        int item = gw;
+        T u0 = T(0);
+        if (item < p.items)
+            prime(item, u0);
+        for (; item < p.items; item += total) {
+            const int ti = item % p.tiles_i, j = item / p.tiles_i;
+            const int i0 = ti * 32, i = i0 + lane;
             const bool active = i < p.ni;
             va_state<T> st;
-            st.u_k = active ? __ldg(p.u_stage.ptr + i + (int64_t)j * p.u_stage.sj) : T(0);
+            st.u_k = u0;
             st.u_km1 = st.wsum_k = st.cc_prev = st.dc_prev = st.up_last = T(0);
-            for (int c = 0; c < nchunks; ++c, ++n) {
-                const int s = n % S;
-                ptx::mbar_wait(&full[s], (n / S) & 1);
-                const T *sd = reinterpret_cast<const T *>(ring + s * stage_bytes);
-                const T *wc = sd + 4 * KC * 32;
-                T us[KC], up[KC], ut[KC], un[KC], w0[KC], w1[KC];
+            T rc[NCR * KC], rd[NCR * KC]; // ccol / dcol of levels k_split .. (statically indexed: registers)
+            auto next_stage = [&](int c) { // refill the stage consumed in the previous iteration, wait for chunk c
+                if (c + S - 1 < nchunks)
+                    issue_f(i0, j, c + S - 1);
+                const int s = fw % S;
+                ptx::mbar_wait(&ffull[s], (fw / S) & 1);
+                ++fw;
+                return reinterpret_cast<const T *>(fring + s * fstage);
+            };
+            // ------------------------------------------------ forward sweep, shared-memory tier (all body levels but k = 0)
+            for (int c = 0; c < c_split; ++c) {
+                const T *sd = next_stage(c);
+                T *q = ss + (int64_t)c * (KC * 2 * 32);
 #pragma unroll
                 for (int u = 0; u < KC; ++u) {
-                    us[u] = sd[u * 32 + lane], up[u] = sd[(KC + u) * 32 + lane], ut[u] = sd[(2 * KC + u) * 32 + lane];
-                    un[u] = sd[(3 * KC + u) * 32 + lane];
-                    w0[u] = wc[u * L::ww + lane], w1[u] = wc[u * L::ww + lane + 1];
+                    lvl v = read_level(sd, u);
+                    T cc, dc;
+                    if (u == 0 && c == 0)
+                        va_forward_level<T>(0, 3, dtr, v.us, v.un, v.w0, v.w1, v.up, v.ut, st, cc, dc); // first, folded
+                    else
+                        va_forward_level<T>(1, 3, dtr, v.us, v.un, v.w0, v.w1, v.up, v.ut, st, cc, dc); // body, folded
+                    q[(u * 2) * 32] = cc;
+                    q[(u * 2 + 1) * 32] = dc;
                 }
-                __syncwarp();
-                if (lane == 0)
-                    ptx::mbar_arrive(&empty[s]); // the stage is in registers: hand it back before the math
+                __syncwarp(); // all lanes are done with the stage before lane 0 refills it
+            }
+            // ------------------------------------------------ forward sweep, register tier
+            // The chunk loop is NOT unrolled (48 unrolled levels overflow the instruction cache: the first version
+            // of this kernel stalled 1.5 cycles per issue on instruction fetch); a chunk's KC results are moved
+            // into the register arrays by a switch on the chunk number, whose cases index them statically.
+            const T *sd_last = nullptr;
+            for (int c = c_split; c < nchunks; ++c) {
+                const T *sd = next_stage(c);
+                sd_last = sd;
+                T ccv[KC], dcv[KC];
+                if (c != 0 && c < (nk - 1) / KC) {
+                    va_forward_body_chunk<T, KC>(
+                        dtr, st,
+                        [&](int u, T &us, T &un, T &w0, T &w1, T &up, T &ut) {
+                            lvl v = read_level(sd, u);
+                            us = v.us, un = v.un, w0 = v.w0, w1 = v.w1, up = v.up, ut = v.ut;
+                        },
+                        [&](int u, T cc, T dc, T) {
+                            ccv[u] = cc;
+                            dcv[u] = dc;
+                        });
+                } else {
 #pragma unroll
-                for (int u = 0; u < KC; ++u) {
-                    const int k = c * KC + u;
-                    if (k < nk) {
-                        T cc, dc;
-                        va_forward_level<T>(k, nk, dtr, us[u], un[u], w0[u], w1[u], up[u], ut[u], st, cc, dc);
+                    for (int u = 0; u < KC; ++u) {
+                        const int k = c * KC + u;
+                        ccv[u] = dcv[u] = T(0);
                         if (k < nk - 1) {
-                            T *q = slab + (int64_t)k * NS * sstride;
-                            ptx::st_hint(q, cc, pol_keep);
-                            ptx::st_hint(q + sstride, dc, pol_keep);
-                            if constexpr (NS == 3)
-                                ptx::st_hint(q + 2 * sstride, up[u], pol_keep);
+                            lvl v = read_level(sd, u);
+                            if (k == 0)
+                                va_forward_level<T>(0, 3, dtr, v.us, v.un, v.w0, v.w1, v.up, v.ut, st, ccv[u], dcv[u]);
+                            else
+                                va_forward_level<T>(1, 3, dtr, v.us, v.un, v.w0, v.w1, v.up, v.ut, st, ccv[u], dcv[u]);
                         }
                     }
                 }
+                reg_tier<T, KC, NCR>::put(c - c_split, rc, rd, ccv, dcv);
+                if (c != nchunks - 1)
+                    __syncwarp(); // the stage of the last chunk is read once more below
             }
-            // backward sweep (u_backward_function)
-            T *us_p = p.utens_stage.ptr + i + (int64_t)j * p.utens_stage.sj;
-            const T *up_p = p.u_pos.ptr + (active ? i : 0) + (int64_t)j * p.u_pos.sj;
-            const int64_t us_sk = p.utens_stage.sk, up_sk = p.u_pos.sk;
-            T data = st.dc_prev;
+            // ------------------------------------------------ last level (:70-83) from the stage of the last chunk
+            {
+                const int u = nk - 1 - (nchunks - 1) * KC;
+                T us = sd_last[u * 32 + lane], up = sd_last[(KC + u) * 32 + lane], ut = sd_last[(2 * KC + u) * 32 + lane];
+                T cc, dc;
+                va_forward_level<T>(2, 3, dtr, us, T(0), T(0), T(0), up, ut, st, cc, dc); // last, folded
+                __syncwarp();
+            }
+            // ------------------------------------------------ backward sweep (u_backward_function)
+            for (int n = 0; n < SB - 1 && cb_top - n >= 0; ++n)
+                issue_b(i0, j, cb_top - n);
+            if (item + total < p.items) // HBM keeps streaming while this warp sweeps back
+                prime(item + total, u0);
+            const int64_t us_sk = p.utens_stage.sk;
+            T *o = p.utens_stage.ptr + i + (int64_t)j * p.utens_stage.sj + (int64_t)(nk - 1) * us_sk;
+            T data = st.dc_prev; // last_level :118-121
             if (active)
-                us_p[(int64_t)(nk - 1) * us_sk] = dtr * (data - st.up_last);
-            constexpr int BU = 8;
-            struct back_level {
-                T cc, dc, up;
+                *o = dtr * (data - st.up_last);
+            auto next_bstage = [&](int cb) {
+                if (cb - (SB - 1) >= 0)
+                    issue_b(i0, j, cb - (SB - 1));
+                const int s = bw % SB;
+                ptx::mbar_wait(&bfull[s], (bw / SB) & 1);
+                ++bw;
+                return reinterpret_cast<const T *>(bring + s * bstage) + lane;
             };
-            auto load_back = [&](int k, back_level &v) {
-                if (k >= 0) {
-                    const T *q = slab + (int64_t)k * NS * sstride;
-                    v.cc = ptx::ld_hint(q, pol_keep);
-                    v.dc = ptx::ld_hint(q + sstride, pol_keep);
-                    if constexpr (NS == 3)
-                        v.up = ptx::ld_hint(q + 2 * sstride, pol_keep);
-                    else
-                        v.up = __ldg(up_p + k * up_sk);
-                }
-            };
-            back_level bcur[BU];
+            for (int cb = cb_top; cb >= c_split; --cb) { // register tier
+                const T *sb = next_bstage(cb);
+                T ccv[KC], dcv[KC];
+                reg_tier<T, KC, NCR>::get(cb - c_split, rc, rd, ccv, dcv);
 #pragma unroll
-            for (int u = 0; u < BU; ++u)
-                load_back(nk - 2 - u, bcur[u]);
-            for (int k0 = nk - 2; k0 >= 0; k0 -= BU) {
-                back_level bnxt[BU];
-#pragma unroll
-                for (int u = 0; u < BU; ++u)
-                    load_back(k0 - BU - u, bnxt[u]);
-#pragma unroll
-                for (int u = 0; u < BU; ++u) {
-                    const int k = k0 - u;
-                    if (k >= 0) { // body :111-116
-                        data = bcur[u].dc - bcur[u].cc * data;
+                for (int u = KC - 1; u >= 0; --u) { // body :111-116
+                    if (cb * KC + u <= nk - 2) {
+                        data = dcv[u] - ccv[u] * data;
+                        o -= us_sk;
                         if (active)
-                            us_p[(int64_t)k * us_sk] = dtr * (data - bcur[u].up);
+                            *o = dtr * (data - sb[u * 32]);
                     }
                 }
+                __syncwarp();
+            }
+            for (int cb = c_split - 1; cb >= 0; --cb) { // shared-memory tier
+                const T *sb = next_bstage(cb);
+                const T *q = ss + (int64_t)cb * (KC * 2 * 32);
 #pragma unroll
-                for (int u = 0; u < BU; ++u)
-                    bcur[u] = bnxt[u];
+                for (int u = KC - 1; u >= 0; --u) {
+                    data = q[(u * 2 + 1) * 32] - q[(u * 2) * 32] * data;
+                    o -= us_sk;
+                    if (active)
+                        *o = dtr * (data - sb[u * 32]);
+                }
+                __syncwarp();
             }
         }
     }
@@ -912,36 +1136,106 @@ namespace {
         return check_launch("va_tma_kernel");
     }
 
-    template <class T, int KC, int S, int NS>
-    int launch_va_fb(const va_maps &maps, const va_params<T> &p, int grid, cudaStream_t stream) {
-        using L = va_tma_layout<T>;
-        auto kernel = va_fb_kernel<T, KC, S, NS>;
-        const int smem = S * L::template stage_bytes<KC>() + (S + 4) * 8 + 2 * 2 * 32 * (int)sizeof(T);
+    template <class T, int KC, int S, int NB, int NS>
+    int launch_va_stream(const va_maps &maps, const va_params<T> &p, int grid, cudaStream_t stream) {
+        auto kernel = va_stream_kernel<T, KC, S, NB, NS>;
+        const int smem = va_stream_smem<T, KC, S>();
         static thread_local int done_dev = -1;
         if (done_dev != dev()->device) {
             GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             done_dev = dev()->device;
         }
-        kernel<<<grid, 64, smem, stream>>>(maps, p);
+        kernel<<<grid, 32, smem, stream>>>(maps, p);
         count_launch();
-        return check_launch("va_fb_kernel");
+        return check_launch("va_stream_kernel");
     }
 
-    template <class T, int KC, int S, int NS>
-    int launch_va_pc(const va_maps &maps, const va_params<T> &p, int grid, cudaStream_t stream) {
-        using L = va_tma_layout<T>;
-        auto kernel = va_pc_kernel<T, KC, S, NS>;
-        const int smem = S * L::template stage_bytes<KC>() + 2 * S * 8;
+    // va.unroll = levels per TMA stage (4 default, 8), va.stages = ring depth, va.threads (re-used) = register blocks
+    // of 8 levels the backward sweep keeps in flight (32 -> 1 ... 128 -> 4; default 4)
+    template <class T, int NS>
+    int dispatch_va_stream(const va_maps &maps, const va_params<T> &p, int kc, int stages, int nb, int grid,
+        cudaStream_t stream) {
+        if (kc == 8)
+            return launch_va_stream<T, 8, 3, 4, NS>(maps, p, grid, stream);
+        if (stages == 2) // shallow rings: room for 14 warps per SM (one round of strips)
+            return nb == 1 ? launch_va_stream<T, 4, 2, 1, NS>(maps, p, grid, stream)
+                           : launch_va_stream<T, 4, 2, 2, NS>(maps, p, grid, stream);
+        switch (nb) {
+        case 1:
+            return launch_va_stream<T, 4, 4, 1, NS>(maps, p, grid, stream);
+        case 2:
+            return launch_va_stream<T, 4, 4, 2, NS>(maps, p, grid, stream);
+        case 3:
+            return launch_va_stream<T, 4, 4, 3, NS>(maps, p, grid, stream);
+        default:
+            break;
+        }
+        switch (stages) {
+        case 3:
+            return launch_va_stream<T, 4, 3, 4, NS>(maps, p, grid, stream);
+        case 6:
+            return launch_va_stream<T, 4, 6, 4, NS>(maps, p, grid, stream);
+        default:
+            return launch_va_stream<T, 4, 4, 4, NS>(maps, p, grid, stream);
+        }
+    }
+
+    template <class T>
+    struct va_resident_cfg { // levels of ccol/dcol a thread keeps in registers
+        static constexpr int rmax = sizeof(T) == 8 ? 48 : 80;
+    };
+
+    template <class T, int KC, int S, int SB>
+    int va_resident_smem(int k_split) {
+        return S * va_tma_layout<T>::template stage_bytes<KC>() + SB * va_bstage_bytes<T, KC>() + 128 +
+               k_split * 2 * 32 * (int)sizeof(T);
+    }
+
+    template <class T, int KC, int S, int SB>
+    int launch_va_resident(const va_maps &maps, const va_params<T> &p, int grid, cudaStream_t stream) {
+        auto kernel = va_resident_kernel<T, KC, S, SB, va_resident_cfg<T>::rmax>;
+        const int smem = va_resident_smem<T, KC, S, SB>(p.k_split);
         static thread_local int done_dev = -1;
         if (done_dev != dev()->device) {
-            GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev()->max_smem_optin));
             GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             done_dev = dev()->device;
         }
-        kernel<<<grid, 64, smem, stream>>>(maps, p);
+        kernel<<<grid, 32, smem, stream>>>(maps, p);
         count_launch();
-        return check_launch("va_pc_kernel");
+        return check_launch("va_resident_kernel");
+    }
+
+    // Resident variant: kc/stages pick the ring shape; returns -1 if the shared-memory slab does not leave room for
+    // `wps` warps per SM (the caller then uses the L2-slab variant 3 unless variant 4 was requested explicitly).
+    template <class T>
+    int vert_adv_resident(va_params<T> &p, const options &o, device_state *d, const va_maps &maps, int kc, int wps,
+        int grid, bool forced, cudaStream_t stream) {
+        constexpr int rmax = va_resident_cfg<T>::rmax;
+        int k_split = p.nk - 1 - rmax;
+        k_split = k_split <= 0 ? 0 : ceil_div(k_split, kc) * kc;
+        p.k_split = k_split;
+        int smem;
+        const int stages = o.va_stages;
+        if (kc == 2)
+            smem = stages == 4 ? va_resident_smem<T, 2, 4, 3>(k_split) : va_resident_smem<T, 2, 5, 3>(k_split);
+        else
+            smem = stages == 2 ? va_resident_smem<T, 4, 2, 2>(k_split)
+                               : (stages == 4 ? va_resident_smem<T, 4, 4, 4>(k_split) : va_resident_smem<T, 4, 3, 2>(k_split));
+        if (smem > d->max_smem_optin)
+            return -1;
+        if (!forced && (int64_t)wps * (smem + 1024) > (int64_t)228 * 1024)
+            return -1;
+        int st = set_l2_persist(0);
+        if (st)
+            return st;
+        if (kc == 2)
+            return stages == 4 ? launch_va_resident<T, 2, 4, 3>(maps, p, grid, stream)
+                               : launch_va_resident<T, 2, 5, 3>(maps, p, grid, stream);
+        return stages == 2 ? launch_va_resident<T, 4, 2, 2>(maps, p, grid, stream)
+                           : (stages == 4 ? launch_va_resident<T, 4, 4, 4>(maps, p, grid, stream)
+                                          : launch_va_resident<T, 4, 3, 2>(maps, p, grid, stream));
     }
 
     // Builds the five tensor maps; false if any field is not TMA-addressable.
@@ -960,45 +1254,69 @@ namespace {
                one(&m.wc, p.wcon.ptr, p.wcon.sj, p.wcon.sk, ni + 1, L::ww, kc);
     }
 
+    // Persistent one-warp CTAs over the 32-column strips.  va.variant 2: per-warp TMA ring + per-thread slab loads;
+    // 3 (and auto): two-ring streaming kernel.  va.ctas_per_sm > 0: warps per SM, < 0: absolute grid size (tests).
     template <class T>
     int vert_adv_tma(va_params<T> &p, const options &o, device_state *d, cudaStream_t stream, bool *done) {
         *done = false;
-        const int kc = o.va_unroll == 8 ? 8 : (o.va_unroll == 2 ? 2 : 4);
+        const bool stream_variant = o.va_variant != 2;
+        const bool resident = o.va_variant == 4; // (auto = variant 3: measured fastest, see profiles/README.md)
+        int kc = o.va_unroll == 8 ? 8 : (o.va_unroll == 2 && !stream_variant ? 2 : 4);
+        if (resident) // auto: 2-level stages for fp64 (shared memory is what limits the warps per SM), 4 for fp32
+            kc = o.va_unroll == 2 ? 2 : (o.va_unroll == 4 ? 4 : (sizeof(T) == 8 ? 2 : 4));
         p.kc = kc;
         p.debug = o.va_debug;
         va_maps maps;
         if (!make_va_maps<T>(maps, p))
             return GTB_OK; // not addressable: the caller falls back to the register-prefetch kernel
-        const bool fb = o.va_variant == 3; // forward/backward warp pairs
-        const int wps = o.va_ctas_per_sm > 0 ? o.va_ctas_per_sm : (fb ? 4 : 7); // (forward) warps per SM
+        const int wps = o.va_ctas_per_sm > 0 ? o.va_ctas_per_sm : 7; // warps per SM
         const int64_t strips = (int64_t)p.tiles_i * p.nj;
         p.items = (int)strips;
         int grid = o.va_ctas_per_sm < 0 ? -o.va_ctas_per_sm : wps * d->sm_count;
         if (grid > strips)
             grid = (int)strips;
-        p.slots = (int64_t)grid * 32 * (fb ? 2 : 1);
+        if (resident) {
+            p.scratch = nullptr;
+            p.slots = 0;
+            p.persistent = 1;
+            int st = vert_adv_resident<T>(p, o, d, maps, kc, wps, grid, o.va_variant == 4, stream);
+            if (st >= 0) {
+                *done = true;
+                return st;
+            }
+            if (o.va_variant == 4)
+                return fail(GTB_ERR_ARG, "gtb_vert_adv: va.variant=4 needs more shared memory than an SM has for nk=%d", p.nk);
+            if (kc != 4) { // variant 3 streams 4-level stages
+                kc = 4;
+                p.kc = kc;
+                if (!make_va_maps<T>(maps, p))
+                    return GTB_OK;
+            }
+        }
         const bool save_upos = o.va_save_upos != 2;
-        p.scratch = static_cast<T *>(scratch((size_t)(save_upos ? 3 : 2) * p.nk * p.slots * sizeof(T)));
+        const int ns = save_upos ? 3 : 2;
+        int64_t slab_elems; // whole scratch
+        if (stream_variant) {
+            p.slots = (int64_t)p.nk * ns * 32; // one contiguous slab per warp
+            slab_elems = p.slots * grid;
+        } else {
+            p.slots = (int64_t)grid * 32;
+            slab_elems = (int64_t)ns * p.nk * p.slots;
+        }
+        p.scratch = static_cast<T *>(scratch((size_t)slab_elems * sizeof(T)));
         if (!p.scratch)
             return GTB_ERR_ALLOC;
         p.persistent = 1;
         *done = true;
         {
-            const int64_t slab = (int64_t)(save_upos ? 3 : 2) * p.nk * p.slots * (int64_t)sizeof(T);
+            const int64_t slab = slab_elems * (int64_t)sizeof(T);
             int st = set_l2_persist(o.l2_persist_mb < 0 ? slab : (int64_t)o.l2_persist_mb << 20);
             if (st)
                 return st;
         }
-        if (fb)
-            return save_upos ? launch_va_fb<T, 4, 4, 3>(maps, p, grid, stream)
-                             : launch_va_fb<T, 4, 4, 2>(maps, p, grid, stream);
-        if (o.va_variant == 4) {
-            if (kc == 8)
-                return save_upos ? launch_va_pc<T, 8, 3, 3>(maps, p, grid, stream)
-                                 : launch_va_pc<T, 8, 3, 2>(maps, p, grid, stream);
-            return save_upos ? launch_va_pc<T, 4, 4, 3>(maps, p, grid, stream)
-                             : launch_va_pc<T, 4, 4, 2>(maps, p, grid, stream);
-        }
+        if (stream_variant)
+            return save_upos ? dispatch_va_stream<T, 3>(maps, p, kc, o.va_stages, o.va_threads / 32, grid, stream)
+                             : dispatch_va_stream<T, 2>(maps, p, kc, o.va_stages, o.va_threads / 32, grid, stream);
         if (save_upos) {
             switch (kc) {
             case 2:

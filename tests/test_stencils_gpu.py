@@ -37,7 +37,7 @@ def gt():
 def reset_options(gt):
     yield
     for k in ("hd.variant", "hd.stages", "hd.ctas_per_sm", "va.variant", "va.threads", "va.unroll", "va.scratch",
-              "va.ctas_per_sm", "va.save_upos"):
+              "va.ctas_per_sm", "va.save_upos", "va.stages"):
         gt.lib.set_option(k, 0)
     gt.lib.set_option("va.hints", 1)
     gt.lib.set_option("copy.vec", 1)
@@ -175,9 +175,13 @@ def test_hori_diff_linearity(gt):
 
 
 # ------------------------------------------------------------------------------------- vertical advection
-VA_CONFIGS = [dict(), dict(variant=4), dict(variant=4, ctas_per_sm=-2, unroll=8), dict(variant=4, ctas_per_sm=-1, save_upos=2),
-              dict(variant=3), dict(variant=3, ctas_per_sm=-2), dict(variant=3, ctas_per_sm=-1, save_upos=2),
+VA_CONFIGS = [dict(), dict(variant=4), dict(variant=4, unroll=4), dict(variant=4, unroll=2, stages=4, ctas_per_sm=-2),
+              dict(variant=4, unroll=4, stages=2, ctas_per_sm=-1), dict(variant=4, ctas_per_sm=-3), dict(variant=3), dict(variant=3, ctas_per_sm=-2, unroll=8), dict(variant=3, ctas_per_sm=-1),
+              dict(variant=3, stages=3, ctas_per_sm=-3), dict(variant=3, stages=6), dict(variant=3, ctas_per_sm=-2, save_upos=2),
+              dict(variant=3, threads=32, ctas_per_sm=-1, save_upos=2), dict(variant=3, threads=64, ctas_per_sm=-2),
+              dict(variant=3, threads=96, save_upos=2), dict(variant=3, unroll=8, save_upos=2, ctas_per_sm=-1),
               dict(variant=2, unroll=8), dict(variant=2, unroll=2, ctas_per_sm=-2), dict(variant=2, ctas_per_sm=-1),
+              dict(variant=2, ctas_per_sm=-1, save_upos=2),
               dict(variant=1), dict(variant=1, threads=32, unroll=1), dict(variant=1, threads=128, unroll=2),
               dict(variant=1, threads=64, unroll=8, save_upos=2), dict(variant=1, scratch=2, threads=32, unroll=4),
               dict(variant=1, scratch=2, threads=64, unroll=2, hints=0, save_upos=2), dict(variant=1, hints=0, unroll=4),
@@ -213,16 +217,18 @@ def test_vert_adv_golden(gt, oracle, golden, name, cfg):
     assert rel_err(out32[inner], g["out_ref_f32"][inner]) < 1e-4  # fp32 Thomas: cancellation in dtr*(x - u_pos)
 
 
-@pytest.mark.parametrize("size,alignment", [((1, 1, 2), 1), ((33, 2, 3), 1), ((70, 9, 80), 128), ((12, 33, 61), 128)])
+@pytest.mark.parametrize("size,alignment", [((1, 1, 2), 1), ((33, 2, 3), 1), ((70, 9, 80), 128), ((12, 33, 61), 128),
+                                            ((40, 3, 2), 128), ((37, 4, 5), 128), ((64, 2, 9), 128), ((5, 5, 4), 128),
+                                            ((33, 3, 3), 128), ((96, 2, 8), 128)])
 def test_vert_adv_random_bit_exact(gt, oracle, size, alignment):
     ni, nj, nk = size
     rng = np.random.default_rng(ni + 10 * nj + 100 * nk)
     shape = (nk, nj + 6, ni + 6)
     arrs = [rng.uniform(5, 9, shape), rng.uniform(5, 9, shape), rng.uniform(-3e-4, 3e-4, shape),
             rng.uniform(5, 9, shape), rng.uniform(-1e-5, 1e-5, shape)]
-    for cfg in (dict(), dict(variant=2, ctas_per_sm=-2), dict(variant=3, ctas_per_sm=-3), dict(variant=4, ctas_per_sm=-3), dict(variant=1), dict(variant=1, scratch=2, threads=32),
-                dict(variant=1, ctas_per_sm=-2, threads=32)):
-        for k in ("variant", "threads", "unroll", "scratch", "ctas_per_sm", "save_upos"):
+    for cfg in (dict(), dict(variant=4, ctas_per_sm=-2), dict(variant=4, unroll=4, ctas_per_sm=-1), dict(variant=2, ctas_per_sm=-2), dict(variant=3, ctas_per_sm=-3), dict(variant=3, ctas_per_sm=-1, unroll=8),
+                dict(variant=3, ctas_per_sm=-2, threads=32, save_upos=2), dict(variant=3, threads=64, save_upos=2), dict(variant=1), dict(variant=1, scratch=2, threads=32), dict(variant=1, ctas_per_sm=-2, threads=32)):
+        for k in ("variant", "threads", "unroll", "scratch", "ctas_per_sm", "save_upos", "stages"):
             gt.lib.set_option("va." + k, 0)
         set_va(gt, cfg)
         try:
@@ -246,6 +252,31 @@ def test_vert_adv_full_size(gt, oracle):
     out, _ = run_va(gt, arrs, 0.15)
     inner = (slice(None), slice(3, -3), slice(3, -3))
     assert np.array_equal(out[inner], oracle.vert_adv(*arrs, 0.15)[inner])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("nk", [49, 50, 51, 78, 79, 97, 200, 700])
+def test_vert_adv_tall_columns(gt, oracle, nk, dtype):
+    """Columns taller than the register tier: the shared-memory tier grows with nk, and beyond what an SM holds the
+    auto variant falls back to the L2-slab kernel (an explicit va.variant=4 is refused)."""
+    ni, nj = 45, 3
+    rng = np.random.default_rng(nk)
+    shape = (nk, nj + 6, ni + 6)
+    arrs = [rng.uniform(5, 9, shape).astype(dtype), rng.uniform(5, 9, shape).astype(dtype),
+            rng.uniform(-3e-4, 3e-4, shape).astype(dtype), rng.uniform(5, 9, shape).astype(dtype),
+            rng.uniform(-1e-5, 1e-5, shape).astype(dtype)]
+    want = oracle.vert_adv(*arrs, 0.15)
+    inner = (slice(None), slice(3, -3), slice(3, -3))
+    for cfg in (dict(), dict(variant=4), dict(variant=4, unroll=4), dict(variant=3), dict(variant=3, threads=32, stages=2, ctas_per_sm=-2)):
+        for k in ("variant", "unroll", "stages", "ctas_per_sm"):
+            gt.lib.set_option("va." + k, 0)
+        set_va(gt, cfg)
+        try:
+            out, _ = run_va(gt, arrs, 0.15)
+        except gt.lib.GtbError as e:
+            assert cfg.get("variant") == 4 and nk == 700 and e.status == gt.lib.GTB_ERR_ARG
+            continue
+        assert np.array_equal(out[inner], want[inner]), cfg
 
 
 def test_vert_adv_rejects_single_level(gt):

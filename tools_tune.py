@@ -81,16 +81,15 @@ def main():
             for f in st:
                 f.const_target_tensor()
         combos = []
-        for wps, save, persist in itertools.product((2, 3, 4, 5, 6, 7), (1, 2), (-1, 0)):
-            combos.append(dict(variant=3, unroll=4, ctas_per_sm=wps, save_upos=save, persist=persist))
-        for kc, wps, save, persist in itertools.product((4,), (6, 7, 8), (1, 2), (-1,)):
-            combos.append(dict(variant=2, unroll=kc, ctas_per_sm=wps, save_upos=save, persist=persist))
-        for threads, unroll, ctas, save in itertools.product((64,), (8,), (0, 7), (1, 2)):
-            combos.append(dict(variant=1, scratch=1, threads=threads, unroll=unroll, ctas_per_sm=ctas, save_upos=save,
-                               persist=-1))
+        for wps, stages in itertools.product((5, 6, 7, 8), (0, 3, 5)):
+            combos.append(dict(variant=5, unroll=4, ctas_per_sm=wps, stages=stages, persist=-1))
+        combos.append(dict(variant=5, unroll=4, ctas_per_sm=7, stages=0, persist=0))
+        combos.append(dict(variant=4, unroll=4, ctas_per_sm=7, stages=2, persist=-1))
+        combos.append(dict(variant=3, unroll=4, ctas_per_sm=7, threads=128, stages=4, save_upos=1, persist=-1))
+        combos.append(dict(variant=2, unroll=4, ctas_per_sm=7, save_upos=1, persist=-1))
         results = []
         for cfg in combos:
-            for k in ("variant", "scratch", "threads", "unroll", "ctas_per_sm", "save_upos"):
+            for k in ("variant", "scratch", "threads", "unroll", "ctas_per_sm", "save_upos", "stages"):
                 _lib.set_option("va." + k, cfg.get(k, 0))
             _lib.set_option("l2.persist_mb", cfg["persist"])
             try:
