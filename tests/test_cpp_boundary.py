@@ -51,3 +51,91 @@ def test_b200_tag_through_gridtools_frontend():
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
     assert "ALL PASSED" in r.stdout
     assert r.stdout.count(" ok ") >= 17
+
+
+# ------------------------------------------------------------------------------------------------ gcl (C++ class)
+GCL_BIN = os.path.join(ROOT, "tests", "_build", "gcl_regression")
+
+GCL_TU = r"""
+#include <gtb200/gcl/halo_exchange.hpp>
+namespace gcl = gtb200::gcl;
+int f(double *a, double *b) {
+    gcl::proc_grid grid(gcl::proc_grid::dims_create(8), {false, true, false}, 3);
+    gcl::halo_exchange_dynamic_ut<gcl::layout_map<2, 1, 0>, gcl::layout_map<0, 1, 2>, double> he(
+        {false, true, false}, grid, gcl::file_channel("/tmp", "x", 3, 8));
+    he.add_halo<0>(2, 2, 2, 65, 80);
+    he.add_halo<1>(gcl::halo_descriptor{2, 2, 2, 33, 36});
+    he.add_halo<2>(0, 0, 0, 79, 80);
+    he.setup(2);
+    he.pack(a, b); he.exchange(); he.unpack(a, b);
+    he.post_receives(); he.do_sends(); he.start_exchange(); he.wait();
+    int i, j, k; he.comm().coords(i, j, k);
+    return he.comm().proc(0, 1, 0) + i;
+}
+"""
+
+
+def test_gcl_header_is_plain_host_code(tmp_path):
+    """include/gtb200/gcl/halo_exchange.hpp needs nothing but the C ABI header and the standard library."""
+    src = tmp_path / "tu.cpp"
+    src.write_text(GCL_TU)
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I" + os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_gcl_proc_grid_matches_python_host():
+    """The C++ proc_grid (coords, proc with periodicity, dims_create) against the Python mirror that the oracle
+    pins (tests/test_gcl_host.py), through a tiny g++-built probe."""
+    import itertools
+    import tempfile
+    from gridtools_b200 import gcl
+    prog = r"""
+#include <cstdio>
+#include <gtb200/gcl/halo_exchange.hpp>
+int main() {
+    namespace gcl = gtb200::gcl;
+    for (int n : {1, 2, 4, 6, 8, 12}) { auto d = gcl::proc_grid::dims_create(n); std::printf("D %d %d %d %d\n", n, d[0], d[1], d[2]); }
+    int dims[2][3] = {{2, 4, 1}, {3, 2, 2}};
+    bool pers[3][3] = {{false, false, false}, {true, false, true}, {true, true, true}};
+    for (auto &dm : dims) for (auto &pr : pers) {
+        int size = dm[0] * dm[1] * dm[2];
+        for (int r = 0; r < size; ++r) {
+            gcl::proc_grid g({dm[0], dm[1], dm[2]}, {pr[0], pr[1], pr[2]}, r);
+            for (int i = -1; i <= 1; ++i) for (int j = -1; j <= 1; ++j) for (int k = -1; k <= 1; ++k)
+                std::printf("P %d %d %d %d %d %d %d %d %d %d %d\n", dm[0], dm[1], dm[2], (int)pr[0], (int)pr[1], (int)pr[2], r, i, j, k, g.proc(i, j, k));
+        }
+    }
+}
+"""
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "p.cpp")
+        open(src, "w").write(prog)
+        exe = os.path.join(d, "p")
+        r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), src, "-o", exe],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+        out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.splitlines()
+    n_checked = 0
+    for line in out:
+        t = line.split()
+        v = [int(x) for x in t[1:]]
+        if t[0] == "D":
+            assert tuple(v[1:]) == gcl.ProcGrid.dims_create(v[0]), line
+        else:
+            g = gcl.ProcGrid(v[0:3], v[3:6], v[6])
+            assert g.proc(*v[7:10]) == v[10], line
+        n_checked += 1
+    assert n_checked > 1000
+
+
+@pytest.mark.gpu
+def test_gcl_class_exchanges_like_the_reference_test():
+    """tests/_build/gcl_regression: the C++ class with ranks as threads on one GPU, coordinate-stamp check of
+    test_halo_exchange_3D.cpp:66-123 (expectation computed from global coordinates only)."""
+    if not os.path.exists(GCL_BIN):
+        pytest.skip("tests/_build/gcl_regression not built (make -C tests/cpp)")
+    r = subprocess.run([GCL_BIN], capture_output=True, text=True, timeout=600)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+    assert "ALL PASSED" in r.stdout and r.stdout.count(" ok ") >= 7

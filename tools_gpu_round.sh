@@ -6,11 +6,11 @@ nproc >> gpurun_out/gpu.txt
 STEP=${1:-all}
 if [ "$STEP" = all ] || [ "$STEP" = test ]; then
   : > gpurun_out/pytest_gpu.log
-  for f in tests/test_stencils_gpu.py tests/test_halo_gpu.py; do   # one process per file: a fault cannot cascade
+  for f in tests/test_stencils_gpu.py tests/test_halo_gpu.py tests/test_cpp_boundary.py; do   # one process per file: a fault cannot cascade
     timeout 900 python -m pytest $f -m gpu -q --maxfail=10 -p no:cacheprovider --timeout=300 >> gpurun_out/pytest_gpu.log 2>&1
     echo "pytest $f exit $?" >> gpurun_out/pytest_gpu.log
   done
-  grep -E "passed|failed|exit" gpurun_out/pytest_gpu.log | tail -6
+  grep -E "passed|failed|exit" gpurun_out/pytest_gpu.log | tail -8
 fi
 if [ "$STEP" = sanitize ]; then
   timeout 900 compute-sanitizer --tool memcheck python tools_sanitize.py > gpurun_out/sanitize.log 2>&1
@@ -35,6 +35,8 @@ if [ "$STEP" = all ] || [ "$STEP" = ncu ]; then
       python bench.py --steps 5 --warmup 3 --no-extras > gpurun_out/ncu_launches.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:va_ -s 3 -c 2 -f -o gpurun_out/prof_va \
       python bench.py --steps 5 --warmup 3 --no-extras > gpurun_out/ncu_va.log 2>&1
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_hd.csv \
+      python bench.py --stencil hori_diff --steps 5 --warmup 3 --no-extras > gpurun_out/ncu_launches_hd.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:hd_ -s 3 -c 2 -f -o gpurun_out/prof_hd \
       python bench.py --stencil hori_diff --steps 5 --warmup 3 --no-extras > gpurun_out/ncu_hd.log 2>&1
   ls -la gpurun_out

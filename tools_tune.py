@@ -81,12 +81,19 @@ def main():
             for f in st:
                 f.const_target_tensor()
         combos = []
-        for wps, stages in itertools.product((5, 6, 7, 8), (0, 3, 5)):
-            combos.append(dict(variant=5, unroll=4, ctas_per_sm=wps, stages=stages, persist=-1))
-        combos.append(dict(variant=5, unroll=4, ctas_per_sm=7, stages=0, persist=0))
-        combos.append(dict(variant=4, unroll=4, ctas_per_sm=7, stages=2, persist=-1))
-        combos.append(dict(variant=3, unroll=4, ctas_per_sm=7, threads=128, stages=4, save_upos=1, persist=-1))
+        for wps, nb, stages, save in itertools.product((6, 7, 8), (1, 2, 4), (4,), (1, 2)):
+            combos.append(dict(variant=3, unroll=4, ctas_per_sm=wps, threads=32 * nb, stages=stages, save_upos=save, persist=-1))
+        for stages in (3, 6):
+            combos.append(dict(variant=3, unroll=4, ctas_per_sm=7, threads=128, stages=stages, save_upos=1, persist=-1))
+        combos.append(dict(variant=3, unroll=8, ctas_per_sm=5, stages=0, save_upos=1, persist=-1))
+        combos.append(dict(variant=3, unroll=8, ctas_per_sm=7, stages=0, save_upos=1, persist=-1))
+        combos.append(dict(variant=3, unroll=4, ctas_per_sm=7, threads=128, stages=4, save_upos=1, persist=0))
+        combos.append(dict(variant=3, unroll=4, ctas_per_sm=14, threads=32, stages=2, save_upos=2, persist=-1))
+        for kc, stages in ((2, 5), (2, 4), (4, 3), (4, 2)):
+            combos.append(dict(variant=4, unroll=kc, ctas_per_sm=7, stages=stages, persist=-1))
         combos.append(dict(variant=2, unroll=4, ctas_per_sm=7, save_upos=1, persist=-1))
+        combos.append(dict(variant=2, unroll=4, ctas_per_sm=7, save_upos=2, persist=-1))
+        combos.append(dict(variant=1, scratch=1, threads=64, unroll=8, ctas_per_sm=0, save_upos=1, persist=-1))
         results = []
         for cfg in combos:
             for k in ("variant", "scratch", "threads", "unroll", "ctas_per_sm", "save_upos", "stages"):
