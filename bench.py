@@ -20,6 +20,7 @@ section 8d) / CUDA-event kernel time against the measured HBM peak; `cpu_baselin
 cpu_kfirst backends (oracle/_ref/libgtref.so, built from the unmodified reference headers) timed on this host.
 """
 import argparse
+import ctypes as C
 import json
 import os
 import statistics
@@ -261,33 +262,32 @@ def b200_arm(args):
 
     exch_index = 2 if name == "vert_adv" else 0
 
-    def run_stencil(s):
-        st = sets[s % n_sets]
-        if name == "vert_adv":
-            stencil.vertical_advection_dycore(*st, dtr)
-        else:
-            stencil.horizontal_diffusion(*st)
+    # Pre-marshalled calls (stencil.plan / halo_exchange.bind): a step is 27-64 us of device time, per-call ctypes
+    # marshalling would bound it from the host.
+    comp = torch.cuda.current_stream()
+    comm = torch.cuda.Stream(priority=-1) if he is not None else None
+    comp_h = C.c_void_p(comp.cuda_stream)
+    comm_h = C.c_void_p(comm.cuda_stream) if comm is not None else None
+    if name == "vert_adv":
+        stencil_plans = [stencil.plan("vertical_advection_dycore", *st, dtr_stage=dtr) for st in sets]
+    else:
+        stencil_plans = [stencil.plan("horizontal_diffusion", *st) for st in sets]
+    exch_plans = [he.bind(st[exch_index]) for st in sets] if he is not None else None
 
-    def run_exchange(s):
-        f = sets[s % n_sets][exch_index]
-        he.pack(f)
-        he.exchange()
-        he.unpack(f)
+    def run_stencil(s):
+        stencil_plans[s % n_sets](comp_h)
 
     # N > 1: the halo exchange of step s+1 (comm stream, high priority) overlaps the stencil of step s (compute
     # stream).  exchange(s+1) touches field set (s+1) % n_sets, last read by stencil(s+1-n_sets): event dependency.
-    comp = torch.cuda.current_stream()
-    comm = torch.cuda.Stream(priority=-1) if he is not None else None
     total_steps = max(args.warmup, 3) + args.steps
-    ev_x = [torch.cuda.Event() for _ in range(total_steps + 2)]
-    ev_c = [torch.cuda.Event() for _ in range(total_steps + 2)]
+    ev_x = [torch.cuda.Event() for _ in range(total_steps + 2)] if he is not None else None
+    ev_c = [torch.cuda.Event() for _ in range(total_steps + 2)] if he is not None else None
 
     def issue_exchange(s):
-        with torch.cuda.stream(comm):
-            if s - n_sets >= 0:
-                comm.wait_event(ev_c[s - n_sets])
-            run_exchange(s)
-            ev_x[s].record(comm)
+        if s - n_sets >= 0:
+            comm.wait_event(ev_c[s - n_sets])
+        exch_plans[s % n_sets](comm_h)
+        ev_x[s].record(comm)
 
     def step(s):
         if he is not None:

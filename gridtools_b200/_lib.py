@@ -67,6 +67,7 @@ _SIG = {
     "gtb_halo_wait": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gtb_halo_unpack": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
     "gtb_halo_wait_unpack": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
+    "gtb_halo_exchange": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
     "gtb_halo_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "gtb_halo_next_epoch": (C.c_int, [C.c_void_p]),
 }

@@ -152,6 +152,18 @@ namespace gtb {
                 "l"(policy)
                 : "memory");
         }
+        // True in exactly one (the lowest active) lane of a converged warp.  Guarding TMA issue with this instead of
+        // `lane == 0` tells ptxas that a single thread executes the region, so UTMALDG's uniform operands need no
+        // per-lane election loop.
+        __device__ __forceinline__ bool elect_one() {
+            uint32_t pred;
+            asm volatile(
+                "{\n\t.reg .pred P;\n\t"
+                "elect.sync _|P, 0xffffffff;\n\t"
+                "selp.u32 %0, 1, 0, P;\n\t}"
+                : "=r"(pred));
+            return pred != 0;
+        }
         // 1-D bulk copy global -> shared (contiguous, 16-byte aligned address and size), completion on an mbarrier.
         __device__ __forceinline__ void bulk_load_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar,
             uint64_t policy) {

@@ -622,6 +622,16 @@ GTB_API int gtb_halo_wait_unpack(gtb_halo *h, void *const *fields, int n_fields,
     return run_xfer<false>(h, fields, n_fields, bufs, as_stream(stream), 2);
 }
 
+GTB_API int gtb_halo_exchange(gtb_halo *h, void *const *fields, int n_fields, void *stream) {
+    int st = gtb_halo_pack_send(h, fields, n_fields, stream);
+    if (st)
+        return st;
+    st = gtb_halo_wait_unpack(h, fields, n_fields, stream);
+    if (st)
+        return st;
+    return gtb_halo_next_epoch(h);
+}
+
 GTB_API int gtb_halo_error(gtb_halo *h, int *code) {
     if (!h || !code)
         return fail(GTB_ERR_ARG, "gtb_halo_error: null argument");

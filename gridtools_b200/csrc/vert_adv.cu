@@ -543,13 +543,15 @@ namespace {
         T *const slab = p.scratch + (int64_t)gw * p.slots + lane; // p.slots = elements per warp slab: nk*NS*32
         const int nchunks = (nk + KC - 1) / KC;
         const int c_tail = (nk - 1) / KC; // first forward chunk that needs per-level checks (holds level nk-1)
-        uint32_t fi = 0, fw = 0;          // ring uses so far (stage = n % S, parity = (n / S) & 1)
+        int f_issue = 0, f_wait = 0; // ring stage the producer fills next / the consumer waits for next
+        uint32_t f_phase = 0;        // parity of the consumer's current trip around the ring
 
         // One lane issues the five boxes of a forward stage back to back (UTMALDG takes uniform operands: letting
         // five lanes issue one box each only makes the compiler serialise them in an election loop).
         auto issue_f = [&](int i0, int j, int c) {
-            const int s = fi % S;
-            if (lane == 0) {
+            const int s = f_issue;
+            f_issue = f_issue + 1 == S ? 0 : f_issue + 1;
+            if (ptx::elect_one()) {
                 unsigned char *st = fring + s * fstage;
                 uint64_t *bar = &ffull[s];
                 ptx::mbar_expect_tx(bar, ftx);
@@ -559,7 +561,6 @@ namespace {
                 ptx::tma_load_3d(st + 3 * KC * 32 * es, &maps.un, bar, i0, j, c * KC + 1); // read one level up
                 ptx::tma_load_3d(st + 4 * KC * 32 * es, &maps.wc, bar, i0, j, c * KC + 1);
             }
-            ++fi;
         };
         auto prime = [&](int item, T &u0) { // first S-1 forward chunks of a strip + u_stage(k = 0)
             const int ti = item % p.tiles_i, j = item / p.tiles_i;
@@ -585,9 +586,12 @@ namespace {
             for (int c = 0; c < nchunks; ++c) {
                 if (c + S - 1 < nchunks) // refill the stage consumed in the previous iteration
                     issue_f(i0, j, c + S - 1);
-                const int s = fw % S;
-                ptx::mbar_wait(&ffull[s], (fw / S) & 1);
-                ++fw;
+                const int s = f_wait;
+                ptx::mbar_wait(&ffull[s], f_phase);
+                if (++f_wait == S) {
+                    f_wait = 0;
+                    f_phase ^= 1;
+                }
                 const T *sd = reinterpret_cast<const T *>(fring + s * fstage);
                 const T *wc = sd + 4 * KC * 32;
                 if (c != 0 && c < c_tail) {
@@ -800,11 +804,13 @@ namespace {
         const int nchunks = (nk + KC - 1) / KC;
         const int k_split = p.k_split, c_split = k_split / KC;
         const int cb_top = (nk - 2) / KC; // backward chunk that holds level nk-2
-        uint32_t fi = 0, fw = 0, bi = 0, bw = 0; // ring uses so far (stage = n % depth, parity = (n / depth) & 1)
+        int f_issue = 0, f_wait = 0, b_issue = 0, b_wait = 0; // ring stages: producer fills next / consumer waits for next
+        uint32_t f_phase = 0, b_phase = 0;                    // parity of the consumer's current trip around each ring
 
         auto issue_f = [&](int i0, int j, int c) {
-            const int s = fi % S;
-            if (lane == 0) {
+            const int s = f_issue;
+            f_issue = f_issue + 1 == S ? 0 : f_issue + 1;
+            if (ptx::elect_one()) {
                 unsigned char *st = fring + s * fstage;
                 uint64_t *bar = &ffull[s];
                 ptx::mbar_expect_tx(bar, ftx);
@@ -814,15 +820,14 @@ namespace {
                 ptx::tma_load_3d_hint(st + 3 * KC * 32 * es, &maps.un, bar, i0, j, c * KC + 1, pol_stream);
                 ptx::tma_load_3d_hint(st + 4 * KC * 32 * es, &maps.wc, bar, i0, j, c * KC + 1, pol_stream);
             }
-            ++fi;
         };
         auto issue_b = [&](int i0, int j, int cb) {
-            const int s = bi % SB;
-            if (lane == 0) {
+            const int s = b_issue;
+            b_issue = b_issue + 1 == SB ? 0 : b_issue + 1;
+            if (ptx::elect_one()) {
                 ptx::mbar_expect_tx(&bfull[s], btx);
                 ptx::tma_load_3d_hint(bring + s * bstage, &maps.up, &bfull[s], i0, j, cb * KC, pol_stream);
             }
-            ++bi;
         };
         auto prime = [&](int item, T &u0) { // first S-1 forward chunks of a strip + u_stage(k = 0)
             const int ti = item % p.tiles_i, j = item / p.tiles_i;
@@ -858,9 +863,12 @@ namespace {
             auto next_stage = [&](int c) { // refill the stage consumed in the previous iteration, wait for chunk c
                 if (c + S - 1 < nchunks)
                     issue_f(i0, j, c + S - 1);
-                const int s = fw % S;
-                ptx::mbar_wait(&ffull[s], (fw / S) & 1);
-                ++fw;
+                const int s = f_wait;
+                ptx::mbar_wait(&ffull[s], f_phase);
+                if (++f_wait == S) {
+                    f_wait = 0;
+                    f_phase ^= 1;
+                }
                 return reinterpret_cast<const T *>(fring + s * fstage);
             };
             // ------------------------------------------------ forward sweep, shared-memory tier (all body levels but k = 0)
@@ -939,9 +947,12 @@ namespace {
             auto next_bstage = [&](int cb) {
                 if (cb - (SB - 1) >= 0)
                     issue_b(i0, j, cb - (SB - 1));
-                const int s = bw % SB;
-                ptx::mbar_wait(&bfull[s], (bw / SB) & 1);
-                ++bw;
+                const int s = b_wait;
+                ptx::mbar_wait(&bfull[s], b_phase);
+                if (++b_wait == SB) {
+                    b_wait = 0;
+                    b_phase ^= 1;
+                }
                 return reinterpret_cast<const T *>(bring + s * bstage) + lane;
             };
             for (int cb = cb_top; cb >= c_split; --cb) { // register tier

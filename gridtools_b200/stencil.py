@@ -118,6 +118,39 @@ def prepare_tracers(outs, ins, rho: DataStore, grid: Grid = None):
     _lib.check(_lib.lib().gtb_prepare_tracers_f64(fo, fi, n, C.byref(fr), g.ni, g.nj, g.nk, _stream()))
 
 
+def plan(name, *stores, grid: Grid = None, **scalars):
+    """Pre-marshalled call: `f = plan("horizontal_diffusion", inp, coeff, out); f()` enqueues the same launch as
+    `horizontal_diffusion(inp, coeff, out)` on torch's current stream (or `f(stream_handle)`), with the argument
+    structures built once -- for time loops whose step is a few tens of microseconds, where ctypes marshalling would
+    otherwise bound the step time.  The stores must stay alive and keep their device buffers."""
+    if name == "horizontal_diffusion":
+        inp, coeff, out = stores
+        g = _grid_of(inp, grid)
+        dt = _same_dtype(inp, coeff, out)
+        fn = _lib.lib().gtb_hori_diff_f64 if dt.itemsize == 8 else _lib.lib().gtb_hori_diff_f32
+        f = [inp.field(True, g.origin), coeff.field(True, g.origin), out.field(False, g.origin)]
+        args = tuple(C.byref(x) for x in f) + (g.ni, g.nj, g.nk)
+    elif name == "vertical_advection_dycore":
+        utens_stage, u_stage, wcon, u_pos, utens = stores
+        g = _grid_of(utens_stage, grid)
+        dt = _same_dtype(*stores)
+        dtr = scalars["dtr_stage"]
+        if dt.itemsize == 8:
+            fn, sc = _lib.lib().gtb_vert_adv_f64, C.c_double(dtr)
+        else:
+            fn, sc = _lib.lib().gtb_vert_adv_f32, C.c_float(dtr)
+        f = [utens_stage.field(False, g.origin)] + [s.field(True, g.origin) for s in (u_stage, wcon, u_pos, utens)]
+        args = tuple(C.byref(x) for x in f) + (sc, g.ni, g.nj, g.nk)
+    else:
+        raise ValueError("plan(): unknown spec %r" % (name,))
+    chk = _lib.check
+
+    def run(stream_handle=None):
+        chk(fn(*args, stream_handle if stream_handle is not None else _stream()))
+    run.keepalive = (f, stores)
+    return run
+
+
 def as_numpy_interior(ds: DataStore, grid: Grid = None):
     g = _grid_of(ds, grid)
     a = ds.const_host_view()

@@ -173,6 +173,10 @@ int gtb_halo_unpack(gtb_halo *h, void *const *fields, int n_fields, void *stream
  * message (needs connect).  Together with gtb_halo_pack_send an exchange is two launches and no host synchronisation,
  * against up to 12 x n_fields launches, a cudaDeviceSynchronize and 2 x 26 MPI calls in the reference. */
 int gtb_halo_wait_unpack(gtb_halo *h, void *const *fields, int n_fields, void *stream);
+/* pack_send + wait_unpack + next_epoch in one call (two launches on `stream`): the whole
+ * pack() / exchange() / unpack() sequence of halo_exchange_dynamic_ut (gcl/halo_exchange.hpp:250-304) for hosts that do
+ * not need the phases separately. */
+int gtb_halo_exchange(gtb_halo *h, void *const *fields, int n_fields, void *stream);
 /* Synchronises the device and reports whether a wait timed out: *code = 0 if not, else 1 + direction that never
  * arrived.  (Halo_Exchange_3D has no error path: a lost MPI peer hangs in MPI_Wait.) */
 int gtb_halo_error(gtb_halo *h, int *code);

@@ -117,3 +117,29 @@ def test_too_many_fields_is_an_error(gt):
     assert gt.lib.lib().gtb_halo_pack(he._h, arr, 2, None) == gt.lib.GTB_ERR_ARG
     assert gt.lib.lib().gtb_halo_pack_send(he._h, arr, 1, None) == gt.lib.GTB_ERR_STATE  # not connected yet
     he.close()
+
+
+def test_bound_exchange_single_call(gt, oracle):
+    """halo_exchange.bind(): pack + exchange + unpack as ONE pre-marshalled C call (gtb_halo_exchange).  A periodic
+    1x1x1 grid is its own neighbour in every direction, so the whole exchange can run in a single stream."""
+    import ctypes as C
+    dims, periodic, n_fields = (1, 1, 1), (1, 1, 1), 3
+    grid = gt.gcl.ProcGrid(dims, periodic, 0)
+    he = gt.gcl.halo_exchange_dynamic_ut(periodic, grid, np.float64, comm=None, transport="p2p")
+    for d in range(3):
+        he.add_halo(d, *HALOS[d])
+    he.setup(n_fields)
+    gt.gcl.connect_local([he])
+    fields = [stamp(he.plan, grid, f, np.float64) for f in range(n_fields)]
+    dev = [gt.torch.from_numpy(a.copy()).cuda() for a in fields]
+    run = he.bind(*[t.data_ptr() for t in dev])
+    stream = C.c_void_p(gt.torch.cuda.current_stream().cuda_stream)
+    for _ in range(3):  # three epochs through the double-buffered arenas
+        run(stream)
+    gt.torch.cuda.synchronize()
+    assert he.check() == 0
+    for _ in range(3):
+        oracle.halo_exchange_all(HALOS, dims, periodic, [fields], 8)
+    for f in range(n_fields):
+        assert np.array_equal(fields[f], dev[f].cpu().numpy())
+    he.close()

@@ -329,6 +329,31 @@ def test_prepare_tracers(gt, oracle, n_tracers, shape, alignment):
         assert np.array_equal(got.to_numpy(), want)
 
 
+def test_planned_calls_match_direct_calls(gt, oracle):
+    """stencil.plan(): the pre-marshalled call enqueues the same kernel as the direct call."""
+    rng = np.random.default_rng(5)
+    inp = rng.standard_normal((6, 24, 70))
+    coeff = rng.uniform(0, 0.05, inp.shape)
+    st = [gt.storage.from_numpy(inp, (2, 2, 0)), gt.storage.from_numpy(coeff, (2, 2, 0)),
+          gt.storage.from_numpy(np.zeros_like(inp), (2, 2, 0))]
+    f = gt.stencil.plan("horizontal_diffusion", *st)
+    f()
+    gt.torch.cuda.synchronize()
+    inner = (slice(None), slice(2, -2), slice(2, -2))
+    assert np.array_equal(st[2].to_numpy()[inner], oracle.hori_diff(inp, coeff)[inner])
+    shape = (12, 5 + 6, 40 + 6)
+    arrs = [rng.uniform(5, 9, shape), rng.uniform(5, 9, shape), rng.uniform(-3e-4, 3e-4, shape),
+            rng.uniform(5, 9, shape), rng.uniform(-1e-5, 1e-5, shape)]
+    sv = [gt.storage.from_numpy(a, (3, 3, 0)) for a in arrs]
+    g = gt.stencil.plan("vertical_advection_dycore", *sv, dtr_stage=0.15)
+    g()
+    gt.torch.cuda.synchronize()
+    inner = (slice(None), slice(3, -3), slice(3, -3))
+    assert np.array_equal(sv[0].to_numpy()[inner], oracle.vert_adv(*arrs, 0.15)[inner])
+    with pytest.raises(ValueError):
+        gt.stencil.plan("no_such_spec")
+
+
 def test_launches_are_counted(gt):
     before = gt.lib.launch_count()
     a = np.zeros((2, 8, 16))
