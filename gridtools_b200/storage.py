@@ -17,14 +17,6 @@ from . import _lib
 BYTE_ALIGNMENT = 128  # storage_alignment(gpu), storage/gpu.hpp:78
 
 
-SKEW_BYTES = 0
-_n_allocated = 0
-
-
-def byte_multiple(isz, alignment):
-    return max(alignment, isz)
-
-
 class DataStore:
     """3-d field with halo, i-first layout, host mirror with lazy synchronisation."""
 
@@ -44,15 +36,9 @@ class DataStore:
         self.length = p0 * d1 * d2
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         tdtype = torch.float64 if isz == 8 else torch.float32
-        # Same-shaped fields allocated back to back start a multiple of 2 MiB apart (torch's allocator granularity),
-        # i.e. element (i,j,k) of every field of a stencil maps to the same position within the DRAM address
-        # interleaving.  SKEW_BYTES > 0 staggers consecutive allocations by that many bytes (mod 8 fields).
-        global _n_allocated
-        skew = (_n_allocated % 8) * SKEW_BYTES // byte_multiple(isz, alignment) * byte_multiple(isz, alignment)
-        _n_allocated += 1
-        self._raw = torch.zeros(self.length + ea + skew // isz, dtype=tdtype, device=self.device)
+        self._raw = torch.zeros(self.length + ea, dtype=tdtype, device=self.device)
         off = sum(h * s for h, s in zip(self.halos, self.strides)) * isz
-        addr = self._raw.data_ptr() + off + skew
+        addr = self._raw.data_ptr() + off
         byte_align = max(alignment, isz)
         self._base = (addr + byte_align - 1) // byte_align * byte_align - off  # data_store.hpp:67-71
         shift = (self._base - self._raw.data_ptr()) // isz
