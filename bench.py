@@ -346,7 +346,7 @@ def b200_arm(args):
     achieved = ALGO_BYTES[name] * pts / (launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic_from_profile(name), "peak_source": peak_src,
-                "kernel": "va_stream_kernel" if name == "vert_adv" else "hd_tma_kernel", "launch_ms": launch_ms,
+                "kernel": "va_pair_kernel" if name == "vert_adv" else "hd_tma_kernel", "launch_ms": launch_ms,
                 "launch_ms_source": "timed region / steps (one launch per step)" if world == 1 else
                 "events around each stencil launch", "isolated_launch_ms": isolated_ms,
                 "algorithmic_bytes_per_launch": ALGO_BYTES[name] * pts,

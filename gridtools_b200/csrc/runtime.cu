@@ -173,6 +173,7 @@ namespace {
             {"l2.persist_mb", &o.l2_persist_mb},
             {"va.debug", &o.va_debug},
             {"va.stages", &o.va_stages},
+            {"va.stagger", &o.va_stagger},
             {"copy.vec", &o.copy_vec}};
         for (auto &t : table)
             if (strcmp(t.name, key) == 0)

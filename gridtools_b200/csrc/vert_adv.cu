@@ -49,6 +49,11 @@ namespace {
         int kc;         // levels per TMA stage (TMA variant)
         int k_split;    // resident variant: levels [0, k_split) keep ccol/dcol in shared memory, the rest in registers
         int debug;      // diagnosis only (va.debug): 1 skip backward sweep, 2 skip forward math, 4 skip scratch stores
+        int stages;     // TMEM variants: TMA ring depth (run-time)
+        int bstages;    // fused TMEM variant: depth of the u_pos ring of the backward sweep
+        int pairs;      // paired-warp variant: F/B warp pairs in use per CTA
+        int stagger_ns; // TMEM variant: warp w of a CTA starts w * stagger_ns late (de-phases forward and backward sweeps)
+        int *tickets;   // TMEM variant: {next strip, finished warps}, self-resetting
     };
 
     template <class T, bool Hints>
@@ -985,6 +990,975 @@ namespace {
         }
     }
 
+    // ------------------------------------------------------------------ TMEM variant (va.variant = 5)
+    // Tensor memory as the k-cache store.  The profile of variant 3 (profiles/README.md) shows the sweep bound by L2
+    // slice traffic: the ccol/dcol/u_pos slab adds 2 x 24 B per point of L2 writes and reads to the 48 B that come
+    // from HBM.  Variant 4 keeps ccol/dcol on the SM but pays for it with statically indexed register tiers
+    // (jump tables, 121 instructions per level).  An SM of this chip has a third large on-chip memory that a stencil
+    // otherwise never touches: 256 KB of tensor memory, 128 lanes x 512 32-bit columns, addressed with a RUNTIME
+    // column index by tcgen05.st / tcgen05.ld (32x32b shape: lane l of warp w owns TMEM lane 32*(w%4)+l).  One
+    // 32-bit column per lane and word is exactly the shape of a per-column k-cache:
+    //  * one CTA per SM with WARPS (7 or 8) independent warps, each the streaming warp of variant 3 (own TMA ring,
+    //    own strips, no block barrier in the sweep); warp w owns lane quarter w%4 and column half w/4 of the CTA's
+    //    512-column allocation: 256 columns = 64 fp64 levels (128 fp32 levels) of {ccol, dcol};
+    //  * a forward chunk of KC levels ends with ONE tcgen05.st.x16 (fp64, KC = 4), a backward chunk starts with ONE
+    //    tcgen05.ld.x16 + wait::ld -- no address arithmetic, no L2 traffic, no shared-memory bandwidth;
+    //  * levels above the TMEM capacity (64..nk-2 for fp64) go to a small per-warp shared-memory slab;
+    //  * u_pos(k) for the backward sweep is re-read with an evict_first load from L2, where the forward TMA load
+    //    left it with an evict_last hint; these loads run 32 levels ahead in a register ring.
+    // L2 traffic per point: 48 B from HBM + 8 B u_pos re-read + 8 B written, against 96 + 48 in variant 3.
+    namespace tm {
+        __device__ __forceinline__ void alloc(uint32_t *slot, uint32_t cols) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_addr(slot)),
+                         "r"(cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        __device__ __forceinline__ void dealloc(uint32_t addr, uint32_t cols) {
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+        }
+        __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+        __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+        __device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+        __device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+        template <int N>
+        __device__ __forceinline__ void st(uint32_t a, const uint32_t (&r)[N]) {
+            static_assert(N == 8 || N == 16 || N == 32, "tcgen05.st width");
+            if constexpr (N == 8)
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(a),
+                             "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                             : "memory");
+            else if constexpr (N == 16)
+                asm volatile(
+                    "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
+                    "%13, %14, %15, %16};" ::"r"(a),
+                    "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+                    "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+                    : "memory");
+            else
+                asm volatile(
+                    "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
+                    "%13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+                    "%32};" ::"r"(a),
+                    "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+                    "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
+                    "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
+                    "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+                    : "memory");
+        }
+        template <int N>
+        __device__ __forceinline__ void ld(uint32_t a, uint32_t (&r)[N]) {
+            static_assert(N == 8 || N == 16 || N == 32, "tcgen05.ld width");
+            if constexpr (N == 8)
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+                             "=r"(r[7])
+                             : "r"(a)
+                             : "memory");
+            else if constexpr (N == 16)
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+                    "%14, %15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(a)
+                    : "memory");
+            else
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+                    "%14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                    "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+                    "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+                    "=r"(r[30]), "=r"(r[31])
+                    : "r"(a)
+                    : "memory");
+        }
+        // {ccol, dcol} of one level <-> CPL 32-bit words
+        template <class T>
+        __device__ __forceinline__ void pack(T cc, T dc, uint32_t *w) {
+            if constexpr (sizeof(T) == 8) {
+                w[0] = (uint32_t)__double2loint(cc), w[1] = (uint32_t)__double2hiint(cc);
+                w[2] = (uint32_t)__double2loint(dc), w[3] = (uint32_t)__double2hiint(dc);
+            } else {
+                w[0] = __float_as_uint(cc), w[1] = __float_as_uint(dc);
+            }
+        }
+        template <class T>
+        __device__ __forceinline__ void unpack(const uint32_t *w, T &cc, T &dc) {
+            if constexpr (sizeof(T) == 8) {
+                cc = __hiloint2double((int)w[1], (int)w[0]);
+                dc = __hiloint2double((int)w[3], (int)w[2]);
+            } else {
+                cc = __uint_as_float(w[0]), dc = __uint_as_float(w[1]);
+            }
+        }
+    } // namespace tm
+
+    template <class T>
+    struct va_tmem_cfg {
+        static constexpr int cpl = 2 * (int)sizeof(T) / 4; // 32-bit columns per level
+        static constexpr int cols(int warps) { return warps <= 4 ? 512 : 256; } // columns per warp
+        static constexpr int levels(int warps) { return cols(warps) / cpl; }     // levels a warp keeps in TMEM
+    };
+
+    // shared memory: [warps][stages][fstage] | [warps][slab_bytes] | [warps][stages] mbarriers | TMEM base address
+    template <class T, int KC>
+    int va_tmem_smem(int warps, int stages, int slab_bytes) {
+        return warps * (stages * va_tma_layout<T>::template stage_bytes<KC>() + slab_bytes + stages * 8) + 16;
+    }
+
+    __device__ __forceinline__ uint64_t globaltimer_ns() {
+        uint64_t t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        return t;
+    }
+
+    // Strips are handed out dynamically: the first one is the warp's own number, the following ones come from a
+    // ticket counter (one atomic per strip), so warps that start late (stagger) or run on a slower SM take fewer.
+    // The last warp to finish resets the counters for the next launch on the stream.
+    template <class T, int KC, int NBC>
+    __global__ void __launch_bounds__(256, 1) va_tmem_kernel(const __grid_constant__ va_maps maps, const va_params<T> p) {
+        using L = va_tma_layout<T>;
+        using CFG = va_tmem_cfg<T>;
+        constexpr int es = L::es;
+        constexpr int fstage = L::template stage_bytes<KC>();
+        constexpr uint32_t ftx = KC * (4 * 32 + L::ww) * es;
+        constexpr int CPL = CFG::cpl;
+        constexpr int NW = KC * CPL; // 32-bit words of a chunk
+        extern __shared__ __align__(128) unsigned char smem_all[];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, WARPS = blockDim.x >> 5;
+        const int S = p.stages;
+        const int slab_bytes = (int)p.slots; // per warp, multiple of 128
+        unsigned char *fring = smem_all + warp * (S * fstage);
+        T *const ss = reinterpret_cast<T *>(smem_all + WARPS * (S * fstage) + warp * slab_bytes) + lane; // [k][2][32]
+        uint64_t *ffull = reinterpret_cast<uint64_t *>(smem_all + WARPS * (S * fstage + slab_bytes)) + warp * S;
+        uint32_t *tslot = reinterpret_cast<uint32_t *>(smem_all + WARPS * (S * fstage + slab_bytes + S * 8));
+        if (lane == 0) {
+            for (int s = 0; s < S; ++s)
+                ptx::mbar_init(&ffull[s], 1);
+            ptx::fence_barrier_init();
+            if (warp == 0) {
+                ptx::prefetch_tensormap(&maps.us);
+                ptx::prefetch_tensormap(&maps.up);
+                ptx::prefetch_tensormap(&maps.ut);
+                ptx::prefetch_tensormap(&maps.un);
+                ptx::prefetch_tensormap(&maps.wc);
+            }
+        }
+        if (warp == 0)
+            tm::alloc(tslot, 512);
+        tm::fence_before();
+        __syncthreads();
+        tm::fence_after();
+        const uint32_t tbase = *tslot;
+        // this warp's window: lane quarter warp % 4, column half warp / 4
+        const uint32_t tw = tbase + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 256);
+
+        const int nk = p.nk;
+        const T dtr = p.dtr;
+        const int dbg = p.debug; // diagnosis only (va.debug): 1 skip backward, 8 skip output stores
+        const uint64_t pol_keep = ptx::policy_evict_last(), pol_stream = ptx::policy_evict_first();
+        const int gw = warp * gridDim.x + blockIdx.x, total = gridDim.x * WARPS;
+        const int nchunks = (nk + KC - 1) / KC;
+        const int c_tail = (nk - 1) / KC; // first forward chunk that needs per-level checks (holds level nk-1)
+        const int k_split = p.k_split, c_split = k_split / KC; // chunks [0, c_split) live in TMEM, the rest in the slab
+        const int cb_top = (nk - 2) / KC; // backward chunk that holds level nk-2
+        int f_issue = 0, f_wait = 0;
+        uint32_t f_phase = 0;
+
+        auto issue_f = [&](int i0, int j, int c) {
+            const int s = f_issue;
+            f_issue = f_issue + 1 == S ? 0 : f_issue + 1;
+            if (ptx::elect_one()) {
+                unsigned char *st = fring + s * fstage;
+                uint64_t *bar = &ffull[s];
+                ptx::mbar_expect_tx(bar, ftx);
+                ptx::tma_load_3d_hint(st, &maps.us, bar, i0, j, c * KC, pol_stream);
+                ptx::tma_load_3d_hint(st + KC * 32 * es, &maps.up, bar, i0, j, c * KC, pol_keep); // read again below
+                ptx::tma_load_3d_hint(st + 2 * KC * 32 * es, &maps.ut, bar, i0, j, c * KC, pol_stream);
+                ptx::tma_load_3d_hint(st + 3 * KC * 32 * es, &maps.un, bar, i0, j, c * KC + 1, pol_stream);
+                ptx::tma_load_3d_hint(st + 4 * KC * 32 * es, &maps.wc, bar, i0, j, c * KC + 1, pol_stream);
+            }
+        };
+        auto prime = [&](int item, T &u0) { // first S-1 forward chunks of a strip + u_stage(k = 0)
+            const int ti = item % p.tiles_i, j = item / p.tiles_i;
+            const int i0 = ti * 32;
+            for (int c = 0; c < S - 1 && c < nchunks; ++c)
+                issue_f(i0, j, c);
+            u0 = i0 + lane < p.ni ? __ldg(p.u_stage.ptr + i0 + lane + (int64_t)j * p.u_stage.sj) : T(0);
+        };
+        auto next_ticket = [&]() {
+            int t = 0;
+            if (lane == 0)
+                t = atomicAdd(p.tickets, 1);
+            return total + __shfl_sync(0xffffffffu, t, 0);
+        };
+        // chunk c of the k-cache: one TMEM store / load, or the shared-memory slab above the TMEM capacity
+        auto put_chunk = [&](int c, const T *ccv, const T *dcv) {
+            if (c < c_split) {
+                uint32_t w[NW];
+#pragma unroll
+                for (int u = 0; u < KC; ++u)
+                    tm::pack<T>(ccv[u], dcv[u], w + u * CPL);
+                tm::st<NW>(tw + (uint32_t)(c * NW), w);
+            } else {
+                T *q = ss + (c * KC - k_split) * 64;
+#pragma unroll
+                for (int u = 0; u < KC; ++u) {
+                    if (c * KC + u < nk - 1) {
+                        q[u * 64] = ccv[u];
+                        q[u * 64 + 32] = dcv[u];
+                    }
+                }
+            }
+        };
+        auto get_chunk = [&](int c, T *ccv, T *dcv) {
+            if (c < c_split) {
+                uint32_t w[NW];
+                tm::ld<NW>(tw + (uint32_t)(c * NW), w);
+                tm::wait_ld();
+#pragma unroll
+                for (int u = 0; u < KC; ++u)
+                    tm::unpack<T>(w + u * CPL, ccv[u], dcv[u]);
+            } else {
+                const T *q = ss + (c * KC - k_split) * 64;
+#pragma unroll
+                for (int u = 0; u < KC; ++u) {
+                    if (c * KC + u < nk - 1) {
+                        ccv[u] = q[u * 64];
+                        dcv[u] = q[u * 64 + 32];
+                    }
+                }
+            }
+        };
+
+        int item = gw;
+        T u0 = T(0);
+        if (item < p.items)
+            prime(item, u0);
+        if (p.stagger_ns > 0 && warp > 0) { // the ring is already filling; de-phase this warp's sweeps
+            const uint64_t until = globaltimer_ns() + (uint64_t)warp * (uint64_t)p.stagger_ns;
+            while (globaltimer_ns() < until)
+                __nanosleep(256);
+        }
+        while (item < p.items) {
+            const int ti = item % p.tiles_i, j = item / p.tiles_i;
+            const int i0 = ti * 32, i = i0 + lane;
+            const bool active = i < p.ni;
+            va_state<T> st;
+            st.u_k = u0;
+            st.u_km1 = st.wsum_k = st.cc_prev = st.dc_prev = st.up_last = T(0);
+            // ---------------------------------------------------------------- forward sweep (u_forward_function)
+            for (int c = 0; c < nchunks; ++c) {
+                if (c + S - 1 < nchunks) // refill the stage consumed in the previous iteration
+                    issue_f(i0, j, c + S - 1);
+                const int s = f_wait;
+                ptx::mbar_wait(&ffull[s], f_phase);
+                if (++f_wait == S) {
+                    f_wait = 0;
+                    f_phase ^= 1;
+                }
+                const T *sd = reinterpret_cast<const T *>(fring + s * fstage);
+                const T *wc = sd + 4 * KC * 32;
+                T ccv[KC], dcv[KC];
+                if (dbg & 2) { // diagnosis: traffic pattern without the forward arithmetic
+#pragma unroll
+                    for (int u = 0; u < KC; ++u) {
+                        ccv[u] = sd[u * 32 + lane] + sd[(KC + u) * 32 + lane] + wc[u * L::ww + lane + 1];
+                        dcv[u] = sd[(2 * KC + u) * 32 + lane] + sd[(3 * KC + u) * 32 + lane];
+                        st.dc_prev = dcv[u];
+                    }
+                } else if (c != 0 && c < c_tail) {
+                    va_forward_body_chunk<T, KC>(
+                        dtr, st,
+                        [&](int u, T &us, T &un, T &w0, T &w1, T &up, T &ut) {
+                            us = sd[u * 32 + lane], up = sd[(KC + u) * 32 + lane], ut = sd[(2 * KC + u) * 32 + lane];
+                            un = sd[(3 * KC + u) * 32 + lane];
+                            w0 = wc[u * L::ww + lane], w1 = wc[u * L::ww + lane + 1];
+                        },
+                        [&](int u, T cc, T dc, T) {
+                            ccv[u] = cc;
+                            dcv[u] = dc;
+                        });
+                } else {
+#pragma unroll
+                    for (int u = 0; u < KC; ++u) {
+                        const int k = c * KC + u;
+                        ccv[u] = dcv[u] = T(0);
+                        if (k < nk) {
+                            T us = sd[u * 32 + lane], up = sd[(KC + u) * 32 + lane], ut = sd[(2 * KC + u) * 32 + lane];
+                            T un = sd[(3 * KC + u) * 32 + lane];
+                            T w0 = wc[u * L::ww + lane], w1 = wc[u * L::ww + lane + 1];
+                            va_forward_level<T>(k, nk, dtr, us, un, w0, w1, up, ut, st, ccv[u], dcv[u]);
+                        }
+                    }
+                }
+                if (c <= cb_top)
+                    put_chunk(c, ccv, dcv);
+                __syncwarp(); // all lanes are done with stage s before lane 0 refills it
+            }
+            const int next = next_ticket();
+            // ---------------------------------------------------------------- backward sweep (u_backward_function)
+            if (dbg & 1) {
+                if (next < p.items)
+                    prime(next, u0);
+                if (active)
+                    p.utens_stage.ptr[i + (int64_t)j * p.utens_stage.sj] = st.dc_prev;
+                item = next;
+                continue;
+            }
+            const int64_t us_sk = p.utens_stage.sk, up_sk = p.u_pos.sk;
+            T *o = p.utens_stage.ptr + i + (int64_t)j * p.utens_stage.sj + (int64_t)(nk - 1) * us_sk;
+            const T *upp = p.u_pos.ptr + (active ? i : 0) + (int64_t)j * p.u_pos.sj;
+            // u_pos(k) of NBC chunks in flight (register ring, statically indexed): L2 hits, last use
+            T bu[NBC][KC];
+            auto load_upos = [&](int b, int cb) {
+                if (cb >= 0) {
+#pragma unroll
+                    for (int u = 0; u < KC; ++u)
+                        if (cb * KC + u <= nk - 2)
+                            bu[b][u] = ptx::ld_hint(upp + (int64_t)(cb * KC + u) * up_sk, pol_stream);
+                }
+            };
+#pragma unroll
+            for (int b = 0; b < NBC; ++b)
+                load_upos(b, cb_top - b);
+            if (next < p.items) // HBM keeps streaming while this warp sweeps back
+                prime(next, u0);
+            tm::wait_st(); // the forward sweep's TMEM stores have landed
+            T data = st.dc_prev; // last_level :118-121
+            if (active)
+                *o = dtr * (data - st.up_last);
+            for (int cb0 = cb_top; cb0 >= 0; cb0 -= NBC) {
+#pragma unroll
+                for (int b = 0; b < NBC; ++b) {
+                    const int cb = cb0 - b;
+                    if (cb >= 0) {
+                        T ccv[KC], dcv[KC];
+                        get_chunk(cb, ccv, dcv);
+#pragma unroll
+                        for (int u = KC - 1; u >= 0; --u) { // body :111-116
+                            if (cb * KC + u <= nk - 2) {
+                                if (dbg & 16) // diagnosis: no dependent chain in the backward sweep
+                                    data = dcv[u] - ccv[u];
+                                else
+                                    data = dcv[u] - ccv[u] * data;
+                                o -= us_sk;
+                                if (active && !(dbg & 8))
+                                    *o = dtr * (data - bu[b][u]);
+                            }
+                        }
+                        load_upos(b, cb - NBC);
+                    }
+                }
+            }
+            item = next;
+        }
+        if (lane == 0 && atomicAdd(p.tickets + 1, 1) == total - 1) { // every warp has drawn its last ticket
+            p.tickets[0] = 0;
+            p.tickets[1] = 0;
+            __threadfence();
+        }
+        tm::fence_before();
+        __syncthreads();
+        if (warp == 0)
+            tm::dealloc(tbase, 512);
+    }
+
+    // ------------------------------------------------------------------ fused-sweep TMEM variant (va.variant = 6)
+    // Variant 5 still runs the two sweeps of a strip one after the other, and every warp of the chip does so in
+    // lock-step: HBM is read for ~20 us, then nearly idle for ~5-10 us while the backward sweeps drain, twice per
+    // launch.  Both sweeps are latency-bound chains of dependent fp64 operations (forward ~10 per level through the
+    // reciprocal, backward 2 per level), so a warp can run them SIDE BY SIDE at no cost in issue slots: here the
+    // backward sweep of strip n is executed inside the forward loop of the warp's next strip n+1, chunk for chunk.
+    //  * One k-cache window serves both strips: at step c the backward sweep reads chunk cb_top-c of strip n out of
+    //    a physical slot, then the forward sweep of strip n+1 stores its chunk c into the slot just freed.  The
+    //    layout therefore alternates between natural and mirrored chunk order from strip to strip.
+    //  * u_pos(k) for the backward sweep arrives through a second small TMA ring (L2 hits: the forward load left the
+    //    lines evict_last), so the loop body needs no statically indexed register ring and is not unrolled.
+    //  * The TMA ring of the forward sweep never drains between strips; the output stores of strip n spread over the
+    //    whole forward sweep of strip n+1 instead of arriving as one burst.
+    // Only the first forward sweep and the last backward sweep of a warp run alone.
+    template <class T, int KC>
+    int va_fused_smem(int warps, int stages, int bstages, int slab_bytes) {
+        return warps * (stages * va_tma_layout<T>::template stage_bytes<KC>() + bstages * va_bstage_bytes<T, KC>() +
+                           slab_bytes + (stages + bstages) * 8) + 16;
+    }
+
+    template <class T, int KC>
+    __global__ void __launch_bounds__(256, 1) va_fused_kernel(const __grid_constant__ va_maps maps, const va_params<T> p) {
+        using L = va_tma_layout<T>;
+        using CFG = va_tmem_cfg<T>;
+        constexpr int es = L::es;
+        constexpr int fstage = L::template stage_bytes<KC>();
+        constexpr int bstage = va_bstage_bytes<T, KC>();
+        constexpr uint32_t ftx = KC * (4 * 32 + L::ww) * es;
+        constexpr uint32_t btx = KC * 32 * es;
+        constexpr int CPL = CFG::cpl;
+        constexpr int NW = KC * CPL; // 32-bit words of a chunk
+        extern __shared__ __align__(128) unsigned char smem_all[];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, WARPS = blockDim.x >> 5;
+        const int S = p.stages, SB = p.bstages;
+        const int slab_bytes = (int)p.slots; // per warp, multiple of 128
+        const int per_warp = S * fstage + SB * bstage + slab_bytes;
+        unsigned char *fring = smem_all + warp * per_warp;
+        unsigned char *bring = fring + S * fstage;
+        T *const ss = reinterpret_cast<T *>(bring + SB * bstage) + lane; // [chunk][level][2][32]
+        uint64_t *ffull = reinterpret_cast<uint64_t *>(smem_all + WARPS * per_warp) + warp * (S + SB);
+        uint64_t *bfull = ffull + S;
+        uint32_t *tslot = reinterpret_cast<uint32_t *>(smem_all + WARPS * (per_warp + (S + SB) * 8));
+        if (lane == 0) {
+            for (int s = 0; s < S + SB; ++s)
+                ptx::mbar_init(&ffull[s], 1);
+            ptx::fence_barrier_init();
+            if (warp == 0) {
+                ptx::prefetch_tensormap(&maps.us);
+                ptx::prefetch_tensormap(&maps.up);
+                ptx::prefetch_tensormap(&maps.ut);
+                ptx::prefetch_tensormap(&maps.un);
+                ptx::prefetch_tensormap(&maps.wc);
+            }
+        }
+        if (warp == 0)
+            tm::alloc(tslot, 512);
+        tm::fence_before();
+        __syncthreads();
+        tm::fence_after();
+        const uint32_t tbase = *tslot;
+        const uint32_t tw = tbase + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 256);
+
+        const int nk = p.nk;
+        const T dtr = p.dtr;
+        const uint64_t pol_keep = ptx::policy_evict_last(), pol_stream = ptx::policy_evict_first();
+        const int gw = warp * gridDim.x + blockIdx.x, total = gridDim.x * WARPS;
+        const int nchunks = (nk + KC - 1) / KC;
+        const int c_tail = (nk - 1) / KC; // first forward chunk that needs per-level checks (holds level nk-1)
+        const int c_split = p.k_split / KC; // physical chunks [0, c_split) live in TMEM, the rest in the slab
+        const int cb_top = (nk - 2) / KC;   // last stored chunk (holds level nk-2)
+        const int64_t us_sk = p.utens_stage.sk;
+        int f_issue = 0, f_wait = 0, b_issue = 0, b_wait = 0;
+        uint32_t f_phase = 0, b_phase = 0;
+
+        auto issue_f = [&](int i0, int j, int c) {
+            const int s = f_issue;
+            f_issue = f_issue + 1 == S ? 0 : f_issue + 1;
+            if (ptx::elect_one()) {
+                unsigned char *st = fring + s * fstage;
+                uint64_t *bar = &ffull[s];
+                ptx::mbar_expect_tx(bar, ftx);
+                ptx::tma_load_3d_hint(st, &maps.us, bar, i0, j, c * KC, pol_stream);
+                ptx::tma_load_3d_hint(st + KC * 32 * es, &maps.up, bar, i0, j, c * KC, pol_keep); // read again by issue_b
+                ptx::tma_load_3d_hint(st + 2 * KC * 32 * es, &maps.ut, bar, i0, j, c * KC, pol_stream);
+                ptx::tma_load_3d_hint(st + 3 * KC * 32 * es, &maps.un, bar, i0, j, c * KC + 1, pol_stream);
+                ptx::tma_load_3d_hint(st + 4 * KC * 32 * es, &maps.wc, bar, i0, j, c * KC + 1, pol_stream);
+            }
+        };
+        auto issue_b = [&](int i0, int j, int cb) {
+            const int s = b_issue;
+            b_issue = b_issue + 1 == SB ? 0 : b_issue + 1;
+            if (ptx::elect_one()) {
+                ptx::mbar_expect_tx(&bfull[s], btx);
+                ptx::tma_load_3d_hint(bring + s * bstage, &maps.up, &bfull[s], i0, j, cb * KC, pol_stream);
+            }
+        };
+        auto prime = [&](int item, T &u0) { // first S-1 forward chunks of a strip + u_stage(k = 0)
+            const int ti = item % p.tiles_i, j = item / p.tiles_i;
+            const int i0 = ti * 32;
+            for (int c = 0; c < S - 1 && c < nchunks; ++c)
+                issue_f(i0, j, c);
+            u0 = i0 + lane < p.ni ? __ldg(p.u_stage.ptr + i0 + lane + (int64_t)j * p.u_stage.sj) : T(0);
+        };
+        auto next_ticket = [&]() {
+            int t = 0;
+            if (lane == 0)
+                t = atomicAdd(p.tickets, 1);
+            return total + __shfl_sync(0xffffffffu, t, 0);
+        };
+        // physical chunk slot `ph` of the k-cache window; `c` is the logical chunk (for the level bound)
+        auto put_chunk = [&](int ph, int c, const T *ccv, const T *dcv) {
+            if (ph < c_split) {
+                uint32_t w[NW];
+#pragma unroll
+                for (int u = 0; u < KC; ++u)
+                    tm::pack<T>(ccv[u], dcv[u], w + u * CPL);
+                tm::st<NW>(tw + (uint32_t)(ph * NW), w);
+            } else {
+                T *q = ss + (ph - c_split) * (KC * 64);
+#pragma unroll
+                for (int u = 0; u < KC; ++u) {
+                    if (c * KC + u < nk - 1) {
+                        q[u * 64] = ccv[u];
+                        q[u * 64 + 32] = dcv[u];
+                    }
+                }
+            }
+        };
+        auto get_chunk = [&](int ph, int c, T *ccv, T *dcv) {
+            if (ph < c_split) {
+                uint32_t w[NW];
+                tm::ld<NW>(tw + (uint32_t)(ph * NW), w);
+                tm::wait_ld();
+#pragma unroll
+                for (int u = 0; u < KC; ++u)
+                    tm::unpack<T>(w + u * CPL, ccv[u], dcv[u]);
+            } else {
+                const T *q = ss + (ph - c_split) * (KC * 64);
+#pragma unroll
+                for (int u = 0; u < KC; ++u) {
+                    ccv[u] = dcv[u] = T(0);
+                    if (c * KC + u < nk - 1) {
+                        ccv[u] = q[u * 64];
+                        dcv[u] = q[u * 64 + 32];
+                    }
+                }
+            }
+        };
+
+        int item = gw;
+        T u0 = T(0);
+        if (item < p.items)
+            prime(item, u0);
+        // backward state of the previous strip of this warp
+        bool have_prev = false;
+        int b_i0 = 0, b_j = 0;
+        bool b_active = false;
+        T data = T(0);
+        T *o = nullptr;
+        int mirrored = 0; // chunk order in which the strip whose forward sweep runs now stores its k-cache
+
+        while (item < p.items || have_prev) {
+            const bool do_f = item < p.items;
+            int i0 = 0, j = 0;
+            if (do_f) {
+                const int ti = item % p.tiles_i;
+                j = item / p.tiles_i;
+                i0 = ti * 32;
+            }
+            va_state<T> st;
+            st.u_k = u0;
+            st.u_km1 = st.wsum_k = st.cc_prev = st.dc_prev = st.up_last = T(0);
+            const int nsteps = do_f ? nchunks : cb_top + 1;
+            for (int c = 0; c < nsteps; ++c) {
+                const bool do_b = have_prev && c <= cb_top;
+                const int ph = mirrored ? cb_top - c : c; // slot the backward sweep frees and the forward sweep fills
+                const int cb = cb_top - c;                // logical chunk of the backward sweep
+                // ---------------- backward: chunk cb of the previous strip out of the k-cache
+                T bcc[KC], bdc[KC];
+                const T *sb = nullptr;
+                if (do_b) {
+                    if (cb - (SB - 1) >= 0)
+                        issue_b(b_i0, b_j, cb - (SB - 1));
+                    get_chunk(ph, cb, bcc, bdc);
+                }
+                // ---------------- forward: chunk c of the current strip
+                T ccv[KC], dcv[KC];
+                if (do_f) {
+                    if (c + S - 1 < nchunks) // refill the stage consumed in the previous iteration
+                        issue_f(i0, j, c + S - 1);
+                    const int s = f_wait;
+                    ptx::mbar_wait(&ffull[s], f_phase);
+                    if (++f_wait == S) {
+                        f_wait = 0;
+                        f_phase ^= 1;
+                    }
+                    const T *sd = reinterpret_cast<const T *>(fring + s * fstage);
+                    const T *wc = sd + 4 * KC * 32;
+                    if (c != 0 && c < c_tail) {
+                        va_forward_body_chunk<T, KC>(
+                            dtr, st,
+                            [&](int u, T &us, T &un, T &w0, T &w1, T &up, T &ut) {
+                                us = sd[u * 32 + lane], up = sd[(KC + u) * 32 + lane], ut = sd[(2 * KC + u) * 32 + lane];
+                                un = sd[(3 * KC + u) * 32 + lane];
+                                w0 = wc[u * L::ww + lane], w1 = wc[u * L::ww + lane + 1];
+                            },
+                            [&](int u, T cc, T dc, T) {
+                                ccv[u] = cc;
+                                dcv[u] = dc;
+                            });
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < KC; ++u) {
+                            const int k = c * KC + u;
+                            ccv[u] = dcv[u] = T(0);
+                            if (k < nk) {
+                                T us = sd[u * 32 + lane], up = sd[(KC + u) * 32 + lane], ut = sd[(2 * KC + u) * 32 + lane];
+                                T un = sd[(3 * KC + u) * 32 + lane];
+                                T w0 = wc[u * L::ww + lane], w1 = wc[u * L::ww + lane + 1];
+                                va_forward_level<T>(k, nk, dtr, us, un, w0, w1, up, ut, st, ccv[u], dcv[u]);
+                            }
+                        }
+                    }
+                }
+                // ---------------- backward: levels of chunk cb, top down (u_backward_function body :111-116)
+                if (do_b) {
+                    const int s = b_wait;
+                    ptx::mbar_wait(&bfull[s], b_phase);
+                    if (++b_wait == SB) {
+                        b_wait = 0;
+                        b_phase ^= 1;
+                    }
+                    sb = reinterpret_cast<const T *>(bring + s * bstage) + lane;
+#pragma unroll
+                    for (int u = KC - 1; u >= 0; --u) {
+                        if (cb * KC + u <= nk - 2) {
+                            data = bdc[u] - bcc[u] * data;
+                            o -= us_sk;
+                            if (b_active)
+                                *o = dtr * (data - sb[u * 32]);
+                        }
+                    }
+                }
+                if (do_f && c <= cb_top)
+                    put_chunk(ph, c, ccv, dcv);
+                __syncwarp(); // all lanes are done with the ring stages before one lane refills them
+            }
+            have_prev = false;
+            if (do_f) { // this strip's backward sweep runs inside the next pass
+                have_prev = true;
+                b_i0 = i0, b_j = j;
+                b_active = i0 + lane < p.ni;
+                o = p.utens_stage.ptr + (b_active ? i0 + lane : 0) + (int64_t)j * p.utens_stage.sj + (int64_t)(nk - 1) * us_sk;
+                data = st.dc_prev; // last_level :118-121
+                if (b_active)
+                    *o = dtr * (data - st.up_last);
+                for (int n = 0; n < SB - 1 && cb_top - n >= 0; ++n)
+                    issue_b(i0, j, cb_top - n);
+                item = next_ticket();
+                if (item < p.items)
+                    prime(item, u0);
+                tm::wait_st(); // this strip's TMEM stores have landed before the next pass reads them
+                mirrored ^= 1;
+            }
+        }
+        if (lane == 0 && atomicAdd(p.tickets + 1, 1) == total - 1) { // every warp has drawn its last ticket
+            p.tickets[0] = 0;
+            p.tickets[1] = 0;
+            __threadfence();
+        }
+        tm::fence_before();
+        __syncthreads();
+        if (warp == 0)
+            tm::dealloc(tbase, 512);
+    }
+
+    // ------------------------------------------------------------------ paired-warp TMEM variant (va.variant = 7)
+    // What the debug knobs of variant 5 show (tools_va_dbg.py, profiles/README.md): with ALL arithmetic removed the
+    // kernel still takes 58 of its 60 us -- 37 us for streaming the forward inputs, 9 us for the backward sweeps'
+    // u_pos re-reads and 11 us for their output stores.  The sweeps are bound by the order in which one warp walks
+    // through its memory operations, not by fp64 latency: while a warp sweeps back it streams nothing, and variant 6
+    // (both sweeps in one instruction stream) only trades that bubble for a 25 % longer forward chunk.  The SM,
+    // meanwhile, issues on 30 % of its cycles and has room for 64 warps.
+    // Here every strip slot is a PAIR of warps that share one k-cache window:
+    //  * the F warp (warps 0..7) runs forward sweeps back to back: its TMA ring never drains, at the end of a strip
+    //    it hands {strip, dcol(nk-1), u_pos(nk-1)} to its partner through shared memory and a named barrier and starts
+    //    the next strip at once;
+    //  * the B warp (warps 8..15: same TMEM lane quarter as its partner) sweeps the previous strip back WHILE the
+    //    F warp fills the window with the next one -- the alternating natural/mirrored chunk order of variant 6 makes
+    //    the slot the backward sweep frees the slot the forward sweep fills next; a monotonic chunk counter in
+    //    shared memory keeps the F warp from overwriting a slot that has not been read (the B warp is ~4x faster per
+    //    chunk, so this never blocks in practice);
+    //  * u_pos(k) reaches the B warp through its own small TMA ring (L2 hits, evict_first).
+    // Output stores, L2 re-reads and HBM streaming now overlap for the whole launch; only the very first forward
+    // sweep and the very last backward sweep of a pair run alone.
+    template <class T, int KC>
+    int va_pair_smem(int pairs, int stages, int bstages, int slab_bytes) {
+        return pairs * (stages * va_tma_layout<T>::template stage_bytes<KC>() + bstages * va_bstage_bytes<T, KC>() +
+                           slab_bytes + 4 * 32 * (int)sizeof(T) + (stages + bstages) * 8 + 32) + 16;
+    }
+
+    __device__ __forceinline__ void named_barrier_sync(int id, int threads) {
+        asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+    }
+
+    template <class T, int KC>
+    __global__ void __launch_bounds__(512, 1) va_pair_kernel(const __grid_constant__ va_maps maps, const va_params<T> p) {
+        using L = va_tma_layout<T>;
+        using CFG = va_tmem_cfg<T>;
+        constexpr int es = L::es;
+        constexpr int fstage = L::template stage_bytes<KC>();
+        constexpr int bstage = va_bstage_bytes<T, KC>();
+        constexpr uint32_t ftx = KC * (4 * 32 + L::ww) * es;
+        constexpr uint32_t btx = KC * 32 * es;
+        constexpr int CPL = CFG::cpl;
+        constexpr int NW = KC * CPL; // 32-bit words of a chunk
+        extern __shared__ __align__(128) unsigned char smem_all[];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, PAIRS = p.pairs; // 16 warps, PAIRS <= 8 pairs in use
+        const int pw = warp & 7;             // pair index in the CTA: warps pw and pw + 8 share a TMEM lane quarter
+        const bool is_b = warp >= 8;         // role
+        const bool idle = pw >= PAIRS;
+        const int S = p.stages, SB = p.bstages;
+        const int slab_bytes = (int)p.slots; // per pair, multiple of 128
+        const int per_pair = S * fstage + SB * bstage + slab_bytes + 4 * 32 * es;
+        unsigned char *fring = smem_all + pw * per_pair;
+        unsigned char *bring = fring + S * fstage;
+        T *const ss = reinterpret_cast<T *>(bring + SB * bstage) + lane;               // [chunk][level][2][32]
+        T *const hand = reinterpret_cast<T *>(bring + SB * bstage + slab_bytes) + lane; // [parity][dcol, u_pos][32]
+        uint64_t *ffull = reinterpret_cast<uint64_t *>(smem_all + PAIRS * per_pair) + pw * (S + SB);
+        uint64_t *bfull = ffull + S;
+        volatile int *ctl = reinterpret_cast<volatile int *>(smem_all + PAIRS * (per_pair + (S + SB) * 8)) + pw * 8;
+        // ctl[0] chunks the B warp has read so far (monotonic), ctl[2 + 3*parity ..]: {strip, more, mirrored}
+        uint32_t *tslot = reinterpret_cast<uint32_t *>(smem_all + PAIRS * (per_pair + (S + SB) * 8 + 32));
+        if (lane == 0 && !is_b && !idle) {
+            for (int s = 0; s < S + SB; ++s)
+                ptx::mbar_init(&ffull[s], 1);
+            ctl[0] = 0;
+            ptx::fence_barrier_init();
+            if (warp == 0) {
+                ptx::prefetch_tensormap(&maps.us);
+                ptx::prefetch_tensormap(&maps.up);
+                ptx::prefetch_tensormap(&maps.ut);
+                ptx::prefetch_tensormap(&maps.un);
+                ptx::prefetch_tensormap(&maps.wc);
+            }
+        }
+        if (warp == 0)
+            tm::alloc(tslot, 512);
+        tm::fence_before();
+        __syncthreads();
+        tm::fence_after();
+        const uint32_t tbase = *tslot;
+        const uint32_t tw = tbase + ((uint32_t)((pw & 3) * 32) << 16) + (uint32_t)((pw >> 2) * 256);
+
+        const int nk = p.nk;
+        const T dtr = p.dtr;
+        const uint64_t pol_keep = ptx::policy_evict_last(), pol_stream = ptx::policy_evict_first();
+        const int total = gridDim.x * PAIRS;
+        const int nchunks = (nk + KC - 1) / KC;
+        const int c_tail = (nk - 1) / KC;   // first forward chunk that needs per-level checks (holds level nk-1)
+        const int c_split = p.k_split / KC; // physical chunks [0, c_split) live in TMEM, the rest in the slab
+        const int cb_top = (nk - 2) / KC;   // last stored chunk (holds level nk-2)
+        const int nstored = cb_top + 1;
+        const int bar_id = 1 + pw;
+
+        if (idle) {
+            // a pair slot left empty so that the strips of a launch divide evenly among the pairs
+        } else if (!is_b) {
+            // ============================================================ F warp: forward sweeps back to back
+            int f_issue = 0, f_wait = 0;
+            uint32_t f_phase = 0;
+            auto issue_f = [&](int i0, int j, int c) {
+                const int s = f_issue;
+                f_issue = f_issue + 1 == S ? 0 : f_issue + 1;
+                if (ptx::elect_one()) {
+                    unsigned char *st = fring + s * fstage;
+                    uint64_t *bar = &ffull[s];
+                    ptx::mbar_expect_tx(bar, ftx);
+                    ptx::tma_load_3d_hint(st, &maps.us, bar, i0, j, c * KC, pol_stream);
+                    ptx::tma_load_3d_hint(st + KC * 32 * es, &maps.up, bar, i0, j, c * KC, pol_keep); // B warp re-reads
+                    ptx::tma_load_3d_hint(st + 2 * KC * 32 * es, &maps.ut, bar, i0, j, c * KC, pol_stream);
+                    ptx::tma_load_3d_hint(st + 3 * KC * 32 * es, &maps.un, bar, i0, j, c * KC + 1, pol_stream);
+                    ptx::tma_load_3d_hint(st + 4 * KC * 32 * es, &maps.wc, bar, i0, j, c * KC + 1, pol_stream);
+                }
+            };
+            auto prime = [&](int item, T &u0) { // first S-1 forward chunks of a strip + u_stage(k = 0)
+                const int ti = item % p.tiles_i, j = item / p.tiles_i;
+                const int i0 = ti * 32;
+                for (int c = 0; c < S - 1 && c < nchunks; ++c)
+                    issue_f(i0, j, c);
+                u0 = i0 + lane < p.ni ? __ldg(p.u_stage.ptr + i0 + lane + (int64_t)j * p.u_stage.sj) : T(0);
+            };
+            int item = pw * gridDim.x + blockIdx.x;
+            T u0 = T(0);
+            if (item < p.items)
+                prime(item, u0);
+            int mirrored = 0, pass = 0;
+            if (item >= p.items) { // no strip for this pair: release the partner
+                if (lane == 0)
+                    ctl[2] = -1;
+                __syncwarp();
+                named_barrier_sync(bar_id, 64);
+            }
+            while (item < p.items) {
+                const int ti = item % p.tiles_i, j = item / p.tiles_i;
+                const int i0 = ti * 32;
+                va_state<T> st;
+                st.u_k = u0;
+                st.u_km1 = st.wsum_k = st.cc_prev = st.dc_prev = st.up_last = T(0);
+                const int need0 = (pass - 1) * nstored; // chunks the partner had read before this pass
+                for (int c = 0; c < nchunks; ++c) {
+                    if (c + S - 1 < nchunks) // refill the stage consumed in the previous iteration
+                        issue_f(i0, j, c + S - 1);
+                    const int s = f_wait;
+                    ptx::mbar_wait(&ffull[s], f_phase);
+                    if (++f_wait == S) {
+                        f_wait = 0;
+                        f_phase ^= 1;
+                    }
+                    const T *sd = reinterpret_cast<const T *>(fring + s * fstage);
+                    const T *wc = sd + 4 * KC * 32;
+                    T ccv[KC], dcv[KC];
+                    if (c != 0 && c < c_tail) {
+                        va_forward_body_chunk<T, KC>(
+                            dtr, st,
+                            [&](int u, T &us, T &un, T &w0, T &w1, T &up, T &ut) {
+                                us = sd[u * 32 + lane], up = sd[(KC + u) * 32 + lane], ut = sd[(2 * KC + u) * 32 + lane];
+                                un = sd[(3 * KC + u) * 32 + lane];
+                                w0 = wc[u * L::ww + lane], w1 = wc[u * L::ww + lane + 1];
+                            },
+                            [&](int u, T cc, T dc, T) {
+                                ccv[u] = cc;
+                                dcv[u] = dc;
+                            });
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < KC; ++u) {
+                            const int k = c * KC + u;
+                            ccv[u] = dcv[u] = T(0);
+                            if (k < nk) {
+                                T us = sd[u * 32 + lane], up = sd[(KC + u) * 32 + lane], ut = sd[(2 * KC + u) * 32 + lane];
+                                T un = sd[(3 * KC + u) * 32 + lane];
+                                T w0 = wc[u * L::ww + lane], w1 = wc[u * L::ww + lane + 1];
+                                va_forward_level<T>(k, nk, dtr, us, un, w0, w1, up, ut, st, ccv[u], dcv[u]);
+                            }
+                        }
+                    }
+                    if (c <= cb_top) {
+                        const int ph = mirrored ? cb_top - c : c;
+                        if (pass > 0) { // the partner must have read this slot (chunk cb_top - c of the previous strip)
+                            while (ctl[0] < need0 + c + 1) {
+                            }
+                            __threadfence_block();
+                            tm::fence_after();
+                        }
+                        if (ph < c_split) {
+                            uint32_t w[NW];
+#pragma unroll
+                            for (int u = 0; u < KC; ++u)
+                                tm::pack<T>(ccv[u], dcv[u], w + u * CPL);
+                            tm::st<NW>(tw + (uint32_t)(ph * NW), w);
+                        } else {
+                            T *q = ss + (ph - c_split) * (KC * 64);
+#pragma unroll
+                            for (int u = 0; u < KC; ++u) {
+                                if (c * KC + u < nk - 1) {
+                                    q[u * 64] = ccv[u];
+                                    q[u * 64 + 32] = dcv[u];
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp(); // all lanes are done with stage s before one lane refills it
+                }
+                // ---- hand the strip to the partner and go on
+                const int par = pass & 1;
+                hand[(par * 2) * 32] = st.dc_prev;
+                hand[(par * 2 + 1) * 32] = st.up_last;
+                int next = 0;
+                if (lane == 0)
+                    next = atomicAdd(p.tickets, 1);
+                next = total + __shfl_sync(0xffffffffu, next, 0);
+                if (lane == 0) {
+                    ctl[2 + par * 3] = item;
+                    ctl[3 + par * 3] = next < p.items;
+                    ctl[4 + par * 3] = mirrored;
+                }
+                if (next < p.items)
+                    prime(next, u0);
+                tm::wait_st();
+                tm::fence_before();
+                __syncwarp();
+                named_barrier_sync(bar_id, 64);
+                item = next;
+                mirrored ^= 1;
+                ++pass;
+            }
+        } else {
+            // ============================================================ B warp: backward sweep of the partner's last strip
+            int b_issue = 0, b_wait = 0;
+            uint32_t b_phase = 0;
+            const int64_t us_sk = p.utens_stage.sk;
+            int done = 0; // chunks read so far (published in ctl[0])
+            for (int pass = 0;; ++pass) {
+                named_barrier_sync(bar_id, 64);
+                tm::fence_after();
+                const int par = pass & 1;
+                const int item = ctl[2 + par * 3];
+                if (item < 0)
+                    break;
+                const int more = ctl[3 + par * 3], mirrored = ctl[4 + par * 3];
+                T data = hand[(par * 2) * 32];
+                const T up_last = hand[(par * 2 + 1) * 32];
+                const int ti = item % p.tiles_i, j = item / p.tiles_i;
+                const int i0 = ti * 32;
+                const bool active = i0 + lane < p.ni;
+                auto issue_b = [&](int cb) {
+                    const int s = b_issue;
+                    b_issue = b_issue + 1 == SB ? 0 : b_issue + 1;
+                    if (ptx::elect_one()) {
+                        ptx::mbar_expect_tx(&bfull[s], btx);
+                        ptx::tma_load_3d_hint(bring + s * bstage, &maps.up, &bfull[s], i0, j, cb * KC, pol_stream);
+                    }
+                };
+                for (int n = 0; n < SB - 1 && cb_top - n >= 0; ++n)
+                    issue_b(cb_top - n);
+                T *o = p.utens_stage.ptr + (active ? i0 + lane : 0) + (int64_t)j * p.utens_stage.sj + (int64_t)(nk - 1) * us_sk;
+                if (active) // last_level :118-121
+                    *o = dtr * (data - up_last);
+                for (int cb = cb_top; cb >= 0; --cb) {
+                    if (cb - (SB - 1) >= 0)
+                        issue_b(cb - (SB - 1));
+                    const int ph = mirrored ? cb_top - cb : cb; // where the strip stored its chunk cb
+                    T bcc[KC], bdc[KC];
+                    if (ph < c_split) {
+                        uint32_t w[NW];
+                        tm::ld<NW>(tw + (uint32_t)(ph * NW), w);
+                        tm::wait_ld();
+#pragma unroll
+                        for (int u = 0; u < KC; ++u)
+                            tm::unpack<T>(w + u * CPL, bcc[u], bdc[u]);
+                        tm::fence_before();
+                    } else {
+                        const T *q = ss + (ph - c_split) * (KC * 64);
+#pragma unroll
+                        for (int u = 0; u < KC; ++u) {
+                            bcc[u] = bdc[u] = T(0);
+                            if (cb * KC + u < nk - 1) {
+                                bcc[u] = q[u * 64];
+                                bdc[u] = q[u * 64 + 32];
+                            }
+                        }
+                    }
+                    __threadfence_block();
+                    __syncwarp();
+                    ++done;
+                    if (lane == 0)
+                        ctl[0] = done; // the slot may be overwritten by the partner's forward sweep
+                    const int s = b_wait;
+                    ptx::mbar_wait(&bfull[s], b_phase);
+                    if (++b_wait == SB) {
+                        b_wait = 0;
+                        b_phase ^= 1;
+                    }
+                    const T *sb = reinterpret_cast<const T *>(bring + s * bstage) + lane;
+#pragma unroll
+                    for (int u = KC - 1; u >= 0; --u) { // body :111-116
+                        if (cb * KC + u <= nk - 2) {
+                            data = bdc[u] - bcc[u] * data;
+                            o -= us_sk;
+                            if (active)
+                                *o = dtr * (data - sb[u * 32]);
+                        }
+                    }
+                    __syncwarp(); // all lanes are done with the ring stage before one lane refills it
+                }
+                if (!more)
+                    break;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(p.tickets + 1, 1) == (int)gridDim.x - 1) { // every F warp has drawn its last ticket
+            p.tickets[0] = 0;
+            p.tickets[1] = 0;
+            __threadfence();
+        }
+        tm::fence_before();
+        __syncthreads();
+        if (warp == 0)
+            tm::dealloc(tbase, 512);
+    }
+
     // ------------------------------------------------------------------------------ Thomas solve (tridiagonal.cpp)
     template <class T>
     struct td_params {
@@ -1249,6 +2223,176 @@ namespace {
                                           : launch_va_resident<T, 4, 3, 2>(maps, p, grid, stream));
     }
 
+    // {next strip, finished warps} of the TMEM variant, one pair per device, zeroed once (the kernel resets it).
+    int *va_ticket_counters() {
+        static int *ctr[64] = {};
+        const int d = dev()->device;
+        if (d < 0 || d >= 64)
+            return nullptr;
+        if (!ctr[d]) {
+            int *q = nullptr;
+            if (cudaMalloc(&q, 256) != cudaSuccess || cudaMemset(q, 0, 256) != cudaSuccess) {
+                cuda_fail(cudaGetLastError(), "va ticket counters");
+                return nullptr;
+            }
+            ctr[d] = q;
+        }
+        return ctr[d];
+    }
+
+    // TMEM variant: one CTA per SM.  va.ctas_per_sm = warps per CTA (4..8, default 8; < 0: an absolute number of
+    // CTAs of 8 warps, tests), va.stages = TMA ring depth (0: as deep as shared memory allows, at most 8),
+    // va.threads (re-used) = start stagger between the warps of a CTA in units of 100 ns.  Returns -1 when the
+    // shared-memory slab for the levels above the TMEM capacity does not fit (tall columns): the caller then uses
+    // variant 3.
+    template <class T>
+    int vert_adv_tmem(va_params<T> &p, const options &o, device_state *d, const va_maps &maps, cudaStream_t stream) {
+        constexpr int KC = 4;
+        const int warps = o.va_ctas_per_sm >= 4 && o.va_ctas_per_sm <= 8 ? o.va_ctas_per_sm : 8;
+        const int levels = va_tmem_cfg<T>::levels(warps);
+        const int cb_top = (p.nk - 2) / KC;
+        int k_split = (cb_top + 1) * KC;
+        if (k_split > levels)
+            k_split = levels;
+        p.k_split = k_split;
+        const int slab_levels = p.nk - 1 - k_split > 0 ? p.nk - 1 - k_split : 0;
+        const int slab_bytes = (slab_levels * 64 * (int)sizeof(T) + 127) / 128 * 128;
+        p.slots = slab_bytes;
+        p.scratch = nullptr;
+        p.persistent = 1;
+        int stages = o.va_stages >= 2 && o.va_stages <= 16 ? o.va_stages : 0;
+        if (stages == 0)
+            for (stages = 8; stages > 2 && va_tmem_smem<T, KC>(warps, stages, slab_bytes) > d->max_smem_optin;)
+                --stages;
+        const int smem = va_tmem_smem<T, KC>(warps, stages, slab_bytes);
+        if (smem > d->max_smem_optin)
+            return -1;
+        p.stages = stages;
+        p.stagger_ns = o.va_stagger > 0 ? o.va_stagger * 100 : 0;
+        p.tickets = va_ticket_counters();
+        if (!p.tickets)
+            return GTB_ERR_ALLOC;
+        const int64_t strips = (int64_t)p.tiles_i * p.nj;
+        int grid = o.va_ctas_per_sm < 0 ? -o.va_ctas_per_sm : d->sm_count;
+        if ((int64_t)grid * warps > strips)
+            grid = (int)((strips + warps - 1) / warps);
+        int st = set_l2_persist(0);
+        if (st)
+            return st;
+        auto kernel = va_tmem_kernel<T, KC, 8>;
+        static thread_local int done_dev = -1;
+        if (done_dev != d->device) {
+            GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->max_smem_optin));
+            GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            done_dev = d->device;
+        }
+        kernel<<<grid, warps * 32, smem, stream>>>(maps, p);
+        count_launch();
+        return check_launch("va_tmem_kernel");
+    }
+
+    // Fused-sweep TMEM variant (va.variant = 6): same knobs as variant 5 (va.ctas_per_sm = warps per CTA, va.stages =
+    // forward ring depth), va.unroll = depth of the backward u_pos ring (default 4).
+    template <class T>
+    int vert_adv_fused(va_params<T> &p, const options &o, device_state *d, const va_maps &maps, cudaStream_t stream) {
+        constexpr int KC = 4;
+        const int warps = o.va_ctas_per_sm >= 4 && o.va_ctas_per_sm <= 8 ? o.va_ctas_per_sm : 8;
+        const int levels = va_tmem_cfg<T>::levels(warps);
+        const int cb_top = (p.nk - 2) / KC;
+        int k_split = (cb_top + 1) * KC;
+        if (k_split > levels)
+            k_split = levels;
+        p.k_split = k_split;
+        const int slab_bytes = (cb_top + 1 - k_split / KC) * KC * 64 * (int)sizeof(T);
+        p.slots = slab_bytes;
+        p.scratch = nullptr;
+        p.persistent = 1;
+        const int bstages = o.va_unroll >= 2 && o.va_unroll <= 8 ? o.va_unroll : 4;
+        int stages = o.va_stages >= 2 && o.va_stages <= 16 ? o.va_stages : 0;
+        if (stages == 0)
+            for (stages = 6; stages > 2 && va_fused_smem<T, KC>(warps, stages, bstages, slab_bytes) > d->max_smem_optin;)
+                --stages;
+        const int smem = va_fused_smem<T, KC>(warps, stages, bstages, slab_bytes);
+        if (smem > d->max_smem_optin)
+            return -1;
+        p.stages = stages;
+        p.bstages = bstages;
+        p.stagger_ns = 0;
+        p.tickets = va_ticket_counters();
+        if (!p.tickets)
+            return GTB_ERR_ALLOC;
+        const int64_t strips = (int64_t)p.tiles_i * p.nj;
+        int grid = o.va_ctas_per_sm < 0 ? -o.va_ctas_per_sm : d->sm_count;
+        if ((int64_t)grid * warps > strips)
+            grid = (int)((strips + warps - 1) / warps);
+        int st = set_l2_persist(0);
+        if (st)
+            return st;
+        auto kernel = va_fused_kernel<T, KC>;
+        static thread_local int done_dev = -1;
+        if (done_dev != d->device) {
+            GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->max_smem_optin));
+            GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            done_dev = d->device;
+        }
+        kernel<<<grid, warps * 32, smem, stream>>>(maps, p);
+        count_launch();
+        return check_launch("va_fused_kernel");
+    }
+
+    // Paired-warp TMEM variant (va.variant = 7): va.ctas_per_sm = F/B warp pairs in use per CTA (1..8, 0 = auto;
+    // < 0: an absolute number of CTAs, tests), va.stages = forward ring depth, va.unroll = depth of the
+    // backward u_pos ring (default 3).
+    template <class T>
+    int vert_adv_pair(va_params<T> &p, const options &o, device_state *d, const va_maps &maps, cudaStream_t stream) {
+        constexpr int KC = 4;
+        int pairs = o.va_ctas_per_sm >= 1 && o.va_ctas_per_sm <= 8 ? o.va_ctas_per_sm : 0;
+        const int64_t strips = (int64_t)p.tiles_i * p.nj;
+        if (pairs == 0)
+            pairs = 8;
+        p.pairs = pairs;
+        const int levels = va_tmem_cfg<T>::levels(8);
+        const int cb_top = (p.nk - 2) / KC;
+        int k_split = (cb_top + 1) * KC;
+        if (k_split > levels)
+            k_split = levels;
+        p.k_split = k_split;
+        const int slab_bytes = (cb_top + 1 - k_split / KC) * KC * 64 * (int)sizeof(T);
+        p.slots = slab_bytes;
+        p.scratch = nullptr;
+        p.persistent = 1;
+        const int bstages = o.va_unroll >= 2 && o.va_unroll <= 8 ? o.va_unroll : 3;
+        int stages = o.va_stages >= 2 && o.va_stages <= 16 ? o.va_stages : 0;
+        if (stages == 0)
+            for (stages = 6; stages > 2 && va_pair_smem<T, KC>(pairs, stages, bstages, slab_bytes) > d->max_smem_optin;)
+                --stages;
+        const int smem = va_pair_smem<T, KC>(pairs, stages, bstages, slab_bytes);
+        if (smem > d->max_smem_optin)
+            return -1;
+        p.stages = stages;
+        p.bstages = bstages;
+        p.stagger_ns = 0;
+        p.tickets = va_ticket_counters();
+        if (!p.tickets)
+            return GTB_ERR_ALLOC;
+        int grid = o.va_ctas_per_sm < 0 ? -o.va_ctas_per_sm : d->sm_count;
+        if ((int64_t)grid * pairs > strips)
+            grid = (int)((strips + pairs - 1) / pairs);
+        int st = set_l2_persist(0);
+        if (st)
+            return st;
+        auto kernel = va_pair_kernel<T, KC>;
+        static thread_local int done_dev = -1;
+        if (done_dev != d->device) {
+            GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->max_smem_optin));
+            GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            done_dev = d->device;
+        }
+        kernel<<<grid, 512, smem, stream>>>(maps, p);
+        count_launch();
+        return check_launch("va_pair_kernel");
+    }
+
     // Builds the five tensor maps; false if any field is not TMA-addressable.
     template <class T>
     bool make_va_maps(va_maps &m, const va_params<T> &p) {
@@ -1272,8 +2416,12 @@ namespace {
         *done = false;
         const bool stream_variant = o.va_variant != 2;
         const bool resident = o.va_variant == 4; // (auto = variant 3: measured fastest, see profiles/README.md)
-        int kc = o.va_unroll == 8 ? 8 : (o.va_unroll == 2 && !stream_variant ? 2 : 4);
-        if (resident) // auto: 2-level stages for fp64 (shared memory is what limits the warps per SM), 4 for fp32
+        // auto: the paired-warp TMEM kernel for fp64 (fastest measured, profiles/README.md); for fp32, where a strip moves
+        // half the bytes and the sweep is latency-bound, the one-warp streaming kernel with its L2 slab
+        const int tm_variant = o.va_variant == 0 ? (sizeof(T) == 8 ? 7 : 0) : o.va_variant;
+        const bool tmem = tm_variant >= 5 && tm_variant <= 7;
+        int kc = o.va_unroll == 8 && !tmem ? 8 : (o.va_unroll == 2 && !stream_variant ? 2 : 4);
+        if (resident && !tmem) // auto: 2-level stages for fp64 (shared memory is what limits the warps per SM), 4 for fp32
             kc = o.va_unroll == 2 ? 2 : (o.va_unroll == 4 ? 4 : (sizeof(T) == 8 ? 2 : 4));
         p.kc = kc;
         p.debug = o.va_debug;
@@ -1286,6 +2434,15 @@ namespace {
         int grid = o.va_ctas_per_sm < 0 ? -o.va_ctas_per_sm : wps * d->sm_count;
         if (grid > strips)
             grid = (int)strips;
+        if (tmem) {
+            int st = tm_variant == 7 ? vert_adv_pair<T>(p, o, d, maps, stream)
+                                     : (tm_variant == 6 ? vert_adv_fused<T>(p, o, d, maps, stream)
+                                                        : vert_adv_tmem<T>(p, o, d, maps, stream));
+            if (st >= 0) {
+                *done = true;
+                return st;
+            }
+        }
         if (resident) {
             p.scratch = nullptr;
             p.slots = 0;

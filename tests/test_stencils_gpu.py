@@ -36,7 +36,7 @@ def gt():
 @pytest.fixture(autouse=True)
 def reset_options(gt):
     yield
-    for k in ("hd.variant", "hd.stages", "hd.ctas_per_sm", "va.variant", "va.threads", "va.unroll", "va.scratch",
+    for k in ("hd.variant", "hd.stages", "hd.ctas_per_sm", "va.variant", "va.threads", "va.unroll", "va.scratch", "va.stagger",
               "va.ctas_per_sm", "va.save_upos", "va.stages"):
         gt.lib.set_option(k, 0)
     gt.lib.set_option("va.hints", 1)
@@ -175,7 +175,10 @@ def test_hori_diff_linearity(gt):
 
 
 # ------------------------------------------------------------------------------------- vertical advection
-VA_CONFIGS = [dict(), dict(variant=4), dict(variant=4, unroll=4), dict(variant=4, unroll=2, stages=4, ctas_per_sm=-2),
+VA_CONFIGS = [dict(), dict(variant=5), dict(variant=5, ctas_per_sm=7), dict(variant=5, stages=3), dict(variant=5, ctas_per_sm=-1),
+              dict(variant=5, ctas_per_sm=-2, stages=3), dict(variant=5, ctas_per_sm=4, stagger=5), dict(variant=6), dict(variant=6, ctas_per_sm=-1, stages=2, unroll=2),
+              dict(variant=6, ctas_per_sm=7, stages=3), dict(variant=7), dict(variant=7, ctas_per_sm=-1), dict(variant=7, ctas_per_sm=3, stages=2, unroll=2),
+              dict(variant=7, ctas_per_sm=7, stages=3, unroll=4), dict(variant=4), dict(variant=4, unroll=4), dict(variant=4, unroll=2, stages=4, ctas_per_sm=-2),
               dict(variant=4, unroll=4, stages=2, ctas_per_sm=-1), dict(variant=4, ctas_per_sm=-3), dict(variant=3), dict(variant=3, ctas_per_sm=-2, unroll=8), dict(variant=3, ctas_per_sm=-1),
               dict(variant=3, stages=3, ctas_per_sm=-3), dict(variant=3, stages=6), dict(variant=3, ctas_per_sm=-2, save_upos=2),
               dict(variant=3, threads=32, ctas_per_sm=-1, save_upos=2), dict(variant=3, threads=64, ctas_per_sm=-2),
@@ -226,19 +229,19 @@ def test_vert_adv_random_bit_exact(gt, oracle, size, alignment):
     shape = (nk, nj + 6, ni + 6)
     arrs = [rng.uniform(5, 9, shape), rng.uniform(5, 9, shape), rng.uniform(-3e-4, 3e-4, shape),
             rng.uniform(5, 9, shape), rng.uniform(-1e-5, 1e-5, shape)]
-    for cfg in (dict(), dict(variant=4, ctas_per_sm=-2), dict(variant=4, unroll=4, ctas_per_sm=-1), dict(variant=2, ctas_per_sm=-2), dict(variant=3, ctas_per_sm=-3), dict(variant=3, ctas_per_sm=-1, unroll=8),
+    for cfg in (dict(), dict(variant=5), dict(variant=5, ctas_per_sm=-1, stages=3), dict(variant=6, ctas_per_sm=-1), dict(variant=7), dict(variant=7, ctas_per_sm=-1, stages=2), dict(variant=4, ctas_per_sm=-2), dict(variant=4, unroll=4, ctas_per_sm=-1), dict(variant=2, ctas_per_sm=-2), dict(variant=3, ctas_per_sm=-3), dict(variant=3, ctas_per_sm=-1, unroll=8),
                 dict(variant=3, ctas_per_sm=-2, threads=32, save_upos=2), dict(variant=3, threads=64, save_upos=2), dict(variant=1), dict(variant=1, scratch=2, threads=32), dict(variant=1, ctas_per_sm=-2, threads=32)):
-        for k in ("variant", "threads", "unroll", "scratch", "ctas_per_sm", "save_upos", "stages"):
+        for k in ("variant", "threads", "unroll", "scratch", "ctas_per_sm", "save_upos", "stages", "stagger"):
             gt.lib.set_option("va." + k, 0)
         set_va(gt, cfg)
         try:
             out, _ = run_va(gt, arrs, 0.15, alignment)
         except gt.lib.GtbError as e:
             # an explicitly requested TMA variant refuses layouts TMA cannot address (auto falls back)
-            assert cfg.get("variant") in (2, 3, 4) and alignment == 1 and e.status == gt.lib.GTB_ERR_LAYOUT
+            assert cfg.get("variant") in (2, 3, 4, 5, 6, 7) and alignment == 1 and e.status == gt.lib.GTB_ERR_LAYOUT
             continue
         inner = (slice(None), slice(3, -3), slice(3, -3))
-        assert np.array_equal(out[inner], oracle.vert_adv(*arrs, 0.15)[inner])
+        assert np.array_equal(out[inner], oracle.vert_adv(*arrs, 0.15)[inner]), cfg
 
 
 def test_vert_adv_full_size(gt, oracle):
@@ -267,7 +270,7 @@ def test_vert_adv_tall_columns(gt, oracle, nk, dtype):
             rng.uniform(-1e-5, 1e-5, shape).astype(dtype)]
     want = oracle.vert_adv(*arrs, 0.15)
     inner = (slice(None), slice(3, -3), slice(3, -3))
-    for cfg in (dict(), dict(variant=4), dict(variant=4, unroll=4), dict(variant=3), dict(variant=3, threads=32, stages=2, ctas_per_sm=-2)):
+    for cfg in (dict(), dict(variant=5), dict(variant=5, ctas_per_sm=-1), dict(variant=5, ctas_per_sm=7, stages=3), dict(variant=6), dict(variant=6, ctas_per_sm=-1), dict(variant=7), dict(variant=7, ctas_per_sm=-1), dict(variant=4), dict(variant=4, unroll=4), dict(variant=3), dict(variant=3, threads=32, stages=2, ctas_per_sm=-2)):
         for k in ("variant", "unroll", "stages", "ctas_per_sm"):
             gt.lib.set_option("va." + k, 0)
         set_va(gt, cfg)
