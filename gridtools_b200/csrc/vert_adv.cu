@@ -1819,8 +1819,10 @@ namespace {
                         if (pass > 0) { // the partner must have read this slot (chunk cb_top - c of the previous strip)
                             while (ctl[0] < need0 + c + 1) {
                             }
-                            __threadfence_block();
-                            tm::fence_after();
+                            if (ph < c_split)
+                                tm::fence_after();
+                            else
+                                __threadfence_block();
                         }
                         if (ph < c_split) {
                             uint32_t w[NW];
@@ -1896,14 +1898,18 @@ namespace {
                 T *o = p.utens_stage.ptr + (active ? i0 + lane : 0) + (int64_t)j * p.utens_stage.sj + (int64_t)(nk - 1) * us_sk;
                 if (active) // last_level :118-121
                     *o = dtr * (data - up_last);
-                for (int cb = cb_top; cb >= 0; --cb) {
-                    if (cb - (SB - 1) >= 0)
-                        issue_b(cb - (SB - 1));
+                // The k-cache is read one chunk ahead of the arithmetic: the TMEM / shared-memory latency of chunk cb-1
+                // hides behind the four levels of chunk cb, and the partner learns early that the slot is free.
+                T bcc[KC], bdc[KC];
+                uint32_t w[NW];
+                auto fetch = [&](int cb) { // issue the loads of chunk cb
                     const int ph = mirrored ? cb_top - cb : cb; // where the strip stored its chunk cb
-                    T bcc[KC], bdc[KC];
-                    if (ph < c_split) {
-                        uint32_t w[NW];
+                    if (ph < c_split)
                         tm::ld<NW>(tw + (uint32_t)(ph * NW), w);
+                    return ph;
+                };
+                auto land = [&](int cb, int ph) { // ... and wait for them; publish the slot as read
+                    if (ph < c_split) {
                         tm::wait_ld();
 #pragma unroll
                         for (int u = 0; u < KC; ++u)
@@ -1919,12 +1925,24 @@ namespace {
                                 bdc[u] = q[u * 64 + 32];
                             }
                         }
+                        __threadfence_block();
                     }
-                    __threadfence_block();
                     __syncwarp();
                     ++done;
                     if (lane == 0)
                         ctl[0] = done; // the slot may be overwritten by the partner's forward sweep
+                };
+                land(cb_top, fetch(cb_top));
+                for (int cb = cb_top; cb >= 0; --cb) {
+                    if (cb - (SB - 1) >= 0)
+                        issue_b(cb - (SB - 1));
+                    T ccv[KC], dcv[KC];
+#pragma unroll
+                    for (int u = 0; u < KC; ++u)
+                        ccv[u] = bcc[u], dcv[u] = bdc[u];
+                    int ph_next = 0;
+                    if (cb > 0)
+                        ph_next = fetch(cb - 1);
                     const int s = b_wait;
                     ptx::mbar_wait(&bfull[s], b_phase);
                     if (++b_wait == SB) {
@@ -1935,13 +1953,16 @@ namespace {
 #pragma unroll
                     for (int u = KC - 1; u >= 0; --u) { // body :111-116
                         if (cb * KC + u <= nk - 2) {
-                            data = bdc[u] - bcc[u] * data;
+                            data = dcv[u] - ccv[u] * data;
                             o -= us_sk;
                             if (active)
                                 *o = dtr * (data - sb[u * 32]);
                         }
                     }
-                    __syncwarp(); // all lanes are done with the ring stage before one lane refills it
+                    if (cb > 0)
+                        land(cb - 1, ph_next);
+                    else
+                        __syncwarp(); // all lanes are done with the ring stage before one lane refills it
                 }
                 if (!more)
                     break;

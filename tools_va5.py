@@ -52,7 +52,7 @@ for dtype in (np.float64, np.float32):
 
 TIMING = {5: [dict(variant=5), dict(variant=5, ctas_per_sm=7)],
           6: [dict(variant=6), dict(variant=6, ctas_per_sm=7)],
-          7: [dict(variant=7, ctas_per_sm=n, stages=st) for n in (0, 8, 7, 6) for st in (0, 3, 2)] + [dict(variant=7, ctas_per_sm=7, stages=4)]}
+          7: [dict(variant=7), dict(variant=7, unroll=2), dict(variant=7, ctas_per_sm=7)]}
 for dtype in (np.float64, np.float32):
     sets = []
     for _ in range(2):
