@@ -70,6 +70,16 @@ _SIG = {
     "gtb_halo_exchange": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
     "gtb_halo_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "gtb_halo_next_epoch": (C.c_int, [C.c_void_p]),
+    "gtb_seq_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "gtb_seq_destroy": (C.c_int, [C.c_void_p]),
+    "gtb_seq_size": (C.c_int, [C.c_void_p]),
+    "gtb_seq_add_hori_diff": (C.c_int, [C.c_void_p, C.c_int, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "gtb_seq_add_vert_adv": (C.c_int, [C.c_void_p, C.c_int, _FP, _FP, _FP, _FP, _FP, C.c_double, C.c_int, C.c_int,
+                                       C.c_int, C.c_void_p]),
+    "gtb_seq_add_halo_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
+    "gtb_seq_add_record": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "gtb_seq_add_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "gtb_seq_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
 }
 
 _lib = None

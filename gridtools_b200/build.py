@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libgtb200.so")
-SOURCES = ["runtime.cu", "copy.cu", "hori_diff.cu", "vert_adv.cu", "halo.cu"]
+SOURCES = ["runtime.cu", "copy.cu", "hori_diff.cu", "vert_adv.cu", "halo.cu", "seq.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -45,6 +45,8 @@ namespace gtb {
         int va_stagger = 0;   // TMEM variant: start stagger between the warps of a CTA, in units of 100 ns
         int copy_vec = 1;     // vectorised copy on/off
         int l2_persist_mb = -1; // L2 set-aside for the k-cache slabs in MB: -1 auto (slab size), 0 off
+        int halo_fused = 0;     // gtb_halo_exchange as ONE launch (pack, signal, wait, unpack); 0: two launches
+        int reserve_sms = 0;    // SMs the persistent stencil grids leave free (for a halo exchange that runs beside them)
     };
     options &opts();
 
@@ -88,6 +90,12 @@ namespace gtb {
     encode_tiled_fn tensor_map_encoder();
 
     constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+    // SMs a persistent stencil grid is sized for: all of them, less the ones reserved for a concurrent halo exchange.
+    inline int stencil_sms(const device_state *d) {
+        const int r = opts().reserve_sms;
+        return r > 0 && r < d->sm_count ? d->sm_count - r : d->sm_count;
+    }
 
 } // namespace gtb
 

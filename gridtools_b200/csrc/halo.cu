@@ -71,7 +71,7 @@ struct gtb_halo {
     bool connected;
     uint64_t epoch; // starts at 1
     int *d_error;   // device flag set by a wait that timed out
-    unsigned *d_counters; // per-direction block counters of the fused pack + signal launch
+    unsigned *d_counters; // block counter of the fused pack + signal launch
 };
 
 namespace {
@@ -82,24 +82,47 @@ namespace {
     int lo_outside(const gtb_halo_desc &h, int e) { return e == 0 ? h.begin : (e == 1 ? h.end + 1 : h.begin - h.minus); }
     int hi_outside(const gtb_halo_desc &h, int e) { return e == 0 ? h.end : (e == 1 ? h.end + h.plus : h.begin - 1); }
 
-    // Fused synchronisation of a transfer launch.  mode 1 (pack towards peers): the last block of every direction
-    // raises the neighbour's flag once all blocks of that direction have made their stores visible system-wide.
-    // mode 2 (unpack): every block first acquires its direction's flag.
+    // Fused synchronisation of a transfer launch.  mode 1 (pack towards peers): the last block of the launch raises
+    // the neighbours' flags once every block has made its stores visible system-wide.  mode 2 (unpack): a block
+    // acquires the flag of a direction before it touches that direction's message.
     struct sync_args {
-        uint64_t *flag[27];
         uint64_t epoch;
-        unsigned *counters;      // [27], zero between launches
-        unsigned blocks_per_dir; // gridDim.x * gridDim.z
+        unsigned *counter; // zero between launches
         int *error;
         long long timeout_cycles;
         int mode; // 0 none, 1 signal after pack, 2 wait before unpack
     };
 
+    constexpr int kMaxSeg = 26;
+    constexpr int kChunk = kThreads * kItems; // elements a block moves per step
+
+    // One launch moves every field of every active direction ("segment").  The work is a flat list of chunks of
+    // kChunk elements, segment-major then field-major, that a SMALL grid walks with a grid stride: the exchange has
+    // to run beside a persistent stencil kernel that owns the SMs, so it must not flood the CTA scheduler -- the first
+    // version launched 27 x n_fields x ceil(count / 1024) blocks, most of them empty, which filled every thread slot
+    // of the chip ahead of the lower-priority stencil launch and serialised the two (profiles/README.md).
+    struct seg_table {
+        int n_seg;
+        int dir[kMaxSeg];             // direction number (0..26) of segment s: reported by a wait that times out
+        region r[kMaxSeg];
+        char *buf[kMaxSeg];           // message buffer per segment (local or NVLink-mapped)
+        uint64_t *flag[kMaxSeg];      // flag to raise (pack) or to wait for (unpack); nullptr: none
+        int chunks_per_field[kMaxSeg];
+        int chunk_start[kMaxSeg + 1]; // prefix sum of chunks_per_field * n_fields
+    };
+
     struct xfer_args {
-        region r[27];
-        char *buf[27]; // message buffer per direction (local or NVLink-mapped)
+        seg_table t;
         char *fields[kMaxFields];
         int64_t s1, s2; // element strides of storage dimensions 1 and 2
+        int n_fields;
+        sync_args sync;
+    };
+
+    struct exchange_args { // pack + signal + wait + unpack in one launch
+        seg_table snd, rcv;
+        char *fields[kMaxFields];
+        int64_t s1, s2;
         int n_fields;
         sync_args sync;
     };
@@ -121,61 +144,96 @@ namespace {
         }
     }
 
-    // PACK: field -> buffer; else buffer -> field.
-    template <class E, bool PACK>
-    __global__ void __launch_bounds__(kThreads) xfer_kernel(const __grid_constant__ xfer_args a) {
-        const int n = blockIdx.y, f = blockIdx.z;
-        const region &r = a.r[n];
-        if (r.count == 0)
-            return;
-        if (!PACK && a.sync.mode == 2 && a.sync.flag[n]) {
-            if (threadIdx.x == 0)
-                wait_flag(a.sync.flag[n], a.sync.epoch, a.sync.error, a.sync.timeout_cycles, n);
-            __syncthreads();
-        }
-        const int64_t base = (int64_t)blockIdx.x * (kThreads * kItems) + threadIdx.x;
-        if (base < r.count) {
-            E *buf = reinterpret_cast<E *>(a.buf[n]) + (int64_t)f * r.count;
-            E *fld = reinterpret_cast<E *>(a.fields[f]);
+    // The chunks of one segment table, walked with a grid stride.  PACK: field -> buffer; else buffer -> field.
+    // WAIT: acquire a segment's flag before its first chunk.
+    template <class E, bool PACK, bool WAIT>
+    __device__ __forceinline__ void move_chunks(const seg_table &t, char *const *fields, int64_t s1, int64_t s2,
+        const sync_args &sy) {
+        const int total = t.chunk_start[t.n_seg];
+        unsigned waited = 0; // segments whose flag this block has acquired (block-uniform)
+        int s = 0;
+        for (int ch = blockIdx.x; ch < total; ch += gridDim.x) {
+            while (ch >= t.chunk_start[s + 1])
+                ++s;
+            if (WAIT && t.flag[s] && !((waited >> s) & 1u)) {
+                if (threadIdx.x == 0)
+                    wait_flag(t.flag[s], sy.epoch, sy.error, sy.timeout_cycles, t.dir[s]);
+                __syncthreads();
+                waited |= 1u << s;
+            }
+            const region &r = t.r[s];
+            const int local = ch - t.chunk_start[s];
+            const int f = local / t.chunks_per_field[s];
+            const int64_t base = (int64_t)(local - f * t.chunks_per_field[s]) * kChunk + threadIdx.x;
+            E *buf = reinterpret_cast<E *>(t.buf[s]) + (int64_t)f * r.count;
+            E *fld = reinterpret_cast<E *>(fields[f]);
             const int l0 = r.len[0], l1 = r.len[1];
             int64_t idx[kItems];
             E v[kItems];
 #pragma unroll
-            for (int t = 0; t < kItems; ++t) {
-                int64_t e = base + (int64_t)t * kThreads;
+            for (int it = 0; it < kItems; ++it) {
+                int64_t e = base + (int64_t)it * kThreads;
                 if (e < r.count) {
                     int64_t q = e / l0;
                     int i0 = (int)(e - q * l0);
                     int64_t q2 = q / l1;
                     int i1 = (int)(q - q2 * l1);
-                    idx[t] = (r.lo[0] + i0) + (r.lo[1] + i1) * a.s1 + (r.lo[2] + q2) * a.s2;
-                    v[t] = PACK ? fld[idx[t]] : buf[e];
+                    idx[it] = (r.lo[0] + i0) + (r.lo[1] + i1) * s1 + (r.lo[2] + q2) * s2;
+                    v[it] = PACK ? fld[idx[it]] : buf[e];
                 }
             }
 #pragma unroll
-            for (int t = 0; t < kItems; ++t) {
-                int64_t e = base + (int64_t)t * kThreads;
+            for (int it = 0; it < kItems; ++it) {
+                int64_t e = base + (int64_t)it * kThreads;
                 if (e < r.count) {
                     if (PACK)
-                        buf[e] = v[t];
+                        buf[e] = v[it];
                     else
-                        fld[idx[t]] = v[t];
+                        fld[idx[it]] = v[it];
                 }
             }
         }
-        if (PACK && a.sync.mode == 1 && a.sync.flag[n]) {
-            __threadfence_system(); // this thread's payload stores are visible to the peer before the block is counted
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                unsigned done = atomicAdd(&a.sync.counters[n], 1u) + 1u;
-                if (done == a.sync.blocks_per_dir) {
-                    a.sync.counters[n] = 0;
-                    __threadfence_system();
-                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.sync.flag[n]), "l"(a.sync.epoch)
-                                 : "memory");
-                }
-            }
+    }
+
+    // After the pack: the last block of the launch raises the neighbours' flags once every block has made its
+    // stores visible system-wide.
+    __device__ __forceinline__ void signal_peers(const seg_table &t, const sync_args &sy, int *s_last) {
+        __threadfence_system(); // this thread's payload stores are visible to the peers before the block is counted
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned done = atomicAdd(sy.counter, 1u) + 1u;
+            *s_last = done == gridDim.x;
+            if (*s_last)
+                *sy.counter = 0;
         }
+        __syncthreads();
+        if (*s_last && threadIdx.x < t.n_seg && t.flag[threadIdx.x]) {
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(t.flag[threadIdx.x]), "l"(sy.epoch) : "memory");
+        }
+    }
+
+    template <class E, bool PACK>
+    __global__ void __launch_bounds__(kThreads) xfer_kernel(const __grid_constant__ xfer_args a) {
+        __shared__ int s_last;
+        if (!PACK && a.sync.mode == 2)
+            move_chunks<E, false, true>(a.t, a.fields, a.s1, a.s2, a.sync);
+        else
+            move_chunks<E, PACK, false>(a.t, a.fields, a.s1, a.s2, a.sync);
+        if (PACK && a.sync.mode == 1)
+            signal_peers(a.t, a.sync, &s_last);
+    }
+
+    // The whole exchange in ONE launch: pack into the neighbours' receive buffers, raise their flags, then acquire
+    // the own flags and unpack.  The grid is small (it fits beside a persistent stencil kernel), so every block is
+    // resident when it starts to wait; a block that waits only depends on the PEERS' pack phases, never on a block of
+    // its own launch that has not started (those only delay the peers' flags until the scheduler places them).
+    template <class E>
+    __global__ void __launch_bounds__(kThreads) exchange_kernel(const __grid_constant__ exchange_args a) {
+        __shared__ int s_last;
+        move_chunks<E, true, false>(a.snd, a.fields, a.s1, a.s2, a.sync);
+        signal_peers(a.snd, a.sync, &s_last);
+        move_chunks<E, false, true>(a.rcv, a.fields, a.s1, a.s2, a.sync);
     }
 
     struct push_args {
@@ -226,56 +284,67 @@ namespace {
 
     constexpr long long kTimeoutCycles = 6000000000ll; // ~3 s at 2 GHz: a lost neighbour must not hang the GPU
 
+    // Segment table of the active directions.  sync_mode 1: flags to raise at the neighbours; 2: own flags to wait for.
+    void fill_table(seg_table &t, const gtb_halo *h, bool pack, char *const bufs[27], int nf, int64_t field_offset,
+        int sync_mode) {
+        const region *regs = pack ? h->send : h->recv;
+        t.n_seg = 0;
+        t.chunk_start[0] = 0;
+        for (int n = 0; n < 27; ++n) {
+            if (n == 13 || !bufs[n] || regs[n].count == 0)
+                continue;
+            const int sg = t.n_seg++;
+            t.dir[sg] = n;
+            t.r[sg] = regs[n];
+            t.buf[sg] = bufs[n] + field_offset * regs[n].count * h->es;
+            t.flag[sg] = nullptr;
+            if (h->nbr[n] >= 0) {
+                if (sync_mode == 1) // the neighbour sees this rank in direction 26 - n
+                    t.flag[sg] = reinterpret_cast<uint64_t *>(h->peer_arena[n]) + (h->epoch & 1) * 32 + (26 - n);
+                else if (sync_mode == 2)
+                    t.flag[sg] = reinterpret_cast<uint64_t *>(h->arena) + (h->epoch & 1) * 32 + n;
+            }
+            t.chunks_per_field[sg] = (int)((regs[n].count + kChunk - 1) / kChunk);
+            t.chunk_start[sg + 1] = t.chunk_start[sg] + t.chunks_per_field[sg] * nf;
+        }
+    }
+
+    void fill_sync(sync_args &sy, const gtb_halo *h, int mode) {
+        sy.mode = mode;
+        sy.epoch = h->epoch;
+        sy.counter = h->d_counters;
+        sy.error = h->d_error;
+        sy.timeout_cycles = kTimeoutCycles;
+    }
+
+    // Blocks of a transfer launch.  Next to a persistent stencil kernel the SMs it leaves free (reserve_sms) hold 8
+    // of these blocks each; otherwise at most one small block per SM.
+    int xfer_grid(int chunks) {
+        device_state *dv = dev();
+        const int rs = opts().reserve_sms;
+        const int cap = rs > 0 ? rs * (2048 / kThreads) : (dv ? dv->sm_count : 128);
+        return chunks < 1 ? 1 : (chunks > cap ? cap : chunks);
+    }
+
     // sync_mode 0: plain copy; 1: raise the neighbours' flags when done (pack); 2: wait for the own flags first (unpack)
     template <bool PACK>
     int run_xfer(gtb_halo *h, void *const *fields, int n_fields, char *const bufs[27], cudaStream_t stream,
         int sync_mode = 0) {
-        int64_t max_count = 0;
-        xfer_args a;
-        a.sync.mode = 0;
-        a.sync.epoch = h->epoch;
-        a.sync.counters = h->d_counters;
-        a.sync.error = h->d_error;
-        a.sync.timeout_cycles = kTimeoutCycles;
-        for (int n = 0; n < 27; ++n)
-            a.sync.flag[n] = nullptr;
-        const region *regs = PACK ? h->send : h->recv;
-        for (int n = 0; n < 27; ++n) {
-            a.r[n] = regs[n];
-            a.buf[n] = bufs[n];
-            if (!bufs[n])
-                a.r[n].count = 0;
-            if (a.r[n].count > max_count)
-                max_count = a.r[n].count;
-        }
-        if (max_count == 0)
-            return GTB_OK;
-        a.s1 = h->d[0].total;
-        a.s2 = (int64_t)h->d[0].total * h->d[1].total;
         for (int f0 = 0; f0 < n_fields; f0 += kMaxFields) {
-            int nf = n_fields - f0 < kMaxFields ? n_fields - f0 : kMaxFields;
-            for (int f = 0; f < nf; ++f)
-                a.fields[f] = static_cast<char *>(fields[f0 + f]);
-            a.n_fields = nf;
-            xfer_args b = a;
-            for (int n = 0; n < 27; ++n)
-                if (b.buf[n])
-                    b.buf[n] += (int64_t)f0 * b.r[n].count * h->es;
-            dim3 grid((unsigned)((max_count + kThreads * kItems - 1) / (kThreads * kItems)), 27, nf);
+            const int nf = n_fields - f0 < kMaxFields ? n_fields - f0 : kMaxFields;
             const bool first = f0 == 0, last = f0 + nf >= n_fields;
-            if ((sync_mode == 1 && last) || (sync_mode == 2 && first)) {
-                b.sync.mode = sync_mode;
-                b.sync.blocks_per_dir = grid.x * grid.z;
-                for (int n = 0; n < 27; ++n) {
-                    if (n == 13 || h->nbr[n] < 0 || b.r[n].count == 0)
-                        continue;
-                    if (sync_mode == 1) // the neighbour sees this rank in direction 26 - n
-                        b.sync.flag[n] =
-                            reinterpret_cast<uint64_t *>(h->peer_arena[n]) + (h->epoch & 1) * 32 + (26 - n);
-                    else
-                        b.sync.flag[n] = reinterpret_cast<uint64_t *>(h->arena) + (h->epoch & 1) * 32 + n;
-                }
-            }
+            const int mode = (sync_mode == 1 && last) || (sync_mode == 2 && first) ? sync_mode : 0;
+            xfer_args b;
+            fill_table(b.t, h, PACK, bufs, nf, f0, mode);
+            if (b.t.n_seg == 0)
+                return GTB_OK;
+            fill_sync(b.sync, h, mode);
+            b.s1 = h->d[0].total;
+            b.s2 = (int64_t)h->d[0].total * h->d[1].total;
+            for (int f = 0; f < nf; ++f)
+                b.fields[f] = static_cast<char *>(fields[f0 + f]);
+            b.n_fields = nf;
+            const int grid = xfer_grid(b.t.chunk_start[b.t.n_seg]);
             if (h->es == 8)
                 xfer_kernel<uint64_t, PACK><<<grid, kThreads, 0, stream>>>(b);
             else
@@ -623,7 +692,43 @@ GTB_API int gtb_halo_wait_unpack(gtb_halo *h, void *const *fields, int n_fields,
 }
 
 GTB_API int gtb_halo_exchange(gtb_halo *h, void *const *fields, int n_fields, void *stream) {
-    int st = gtb_halo_pack_send(h, fields, n_fields, stream);
+    int st = check_fields(h, fields, n_fields, "gtb_halo_exchange");
+    if (st)
+        return st;
+    if (!h->connected)
+        return fail(GTB_ERR_STATE, "gtb_halo_exchange: gtb_halo_connect has not been called");
+    if (n_fields >= 1 && n_fields <= kMaxFields && opts().halo_fused) { // one launch: pack, signal, wait, unpack
+        char *sbufs[27], *rbufs[27];
+        for (int n = 0; n < 27; ++n) {
+            sbufs[n] = h->send[n].count ? peer_slot(h, n, h->epoch) : nullptr;
+            rbufs[n] = h->recv[n].count ? recv_slot(h, n, h->epoch) : nullptr;
+        }
+        exchange_args a;
+        fill_table(a.snd, h, true, sbufs, n_fields, 0, 1);
+        fill_table(a.rcv, h, false, rbufs, n_fields, 0, 2);
+        if (a.snd.n_seg == 0 && a.rcv.n_seg == 0)
+            return gtb_halo_next_epoch(h);
+        fill_sync(a.sync, h, 1);
+        a.s1 = h->d[0].total;
+        a.s2 = (int64_t)h->d[0].total * h->d[1].total;
+        for (int f = 0; f < n_fields; ++f)
+            a.fields[f] = static_cast<char *>(fields[f]);
+        a.n_fields = n_fields;
+        const int cs = a.snd.chunk_start[a.snd.n_seg], cr = a.rcv.chunk_start[a.rcv.n_seg];
+        int grid = xfer_grid(cs > cr ? cs : cr);
+        if (grid > 64)
+            grid = 64; // every block must be resident while it waits for the peers
+        if (h->es == 8)
+            exchange_kernel<uint64_t><<<grid, kThreads, 0, as_stream(stream)>>>(a);
+        else
+            exchange_kernel<uint32_t><<<grid, kThreads, 0, as_stream(stream)>>>(a);
+        count_launch();
+        st = check_launch("halo exchange");
+        if (st)
+            return st;
+        return gtb_halo_next_epoch(h);
+    }
+    st = gtb_halo_pack_send(h, fields, n_fields, stream);
     if (st)
         return st;
     st = gtb_halo_wait_unpack(h, fields, n_fields, stream);

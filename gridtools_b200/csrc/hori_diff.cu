@@ -326,7 +326,7 @@ namespace {
         const int64_t items = (int64_t)p.tiles_i * p.tiles_j * p.nk;
         if (items >= (int64_t)1 << 31)
             return fail(GTB_ERR_ARG, "gtb_hori_diff: domain too large (%lld tile-levels)", (long long)items);
-        int grid = d->sm_count * ctas_per_sm;
+        int grid = stencil_sms(d) * ctas_per_sm;
         if (grid > items)
             grid = (int)items;
         p.step_i = grid % p.tiles_i;

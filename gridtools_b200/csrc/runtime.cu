@@ -174,6 +174,8 @@ namespace {
             {"va.debug", &o.va_debug},
             {"va.stages", &o.va_stages},
             {"va.stagger", &o.va_stagger},
+            {"reserve_sms", &o.reserve_sms},
+            {"halo.fused", &o.halo_fused},
             {"copy.vec", &o.copy_vec}};
         for (auto &t : table)
             if (strcmp(t.name, key) == 0)

@@ -2294,7 +2294,7 @@ namespace {
         if (!p.tickets)
             return GTB_ERR_ALLOC;
         const int64_t strips = (int64_t)p.tiles_i * p.nj;
-        int grid = o.va_ctas_per_sm < 0 ? -o.va_ctas_per_sm : d->sm_count;
+        int grid = o.va_ctas_per_sm < 0 ? -o.va_ctas_per_sm : stencil_sms(d);
         if ((int64_t)grid * warps > strips)
             grid = (int)((strips + warps - 1) / warps);
         int st = set_l2_persist(0);
@@ -2343,7 +2343,7 @@ namespace {
         if (!p.tickets)
             return GTB_ERR_ALLOC;
         const int64_t strips = (int64_t)p.tiles_i * p.nj;
-        int grid = o.va_ctas_per_sm < 0 ? -o.va_ctas_per_sm : d->sm_count;
+        int grid = o.va_ctas_per_sm < 0 ? -o.va_ctas_per_sm : stencil_sms(d);
         if ((int64_t)grid * warps > strips)
             grid = (int)((strips + warps - 1) / warps);
         int st = set_l2_persist(0);
@@ -2396,7 +2396,7 @@ namespace {
         p.tickets = va_ticket_counters();
         if (!p.tickets)
             return GTB_ERR_ALLOC;
-        int grid = o.va_ctas_per_sm < 0 ? -o.va_ctas_per_sm : d->sm_count;
+        int grid = o.va_ctas_per_sm < 0 ? -o.va_ctas_per_sm : stencil_sms(d);
         if ((int64_t)grid * pairs > strips)
             grid = (int)((strips + pairs - 1) / pairs);
         int st = set_l2_persist(0);
@@ -2452,7 +2452,7 @@ namespace {
         const int wps = o.va_ctas_per_sm > 0 ? o.va_ctas_per_sm : 7; // warps per SM
         const int64_t strips = (int64_t)p.tiles_i * p.nj;
         p.items = (int)strips;
-        int grid = o.va_ctas_per_sm < 0 ? -o.va_ctas_per_sm : wps * d->sm_count;
+        int grid = o.va_ctas_per_sm < 0 ? -o.va_ctas_per_sm : wps * stencil_sms(d);
         if (grid > strips)
             grid = (int)strips;
         if (tmem) {

@@ -151,6 +151,72 @@ def plan(name, *stores, grid: Grid = None, **scalars):
     return run
 
 
+class Sequence:
+    """Recorded time loop (gtb_seq, include/gtb200.h): stencil launches, halo exchanges and the event record / wait
+    operations between streams are recorded once and replayed slice by slice with one native call each -- the
+    per-call cost of the reference's own C++ driver loop (copy_stencil_parallel.cpp:126-145) instead of ctypes'.
+
+        seq = Sequence()
+        seq.wait(comm, 0); seq.halo_exchange(he, [field], comm); seq.record(1, comm)
+        seq.wait(comp, 1); seq.horizontal_diffusion(inp, coeff, out, stream=comp); seq.record(0, comp)
+        seq.run()            # or seq.run(first, count)
+
+    Streams are raw cudaStream_t handles (ints / c_void_p).  Stores and halo objects must outlive the sequence."""
+
+    def __init__(self):
+        h = C.c_void_p()
+        _lib.check(_lib.lib().gtb_seq_create(C.byref(h)))
+        self._h = h
+        self._keep = []
+
+    def __len__(self):
+        return _lib.lib().gtb_seq_size(self._h)
+
+    def horizontal_diffusion(self, inp, coeff, out, grid: Grid = None, stream=None):
+        g = _grid_of(inp, grid)
+        dt = _same_dtype(inp, coeff, out)
+        f = [inp.field(True, g.origin), coeff.field(True, g.origin), out.field(False, g.origin)]
+        _lib.check(_lib.lib().gtb_seq_add_hori_diff(self._h, dt.itemsize, *[C.byref(x) for x in f], g.ni, g.nj, g.nk,
+                                                    stream))
+        self._keep.append((inp, coeff, out))
+
+    def vertical_advection_dycore(self, utens_stage, u_stage, wcon, u_pos, utens, dtr_stage, grid: Grid = None,
+                                  stream=None):
+        g = _grid_of(utens_stage, grid)
+        dt = _same_dtype(utens_stage, u_stage, wcon, u_pos, utens)
+        f = [utens_stage.field(False, g.origin)] + [s.field(True, g.origin) for s in (u_stage, wcon, u_pos, utens)]
+        _lib.check(_lib.lib().gtb_seq_add_vert_adv(self._h, dt.itemsize, *[C.byref(x) for x in f], float(dtr_stage),
+                                                   g.ni, g.nj, g.nk, stream))
+        self._keep.append((utens_stage, u_stage, wcon, u_pos, utens))
+
+    def halo_exchange(self, he, fields, stream=None):
+        """pack + exchange + unpack of `fields` through the halo_exchange_dynamic_ut `he` (p2p transport)."""
+        arr, n = he._ptrs(list(fields))
+        _lib.check(_lib.lib().gtb_seq_add_halo_exchange(self._h, he._h, arr, n, stream))
+        self._keep.append((he, fields))
+
+    def record(self, event, stream=None):
+        _lib.check(_lib.lib().gtb_seq_add_record(self._h, int(event), stream))
+
+    def wait(self, stream, event):
+        _lib.check(_lib.lib().gtb_seq_add_wait(self._h, stream, int(event)))
+
+    def run(self, first=0, count=None):
+        n = len(self) - first if count is None else count
+        _lib.check(_lib.lib().gtb_seq_run(self._h, int(first), int(n)))
+
+    def close(self):
+        if self._h is not None:
+            _lib.lib().gtb_seq_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def as_numpy_interior(ds: DataStore, grid: Grid = None):
     g = _grid_of(ds, grid)
     a = ds.const_host_view()

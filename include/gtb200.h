@@ -173,7 +173,7 @@ int gtb_halo_unpack(gtb_halo *h, void *const *fields, int n_fields, void *stream
  * message (needs connect).  Together with gtb_halo_pack_send an exchange is two launches and no host synchronisation,
  * against up to 12 x n_fields launches, a cudaDeviceSynchronize and 2 x 26 MPI calls in the reference. */
 int gtb_halo_wait_unpack(gtb_halo *h, void *const *fields, int n_fields, void *stream);
-/* pack_send + wait_unpack + next_epoch in one call (two launches on `stream`): the whole
+/* pack_send + wait_unpack + next_epoch in one call (two launches on `stream`, or one with option "halo.fused"): the whole
  * pack() / exchange() / unpack() sequence of halo_exchange_dynamic_ut (gcl/halo_exchange.hpp:250-304) for hosts that do
  * not need the phases separately. */
 int gtb_halo_exchange(gtb_halo *h, void *const *fields, int n_fields, void *stream);
@@ -183,6 +183,31 @@ int gtb_halo_error(gtb_halo *h, int *code);
 /* Advances the epoch after unpack (double-buffered arenas: a neighbour may already send epoch e+1 while this rank
  * still unpacks epoch e). */
 int gtb_halo_next_epoch(gtb_halo *h);
+
+/* ------------------------------------------------------------------------------------- recorded call sequences
+ * The reference's user programs drive their time loop from C++ (tests/regression/gcl/copy_stencil_parallel.cpp:126-145:
+ * he.pack / he.exchange / he.unpack followed by run(spec, backend, grid, fields...)), a microsecond or two of host
+ * time per call.  Hosts that reach this library through ctypes / JNI / cgo pay several microseconds per call, more
+ * than a 256x256x80 stencil step leaves.  A gtb_seq records such a loop once -- stencil launches, halo exchanges and
+ * the event record / wait operations that order a compute stream against a communication stream -- and
+ * gtb_seq_run() issues any slice of it in recorded order with ONE call.  Fields and halo objects are borrowed and must
+ * outlive the sequence.  Event numbers are small non-negative slots owned by the sequence (timing disabled);
+ * a wait refers to the most recent record of that slot at the time it is issued, as with cudaStreamWaitEvent. */
+typedef struct gtb_seq gtb_seq;
+int gtb_seq_create(gtb_seq **out);
+int gtb_seq_destroy(gtb_seq *s);
+int gtb_seq_size(const gtb_seq *s);
+/* elem_size 8 -> gtb_hori_diff_f64 / gtb_vert_adv_f64, 4 -> the _f32 entry points */
+int gtb_seq_add_hori_diff(gtb_seq *s, int elem_size, const gtb_field *in, const gtb_field *coeff, const gtb_field *out,
+    int ni, int nj, int nk, void *stream);
+int gtb_seq_add_vert_adv(gtb_seq *s, int elem_size, const gtb_field *utens_stage, const gtb_field *u_stage,
+    const gtb_field *wcon, const gtb_field *u_pos, const gtb_field *utens, double dtr_stage, int ni, int nj, int nk,
+    void *stream);
+int gtb_seq_add_halo_exchange(gtb_seq *s, gtb_halo *h, void *const *fields, int n_fields, void *stream);
+int gtb_seq_add_record(gtb_seq *s, int event, void *stream);
+int gtb_seq_add_wait(gtb_seq *s, void *stream, int event);
+/* Issues operations [first, first + count) of the sequence. */
+int gtb_seq_run(gtb_seq *s, int first, int count);
 
 #ifdef __cplusplus
 }
