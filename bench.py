@@ -49,7 +49,15 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--stencil", default="vert_adv", choices=["vert_adv", "hori_diff"])
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / secondary stencil")
-    return ap.parse_args()
+    ap.add_argument("--ni", type=int, default=256, help="interior size in i (per GPU for weak, global for strong scaling)")
+    ap.add_argument("--nj", type=int, default=256)
+    ap.add_argument("--nk", type=int, default=80)
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    a = ap.parse_args()
+    global NI, NJ, NK
+    NI, NJ, NK = a.ni, a.nj, a.nk
+    return a
 
 
 # --------------------------------------------------------------------------------------- synthetic fields
@@ -80,6 +88,36 @@ def repo_hori_diff(ni, nj, nk, i_off=0, j_off=0, gi=None, gj=None):
     inp = 5. + 8 * (2. + np.cos(np.pi * (x + 1.5 * y)) + np.sin(2 * np.pi * (x + 1.5 * y))) / 4. + 0. * k
     shape = (nk, nj + 4, ni + 4)
     return np.ascontiguousarray(np.broadcast_to(inp, shape)), np.full(shape, 0.025)
+
+
+def device_fields(torch, storage, name, ni, nj, nk, dtype, i_off=0, j_off=0, gi=None, gj=None):
+    """The same analytic fields evaluated on the device, straight into the stores' target tensors: a 4096x4096x80
+    field is 10.7 GB, which neither a numpy temporary nor a pinned host mirror should have to hold."""
+    H = HALO[name]
+    d0, d1 = (gi or ni) + 2 * H, (gj or nj) + 2 * H
+    tdt = torch.float64
+    i = (torch.arange(ni + 2 * H, device="cuda", dtype=tdt) + i_off).view(1, 1, -1)
+    j = (torch.arange(nj + 2 * H, device="cuda", dtype=tdt) + j_off).view(1, -1, 1)
+    k = torch.arange(nk, device="cuda", dtype=tdt).view(-1, 1, 1)
+    x, y, z = i / d0, j / d1, k / nk
+    pi = np.pi
+
+    def store(expr):
+        ds = storage.builder.type(dtype).dimensions(ni + 2 * H, nj + 2 * H, nk).halos(H, H, 0).build()
+        t = ds.target_tensor()
+        t[:, :, :ni + 2 * H] = (expr + 0 * (x + y + z)).to(t.dtype)
+        return ds
+
+    if name == "hori_diff":
+        inp = 5. + 8 * (2. + torch.cos(pi * (x + 1.5 * y)) + torch.sin(2 * pi * (x + 1.5 * y))) / 4.
+        return [store(inp), store(torch.full((1, 1, 1), 0.025, device="cuda", dtype=tdt)),
+                store(torch.zeros((1, 1, 1), device="cuda", dtype=tdt))], None
+    t = x + y
+    u = 7.0 + torch.cos(pi * t) + torch.sin(2 * pi * t)
+    wcon = 2e-4 * (-1.07 + (2. + torch.cos(pi * (x + z)) + torch.cos(pi * y)) / 2.)
+    utens = 3e-6 * (-1.0235 + (2. + torch.cos(pi * (x + y)) + torch.cos(pi * y * z)) / 2.)
+    us = 7.0 + 1.25 * (2. + torch.cos(pi * (x + y)) + torch.sin(2 * pi * (x + y))) + 0.1 * k
+    return [store(us), store(u), store(wcon), store(u), store(utens)], 3. / 20.
 
 
 # --------------------------------------------------------------------------------------- clocks sampler
@@ -230,21 +268,39 @@ def b200_arm(args):
         torch.cuda.synchronize()
 
     # ---- fields: two rotating sets per rank
+    global NI, NJ
     dims = gcl.ProcGrid.dims_create(world)
     grid = gcl.ProcGrid(dims, (False, False, False), rank)
-    i_off, j_off = grid.coords[0] * NI, grid.coords[1] * NJ
     name = args.stencil
     H = HALO[name]
+    np_dtype = np.float64 if args.dtype == "f64" else np.float32
+    itemsize = np.dtype(np_dtype).itemsize
+    global_ni, global_nj = (NI, NJ) if args.scaling == "strong" else (NI * dims[0], NJ * dims[1])
+    if args.scaling == "strong":  # the global domain is divided among the ranks
+        if NI % dims[0] or NJ % dims[1]:
+            raise SystemExit("bench.py: --scaling strong needs sizes divisible by the %dx%d process grid" % dims[:2])
+        NI, NJ = NI // dims[0], NJ // dims[1]
+    i_off, j_off = grid.coords[0] * NI, grid.coords[1] * NJ
+    n_fields = 5 if name == "vert_adv" else 3
+    set_bytes = n_fields * (NI + 2 * H + 16) * (NJ + 2 * H) * NK * itemsize
+    # enough rotating sets that no step finds its inputs in the 126 MB L2; one set when a set alone is far larger
+    n_sets = 1 if set_bytes > (1 << 30) else (2 if name == "vert_adv" else 3)
+    on_device = NI * NJ * NK > 32 * 2**20
     sets = []
-    n_sets = 2 if name == "vert_adv" else 3
+    dtr = None
     for s in range(n_sets):
-        if name == "vert_adv":
-            arrs, dtr = repo_vert_adv(NI, NJ, NK, i_off, j_off, NI * dims[0], NJ * dims[1])
-            sets.append([storage.from_numpy(a, (H, H, 0)) for a in arrs])
+        if on_device:
+            st, dtr_ = device_fields(torch, storage, name, NI, NJ, NK, np_dtype, i_off, j_off, global_ni, global_nj)
+            dtr = dtr_ if dtr_ is not None else dtr
+            sets.append(st)
+        elif name == "vert_adv":
+            arrs, dtr = repo_vert_adv(NI, NJ, NK, i_off, j_off, global_ni, global_nj)
+            sets.append([storage.from_numpy(a.astype(np_dtype), (H, H, 0)) for a in arrs])
         else:
-            inp, coeff = repo_hori_diff(NI, NJ, NK, i_off, j_off, NI * dims[0], NJ * dims[1])
-            sets.append([storage.from_numpy(inp, (H, H, 0)), storage.from_numpy(coeff, (H, H, 0)),
-                         storage.from_numpy(np.zeros_like(inp), (H, H, 0))])
+            inp, coeff = repo_hori_diff(NI, NJ, NK, i_off, j_off, global_ni, global_nj)
+            sets.append([storage.from_numpy(inp.astype(np_dtype), (H, H, 0)),
+                         storage.from_numpy(coeff.astype(np_dtype), (H, H, 0)),
+                         storage.from_numpy(np.zeros_like(inp, dtype=np_dtype), (H, H, 0))])
     for st in sets:
         for f in st:
             f.const_target_tensor()  # upload now
@@ -252,7 +308,7 @@ def b200_arm(args):
     # ---- halo exchange object (N > 1): the field with an IJ extent (wcon resp. in), one per set
     he = None
     if world > 1:
-        he = gcl.halo_exchange_dynamic_ut((False, False, False), grid, np.float64, comm=gcl.TorchComm(),
+        he = gcl.halo_exchange_dynamic_ut((False, False, False), grid, np_dtype, comm=gcl.TorchComm(),
                                           transport="p2p")
         f0 = sets[0][0]
         p0, d1, d2 = f0.padded_lengths
@@ -351,6 +407,7 @@ def b200_arm(args):
     ms_per_step = total_ms / args.steps
     pts = NI * NJ * NK
     value = n_gpus * pts / (ms_per_step * 1e-3) / 1e6
+    default_size = (NI, NJ, NK) == (256, 256, 80) and args.scaling == "weak"
 
     # ---- roofline of the dominant kernel (the stencil kernel: the only launch of a step at N = 1)
     # launch_ms: average duration of one stencil launch inside the timed region.  At N = 1 a step IS one launch, so
@@ -369,34 +426,43 @@ def b200_arm(args):
     launch_ms = ms_per_step if world == 1 else isolated_ms
     clocks = sampler.stop()
     peak, peak_src = measured_peak()
-    achieved = ALGO_BYTES[name] * pts / (launch_ms * 1e-3) / 1e9
+    algo_bytes = ALGO_BYTES[name] * itemsize // 8
+    achieved = algo_bytes * pts / (launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic_from_profile(name), "peak_source": peak_src,
                 "kernel": "va_pair_kernel" if name == "vert_adv" else "hd_tma_kernel", "launch_ms": launch_ms,
                 "launch_ms_source": "timed region / steps (one launch per step)" if world == 1 else
                 "events around each stencil launch", "isolated_launch_ms": isolated_ms,
-                "algorithmic_bytes_per_launch": ALGO_BYTES[name] * pts,
+                "algorithmic_bytes_per_launch": algo_bytes * pts,
                 "frac_of_nominal_8TBs": achieved / 8000.0}
 
     line = {
-        "metric": "Mpts/s %s %dx%dx%d fp64" % (name, NI, NJ, NK), "value": value, "unit": "Mpts/s",
+        "metric": "Mpts/s %s %dx%dx%d %s" % (name, global_ni if args.scaling == "strong" else NI,
+                                              global_nj if args.scaling == "strong" else NJ, NK,
+                                              "fp64" if itemsize == 8 else "fp32"), "value": value, "unit": "Mpts/s",
         "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": value / n_gpus / P100_MPTS[name] if n_gpus == 1
-        else None, "dtype": "f64", "data": "synthetic (reference repository's analytic fields)",
-        "config": {"workload": "%s %dx%dx%d fp64 per GPU (BASELINE.json configs[1] family)" % (name, NI, NJ, NK),
+        "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": value / n_gpus / P100_MPTS[name] if n_gpus == 1 and default_size and itemsize == 8 else None,
+        "dtype": args.dtype, "data": "synthetic (reference repository's analytic fields%s)" % (
+            ", evaluated on the device" if on_device else ""),
+        "config": {"workload": "%s %dx%dx%d %s per GPU%s" % (
+            name, NI, NJ, NK, "fp64" if itemsize == 8 else "fp32",
+            " (BASELINE.json configs[1] family)" if default_size else
+            " (%s scaling of a %dx%dx%d global domain)" % (args.scaling, global_ni, global_nj, NK)),
                    "decomposition": "%dx%dx1 IJ process grid, halo exchange of %s every step over NVLink (fused pack + peer "
                                     "stores, device-side flags), overlapped with the previous step's stencil on a "
                                     "high-priority stream; %d SMs reserved for it; loop issued as one recorded gtb_seq" % (
                        dims[0], dims[1], "wcon" if name == "vert_adv" else "in", RESERVE_SMS) if world > 1 else "single GPU",
-                   "l2": "inputs of one step (%d MB) exceed L2 and %d field sets are rotated" % (
-                       sum(f.nbytes_host for f in sets[0]) // 2**20, n_sets),
+                   "l2": "inputs of one step (%d MB) exceed L2 and %d field set(s) are rotated" % (
+                       sum(f.nbytes_host for f in sets[0][:5 if name == "vert_adv" else 2]) // 2**20, n_sets),
                    "vs_baseline_ref": "reference stencil::gpu on P100, BASELINE.md section 1"},
         "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
         "step_ms_median": statistics.median(per_step), "step_ms_p90": sorted(per_step)[int(0.9 * len(per_step))],
         "step_ms_max": max(per_step),
     }
 
-    if not args.no_extras:  # every rank moves its own sub-domain over its own PCIe link; max over ranks
+    extras = not args.no_extras and default_size and itemsize == 8 and not on_device
+    if extras:  # every rank moves its own sub-domain over its own PCIe link; max over ranks
         e = e2e(torch, stencil, storage, name, sets, dtr if name == "vert_adv" else None, args, n_gpus)
         if world > 1:
             t = torch.tensor([e["ms_per_step"]], device="cuda", dtype=torch.float64)
@@ -404,7 +470,7 @@ def b200_arm(args):
             e["ms_per_step"] = float(t.item())
             e["value"] = n_gpus * pts / (e["ms_per_step"] * 1e-3) / 1e6
         line["e2e"] = e
-    if rank == 0 and not args.no_extras and world == 1:
+    if rank == 0 and extras and world == 1:
         try:
             backend, times, cores = time_reference(name, 20, 2)
             sec = statistics.median(times)
@@ -425,40 +491,72 @@ def b200_arm(args):
 
 def e2e(torch, stencil, storage, name, sets, dtr, args, n_gpus):
     """Same metric through the public API with host buffers: every step copies the step's input fields from pinned
-    host memory to the device, runs the stencil and copies the result back to the host."""
-    st = sets[0]
-    steps = max(3, min(args.steps, 20))
+    host memory to the device, runs the stencil and copies the result back to the host.  The three phases of
+    consecutive steps are software-pipelined over the rotating device sets the way a user of the storage API would
+    do it (upload of step n+1 and download of step n-1 run beside the stencil of step n: PCIe is full duplex), so a
+    step costs max(upload, stencil, download) instead of their sum; nothing is skipped or cached."""
+    steps = max(4, min(args.steps, 20))
     n_in = 5 if name == "vert_adv" else 2
-    out = st[0] if name == "vert_adv" else st[2]
-    h2d = sum(f.nbytes_host for f in st[:n_in])
-    d2h = out.nbytes_host
-    for f in st:
-        f.const_host_view()
+    oi = 0 if name == "vert_adv" else 2
+    h2d = sum(f.nbytes_host for f in sets[0][:n_in])
+    d2h = sets[0][oi].nbytes_host
+    for st in sets:
+        for f in st:
+            f.const_host_view()
+    comp = torch.cuda.current_stream()
+    up, down = torch.cuda.Stream(), torch.cuda.Stream()
+    n = len(sets)
+    total = steps + 3
+    ev_up = [torch.cuda.Event() for _ in range(total + 1)]
+    ev_run = [torch.cuda.Event() for _ in range(total + 1)]
+    ev_down = [torch.cuda.Event() for _ in range(total + 1)]
 
-    def one():
-        for f in st[:n_in]:
-            f.update_target_async()
+    def upload(s):  # inputs of step s; the set was last used by step s - n (its stencil read them, its download read the result)
+        with torch.cuda.stream(up):
+            if s - n >= 0:
+                up.wait_event(ev_run[s - n])
+                up.wait_event(ev_down[s - n])  # in-place result (vert_adv) is an input buffer too
+            for f in sets[s % n][:n_in]:
+                f.update_target_async()
+            ev_up[s].record(up)
+
+    def run(s):
+        comp.wait_event(ev_up[s])
+        if s - n >= 0:
+            comp.wait_event(ev_down[s - n])  # the result buffer of this set has been read back
         if name == "vert_adv":
-            stencil.vertical_advection_dycore(*st, dtr)
+            stencil.vertical_advection_dycore(*sets[s % n], dtr)
         else:
-            stencil.horizontal_diffusion(*st)
-        out.update_host_async()
+            stencil.horizontal_diffusion(*sets[s % n])
+        ev_run[s].record(comp)
 
-    for _ in range(3):
-        one()
+    def download(s):
+        with torch.cuda.stream(down):
+            down.wait_event(ev_run[s])
+            sets[s % n][oi].update_host_async()
+            ev_down[s].record(down)
+
+    def one(s):
+        if s == 0:
+            upload(0)
+        if s + 1 < total:
+            upload(s + 1)
+        run(s)
+        download(s)
+
+    for s in range(3):
+        one(s)
     torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
-    a.record()
-    for _ in range(steps):
-        one()
-    b.record()
+    for s in range(3, total):
+        one(s)
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) / steps
-    ms = max(a.elapsed_time(b) / steps, wall * 1e3)
+    ms = wall * 1e3
     return {"value": n_gpus * NI * NJ * NK / (ms * 1e-3) / 1e6, "unit": "Mpts/s",
             "h2d_bytes_per_step": int(h2d) * n_gpus, "d2h_bytes_per_step": int(d2h) * n_gpus, "ms_per_step": ms,
-            "steps": steps}
+            "steps": steps, "pipelined": "upload(n+1) | stencil(n) | download(n-1) on three streams",
+            "timed_by": "host wall clock around %d steps, device synchronised on both sides" % steps}
 
 
 def secondary(torch, stencil, storage, name, peak):

@@ -76,6 +76,7 @@ _SIG = {
     "gtb_seq_add_hori_diff": (C.c_int, [C.c_void_p, C.c_int, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gtb_seq_add_vert_adv": (C.c_int, [C.c_void_p, C.c_int, _FP, _FP, _FP, _FP, _FP, C.c_double, C.c_int, C.c_int,
                                        C.c_int, C.c_void_p]),
+    "gtb_seq_add_prepare_tracers": (C.c_int, [C.c_void_p, _FP, _FP, C.c_int, _FP, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gtb_seq_add_halo_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
     "gtb_seq_add_record": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "gtb_seq_add_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),

@@ -29,7 +29,7 @@ namespace {
 
     constexpr int kMaxFields = 16; // per launch; more fields are handled by looping launches
     constexpr int kThreads = 256;
-    constexpr int kItems = 4;
+    constexpr int kItems = 8;
     constexpr uint64_t kMagic = 0x6774623230306831ull; // "gtb200h1"
     constexpr int64_t kFlagBytes = 2 * 32 * 8;         // flags[parity][direction], uint64 epoch numbers
     constexpr int64_t kAlign = 256;

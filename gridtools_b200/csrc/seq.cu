@@ -15,7 +15,7 @@
 using namespace gtb;
 
 namespace {
-    enum op_kind { OP_HD64, OP_HD32, OP_VA64, OP_VA32, OP_HALO, OP_RECORD, OP_WAIT };
+    enum op_kind { OP_HD64, OP_HD32, OP_VA64, OP_VA32, OP_TRACERS, OP_HALO, OP_RECORD, OP_WAIT };
 
     struct op {
         op_kind kind;
@@ -25,6 +25,7 @@ namespace {
         void *stream;
         gtb_halo *halo;
         std::vector<void *> ptrs;
+        std::vector<gtb_field> outs, ins; // prepare_tracers
         int event;
     };
 } // namespace
@@ -96,6 +97,21 @@ GTB_API int gtb_seq_add_vert_adv(gtb_seq *s, int elem_size, const gtb_field *ute
     return GTB_OK;
 }
 
+GTB_API int gtb_seq_add_prepare_tracers(gtb_seq *s, const gtb_field *out, const gtb_field *in, int n_tracers,
+    const gtb_field *rho, int ni, int nj, int nk, void *stream) {
+    if (!s || !out || !in || !rho || n_tracers < 0)
+        return fail(GTB_ERR_ARG, "gtb_seq_add_prepare_tracers: bad argument");
+    op o{};
+    o.kind = OP_TRACERS;
+    o.outs.assign(out, out + n_tracers);
+    o.ins.assign(in, in + n_tracers);
+    o.f[0] = *rho;
+    o.ni = ni, o.nj = nj, o.nk = nk;
+    o.stream = stream;
+    s->ops.push_back(o);
+    return GTB_OK;
+}
+
 GTB_API int gtb_seq_add_halo_exchange(gtb_seq *s, gtb_halo *h, void *const *fields, int n_fields, void *stream) {
     if (!s || !h || !fields || n_fields < 0)
         return fail(GTB_ERR_ARG, "gtb_seq_add_halo_exchange: bad argument");
@@ -156,6 +172,10 @@ GTB_API int gtb_seq_run(gtb_seq *s, int first, int count) {
             break;
         case OP_VA32:
             st = gtb_vert_adv_f32(&o.f[0], &o.f[1], &o.f[2], &o.f[3], &o.f[4], (float)o.scalar, o.ni, o.nj, o.nk,
+                o.stream);
+            break;
+        case OP_TRACERS:
+            st = gtb_prepare_tracers_f64(o.outs.data(), o.ins.data(), (int)o.outs.size(), &o.f[0], o.ni, o.nj, o.nk,
                 o.stream);
             break;
         case OP_HALO:

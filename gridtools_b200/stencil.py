@@ -189,6 +189,15 @@ class Sequence:
                                                    g.ni, g.nj, g.nk, stream))
         self._keep.append((utens_stage, u_stage, wcon, u_pos, utens))
 
+    def prepare_tracers(self, outs, ins, rho, grid: Grid = None, stream=None):
+        g = _grid_of(rho, grid)
+        n = len(outs)
+        fo = (_lib.Field * max(n, 1))(*[s.field(False, g.origin) for s in outs])
+        fi = (_lib.Field * max(n, 1))(*[s.field(True, g.origin) for s in ins])
+        fr = rho.field(True, g.origin)
+        _lib.check(_lib.lib().gtb_seq_add_prepare_tracers(self._h, fo, fi, n, C.byref(fr), g.ni, g.nj, g.nk, stream))
+        self._keep.append((outs, ins, rho))
+
     def halo_exchange(self, he, fields, stream=None):
         """pack + exchange + unpack of `fields` through the halo_exchange_dynamic_ut `he` (p2p transport)."""
         arr, n = he._ptrs(list(fields))

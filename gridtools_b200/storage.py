@@ -43,11 +43,26 @@ class DataStore:
         self._base = (addr + byte_align - 1) // byte_align * byte_align - off  # data_store.hpp:67-71
         shift = (self._base - self._raw.data_ptr()) // isz
         self._dev = self._raw[shift:shift + self.length].view(d2, d1, p0)
-        self._host_t = torch.zeros((d2, d1, p0), dtype=tdtype).pin_memory() if self.device.type == "cuda" \
-            else torch.zeros((d2, d1, p0), dtype=tdtype)
-        self._host = self._host_t.numpy()
+        # the pinned host mirror is allocated on first host access (a 4096x4096x80 field is 10.7 GB): a store that is
+        # only ever filled and read on the device (target_tensor()) never pays for it
+        self._host_shape, self._tdtype = (d2, d1, p0), tdtype
+        self._host_buf = None
+        self._host_np = None
         self._host_stale = False
         self._dev_stale = False
+
+    @property
+    def _host_t(self):
+        if self._host_buf is None:
+            t = torch.zeros(self._host_shape, dtype=self._tdtype)
+            self._host_buf = t.pin_memory() if self.device.type == "cuda" else t
+            self._host_np = self._host_buf.numpy()
+        return self._host_buf
+
+    @property
+    def _host(self):
+        self._host_t
+        return self._host_np
 
     # ------------------------------------------------------------------ host / target access (data_store.hpp:86-147)
     def host_view(self):
@@ -76,7 +91,7 @@ class DataStore:
             self._host_stale = False
 
     def _sync_dev(self):
-        if self._dev_stale:
+        if self._dev_stale and self._host_buf is not None:
             self._dev.copy_(self._host_t)
             self._dev_stale = False
 
@@ -91,7 +106,7 @@ class DataStore:
 
     @property
     def nbytes_host(self):
-        return self._host_t.numel() * self.dtype.itemsize
+        return self.length * self.dtype.itemsize
 
     # ------------------------------------------------------------------ descriptors for the C ABI
     def raw_ptr(self, const=False):

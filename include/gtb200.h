@@ -203,6 +203,8 @@ int gtb_seq_add_hori_diff(gtb_seq *s, int elem_size, const gtb_field *in, const 
 int gtb_seq_add_vert_adv(gtb_seq *s, int elem_size, const gtb_field *utens_stage, const gtb_field *u_stage,
     const gtb_field *wcon, const gtb_field *u_pos, const gtb_field *utens, double dtr_stage, int ni, int nj, int nk,
     void *stream);
+int gtb_seq_add_prepare_tracers(gtb_seq *s, const gtb_field *out, const gtb_field *in, int n_tracers,
+    const gtb_field *rho, int ni, int nj, int nk, void *stream);
 int gtb_seq_add_halo_exchange(gtb_seq *s, gtb_halo *h, void *const *fields, int n_fields, void *stream);
 int gtb_seq_add_record(gtb_seq *s, int event, void *stream);
 int gtb_seq_add_wait(gtb_seq *s, void *stream, int event);

@@ -54,6 +54,10 @@ def test_argument_validation_needs_no_device(L):
     assert h.gtb_tridiagonal_f64(*[C.byref(f)] * 4, C.byref(null), 4, 4, 4, None) == L.GTB_ERR_ARG
     assert h.gtb_halo_create(None, None, 0, 1, 8, None) == L.GTB_ERR_ARG
     assert h.gtb_halo_send_bytes(None, 0, 1) == 0
+    assert h.gtb_seq_create(None) == L.GTB_ERR_ARG
+    assert h.gtb_seq_size(None) == 0 and h.gtb_seq_destroy(None) == L.GTB_OK
+    assert h.gtb_seq_run(None, 0, 0) == L.GTB_ERR_ARG
+    assert h.gtb_seq_add_record(None, 0, None) == L.GTB_ERR_ARG
 
 
 def test_no_cpu_fallback_without_device(L):
@@ -66,6 +70,8 @@ def test_no_cpu_fallback_without_device(L):
     st = h.gtb_copy(C.byref(f), C.byref(g), 4, 4, 4, 8, None)
     assert st == L.GTB_ERR_CUDA and "CUDA" in L.last_error()
     assert h.gtb_init(0) == L.GTB_ERR_CUDA
+    seq = C.c_void_p()
+    assert h.gtb_seq_create(C.byref(seq)) == L.GTB_ERR_CUDA  # a sequence only ever replays device work
 
 
 def test_product_never_uses_the_oracle():

@@ -4,6 +4,8 @@ Bar: bit-exact for copy; for the arithmetic stencils the kernels evaluate the fu
 operation without FMA contraction, so they are also BIT-EXACT against oracle/gt_oracle.c (-ffp-contract=off), and
 within 1e-12 (fp64) / 1e-5 (fp32) relative of the reference's cpu_ifirst output stored in tests/golden/ (the
 reference build contracts FMAs)."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -363,3 +365,66 @@ def test_launches_are_counted(gt):
     src, dst = gt.storage.from_numpy(a, (0, 0, 0)), gt.storage.from_numpy(a, (0, 0, 0))
     gt.stencil.copy(src, dst)
     assert gt.lib.launch_count() == before + 1
+
+
+# ------------------------------------------------------------------------------------- recorded sequences (gtb_seq)
+def test_sequence_replays_a_two_stream_loop(gt, oracle):
+    """A recorded loop (stencil on one stream, ordered against a second stream with events) gives the same fields as
+    the direct calls, slice by slice and in one go."""
+    torch = gt.torch
+    rng = np.random.default_rng(5)
+    ni, nj, nk = 70, 19, 5
+    inp = rng.standard_normal((nk, nj + 4, ni + 4))
+    coeff = rng.uniform(0, 0.05, inp.shape)
+    want1 = oracle.hori_diff(inp, coeff)
+    inner = (slice(None), slice(2, -2), slice(2, -2))
+    a = gt.storage.from_numpy(inp, (2, 2, 0))
+    c = gt.storage.from_numpy(coeff, (2, 2, 0))
+    b = gt.storage.from_numpy(np.zeros_like(inp), (2, 2, 0))
+    d = gt.storage.from_numpy(np.zeros_like(inp), (2, 2, 0))
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    h1, h2 = C.c_void_p(s1.cuda_stream), C.c_void_p(s2.cuda_stream)
+    torch.cuda.synchronize()
+    seq = gt.stencil.Sequence()
+    seq.horizontal_diffusion(a, c, b, stream=h1)      # b = hd(a)
+    seq.record(0, h1)
+    seq.wait(h2, 0)
+    seq.horizontal_diffusion(b, c, d, stream=h2)      # d = hd(b) on the other stream, after the event
+    seq.record(1, h2)
+    assert len(seq) == 5
+    seq.run(0, 2)
+    seq.run(2, 3)
+    torch.cuda.synchronize()
+    got_b = b.to_numpy()
+    assert np.array_equal(got_b[inner], want1[inner])
+    want2 = oracle.hori_diff(got_b, coeff)
+    assert np.array_equal(d.to_numpy()[inner], want2[inner])
+    d.host_view()[...] = 0
+    b.host_view()[...] = 0
+    b.const_target_tensor(), d.const_target_tensor()
+    torch.cuda.synchronize()
+    seq.run()
+    torch.cuda.synchronize()
+    b._host_stale = d._host_stale = True
+    assert np.array_equal(b.to_numpy()[inner], want1[inner]) and np.array_equal(d.to_numpy()[inner], want2[inner])
+    with pytest.raises(gt.lib.GtbError):
+        seq.run(3, 9)
+    seq.close()
+
+
+def test_sequence_vertical_advection(gt, oracle):
+    rng = np.random.default_rng(6)
+    ni, nj, nk = 40, 6, 17
+    shape = (nk, nj + 6, ni + 6)
+    arrs = [rng.uniform(5, 9, shape), rng.uniform(5, 9, shape), rng.uniform(-3e-4, 3e-4, shape),
+            rng.uniform(5, 9, shape), rng.uniform(-1e-5, 1e-5, shape)]
+    for dtype in (np.float64, np.float32):
+        xs = [x.astype(dtype) for x in arrs]
+        st = [gt.storage.from_numpy(x, (3, 3, 0)) for x in xs]
+        seq = gt.stencil.Sequence()
+        seq.vertical_advection_dycore(*st, 0.15, stream=None)
+        seq.run()
+        gt.torch.cuda.synchronize()
+        st[0]._host_stale = True
+        inner = (slice(None), slice(3, -3), slice(3, -3))
+        assert np.array_equal(st[0].to_numpy()[inner], oracle.vert_adv(*xs, 0.15)[inner])
