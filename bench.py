@@ -38,6 +38,7 @@ NK = 80
 ALGO_BYTES = {"vert_adv": 48, "hori_diff": 24}  # per interior point, fp64
 P100_MPTS = {"vert_adv": 5117.0, "hori_diff": 10300.0}  # reference stencil::gpu on P100
 HALO = {"vert_adv": 3, "hori_diff": 2}
+HALO_FUSED = 0   # N > 1: gtb_halo_exchange as one launch (pack, signal, wait, unpack)
 RESERVE_SMS = 4  # N > 1: SMs the persistent stencil grids leave free for the concurrent halo exchange kernels
 
 
@@ -342,7 +343,8 @@ def b200_arm(args):
     n_warm = max(args.warmup, 3)
     seq, step_ops = None, []
     if he is not None:
-        _lib.set_option("reserve_sms", RESERVE_SMS)  # the persistent stencil grids leave these SMs to the exchange
+        _lib.set_option("reserve_sms", int(os.environ.get("GTB_RESERVE_SMS", RESERVE_SMS)))  # left to the exchange
+        _lib.set_option("halo.fused", int(os.environ.get("GTB_HALO_FUSED", HALO_FUSED)))
         seq = stencil.Sequence()
         M = n_sets + 2  # event slots: exchange done = s % M, stencil done = M + s % M
 

@@ -48,6 +48,8 @@ _SIG = {
     "gtb_copy": (C.c_int, [_FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gtb_hori_diff_f64": (C.c_int, [_FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gtb_hori_diff_f32": (C.c_int, [_FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "gtb_simple_hori_diff_f64": (C.c_int, [_FP, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "gtb_simple_hori_diff_f32": (C.c_int, [_FP, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gtb_vert_adv_f64": (C.c_int, [_FP, _FP, _FP, _FP, _FP, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gtb_vert_adv_f32": (C.c_int, [_FP, _FP, _FP, _FP, _FP, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gtb_tridiagonal_f64": (C.c_int, [_FP, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_void_p]),

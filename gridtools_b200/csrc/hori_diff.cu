@@ -424,3 +424,118 @@ GTB_API int gtb_hori_diff_f32(const gtb_field *in, const gtb_field *coeff, const
     int nk, void *stream) {
     return hori_diff<float>(in, coeff, out, ni, nj, nk, stream);
 }
+
+// ------------------------------------------------------------------------------------ simple_hori_diff.cpp:25-61
+// Two stages (wlap on the 1-extended domain, divflux), one ij_cached temporary, j-only coefficients crlato / crlatu.
+// One launch: persistent 64x4-thread CTAs walk (tile, level) items; the halo-2 tile of `in` is staged in shared
+// memory once, the laplacian tile (the reference's ij_cache) is computed into shared memory on the 1-extended tile,
+// then every thread produces two outputs.  12 + 12 loads per point in the reference's kernel become one global load
+// of `in`, one of `coeff` and one store.  Arithmetic in the functors' order (no FMA contraction): bit-identical to
+// oracle/gt_oracle.c.
+namespace {
+    constexpr int SH_TI = 64, SH_TJ = 8, SH_TX = 64, SH_TY = 4;
+
+    template <class T>
+    struct shd_params {
+        const T *in, *coeff, *crlato, *crlatu;
+        T *out;
+        int64_t in_sj, in_sk, co_sj, co_sk, out_sj, out_sk, cro_sj, cru_sj;
+        int ni, nj, nk, tiles_i, tiles_j;
+        int64_t items;
+    };
+
+    template <class T>
+    __global__ void __launch_bounds__(SH_TX *SH_TY) shd_kernel(const shd_params<T> p) {
+        constexpr int IW = SH_TI + 4 + 1, LW = SH_TI + 2 + 1; // padded row widths
+        __shared__ T in_t[SH_TJ + 4][IW];
+        __shared__ T lap_t[SH_TJ + 2][LW];
+        const int tid = threadIdx.y * SH_TX + threadIdx.x;
+        for (int64_t item = blockIdx.x; item < p.items; item += gridDim.x) {
+            const int ti = (int)(item % p.tiles_i);
+            const int64_t r = item / p.tiles_i;
+            const int tj = (int)(r % p.tiles_j), k = (int)(r / p.tiles_j);
+            const int i0 = ti * SH_TI, j0 = tj * SH_TJ;
+            const T *in_k = p.in + (int64_t)k * p.in_sk;
+            for (int idx = tid; idx < (SH_TJ + 4) * (SH_TI + 4); idx += SH_TX * SH_TY) {
+                const int jj = idx / (SH_TI + 4), ii = idx - jj * (SH_TI + 4);
+                const int gi = i0 - 2 + ii, gj = j0 - 2 + jj;
+                in_t[jj][ii] = gi < p.ni + 2 && gj < p.nj + 2 ? in_k[gi + (int64_t)gj * p.in_sj] : T(0);
+            }
+            __syncthreads();
+            for (int idx = tid; idx < (SH_TJ + 2) * (SH_TI + 2); idx += SH_TX * SH_TY) { // wlap_function :25-41
+                const int jj = idx / (SH_TI + 2), ii = idx - jj * (SH_TI + 2);
+                const int gi = i0 - 1 + ii, gj = j0 - 1 + jj;
+                if (gi <= p.ni && gj <= p.nj) {
+                    const T c = in_t[jj + 1][ii + 1];
+                    lap_t[jj][ii] = in_t[jj + 1][ii + 2] + in_t[jj + 1][ii] - T(2) * c +
+                                    p.crlato[(int64_t)gj * p.cro_sj] * (in_t[jj + 2][ii + 1] - c) +
+                                    p.crlatu[(int64_t)gj * p.cru_sj] * (in_t[jj][ii + 1] - c);
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int h = 0; h < SH_TJ / SH_TY; ++h) { // divflux_function :43-61
+                const int jj = threadIdx.y + h * SH_TY, ii = threadIdx.x;
+                const int gi = i0 + ii, gj = j0 + jj;
+                if (gi < p.ni && gj < p.nj) {
+                    const T c = lap_t[jj + 1][ii + 1];
+                    const T cro = p.crlato[(int64_t)gj * p.cro_sj];
+                    const T fluxx = lap_t[jj + 1][ii + 2] - c;
+                    const T fluxx_m = c - lap_t[jj + 1][ii];
+                    const T fluxy = cro * (lap_t[jj + 2][ii + 1] - c);
+                    const T fluxy_m = cro * (c - lap_t[jj][ii + 1]);
+                    p.out[gi + (int64_t)gj * p.out_sj + (int64_t)k * p.out_sk] =
+                        in_t[jj + 2][ii + 2] +
+                        ((fluxx_m - fluxx) + (fluxy_m - fluxy)) * p.coeff[gi + (int64_t)gj * p.co_sj + (int64_t)k * p.co_sk];
+                }
+            }
+            __syncthreads(); // the tiles are rewritten by the next item
+        }
+    }
+
+    template <class T>
+    int simple_hori_diff(const gtb_field *in, const gtb_field *coeff, const gtb_field *crlato, const gtb_field *crlatu,
+        const gtb_field *out, int ni, int nj, int nk, void *stream) {
+        const gtb_field *all[5] = {in, coeff, crlato, crlatu, out};
+        for (auto f : all)
+            if (!field_ok(f))
+                return fail(GTB_ERR_ARG, "gtb_simple_hori_diff: null field");
+        if (in->stride_i != 1 || coeff->stride_i != 1 || out->stride_i != 1)
+            return fail(GTB_ERR_LAYOUT, "gtb_simple_hori_diff: stride_i must be 1 (i is the unit-stride axis of storage::gpu)");
+        if (ni < 0 || nj < 0 || nk < 0)
+            return fail(GTB_ERR_ARG, "gtb_simple_hori_diff: negative size");
+        if (out->ptr == in->ptr || out->ptr == coeff->ptr)
+            return fail(GTB_ERR_ARG, "gtb_simple_hori_diff: out must not alias in / coeff");
+        device_state *d = dev();
+        if (!d)
+            return GTB_ERR_CUDA;
+        if (ni == 0 || nj == 0 || nk == 0)
+            return GTB_OK;
+        shd_params<T> p;
+        p.in = static_cast<const T *>(in->ptr), p.coeff = static_cast<const T *>(coeff->ptr);
+        p.crlato = static_cast<const T *>(crlato->ptr), p.crlatu = static_cast<const T *>(crlatu->ptr);
+        p.out = static_cast<T *>(out->ptr);
+        p.in_sj = in->stride_j, p.in_sk = in->stride_k, p.co_sj = coeff->stride_j, p.co_sk = coeff->stride_k;
+        p.out_sj = out->stride_j, p.out_sk = out->stride_k;
+        p.cro_sj = crlato->stride_j, p.cru_sj = crlatu->stride_j;
+        p.ni = ni, p.nj = nj, p.nk = nk;
+        p.tiles_i = ceil_div(ni, SH_TI), p.tiles_j = ceil_div(nj, SH_TJ);
+        p.items = (int64_t)p.tiles_i * p.tiles_j * nk;
+        int64_t grid = (int64_t)stencil_sms(d) * 8;
+        if (grid > p.items)
+            grid = p.items;
+        shd_kernel<T><<<(unsigned)grid, dim3(SH_TX, SH_TY), 0, as_stream(stream)>>>(p);
+        count_launch();
+        return check_launch("shd_kernel");
+    }
+} // namespace
+
+GTB_API int gtb_simple_hori_diff_f64(const gtb_field *in, const gtb_field *coeff, const gtb_field *crlato,
+    const gtb_field *crlatu, const gtb_field *out, int ni, int nj, int nk, void *stream) {
+    return simple_hori_diff<double>(in, coeff, crlato, crlatu, out, ni, nj, nk, stream);
+}
+
+GTB_API int gtb_simple_hori_diff_f32(const gtb_field *in, const gtb_field *coeff, const gtb_field *crlato,
+    const gtb_field *crlatu, const gtb_field *out, int ni, int nj, int nk, void *stream) {
+    return simple_hori_diff<float>(in, coeff, crlato, crlatu, out, ni, nj, nk, stream);
+}

@@ -77,6 +77,18 @@ def horizontal_diffusion(inp: DataStore, coeff: DataStore, out: DataStore, grid:
     _lib.check(fn(C.byref(fi), C.byref(fc), C.byref(fo), g.ni, g.nj, g.nk, _stream()))
 
 
+def simple_hori_diff(coeff: DataStore, inp: DataStore, out: DataStore, crlato: DataStore, crlatu: DataStore,
+                     grid: Grid = None):
+    """simple_hori_diff.cpp:63-88 : run(spec, backend, grid, coeff, in, out, crlato, crlatu); crlato / crlatu are
+    j-only stores (`storage.builder...selector(0, 1, 0)`)."""
+    g = _grid_of(inp, grid)
+    dt = _same_dtype(inp, coeff, out, crlato, crlatu)
+    fn = _lib.lib().gtb_simple_hori_diff_f64 if dt.itemsize == 8 else _lib.lib().gtb_simple_hori_diff_f32
+    fi, fc, fo = inp.field(True, g.origin), coeff.field(True, g.origin), out.field(False, g.origin)
+    fro, fru = crlato.field(True), crlatu.field(True)  # origin = their own j halo
+    _lib.check(fn(C.byref(fi), C.byref(fc), C.byref(fro), C.byref(fru), C.byref(fo), g.ni, g.nj, g.nk, _stream()))
+
+
 def vertical_advection_dycore(utens_stage: DataStore, u_stage: DataStore, wcon: DataStore, u_pos: DataStore,
                               utens: DataStore, dtr_stage: float, grid: Grid = None):
     """vertical_advection_dycore.cpp:140-149 : run(spec, backend, grid, utens_stage, u_stage, wcon, u_pos, utens,

@@ -164,6 +164,11 @@ class _Builder:
     def name(self, n):
         return self._with(name=n)
 
+    def selector(self, *mask):
+        """builder.selector<0,1,0>() (storage/builder.hpp): masked-out dimensions have extent 1 and no halo, e.g. the
+        j-only coefficient fields of simple_hori_diff.cpp:66; the kernels ignore their strides."""
+        return self._with(selector=tuple(bool(m) for m in mask))
+
     def alignment(self, a):
         """Not in the reference builder: lets tests build unaligned / unpadded layouts (alignment=1)."""
         return self._with(alignment=a)
@@ -173,7 +178,11 @@ class _Builder:
         if "dtype" not in kw or "lengths" not in kw:
             raise ValueError("builder needs .type() and .dimensions() before .build()")  # static_assert in C++
         lengths = kw["lengths"]
-        ds = DataStore(kw["dtype"], lengths, kw.get("halos", (0,) * len(lengths)),
+        halos = kw.get("halos", (0,) * len(lengths))
+        if kw.get("selector") is not None:
+            lengths = tuple(n if m else 1 for n, m in zip(lengths, kw["selector"]))
+            halos = tuple(h if m else 0 for h, m in zip(halos, kw["selector"]))
+        ds = DataStore(kw["dtype"], lengths, halos,
                        alignment=kw.get("alignment", BYTE_ALIGNMENT), name=kw.get("name", ""))
         if kw.get("value") is not None:
             ds.host_view()[...] = kw["value"]

@@ -88,6 +88,14 @@ int gtb_hori_diff_f64(const gtb_field *in, const gtb_field *coeff, const gtb_fie
 int gtb_hori_diff_f32(const gtb_field *in, const gtb_field *coeff, const gtb_field *out, int ni, int nj, int nk,
     void *stream);
 
+/* simple_hori_diff.cpp:25-88 : execute_parallel, ij_cached(lap), wlap_function + divflux_function in one kernel.
+ * crlato / crlatu are the reference's j-only fields (builder selector<0,1,0>): {pointer to the compute domain's j = 0,
+ * stride_j}, read on j in [-1, nj]; stride_i / stride_k are ignored.  Reads `in` on [-2, n+2) in i and j. */
+int gtb_simple_hori_diff_f64(const gtb_field *in, const gtb_field *coeff, const gtb_field *crlato,
+    const gtb_field *crlatu, const gtb_field *out, int ni, int nj, int nk, void *stream);
+int gtb_simple_hori_diff_f32(const gtb_field *in, const gtb_field *coeff, const gtb_field *crlato,
+    const gtb_field *crlatu, const gtb_field *out, int ni, int nj, int nk, void *stream);
+
 /* vertical_advection_dycore.cpp:32-149 : forward sweep (k_cached ccol/dcol flush, u_stage fill) + backward sweep
  * (k_cached data_col) fused into one kernel; utens_stage is updated in place.  Reads wcon at i+1 and k+1.
  * nk >= 2.  stride_i must be 1. */

@@ -63,7 +63,7 @@
 namespace gtb200 {
 
     /// Kernels of libgtb200.so a whole spec can be bound to.
-    enum class kernel { none, copy, hori_diff, vert_adv, tridiagonal };
+    enum class kernel { none, copy, hori_diff, simple_hori_diff, vert_adv, tridiagonal };
 
     /// Primary template: a spec made of these user functors (in stage order, duplicates removed) has no named kernel.
     template <class FunctorList>
@@ -158,6 +158,25 @@ namespace gridtools {
                              ? gtb_hori_diff_f64(&in, &coeff, &out, grid.i_size(), grid.j_size(), grid.k_size(), stream)
                              : gtb_hori_diff_f32(&in, &coeff, &out, grid.i_size(), grid.j_size(), grid.k_size(), stream);
                 gtb200::check(st, "gtb_hori_diff");
+            }
+
+            // simple_hori_diff.cpp:63-88 : run(spec, backend, grid, coeff, in, out, crlato, crlatu); crlato / crlatu are
+            // j-only stores (builder selector<0,1,0>): their SIDs have no i / k stride
+            template <class Grid, class DataStores>
+            void run_named(kernel_c<kernel::simple_hori_diff>, Grid const &grid, DataStores &ds, void *stream) {
+                static_assert(tuple_util::size<DataStores>::value == 5,
+                    "simple_hori_diff takes (coeff, in, out, crlato, crlatu)");
+                auto coeff = as_field(tuple_util::get<0>(ds)), in = as_field(tuple_util::get<1>(ds)),
+                     out = as_field(tuple_util::get<2>(ds)), crlato = as_field(tuple_util::get<3>(ds)),
+                     crlatu = as_field(tuple_util::get<4>(ds));
+                using T = element_of<std::decay_t<decltype(tuple_util::get<2>(ds))>>;
+                static_assert(std::is_same<T, double>::value || std::is_same<T, float>::value, "float or double");
+                int st = std::is_same<T, double>::value
+                             ? gtb_simple_hori_diff_f64(
+                                   &in, &coeff, &crlato, &crlatu, &out, grid.i_size(), grid.j_size(), grid.k_size(), stream)
+                             : gtb_simple_hori_diff_f32(
+                                   &in, &coeff, &crlato, &crlatu, &out, grid.i_size(), grid.j_size(), grid.k_size(), stream);
+                gtb200::check(st, "gtb_simple_hori_diff");
             }
 
             // vertical_advection_dycore.cpp:140-149 : run(spec, backend, grid, utens_stage, u_stage, wcon, u_pos, utens,

@@ -81,6 +81,41 @@ int gto_copy(const gto_field *in, const gto_field *out, int ni, int nj, int nk, 
 GTO_HORI_DIFF(gto_hori_diff_f64, double)
 GTO_HORI_DIFF(gto_hori_diff_f32, float)
 
+/* --------------------------------- simple horizontal diffusion (simple_hori_diff.cpp:25-61)
+ * crlato / crlatu depend on j only (selector<0,1,0> storages in the reference): plain arrays indexed by the compute
+ * domain's j, valid on [-1, nj].  wlap_function :25-41 on the 1-extended domain, divflux_function :43-61. */
+#define GTO_SIMPLE_HORI_DIFF(NAME, T)                                                                            \
+    int NAME(const gto_field *in, const gto_field *coeff, const T *crlato, const T *crlatu, const gto_field *out, \
+        int ni, int nj, int nk) {                                                                                \
+        const int li = ni + 2, lj = nj + 2;                                                                      \
+        T *lap = (T *)malloc(sizeof(T) * (size_t)li * lj);                                                       \
+        if (!lap)                                                                                                \
+            return 2;                                                                                            \
+        for (int k = 0; k < nk; ++k) {                                                                           \
+            for (int j = -1; j <= nj; ++j)                                                                       \
+                for (int i = -1; i <= ni; ++i)                                                                   \
+                    lap[(j + 1) * li + (i + 1)] =                                                                \
+                        AT(T, in, i + 1, j, k) + AT(T, in, i - 1, j, k) - (T)2 * AT(T, in, i, j, k) +            \
+                        crlato[j] * (AT(T, in, i, j + 1, k) - AT(T, in, i, j, k)) +                              \
+                        crlatu[j] * (AT(T, in, i, j - 1, k) - AT(T, in, i, j, k));                               \
+            for (int j = 0; j < nj; ++j)                                                                         \
+                for (int i = 0; i < ni; ++i) {                                                                   \
+                    const T c = lap[(j + 1) * li + (i + 1)];                                                     \
+                    T fluxx = lap[(j + 1) * li + (i + 2)] - c;                                                   \
+                    T fluxx_m = c - lap[(j + 1) * li + i];                                                       \
+                    T fluxy = crlato[j] * (lap[(j + 2) * li + (i + 1)] - c);                                     \
+                    T fluxy_m = crlato[j] * (c - lap[j * li + (i + 1)]);                                         \
+                    AT(T, out, i, j, k) =                                                                        \
+                        AT(T, in, i, j, k) + ((fluxx_m - fluxx) + (fluxy_m - fluxy)) * AT(T, coeff, i, j, k);    \
+                }                                                                                                \
+        }                                                                                                        \
+        free(lap);                                                                                               \
+        return 0;                                                                                                \
+    }
+
+GTO_SIMPLE_HORI_DIFF(gto_simple_hori_diff_f64, double)
+GTO_SIMPLE_HORI_DIFF(gto_simple_hori_diff_f32, float)
+
 /* --------------------------------- vertical advection (vertical_advection_dycore.cpp:32-149)
  * BET_M = BET_P = 0.5 (vertical_advection_defs.hpp).  Forward sweep: first_level :85-98, body :50-68,
  * last_level :70-83.  Backward sweep: last_level :118-121, body :111-116.  ccol/dcol are column

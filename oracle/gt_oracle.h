@@ -40,6 +40,11 @@ int gto_copy(const gto_field *in, const gto_field *out, int ni, int nj, int nk, 
 /* horizontal_diffusion.cpp:35-106 -- lap / flx / fly / out, 4 stages, lap on [-1,1]^2 etc. */
 int gto_hori_diff_f64(const gto_field *in, const gto_field *coeff, const gto_field *out, int ni, int nj, int nk);
 int gto_hori_diff_f32(const gto_field *in, const gto_field *coeff, const gto_field *out, int ni, int nj, int nk);
+/* simple_hori_diff.cpp:25-61; crlato / crlatu point at the compute domain's j = 0 and are read on [-1, nj] */
+int gto_simple_hori_diff_f64(const gto_field *in, const gto_field *coeff, const double *crlato, const double *crlatu,
+    const gto_field *out, int ni, int nj, int nk);
+int gto_simple_hori_diff_f32(const gto_field *in, const gto_field *coeff, const float *crlato, const float *crlatu,
+    const gto_field *out, int ni, int nj, int nk);
 
 /* vertical_advection_dycore.cpp:32-149 -- forward elimination + back substitution, in place on utens_stage. */
 int gto_vert_adv_f64(const gto_field *utens_stage, const gto_field *u_stage, const gto_field *wcon,

@@ -90,6 +90,19 @@ def hori_diff(inp, coeff, out=None, halo=2):
     return out
 
 
+def simple_hori_diff(inp, coeff, crlato, crlatu, halo=2):
+    """simple_hori_diff.cpp:25-61.  crlato / crlatu: 1-d arrays over the storage's j (length d1, halo included)."""
+    d2, d1, d0 = inp.shape
+    out = np.zeros_like(inp)
+    crlato, crlatu = np.ascontiguousarray(crlato, inp.dtype), np.ascontiguousarray(crlatu, inp.dtype)
+    assert crlato.shape == (d1,) and crlatu.shape == (d1,)
+    fn = {np.dtype("f8"): lib().gto_simple_hori_diff_f64, np.dtype("f4"): lib().gto_simple_hori_diff_f32}[inp.dtype]
+    _chk(fn(C.byref(field(inp, halo)), C.byref(field(coeff, halo)), C.c_void_p(crlato.ctypes.data + halo * inp.itemsize),
+            C.c_void_p(crlatu.ctypes.data + halo * inp.itemsize), C.byref(field(out, halo)), d0 - 2 * halo,
+            d1 - 2 * halo, d2), "gto_simple_hori_diff")
+    return out
+
+
 def vert_adv(utens_stage, u_stage, wcon, u_pos, utens, dtr_stage, halo=3):
     """Returns the updated utens_stage (input is not modified)."""
     d2, d1, d0 = utens_stage.shape
@@ -138,7 +151,7 @@ def halo_exchange_all(h, dims, periodic, fields, elem_size):
 
 
 # ------------------------------------------------------------------------------- reference build
-COPY, HORI_DIFF, VERT_ADV, TRIDIAGONAL = 0, 1, 2, 3
+COPY, HORI_DIFF, VERT_ADV, TRIDIAGONAL, SIMPLE_HORI_DIFF = 0, 1, 2, 3, 4
 CPU_IFIRST, CPU_KFIRST, NAIVE = 0, 1, 2
 BACKENDS = {"cpu_ifirst": CPU_IFIRST, "cpu_kfirst": CPU_KFIRST, "naive": NAIVE}
 
@@ -164,6 +177,17 @@ def repo_hori_diff(ni, nj, nk):
     arrs = [np.zeros((nk, d1, d0)) for _ in range(3)]
     ref().gtref_repo_hori_diff(d0, d1, nk, *[C.c_void_p(a.ctypes.data) for a in arrs])
     return arrs
+
+
+def repo_simple_hori_diff(ni, nj, nk):
+    """(in, coeff, crlato[d1], crlatu[d1], out_simple) of horizontal_diffusion_repository on the (nk, nj+4, ni+4) box."""
+    d0, d1 = ni + 4, nj + 4
+    arrs = [np.zeros((nk, d1, d0)) for _ in range(3)]
+    cro, cru = np.zeros(d1), np.zeros(d1)
+    ref().gtref_repo_simple_hori_diff(d0, d1, nk, *[C.c_void_p(a.ctypes.data) for a in arrs[:2]],
+                                      C.c_void_p(cro.ctypes.data), C.c_void_p(cru.ctypes.data),
+                                      C.c_void_p(arrs[2].ctypes.data))
+    return arrs[0], arrs[1], cro, cru, arrs[2]
 
 
 def repo_vert_adv(ni, nj, nk, want_out=True):

@@ -87,6 +87,37 @@ namespace {
         }
     };
 
+    // simple_hori_diff.cpp:25-61
+    struct shd_wlap {
+        using out = inout_accessor<0>;
+        using in = in_accessor<1, extent<-1, 1, -1, 1>>;
+        using crlato = in_accessor<2>;
+        using crlatu = in_accessor<3>;
+        using param_list = make_param_list<out, in, crlato, crlatu>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval) {
+            using T = std::decay_t<decltype(eval(out()))>;
+            eval(out()) = eval(in(1, 0)) + eval(in(-1, 0)) - T{2} * eval(in()) +
+                          eval(crlato()) * (eval(in(0, 1)) - eval(in())) + eval(crlatu()) * (eval(in(0, -1)) - eval(in()));
+        }
+    };
+    struct shd_divflux {
+        using out = inout_accessor<0>;
+        using in = in_accessor<1>;
+        using lap = in_accessor<2, extent<-1, 1, -1, 1>>;
+        using crlato = in_accessor<3>;
+        using coeff = in_accessor<4>;
+        using param_list = make_param_list<out, in, lap, crlato, coeff>;
+        template <class E>
+        GT_FUNCTION static void apply(E &eval) {
+            auto fluxx = eval(lap(1, 0)) - eval(lap());
+            auto fluxx_m = eval(lap()) - eval(lap(-1, 0));
+            auto fluxy = eval(crlato()) * (eval(lap(0, 1)) - eval(lap()));
+            auto fluxy_m = eval(crlato()) * (eval(lap()) - eval(lap(0, -1)));
+            eval(out()) = eval(in()) + ((fluxx_m - fluxx) + (fluxy_m - fluxy)) * eval(coeff());
+        }
+    };
+
     using va_axis_t = st::axis<1, st::axis_config::offset_limit<3>>;
     using va_full_t = va_axis_t::full_interval;
 
@@ -285,6 +316,33 @@ namespace {
         return 0;
     }
 
+    // in: {in, coeff, crlato[d1], crlatu[d1]} (the last two are 1-d over the storage's j, selector<0,1,0> stores)
+    template <class Backend, class Traits, class T>
+    int run_shd(int ni, int nj, int nk, const void *const *in, void *const *out, int nrep, int flush, double *times) {
+        constexpr int H = 2;
+        const int d0 = ni + 2 * H, d1 = nj + 2 * H;
+        auto u = make_store<Traits, T const>(d0, d1, nk, H, in[0]);
+        auto cf = make_store<Traits, T const>(d0, d1, nk, H, in[1]);
+        auto res = make_store<Traits, T>(d0, d1, nk, H, out[0]);
+        const T *po = static_cast<const T *>(in[2]), *pu = static_cast<const T *>(in[3]);
+        auto jb = gt::storage::builder<Traits>.template type<T const>().dimensions(d0, d1, nk).halos(H, H, 0)
+                      .template selector<0, 1, 0>();
+        auto crlato = jb.initializer([=](int, int j, int) { return po[j]; }).build();
+        auto crlatu = jb.initializer([=](int, int j, int) { return pu[j]; }).build();
+        auto hh = ij_grid(d0, d1, H);
+        auto grid = st::make_grid(hh.first, hh.second, st::axis<1>(nk));
+        auto spec = [](auto coeff, auto in, auto out, auto crlato, auto crlatu) {
+            GT_DECLARE_TMP(T, lap);
+            return st::execute_parallel()
+                .ij_cached(lap)
+                .stage(shd_wlap(), lap, in, crlato, crlatu)
+                .stage(shd_divflux(), out, in, lap, crlato, coeff);
+        };
+        timed([&] { st::run(spec, Backend(), grid, cf, u, res, crlato, crlatu); }, nrep, flush, times);
+        read_store<T>(res, d0, d1, nk, out[0]);
+        return 0;
+    }
+
     template <class Backend, class Traits, class T>
     int run_va(int ni, int nj, int nk, const void *const *in, void *const *out, double dtr_stage, int nrep, int flush,
         double *times) {
@@ -364,7 +422,7 @@ namespace {
 
 extern "C" {
 
-enum { GTREF_COPY = 0, GTREF_HORI_DIFF = 1, GTREF_VERT_ADV = 2, GTREF_TRIDIAGONAL = 3 };
+enum { GTREF_COPY = 0, GTREF_HORI_DIFF = 1, GTREF_VERT_ADV = 2, GTREF_TRIDIAGONAL = 3, GTREF_SIMPLE_HORI_DIFF = 4 };
 enum { GTREF_CPU_IFIRST = 0, GTREF_CPU_KFIRST = 1, GTREF_NAIVE = 2 };
 
 int gtref_num_threads() { return omp_get_max_threads(); }
@@ -410,6 +468,13 @@ int gtref_run(int stencil, int backend, int elem_size, int ni, int nj, int nk, c
             DISPATCH(run_td, double, ni, nj, nk, in, out, nrep, flush, times)
         }
         return 1;
+    case GTREF_SIMPLE_HORI_DIFF:
+        if (elem_size == 8) {
+            DISPATCH(run_shd, double, ni, nj, nk, in, out, nrep, flush, times)
+        } else if (elem_size == 4) {
+            DISPATCH(run_shd, float, ni, nj, nk, in, out, nrep, flush, times)
+        }
+        return 1;
     }
     return 1;
 #undef DISPATCH
@@ -428,6 +493,25 @@ void gtref_repo_hori_diff(int d0, int d1, int d2, double *in, double *coeff, dou
                 coeff[o] = repo.coeff(i, j, k);
                 bool interior = i >= 2 && i < d0 - 2 && j >= 2 && j < d1 - 2;
                 out[o] = interior ? repo.out(i, j, k) : 0.;
+            }
+}
+
+/* horizontal_diffusion_repository.hpp:32-46,68-79: in, coeff, crlato(j), crlatu(j) and out_simple (interior). */
+void gtref_repo_simple_hori_diff(int d0, int d1, int d2, double *in, double *coeff, double *crlato, double *crlatu,
+    double *out_simple) {
+    gt::horizontal_diffusion_repository repo(d0, d1, d2);
+    for (int j = 0; j < d1; ++j) {
+        crlato[j] = repo.crlato(0, j, 0);
+        crlatu[j] = repo.crlatu(0, j, 0);
+    }
+    for (int k = 0; k < d2; ++k)
+        for (int j = 0; j < d1; ++j)
+            for (int i = 0; i < d0; ++i) {
+                int64_t o = i + (int64_t)d0 * (j + (int64_t)d1 * k);
+                in[o] = repo.in(i, j, k);
+                coeff[o] = repo.coeff(i, j, k);
+                bool interior = i >= 2 && i < d0 - 2 && j >= 2 && j < d1 - 2;
+                out_simple[o] = interior ? repo.out_simple(i, j, k) : 0.;
             }
 }
 

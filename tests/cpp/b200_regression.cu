@@ -23,6 +23,7 @@
 
 GTB200_REGISTER_SPEC(gtb200::kernel::copy, user::copy_f<0>);
 GTB200_REGISTER_SPEC(gtb200::kernel::hori_diff, user::lap_f<0>, user::flx_f<0>, user::fly_f<0>, user::out_f<0>);
+GTB200_REGISTER_SPEC(gtb200::kernel::simple_hori_diff, user::wlap_f<0>, user::divflux_f<0>);
 GTB200_REGISTER_SPEC(gtb200::kernel::vert_adv, user::va_forward_f<0>, user::va_backward_f<0>);
 GTB200_REGISTER_SPEC(gtb200::kernel::tridiagonal, user::td_forward_f<0>, user::td_backward_f<0>);
 
@@ -108,6 +109,39 @@ namespace {
     }
 
     template <class T, int Tag>
+    void test_simple_hori_diff(int ni, int nj, int nk) {
+        constexpr int H = 2;
+        const int d0 = ni + 2 * H, d1 = nj + 2 * H;
+        fun_t in_f = [=](int i, int j, int k) {
+            double x = 1. * i / d0, y = 1. * j / d1;
+            return 5. + 8 * (2. + std::cos(M_PI * (x + 1.5 * y)) + std::sin(2 * M_PI * (x + 1.5 * y))) / 4. + 0.01 * k;
+        };
+        fun_t co_f = [](int i, int j, int) { return 0.025 + 1e-4 * ((i + j) % 5); };
+        fun_t cro_f = [=](int, int j, int) { return 1. + 0.3 * std::cos(3. * j / d1); };
+        fun_t cru_f = [=](int, int j, int) { return j == 0 ? 0. : 1. - 0.2 * std::sin(2. * j / d1); };
+        auto hh = make_ij_grid(d0, d1, H);
+        auto grid = st::make_grid(hh.first, hh.second, st::axis<1>(nk));
+        auto run_on = [&](auto traits, auto backend, auto tag) {
+            using traits_t = decltype(traits);
+            auto in = make_store<traits_t, T const>(d0, d1, nk, H, in_f);
+            auto co = make_store<traits_t, T const>(d0, d1, nk, H, co_f);
+            auto out = make_store<traits_t, T>(d0, d1, nk, H, [](int, int, int) { return 0.; });
+            auto jb = gt::storage::builder<traits_t>.template type<T const>().dimensions(d0, d1, nk).halos(H, H, 0)
+                          .template selector<0, 1, 0>();
+            auto cro = jb.initializer([=](int i, int j, int k) { return T(cro_f(i, j, k)); }).build();
+            auto cru = jb.initializer([=](int i, int j, int k) { return T(cru_f(i, j, k)); }).build();
+            st::run(user::simple_hori_diff_spec<T, decltype(tag)::value>(), backend, grid, co, in, out, cro, cru);
+            return out;
+        };
+        auto got = run_on(gt::storage::gpu(), st::b200<>(), std::integral_constant<int, Tag>());
+        auto ref = run_on(gt::storage::cpu_ifirst(), st::cpu_ifirst<>(), std::integral_constant<int, 1>());
+        std::string name = std::string("simple_hori_diff ") + (Tag ? "generic" : "named") +
+                           (sizeof(T) == 8 ? " f64 " : " f32 ") + std::to_string(ni) + "x" + std::to_string(nj) + "x" +
+                           std::to_string(nk);
+        verify(name.c_str(), got, ref, d0, d1, nk, H, sizeof(T) == 8 ? 1e-12 : 1e-5);
+    }
+
+    template <class T, int Tag>
     void test_vert_adv(int ni, int nj, int nk) {
         constexpr int H = 3;
         const int d0 = ni + 2 * H, d1 = nj + 2 * H;
@@ -176,6 +210,10 @@ int main() {
         test_hori_diff<float, 0>(70, 19, 5);
         test_hori_diff<double, 1>(23, 11, 7); // generic path
         test_hori_diff<float, 1>(33, 9, 3);
+        test_simple_hori_diff<double, 0>(12, 33, 61);
+        test_simple_hori_diff<double, 0>(70, 19, 5);
+        test_simple_hori_diff<float, 0>(23, 11, 7);
+        test_simple_hori_diff<double, 1>(23, 11, 7); // generic path with j-only fields
         test_vert_adv<double, 0>(12, 33, 61);
         test_vert_adv<double, 0>(23, 11, 43);
         test_vert_adv<double, 0>(256, 256, 80); // BASELINE.json configs[1]

@@ -86,6 +86,49 @@ namespace user {
         };
     }
 
+    // ---- simple horizontal diffusion (simple_hori_diff.cpp:25-61): j-only coefficient fields
+    template <int Tag>
+    struct wlap_f {
+        using out = inout_accessor<0>;
+        using in = in_accessor<1, extent<-1, 1, -1, 1>>;
+        using crlato = in_accessor<2>;
+        using crlatu = in_accessor<3>;
+        using param_list = make_param_list<out, in, crlato, crlatu>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval) {
+            using float_t = std::decay_t<decltype(eval(out()))>;
+            eval(out()) = eval(in(1, 0)) + eval(in(-1, 0)) - float_t{2} * eval(in()) +
+                          eval(crlato()) * (eval(in(0, 1)) - eval(in())) + eval(crlatu()) * (eval(in(0, -1)) - eval(in()));
+        }
+    };
+    template <int Tag>
+    struct divflux_f {
+        using out = inout_accessor<0>;
+        using in = in_accessor<1>;
+        using lap = in_accessor<2, extent<-1, 1, -1, 1>>;
+        using crlato = in_accessor<3>;
+        using coeff = in_accessor<4>;
+        using param_list = make_param_list<out, in, lap, crlato, coeff>;
+        template <class E>
+        GT_FUNCTION static void apply(E &eval) {
+            auto fluxx = eval(lap(1, 0)) - eval(lap());
+            auto fluxx_m = eval(lap()) - eval(lap(-1, 0));
+            auto fluxy = eval(crlato()) * (eval(lap(0, 1)) - eval(lap()));
+            auto fluxy_m = eval(crlato()) * (eval(lap()) - eval(lap(0, -1)));
+            eval(out()) = eval(in()) + ((fluxx_m - fluxx) + (fluxy_m - fluxy)) * eval(coeff());
+        }
+    };
+    template <class T, int Tag>
+    auto simple_hori_diff_spec() {
+        return [](auto coeff, auto in, auto out, auto crlato, auto crlatu) {
+            GT_DECLARE_TMP(T, lap);
+            return st::execute_parallel()
+                .ij_cached(lap)
+                .stage(wlap_f<Tag>(), lap, in, crlato, crlatu)
+                .stage(divflux_f<Tag>(), out, in, lap, crlato, coeff);
+        };
+    }
+
     // ---- vertical advection (vertical_advection_dycore.cpp), BET_M = BET_P = 0.5 (vertical_advection_defs.hpp)
     using va_axis_t = st::axis<1, st::axis_config::offset_limit<3>>;
     using va_full_t = va_axis_t::full_interval;

@@ -33,6 +33,21 @@ def hori_diff(ni, nj, nk, name):
                         out_ref=outs["cpu_ifirst"], out_repo=repo_out, out_ref_f32=res32)
 
 
+def simple_hori_diff(ni, nj, nk, name):
+    inp, coeff, cro, cru, repo_out = o.repo_simple_hori_diff(ni, nj, nk)
+    outs = {}
+    for be in ("cpu_ifirst", "cpu_kfirst", "naive"):
+        res = np.zeros_like(inp)
+        o.ref_run(o.SIMPLE_HORI_DIFF, be, [inp, coeff, cro, cru], [res], ni, nj, nk)
+        outs[be] = res
+    assert all(np.array_equal(outs["cpu_ifirst"], v) for v in outs.values()), "reference backends disagree"
+    f32 = [a.astype(np.float32) for a in (inp, coeff, cro, cru)]
+    res32 = np.zeros_like(f32[0])
+    o.ref_run(o.SIMPLE_HORI_DIFF, "cpu_ifirst", f32, [res32], ni, nj, nk)
+    np.savez_compressed(os.path.join(HERE, name), ni=ni, nj=nj, nk=nk, halo=2, inp=inp, coeff=coeff, crlato=cro,
+                        crlatu=cru, out_ref=outs["cpu_ifirst"], out_repo=repo_out, out_ref_f32=res32)
+
+
 def vert_adv(ni, nj, nk, name):
     arrs, repo_out, dtr = o.repo_vert_adv(ni, nj, nk)
     outs = {}
@@ -68,6 +83,8 @@ if __name__ == "__main__":
     vert_adv(13, 7, 61, "vert_adv_13x7x61.npz")       # 61 levels like the 12x33x61 environment
     vert_adv(35, 5, 9, "vert_adv_35x5x9.npz")         # crosses a warp boundary, short column
     tridiagonal(12, 33, 6, "tridiagonal_12x33x6.npz") # tridiagonal.cpp sizes
+    simple_hori_diff(70, 19, 3, "simple_hori_diff_70x19x3.npz")
+    simple_hori_diff(12, 33, 6, "simple_hori_diff_12x33x6.npz")
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

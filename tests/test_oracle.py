@@ -34,6 +34,19 @@ def test_hori_diff_golden(oracle, golden, name):
     assert rel_err(g["out_ref_f32"][inner].astype(np.float64), out32[inner].astype(np.float64)) < TOL32
 
 
+@pytest.mark.parametrize("name", ["simple_hori_diff_12x33x6.npz", "simple_hori_diff_70x19x3.npz"])
+def test_simple_hori_diff_golden(oracle, golden, name):
+    g = golden(name)
+    H = int(g["halo"])
+    out = oracle.simple_hori_diff(g["inp"], g["coeff"], g["crlato"], g["crlatu"])
+    inner = (slice(None), slice(H, -H), slice(H, -H))
+    assert verifier_ok(g["out_ref"][inner], out[inner], 1e-14)      # the reference's cpu_ifirst run
+    assert verifier_ok(g["out_repo"][inner], out[inner], 1e-14)     # horizontal_diffusion_repository.hpp:68-79
+    f32 = [g[k].astype(np.float32) for k in ("inp", "coeff", "crlato", "crlatu")]
+    out32 = oracle.simple_hori_diff(*f32)
+    assert rel_err(g["out_ref_f32"][inner].astype(np.float64), out32[inner].astype(np.float64)) < TOL32
+
+
 @pytest.mark.parametrize("name", ["vert_adv_13x7x61.npz", "vert_adv_35x5x9.npz"])
 def test_vert_adv_golden(oracle, golden, name):
     g = golden(name)
@@ -85,6 +98,22 @@ def test_hori_diff_vs_reference(oracle, backend, size):
     res = np.zeros_like(inp)
     oracle.ref_run(oracle.HORI_DIFF, backend, [inp, coeff], [res], ni, nj, nk)
     out = oracle.hori_diff(inp, coeff)
+    inner = (slice(None), slice(2, -2), slice(2, -2))
+    assert verifier_ok(res[inner], out[inner], 1e-13)
+
+
+@needs_ref
+@pytest.mark.parametrize("backend", ["cpu_ifirst", "cpu_kfirst", "naive"])
+@pytest.mark.parametrize("size", [(12, 33, 5), (70, 9, 2)])
+def test_simple_hori_diff_vs_reference(oracle, backend, size):
+    ni, nj, nk = size
+    rng = np.random.default_rng(ni * 77 + nj)
+    inp = rng.standard_normal((nk, nj + 4, ni + 4))
+    coeff = rng.uniform(0.0, 0.05, inp.shape)
+    cro, cru = rng.uniform(0.5, 1.5, nj + 4), rng.uniform(0.5, 1.5, nj + 4)
+    res = np.zeros_like(inp)
+    oracle.ref_run(oracle.SIMPLE_HORI_DIFF, backend, [inp, coeff, cro, cru], [res], ni, nj, nk)
+    out = oracle.simple_hori_diff(inp, coeff, cro, cru)
     inner = (slice(None), slice(2, -2), slice(2, -2))
     assert verifier_ok(res[inner], out[inner], 1e-13)
 

@@ -176,6 +176,51 @@ def test_hori_diff_linearity(gt):
     assert np.array_equal(a[inner] * np.float32(4), b[inner])
 
 
+# ------------------------------------------------------------------------------------- simple horizontal diffusion
+def run_shd(gt, inp, coeff, cro, cru, alignment=128):
+    H = 2
+    si = gt.storage.from_numpy(inp, (H, H, 0), alignment)
+    sc = gt.storage.from_numpy(coeff, (H, H, 0), alignment)
+    so = gt.storage.from_numpy(np.full_like(inp, -7.0), (H, H, 0), alignment)
+    d2, d1, d0 = inp.shape
+    jb = gt.storage.builder.type(inp.dtype).dimensions(d0, d1, d2).halos(H, H, 0).selector(0, 1, 0)
+    so_, su_ = jb.build(), jb.build()
+    so_.host_view()[0, :, 0] = cro
+    su_.host_view()[0, :, 0] = cru
+    gt.stencil.simple_hori_diff(sc, si, so, so_, su_)
+    gt.torch.cuda.synchronize()
+    return so.to_numpy()
+
+
+@pytest.mark.parametrize("name", ["simple_hori_diff_12x33x6.npz", "simple_hori_diff_70x19x3.npz"])
+def test_simple_hori_diff_golden(gt, oracle, golden, name):
+    g = golden(name)
+    out = run_shd(gt, g["inp"], g["coeff"], g["crlato"], g["crlatu"])
+    inner = (slice(None), slice(2, -2), slice(2, -2))
+    assert np.array_equal(out[inner], oracle.simple_hori_diff(g["inp"], g["coeff"], g["crlato"], g["crlatu"])[inner])
+    assert rel_err(out[inner], g["out_ref"][inner]) < TOL64 and rel_err(out[inner], g["out_repo"][inner]) < TOL64
+    halo_mask = np.ones(out.shape, bool)
+    halo_mask[inner] = False
+    assert np.all(out[halo_mask] == -7.0), "halo of out was modified"
+    f32 = [g[k].astype(np.float32) for k in ("inp", "coeff", "crlato", "crlatu")]
+    out32 = run_shd(gt, *f32)
+    assert np.array_equal(out32[inner], oracle.simple_hori_diff(*f32)[inner])
+    assert rel_err(out32[inner], g["out_ref_f32"][inner]) < TOL32
+
+
+@pytest.mark.parametrize("size", [(1, 1, 1), (64, 8, 2), (65, 9, 3), (130, 17, 4), (256, 256, 5), (33, 70, 2)])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_simple_hori_diff_random_bit_exact(gt, oracle, size, dtype):
+    ni, nj, nk = size
+    rng = np.random.default_rng(ni + 31 * nj)
+    inp = rng.standard_normal((nk, nj + 4, ni + 4)).astype(dtype)
+    coeff = rng.uniform(0, 0.05, inp.shape).astype(dtype)
+    cro, cru = rng.uniform(0.5, 1.5, nj + 4).astype(dtype), rng.uniform(0.5, 1.5, nj + 4).astype(dtype)
+    out = run_shd(gt, inp, coeff, cro, cru)
+    inner = (slice(None), slice(2, -2), slice(2, -2))
+    assert np.array_equal(out[inner], oracle.simple_hori_diff(inp, coeff, cro, cru)[inner])
+
+
 # ------------------------------------------------------------------------------------- vertical advection
 VA_CONFIGS = [dict(), dict(variant=5), dict(variant=5, ctas_per_sm=7), dict(variant=5, stages=3), dict(variant=5, ctas_per_sm=-1),
               dict(variant=5, ctas_per_sm=-2, stages=3), dict(variant=5, ctas_per_sm=4, stagger=5), dict(variant=6), dict(variant=6, ctas_per_sm=-1, stages=2, unroll=2),
