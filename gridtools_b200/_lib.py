@@ -11,6 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgtb200.so")
 
+GTB_BC_VALUE, GTB_BC_COPY = 0, 1
 GTB_OK, GTB_ERR_ARG, GTB_ERR_LAYOUT, GTB_ERR_CUDA, GTB_ERR_ALLOC, GTB_ERR_STATE = range(6)
 HALO_BLOB_BYTES = 512
 
@@ -72,6 +73,9 @@ _SIG = {
     "gtb_halo_exchange": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
     "gtb_halo_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "gtb_halo_next_epoch": (C.c_int, [C.c_void_p]),
+    "gtb_boundary_apply": (C.c_int, [C.POINTER(HaloDesc), C.POINTER(C.c_int), C.c_int, C.c_double, C.POINTER(C.c_void_p),
+                                     C.c_int, C.c_int, C.c_void_p]),
+    "gtb_halo_set_boundary": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "gtb_seq_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "gtb_seq_destroy": (C.c_int, [C.c_void_p]),
     "gtb_seq_size": (C.c_int, [C.c_void_p]),

@@ -60,6 +60,9 @@ struct gtb_halo {
     int nbr[27];
     int my_rank, max_fields, es, device;
     region send[27], recv[27];
+    region border[27];      // outside region of the directions that have no neighbour (domain border)
+    int bc_kind;            // -1 none; GTB_BC_VALUE: unpack launches also fill the border regions with bc_bits
+    uint64_t bc_bits;
     int64_t send_off[27], recv_off[27]; // byte offsets (max_fields sized slots)
     int64_t send_total, recv_total;
     char *send_arena; // local staging buffers
@@ -116,6 +119,7 @@ namespace {
         char *fields[kMaxFields];
         int64_t s1, s2; // element strides of storage dimensions 1 and 2
         int n_fields;
+        uint64_t fill_bits; // value written into segments without a buffer (boundary condition fused into the unpack)
         sync_args sync;
     };
 
@@ -124,6 +128,7 @@ namespace {
         char *fields[kMaxFields];
         int64_t s1, s2;
         int n_fields;
+        uint64_t fill_bits;
         sync_args sync;
     };
 
@@ -148,7 +153,7 @@ namespace {
     // WAIT: acquire a segment's flag before its first chunk.
     template <class E, bool PACK, bool WAIT>
     __device__ __forceinline__ void move_chunks(const seg_table &t, char *const *fields, int64_t s1, int64_t s2,
-        const sync_args &sy) {
+        const sync_args &sy, uint64_t fill_bits = 0) {
         const int total = t.chunk_start[t.n_seg];
         unsigned waited = 0; // segments whose flag this block has acquired (block-uniform)
         int s = 0;
@@ -165,6 +170,7 @@ namespace {
             const int local = ch - t.chunk_start[s];
             const int f = local / t.chunks_per_field[s];
             const int64_t base = (int64_t)(local - f * t.chunks_per_field[s]) * kChunk + threadIdx.x;
+            const bool fill = !PACK && t.buf[s] == nullptr; // border segment: boundary value instead of a message
             E *buf = reinterpret_cast<E *>(t.buf[s]) + (int64_t)f * r.count;
             E *fld = reinterpret_cast<E *>(fields[f]);
             const int l0 = r.len[0], l1 = r.len[1];
@@ -179,7 +185,7 @@ namespace {
                     int64_t q2 = q / l1;
                     int i1 = (int)(q - q2 * l1);
                     idx[it] = (r.lo[0] + i0) + (r.lo[1] + i1) * s1 + (r.lo[2] + q2) * s2;
-                    v[it] = PACK ? fld[idx[it]] : buf[e];
+                    v[it] = PACK ? fld[idx[it]] : (fill ? (E)fill_bits : buf[e]);
                 }
             }
 #pragma unroll
@@ -217,9 +223,9 @@ namespace {
     __global__ void __launch_bounds__(kThreads) xfer_kernel(const __grid_constant__ xfer_args a) {
         __shared__ int s_last;
         if (!PACK && a.sync.mode == 2)
-            move_chunks<E, false, true>(a.t, a.fields, a.s1, a.s2, a.sync);
+            move_chunks<E, false, true>(a.t, a.fields, a.s1, a.s2, a.sync, a.fill_bits);
         else
-            move_chunks<E, PACK, false>(a.t, a.fields, a.s1, a.s2, a.sync);
+            move_chunks<E, PACK, false>(a.t, a.fields, a.s1, a.s2, a.sync, a.fill_bits);
         if (PACK && a.sync.mode == 1)
             signal_peers(a.t, a.sync, &s_last);
     }
@@ -233,7 +239,7 @@ namespace {
         __shared__ int s_last;
         move_chunks<E, true, false>(a.snd, a.fields, a.s1, a.s2, a.sync);
         signal_peers(a.snd, a.sync, &s_last);
-        move_chunks<E, false, true>(a.rcv, a.fields, a.s1, a.s2, a.sync);
+        move_chunks<E, false, true>(a.rcv, a.fields, a.s1, a.s2, a.sync, a.fill_bits);
     }
 
     struct push_args {
@@ -307,6 +313,18 @@ namespace {
             t.chunks_per_field[sg] = (int)((regs[n].count + kChunk - 1) / kChunk);
             t.chunk_start[sg + 1] = t.chunk_start[sg] + t.chunks_per_field[sg] * nf;
         }
+        if (!pack && h->bc_kind == GTB_BC_VALUE) // distributed_boundaries.hpp: value condition where there is no neighbour
+            for (int n = 0; n < 27 && t.n_seg < kMaxSeg; ++n) {
+                if (h->border[n].count == 0)
+                    continue;
+                const int sg = t.n_seg++;
+                t.dir[sg] = n;
+                t.r[sg] = h->border[n];
+                t.buf[sg] = nullptr;
+                t.flag[sg] = nullptr;
+                t.chunks_per_field[sg] = (int)((h->border[n].count + kChunk - 1) / kChunk);
+                t.chunk_start[sg + 1] = t.chunk_start[sg] + t.chunks_per_field[sg] * nf;
+            }
     }
 
     void fill_sync(sync_args &sy, const gtb_halo *h, int mode) {
@@ -338,6 +356,7 @@ namespace {
             fill_table(b.t, h, PACK, bufs, nf, f0, mode);
             if (b.t.n_seg == 0)
                 return GTB_OK;
+            b.fill_bits = h->bc_bits;
             fill_sync(b.sync, h, mode);
             b.s1 = h->d[0].total;
             b.s2 = (int64_t)h->d[0].total * h->d[1].total;
@@ -425,6 +444,8 @@ GTB_API int gtb_halo_create(const gtb_halo_desc desc[3], const int neighbour_ran
     h->device = dv->device;
     h->connected = false;
     h->epoch = 1;
+    h->bc_kind = -1;
+    h->bc_bits = 0;
     h->send_total = h->recv_total = 0;
     for (int e2 = -1; e2 <= 1; ++e2)
         for (int e1 = -1; e1 <= 1; ++e1)
@@ -441,6 +462,9 @@ GTB_API int gtb_halo_create(const gtb_halo_desc desc[3], const int neighbour_ran
                     s.count *= s.len[d] > 0 ? s.len[d] : 0;
                     r.count *= r.len[d] > 0 ? r.len[d] : 0;
                 }
+                h->border[n] = r;
+                if (n == 13 || h->nbr[n] >= 0)
+                    h->border[n].count = 0;
                 if (n == 13 || h->nbr[n] < 0)
                     s.count = r.count = 0;
                 h->send_off[n] = h->send_total;
@@ -709,6 +733,7 @@ GTB_API int gtb_halo_exchange(gtb_halo *h, void *const *fields, int n_fields, vo
         if (a.snd.n_seg == 0 && a.rcv.n_seg == 0)
             return gtb_halo_next_epoch(h);
         fill_sync(a.sync, h, 1);
+        a.fill_bits = h->bc_bits;
         a.s1 = h->d[0].total;
         a.s2 = (int64_t)h->d[0].total * h->d[1].total;
         for (int f = 0; f < n_fields; ++f)
@@ -749,5 +774,148 @@ GTB_API int gtb_halo_next_epoch(gtb_halo *h) {
     if (!h)
         return fail(GTB_ERR_ARG, "gtb_halo_next_epoch: null handle");
     h->epoch += 1;
+    return GTB_OK;
+}
+
+// ------------------------------------------------------------------------------------------- boundary conditions
+// boundaries/boundary.hpp:57-72 with the predefined conditions of zero.hpp / value.hpp / copy.hpp.  The reference's GPU
+// path (apply_gpu.hpp:236-313) launches one kernel per call with a 3-d thread block per direction group; here the
+// outside regions of all selected directions and all fields are one flat chunk list walked by a small grid.
+namespace {
+    struct bc_args {
+        seg_table t;
+        char *fields[kMaxFields];
+        const char *src; // copy_boundary: the last field
+        int64_t s1, s2;
+        int n_fields;
+        uint64_t fill_bits;
+    };
+
+    template <class E, bool COPY>
+    __global__ void __launch_bounds__(kThreads) bc_kernel(const __grid_constant__ bc_args a) {
+        const seg_table &t = a.t;
+        const int total = t.chunk_start[t.n_seg];
+        int s = 0;
+        for (int ch = blockIdx.x; ch < total; ch += gridDim.x) {
+            while (ch >= t.chunk_start[s + 1])
+                ++s;
+            const region &r = t.r[s];
+            const int local = ch - t.chunk_start[s];
+            const int f = local / t.chunks_per_field[s];
+            const int64_t base = (int64_t)(local - f * t.chunks_per_field[s]) * kChunk + threadIdx.x;
+            E *fld = reinterpret_cast<E *>(a.fields[f]);
+            const E *src = reinterpret_cast<const E *>(a.src);
+            const int l0 = r.len[0], l1 = r.len[1];
+#pragma unroll
+            for (int it = 0; it < kItems; ++it) {
+                int64_t e = base + (int64_t)it * kThreads;
+                if (e < r.count) {
+                    int64_t q = e / l0;
+                    int i0 = (int)(e - q * l0);
+                    int64_t q2 = q / l1;
+                    int i1 = (int)(q - q2 * l1);
+                    const int64_t idx = (r.lo[0] + i0) + (r.lo[1] + i1) * a.s1 + (r.lo[2] + q2) * a.s2;
+                    fld[idx] = COPY ? src[idx] : (E)a.fill_bits;
+                }
+            }
+        }
+    }
+
+    uint64_t value_bits(double value, int es) {
+        uint64_t bits = 0;
+        if (es == 8)
+            memcpy(&bits, &value, 8);
+        else {
+            float f = (float)value;
+            uint32_t b32;
+            memcpy(&b32, &f, 4);
+            bits = b32;
+        }
+        return bits;
+    }
+} // namespace
+
+GTB_API int gtb_boundary_apply(const gtb_halo_desc desc[3], const int direction_mask[27], int kind, double value,
+    void *const *fields, int n_fields, int elem_size, void *stream) {
+    if (!desc || !fields)
+        return fail(GTB_ERR_ARG, "gtb_boundary_apply: null argument");
+    if (elem_size != 4 && elem_size != 8)
+        return fail(GTB_ERR_ARG, "gtb_boundary_apply: elem_size %d not in {4,8}", elem_size);
+    if (kind != GTB_BC_VALUE && kind != GTB_BC_COPY)
+        return fail(GTB_ERR_ARG, "gtb_boundary_apply: unknown condition %d", kind);
+    const int n_dst = kind == GTB_BC_COPY ? n_fields - 1 : n_fields;
+    if (n_dst < 1 || n_dst > kMaxFields)
+        return fail(GTB_ERR_ARG, "gtb_boundary_apply: %d destination fields (1..%d; copy_boundary needs a source as the last field)",
+            n_dst, kMaxFields);
+    for (int f = 0; f < n_fields; ++f)
+        if (!fields[f])
+            return fail(GTB_ERR_ARG, "gtb_boundary_apply: field %d is null", f);
+    for (int d = 0; d < 3; ++d) {
+        const gtb_halo_desc &h = desc[d];
+        if (h.minus < 0 || h.plus < 0 || h.begin < h.minus || h.end < h.begin || h.end + h.plus >= h.total)
+            return fail(GTB_ERR_ARG, "gtb_boundary_apply: inconsistent halo descriptor %d", d);
+    }
+    if (!dev())
+        return GTB_ERR_CUDA;
+    bc_args a;
+    a.t.n_seg = 0;
+    a.t.chunk_start[0] = 0;
+    for (int e2 = -1; e2 <= 1; ++e2)
+        for (int e1 = -1; e1 <= 1; ++e1)
+            for (int e0 = -1; e0 <= 1; ++e0) {
+                const int n = n_of(e0, e1, e2);
+                if (n == 13 || (direction_mask && !direction_mask[n]))
+                    continue;
+                const int e[3] = {e0, e1, e2};
+                region r;
+                r.count = 1;
+                for (int d = 0; d < 3; ++d) {
+                    r.lo[d] = lo_outside(desc[d], e[d]);
+                    r.len[d] = hi_outside(desc[d], e[d]) - r.lo[d] + 1;
+                    r.count *= r.len[d] > 0 ? r.len[d] : 0;
+                }
+                if (r.count == 0)
+                    continue;
+                const int sg = a.t.n_seg++;
+                a.t.dir[sg] = n;
+                a.t.r[sg] = r;
+                a.t.buf[sg] = nullptr;
+                a.t.flag[sg] = nullptr;
+                a.t.chunks_per_field[sg] = (int)((r.count + kChunk - 1) / kChunk);
+                a.t.chunk_start[sg + 1] = a.t.chunk_start[sg] + a.t.chunks_per_field[sg] * n_dst;
+            }
+    if (a.t.n_seg == 0)
+        return GTB_OK;
+    for (int f = 0; f < n_dst; ++f)
+        a.fields[f] = static_cast<char *>(fields[f]);
+    a.src = kind == GTB_BC_COPY ? static_cast<const char *>(fields[n_fields - 1]) : nullptr;
+    a.s1 = desc[0].total;
+    a.s2 = (int64_t)desc[0].total * desc[1].total;
+    a.n_fields = n_dst;
+    a.fill_bits = value_bits(value, elem_size);
+    const int grid = xfer_grid(a.t.chunk_start[a.t.n_seg]);
+    cudaStream_t st = as_stream(stream);
+    if (kind == GTB_BC_COPY) {
+        if (elem_size == 8)
+            bc_kernel<uint64_t, true><<<grid, kThreads, 0, st>>>(a);
+        else
+            bc_kernel<uint32_t, true><<<grid, kThreads, 0, st>>>(a);
+    } else {
+        if (elem_size == 8)
+            bc_kernel<uint64_t, false><<<grid, kThreads, 0, st>>>(a);
+        else
+            bc_kernel<uint32_t, false><<<grid, kThreads, 0, st>>>(a);
+    }
+    count_launch();
+    return check_launch("boundary apply");
+}
+
+GTB_API int gtb_halo_set_boundary(gtb_halo *h, int kind, double value) {
+    if (!h)
+        return fail(GTB_ERR_ARG, "gtb_halo_set_boundary: null handle");
+    if (kind != -1 && kind != GTB_BC_VALUE)
+        return fail(GTB_ERR_ARG, "gtb_halo_set_boundary: only GTB_BC_VALUE (or -1 = none) can be fused into the unpack");
+    h->bc_kind = kind;
+    h->bc_bits = value_bits(value, h->es);
     return GTB_OK;
 }

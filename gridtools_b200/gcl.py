@@ -331,6 +331,15 @@ class halo_exchange_dynamic_ut:
         _lib.check(fn(self._h, arr, n, self._stream()))
         _lib.check(_lib.lib().gtb_halo_next_epoch(self._h))
 
+    def set_boundary(self, value):
+        """distributed_boundaries.hpp:141-200 with value_boundary and proc_grid_predicate: from now on every unpack /
+        exchange of this object also writes `value` into the halo regions that face no neighbour, in the same launch.
+        None switches it off."""
+        if self._h is None:
+            raise RuntimeError("set_boundary() needs setup() first (p2p / nccl transports)")
+        _lib.check(_lib.lib().gtb_halo_set_boundary(self._h, -1 if value is None else _lib.GTB_BC_VALUE,
+                                                    0.0 if value is None else float(value)))
+
     def bind(self, *fields):
         """Pre-marshals a field list: returns a callable f(stream_handle=None) that runs pack + exchange + unpack for
         these fields with ONE C call (gtb_halo_exchange, two launches) and no per-call Python marshalling -- for time

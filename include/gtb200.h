@@ -192,6 +192,23 @@ int gtb_halo_error(gtb_halo *h, int *code);
  * still unpacks epoch e). */
 int gtb_halo_next_epoch(gtb_halo *h);
 
+/* ------------------------------------------------------------------------------------------ boundary conditions
+ * boundaries/boundary.hpp:57-72 (`boundary<BoundaryFunction, Arch, Predicate>::apply`) for the predefined conditions:
+ * GTB_BC_VALUE = value_boundary<T> / zero_boundary (value.hpp:27-66, zero.hpp: every field is set to `value`),
+ * GTB_BC_COPY = copy_boundary (copy.hpp:26-46: fields[0 .. n-2] receive fields[n-1]).  The condition is applied on
+ * the OUTSIDE region (halo_descriptor::loop_{low,high}_bound_outside, apply.hpp:44-56) of every direction n with
+ * direction_mask[n] != 0 (the Predicate; NULL = default_predicate = all 26).  Fields as in the gcl calls: pointer to
+ * storage element (0,0,0) including the halo, layout given by the descriptors' total lengths.  One launch for all
+ * directions and fields (apply_gpu.hpp:236-313 is one launch per call too, but per-direction 3-d thread blocks). */
+typedef enum { GTB_BC_VALUE = 0, GTB_BC_COPY = 1 } gtb_bc_kind;
+int gtb_boundary_apply(const gtb_halo_desc desc[3], const int direction_mask[27], int kind, double value,
+    void *const *fields, int n_fields, int elem_size, void *stream);
+/* distributed_boundaries.hpp:141-200 (exchange, then the boundary condition where the process grid has no neighbour,
+ * proc_grid_predicate): after this call every unpack / wait_unpack / exchange launch of the halo object also writes
+ * `value` into the outside regions of the directions without a neighbour -- the condition costs no extra launch.
+ * kind = GTB_BC_VALUE, or -1 to switch it off again. */
+int gtb_halo_set_boundary(gtb_halo *h, int kind, double value);
+
 /* ------------------------------------------------------------------------------------- recorded call sequences
  * The reference's user programs drive their time loop from C++ (tests/regression/gcl/copy_stencil_parallel.cpp:126-145:
  * he.pack / he.exchange / he.unpack followed by run(spec, backend, grid, fields...)), a microsecond or two of host

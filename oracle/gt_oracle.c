@@ -332,3 +332,35 @@ int gto_halo_exchange_all(const gto_halo h[3], const int dims[3], const int peri
     free(bufs);
     return 0;
 }
+
+/* --------------------------------- boundary conditions (boundaries/apply.hpp:44-56, value.hpp:27-66, zero.hpp,
+ * copy.hpp:26-46).  For every direction (ei, ej, ek) != 0 with mask[n] != 0 (n = (ei+1) + 3 (ej+1) + 9 (ek+1); mask
+ * NULL = default_predicate) the functor runs on loop_{low,high}_bound_outside of the three halo descriptors.
+ * kind 0: every field = value; kind 1: fields[0 .. n-2] = fields[n-1] (copy_boundary). */
+int gto_boundary_apply(const gto_halo h[3], const int *mask, int kind, double value, void **fields, int n_fields,
+    int elem_size) {
+    const int n_dst = kind == 1 ? n_fields - 1 : n_fields;
+    if (n_dst < 1 || (elem_size != 4 && elem_size != 8) || (kind != 0 && kind != 1))
+        return 1;
+    const int64_t s1 = h[0].total, s2 = (int64_t)h[0].total * h[1].total;
+    for (int ek = -1; ek <= 1; ++ek)
+        for (int ej = -1; ej <= 1; ++ej)
+            for (int ei = -1; ei <= 1; ++ei) {
+                const int n = (ei + 1) + 3 * (ej + 1) + 9 * (ek + 1);
+                if (n == 13 || (mask && !mask[n]))
+                    continue;
+                for (int k = lo_outside(&h[2], ek); k <= hi_outside(&h[2], ek); ++k)
+                    for (int j = lo_outside(&h[1], ej); j <= hi_outside(&h[1], ej); ++j)
+                        for (int i = lo_outside(&h[0], ei); i <= hi_outside(&h[0], ei); ++i) {
+                            const int64_t o = i + j * s1 + k * s2;
+                            for (int f = 0; f < n_dst; ++f) {
+                                if (elem_size == 8)
+                                    ((double *)fields[f])[o] = kind == 1 ? ((const double *)fields[n_fields - 1])[o] : value;
+                                else
+                                    ((float *)fields[f])[o] =
+                                        kind == 1 ? ((const float *)fields[n_fields - 1])[o] : (float)value;
+                            }
+                        }
+            }
+    return 0;
+}

@@ -89,6 +89,9 @@ int gto_proc_neighbour(const int dims[3], const int periodic[3], int pi, int pj,
 
 /* Full exchange among all ranks of a dims[3] process grid: fields[r*n_fields + f] is field f of rank r (all the
  * same halo layout h).  pack -> deliver -> unpack, exactly what pack()/exchange()/unpack() do together. */
+/* boundaries/apply.hpp:44-56 with value_boundary / zero_boundary (kind 0) or copy_boundary (kind 1) */
+int gto_boundary_apply(const gto_halo h[3], const int *mask, int kind, double value, void **fields, int n_fields,
+    int elem_size);
 int gto_halo_exchange_all(const gto_halo h[3], const int dims[3], const int periodic[3], void **fields, int n_fields,
     int elem_size);
 

@@ -150,6 +150,24 @@ def halo_exchange_all(h, dims, periodic, fields, elem_size):
                                      ptrs, n_fields, elem_size), "gto_halo_exchange_all")
 
 
+def boundary_apply(h, mask, kind, value, fields):
+    """boundaries/apply.hpp:44-56; fields: numpy arrays [d2, d1, d0] (modified in place); mask: 27 ints or None."""
+    ptrs = (C.c_void_p * len(fields))(*[f.ctypes.data for f in fields])
+    m = (C.c_int * 27)(*[int(x) for x in mask]) if mask is not None else None
+    _chk(lib().gto_boundary_apply(halos3(h), m, int(kind), C.c_double(value), ptrs, len(fields), fields[0].itemsize),
+         "gto_boundary_apply")
+
+
+def ref_boundary(h, mask, kind, value, fields):
+    """The reference's boundary<value_boundary / copy_boundary, gcl::cpu, predicate>::apply on cpu_ifirst stores
+    (oracle/_ref/libgtref.so); double precision."""
+    d2, d1, d0 = fields[0].shape
+    hh = (C.c_int * 15)(*[int(x) for t in h for x in t])
+    m = (C.c_int * 27)(*[int(x) for x in (mask if mask is not None else [1] * 27)])
+    ptrs = (C.c_void_p * 3)(*([f.ctypes.data for f in fields] + [None] * (3 - len(fields))))
+    _chk(ref().gtref_boundary(int(kind), C.c_double(value), hh, m, d0, d1, d2, ptrs, len(fields)), "gtref_boundary")
+
+
 # ------------------------------------------------------------------------------- reference build
 COPY, HORI_DIFF, VERT_ADV, TRIDIAGONAL, SIMPLE_HORI_DIFF = 0, 1, 2, 3, 4
 CPU_IFIRST, CPU_KFIRST, NAIVE = 0, 1, 2

@@ -22,6 +22,9 @@
 
 #include <omp.h>
 
+#include <gridtools/boundaries/boundary.hpp>
+#include <gridtools/boundaries/copy.hpp>
+#include <gridtools/boundaries/value.hpp>
 #include <gridtools/stencil/cartesian.hpp>
 #include <gridtools/stencil/cpu_ifirst.hpp>
 #include <gridtools/stencil/cpu_kfirst.hpp>
@@ -420,6 +423,16 @@ namespace {
     using tr_kfirst = gt::storage::cpu_kfirst;
 } // namespace
 
+namespace {
+    struct mask_predicate {
+        const int *mask;
+        template <class D>
+        bool operator()(D) const {
+            return mask[((int)D::i + 1) + 3 * ((int)D::j + 1) + 9 * ((int)D::k + 1)] != 0;
+        }
+    };
+} // namespace
+
 extern "C" {
 
 enum { GTREF_COPY = 0, GTREF_HORI_DIFF = 1, GTREF_VERT_ADV = 2, GTREF_TRIDIAGONAL = 3, GTREF_SIMPLE_HORI_DIFF = 4 };
@@ -513,6 +526,52 @@ void gtref_repo_simple_hori_diff(int d0, int d1, int d2, double *in, double *coe
                 bool interior = i >= 2 && i < d0 - 2 && j >= 2 && j < d1 - 2;
                 out_simple[o] = interior ? repo.out_simple(i, j, k) : 0.;
             }
+}
+
+/* The reference's boundary<BoundaryFunction, gcl::cpu, Predicate>::apply (boundaries/boundary.hpp:57-72) on cpu_ifirst
+ * stores built from dense boxes [d2][d1][d0]; kind 0 = value_boundary<double>(value), 1 = copy_boundary (the last field
+ * is the source); halo[15] = (minus, plus, begin, end, total) x 3; mask[27] = the predicate.  1 to 3 fields. */
+int gtref_boundary(int kind, double value, const int halo[15], const int mask[27], int d0, int d1, int d2,
+    double *const *fields, int n_fields) {
+    namespace bd = gt::boundaries;
+    if (n_fields < 1 || n_fields > 3)
+        return 1;
+    gt::array<gt::halo_descriptor, 3> hd{gt::halo_descriptor(halo[0], halo[1], halo[2], halo[3], halo[4]),
+        gt::halo_descriptor(halo[5], halo[6], halo[7], halo[8], halo[9]),
+        gt::halo_descriptor(halo[10], halo[11], halo[12], halo[13], halo[14])};
+    auto mk = [&](const double *p) {
+        return gt::storage::builder<gt::storage::cpu_ifirst>.type<double>().dimensions(d0, d1, d2)
+            .initializer([=](int i, int j, int k) { return p[i + (int64_t)d0 * (j + (int64_t)d1 * k)]; })
+            .build();
+    };
+    auto a = mk(fields[0]);
+    auto b = mk(fields[n_fields > 1 ? 1 : 0]);
+    auto c = mk(fields[n_fields > 2 ? 2 : 0]);
+    mask_predicate pred{mask};
+    if (kind == 0) {
+        auto bc = bd::make_boundary<gt::gcl::cpu>(hd, bd::value_boundary<double>(value), pred);
+        if (n_fields == 1)
+            bc.apply(a);
+        else if (n_fields == 2)
+            bc.apply(a, b);
+        else
+            bc.apply(a, b, c);
+    } else if (kind == 1) {
+        auto bc = bd::make_boundary<gt::gcl::cpu>(hd, bd::copy_boundary(), pred);
+        if (n_fields == 2)
+            bc.apply(a, b);
+        else if (n_fields == 3)
+            bc.apply(a, b, c);
+        else
+            return 1;
+    } else
+        return 1;
+    read_store<double>(a, d0, d1, d2, fields[0]);
+    if (n_fields > 1)
+        read_store<double>(b, d0, d1, d2, fields[1]);
+    if (n_fields > 2)
+        read_store<double>(c, d0, d1, d2, fields[2]);
+    return 0;
 }
 
 /* vertical_advection_repository.hpp:70-151; fields[5] = utens_stage_in, u_stage, wcon, u_pos, utens. */

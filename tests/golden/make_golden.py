@@ -76,6 +76,23 @@ def tridiagonal(ni, nj, nk, name):
                         out_ref=out, sup_ref=sup2, rhs_ref=rhs2)
 
 
+def boundary(name):
+    """boundary<value_boundary / copy_boundary, gcl::cpu, predicate>::apply of the reference on random boxes."""
+    h = [(2, 3, 2, 9, 14), (1, 2, 1, 6, 10), (1, 1, 1, 4, 6)]
+    shape = (6, 10, 14)
+    rng = np.random.default_rng(42)
+    mask = [int(x) for x in rng.integers(0, 2, 27)]
+    mask[13] = 0
+    value = 3.25
+    out = dict(halos=np.array(h), mask=np.array(mask), value=value)
+    for case, kind, nf, m in (("value_all", 0, 2, None), ("value_masked", 0, 3, mask), ("copy_masked", 1, 3, mask)):
+        f = [rng.standard_normal(shape) for _ in range(nf)]
+        r = [a.copy() for a in f]
+        o.ref_boundary(h, m, kind, value, r)
+        out[case + "_in"], out[case + "_ref"] = np.array(f), np.array(r)
+    np.savez_compressed(os.path.join(HERE, name), **out)
+
+
 if __name__ == "__main__":
     o.build(ref=True)
     hori_diff(12, 33, 6, "hori_diff_12x33x6.npz")     # test_environment sizes 12x33 (k shortened)
@@ -85,6 +102,7 @@ if __name__ == "__main__":
     tridiagonal(12, 33, 6, "tridiagonal_12x33x6.npz") # tridiagonal.cpp sizes
     simple_hori_diff(70, 19, 3, "simple_hori_diff_70x19x3.npz")
     simple_hori_diff(12, 33, 6, "simple_hori_diff_12x33x6.npz")
+    boundary("boundary_14x10x6.npz")
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -139,3 +139,24 @@ def test_gcl_class_exchanges_like_the_reference_test():
     print(r.stdout)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
     assert "ALL PASSED" in r.stdout and r.stdout.count(" ok ") >= 7
+
+
+# ------------------------------------------------------------------------------------------------ boundaries (C++ class)
+BC_TU = r"""
+#include <gtb200/boundaries/boundary.hpp>
+namespace bd = gtb200::boundaries;
+void f(double *a, double *b, float *c) {
+    std::array<gtb_halo_desc, 3> h = {{{2, 2, 2, 33, 36}, {2, 2, 2, 17, 20}, {0, 0, 0, 4, 5}}};
+    bd::make_boundary(h, bd::value_boundary<double>(3.5)).apply(a, b);
+    bd::make_boundary(h, bd::zero_boundary<float>()).apply(c);
+    bd::make_boundary(h, bd::copy_boundary(), [](int ei, int, int) { return ei < 0; }).apply_on(nullptr, a, b);
+}
+"""
+
+
+def test_boundary_header_is_plain_host_code(tmp_path):
+    src = tmp_path / "bc.cpp"
+    src.write_text(BC_TU)
+    cmd = ["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"), str(src)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
