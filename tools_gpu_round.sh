@@ -6,7 +6,7 @@ nproc >> gpurun_out/gpu.txt
 STEP=${1:-all}
 if [ "$STEP" = all ] || [ "$STEP" = test ]; then
   : > gpurun_out/pytest_gpu.log
-  for f in tests/test_stencils_gpu.py tests/test_halo_gpu.py tests/test_cpp_boundary.py; do   # one process per file: a fault cannot cascade
+  for f in tests/test_stencils_gpu.py tests/test_halo_gpu.py tests/test_cpp_boundary.py tests/test_boundaries.py; do   # one process per file: a fault cannot cascade
     timeout 900 python -m pytest $f -m gpu -q --maxfail=10 -p no:cacheprovider --timeout=300 >> gpurun_out/pytest_gpu.log 2>&1
     echo "pytest $f exit $?" >> gpurun_out/pytest_gpu.log
   done
