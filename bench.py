@@ -125,8 +125,9 @@ def device_fields(torch, storage, name, ni, nj, nk, dtype, i_off=0, j_off=0, gi=
 class ClockSampler:
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.002):
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.period = period
         self._stop = threading.Event()
         self._thread = None
         try:
@@ -154,7 +155,7 @@ class ClockSampler:
                         self.reasons.add(n)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(self.period)
 
     def start(self):
         if self.nv:
@@ -286,6 +287,7 @@ def b200_arm(args):
     set_bytes = n_fields * (NI + 2 * H + 16) * (NJ + 2 * H) * NK * itemsize
     # enough rotating sets that no step finds its inputs in the 126 MB L2; one set when a set alone is far larger
     n_sets = 1 if set_bytes > (1 << 30) else (2 if name == "vert_adv" else 3)
+    n_sets = int(os.environ.get("GTB_NSETS", n_sets))
     on_device = NI * NJ * NK > 32 * 2**20
     sets = []
     dtr = None
@@ -374,7 +376,12 @@ def b200_arm(args):
         else:
             run_stencil(s)
 
-    sampler = ClockSampler(local)
+    # An NVML query stalls the GPU it reads for tens of microseconds: eight ranks sampling every 5 ms cost 5 us of a
+    # 64 us step (profiles/r01_mgpu_ab_8.txt).  One GPU is sampled (rank 0's), immediately when the timed region starts
+    # and then every 5 ms (10 ms with several ranks); GTB_NO_SAMPLER=1 switches it off to measure what is left.
+    sampler = ClockSampler(local, 0.005 if world == 1 else 0.010)
+    if os.environ.get("GTB_NO_SAMPLER") == "1" or rank != 0:
+        sampler.nv = None
     for s in range(n_warm):
         step(s)
     barrier()
