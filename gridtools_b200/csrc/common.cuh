@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <utility>
 
 #include "../../include/gtb200.h"
 
@@ -46,6 +47,7 @@ namespace gtb {
         int copy_vec = 1;     // vectorised copy on/off
         int l2_persist_mb = -1; // L2 set-aside for the k-cache slabs in MB: -1 auto (slab size), 0 off
         int halo_fused = 0;     // gtb_halo_exchange as ONE launch (pack, signal, wait, unpack); 0: two launches
+        int pdl = 1;            // programmatic dependent launch of the vertical advection kernel (prologue under the previous kernel's tail)
         int reserve_sms = 0;    // SMs the persistent stencil grids leave free (for a halo exchange that runs beside them)
     };
     options &opts();
@@ -82,6 +84,24 @@ namespace gtb {
     }
 
     inline bool field_ok(const gtb_field *f) { return f && f->ptr; }
+
+    // Launch with the programmatic-stream-serialization attribute (option "pdl"): the kernel must call ptx::pdl_wait()
+    // before it reads or writes anything an earlier kernel of the stream may have touched.
+    template <class... KArgs, class... Args>
+    inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+        Args &&...args) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = block;
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = opts().pdl ? 1 : 0;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+    }
 
     // TMA descriptor encoder, resolved from the driver at run time (no link-time dependency on libcuda).
     typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -221,6 +241,13 @@ namespace gtb {
         __device__ __forceinline__ void cp_async_wait() {
             asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
         }
+
+        // Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may be
+        // scheduled while the previous kernel of the stream is still draining; pdl_wait() blocks until that kernel has
+        // completed and its memory operations are visible (nothing it wrote may be touched before), pdl_launch_dependents()
+        // lets the NEXT kernel of the stream start being scheduled as SMs free up.  Both are no-ops for a plain launch.
+        __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+        __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
         // Streaming global accesses with an L2 eviction policy.
         template <class T>

@@ -342,6 +342,8 @@ namespace {
                 int st = prepare_kernel(kernel, smem);
                 if (st)
                     return st;
+                // (no programmatic dependent launch here: with two CTAs per SM the early CTAs of the next launch take
+                // slots from the running one -- 24.6 -> 29.8 us measured)
                 kernel<<<grid, THREADS, smem, stream>>>(map_in, map_co, p);
                 count_launch();
                 return check_launch("hd_tma_kernel");

@@ -175,6 +175,7 @@ namespace {
             {"va.stages", &o.va_stages},
             {"va.stagger", &o.va_stagger},
             {"reserve_sms", &o.reserve_sms},
+            {"pdl", &o.pdl},
             {"halo.fused", &o.halo_fused},
             {"copy.vec", &o.copy_vec}};
         for (auto &t : table)

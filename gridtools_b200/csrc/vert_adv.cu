@@ -1718,6 +1718,8 @@ namespace {
         tm::fence_before();
         __syncthreads();
         tm::fence_after();
+        ptx::pdl_launch_dependents(); // the next kernel of the stream may be scheduled as this one's CTAs retire
+        ptx::pdl_wait();              // set-up above ran under the previous kernel's tail; its data is visible from here
         const uint32_t tbase = *tslot;
         const uint32_t tw = tbase + ((uint32_t)((pw & 3) * 32) << 16) + (uint32_t)((pw >> 2) * 256);
 
@@ -1731,6 +1733,18 @@ namespace {
         const int cb_top = (nk - 2) / KC;   // last stored chunk (holds level nk-2)
         const int nstored = cb_top + 1;
         const int bar_id = 1 + pw;
+        // diagnosis only (va.debug & 128): globaltimer stamps per pair -- [0] start, F warp pass p: [1 + 4p] begin,
+        // [2 + 4p] end; B warp pass p: [3 + 4p] begin, [4 + 4p] end
+        long long *const trace = (p.debug & 128) && lane == 0 && !idle
+                                     ? reinterpret_cast<long long *>(reinterpret_cast<char *>(p.tickets) + 256) +
+                                           (size_t)(blockIdx.x * 8 + pw) * 32
+                                     : nullptr;
+        auto stamp = [&](int e) {
+            if (trace && e < 32)
+                trace[e] = (long long)globaltimer_ns();
+        };
+        if (!is_b)
+            stamp(0);
 
         if (idle) {
             // a pair slot left empty so that the strips of a launch divide evenly among the pairs
@@ -1777,6 +1791,7 @@ namespace {
                 st.u_k = u0;
                 st.u_km1 = st.wsum_k = st.cc_prev = st.dc_prev = st.up_last = T(0);
                 const int need0 = (pass - 1) * nstored; // chunks the partner had read before this pass
+                stamp(1 + 4 * pass);
                 for (int c = 0; c < nchunks; ++c) {
                     if (c + S - 1 < nchunks) // refill the stage consumed in the previous iteration
                         issue_f(i0, j, c + S - 1);
@@ -1844,6 +1859,7 @@ namespace {
                     __syncwarp(); // all lanes are done with stage s before one lane refills it
                 }
                 // ---- hand the strip to the partner and go on
+                stamp(2 + 4 * pass);
                 const int par = pass & 1;
                 hand[(par * 2) * 32] = st.dc_prev;
                 hand[(par * 2 + 1) * 32] = st.up_last;
@@ -1880,12 +1896,13 @@ namespace {
                 if (item < 0)
                     break;
                 const int more = ctl[3 + par * 3], mirrored = ctl[4 + par * 3];
+                stamp(3 + 4 * pass);
                 T data = hand[(par * 2) * 32];
                 const T up_last = hand[(par * 2 + 1) * 32];
                 const int ti = item % p.tiles_i, j = item / p.tiles_i;
                 const int i0 = ti * 32;
                 const bool active = i0 + lane < p.ni;
-                auto issue_b = [&](int cb) {
+                auto issue_b = [&](int cb) { // u_pos of chunk cb: an L2 hit (the forward load left the lines evict_last)
                     const int s = b_issue;
                     b_issue = b_issue + 1 == SB ? 0 : b_issue + 1;
                     if (ptx::elect_one()) {
@@ -1899,7 +1916,8 @@ namespace {
                 if (active) // last_level :118-121
                     *o = dtr * (data - up_last);
                 // The k-cache is read one chunk ahead of the arithmetic: the TMEM / shared-memory latency of chunk cb-1
-                // hides behind the four levels of chunk cb, and the partner learns early that the slot is free.
+                // hides behind the four levels of chunk cb.  While the partner sweeps forward (`more`) it is told
+                // after every second chunk which slots are free; in the last, backward-only pass nobody listens.
                 T bcc[KC], bdc[KC];
                 uint32_t w[NW];
                 auto fetch = [&](int cb) { // issue the loads of chunk cb
@@ -1908,13 +1926,12 @@ namespace {
                         tm::ld<NW>(tw + (uint32_t)(ph * NW), w);
                     return ph;
                 };
-                auto land = [&](int cb, int ph) { // ... and wait for them; publish the slot as read
+                auto land = [&](int cb, int ph) { // ... and wait for them
                     if (ph < c_split) {
                         tm::wait_ld();
 #pragma unroll
                         for (int u = 0; u < KC; ++u)
                             tm::unpack<T>(w + u * CPL, bcc[u], bdc[u]);
-                        tm::fence_before();
                     } else {
                         const T *q = ss + (ph - c_split) * (KC * 64);
 #pragma unroll
@@ -1925,17 +1942,17 @@ namespace {
                                 bdc[u] = q[u * 64 + 32];
                             }
                         }
-                        __threadfence_block();
                     }
-                    __syncwarp();
                     ++done;
-                    if (lane == 0)
-                        ctl[0] = done; // the slot may be overwritten by the partner's forward sweep
+                    if (more && ((done & 1) == 0 || cb == 0)) { // the slots read so far may be overwritten by the partner
+                        tm::fence_before();
+                        __threadfence_block();
+                        __syncwarp();
+                        if (lane == 0)
+                            ctl[0] = done;
+                    }
                 };
-                land(cb_top, fetch(cb_top));
-                for (int cb = cb_top; cb >= 0; --cb) {
-                    if (cb - (SB - 1) >= 0)
-                        issue_b(cb - (SB - 1));
+                auto sweep = [&](int cb, auto checked) { // levels of chunk cb, top down (body :111-116)
                     T ccv[KC], dcv[KC];
 #pragma unroll
                     for (int u = 0; u < KC; ++u)
@@ -1943,6 +1960,8 @@ namespace {
                     int ph_next = 0;
                     if (cb > 0)
                         ph_next = fetch(cb - 1);
+                    if (cb - (SB - 1) >= 0)
+                        issue_b(cb - (SB - 1));
                     const int s = b_wait;
                     ptx::mbar_wait(&bfull[s], b_phase);
                     if (++b_wait == SB) {
@@ -1951,8 +1970,8 @@ namespace {
                     }
                     const T *sb = reinterpret_cast<const T *>(bring + s * bstage) + lane;
 #pragma unroll
-                    for (int u = KC - 1; u >= 0; --u) { // body :111-116
-                        if (cb * KC + u <= nk - 2) {
+                    for (int u = KC - 1; u >= 0; --u) {
+                        if (!decltype(checked)::value || cb * KC + u <= nk - 2) {
                             data = dcv[u] - ccv[u] * data;
                             o -= us_sk;
                             if (active)
@@ -1961,9 +1980,13 @@ namespace {
                     }
                     if (cb > 0)
                         land(cb - 1, ph_next);
-                    else
-                        __syncwarp(); // all lanes are done with the ring stage before one lane refills it
-                }
+                    __syncwarp(); // all lanes are done with the ring stage before one lane refills it
+                };
+                land(cb_top, fetch(cb_top));
+                sweep(cb_top, std::true_type()); // the top chunk may hold fewer than KC levels
+                for (int cb = cb_top - 1; cb >= 0; --cb)
+                    sweep(cb, std::false_type());
+                stamp(4 + 4 * pass);
                 if (!more)
                     break;
             }
@@ -2244,6 +2267,9 @@ namespace {
                                           : launch_va_resident<T, 4, 3, 2>(maps, p, grid, stream));
     }
 
+    constexpr int kTraceEvents = 32, kTraceSlots = 2048;
+    constexpr size_t kTraceBytes = (size_t)kTraceSlots * kTraceEvents * sizeof(long long);
+
     // {next strip, finished warps} of the TMEM variant, one pair per device, zeroed once (the kernel resets it).
     int *va_ticket_counters() {
         static int *ctr[64] = {};
@@ -2251,8 +2277,8 @@ namespace {
         if (d < 0 || d >= 64)
             return nullptr;
         if (!ctr[d]) {
-            int *q = nullptr;
-            if (cudaMalloc(&q, 256) != cudaSuccess || cudaMemset(q, 0, 256) != cudaSuccess) {
+            int *q = nullptr; // 256 bytes of counters + the (diagnosis only) time-stamp trace of va.debug & 128
+            if (cudaMalloc(&q, 256 + kTraceBytes) != cudaSuccess || cudaMemset(q, 0, 256 + kTraceBytes) != cudaSuccess) {
                 cuda_fail(cudaGetLastError(), "va ticket counters");
                 return nullptr;
             }
@@ -2363,7 +2389,7 @@ namespace {
 
     // Paired-warp TMEM variant (va.variant = 7): va.ctas_per_sm = F/B warp pairs in use per CTA (1..8, 0 = auto;
     // < 0: an absolute number of CTAs, tests), va.stages = forward ring depth, va.unroll = depth of the
-    // backward u_pos ring (default 3).
+    // (no further knobs).
     template <class T>
     int vert_adv_pair(va_params<T> &p, const options &o, device_state *d, const va_maps &maps, cudaStream_t stream) {
         constexpr int KC = 4;
@@ -2372,6 +2398,7 @@ namespace {
         if (pairs == 0)
             pairs = 8;
         p.pairs = pairs;
+        p.debug = o.va_debug;
         const int levels = va_tmem_cfg<T>::levels(8);
         const int cb_top = (p.nk - 2) / KC;
         int k_split = (cb_top + 1) * KC;
@@ -2409,7 +2436,7 @@ namespace {
             GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             done_dev = d->device;
         }
-        kernel<<<grid, 512, smem, stream>>>(maps, p);
+        GTB_CUDA(launch_pdl(kernel, dim3(grid), dim3(512), (size_t)smem, stream, maps, p));
         count_launch();
         return check_launch("va_pair_kernel");
     }
@@ -2650,4 +2677,20 @@ GTB_API int gtb_tridiagonal_f64(const gtb_field *inf, const gtb_field *diag, con
     td_kernel<double, 4><<<(unsigned)blocks, threads, 0, as_stream(stream)>>>(p);
     count_launch();
     return check_launch("td_kernel");
+}
+
+GTB_API int gtb_debug_trace(void *dst, int64_t bytes) {
+    if (!dst || bytes < 0)
+        return fail(GTB_ERR_ARG, "gtb_debug_trace: bad argument");
+    if (!dev())
+        return GTB_ERR_CUDA;
+    int *base = va_ticket_counters();
+    if (!base)
+        return GTB_ERR_ALLOC;
+    if ((size_t)bytes > kTraceBytes)
+        bytes = (int64_t)kTraceBytes;
+    GTB_CUDA(cudaDeviceSynchronize());
+    GTB_CUDA(cudaMemcpy(dst, reinterpret_cast<char *>(base) + 256, (size_t)bytes, cudaMemcpyDeviceToHost));
+    GTB_CUDA(cudaMemset(reinterpret_cast<char *>(base) + 256, 0, kTraceBytes));
+    return GTB_OK;
 }

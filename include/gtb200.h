@@ -70,6 +70,10 @@ int gtb_get_option(const char *key, int *value);
 /* Releases the cached scratch (temporaries) of the calling device; the reference keeps them in a thread-local
  * sid::device::cached_allocator (sid/allocator.hpp:65-95, stencil/gpu/entry_point.hpp:155-175). */
 int gtb_release_scratch(void);
+/* Diagnosis only: with option ("va.debug", 128) the paired-warp vertical advection kernel writes globaltimer stamps
+ * per warp pair ([pair][32] int64: [0] start, forward pass p [1+4p] begin / [2+4p] end, backward pass p [3+4p] / [4+4p]);
+ * this synchronises the device, copies up to `bytes` of them to `dst` (host) and clears them. */
+int gtb_debug_trace(void *dst, int64_t bytes);
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t gtb_launch_count(void);
 
