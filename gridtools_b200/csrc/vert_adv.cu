@@ -1668,8 +1668,10 @@ namespace {
                            slab_bytes + 4 * 32 * (int)sizeof(T) + (stages + bstages) * 8 + 32) + 16;
     }
 
+    // Named barrier between the two warps of a pair (the non-.aligned form: the warps reach it from different code).
     __device__ __forceinline__ void named_barrier_sync(int id, int threads) {
-        asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+        __syncwarp();
+        asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
     }
 
     template <class T, int KC>
