@@ -46,6 +46,7 @@ namespace gtb {
         int va_stagger = 0;   // TMEM variant: start stagger between the warps of a CTA, in units of 100 ns
         int copy_vec = 1;     // vectorised copy on/off
         int l2_persist_mb = -1; // L2 set-aside for the k-cache slabs in MB: -1 auto (slab size), 0 off
+        int halo_max_blocks = 0; // > 0: grid size cap of the halo transfer kernels (0: one block per SM)
         int halo_fused = 0;     // gtb_halo_exchange as ONE launch (pack, signal, wait, unpack); 0: two launches
         int pdl = 1;            // programmatic dependent launch of the vertical advection kernel (prologue under the previous kernel's tail)
         int reserve_sms = 0;    // SMs the persistent stencil grids leave free (for a halo exchange that runs beside them)

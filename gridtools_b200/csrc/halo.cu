@@ -335,12 +335,14 @@ namespace {
         sy.timeout_cycles = kTimeoutCycles;
     }
 
-    // Blocks of a transfer launch.  Next to a persistent stencil kernel the SMs it leaves free (reserve_sms) hold 8
-    // of these blocks each; otherwise at most one small block per SM.
+    // Blocks of a transfer launch: at most one small block per SM (option halo.max_blocks overrides).  The first of
+    // them start at once on the SMs a persistent stencil kernel leaves free (reserve_sms), the rest as its CTAs retire;
+    // capping the grid at what the reserved SMs hold makes an 8-neighbour exchange 7 us slower (r01_overlap_schemes.txt).
     int xfer_grid(int chunks) {
         device_state *dv = dev();
-        const int rs = opts().reserve_sms;
-        const int cap = rs > 0 ? rs * (2048 / kThreads) : (dv ? dv->sm_count : 128);
+        int cap = dv ? dv->sm_count : 128;
+        if (opts().halo_max_blocks > 0)
+            cap = opts().halo_max_blocks;
         return chunks < 1 ? 1 : (chunks > cap ? cap : chunks);
     }
 

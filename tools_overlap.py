@@ -145,9 +145,8 @@ def run(scheme):
     return a.elapsed_time(b) / STEPS * 1e3
 
 
-for fused in (0, 1):
-    _lib.set_option("halo.fused", fused)
-    for rs in (0, 4):
-        _lib.set_option("reserve_sms", rs)
-        for scheme in ("A", "B", "S", "C"):
-            print("%s fused=%d reserve_sms=%d scheme %s: %.2f us per step" % (name, fused, rs, scheme, run(scheme)), flush=True)
+for rs, cap in ((4, 0), (4, 64), (4, 148), (0, 0), (8, 148), (2, 148)):
+    _lib.set_option("reserve_sms", rs)
+    _lib.set_option("halo.max_blocks", cap)
+    for scheme in ("S", "C"):
+        print("%s reserve_sms=%d max_blocks=%d scheme %s: %.2f us per step" % (name, rs, cap, scheme, run(scheme)), flush=True)
