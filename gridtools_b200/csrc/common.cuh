@@ -47,6 +47,7 @@ namespace gtb {
         int copy_vec = 1;     // vectorised copy on/off
         int l2_persist_mb = -1; // L2 set-aside for the k-cache slabs in MB: -1 auto (slab size), 0 off
         int halo_max_blocks = 0; // > 0: grid size cap of the halo transfer kernels (0: one block per SM)
+        int halo_vec = 1;       // 16-byte vector transfers where the halo regions allow it
         int halo_fused = 0;     // gtb_halo_exchange as ONE launch (pack, signal, wait, unpack); 0: two launches
         int pdl = 1;            // programmatic dependent launch of the vertical advection kernel (prologue under the previous kernel's tail)
         int reserve_sms = 0;    // SMs the persistent stencil grids leave free (for a halo exchange that runs beside them)

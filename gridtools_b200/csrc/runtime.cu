@@ -177,6 +177,7 @@ namespace {
             {"reserve_sms", &o.reserve_sms},
             {"pdl", &o.pdl},
             {"halo.fused", &o.halo_fused},
+            {"halo.vec", &o.halo_vec},
             {"halo.max_blocks", &o.halo_max_blocks},
             {"copy.vec", &o.copy_vec}};
         for (auto &t : table)
