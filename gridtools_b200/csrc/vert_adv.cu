@@ -53,7 +53,8 @@ namespace {
         int bstages;    // fused TMEM variant: depth of the u_pos ring of the backward sweep
         int pairs;      // paired-warp variant: F/B warp pairs in use per CTA
         int stagger_ns; // TMEM variant: warp w of a CTA starts w * stagger_ns late (de-phases forward and backward sweeps)
-        int *tickets;   // TMEM variant: {next strip, finished warps}, self-resetting
+        int *tickets;   // TMEM variants: {next strip, finished warps}, self-resetting; one of 16 slots per launch
+        long long *trace; // diagnosis only (va.debug & 128): time stamps per warp pair
     };
 
     template <class T, bool Hints>
@@ -1738,8 +1739,7 @@ namespace {
         // diagnosis only (va.debug & 128): globaltimer stamps per pair -- [0] start, F warp pass p: [1 + 4p] begin,
         // [2 + 4p] end; B warp pass p: [3 + 4p] begin, [4 + 4p] end
         long long *const trace = (p.debug & 128) && lane == 0 && !idle
-                                     ? reinterpret_cast<long long *>(reinterpret_cast<char *>(p.tickets) + 256) +
-                                           (size_t)(blockIdx.x * 8 + pw) * 32
+                                     ? p.trace + (size_t)(blockIdx.x * 8 + pw) * 32
                                      : nullptr;
         auto stamp = [&](int e) {
             if (trace && e < 32)
@@ -2272,8 +2272,15 @@ namespace {
     constexpr int kTraceEvents = 32, kTraceSlots = 2048;
     constexpr size_t kTraceBytes = (size_t)kTraceSlots * kTraceEvents * sizeof(long long);
 
-    // {next strip, finished warps} of the TMEM variant, one pair per device, zeroed once (the kernel resets it).
+    // {next strip, finished warps} of the TMEM variants, zeroed once (every launch resets its own pair when it ends).
+    // Launches rotate over 16 pairs, so launches that run at the same time on different streams do not share one.
+    int *va_ticket_base();
+    std::atomic<unsigned> g_va_launch{0};
     int *va_ticket_counters() {
+        int *base = va_ticket_base();
+        return base ? base + 2 * (g_va_launch.fetch_add(1, std::memory_order_relaxed) % 16) : nullptr;
+    }
+    int *va_ticket_base() {
         static int *ctr[64] = {};
         const int d = dev()->device;
         if (d < 0 || d >= 64)
@@ -2319,6 +2326,7 @@ namespace {
         p.stages = stages;
         p.stagger_ns = o.va_stagger > 0 ? o.va_stagger * 100 : 0;
         p.tickets = va_ticket_counters();
+        p.trace = reinterpret_cast<long long *>(reinterpret_cast<char *>(va_ticket_base()) + 256);
         if (!p.tickets)
             return GTB_ERR_ALLOC;
         const int64_t strips = (int64_t)p.tiles_i * p.nj;
@@ -2368,6 +2376,7 @@ namespace {
         p.bstages = bstages;
         p.stagger_ns = 0;
         p.tickets = va_ticket_counters();
+        p.trace = reinterpret_cast<long long *>(reinterpret_cast<char *>(va_ticket_base()) + 256);
         if (!p.tickets)
             return GTB_ERR_ALLOC;
         const int64_t strips = (int64_t)p.tiles_i * p.nj;
@@ -2423,6 +2432,7 @@ namespace {
         p.bstages = bstages;
         p.stagger_ns = 0;
         p.tickets = va_ticket_counters();
+        p.trace = reinterpret_cast<long long *>(reinterpret_cast<char *>(va_ticket_base()) + 256);
         if (!p.tickets)
             return GTB_ERR_ALLOC;
         int grid = o.va_ctas_per_sm < 0 ? -o.va_ctas_per_sm : stencil_sms(d);
@@ -2686,7 +2696,7 @@ GTB_API int gtb_debug_trace(void *dst, int64_t bytes) {
         return fail(GTB_ERR_ARG, "gtb_debug_trace: bad argument");
     if (!dev())
         return GTB_ERR_CUDA;
-    int *base = va_ticket_counters();
+    int *base = va_ticket_base();
     if (!base)
         return GTB_ERR_ALLOC;
     if ((size_t)bytes > kTraceBytes)

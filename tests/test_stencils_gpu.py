@@ -473,3 +473,33 @@ def test_sequence_vertical_advection(gt, oracle):
         st[0]._host_stale = True
         inner = (slice(None), slice(3, -3), slice(3, -3))
         assert np.array_equal(st[0].to_numpy()[inner], oracle.vert_adv(*xs, 0.15)[inner])
+
+
+def test_vert_adv_concurrent_streams(gt, oracle):
+    """Two launches of the (ticket-scheduled) vertical advection kernel that run at the same time on different streams
+    must not share their strip counters."""
+    torch = gt.torch
+    rng = np.random.default_rng(8)
+    ni, nj, nk = 96, 40, 80
+    shape = (nk, nj + 6, ni + 6)
+    problems = []
+    for _ in range(4):
+        arrs = [rng.uniform(5, 9, shape), rng.uniform(5, 9, shape), rng.uniform(-3e-4, 3e-4, shape),
+                rng.uniform(5, 9, shape), rng.uniform(-1e-5, 1e-5, shape)]
+        st = [gt.storage.from_numpy(a, (3, 3, 0)) for a in arrs]
+        for f in st:
+            f.const_target_tensor()
+        problems.append((arrs, st, torch.cuda.Stream()))
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for arrs, st, stream in problems:
+            with torch.cuda.stream(stream):
+                gt.stencil.vertical_advection_dycore(*st, 0.15)
+    torch.cuda.synchronize()
+    inner = (slice(None), slice(3, -3), slice(3, -3))
+    for arrs, st, _ in problems:
+        want = arrs[0]
+        for rep in range(3):
+            want = oracle.vert_adv(want, *arrs[1:], 0.15)
+        st[0]._host_stale = True
+        assert np.array_equal(st[0].to_numpy()[inner], want[inner])
