@@ -344,31 +344,55 @@ def b200_arm(args):
     total_steps = max(args.warmup, 3) + args.steps
     n_warm = max(args.warmup, 3)
     seq, step_ops = None, []
-    if he is not None:
-        _lib.set_option("reserve_sms", int(os.environ.get("GTB_RESERVE_SMS", RESERVE_SMS)))  # left to the exchange
-        _lib.set_option("halo.fused", int(os.environ.get("GTB_HALO_FUSED", HALO_FUSED)))
-        seq = stencil.Sequence()
+    gated = False
+
+    def build_sequence(use_gates):
+        """The loop of total_steps steps as one gtb_seq.  use_gates: the two orderings between the streams (stencil
+        after unpack, unpack after the stencil that last read the halos) are waits ON THE DEVICE (gtb_stencil_gate /
+        gtb_halo_gate) instead of stream events.  Measured (profiles/README.md): 2 us per step cheaper for vert_adv on one
+        GPU that is its own neighbour, no gain between two real GPUs (57.9 against 56.6-56.8 us), 3 us dearer for
+        hori_diff -- so stream events stay the default and GTB_GATES=1 selects the gates."""
+        sq, ops = stencil.Sequence(), []
         M = n_sets + 2  # event slots: exchange done = s % M, stencil done = M + s % M
+        done = torch.zeros(1, dtype=torch.int64, device="cuda") if use_gates else None
+        flag, e0 = (he.unpacked_flag(), he.epoch()) if use_gates else (None, 0)
+        torch.cuda.synchronize()
 
         def add_exchange(t):
             if t - n_sets >= 0:
-                seq.wait(comm_h, M + (t - n_sets) % M)
-            seq.halo_exchange(he, [sets[t % n_sets][exch_index]], comm_h)
-            seq.record(t % M, comm_h)
+                if use_gates:
+                    sq.halo_gate(he, done.data_ptr(), t - n_sets + 1)
+                else:
+                    sq.wait(comm_h, M + (t - n_sets) % M)
+            sq.halo_exchange(he, [sets[t % n_sets][exch_index]], comm_h)
+            if not use_gates:
+                sq.record(t % M, comm_h)
 
         for s in range(total_steps):
-            first = len(seq)
+            first = len(sq)
             if s == 0:
                 add_exchange(0)
             if s + 1 < total_steps:
                 add_exchange(s + 1)
-            seq.wait(comp_h, s % M)
-            if name == "vert_adv":
-                seq.vertical_advection_dycore(*sets[s % n_sets], dtr, stream=comp_h)
+            if use_gates:
+                sq.stencil_gate(flag, e0 + s, done.data_ptr())
             else:
-                seq.horizontal_diffusion(*sets[s % n_sets], stream=comp_h)
-            seq.record(M + s % M, comp_h)
-            step_ops.append((first, len(seq) - first))
+                sq.wait(comp_h, s % M)
+            if name == "vert_adv":
+                sq.vertical_advection_dycore(*sets[s % n_sets], dtr, stream=comp_h)
+            else:
+                sq.horizontal_diffusion(*sets[s % n_sets], stream=comp_h)
+            if not use_gates:
+                sq.record(M + s % M, comp_h)
+            ops.append((first, len(sq) - first))
+        sq.keep = done
+        return sq, ops
+
+    if he is not None:
+        _lib.set_option("reserve_sms", int(os.environ.get("GTB_RESERVE_SMS", RESERVE_SMS)))  # left to the exchange
+        _lib.set_option("halo.fused", int(os.environ.get("GTB_HALO_FUSED", HALO_FUSED)))
+        gated = name == "vert_adv" and itemsize == 8 and os.environ.get("GTB_GATES", "0") == "1"  # opt-in, see docstring
+        seq, step_ops = build_sequence(gated)
 
     def step(s):
         if seq is not None:
@@ -387,6 +411,17 @@ def b200_arm(args):
     barrier()
     if he is not None and he.check() != 0:
         raise SystemExit("bench.py: a halo wait timed out during warm-up")
+    if gated:  # a device-side wait that gave up means the choreography is broken on this box: use stream events
+        t = torch.tensor([_lib.gate_timeouts()], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if int(t.item()) > 0:
+            gated = False
+            torch.cuda.synchronize()
+            seq, step_ops = build_sequence(False)
+            # the halo object's epochs went on during the gated warm-up: nothing to reset, events carry no numbers
+            for s in range(n_warm):
+                step(s)
+            barrier()
     sampler.start()
     launches0 = _lib.launch_count()
     if seq is None:
@@ -470,8 +505,9 @@ def b200_arm(args):
             " (%s scaling of a %dx%dx%d global domain)" % (args.scaling, global_ni, global_nj, NK)),
                    "decomposition": "%dx%dx1 IJ process grid, halo exchange of %s every step over NVLink (fused pack + peer "
                                     "stores, device-side flags), overlapped with the previous step's stencil on a "
-                                    "high-priority stream; %d SMs reserved for it; loop issued as one recorded gtb_seq" % (
-                       dims[0], dims[1], "wcon" if name == "vert_adv" else "in", RESERVE_SMS) if world > 1 else "single GPU",
+                                    "high-priority stream, ordered by %s; %d SMs reserved for it; loop issued as one recorded gtb_seq" % (
+                       dims[0], dims[1], "wcon" if name == "vert_adv" else "in",
+                       "device-side gates" if gated else "stream events", RESERVE_SMS) if world > 1 else "single GPU",
                    "l2": "inputs of one step (%d MB) exceed L2 and %d field set(s) are rotated" % (
                        sum(f.nbytes_host for f in sets[0][:5 if name == "vert_adv" else 2]) // 2**20, n_sets),
                    "vs_baseline_ref": "reference stencil::gpu on P100, BASELINE.md section 1"},

@@ -77,6 +77,13 @@ _SIG = {
     "gtb_boundary_apply": (C.c_int, [C.POINTER(HaloDesc), C.POINTER(C.c_int), C.c_int, C.c_double, C.POINTER(C.c_void_p),
                                      C.c_int, C.c_int, C.c_void_p]),
     "gtb_halo_set_boundary": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
+    "gtb_halo_unpacked_flag": (C.c_void_p, [C.c_void_p]),
+    "gtb_halo_epoch": (C.c_uint64, [C.c_void_p]),
+    "gtb_stencil_gate": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
+    "gtb_halo_gate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "gtb_gate_timeouts": (C.c_int, [C.POINTER(C.c_int64)]),
+    "gtb_seq_add_stencil_gate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "gtb_seq_add_halo_gate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     "gtb_seq_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "gtb_seq_destroy": (C.c_int, [C.c_void_p]),
     "gtb_seq_size": (C.c_int, [C.c_void_p]),
@@ -131,6 +138,12 @@ def get_option(key):
     v = C.c_int()
     check(lib().gtb_get_option(key.encode(), C.byref(v)))
     return v.value
+
+
+def gate_timeouts():
+    n = C.c_int64()
+    check(lib().gtb_gate_timeouts(C.byref(n)))
+    return n.value
 
 
 def launch_count():

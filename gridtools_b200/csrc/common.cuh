@@ -73,6 +73,21 @@ namespace gtb {
     void *scratch(size_t bytes);
     int set_l2_persist(int64_t bytes);
 
+    // Device-side ordering of a stencil launch against a halo exchange that runs beside it on another stream
+    // (gtb_stencil_gate, include/gtb200.h): the kernel waits until *wait_flag >= wait_value before it touches global
+    // memory and its last CTA adds 1 to *post when every CTA is done.  `cta_done` is a zeroed, self-resetting counter.
+    struct stencil_gate {
+        const unsigned long long *wait_flag = nullptr;
+        unsigned long long wait_value = 0;
+        unsigned long long *post = nullptr;
+        int *cta_done = nullptr;
+        unsigned long long *timeouts = nullptr; // device counter of waits that gave up (gtb_gate_timeouts)
+    };
+    unsigned long long *gate_timeout_counter(); // per device, zeroed once
+    // The gate armed for the next gated-capable stencil launch of this thread (consumed by it); empty otherwise.
+    stencil_gate take_gate();
+    int *gate_counter_slot(); // one of 16 rotating zeroed ints per device
+
     extern std::atomic<int64_t> g_launches;
     inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
@@ -99,7 +114,8 @@ namespace gtb {
         cfg.stream = stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = opts().pdl ? 1 : 0;
+        // not next to a concurrent exchange: the early CTAs of the NEXT launch would settle on the reserved SMs
+        attr[0].val.programmaticStreamSerializationAllowed = opts().pdl && opts().reserve_sms == 0 ? 1 : 0;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
@@ -250,6 +266,26 @@ namespace gtb {
         // lets the NEXT kernel of the stream start being scheduled as SMs free up.  Both are no-ops for a plain launch.
         __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
         __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+        __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p) {
+            unsigned long long v;
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+            return v;
+        }
+        // Spins (one thread) until *flag >= value; gives up after ~0.2 s so that a lost producer cannot hang the device,
+        // and counts that in *timeouts (the host asks with gtb_gate_timeouts).
+        __device__ __forceinline__ void gate_wait(const unsigned long long *flag, unsigned long long value,
+            unsigned long long *timeouts) {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(flag) < value) {
+                if (clock64() - t0 > 400000000ll) {
+                    if (timeouts)
+                        atomicAdd(timeouts, 1ULL);
+                    break;
+                }
+                __nanosleep(64);
+            }
+        }
 
         // Streaming global accesses with an L2 eviction policy.
         template <class T>

@@ -61,6 +61,9 @@ struct gtb_halo {
     int my_rank, max_fields, es, device;
     region send[27], recv[27];
     region border[27];      // outside region of the directions that have no neighbour (domain border)
+    const unsigned long long *gate_counter; // one-shot: the next wait_unpack launch waits for *gate_counter >= gate_value
+    unsigned long long gate_value;
+    unsigned long long *d_unpacked;         // epoch of the last completed unpack (device)
     int bc_kind;            // -1 none; GTB_BC_VALUE: unpack launches also fill the border regions with bc_bits
     uint64_t bc_bits;
     int64_t send_off[27], recv_off[27]; // byte offsets (max_fields sized slots)
@@ -94,6 +97,11 @@ namespace {
         int *error;
         long long timeout_cycles;
         int mode; // 0 none, 1 signal after pack, 2 wait before unpack
+        const unsigned long long *gate; // unpack: wait for *gate >= gate_value before scattering (stencil still reads the halos)
+        unsigned long long gate_value;
+        unsigned long long *gate_timeouts;
+        unsigned long long *unpacked;   // unpack: the last block stores the epoch here when every block is done
+        unsigned *counter2;             // block counter of that, zero between launches
     };
 
     constexpr int kMaxSeg = 26;
@@ -231,12 +239,26 @@ namespace {
     template <class E, bool PACK>
     __global__ void __launch_bounds__(kThreads) xfer_kernel(const __grid_constant__ xfer_args a) {
         __shared__ int s_last;
+        if (!PACK && a.sync.gate) { // a stencil launch on another stream may still be reading the halos
+            if (threadIdx.x == 0)
+                ptx::gate_wait(a.sync.gate, a.sync.gate_value, a.sync.gate_timeouts);
+            __syncthreads();
+        }
         if (!PACK && a.sync.mode == 2)
             move_chunks<E, false, true>(a.t, a.fields, a.s1, a.s2, a.sync, a.fill_bits);
         else
             move_chunks<E, PACK, false>(a.t, a.fields, a.s1, a.s2, a.sync, a.fill_bits);
         if (PACK && a.sync.mode == 1)
             signal_peers(a.t, a.sync, &s_last);
+        if (!PACK && a.sync.unpacked) { // publish "halos of epoch e are in place" for device-side gates
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0 && atomicAdd(a.sync.counter2, 1u) + 1u == gridDim.x) {
+                *a.sync.counter2 = 0;
+                __threadfence();
+                asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(a.sync.unpacked), "l"(a.sync.epoch) : "memory");
+            }
+        }
     }
 
     // The whole exchange in ONE launch: pack into the neighbours' receive buffers, raise their flags, then acquire
@@ -342,6 +364,11 @@ namespace {
         sy.counter = h->d_counters;
         sy.error = h->d_error;
         sy.timeout_cycles = kTimeoutCycles;
+        sy.gate = nullptr;
+        sy.gate_value = 0;
+        sy.gate_timeouts = nullptr;
+        sy.unpacked = nullptr;
+        sy.counter2 = h->d_counters + 1;
     }
 
     // Blocks of a transfer launch: at most one small block per SM (option halo.max_blocks overrides).  The first of
@@ -398,6 +425,16 @@ namespace {
                 return GTB_OK;
             b.fill_bits = h->bc_bits;
             fill_sync(b.sync, h, mode);
+            if (!PACK && sync_mode == 2) {
+                if (first && h->gate_counter) {
+                    b.sync.gate = h->gate_counter;
+                    b.sync.gate_value = h->gate_value;
+                    b.sync.gate_timeouts = gate_timeout_counter();
+                    h->gate_counter = nullptr; // one-shot
+                }
+                if (last)
+                    b.sync.unpacked = h->d_unpacked;
+            }
             b.s1 = h->d[0].total;
             b.s2 = (int64_t)h->d[0].total * h->d[1].total;
             for (int f = 0; f < nf; ++f)
@@ -488,6 +525,9 @@ GTB_API int gtb_halo_create(const gtb_halo_desc desc[3], const int neighbour_ran
     h->connected = false;
     h->epoch = 1;
     h->bc_kind = -1;
+    h->gate_counter = nullptr;
+    h->gate_value = 0;
+    h->d_unpacked = nullptr;
     h->bc_bits = 0;
     h->send_total = h->recv_total = 0;
     for (int e2 = -1; e2 <= 1; ++e2)
@@ -533,13 +573,17 @@ GTB_API int gtb_halo_create(const gtb_halo_desc desc[3], const int neighbour_ran
     if (e == cudaSuccess)
         e = cudaMemset(h->d_counters, 0, 32 * sizeof(unsigned));
     if (e == cudaSuccess)
+        e = cudaMalloc(&h->d_unpacked, sizeof(unsigned long long));
+    if (e == cudaSuccess)
+        e = cudaMemset(h->d_unpacked, 0, sizeof(unsigned long long));
+    if (e == cudaSuccess)
         e = cudaMemset(h->arena, 0, (size_t)h->arena_bytes);
     if (e == cudaSuccess)
         e = cudaMemset(h->d_error, 0, sizeof(int));
     if (e == cudaSuccess)
         e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
-        cudaFree(h->send_arena), cudaFree(h->arena), cudaFree(h->d_error), cudaFree(h->d_counters);
+        cudaFree(h->send_arena), cudaFree(h->arena), cudaFree(h->d_error), cudaFree(h->d_counters), cudaFree(h->d_unpacked);
         delete h;
         cuda_fail(e, "gtb_halo_create: buffer allocation");
         return GTB_ERR_ALLOC;
@@ -564,6 +608,7 @@ GTB_API int gtb_halo_destroy(gtb_halo *h) {
     cudaFree(h->arena);
     cudaFree(h->d_error);
     cudaFree(h->d_counters);
+    cudaFree(h->d_unpacked);
     delete h;
     return GTB_OK;
 }
@@ -764,7 +809,8 @@ GTB_API int gtb_halo_exchange(gtb_halo *h, void *const *fields, int n_fields, vo
         return st;
     if (!h->connected)
         return fail(GTB_ERR_STATE, "gtb_halo_exchange: gtb_halo_connect has not been called");
-    if (n_fields >= 1 && n_fields <= kMaxFields && opts().halo_fused) { // one launch: pack, signal, wait, unpack
+    // (the one-launch kernel takes no device-side gate and does not publish the unpacked epoch)
+    if (n_fields >= 1 && n_fields <= kMaxFields && opts().halo_fused && !h->gate_counter) { // one launch: pack, signal, wait, unpack
         char *sbufs[27], *rbufs[27];
         for (int n = 0; n < 27; ++n) {
             sbufs[n] = h->send[n].count ? peer_slot(h, n, h->epoch) : nullptr;
@@ -962,3 +1008,16 @@ GTB_API int gtb_halo_set_boundary(gtb_halo *h, int kind, double value) {
     h->bc_bits = value_bits(value, h->es);
     return GTB_OK;
 }
+
+// ------------------------------------------------------------------------------------------- device-side gates
+GTB_API void *gtb_halo_unpacked_flag(gtb_halo *h) { return h ? h->d_unpacked : nullptr; }
+
+GTB_API int gtb_halo_gate(gtb_halo *h, const void *counter, uint64_t value) {
+    if (!h)
+        return fail(GTB_ERR_ARG, "gtb_halo_gate: null handle");
+    h->gate_counter = static_cast<const unsigned long long *>(counter);
+    h->gate_value = value;
+    return GTB_OK;
+}
+
+GTB_API uint64_t gtb_halo_epoch(const gtb_halo *h) { return h ? h->epoch : 0; }

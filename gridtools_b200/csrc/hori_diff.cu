@@ -56,6 +56,7 @@ namespace {
         int ni, nj, nk;
         int tiles_i, tiles_j;
         int step_i, step_j, step_k; // gridDim.x decomposed in (tile_i, tile_j, k) digits
+        stencil_gate gate;          // device-side ordering against a concurrent halo exchange (empty: none)
     };
 
     // Position of a CTA in the flat item list (i fastest, then j, then k: CTAs that run side by side work on
@@ -224,6 +225,10 @@ namespace {
             for (int s = 0; s < STAGES; ++s)
                 ptx::mbar_init(&full[s], 1);
             ptx::fence_barrier_init();
+            if (p.gate.wait_flag) { // the halo of `in` is being unpacked by a kernel on another stream
+                ptx::gate_wait(p.gate.wait_flag, p.gate.wait_value, p.gate.timeouts);
+                ptx::fence_proxy_async_all(); // ... and is read through the async proxy (TMA) below
+            }
         }
         __syncthreads();
         item_iter it, ahead;
@@ -243,6 +248,15 @@ namespace {
             if (tid == 0 && ahead.k < p.nk) {
                 tma_issue<T>(&map_in, &map_co, smem + s * L::stage_bytes, &full[s], ahead);
                 ahead.next(p);
+            }
+        }
+        if (p.gate.post) { // tell whoever waits for this launch (the unpack of a later exchange) that it is done
+            __threadfence();
+            __syncthreads();
+            if (tid == 0 && atomicAdd(p.gate.cta_done, 1) == (int)gridDim.x - 1) {
+                *p.gate.cta_done = 0;
+                __threadfence();
+                atomicAdd(p.gate.post, 1ULL);
             }
         }
     }
@@ -332,6 +346,10 @@ namespace {
         p.step_i = grid % p.tiles_i;
         p.step_j = (grid / p.tiles_i) % p.tiles_j;
         p.step_k = (grid / p.tiles_i) / p.tiles_j;
+        p.gate = take_gate();
+        const bool gated = p.gate.wait_flag || p.gate.post;
+        if (gated && p.gate.post && !p.gate.cta_done)
+            return GTB_ERR_ALLOC;
         if (variant != 1) {
             CUtensorMap map_in, map_co;
             bool ok = make_map<T>(&map_in, p.in, p.in_sj, p.in_sk, L::lead, 2, (int64_t)L::lead + p.ni + 2, p.nj + 4,
@@ -348,6 +366,9 @@ namespace {
                 count_launch();
                 return check_launch("hd_tma_kernel");
             }
+            if (gated)
+                return fail(GTB_ERR_ARG, "gtb_hori_diff: a gate (gtb_stencil_gate) needs the default TMA kernel "
+                                         "(hd.variant 0 or 2, TMA-addressable layout)");
             if (ok) {
                 auto kernel = hd_tma_ws_kernel<T, STAGES>;
                 int st = prepare_kernel(kernel, smem);
@@ -362,6 +383,8 @@ namespace {
                     "gtb_hori_diff: hd.variant=%d (TMA) needs 16-byte aligned origins and stride_j/stride_k that "
                     "are multiples of 16 bytes", variant);
         }
+        if (gated)
+            return fail(GTB_ERR_ARG, "gtb_hori_diff: a gate (gtb_stencil_gate) needs the default TMA kernel");
         auto kernel = hd_cpasync_kernel<T, STAGES>;
         int st = prepare_kernel(kernel, smem);
         if (st)

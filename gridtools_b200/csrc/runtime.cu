@@ -236,3 +236,82 @@ GTB_API int gtb_release_scratch(void) {
 }
 
 GTB_API int64_t gtb_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------------ stencil gates
+namespace gtb {
+    namespace {
+        thread_local stencil_gate t_gate;
+        std::atomic<unsigned> g_gate_launch{0};
+    } // namespace
+
+    int *gate_counter_slot() {
+        static int *base[64] = {};
+        device_state *d = dev();
+        if (!d || d->device < 0 || d->device >= 64)
+            return nullptr;
+        if (!base[d->device]) {
+            int *q = nullptr;
+            if (cudaMalloc(&q, 64 * sizeof(int)) != cudaSuccess || cudaMemset(q, 0, 64 * sizeof(int)) != cudaSuccess) {
+                cuda_fail(cudaGetLastError(), "gate counters");
+                return nullptr;
+            }
+            base[d->device] = q;
+        }
+        return base[d->device] + (g_gate_launch.fetch_add(1, std::memory_order_relaxed) % 16);
+    }
+
+    unsigned long long *gate_timeout_counter() {
+        static unsigned long long *ctr[64] = {};
+        device_state *d = dev();
+        if (!d || d->device < 0 || d->device >= 64)
+            return nullptr;
+        if (!ctr[d->device]) {
+            unsigned long long *q = nullptr;
+            if (cudaMalloc(&q, sizeof(*q)) != cudaSuccess || cudaMemset(q, 0, sizeof(*q)) != cudaSuccess) {
+                cuda_fail(cudaGetLastError(), "gate timeout counter");
+                return nullptr;
+            }
+            ctr[d->device] = q;
+        }
+        return ctr[d->device];
+    }
+
+    stencil_gate take_gate() {
+        stencil_gate g = t_gate;
+        t_gate = stencil_gate();
+        if (g.post && !g.cta_done)
+            g.cta_done = gate_counter_slot();
+        if (g.wait_flag)
+            g.timeouts = gate_timeout_counter();
+        return g;
+    }
+} // namespace gtb
+
+GTB_API int gtb_stencil_gate(const void *wait_flag, uint64_t wait_value, void *post_counter) {
+    if (!gtb::dev())
+        return GTB_ERR_CUDA;
+    if ((wait_flag || post_counter) && gtb::opts().reserve_sms < 1)
+        return gtb::fail(GTB_ERR_STATE,
+            "gtb_stencil_gate: a gated stencil spins on the device until another kernel raises its flag; that kernel needs "
+            "SMs the stencil does not occupy -- set option reserve_sms >= 1 first");
+    gtb::t_gate.wait_flag = static_cast<const unsigned long long *>(wait_flag);
+    gtb::t_gate.wait_value = wait_value;
+    gtb::t_gate.post = static_cast<unsigned long long *>(post_counter);
+    gtb::t_gate.cta_done = nullptr;
+    return GTB_OK;
+}
+
+GTB_API int gtb_gate_timeouts(int64_t *count) {
+    if (!count)
+        return gtb::fail(GTB_ERR_ARG, "gtb_gate_timeouts: null argument");
+    if (!gtb::dev())
+        return GTB_ERR_CUDA;
+    unsigned long long *c = gtb::gate_timeout_counter();
+    if (!c)
+        return GTB_ERR_ALLOC;
+    unsigned long long v = 0;
+    GTB_CUDA(cudaDeviceSynchronize());
+    GTB_CUDA(cudaMemcpy(&v, c, sizeof(v), cudaMemcpyDeviceToHost));
+    *count = (int64_t)v;
+    return GTB_OK;
+}

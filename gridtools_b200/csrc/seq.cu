@@ -15,7 +15,7 @@
 using namespace gtb;
 
 namespace {
-    enum op_kind { OP_HD64, OP_HD32, OP_VA64, OP_VA32, OP_TRACERS, OP_HALO, OP_RECORD, OP_WAIT };
+    enum op_kind { OP_HD64, OP_HD32, OP_VA64, OP_VA32, OP_TRACERS, OP_HALO, OP_RECORD, OP_WAIT, OP_SGATE, OP_HGATE };
 
     struct op {
         op_kind kind;
@@ -27,6 +27,9 @@ namespace {
         std::vector<void *> ptrs;
         std::vector<gtb_field> outs, ins; // prepare_tracers
         int event;
+        const void *gate_flag;
+        uint64_t gate_value;
+        void *gate_post;
     };
 } // namespace
 
@@ -124,6 +127,27 @@ GTB_API int gtb_seq_add_halo_exchange(gtb_seq *s, gtb_halo *h, void *const *fiel
     return GTB_OK;
 }
 
+GTB_API int gtb_seq_add_stencil_gate(gtb_seq *s, const void *wait_flag, uint64_t wait_value, void *post_counter) {
+    if (!s)
+        return fail(GTB_ERR_ARG, "gtb_seq_add_stencil_gate: null sequence");
+    op o{};
+    o.kind = OP_SGATE;
+    o.gate_flag = wait_flag, o.gate_value = wait_value, o.gate_post = post_counter;
+    s->ops.push_back(o);
+    return GTB_OK;
+}
+
+GTB_API int gtb_seq_add_halo_gate(gtb_seq *s, gtb_halo *h, const void *counter, uint64_t value) {
+    if (!s || !h)
+        return fail(GTB_ERR_ARG, "gtb_seq_add_halo_gate: null argument");
+    op o{};
+    o.kind = OP_HGATE;
+    o.halo = h;
+    o.gate_flag = counter, o.gate_value = value;
+    s->ops.push_back(o);
+    return GTB_OK;
+}
+
 GTB_API int gtb_seq_add_record(gtb_seq *s, int event, void *stream) {
     if (!s)
         return fail(GTB_ERR_ARG, "gtb_seq_add_record: null sequence");
@@ -180,6 +204,12 @@ GTB_API int gtb_seq_run(gtb_seq *s, int first, int count) {
             break;
         case OP_HALO:
             st = gtb_halo_exchange(o.halo, o.ptrs.data(), (int)o.ptrs.size(), o.stream);
+            break;
+        case OP_SGATE:
+            st = gtb_stencil_gate(o.gate_flag, o.gate_value, o.gate_post);
+            break;
+        case OP_HGATE:
+            st = gtb_halo_gate(o.halo, o.gate_flag, o.gate_value);
             break;
         case OP_RECORD:
             GTB_CUDA(cudaEventRecord(s->events[o.event], as_stream(o.stream)));

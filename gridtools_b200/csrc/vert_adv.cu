@@ -55,6 +55,7 @@ namespace {
         int stagger_ns; // TMEM variant: warp w of a CTA starts w * stagger_ns late (de-phases forward and backward sweeps)
         int *tickets;   // TMEM variants: {next strip, finished warps}, self-resetting; one of 16 slots per launch
         long long *trace; // diagnosis only (va.debug & 128): time stamps per warp pair
+        stencil_gate gate; // device-side ordering against a concurrent halo exchange (paired-warp kernel only)
     };
 
     template <class T, bool Hints>
@@ -1723,6 +1724,13 @@ namespace {
         tm::fence_after();
         ptx::pdl_launch_dependents(); // the next kernel of the stream may be scheduled as this one's CTAs retire
         ptx::pdl_wait();              // set-up above ran under the previous kernel's tail; its data is visible from here
+        if (p.gate.wait_flag) { // the halo of wcon is being unpacked by a kernel on another stream
+            if (threadIdx.x == 0) {
+                ptx::gate_wait(p.gate.wait_flag, p.gate.wait_value, p.gate.timeouts);
+                ptx::fence_proxy_async_all();
+            }
+            __syncthreads();
+        }
         const uint32_t tbase = *tslot;
         const uint32_t tw = tbase + ((uint32_t)((pw & 3) * 32) << 16) + (uint32_t)((pw >> 2) * 256);
 
@@ -1994,10 +2002,15 @@ namespace {
             }
         }
         __syncthreads();
-        if (threadIdx.x == 0 && atomicAdd(p.tickets + 1, 1) == (int)gridDim.x - 1) { // every F warp has drawn its last ticket
-            p.tickets[0] = 0;
-            p.tickets[1] = 0;
+        if (threadIdx.x == 0) {
             __threadfence();
+            if (atomicAdd(p.tickets + 1, 1) == (int)gridDim.x - 1) { // every F warp has drawn its last ticket
+                p.tickets[0] = 0;
+                p.tickets[1] = 0;
+                __threadfence();
+                if (p.gate.post)
+                    atomicAdd(p.gate.post, 1ULL); // the launch is done: a later unpack may overwrite the halos it read
+            }
         }
         tm::fence_before();
         __syncthreads();
@@ -2494,6 +2507,8 @@ namespace {
         int grid = o.va_ctas_per_sm < 0 ? -o.va_ctas_per_sm : wps * stencil_sms(d);
         if (grid > strips)
             grid = (int)strips;
+        if (!tmem && (p.gate.wait_flag || p.gate.post))
+            return fail(GTB_ERR_ARG, "gtb_vert_adv: a gate needs the paired-warp kernel");
         if (tmem) {
             int st = tm_variant == 7 ? vert_adv_pair<T>(p, o, d, maps, stream)
                                      : (tm_variant == 6 ? vert_adv_fused<T>(p, o, d, maps, stream)
@@ -2502,6 +2517,8 @@ namespace {
                 *done = true;
                 return st;
             }
+            if (p.gate.wait_flag || p.gate.post)
+                return fail(GTB_ERR_ARG, "gtb_vert_adv: a gate needs the paired-warp kernel, which cannot hold nk = %d levels", p.nk);
         }
         if (resident) {
             p.scratch = nullptr;
@@ -2606,6 +2623,9 @@ namespace {
         p.tiles_i = ceil_div(ni, 32);
         if ((int64_t)p.tiles_i * nj >= (int64_t)1 << 31)
             return fail(GTB_ERR_ARG, "gtb_vert_adv: domain too large");
+        p.gate = take_gate();
+        if ((p.gate.wait_flag || p.gate.post) && !(sizeof(T) == 8 && (o.va_variant == 0 || o.va_variant == 7)))
+            return fail(GTB_ERR_ARG, "gtb_vert_adv: a gate (gtb_stencil_gate) needs the paired-warp fp64 kernel (va.variant 0 or 7)");
         if (o.va_variant != 1) { // 0 auto / 2: TMA-streamed persistent warps
             bool done = false;
             int st = vert_adv_tma<T>(p, o, d, as_stream(stream), &done);

@@ -331,6 +331,14 @@ class halo_exchange_dynamic_ut:
         _lib.check(fn(self._h, arr, n, self._stream()))
         _lib.check(_lib.lib().gtb_halo_next_epoch(self._h))
 
+    def unpacked_flag(self):
+        """Device address of the uint64 holding the epoch of the last completed unpack (gtb_halo_unpacked_flag)."""
+        return _lib.lib().gtb_halo_unpacked_flag(self._h)
+
+    def epoch(self):
+        """Epoch number the next exchange of this object carries (1, 2, ...)."""
+        return int(_lib.lib().gtb_halo_epoch(self._h))
+
     def set_boundary(self, value):
         """distributed_boundaries.hpp:141-200 with value_boundary and proc_grid_predicate: from now on every unpack /
         exchange of this object also writes `value` into the halo regions that face no neighbour, in the same launch.

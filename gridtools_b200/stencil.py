@@ -216,6 +216,15 @@ class Sequence:
         _lib.check(_lib.lib().gtb_seq_add_halo_exchange(self._h, he._h, arr, n, stream))
         self._keep.append((he, fields))
 
+    def stencil_gate(self, wait_flag=None, wait_value=0, post_counter=None):
+        """Device-side gate for the stencil recorded next (gtb_stencil_gate): wait until *wait_flag >= wait_value, add 1
+        to *post_counter when done.  Pointers are raw device addresses (ints) or None."""
+        _lib.check(_lib.lib().gtb_seq_add_stencil_gate(self._h, wait_flag, int(wait_value), post_counter))
+
+    def halo_gate(self, he, counter, value):
+        """The unpack of the exchange recorded next waits on the device until *counter >= value (gtb_halo_gate)."""
+        _lib.check(_lib.lib().gtb_seq_add_halo_gate(self._h, he._h, counter, int(value)))
+
     def record(self, event, stream=None):
         _lib.check(_lib.lib().gtb_seq_add_record(self._h, int(event), stream))
 

@@ -213,6 +213,32 @@ int gtb_boundary_apply(const gtb_halo_desc desc[3], const int direction_mask[27]
  * kind = GTB_BC_VALUE, or -1 to switch it off again. */
 int gtb_halo_set_boundary(gtb_halo *h, int kind, double value);
 
+/* ------------------------------------------------------------------------------------------ device-side gates
+ * A halo exchange that runs on its own stream beside the stencils has to be ordered against them twice per step: the
+ * stencil must not read a halo before it is unpacked, and the unpack of a later exchange must not overwrite a halo a
+ * stencil launch is still reading.  Stream events do that (and the reference's host-synchronous exchange does it by
+ * blocking), but an event record plus a cross-stream wait around every launch cost ~5 us of a 25-60 us step.  These
+ * calls move both orderings onto the device:
+ *   gtb_halo_unpacked_flag(h)         device address of a uint64 that holds the epoch (1, 2, ...: one per exchange,
+ *                                     gtb_halo_epoch(h) is the epoch the NEXT exchange will carry) of the last
+ *                                     completed wait_unpack of this handle;
+ *   gtb_stencil_gate(flag, v, post)   one-shot, for the next gtb_hori_diff_* / gtb_vert_adv_f64 launch of the calling
+ *                                     thread: the kernel waits on the device until *flag >= v before it reads global
+ *                                     memory (flag = NULL: no wait) and adds 1 to the uint64 *post when all of it is
+ *                                     done (post = NULL: nothing).  Needs option "reserve_sms" >= 1: the kernel that
+ *                                     raises the flag must find SMs the spinning stencil does not occupy
+ *                                     (GTB_ERR_STATE otherwise).  Only the default kernels take a gate (GTB_ERR_ARG);
+ *   gtb_halo_gate(h, counter, v)      one-shot, for the next wait_unpack / exchange of h: the unpack waits on the
+ *                                     device until *counter >= v (typically `post` of the stencil launch that last
+ *                                     read these halos) before it scatters.
+ * A wait gives up after ~0.2 s instead of hanging the device; gtb_gate_timeouts() synchronises the device and reports
+ * how many waits did so far (0 in a correct program). */
+void *gtb_halo_unpacked_flag(gtb_halo *h);
+uint64_t gtb_halo_epoch(const gtb_halo *h);
+int gtb_stencil_gate(const void *wait_flag, uint64_t wait_value, void *post_counter);
+int gtb_halo_gate(gtb_halo *h, const void *counter, uint64_t value);
+int gtb_gate_timeouts(int64_t *count);
+
 /* ------------------------------------------------------------------------------------- recorded call sequences
  * The reference's user programs drive their time loop from C++ (tests/regression/gcl/copy_stencil_parallel.cpp:126-145:
  * he.pack / he.exchange / he.unpack followed by run(spec, backend, grid, fields...)), a microsecond or two of host
@@ -235,6 +261,9 @@ int gtb_seq_add_vert_adv(gtb_seq *s, int elem_size, const gtb_field *utens_stage
 int gtb_seq_add_prepare_tracers(gtb_seq *s, const gtb_field *out, const gtb_field *in, int n_tracers,
     const gtb_field *rho, int ni, int nj, int nk, void *stream);
 int gtb_seq_add_halo_exchange(gtb_seq *s, gtb_halo *h, void *const *fields, int n_fields, void *stream);
+/* gtb_stencil_gate / gtb_halo_gate for the operation recorded NEXT (armed when the sequence reaches them) */
+int gtb_seq_add_stencil_gate(gtb_seq *s, const void *wait_flag, uint64_t wait_value, void *post_counter);
+int gtb_seq_add_halo_gate(gtb_seq *s, gtb_halo *h, const void *counter, uint64_t value);
 int gtb_seq_add_record(gtb_seq *s, int event, void *stream);
 int gtb_seq_add_wait(gtb_seq *s, void *stream, int event);
 /* Issues operations [first, first + count) of the sequence. */

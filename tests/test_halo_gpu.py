@@ -143,3 +143,62 @@ def test_bound_exchange_single_call(gt, oracle):
     for f in range(n_fields):
         assert np.array_equal(fields[f], dev[f].cpu().numpy())
     he.close()
+
+
+def test_device_side_gates_order_stencil_and_exchange(gt):
+    """gtb_stencil_gate / gtb_halo_gate: a periodic rank that is its own neighbour runs `exchange -> hori_diff` steps on two
+    streams with no stream events; every step must see the halos of ITS exchange (the field is rewritten in between)."""
+    import ctypes as C
+    from gridtools_b200 import stencil
+    torch = gt.torch
+    ni, nj, nk, H = 64, 32, 4, 2
+    per = (True, True, False)
+    grid = gt.gcl.ProcGrid((1, 1, 1), per, 0)
+    he = gt.gcl.halo_exchange_dynamic_ut(per, grid, np.float64, comm=None, transport="p2p")
+    rng = np.random.default_rng(12)
+    box = rng.standard_normal((nk, nj + 2 * H, ni + 2 * H))
+    inp = gt.storage.from_numpy(box, (H, H, 0))
+    coeff = gt.storage.from_numpy(np.full_like(box, 0.025), (H, H, 0))
+    outs = [gt.storage.from_numpy(np.zeros_like(box), (H, H, 0)) for _ in range(3)]
+    p0 = inp.padded_lengths[0]
+    he.add_halo(0, H, H, H, H + ni - 1, p0)
+    he.add_halo(1, H, H, H, H + nj - 1, nj + 2 * H)
+    he.add_halo(2, 0, 0, 0, nk - 1, nk)
+    he.setup(1)
+    he._connect([he.blob])
+    for f in [inp, coeff] + outs:
+        f.const_target_tensor()
+    gt.lib.set_option("reserve_sms", 4)
+    try:
+        comp, comm = torch.cuda.Stream(), torch.cuda.Stream(priority=-1)
+        comp_h, comm_h = C.c_void_p(comp.cuda_stream), C.c_void_p(comm.cuda_stream)
+        done = torch.zeros(1, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        flag, e0 = he.unpacked_flag(), he.epoch()
+        seq = stencil.Sequence()
+        steps = 3
+        for t in range(steps):
+            if t >= 1:
+                seq.halo_gate(he, done.data_ptr(), t)  # the previous stencil has read the halos
+            seq.halo_exchange(he, [inp], comm_h)
+            seq.stencil_gate(flag, e0 + t, done.data_ptr())
+            seq.horizontal_diffusion(inp, coeff, outs[t], stream=comp_h)
+        seq.run()
+        torch.cuda.synchronize()
+        assert he.check() == 0 and int(done.item()) == steps and gt.lib.gate_timeouts() == 0
+        # expected: periodic halo fill, then the stencil (the field itself never changes)
+        from oracle import pyoracle as o
+        want_in = box.copy()
+        o.halo_exchange_all([(H, H, H, H + ni - 1, ni + 2 * H), (H, H, H, H + nj - 1, nj + 2 * H), (0, 0, 0, nk - 1, nk)],
+                            (1, 1, 1), per, [[want_in]], 8)
+        want = o.hori_diff(want_in, np.full_like(box, 0.025))
+        inner = (slice(None), slice(H, -H), slice(H, -H))
+        for t in range(steps):
+            outs[t]._host_stale = True
+            assert np.array_equal(outs[t].to_numpy()[inner], want[inner]), t
+        with pytest.raises(gt.lib.GtbError):  # a gate without reserved SMs could deadlock: refused
+            gt.lib.set_option("reserve_sms", 0)
+            gt.lib.check(gt.lib.lib().gtb_stencil_gate(flag, 1, None))
+    finally:
+        gt.lib.set_option("reserve_sms", 0)
+        he.close()
