@@ -422,6 +422,123 @@ class NumpyCodec:
         plan.unpack_numpy(n, fields, msg)
 
 
+class field_on_the_fly:
+    """gcl::field_on_the_fly<T, layout, traits>(ptr, halos) (gcl/high_level/field_on_the_fly.hpp:27-95): a field together
+    with ITS OWN three halo descriptors (minus, plus, begin, end, total) in increasing-stride order."""
+
+    def __init__(self, field, halos, dtype=None):
+        self.field = field
+        self.halos = tuple(tuple(int(x) for x in h) for h in halos)
+        if len(self.halos) != 3 or any(len(h) != 5 for h in self.halos):
+            raise ValueError("field_on_the_fly needs three (minus, plus, begin, end, total) descriptors")
+        self.dtype = np.dtype(dtype if dtype is not None else getattr(field, "dtype", np.float64))
+
+    def signature(self):
+        return (self.halos, self.dtype.str)
+
+
+class halo_exchange_generic:
+    """gcl::halo_exchange_generic<ProcLayout, Arch> (gcl/halo_exchange.hpp:334-470): every field brings its own halo
+    descriptors, so fields of different sizes, halo widths and element types travel in one pack / exchange / unpack.
+
+        hg = halo_exchange_generic(periodicity, grid, comm=TorchComm())
+        hg.setup(max_fields)
+        hg.pack(field_on_the_fly(a, halos_a), field_on_the_fly(b, halos_b)); hg.exchange(); hg.unpack(...)
+
+    The reference concatenates all fields into one message per neighbour (descriptor_generic_manual.hpp:370-796).  Here
+    the fields are grouped by (halo descriptors, element type); every group is one halo_exchange_dynamic_ut of this
+    package -- created at the first pack() that shows the group, which is a collective call like setup() itself, so
+    all ranks must present the same groups in the same order (they do in an SPMD program: message sizes have to agree
+    in the reference as well).  A pack() is one fused pack + NVLink store launch per group, an unpack() one wait +
+    scatter launch per group."""
+
+    def __init__(self, periodicity, grid: ProcGrid, comm=None, transport="p2p", proc_layout=(0, 1, 2), codec=None):
+        self.periodicity, self.grid, self.comm, self.transport = tuple(periodicity), grid, comm, transport
+        self.proc_layout, self.codec = tuple(proc_layout), codec
+        self.max_fields = None
+        self._groups = {}   # signature -> halo_exchange_dynamic_ut
+        self._order = []    # signatures in creation order
+        self._last = []     # [(exchanger, [fields])] of the current pack
+        self.pending = []   # exchangers created by prepare() that still need connect_local (in-process ranks)
+
+    def setup(self, max_fields, halo_example=None, typesize=8):
+        """setup(max_fields_n, halo_example, typesize) (:389-393); the example and type size of the reference size its
+        buffers, here every group sizes its own."""
+        self.max_fields = int(max_fields)
+
+    def _exchanger(self, fotf):
+        sig = fotf.signature()
+        he = self._groups.get(sig)
+        if he is None:
+            if self.max_fields is None:
+                raise RuntimeError("pack() called before setup()")
+            he = halo_exchange_dynamic_ut(self.periodicity, self.grid, fotf.dtype, proc_layout=self.proc_layout,
+                                          comm=self.comm, transport=self.transport, codec=self.codec)
+            for d in range(3):
+                he.add_halo(d, *fotf.halos[d])
+            he.setup(self.max_fields)
+            if self.comm is None and self.transport != "host":
+                self.pending.append(he)
+            self._groups[sig] = he
+            self._order.append(sig)
+        return he
+
+    def prepare(self, *fields):
+        """Creates the exchange objects for the groups these fields form (collective).  Only needed when several ranks
+        live in one process (comm=None): call it on every rank, then connect_local_generic([...])."""
+        for f in fields:
+            self._exchanger(f)
+
+    def _grouped(self, fields):
+        if len(fields) == 1 and isinstance(fields[0], (list, tuple)):
+            fields = fields[0]  # pack(std::vector<field_on_the_fly>) overload (:421-424)
+        by_sig = {}
+        for f in fields:
+            self._exchanger(f)
+            by_sig.setdefault(f.signature(), []).append(f.field)
+        return [(self._groups[sig], by_sig[sig]) for sig in self._order if sig in by_sig]
+
+    def pack(self, *fields):
+        self._last = self._grouped(fields)
+        for he, fs in self._last:
+            he.pack(fs)
+
+    def exchange(self):
+        for he, _ in self._last:
+            he.exchange()
+
+    def start_exchange(self):
+        for he, _ in self._last:
+            he.start_exchange()
+
+    def wait(self):
+        for he, _ in self._last:
+            he.wait()
+
+    def unpack(self, *fields):
+        for he, fs in self._grouped(fields):
+            he.unpack(fs)
+
+    def check(self):
+        return max([he.check() for he in self._groups.values()] + [0])
+
+    def close(self):
+        for he in self._groups.values():
+            he.close()
+        self._groups.clear()
+
+
+def connect_local_generic(exchangers):
+    """In-process ranks of halo_exchange_generic objects: connects the groups created by prepare(), group by group."""
+    n = len(exchangers[0].pending)
+    if any(len(hg.pending) != n for hg in exchangers):
+        raise RuntimeError("the ranks prepared different numbers of groups")
+    for g in range(n):
+        connect_local([hg.pending[g] for hg in exchangers])
+    for hg in exchangers:
+        hg.pending = []
+
+
 def connect_local(exchangers):
     """Several ranks inside ONE process (tests on a single GPU): export all, then connect all."""
     for he in exchangers:

@@ -13,7 +13,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from gridtools_b200.gcl import HaloPlan, NumpyCodec, ProcGrid, TorchComm, dir_of, halo_exchange_dynamic_ut
+from gridtools_b200.gcl import (HaloPlan, NumpyCodec, ProcGrid, TorchComm, dir_of, field_on_the_fly,
+                                halo_exchange_dynamic_ut, halo_exchange_generic)
 
 
 @pytest.mark.parametrize("dims", [(1, 1, 1), (2, 1, 1), (2, 2, 1), (2, 4, 1), (3, 2, 2)])
@@ -122,3 +123,48 @@ def test_gloo_exchange_matches_oracle(oracle, tmp_path, dims, periodic):
         assert np.array_equal(got, np.stack(expect[r])), "rank %d differs from the oracle" % r
     if not any(periodic):
         assert (np.stack(expect[0]) == -1).any()  # non-periodic borders keep their -1 (test_halo_exchange_3D.cpp:106-123)
+
+
+# ------------------------------------------------------------------------------------------- halo_exchange_generic
+HALOS_B = [(1, 1, 1, 7, 9), (2, 2, 2, 9, 12), (0, 0, 0, 2, 3)]  # a second field shape with its own halos
+
+
+def _stamp_h(halos, grid, field_id):
+    return stamp(HaloPlan(halos, grid), grid, field_id)
+
+
+def _generic_worker(rank, size, port, dims, periodic, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        grid = ProcGrid(dims, periodic, rank)
+        hg = halo_exchange_generic(periodic, grid, comm=TorchComm(), transport="host", codec=NumpyCodec)
+        hg.setup(4)
+        a = [_stamp_h(HALOS, grid, f) for f in range(2)]
+        b = [_stamp_h(HALOS_B, grid, 7)]
+        fields = [field_on_the_fly(a[0], HALOS), field_on_the_fly(b[0], HALOS_B), field_on_the_fly(a[1], HALOS)]
+        hg.pack(*fields)
+        hg.exchange()
+        hg.unpack(*fields)
+        np.savez(os.path.join(out_dir, "rank%d.npz" % rank), a=np.stack(a), b=np.stack(b))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dims,periodic", [((2, 1, 1), (1, 0, 0)), ((2, 2, 1), (1, 1, 0))])
+def test_gloo_generic_exchange_matches_oracle(oracle, tmp_path, dims, periodic):
+    """Fields with different sizes and halos in one pack / exchange / unpack: each group must equal the oracle's
+    exchange of that group alone."""
+    size = dims[0] * dims[1] * dims[2]
+    expect_a, expect_b = [], []
+    for r in range(size):
+        g = ProcGrid(dims, periodic, r)
+        expect_a.append([_stamp_h(HALOS, g, f) for f in range(2)])
+        expect_b.append([_stamp_h(HALOS_B, g, 7)])
+    oracle.halo_exchange_all(HALOS, dims, periodic, expect_a, 8)
+    oracle.halo_exchange_all(HALOS_B, dims, periodic, expect_b, 8)
+    mp.spawn(_generic_worker, args=(size, _free_port(), dims, periodic, str(tmp_path)), nprocs=size, join=True)
+    for r in range(size):
+        got = np.load(tmp_path / ("rank%d.npz" % r))
+        assert np.array_equal(got["a"], np.stack(expect_a[r])) and np.array_equal(got["b"], np.stack(expect_b[r])), r

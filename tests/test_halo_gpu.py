@@ -202,3 +202,42 @@ def test_device_side_gates_order_stencil_and_exchange(gt):
     finally:
         gt.lib.set_option("reserve_sms", 0)
         he.close()
+
+
+def test_generic_exchange_two_field_shapes(gt, oracle):
+    """halo_exchange_generic on the device: two field shapes with their own halo descriptors (and element types) in one
+    pack / exchange / unpack, 2x2 ranks in this process."""
+    HB = [(1, 1, 1, 7, 9), (2, 2, 2, 9, 12), (0, 0, 0, 2, 3)]
+    dims, periodic = (2, 2, 1), (True, False, False)
+    size = 4
+    hgs, host, dev = [], [], []
+    for r in range(size):
+        grid = gt.gcl.ProcGrid(dims, periodic, r)
+        hg = gt.gcl.halo_exchange_generic(periodic, grid, comm=None, transport="p2p")
+        hg.setup(3)
+        pa, pb = gt.gcl.HaloPlan(HALOS, grid), gt.gcl.HaloPlan(HB, grid)
+        a = [stamp(pa, grid, f, np.float64) for f in range(2)]
+        b = [stamp(pb, grid, 5, np.float32)]
+        da = [gt.torch.from_numpy(x.copy()).cuda() for x in a]
+        db = [gt.torch.from_numpy(x.copy()).cuda() for x in b]
+        fo = [gt.gcl.field_on_the_fly(da[0].data_ptr(), HALOS, np.float64), gt.gcl.field_on_the_fly(db[0].data_ptr(), HB, np.float32),
+              gt.gcl.field_on_the_fly(da[1].data_ptr(), HALOS, np.float64)]
+        hg.prepare(*fo)
+        hgs.append(hg), host.append((a, b)), dev.append((da, db, fo))
+    gt.gcl.connect_local_generic(hgs)
+    for hg, (_, _, fo) in zip(hgs, dev):
+        hg.pack(*fo)
+    for hg, (_, _, fo) in zip(hgs, dev):
+        hg.exchange()
+        hg.unpack(*fo)
+    gt.torch.cuda.synchronize()
+    ea, eb = [[x.copy() for x in h[0]] for h in host], [[x.copy() for x in h[1]] for h in host]
+    oracle.halo_exchange_all(HALOS, dims, periodic, ea, 8)
+    oracle.halo_exchange_all(HB, dims, periodic, eb, 4)
+    for r in range(size):
+        assert hgs[r].check() == 0
+        for t, w in zip(dev[r][0], ea[r]):
+            assert np.array_equal(t.cpu().numpy(), w), r
+        assert np.array_equal(dev[r][1][0].cpu().numpy(), eb[r][0]), r
+    for hg in hgs:
+        hg.close()
