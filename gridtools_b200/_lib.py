@@ -46,6 +46,8 @@ _SIG = {
     "gtb_get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
     "gtb_release_scratch": (C.c_int, []),
     "gtb_launch_count": (C.c_int64, []),
+    "gtb_copy_box_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p]),
     "gtb_debug_trace": (C.c_int, [C.c_void_p, C.c_int64]),
     "gtb_copy": (C.c_int, [_FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gtb_hori_diff_f64": (C.c_int, [_FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_void_p]),

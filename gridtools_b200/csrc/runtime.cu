@@ -315,3 +315,39 @@ GTB_API int gtb_gate_timeouts(int64_t *count) {
     *count = (int64_t)v;
     return GTB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ box copies
+// Host <-> device copy of a sub-box of a 3-d field (i contiguous) on a stream: what storage::gpu's update_target /
+// update_host (storage/gpu.hpp:86-99: one blocking cudaMemcpy of the whole padded allocation) would move if it only
+// moved the points a stencil reads or writes.  `host` must be pinned for the copy to be asynchronous.
+GTB_API int gtb_copy_box_async(void *device_origin, void *host_origin, int elem_size, int64_t stride_j, int64_t stride_k,
+    int ni, int nj, int nk, int to_device, void *stream) {
+    if (!device_origin || !host_origin || (elem_size != 4 && elem_size != 8) || ni < 0 || nj < 0 || nk < 0 ||
+        stride_j < ni || stride_k < stride_j * nj)
+        return gtb::fail(GTB_ERR_ARG, "gtb_copy_box_async: bad argument");
+    if (!gtb::dev())
+        return GTB_ERR_CUDA;
+    if (ni == 0 || nj == 0 || nk == 0)
+        return GTB_OK;
+    if (stride_k % stride_j != 0) // cudaMemcpy3D needs whole rows per slice: fall back to one 2-d copy per level
+    {
+        for (int k = 0; k < nk; ++k) {
+            char *d = static_cast<char *>(device_origin) + (size_t)k * stride_k * elem_size;
+            char *h = static_cast<char *>(host_origin) + (size_t)k * stride_k * elem_size;
+            GTB_CUDA(cudaMemcpy2DAsync(to_device ? d : h, (size_t)stride_j * elem_size, to_device ? h : d,
+                (size_t)stride_j * elem_size, (size_t)ni * elem_size, (size_t)nj,
+                to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, gtb::as_stream(stream)));
+        }
+        return GTB_OK;
+    }
+    cudaMemcpy3DParms prm = {};
+    const size_t pitch = (size_t)stride_j * elem_size, rows = (size_t)(stride_k / stride_j);
+    cudaPitchedPtr dp = make_cudaPitchedPtr(device_origin, pitch, pitch, rows);
+    cudaPitchedPtr hp = make_cudaPitchedPtr(host_origin, pitch, pitch, rows);
+    prm.srcPtr = to_device ? hp : dp;
+    prm.dstPtr = to_device ? dp : hp;
+    prm.extent = make_cudaExtent((size_t)ni * elem_size, (size_t)nj, (size_t)nk);
+    prm.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    GTB_CUDA(cudaMemcpy3DAsync(&prm, gtb::as_stream(stream)));
+    return GTB_OK;
+}

@@ -104,6 +104,29 @@ class DataStore:
         self._host_t.copy_(self._dev, non_blocking=True)
         self._host_stale = False
 
+    def _box_copy(self, lo, hi, to_device):
+        """Sub-box [lo, hi) (storage coordinates i, j, k) between the pinned host mirror and the device on torch's
+        current stream (gtb_copy_box_async)."""
+        import ctypes as C
+        isz = self.dtype.itemsize
+        off = sum(o * s for o, s in zip(lo, self.strides)) * isz
+        n = [h - o for o, h in zip(lo, hi)]
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.lib().gtb_copy_box_async(self._base + off, self._host_t.data_ptr() + off, isz, self.strides[1],
+                                                 self.strides[2], n[0], n[1], n[2], int(to_device), stream))
+        return n[0] * n[1] * n[2] * isz
+
+    def update_target_box_async(self, lo, hi):
+        """Host -> device of the sub-box only (e.g. the compute domain plus the halo a stencil reads)."""
+        nbytes = self._box_copy(lo, hi, True)
+        self._dev_stale = False
+        return nbytes
+
+    def update_host_box_async(self, lo, hi):
+        nbytes = self._box_copy(lo, hi, False)
+        self._host_stale = False
+        return nbytes
+
     @property
     def nbytes_host(self):
         return self.length * self.dtype.itemsize

@@ -74,6 +74,12 @@ int gtb_release_scratch(void);
  * per warp pair ([pair][32] int64: [0] start, forward pass p [1+4p] begin / [2+4p] end, backward pass p [3+4p] / [4+4p]);
  * this synchronises the device, copies up to `bytes` of them to `dst` (host) and clears them. */
 int gtb_debug_trace(void *dst, int64_t bytes);
+/* Host <-> device copy of the ni x nj x nk sub-box that starts at the given origins (same element strides on both sides,
+ * i contiguous) on `stream`: storage::gpu's update_target / update_host (storage/gpu.hpp:86-99, one blocking cudaMemcpy of
+ * the whole padded allocation) restricted to the points a stencil reads or writes.  Asynchronous when the host memory is
+ * pinned.  to_device != 0: host -> device. */
+int gtb_copy_box_async(void *device_origin, void *host_origin, int elem_size, int64_t stride_j, int64_t stride_k, int ni,
+    int nj, int nk, int to_device, void *stream);
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t gtb_launch_count(void);
 

@@ -503,3 +503,29 @@ def test_vert_adv_concurrent_streams(gt, oracle):
             want = oracle.vert_adv(want, *arrs[1:], 0.15)
         st[0]._host_stale = True
         assert np.array_equal(st[0].to_numpy()[inner], want[inner])
+
+
+def test_box_copies_between_host_mirror_and_device(gt):
+    """gtb_copy_box_async through DataStore.update_{target,host}_box_async: only the box moves, in both directions."""
+    rng = np.random.default_rng(3)
+    for dtype in (np.float64, np.float32):
+        box = rng.standard_normal((5, 13, 37)).astype(dtype)
+        ds = gt.storage.from_numpy(np.zeros_like(box), (3, 3, 0))
+        ds.const_target_tensor()                      # device = zeros
+        ds.host_view()[...] = box                     # host = data, device stale
+        lo, hi = (3, 2, 1), (30, 11, 4)
+        n = ds.update_target_box_async(lo, hi)
+        gt.torch.cuda.synchronize()
+        assert n == 27 * 9 * 3 * np.dtype(dtype).itemsize
+        dev = ds.const_target_tensor().cpu().numpy()[:, :, :37]
+        want = np.zeros_like(box)
+        want[1:4, 2:11, 3:30] = box[1:4, 2:11, 3:30]
+        assert np.array_equal(dev, want)
+        ds.target_tensor().mul_(2)                    # device = 2 * box inside the box
+        ds._host_np[...] = -1
+        ds.update_host_box_async((4, 3, 2), (20, 9, 3))
+        gt.torch.cuda.synchronize()
+        got = ds._host_np[:, :, :37]
+        want = -np.ones_like(box)
+        want[2:3, 3:9, 4:20] = 2 * box[2:3, 3:9, 4:20]
+        assert np.array_equal(got, want)
