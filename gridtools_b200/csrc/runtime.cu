@@ -246,6 +246,8 @@ namespace gtb {
 
     int *gate_counter_slot() {
         static int *base[64] = {};
+        static std::mutex mtx;
+        std::lock_guard<std::mutex> lock(mtx);
         device_state *d = dev();
         if (!d || d->device < 0 || d->device >= 64)
             return nullptr;
@@ -262,6 +264,8 @@ namespace gtb {
 
     unsigned long long *gate_timeout_counter() {
         static unsigned long long *ctr[64] = {};
+        static std::mutex mtx;
+        std::lock_guard<std::mutex> lock(mtx);
         device_state *d = dev();
         if (!d || d->device < 0 || d->device >= 64)
             return nullptr;

@@ -25,6 +25,8 @@
 #include "common.cuh"
 #include "tma.cuh"
 
+#include <mutex>
+
 using namespace gtb;
 
 namespace {
@@ -2295,6 +2297,8 @@ namespace {
     }
     int *va_ticket_base() {
         static int *ctr[64] = {};
+        static std::mutex mtx; // first use may come from several host threads
+        std::lock_guard<std::mutex> lock(mtx);
         const int d = dev()->device;
         if (d < 0 || d >= 64)
             return nullptr;
