@@ -17,6 +17,11 @@
 #include <gridtools/storage/gpu.hpp>
 #include <gridtools/storage/sid.hpp>
 
+#include <gridtools/boundaries/boundary.hpp>
+#include <gridtools/boundaries/copy.hpp>
+#include <gridtools/boundaries/value.hpp>
+
+#include <gtb200/boundaries/boundary.hpp>
 #include <gtb200/stencil/b200.hpp>
 
 #include "functors.hpp"
@@ -184,6 +189,57 @@ namespace {
         verify(name.c_str(), got, ref, d0, d1, nk, H, sizeof(T) == 8 ? 1e-12 : 1e-4);
     }
 
+    // boundaries/boundary.hpp:57-72: the reference's boundary<..., gcl::cpu>::apply on cpu_ifirst stores against
+    // gtb200::boundaries::boundary on storage::gpu stores (raw target pointers), whole storages compared bit for bit.
+    struct all_predicate { // both call forms: the reference passes a direction type, gtb200 three ints
+        template <class D>
+        bool operator()(D) const {
+            return true;
+        }
+        bool operator()(int, int, int) const { return true; }
+    };
+    struct i_minus_predicate { // applies the condition only on the directions that point towards -i
+        template <class D>
+        bool operator()(D) const {
+            return D::i == gt::boundaries::minus_;
+        }
+        bool operator()(int ei, int, int) const { return ei < 0; }
+    };
+
+    template <class Pred>
+    void test_boundary(const char *what, Pred pred) {
+        const int d0 = 21, d1 = 13, d2 = 6;
+        namespace rb = gt::boundaries;
+        namespace bd = gtb200::boundaries;
+        fun_t fa = [](int i, int j, int k) { return 1. + i + 100. * j + 1e4 * k; };
+        fun_t fb = [](int i, int j, int k) { return -2. - i - 50. * j - 1e3 * k; };
+        gt::array<gt::halo_descriptor, 3> hd{gt::halo_descriptor(2, 3, 2, d0 - 4, d0),
+            gt::halo_descriptor(1, 2, 1, d1 - 3, d1), gt::halo_descriptor(1, 1, 1, d2 - 2, d2)};
+        auto mk = [&](auto traits, fun_t f) {
+            using traits_t = decltype(traits);
+            return gt::storage::builder<traits_t>.template type<double>().dimensions(d0, d1, d2)
+                .initializer([f](int i, int j, int k) { return f(i, j, k); }).build();
+        };
+        for (int kind = 0; kind < 2; ++kind) {
+            auto ra = mk(gt::storage::cpu_ifirst(), fa), rb_ = mk(gt::storage::cpu_ifirst(), fb);
+            auto ga = mk(gt::storage::gpu(), fa), gb = mk(gt::storage::gpu(), fb);
+            // storage::gpu pads the i-length: the device layout's total length in i is the j stride
+            const int p0 = (int)ga->strides()[1];
+            std::array<gtb_halo_desc, 3> h = {{{2, 3, 2, d0 - 4, p0}, {1, 2, 1, d1 - 3, d1}, {1, 1, 1, d2 - 2, d2}}};
+            if (kind == 0) {
+                rb::make_boundary<gt::gcl::cpu>(hd, rb::value_boundary<double>(7.25), pred).apply(ra, rb_);
+                bd::make_boundary(h, bd::value_boundary<double>(7.25), pred).apply(ga->get_target_ptr(), gb->get_target_ptr());
+            } else {
+                rb::make_boundary<gt::gcl::cpu>(hd, rb::copy_boundary(), pred).apply(ra, rb_);
+                bd::make_boundary(h, bd::copy_boundary(), pred).apply(ga->get_target_ptr(), gb->get_target_ptr());
+            }
+            cudaDeviceSynchronize();
+            std::string name = std::string("boundary ") + (kind ? "copy " : "value ") + what;
+            verify((name + " field 0").c_str(), ga, ra, d0, d1, d2, 0, 0);
+            verify((name + " field 1").c_str(), gb, rb_, d0, d1, d2, 0, 0);
+        }
+    }
+
     template <int Tag>
     void test_tridiagonal(int ni, int nj, int nk) {
         auto hh = make_ij_grid(ni, nj, 0);
@@ -219,6 +275,8 @@ int main() {
         test_vert_adv<double, 0>(256, 256, 80); // BASELINE.json configs[1]
         test_vert_adv<float, 0>(40, 9, 20);
         test_vert_adv<double, 1>(23, 11, 43); // generic path: forward/backward sweeps, k-cached temporaries
+        test_boundary("all directions", all_predicate());
+        test_boundary("-i directions", i_minus_predicate());
         test_tridiagonal<0>(12, 33, 6);
         test_tridiagonal<0>(23, 11, 6);
         test_tridiagonal<1>(23, 11, 6);
