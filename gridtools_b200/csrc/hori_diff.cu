@@ -57,6 +57,8 @@ namespace {
         int tiles_i, tiles_j;
         int step_i, step_j, step_k; // gridDim.x decomposed in (tile_i, tile_j, k) digits
         stencil_gate gate;          // device-side ordering against a concurrent halo exchange (empty: none)
+        const T *crlato, *crlatu;   // simple_hori_diff only: j-only coefficients (compute-domain j = 0), element strides
+        int64_t cro_sj, cru_sj;
     };
 
     // Position of a CTA in the flat item list (i fastest, then j, then k: CTAs that run side by side work on
@@ -87,7 +89,7 @@ namespace {
 
     // The four stages for one thread: column i = tx, rows j0+ty*R .. +R-1, reading the staged tiles.  `release` is
     // called once the thread's shared-memory reads are done (the stage can be refilled while the math runs).
-    template <class T, class Release>
+    template <class T, bool SIMPLE = false, class Release>
     __device__ __forceinline__ void compute_item(const hd_params<T> &p, const T *__restrict__ sin,
         const T *__restrict__ sco, const item_iter &it, int tx, int ty, Release &&release) {
         constexpr int W = layout<T>::in_w;
@@ -112,6 +114,47 @@ namespace {
         for (int d = 0; d < R; ++d)
             co[d] = sco[(jl + d) * BI + tx];
         release();
+
+        if constexpr (SIMPLE) {
+            // simple_hori_diff.cpp:25-61 on the same staged neighbourhood.  wlap_function: in(1,0) + in(-1,0) - 2 in +
+            // crlato (in(0,1) - in) + crlatu (in(0,-1) - in); divflux_function: in + ((fluxx_m - fluxx) +
+            // (fluxy_m - fluxy)) coeff.  crlato / crlatu depend on j only.
+            T cro[R + 2], cru[R + 2]; // rows j = -1 .. R
+#pragma unroll
+            for (int d = 0; d < R + 2; ++d) {
+                int gj = it.j0() + jl - 1 + d;
+                gj = gj > p.nj + 1 ? p.nj + 1 : gj; // rows past the domain only feed masked outputs
+                cro[d] = p.crlato[(int64_t)gj * p.cro_sj];
+                cru[d] = p.crlatu[(int64_t)gj * p.cru_sj];
+            }
+            T lap_c[R + 2], lap_p[R], lap_m[R];
+#pragma unroll
+            for (int d = 0; d < R + 2; ++d) {
+                const T cc = c0[d + 1];
+                lap_c[d] = cp1[d] + cm1[d] - T(2) * cc + cro[d] * (c0[d + 2] - cc) + cru[d] * (c0[d] - cc);
+            }
+#pragma unroll
+            for (int d = 0; d < R; ++d) {
+                const T cpp = cp1[d + 1], cmm = cm1[d + 1];
+                lap_p[d] = cp2[d] + c0[d + 2] - T(2) * cpp + cro[d + 1] * (cp1[d + 2] - cpp) + cru[d + 1] * (cp1[d] - cpp);
+                lap_m[d] = c0[d + 2] + cm2[d] - T(2) * cmm + cro[d + 1] * (cm1[d + 2] - cmm) + cru[d + 1] * (cm1[d] - cmm);
+            }
+            const int i = it.i0() + tx;
+            const int j = it.j0() + jl;
+            T *o = p.out + i + (int64_t)j * p.out_sj + (int64_t)it.k * p.out_sk;
+#pragma unroll
+            for (int d = 0; d < R; ++d) {
+                const T lc = lap_c[d + 1];
+                const T fluxx = lap_p[d] - lc;
+                const T fluxx_m = lc - lap_m[d];
+                const T fluxy = cro[d + 1] * (lap_c[d + 2] - lc);
+                const T fluxy_m = cro[d + 1] * (lc - lap_c[d]);
+                const T res = c0[d + 2] + ((fluxx_m - fluxx) + (fluxy_m - fluxy)) * co[d];
+                if (i < p.ni && j + d < p.nj)
+                    o[(int64_t)d * p.out_sj] = res;
+            }
+            return;
+        }
 
         // lap_function (horizontal_diffusion.cpp:35-47): 4*in - (in(1,0) + in(0,1) + in(-1,0) + in(0,-1))
         T lap_c[R + 2]; // lap(i, j) for j = -1 .. R
@@ -210,7 +253,7 @@ namespace {
     }
 
     // ------------------------------------------------ TMA variant with a block barrier per item (hd.variant = 2)
-    template <class T, int STAGES>
+    template <class T, int STAGES, bool SIMPLE = false>
     __global__ void __launch_bounds__(THREADS, 2) hd_tma_kernel(const __grid_constant__ CUtensorMap map_in,
         const __grid_constant__ CUtensorMap map_co, const hd_params<T> p) {
         using L = layout<T>;
@@ -242,8 +285,8 @@ namespace {
             const int s = n % STAGES;
             ptx::mbar_wait(&full[s], (uint32_t)((n / STAGES) & 1));
             const unsigned char *base = smem + s * L::stage_bytes;
-            compute_item<T>(p, reinterpret_cast<const T *>(base), reinterpret_cast<const T *>(base + L::in_alloc), it,
-                tx, ty, [] {});
+            compute_item<T, SIMPLE>(p, reinterpret_cast<const T *>(base), reinterpret_cast<const T *>(base + L::in_alloc),
+                it, tx, ty, [] {});
             __syncthreads(); // every thread has consumed stage s: hand it back to the TMA unit
             if (tid == 0 && ahead.k < p.nk) {
                 tma_issue<T>(&map_in, &map_co, smem + s * L::stage_bytes, &full[s], ahead);
@@ -536,7 +579,41 @@ namespace {
             return GTB_ERR_CUDA;
         if (ni == 0 || nj == 0 || nk == 0)
             return GTB_OK;
-        shd_params<T> p;
+        if (opts().hd_variant != 1) { // the TMA-staged register-tile kernel of hori_diff with the simple functors
+            hd_params<T> q;
+            q.in = static_cast<const T *>(in->ptr), q.coeff = static_cast<const T *>(coeff->ptr);
+            q.out = static_cast<T *>(out->ptr);
+            q.in_sj = in->stride_j, q.in_sk = in->stride_k, q.co_sj = coeff->stride_j, q.co_sk = coeff->stride_k;
+            q.out_sj = out->stride_j, q.out_sk = out->stride_k;
+            q.ni = ni, q.nj = nj, q.nk = nk;
+            q.tiles_i = ceil_div(ni, BI), q.tiles_j = ceil_div(nj, BJ);
+            q.crlato = static_cast<const T *>(crlato->ptr), q.crlatu = static_cast<const T *>(crlatu->ptr);
+            q.cro_sj = crlato->stride_j, q.cru_sj = crlatu->stride_j;
+            q.gate = stencil_gate();
+            using L = layout<T>;
+            constexpr int STAGES = 3;
+            const int smem = STAGES * L::stage_bytes + 16 * STAGES;
+            const int64_t items = (int64_t)q.tiles_i * q.tiles_j * nk;
+            CUtensorMap map_in, map_co;
+            if (items < ((int64_t)1 << 31) &&
+                make_map<T>(&map_in, q.in, q.in_sj, q.in_sk, L::lead, 2, (int64_t)L::lead + ni + 2, nj + 4, nk, L::in_w, IN_H) &&
+                make_map<T>(&map_co, q.coeff, q.co_sj, q.co_sk, 0, 0, ni, nj, nk, BI, BJ)) {
+                int grid = stencil_sms(d) * 2;
+                if (grid > items)
+                    grid = (int)items;
+                q.step_i = grid % q.tiles_i;
+                q.step_j = (grid / q.tiles_i) % q.tiles_j;
+                q.step_k = (grid / q.tiles_i) / q.tiles_j;
+                auto kernel = hd_tma_kernel<T, STAGES, true>;
+                int st = prepare_kernel(kernel, smem);
+                if (st)
+                    return st;
+                kernel<<<grid, THREADS, smem, as_stream(stream)>>>(map_in, map_co, q);
+                count_launch();
+                return check_launch("hd_tma_kernel (simple_hori_diff)");
+            }
+        }
+        shd_params<T> p; // layouts TMA cannot address (or hd.variant = 1): plain shared-memory tile kernel
         p.in = static_cast<const T *>(in->ptr), p.coeff = static_cast<const T *>(coeff->ptr);
         p.crlato = static_cast<const T *>(crlato->ptr), p.crlatu = static_cast<const T *>(crlatu->ptr);
         p.out = static_cast<T *>(out->ptr);

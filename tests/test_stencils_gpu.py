@@ -216,9 +216,14 @@ def test_simple_hori_diff_random_bit_exact(gt, oracle, size, dtype):
     inp = rng.standard_normal((nk, nj + 4, ni + 4)).astype(dtype)
     coeff = rng.uniform(0, 0.05, inp.shape).astype(dtype)
     cro, cru = rng.uniform(0.5, 1.5, nj + 4).astype(dtype), rng.uniform(0.5, 1.5, nj + 4).astype(dtype)
-    out = run_shd(gt, inp, coeff, cro, cru)
+    want = oracle.simple_hori_diff(inp, coeff, cro, cru)
     inner = (slice(None), slice(2, -2), slice(2, -2))
-    assert np.array_equal(out[inner], oracle.simple_hori_diff(inp, coeff, cro, cru)[inner])
+    for variant in (0, 1):  # 0: TMA-staged register-tile kernel; 1: plain shared-memory tile kernel (any layout)
+        gt.lib.set_option("hd.variant", variant)
+        out = run_shd(gt, inp, coeff, cro, cru)
+        assert np.array_equal(out[inner], want[inner]), variant
+    out = run_shd(gt, inp, coeff, cro, cru, alignment=1)  # not TMA-addressable: falls back by itself
+    assert np.array_equal(out[inner], want[inner])
 
 
 # ------------------------------------------------------------------------------------- vertical advection
