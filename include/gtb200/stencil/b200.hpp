@@ -21,12 +21,17 @@
  *     copy_stencil.cpp:42-47).  User functors are compile-time types a shared library cannot see, hence the one-line
  *     registration next to the functor definitions.
  *
- *  2. GENERIC PATH (needs nvcc: the user functors are instantiated inside a __global__ template in the user's
- *     translation unit).  Any other spec runs stage by stage: be_api::make_split_view, one launch per stage over
- *     the extent-extended IJ domain, k levels in parallel for execute_parallel and swept by one thread per column
- *     for execute_forward/backward, temporaries in device memory.  This is the semantics of the reference's `naive`
- *     backend (stencil/naive.hpp:32-78) executed on the GPU; ij/k caches are honoured as what they are
- *     semantically -- plain temporaries.
+ *  2. GENERIC PATHS (need nvcc: the user functors are instantiated inside a __global__ template in the user's
+ *     translation unit).
+ *     a. FUSED (b200_fused.hpp, the default where it applies): one launch per multi-stage, `__syncthreads` where
+ *        be_api's need_sync asks for it, ij caches as shared-memory tiles, k caches as register windows with run-time
+ *        checked fill / flush, forward / backward sweeps by one thread per column.
+ *     b. STAGE BY STAGE: specs the fused path does not take (`fused::fusable`: non-cached temporaries read at IJ
+ *        offsets, sweeps with IJ extents, k caches in parallel multi-stages) or `b200<..., gtb200::stage_by_stage>`:
+ *        be_api::make_split_view, one launch per stage over the extent-extended IJ domain, k levels in parallel for
+ *        execute_parallel and swept by one thread per column for execute_forward/backward, temporaries in device
+ *        memory -- the semantics of the reference's `naive` backend (stencil/naive.hpp:32-78) executed on the GPU;
+ *        ij/k caches are honoured as what they are semantically, plain temporaries.
  *
  * Errors: a non-zero status of the C ABI becomes the std::runtime_error the reference throws from GT_CUDA_CHECK
  * (common/cuda_util.hpp:20-35).  Launches go to the legacy default stream and do not synchronise, like the
@@ -59,6 +64,9 @@
 #endif
 
 #include "../../gtb200.h"
+#ifdef __CUDACC__
+#include "b200_fused.hpp"
+#endif
 
 namespace gtb200 {
 
@@ -72,6 +80,18 @@ namespace gtb200 {
     struct default_stream {
         void *operator()() const { return nullptr; } // legacy default stream, like the reference
     };
+
+    /// How specs without a named kernel are executed (second template argument of stencil::b200).
+    struct fused_when_possible {};
+    struct stage_by_stage {};
+#ifdef __CUDACC__
+    /// IJ block and levels per CTA of the fused generic path (third template argument of stencil::b200).
+    template <int BI, int BJ, int KB>
+    using block_geometry = ::gridtools::stencil::b200_backend::fused::geometry<BI, BJ, KB>;
+    using default_geometry = block_geometry<32, 8, 8>;
+#else
+    struct default_geometry {};
+#endif
 
     inline void check(int status, const char *what) {
         if (status != GTB_OK)
@@ -307,8 +327,9 @@ namespace gridtools {
                     auto num_colors = info.num_colors();
                     auto offsets = hymap::keys<dim::i, dim::j, dim::k>::make_values(
                         -extent.minus(dim::i()), -extent.minus(dim::j()), -grid.k_start(interval) - extent.minus(dim::k()));
-                    auto sizes = hymap::keys<dim::c, dim::k, dim::j, dim::i>::make_values(
-                        num_colors, grid.k_size(interval, extent), grid.j_size(extent), grid.i_size(extent));
+                    // first key = stride 1 (stride_util::make_strides_from_sizes): i fastest, like the fields
+                    auto sizes = hymap::keys<dim::i, dim::j, dim::c, dim::k>::make_values(
+                        grid.i_size(extent), grid.j_size(extent), num_colors, grid.k_size(interval, extent));
                     using stride_kind = meta::list<decltype(extent), decltype(num_colors)>;
                     return sid::shift_sid_origin(
                         sid::make_contiguous<decltype(info.data()), ptrdiff_t, stride_kind>(alloc, sizes), offsets);
@@ -320,7 +341,9 @@ namespace gridtools {
 #endif
 
             // ---------------------------------------------------------------- the tag
-            template <class StreamGetter = ::gtb200::default_stream>
+            template <class StreamGetter = ::gtb200::default_stream,
+                class Generic = ::gtb200::fused_when_possible,
+                class Geometry = ::gtb200::default_geometry>
             struct b200 {
                 template <class Spec, class Grid, class DataStores>
                 static void dispatch(std::true_type /*named*/, Spec, Grid const &grid, DataStores &data_stores) {
@@ -330,13 +353,27 @@ namespace gridtools {
                 template <class Spec, class Grid, class DataStores>
                 static void dispatch(std::false_type, Spec spec, Grid const &grid, DataStores &data_stores) {
 #ifdef __CUDACC__
-                    run_generic(spec, grid, std::move(data_stores), StreamGetter()());
+                    constexpr bool fuse =
+                        std::is_same<Generic, ::gtb200::fused_when_possible>::value && fused::fusable<Spec>::value;
+                    b200::generic(std::integral_constant<bool, fuse>(), spec, grid, data_stores);
 #else
                     static_assert(sizeof(Spec) == 0,
                         "stencil::b200: this spec is not bound to a named kernel (GTB200_REGISTER_SPEC); the generic "
                         "path instantiates the user functors in a CUDA kernel and needs this file to be compiled by nvcc");
 #endif
                 }
+
+#ifdef __CUDACC__
+                template <class Spec, class Grid, class DataStores>
+                static void generic(std::true_type /*fused*/, Spec spec, Grid const &grid, DataStores &data_stores) {
+                    fused::cuda_launcher launcher{static_cast<cudaStream_t>(StreamGetter()())};
+                    fused::run<Geometry>(launcher, spec, grid, std::move(data_stores));
+                }
+                template <class Spec, class Grid, class DataStores>
+                static void generic(std::false_type, Spec spec, Grid const &grid, DataStores &data_stores) {
+                    run_generic(spec, grid, std::move(data_stores), StreamGetter()());
+                }
+#endif
 
                 template <class Spec, class Grid, class DataStores>
                 friend void gridtools_backend_entry_point(b200, Spec spec, Grid const &grid, DataStores data_stores) {

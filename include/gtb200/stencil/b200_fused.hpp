@@ -1,0 +1,561 @@
+/*
+ * gtb200/stencil/b200_fused.hpp -- the fused generic path of the stencil::b200 backend: ONE launch per multi-stage for
+ * specs that are not bound to a hand-written kernel (included by b200.hpp; needs nvcc).
+ *
+ * What it replaces in the reference's stencil::gpu backend, and how it differs:
+ *
+ *   a2  stage/multi-stage fusion (gpu/entry_point.hpp:97-124, be_api.hpp:211-222): all stages of a multi-stage run in
+ *       one kernel, `__syncthreads` exactly where be_api's `need_sync` asks for it.
+ *   a3  thread mapping (gpu/launch_kernel.hpp:46-166): the reference adds rows of 64 threads for the i-halo columns
+ *       and masks them per cell.  Here a CTA has ONE thread per point of the halo-extended IJ tile,
+ *       (BI + i-extent) x (BJ + j-extent) rounded up to whole warps, i fastest; a thread keeps its point for every
+ *       cell of the multi-stage (so un-synchronised zero-offset dependencies stay inside a thread) and a cell masks
+ *       the points outside its own extent.
+ *   a4  ij caches (gpu/ij_cache.hpp:38-47, gpu/shared_allocator.hpp:21-53): shared-memory tiles with compile-time
+ *       strides (1, tile width), built with sid::synthetic.
+ *   a5  k loops (gpu/make_kernel_fun.hpp:33-142): parallel multi-stages take KB levels per CTA; forward / backward
+ *       multi-stages sweep a column per thread.
+ *   a6  k caches and their fill / flush (gpu/k_cache.hpp:24-75, gpu/fill_flush.hpp:123-324): register windows
+ *       [kminus, kplus] slid once per level.  The reference rewrites the spec at compile time (extra fill and flush
+ *       stages per elementary interval, bound checks chosen from the interval levels); here the loads and stores are
+ *       part of the sweep itself and are checked at run time against the k bounds of the field: on the first level
+ *       of the sweep the whole window is filled, afterwards the entry that slides in; every level flushes the entry
+ *       that slides out, the last level the whole window.  Same values in the same places, no spec surgery.
+ *   a7  temporaries that are neither ij- nor k-cached live in device memory (whole domain).  A spec whose non-cached
+ *       temporaries are read at IJ offsets would need CTA-private blocked copies (gpu/tmp_storage_sid.hpp:54-69);
+ *       such specs -- and sweeps with IJ extents, and k caches in parallel multi-stages -- are not `fusable` and take
+ *       the stage-by-stage path of b200.hpp instead.
+ *
+ * Everything here is written against a `Cta` policy (block / thread indices, barrier, shared-memory base): `cuda_cta`
+ * is the product; tests/cpp/emulated_cta.hpp runs the very same body on the host, one OpenMP team per CTA, to pin
+ * the index algebra against the reference's cpu_ifirst backend without a GPU (test infrastructure, not a fallback).
+ */
+#pragma once
+
+#include <limits>
+#include <type_traits>
+#include <utility>
+
+#include <gridtools/common/for_each.hpp>
+#include <gridtools/common/functional.hpp>
+#include <gridtools/common/host_device.hpp>
+#include <gridtools/common/hymap.hpp>
+#include <gridtools/common/integral_constant.hpp>
+#include <gridtools/common/tuple.hpp>
+#include <gridtools/common/tuple_util.hpp>
+#include <gridtools/meta.hpp>
+#include <gridtools/sid/allocator.hpp>
+#include <gridtools/sid/block.hpp>
+#include <gridtools/sid/composite.hpp>
+#include <gridtools/sid/concept.hpp>
+#include <gridtools/sid/contiguous.hpp>
+#include <gridtools/sid/sid_shift_origin.hpp>
+#include <gridtools/sid/synthetic.hpp>
+#include <gridtools/stencil/be_api.hpp>
+#include <gridtools/stencil/common/caches.hpp>
+#include <gridtools/stencil/common/dim.hpp>
+#include <gridtools/stencil/common/extent.hpp>
+
+#ifdef __CUDACC__
+#include <gridtools/common/cuda_util.hpp>
+#endif
+
+namespace gridtools {
+    namespace stencil {
+        namespace b200_backend {
+            namespace fused {
+                // ---------------------------------------------------------------- geometry
+                template <int_t BI = 32, int_t BJ = 8, int_t KB = 8>
+                struct geometry {
+                    static constexpr int_t bi = BI, bj = BJ, kb = KB;
+                };
+
+                template <class Extent>
+                using has_ij_extent = std::bool_constant<Extent::iminus::value != 0 || Extent::iplus::value != 0 ||
+                                                         Extent::jminus::value != 0 || Extent::jplus::value != 0>;
+
+                // ---------------------------------------------------------------- what a placeholder is inside a MSS
+                template <class Info>
+                using is_ij_cached = std::is_same<typename Info::caches_t, meta::list<cache_type::ij>>;
+                template <class Info>
+                using is_k_cached = std::is_same<typename Info::caches_t, meta::list<cache_type::k>>;
+                template <class Info>
+                using is_plain = meta::is_empty<typename Info::caches_t>;
+                template <class Info>
+                using has_fill = meta::st_contains<typename Info::cache_io_policies_t, cache_io_policy::fill>;
+                template <class Info>
+                using has_flush = meta::st_contains<typename Info::cache_io_policies_t, cache_io_policy::flush>;
+                template <class Info>
+                using is_io_cached = std::bool_constant<is_k_cached<Info>::value &&
+                                                        (has_fill<Info>::value || has_flush<Info>::value)>;
+                // does the placeholder need memory behind it (device memory for a temporary)?
+                template <class Info>
+                using needs_memory = std::bool_constant<is_plain<Info>::value || is_io_cached<Info>::value>;
+
+                /// Key of the field behind a filled / flushed k cache inside the composite of a multi-stage.
+                template <class Plh>
+                struct behind {};
+
+                // ---------------------------------------------------------------- can a spec take the fused path?
+                template <class Mss>
+                using mss_is_fusable = std::bool_constant<
+                    be_api::is_parallel<typename Mss::execution_t>::value
+                        ? !meta::any_of<is_k_cached, typename Mss::plh_map_t>::value
+                        : !has_ij_extent<typename Mss::extent_t>::value>;
+
+                template <class Info>
+                using tmp_is_fusable =
+                    std::bool_constant<!needs_memory<Info>::value || !has_ij_extent<typename Info::extent_t>::value>;
+
+                template <class Spec, class Msses = be_api::make_fused_view<Spec>>
+                using fusable = std::bool_constant<meta::all_of<mss_is_fusable, meta::rename<meta::list, Msses>>::value &&
+                                                   meta::all_of<tmp_is_fusable, typename Msses::tmp_plh_map_t>::value>;
+
+                // ---------------------------------------------------------------- shared-memory tiles (ij caches)
+                template <class T, class Cta>
+                struct tile_holder {
+                    int_t m_bytes; // start of the tile in the CTA's dynamic shared memory (16-byte aligned)
+                    int_t m_elems; // offset of the addressed element inside the tile
+                    GT_FUNCTION T *operator()() const { return reinterpret_cast<T *>(Cta::smem() + m_bytes) + m_elems; }
+                    friend GT_FUNCTION tile_holder operator+(tile_holder h, int_t d) {
+                        h.m_elems += d;
+                        return h;
+                    }
+                };
+
+                template <class Tag>
+                struct tile_kind {};
+
+                // tile of a temporary with extent E under a BI x BJ block: (BI + i-extent) x (BJ + j-extent), i fastest,
+                // origin at the block's first interior point
+                template <class T, class Cta, class Geo, class Extent>
+                auto make_tile(int_t &smem_bytes) {
+                    constexpr int_t w = Geo::bi - Extent::iminus::value + Extent::iplus::value;
+                    constexpr int_t h = Geo::bj - Extent::jminus::value + Extent::jplus::value;
+                    const int_t start = (smem_bytes + 15) / 16 * 16;
+                    smem_bytes = start + int_t(sizeof(T)) * w * h;
+                    return sid::synthetic()
+                        .template set<sid::property::origin>(
+                            tile_holder<T, Cta>{start, -Extent::iminus::value - Extent::jminus::value * w})
+                        .template set<sid::property::strides>(hymap::keys<dim::i, dim::j>::make_values(
+                            integral_constant<int_t, 1>(), integral_constant<int_t, w>()))
+                        .template set<sid::property::ptr_diff, int_t>()
+                        .template set<sid::property::strides_kind, tile_kind<integral_constant<int_t, w>>>();
+                }
+
+                // ---------------------------------------------------------------- register windows (k caches)
+                template <class T, int_t Minus, int_t Plus>
+                struct window {
+                    static constexpr int_t minus = Minus, plus = Plus;
+                    T m_v[Plus - Minus + 1];
+                    GT_FUNCTION T *ptr() { return m_v - Minus; }
+                    GT_FUNCTION void slide(integral_constant<int_t, 1>) {
+#pragma unroll
+                        for (int_t n = 0; n < Plus - Minus; ++n)
+                            m_v[n] = m_v[n + 1];
+                    }
+                    GT_FUNCTION void slide(integral_constant<int_t, -1>) {
+#pragma unroll
+                        for (int_t n = Plus - Minus; n > 0; --n)
+                            m_v[n] = m_v[n - 1];
+                    }
+                };
+                template <class Info, class E = typename Info::extent_t>
+                using window_of = window<std::remove_const_t<typename Info::data_t>, E::kminus::value, E::kplus::value>;
+
+                // what stands for a k-cached placeholder inside the composite: no memory, k stride 1 (the window); the
+                // real pointer is put in front of it per thread (hymap merge)
+                template <class T>
+                struct null_holder {
+                    GT_FUNCTION T *operator()() const { return nullptr; }
+                    friend GT_FUNCTION null_holder operator+(null_holder h, int_t) { return h; }
+                };
+                struct window_kind {};
+                template <class T>
+                auto make_window_stub() {
+                    return sid::synthetic()
+                        .template set<sid::property::origin>(null_holder<T>{})
+                        .template set<sid::property::strides>(
+                            hymap::keys<dim::k>::make_values(integral_constant<int_t, 1>()))
+                        .template set<sid::property::ptr_diff, int_t>()
+                        .template set<sid::property::strides_kind, window_kind>();
+                }
+
+                // Fields a multi-stage only reads go through the read-only data path (ld.global.nc), which also lets the
+                // compiler move their loads across the stores of the sweep (the reference: gpu/entry_point.hpp:135-147).
+                // Window and tile pointers are pointers to non-const and never take this overload.
+                template <class ConstKeys>
+                struct read_only_deref {
+                    template <class Key,
+                        class T,
+                        std::enable_if_t<meta::st_contains<ConstKeys, Key>::value && std::is_arithmetic<T>::value, int> = 0>
+                    GT_FUNCTION T operator()(Key, T const *ptr) const {
+#ifdef __CUDA_ARCH__
+                        return __ldg(ptr);
+#else
+                        return *ptr;
+#endif
+                    }
+                    template <class Key, class Ptr>
+                    GT_FUNCTION decltype(auto) operator()(Key, Ptr ptr) const {
+                        return *ptr;
+                    }
+                };
+
+                struct k_bounds {
+                    int_t lo, hi; // valid levels of the field behind a cache, relative to the grid's k origin
+                };
+
+                // ---------------------------------------------------------------- per-thread body of one multi-stage
+                template <class Cta, class Mss, class Geo, class Holder, class Strides, class KSizes, class Bounds>
+                struct mss_body {
+                    using extent_t = typename Mss::extent_t;
+                    using plh_map_t = typename Mss::plh_map_t;
+                    using k_cached_t = meta::filter<is_k_cached, plh_map_t>;
+                    using io_cached_t = meta::filter<is_io_cached, plh_map_t>;
+                    using step_t = typename Mss::k_step_t;
+                    using deref_t = read_only_deref<
+                        meta::transform<be_api::get_key, meta::filter<be_api::get_is_const, plh_map_t>>>;
+
+                    static constexpr bool parallel = be_api::is_parallel<typename Mss::execution_t>::value;
+                    static constexpr int_t imin = extent_t::iminus::value, jmin = extent_t::jminus::value;
+                    static constexpr int_t width = Geo::bi - imin + extent_t::iplus::value;
+                    static constexpr int_t height = Geo::bj - jmin + extent_t::jplus::value;
+                    static constexpr int_t threads = (width * height + 31) / 32 * 32;
+                    static_assert(threads <= 1024, "stencil::b200 fused path: IJ block plus extents exceed one CTA");
+
+                    Holder m_holder;   // composite of fields, tiles, window stubs; at the first level of the sweep
+                    Strides m_strides; //
+                    KSizes m_k_sizes;  // levels per elementary interval, in execution order
+                    Bounds m_bounds;   // k_bounds per filled / flushed cache (order of io_cached_t)
+                    int_t m_ni, m_nj;  // compute domain
+                    int_t m_k_first;   // level of the first step of the sweep
+
+                    struct point {
+                        int_t ti, tj, gi, gj;
+                    };
+
+                    template <class Extent>
+                    GT_FUNCTION bool active(point const &p, Extent) const {
+                        return p.ti >= Extent::iminus::value && p.ti < Geo::bi + Extent::iplus::value &&
+                               p.tj >= Extent::jminus::value && p.tj < Geo::bj + Extent::jplus::value &&
+                               p.gi < m_ni + Extent::iplus::value && p.gj < m_nj + Extent::jplus::value;
+                    }
+
+                    template <class Info, class Ptr>
+                    GT_FUNCTION void exec_cells(Info, Ptr const &ptr, point const &p) const {
+                        host_device::for_each<typename Info::cells_t>([&](auto cell) GT_FORCE_INLINE_LAMBDA {
+                            if (decltype(cell.need_sync())::value)
+                                Cta::sync();
+                            if (active(p, cell.extent()))
+                                cell.template operator()<deref_t>(ptr, m_strides);
+                        });
+                    }
+
+                    GT_FUNCTION void operator()() const {
+                        const int_t tid = Cta::tid();
+                        point p;
+                        p.ti = tid % width + imin;
+                        p.tj = tid / width + jmin;
+                        p.gi = Cta::block_i() * Geo::bi + p.ti;
+                        p.gj = Cta::block_j() * Geo::bj + p.tj;
+                        auto ptr = m_holder();
+                        sid::shift(ptr, sid::get_stride<sid::blocked_dim<dim::i>>(m_strides), Cta::block_i());
+                        sid::shift(ptr, sid::get_stride<sid::blocked_dim<dim::j>>(m_strides), Cta::block_j());
+                        sid::shift(ptr, sid::get_stride<dim::i>(m_strides), p.ti);
+                        sid::shift(ptr, sid::get_stride<dim::j>(m_strides), p.tj);
+                        run(std::bool_constant<parallel>(), ptr, p);
+                    }
+
+                    // parallel multi-stage: this CTA takes levels [kb * KB, kb * KB + KB) of the multi-stage's interval
+                    template <class Ptr>
+                    GT_FUNCTION void run(std::true_type, Ptr &ptr, point const &p) const {
+                        const int_t first = Cta::block_k() * Geo::kb, last = first + Geo::kb;
+                        int_t cur = 0;
+                        tuple_util::host_device::for_each(
+                            [&](int_t size, auto info) GT_FORCE_INLINE_LAMBDA {
+                                int_t lo = first - cur, hi = last - cur;
+                                if (lo < 0)
+                                    lo = 0;
+                                if (hi > size)
+                                    hi = size;
+                                cur += size;
+                                if (lo >= hi) {
+                                    sid::shift(ptr, sid::get_stride<dim::k>(m_strides), size);
+                                    return;
+                                }
+                                sid::shift(ptr, sid::get_stride<dim::k>(m_strides), lo);
+                                for (int_t k = lo; k < hi; ++k) {
+                                    exec_cells(info, ptr, p);
+                                    info.inc_k(ptr, m_strides);
+                                }
+                                sid::shift(ptr, sid::get_stride<dim::k>(m_strides), size - hi);
+                            },
+                            m_k_sizes,
+                            Mss::interval_infos());
+                    }
+
+                    // ---- k caches
+                    template <class Info>
+                    using behind_key = behind<typename Info::plh_t>;
+
+                    // moves window entry `W` of one cache from (Fill) / to the field behind it if level k_pos + W exists there
+                    template <bool Fill, class Info, int_t W, class Windows, class Ptr>
+                    GT_FUNCTION void sync_entry(Windows &windows, Ptr const &ptr, int_t k_pos, k_bounds b) const {
+                        if (k_pos + W < b.lo || k_pos + W >= b.hi)
+                            return;
+                        auto mem = host_device::at_key<behind_key<Info>>(ptr);
+                        sid::shift(mem,
+                            sid::get_stride_element<behind_key<Info>, dim::k>(m_strides),
+                            integral_constant<int_t, W>());
+                        auto &win = host_device::at_key<typename Info::key_t>(windows);
+                        if constexpr (Fill)
+                            win.ptr()[W] = *mem;
+                        else
+                            *mem = win.ptr()[W];
+                    }
+
+                    template <bool Fill, class Info, int_t From, int_t To, class Windows, class Ptr>
+                    GT_FUNCTION void sync_range(Windows &windows, Ptr const &ptr, int_t k_pos, k_bounds b) const {
+                        sync_entry<Fill, Info, From>(windows, ptr, k_pos, b);
+                        if constexpr (From < To)
+                            sync_range<Fill, Info, From + 1, To>(windows, ptr, k_pos, b);
+                    }
+
+                    // `whole`: first level of the sweep for fills, last level for flushes
+                    template <bool Fill, class Windows, class Ptr>
+                    GT_FUNCTION void sync_caches(Windows &windows, Ptr const &ptr, int_t k_pos, bool whole) const {
+                        // the entry that enters (fill) or leaves (flush) the window at every step of the sweep
+                        constexpr bool at_plus = (step_t::value > 0) == Fill;
+                        tuple_util::host_device::for_each(
+                            [&](auto info, k_bounds b) GT_FORCE_INLINE_LAMBDA {
+                                using info_t = decltype(info);
+                                using win_t = window_of<info_t>;
+                                if constexpr (Fill ? has_fill<info_t>::value : has_flush<info_t>::value) {
+                                    if (whole)
+                                        sync_range<Fill, info_t, win_t::minus, win_t::plus>(windows, ptr, k_pos, b);
+                                    else
+                                        sync_entry<Fill, info_t, at_plus ? win_t::plus : win_t::minus>(
+                                            windows, ptr, k_pos, b);
+                                }
+                            },
+                            meta::rename<tuple, io_cached_t>(),
+                            m_bounds);
+                    }
+
+                    // forward / backward multi-stage: one column per thread, k caches in registers
+                    template <class Ptr>
+                    GT_FUNCTION void run(std::false_type, Ptr &ptr, point const &p) const {
+                        using keys_t = meta::transform<be_api::get_key, k_cached_t>;
+                        using windows_t = hymap::from_keys_values<keys_t, meta::transform<window_of, k_cached_t>>;
+                        windows_t windows;
+                        auto mixed = hymap::host_device::merge(
+                            tuple_util::host_device::transform(
+                                [](auto &w) GT_FORCE_INLINE_LAMBDA { return w.ptr(); }, windows),
+                            std::move(ptr));
+                        const bool on = active(p, extent<>());
+                        int_t total = 0;
+                        tuple_util::host_device::for_each(
+                            [&](int_t size) GT_FORCE_INLINE_LAMBDA { total += size; }, m_k_sizes);
+                        int_t n = 0, k_pos = m_k_first;
+                        tuple_util::host_device::for_each(
+                            [&](int_t size, auto info) GT_FORCE_INLINE_LAMBDA {
+                                for (int_t k = 0; k < size; ++k) {
+                                    if (on)
+                                        sync_caches<true>(windows, mixed.secondary(), k_pos, n == 0);
+                                    exec_cells(info, mixed, p);
+                                    if (on)
+                                        sync_caches<false>(windows, mixed.secondary(), k_pos, n == total - 1);
+                                    tuple_util::host_device::for_each(
+                                        [](auto &w) GT_FORCE_INLINE_LAMBDA { w.slide(step_t()); }, windows);
+                                    info.inc_k(mixed.secondary(), m_strides);
+                                    k_pos += step_t::value;
+                                    ++n;
+                                }
+                            },
+                            m_k_sizes,
+                            Mss::interval_infos());
+                    }
+                };
+
+                // ---------------------------------------------------------------- host side: one multi-stage
+                template <class Plh, class DataStores>
+                k_bounds field_k_bounds(DataStores const &data_stores) {
+                    auto const &store = at_key<Plh>(data_stores);
+                    return {int_t(sid::get_lower_bound<dim::k>(sid::get_lower_bounds(store))),
+                        int_t(sid::get_upper_bound<dim::k>(sid::get_upper_bounds(store)))};
+                }
+
+                template <class Launcher, class Geo, class Mss, class Grid, class DataStores>
+                void launch_mss(Launcher &launcher, Mss, Grid const &grid, DataStores &data_stores) {
+                    using cta_t = typename Launcher::cta_t;
+                    using plh_map_t = typename Mss::plh_map_t;
+                    using io_cached_t = meta::filter<is_io_cached, plh_map_t>;
+                    int_t smem_bytes = 0;
+
+                    // fields, shared-memory tiles and window stubs under the keys the stages look them up with ...
+                    auto members = tuple_util::transform(
+                        overload(
+                            [&](meta::list<cache_type::ij>, auto info) {
+                                using info_t = decltype(info);
+                                return make_tile<std::remove_const_t<typename info_t::data_t>,
+                                    cta_t,
+                                    Geo,
+                                    typename info_t::extent_t>(smem_bytes);
+                            },
+                            [](meta::list<cache_type::k>, auto info) {
+                                return make_window_stub<std::remove_const_t<typename decltype(info)::data_t>>();
+                            },
+                            [&](meta::list<>, auto info) {
+                                return sid::add_const(info.is_const(), at_key<decltype(info.plh())>(data_stores));
+                            }),
+                        meta::rename<tuple, meta::transform<be_api::get_caches, plh_map_t>>(),
+                        meta::rename<tuple, plh_map_t>());
+                    // ... plus the fields behind filled / flushed k caches
+                    auto behinds = tuple_util::transform(
+                        [&](auto info) {
+                            return sid::add_const(std::bool_constant<!has_flush<decltype(info)>::value>(),
+                                at_key<decltype(info.plh())>(data_stores));
+                        },
+                        meta::rename<tuple, io_cached_t>());
+                    using keys_t = meta::rename<sid::composite::keys,
+                        meta::concat<meta::transform<be_api::get_key, plh_map_t>,
+                            meta::transform<behind, meta::transform<be_api::get_plh, io_cached_t>>>>;
+                    auto composite = tuple_util::convert_to<keys_t::template values>(
+                        tuple_util::concat(std::move(members), std::move(behinds)));
+
+                    auto bounds = tuple_util::transform(
+                        [&](auto info) { return field_k_bounds<decltype(info.plh())>(data_stores); },
+                        meta::rename<tuple, io_cached_t>());
+
+                    auto strides = sid::get_strides(composite);
+                    sid::ptr_diff_type<decltype(composite)> offset{};
+                    const int_t k_first = grid.k_start(Mss::interval(), Mss::execution());
+                    sid::shift(offset, sid::get_stride<dim::k>(strides), k_first);
+                    auto k_sizes = be_api::make_k_sizes(Mss::interval_infos(), grid);
+                    int_t k_total = 0;
+                    tuple_util::for_each([&](int_t n) { k_total += n; }, k_sizes);
+                    const int_t ni = grid.i_size(), nj = grid.j_size();
+                    if (ni <= 0 || nj <= 0 || k_total <= 0)
+                        return;
+
+                    using body_t = mss_body<cta_t,
+                        Mss,
+                        Geo,
+                        decltype(sid::get_origin(composite) + offset),
+                        decltype(strides),
+                        decltype(k_sizes),
+                        decltype(bounds)>;
+                    body_t body{sid::get_origin(composite) + offset, strides, k_sizes, bounds, ni, nj, k_first};
+                    launcher.launch(body,
+                        (ni + Geo::bi - 1) / Geo::bi,
+                        (nj + Geo::bj - 1) / Geo::bj,
+                        body_t::parallel ? (k_total + Geo::kb - 1) / Geo::kb : 1,
+                        body_t::threads,
+                        smem_bytes);
+                }
+
+                // ---------------------------------------------------------------- host side: the whole spec
+                template <class Geo = geometry<>, class Launcher, class Spec, class Grid, class DataStores>
+                void run(Launcher &launcher, Spec, Grid const &grid, DataStores external) {
+                    using msses_t = be_api::make_fused_view<Spec>;
+                    static_assert(fusable<Spec>::value, "stencil::b200: spec cannot take the fused path");
+                    // device memory behind the temporaries that are not (purely) cached
+                    using tmp_plh_map_t = be_api::remove_caches_from_plh_map<
+                        meta::filter<needs_memory, typename msses_t::tmp_plh_map_t>>;
+                    auto alloc = launcher.allocator();
+                    auto temporaries = be_api::make_data_stores(tmp_plh_map_t(), [&](auto info) {
+                        auto extent = info.extent();
+                        auto interval = msses_t::interval();
+                        auto offsets = hymap::keys<dim::i, dim::j, dim::k>::make_values(-extent.minus(dim::i()),
+                            -extent.minus(dim::j()),
+                            -grid.k_start(interval) - extent.minus(dim::k()));
+                        // first key = stride 1 (stride_util::make_strides_from_sizes): i fastest, like the fields
+                        auto sizes = hymap::keys<dim::i, dim::j, dim::k>::make_values(
+                            grid.i_size(extent), grid.j_size(extent), grid.k_size(interval, extent));
+                        using stride_kind = meta::list<decltype(extent), behind<void>>;
+                        return sid::shift_sid_origin(
+                            sid::make_contiguous<decltype(info.data()), ptrdiff_t, stride_kind>(alloc, sizes), offsets);
+                    });
+                    auto blocked = tuple_util::transform(
+                        [](auto &&store) {
+                            return sid::block(std::forward<decltype(store)>(store),
+                                hymap::keys<dim::i, dim::j>::make_values(
+                                    integral_constant<int_t, Geo::bi>(), integral_constant<int_t, Geo::bj>()));
+                        },
+                        hymap::concat(std::move(external), std::move(temporaries)));
+                    for_each<meta::rename<meta::list, msses_t>>(
+                        [&](auto mss) { launch_mss<Launcher, Geo>(launcher, mss, grid, blocked); });
+                }
+
+#ifdef __CUDACC__
+                // ---------------------------------------------------------------- the CUDA side
+                struct cuda_cta {
+                    static GT_FUNCTION int_t tid() {
+#ifdef __CUDA_ARCH__
+                        return threadIdx.x;
+#else
+                        return 0;
+#endif
+                    }
+                    static GT_FUNCTION int_t block_i() {
+#ifdef __CUDA_ARCH__
+                        return blockIdx.x;
+#else
+                        return 0;
+#endif
+                    }
+                    static GT_FUNCTION int_t block_j() {
+#ifdef __CUDA_ARCH__
+                        return blockIdx.y;
+#else
+                        return 0;
+#endif
+                    }
+                    static GT_FUNCTION int_t block_k() {
+#ifdef __CUDA_ARCH__
+                        return blockIdx.z;
+#else
+                        return 0;
+#endif
+                    }
+                    static GT_FUNCTION void sync() {
+#ifdef __CUDA_ARCH__
+                        __syncthreads();
+#endif
+                    }
+                    static GT_FUNCTION char *smem() {
+#ifdef __CUDA_ARCH__
+                        extern __shared__ __align__(16) char gtb200_fused_smem[];
+                        return gtb200_fused_smem;
+#else
+                        return nullptr;
+#endif
+                    }
+                };
+
+                template <class Body>
+                __global__ void __launch_bounds__(Body::threads) mss_kernel(Body body) {
+                    body();
+                }
+
+                struct cuda_launcher {
+                    using cta_t = cuda_cta;
+                    cudaStream_t m_stream;
+
+                    static auto allocator() { return sid::device::cached_allocator(&cuda_util::cuda_malloc<char[]>); }
+
+                    template <class Body>
+                    void launch(Body const &body, int_t nbi, int_t nbj, int_t nbk, int_t threads, int_t smem) const {
+                        if (smem > 48 * 1024)
+                            GT_CUDA_CHECK(cudaFuncSetAttribute(
+                                mss_kernel<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                        mss_kernel<Body><<<dim3(nbi, nbj, nbk), dim3(threads), smem, m_stream>>>(body);
+                        GT_CUDA_CHECK(cudaGetLastError());
+                    }
+                };
+#endif
+            } // namespace fused
+        } // namespace b200_backend
+    } // namespace stencil
+} // namespace gridtools

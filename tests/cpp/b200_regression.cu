@@ -24,6 +24,7 @@
 #include <gtb200/boundaries/boundary.hpp>
 #include <gtb200/stencil/b200.hpp>
 
+#include "cases.hpp"
 #include "functors.hpp"
 
 GTB200_REGISTER_SPEC(gtb200::kernel::copy, user::copy_f<0>);
@@ -253,6 +254,50 @@ namespace {
         std::string name = std::string("tridiagonal ") + (Tag ? "generic" : "named") + " (solution == 1)";
         verify(name.c_str(), out, ones, ni, nj, nk, 0, 1e-14); // tridiagonal.cpp:97
     }
+
+    // Every case of cases.hpp through one of the generic paths of the tag, against cpu_ifirst (whole storages: the
+    // halo must come back untouched).  `Backend` = st::b200<> (fused where fusable: all of these are) or
+    // st::b200<default_stream, stage_by_stage>.
+    template <class Backend>
+    void test_generic_cases(std::string label, int ni, int nj, int nk) {
+        gt::storage::gpu dev;
+        gt::storage::cpu_ifirst host;
+        st::cpu_ifirst<> ref_be;
+        Backend be;
+        auto fwd = [] { return st::execute_forward(); };
+        auto bwd = [] { return st::execute_backward(); };
+        auto name = [&](const char *what) {
+            return label + " " + what + " " + std::to_string(ni) + "x" + std::to_string(nj) + "x" + std::to_string(nk);
+        };
+        cases::same(name("hori_diff f64").c_str(), cases::hori_diff<double>(dev, be, ni, nj, nk),
+            cases::hori_diff<double>(host, ref_be, ni, nj, nk), ni + 4, nj + 4, nk, 1e-12, g_failed);
+        cases::same(name("hori_diff f32").c_str(), cases::hori_diff<float>(dev, be, ni, nj, nk),
+            cases::hori_diff<float>(host, ref_be, ni, nj, nk), ni + 4, nj + 4, nk, 1e-5, g_failed);
+        cases::same(name("simple_hori_diff f64").c_str(), cases::simple_hori_diff<double>(dev, be, ni, nj, nk),
+            cases::simple_hori_diff<double>(host, ref_be, ni, nj, nk), ni + 4, nj + 4, nk, 1e-12, g_failed);
+        cases::same(name("vert_adv f64").c_str(), cases::vert_adv<double>(dev, be, ni, nj, nk),
+            cases::vert_adv<double>(host, ref_be, ni, nj, nk), ni + 6, nj + 6, nk, 1e-12, g_failed);
+        cases::same(name("vert_adv f32").c_str(), cases::vert_adv<float>(dev, be, ni, nj, nk),
+            cases::vert_adv<float>(host, ref_be, ni, nj, nk), ni + 6, nj + 6, nk, 1e-4, g_failed);
+        cases::same(name("tridiagonal").c_str(), cases::tridiagonal(dev, be, ni, nj, 6),
+            cases::tridiagonal(host, ref_be, ni, nj, 6), ni, nj, 6, 1e-12, g_failed);
+        cases::same(name("k-cache fill forward").c_str(), cases::kcache_fill(fwd, dev, be, ni, nj, nk),
+            cases::kcache_fill(fwd, host, ref_be, ni, nj, nk), ni, nj, nk, 0, g_failed);
+        cases::same(name("k-cache fill backward").c_str(), cases::kcache_fill(bwd, dev, be, ni, nj, nk),
+            cases::kcache_fill(bwd, host, ref_be, ni, nj, nk), ni, nj, nk, 0, g_failed);
+        for (bool forward : {true, false}) {
+            cases::same(name(forward ? "k-cache flush forward" : "k-cache flush backward").c_str(),
+                cases::kcache_flush(forward, dev, be, ni, nj, nk), cases::kcache_flush(forward, host, ref_be, ni, nj, nk),
+                ni, nj, nk, 0, g_failed);
+            cases::same(name(forward ? "k-cache fill+flush forward" : "k-cache fill+flush backward").c_str(),
+                cases::kcache_fill_and_flush(forward, dev, be, ni, nj, nk),
+                cases::kcache_fill_and_flush(forward, host, ref_be, ni, nj, nk), ni, nj, nk, 0, g_failed);
+        }
+        cases::same(name("k-cache local, two stages").c_str(), cases::kcache_local(dev, be, ni, nj, nk),
+            cases::kcache_local(host, ref_be, ni, nj, nk), ni, nj, nk, 1e-14, g_failed);
+        cases::same(name("mixed tiles + plain temporaries").c_str(), cases::mixed<double>(dev, be, ni, nj, 2, nk),
+            cases::mixed<double>(host, ref_be, ni, nj, 2, nk), ni + 4, nj + 4, nk + 2, 1e-12, g_failed);
+    }
 } // namespace
 
 int main() {
@@ -280,6 +325,11 @@ int main() {
         test_tridiagonal<0>(12, 33, 6);
         test_tridiagonal<0>(23, 11, 6);
         test_tridiagonal<1>(23, 11, 6);
+        using staged_t = st::b200<gtb200::default_stream, gtb200::stage_by_stage>;
+        test_generic_cases<st::b200<>>("fused", 70, 19, 13);   // partial tiles in i and j, partial k block
+        test_generic_cases<st::b200<>>("fused", 1, 1, 2);
+        test_generic_cases<st::b200<>>("fused", 128, 64, 80);
+        test_generic_cases<staged_t>("staged", 70, 19, 13);
     } catch (std::exception const &e) {
         std::printf("EXCEPTION: %s\n", e.what());
         return 2;

@@ -1,0 +1,395 @@
+// cases.hpp -- stencil cases for the generic paths of stencil::b200, written once against (storage traits, backend) so
+// that the same case runs (a) on the device through st::b200<> (b200_regression.cu), (b) on the host through the
+// emulated CTAs of the fused path (fused_emulation.cpp) and (c) on the reference's cpu_ifirst backend, which is what
+// (a) and (b) are compared with.  The specs are those of functors.hpp (tag 1 = not bound to a named kernel) plus the
+// k-cache patterns of the reference's unit tests (tests/unit_tests/stencil/frontend/cartesian/test_kcache_fill.cpp,
+// test_kcache_flush.cpp, test_kcache_fill_and_flush.cpp, test_kcache_local.cpp: shifted sums through filled, flushed
+// and local register windows, forward and backward) and two mixed specs that exercise shared-memory tiles beside
+// plain temporaries and several elementary k intervals inside one parallel multi-stage.
+#pragma once
+
+#include <cmath>
+#include <cstdio>
+#include <functional>
+#include <string>
+
+#include <gridtools/stencil/cartesian.hpp>
+#include <gridtools/stencil/global_parameter.hpp>
+#include <gridtools/storage/builder.hpp>
+#include <gridtools/storage/sid.hpp>
+
+#include "functors.hpp"
+
+namespace cases {
+    namespace gt = gridtools;
+    namespace st = gridtools::stencil;
+    using namespace gridtools::stencil;
+    using namespace gridtools::stencil::cartesian;
+    using fun_t = std::function<double(int, int, int)>;
+
+    template <class Traits, class T>
+    auto make_store(int d0, int d1, int d2, int halo, fun_t f) {
+        return gt::storage::builder<Traits>.template type<T>().dimensions(d0, d1, d2).halos(halo, halo, 0)
+            .initializer([f](int i, int j, int k) { return T(f(i, j, k)); })
+            .build();
+    }
+
+    inline auto ij_halos(int d0, int d1, int halo) {
+        auto h = [&](int d) { return gt::halo_descriptor(halo, halo, halo, d - halo - 1, d); };
+        return std::make_pair(h(d0), h(d1));
+    }
+
+    // tests/include/verifier.hpp:26-52 on the whole storage (halo included: a backend must not touch it)
+    template <class A, class B>
+    bool same(const char *name, A const &a, B const &b, int d0, int d1, int d2, double tol, int &failed) {
+        auto va = a->const_host_view();
+        auto vb = b->const_host_view();
+        double worst = 0;
+        long bad = 0;
+        for (int k = 0; k < d2; ++k)
+            for (int j = 0; j < d1; ++j)
+                for (int i = 0; i < d0; ++i) {
+                    double x = va(i, j, k), y = vb(i, j, k);
+                    double d = std::fabs(x - y), s = std::fmax(std::fabs(x), std::fabs(y));
+                    double rel = s > 0 ? d / s : 0;
+                    if (tol == 0 ? x != y : !(d < tol || rel < tol))
+                        ++bad;
+                    if (rel > worst)
+                        worst = rel;
+                }
+        std::printf("%-58s %s (mismatches %ld, worst rel %.3g)\n", name, bad ? "FAILED" : "ok", bad, worst);
+        if (bad)
+            ++failed;
+        return bad == 0;
+    }
+
+    // ------------------------------------------------------------------ specs of functors.hpp
+    template <class T, class Traits, class Backend>
+    auto hori_diff(Traits, Backend backend, int ni, int nj, int nk) {
+        constexpr int H = 2;
+        const int d0 = ni + 2 * H, d1 = nj + 2 * H;
+        fun_t in_f = [=](int i, int j, int k) {
+            double x = 1. * i / d0, y = 1. * j / d1;
+            return 5. + 8 * (2. + std::cos(M_PI * (x + 1.5 * y)) + std::sin(2 * M_PI * (x + 1.5 * y))) / 4. + 0.02 * k;
+        };
+        auto hh = ij_halos(d0, d1, H);
+        auto grid = st::make_grid(hh.first, hh.second, st::axis<1>(nk));
+        auto in = make_store<Traits, T const>(d0, d1, nk, H, in_f);
+        auto co = make_store<Traits, T const>(d0, d1, nk, H, [](int i, int j, int) { return 0.025 + 1e-4 * ((i + j) % 5); });
+        auto out = make_store<Traits, T>(d0, d1, nk, H, [](int, int, int) { return -1.; });
+        st::run(user::hori_diff_spec<T, 1>(), backend, grid, in, co, out);
+        return out;
+    }
+
+    template <class T, class Traits, class Backend>
+    auto simple_hori_diff(Traits, Backend backend, int ni, int nj, int nk) {
+        constexpr int H = 2;
+        const int d0 = ni + 2 * H, d1 = nj + 2 * H;
+        fun_t in_f = [=](int i, int j, int k) {
+            double x = 1. * i / d0, y = 1. * j / d1;
+            return 5. + 8 * (2. + std::cos(M_PI * (x + 1.5 * y)) + std::sin(2 * M_PI * (x + 1.5 * y))) / 4. + 0.01 * k;
+        };
+        auto hh = ij_halos(d0, d1, H);
+        auto grid = st::make_grid(hh.first, hh.second, st::axis<1>(nk));
+        auto in = make_store<Traits, T const>(d0, d1, nk, H, in_f);
+        auto co = make_store<Traits, T const>(d0, d1, nk, H, [](int i, int j, int) { return 0.025 + 1e-4 * ((i + j) % 5); });
+        auto out = make_store<Traits, T>(d0, d1, nk, H, [](int, int, int) { return 0.; });
+        auto jb = gt::storage::builder<Traits>.template type<T const>().dimensions(d0, d1, nk).halos(H, H, 0)
+                      .template selector<0, 1, 0>();
+        auto cro = jb.initializer([=](int, int j, int) { return T(1. + 0.3 * std::cos(3. * j / d1)); }).build();
+        auto cru = jb.initializer([=](int, int j, int) { return T(j == 0 ? 0. : 1. - 0.2 * std::sin(2. * j / d1)); }).build();
+        st::run(user::simple_hori_diff_spec<T, 1>(), backend, grid, co, in, out, cro, cru);
+        return out;
+    }
+
+    template <class T, class Traits, class Backend>
+    auto vert_adv(Traits, Backend backend, int ni, int nj, int nk) {
+        constexpr int H = 3;
+        const int d0 = ni + 2 * H, d1 = nj + 2 * H;
+        auto x = [=](int i) { return 1. * i / d0; };
+        auto y = [=](int j) { return 1. * j / d1; };
+        auto z = [=](int k) { return 1. * k / nk; };
+        fun_t u_stage_f = [=](int i, int j, int) {
+            double t = x(i) + y(j);
+            return 7 + std::cos(M_PI * t) + std::sin(2 * M_PI * t);
+        };
+        fun_t wcon_f = [=](int i, int j, int k) {
+            return 2e-4 * (-1.07 + (2 + std::cos(M_PI * (x(i) + z(k))) + std::cos(M_PI * y(j))) / 2);
+        };
+        fun_t utens_f = [=](int i, int j, int k) {
+            return 3e-6 * (-1.0235 + (2. + std::cos(M_PI * (x(i) + y(j))) + std::cos(M_PI * y(j) * z(k))) / 2);
+        };
+        fun_t utens_stage_f = [=](int i, int j, int k) {
+            double t = x(i) + y(j);
+            return 7 + 1.25 * (2. + std::cos(M_PI * t) + std::sin(2 * M_PI * t)) + .1 * k;
+        };
+        auto hh = ij_halos(d0, d1, H);
+        auto grid = st::make_grid(hh.first, hh.second, user::va_axis_t(nk));
+        auto utens_stage = make_store<Traits, T>(d0, d1, nk, H, utens_stage_f);
+        auto u_stage = make_store<Traits, T>(d0, d1, nk, H, u_stage_f);
+        auto wcon = make_store<Traits, T>(d0, d1, nk, H, wcon_f);
+        auto u_pos = make_store<Traits, T>(d0, d1, nk, H, u_stage_f);
+        auto utens = make_store<Traits, T>(d0, d1, nk, H, utens_f);
+        st::run(user::vert_adv_spec<T, 1>(), backend, grid, utens_stage, u_stage, wcon, u_pos, utens,
+            st::global_parameter(T(3. / 20.)));
+        return utens_stage;
+    }
+
+    template <class Traits, class Backend>
+    auto tridiagonal(Traits, Backend backend, int ni, int nj, int nk) {
+        constexpr int H = 0;
+        auto hh = ij_halos(ni, nj, H);
+        auto grid = st::make_grid(hh.first, hh.second, user::td_axis_t(nk));
+        auto mk = [&](fun_t f) { return make_store<Traits, double>(ni, nj, nk, H, f); };
+        auto out = mk([](int, int, int) { return 0.; });
+        st::run(user::tridiagonal_spec<1>(), backend, grid, mk([](int, int, int) { return -1.; }),
+            mk([](int, int, int) { return 3.; }), mk([](int, int, int) { return 1.; }),
+            mk([=](int i, int, int k) { return (k == 0 ? 4. : k == nk - 1 ? 2. : 3.) + 1e-3 * i; }), out);
+        return out;
+    }
+
+    // ------------------------------------------------------------------ k-cache patterns
+    using kc_axis_t = st::axis<1, st::axis_config::offset_limit<3>>;
+    using kc_full_t = kc_axis_t::full_interval;
+
+    inline double ramp(int i, int j, int k) { return 1 + i + 0.5 * j + 0.25 * k * k; }
+
+    // out(k) = in(k-1) + in(k) + in(k+1), clipped at both ends: a filled window [-1, 1]
+    struct shifted_sum_f {
+        using in = in_accessor<0, extent<0, 0, 0, 0, -1, 1>>;
+        using out = inout_accessor<1>;
+        using param_list = make_param_list<in, out>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval, kc_full_t::first_level) {
+            eval(out()) = eval(in()) + eval(in(0, 0, 1));
+        }
+        template <class E>
+        GT_FUNCTION static void apply(E eval, kc_full_t::modify<1, -1>) {
+            eval(out()) = eval(in(0, 0, -1)) + eval(in()) + eval(in(0, 0, 1));
+        }
+        template <class E>
+        GT_FUNCTION static void apply(E eval, kc_full_t::last_level) {
+            eval(out()) = eval(in(0, 0, -1)) + eval(in());
+        }
+    };
+    template <class Execute, class Traits, class Backend>
+    auto kcache_fill(Execute execute, Traits, Backend backend, int ni, int nj, int nk) {
+        auto hh = ij_halos(ni, nj, 0);
+        auto grid = st::make_grid(hh.first, hh.second, kc_axis_t(nk));
+        auto in = make_store<Traits, double>(ni, nj, nk, 0, ramp);
+        auto out = make_store<Traits, double>(ni, nj, nk, 0, [](int, int, int) { return -7.; });
+        st::run(
+            [=](auto in, auto out) {
+                return execute().k_cached(st::cache_io_policy::fill(), in).stage(shifted_sum_f(), in, out);
+            },
+            backend, grid, in, out);
+        return out;
+    }
+
+    // running sums through a flushed window: forward out(k) = out(k-1) + in(k), backward out(k) = out(k+1) + in(k)
+    struct prefix_sum_f {
+        using in = in_accessor<0>;
+        using out = inout_accessor<1, extent<0, 0, 0, 0, -1, 0>>;
+        using param_list = make_param_list<in, out>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval, kc_full_t::first_level) {
+            eval(out()) = eval(in());
+        }
+        template <class E>
+        GT_FUNCTION static void apply(E eval, kc_full_t::modify<1, 0>) {
+            eval(out()) = eval(out(0, 0, -1)) + eval(in());
+        }
+    };
+    struct suffix_sum_f {
+        using in = in_accessor<0>;
+        using out = inout_accessor<1, extent<0, 0, 0, 0, 0, 1>>;
+        using param_list = make_param_list<in, out>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval, kc_full_t::last_level) {
+            eval(out()) = eval(in());
+        }
+        template <class E>
+        GT_FUNCTION static void apply(E eval, kc_full_t::modify<0, -1>) {
+            eval(out()) = eval(out(0, 0, 1)) + eval(in());
+        }
+    };
+    template <class Traits, class Backend>
+    auto kcache_flush(bool forward, Traits, Backend backend, int ni, int nj, int nk) {
+        auto hh = ij_halos(ni, nj, 0);
+        auto grid = st::make_grid(hh.first, hh.second, kc_axis_t(nk));
+        auto in = make_store<Traits, double>(ni, nj, nk, 0, ramp);
+        auto out = make_store<Traits, double>(ni, nj, nk, 0, [](int, int, int) { return -7.; });
+        if (forward)
+            st::run(
+                [](auto in, auto out) {
+                    return st::execute_forward().k_cached(st::cache_io_policy::flush(), out).stage(prefix_sum_f(), in, out);
+                },
+                backend, grid, in, out);
+        else
+            st::run(
+                [](auto in, auto out) {
+                    return st::execute_backward().k_cached(st::cache_io_policy::flush(), out).stage(suffix_sum_f(), in, out);
+                },
+                backend, grid, in, out);
+        return out;
+    }
+
+    // in-place running sums: the same field filled and flushed
+    struct inplace_prefix_f {
+        using f = inout_accessor<0, extent<0, 0, 0, 0, -1, 0>>;
+        using param_list = make_param_list<f>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval, kc_full_t::first_level) {
+            eval(f()) = eval(f());
+        }
+        template <class E>
+        GT_FUNCTION static void apply(E eval, kc_full_t::modify<1, 0>) {
+            eval(f()) = eval(f()) + eval(f(0, 0, -1));
+        }
+    };
+    struct inplace_suffix_f {
+        using f = inout_accessor<0, extent<0, 0, 0, 0, 0, 1>>;
+        using param_list = make_param_list<f>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval, kc_full_t::last_level) {
+            eval(f()) = eval(f());
+        }
+        template <class E>
+        GT_FUNCTION static void apply(E eval, kc_full_t::modify<0, -1>) {
+            eval(f()) = eval(f()) + eval(f(0, 0, 1));
+        }
+    };
+    template <class Traits, class Backend>
+    auto kcache_fill_and_flush(bool forward, Traits, Backend backend, int ni, int nj, int nk) {
+        auto hh = ij_halos(ni, nj, 0);
+        auto grid = st::make_grid(hh.first, hh.second, kc_axis_t(nk));
+        auto field = make_store<Traits, double>(ni, nj, nk, 0, ramp);
+        if (forward)
+            st::run(
+                [](auto f) {
+                    return st::execute_forward()
+                        .k_cached(st::cache_io_policy::fill(), st::cache_io_policy::flush(), f)
+                        .stage(inplace_prefix_f(), f);
+                },
+                backend, grid, field);
+        else
+            st::run(
+                [](auto f) {
+                    return st::execute_backward()
+                        .k_cached(st::cache_io_policy::fill(), st::cache_io_policy::flush(), f)
+                        .stage(inplace_suffix_f(), f);
+                },
+                backend, grid, field);
+        return field;
+    }
+
+    // a local window (temporary, no policy) carried through two stages of one sweep
+    struct carry_f {
+        using in = in_accessor<0>;
+        using acc = inout_accessor<1, extent<0, 0, 0, 0, -1, 0>>;
+        using param_list = make_param_list<in, acc>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval, kc_full_t::first_level) {
+            eval(acc()) = eval(in());
+        }
+        template <class E>
+        GT_FUNCTION static void apply(E eval, kc_full_t::modify<1, 0>) {
+            eval(acc()) = 0.5 * eval(acc(0, 0, -1)) + eval(in());
+        }
+    };
+    struct emit_f {
+        using acc = in_accessor<0, extent<0, 0, 0, 0, -1, 0>>;
+        using out = inout_accessor<1>;
+        using param_list = make_param_list<acc, out>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval, kc_full_t::first_level) {
+            eval(out()) = eval(acc());
+        }
+        template <class E>
+        GT_FUNCTION static void apply(E eval, kc_full_t::modify<1, 0>) {
+            eval(out()) = eval(acc()) - eval(acc(0, 0, -1));
+        }
+    };
+    template <class Traits, class Backend>
+    auto kcache_local(Traits, Backend backend, int ni, int nj, int nk) {
+        auto hh = ij_halos(ni, nj, 0);
+        auto grid = st::make_grid(hh.first, hh.second, kc_axis_t(nk));
+        auto in = make_store<Traits, double>(ni, nj, nk, 0, ramp);
+        auto out = make_store<Traits, double>(ni, nj, nk, 0, [](int, int, int) { return -7.; });
+        st::run(
+            [](auto in, auto out) {
+                GT_DECLARE_TMP(double, acc);
+                return st::execute_forward().k_cached(acc).stage(carry_f(), in, acc).stage(emit_f(), acc, out);
+            },
+            backend, grid, in, out);
+        return out;
+    }
+
+    // ------------------------------------------------------------------ mixed parallel multi-stage
+    // two elementary intervals with different functors, an ij-cached temporary read at IJ offsets and a plain
+    // temporary read at offset zero, followed by a second multi-stage that reads the plain temporary again
+    using mx_axis_t = st::axis<2>;
+    struct grad_f {
+        using out = inout_accessor<0>;
+        using in = in_accessor<1, extent<-1, 1, -1, 1>>;
+        using param_list = make_param_list<out, in>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval, mx_axis_t::get_interval<0>) {
+            eval(out()) = eval(in(1, 0)) - eval(in(-1, 0));
+        }
+        template <class E>
+        GT_FUNCTION static void apply(E eval, mx_axis_t::get_interval<1>) {
+            eval(out()) = eval(in(0, 1)) - eval(in(0, -1));
+        }
+    };
+    struct smooth_f {
+        using out = inout_accessor<0>;
+        using g = in_accessor<1, extent<-1, 1, -1, 1>>;
+        using param_list = make_param_list<out, g>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval) {
+            eval(out()) = 0.25 * (eval(g(-1, 0)) + eval(g(1, 0)) + eval(g(0, -1)) + eval(g(0, 1)));
+        }
+    };
+    struct combine_f {
+        using out = inout_accessor<0>;
+        using a = in_accessor<1>;
+        using in = in_accessor<2>;
+        using param_list = make_param_list<out, a, in>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval) {
+            eval(out()) = eval(in()) + 2 * eval(a());
+        }
+    };
+    struct add_f {
+        using out = inout_accessor<0>;
+        using a = in_accessor<1>;
+        using param_list = make_param_list<out, a>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval) {
+            eval(out()) = eval(out()) + eval(a());
+        }
+    };
+    template <class T, class Traits, class Backend>
+    auto mixed(Traits, Backend backend, int ni, int nj, int nk0, int nk1) {
+        constexpr int H = 2;
+        const int d0 = ni + 2 * H, d1 = nj + 2 * H, nk = nk0 + nk1;
+        auto hh = ij_halos(d0, d1, H);
+        auto grid = st::make_grid(hh.first, hh.second, mx_axis_t(nk0, nk1));
+        auto in = make_store<Traits, T>(
+            d0, d1, nk, H, [](int i, int j, int k) { return std::sin(0.3 * i) + std::cos(0.2 * j) * (1 + 0.1 * k); });
+        auto out = make_store<Traits, T>(d0, d1, nk, H, [](int, int, int) { return -3.; });
+        st::run(
+            [](auto in, auto out) {
+                GT_DECLARE_TMP(T, g, s);
+                return st::multi_pass(st::execute_parallel()
+                                          .ij_cached(g)
+                                          .stage(grad_f(), g, in)
+                                          .stage(smooth_f(), s, g)
+                                          .stage(combine_f(), out, s, in),
+                    st::execute_parallel().stage(add_f(), out, s));
+            },
+            backend, grid, in, out);
+        return out;
+    }
+} // namespace cases

@@ -1,0 +1,81 @@
+// emulated_cta.hpp -- TEST INFRASTRUCTURE: runs the per-thread body of the fused generic path
+// (include/gtb200/stencil/b200_fused.hpp) on the host, one OpenMP team per CTA, `#pragma omp barrier` standing in for
+// `__syncthreads` and a heap buffer for the CTA's shared memory.  It exists so that the thread-to-point mapping, the
+// shared-memory tiles, the register windows and their fill / flush can be pinned against the reference's cpu_ifirst
+// backend in the build container, which has no GPU.  Nothing under include/ or gridtools_b200/ refers to it.
+#pragma once
+
+#include <memory>
+#include <vector>
+
+#include <omp.h>
+
+#include <gridtools/sid/allocator.hpp>
+#include <gtb200/stencil/b200_fused.hpp>
+
+namespace emulated {
+    using gridtools::int_t;
+
+    struct state {
+        int_t block[3];
+        char *smem;
+    };
+    inline state &cta_state() {
+        static state s{};
+        return s;
+    }
+
+    struct cta {
+        static int_t tid() { return omp_get_thread_num(); }
+        static int_t block_i() { return cta_state().block[0]; }
+        static int_t block_j() { return cta_state().block[1]; }
+        static int_t block_k() { return cta_state().block[2]; }
+        static void sync() {
+#pragma omp barrier
+        }
+        static char *smem() { return cta_state().smem; }
+    };
+
+    struct launcher {
+        using cta_t = cta;
+        long launches = 0, syncs_possible = 0;
+
+        static auto allocator() { return gridtools::sid::cached_allocator(&std::make_unique<char[]>); }
+
+        template <class Body>
+        void launch(Body const &body, int_t nbi, int_t nbj, int_t nbk, int_t threads, int_t smem) {
+            ++launches;
+            std::vector<char> shared(smem + 16);
+            omp_set_dynamic(0);
+            for (int_t bk = 0; bk < nbk; ++bk)
+                for (int_t bj = 0; bj < nbj; ++bj)
+                    for (int_t bi = 0; bi < nbi; ++bi) {
+                        cta_state() = {{bi, bj, bk}, shared.data()};
+                        // poison the tiles: nothing may be read that this CTA did not write
+                        for (auto &c : shared)
+                            c = char(0xff);
+#pragma omp parallel num_threads(threads)
+                        {
+                            if (omp_get_num_threads() != threads)
+                                std::abort();
+                            body();
+                        }
+                    }
+        }
+    };
+
+    /// backend tag: the fused path of stencil::b200, executed by the emulated CTAs
+    template <class Geo = gridtools::stencil::b200_backend::fused::geometry<>>
+    struct backend {
+        template <class Spec, class Grid, class DataStores>
+        friend void gridtools_backend_entry_point(backend, Spec spec, Grid const &grid, DataStores data_stores) {
+            launcher l;
+            gridtools::stencil::b200_backend::fused::run<Geo>(l, spec, grid, std::move(data_stores));
+            last_launches() = l.launches;
+        }
+        static long &last_launches() {
+            static long n = 0;
+            return n;
+        }
+    };
+} // namespace emulated

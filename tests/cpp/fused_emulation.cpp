@@ -1,0 +1,122 @@
+// fused_emulation.cpp -- TEST: the per-thread body of stencil::b200's fused generic path
+// (include/gtb200/stencil/b200_fused.hpp), executed on the host by emulated CTAs (emulated_cta.hpp), against the
+// reference's cpu_ifirst backend on the same inputs.  Plain g++ (-fopenmp), no GPU, no CUDA headers:
+//
+//   g++ -std=c++17 -O1 -fopenmp -I/root/reference/include -I include tests/cpp/fused_emulation.cpp
+//
+// prints one line per case and "ALL PASSED" / "FAILED"; exit code 0 / 1.
+#include <cstdio>
+#include <string>
+
+#include <gridtools/stencil/cartesian.hpp>
+#include <gridtools/stencil/cpu_ifirst.hpp>
+#include <gridtools/storage/cpu_ifirst.hpp>
+#include <gridtools/storage/cpu_kfirst.hpp>
+
+#include "cases.hpp"
+#include "emulated_cta.hpp"
+
+namespace {
+    namespace gt = gridtools;
+    namespace st = gridtools::stencil;
+    namespace fused = gridtools::stencil::b200_backend::fused;
+
+    int g_failed = 0;
+
+    template <class Geo>
+    struct run {
+        using be_t = emulated::backend<Geo>;
+        using ref_t = st::cpu_ifirst<>;
+        // cpu_kfirst storage has i-stride 1 like storage::gpu
+        using traits_t = gt::storage::cpu_kfirst;
+        std::string m_geo;
+
+        void expect_launches(const char *what, long n) {
+            if (be_t::last_launches() != n) {
+                std::printf("%-58s FAILED (%ld launches, expected %ld)\n", what, be_t::last_launches(), n);
+                ++g_failed;
+            }
+        }
+        std::string name(std::string what, int ni, int nj, int nk) {
+            return what + " " + std::to_string(ni) + "x" + std::to_string(nj) + "x" + std::to_string(nk) + " " + m_geo;
+        }
+
+        void all(int ni, int nj, int nk) {
+            auto fwd = [] { return st::execute_forward(); };
+            auto bwd = [] { return st::execute_backward(); };
+            traits_t tr;
+            {
+                auto got = cases::hori_diff<double>(tr, be_t(), ni, nj, nk);
+                expect_launches("hori_diff launches", 1);
+                auto ref = cases::hori_diff<double>(tr, ref_t(), ni, nj, nk);
+                cases::same(name("hori_diff f64", ni, nj, nk).c_str(), got, ref, ni + 4, nj + 4, nk, 1e-13, g_failed);
+            }
+            {
+                auto got = cases::hori_diff<float>(tr, be_t(), ni, nj, 3);
+                auto ref = cases::hori_diff<float>(tr, ref_t(), ni, nj, 3);
+                cases::same(name("hori_diff f32", ni, nj, 3).c_str(), got, ref, ni + 4, nj + 4, 3, 1e-5, g_failed);
+            }
+            {
+                auto got = cases::simple_hori_diff<double>(tr, be_t(), ni, nj, nk);
+                expect_launches("simple_hori_diff launches", 1);
+                auto ref = cases::simple_hori_diff<double>(tr, ref_t(), ni, nj, nk);
+                cases::same(name("simple_hori_diff f64", ni, nj, nk).c_str(), got, ref, ni + 4, nj + 4, nk, 1e-13, g_failed);
+            }
+            {
+                auto got = cases::vert_adv<double>(tr, be_t(), ni, nj, nk + 4);
+                expect_launches("vert_adv launches", 2);
+                auto ref = cases::vert_adv<double>(tr, ref_t(), ni, nj, nk + 4);
+                cases::same(name("vert_adv f64", ni, nj, nk + 4).c_str(), got, ref, ni + 6, nj + 6, nk + 4, 1e-12, g_failed);
+            }
+            {
+                auto got = cases::tridiagonal(tr, be_t(), ni, nj, 6);
+                expect_launches("tridiagonal launches", 2);
+                auto ref = cases::tridiagonal(tr, ref_t(), ni, nj, 6);
+                cases::same(name("tridiagonal", ni, nj, 6).c_str(), got, ref, ni, nj, 6, 1e-13, g_failed);
+            }
+            {
+                auto got = cases::kcache_fill(fwd, tr, be_t(), ni, nj, nk);
+                auto ref = cases::kcache_fill(fwd, tr, ref_t(), ni, nj, nk);
+                cases::same(name("k-cache fill forward", ni, nj, nk).c_str(), got, ref, ni, nj, nk, 0, g_failed);
+                got = cases::kcache_fill(bwd, tr, be_t(), ni, nj, nk);
+                ref = cases::kcache_fill(bwd, tr, ref_t(), ni, nj, nk);
+                cases::same(name("k-cache fill backward", ni, nj, nk).c_str(), got, ref, ni, nj, nk, 0, g_failed);
+            }
+            for (bool forward : {true, false}) {
+                auto got = cases::kcache_flush(forward, tr, be_t(), ni, nj, nk);
+                auto ref = cases::kcache_flush(forward, tr, ref_t(), ni, nj, nk);
+                cases::same(name(forward ? "k-cache flush forward" : "k-cache flush backward", ni, nj, nk).c_str(), got,
+                    ref, ni, nj, nk, 0, g_failed);
+                got = cases::kcache_fill_and_flush(forward, tr, be_t(), ni, nj, nk);
+                ref = cases::kcache_fill_and_flush(forward, tr, ref_t(), ni, nj, nk);
+                cases::same(
+                    name(forward ? "k-cache fill+flush forward" : "k-cache fill+flush backward", ni, nj, nk).c_str(),
+                    got, ref, ni, nj, nk, 0, g_failed);
+            }
+            {
+                auto got = cases::kcache_local(tr, be_t(), ni, nj, nk);
+                expect_launches("k-cache local launches", 1);
+                auto ref = cases::kcache_local(tr, ref_t(), ni, nj, nk);
+                cases::same(name("k-cache local, two stages", ni, nj, nk).c_str(), got, ref, ni, nj, nk, 0, g_failed);
+            }
+            {
+                auto got = cases::mixed<double>(tr, be_t(), ni, nj, 2, nk);
+                expect_launches("mixed launches", 2);
+                auto ref = cases::mixed<double>(tr, ref_t(), ni, nj, 2, nk);
+                cases::same(name("mixed tiles + plain temporaries, 2 intervals", ni, nj, nk + 2).c_str(), got, ref,
+                    ni + 4, nj + 4, nk + 2, 1e-13, g_failed);
+            }
+        }
+    };
+} // namespace
+
+int main() {
+    // small blocks: many CTAs, partial tiles in i and j, partial k blocks
+    run<fused::geometry<8, 4, 3>>{"[8x4x3 blocks]"}.all(19, 9, 7);
+    run<fused::geometry<8, 4, 3>>{"[8x4x3 blocks]"}.all(8, 4, 3);
+    run<fused::geometry<8, 4, 3>>{"[8x4x3 blocks]"}.all(1, 1, 2);
+    // the default geometry on a domain of a few blocks
+    run<fused::geometry<>>{"[32x8x8 blocks]"}.all(37, 11, 10);
+    std::printf(g_failed ? "FAILED (%d)\n" : "ALL PASSED\n", g_failed);
+    return g_failed ? 1 : 0;
+}

@@ -62,11 +62,11 @@ namespace {
     }
 
     void report(const char *stencil, const char *backend, double us, double pts, double bytes_per_pt) {
-        std::printf("%-28s %-14s %9.2f us/run %10.0f Mpts/s %8.0f GB/s algorithmic\n", stencil, backend, us, pts / us,
+        std::printf("%-28s %-24s %9.2f us/run %10.0f Mpts/s %8.0f GB/s algorithmic\n", stencil, backend, us, pts / us,
             pts * bytes_per_pt / us / 1e3);
     }
 
-    template <class Backend>
+    template <int Tag, class Backend>
     void hori_diff(const char *name, Backend backend, int ni, int nj, int nk) {
         constexpr int H = 2, SETS = 3;
         const int d0 = ni + 2 * H, d1 = nj + 2 * H;
@@ -82,7 +82,6 @@ namespace {
                 make_store<double>(d0, d1, nk, H, [](int, int, int) { return 0.; }));
         };
         auto s0 = make_set(), s1 = make_set(), s2 = make_set();
-        constexpr int Tag = std::is_same<Backend, st::b200<>>::value ? 0 : 1;
         auto call = [&](auto &f) {
             st::run(user::hori_diff_spec<double, Tag>(), backend, grid, std::get<0>(f), std::get<1>(f), std::get<2>(f));
         };
@@ -90,7 +89,7 @@ namespace {
         report("horizontal_diffusion", name, us, 1. * ni * nj * nk, 24);
     }
 
-    template <class Backend>
+    template <int Tag, class Backend>
     void vert_adv(const char *name, Backend backend, int ni, int nj, int nk) {
         constexpr int H = 3, SETS = 2;
         const int d0 = ni + 2 * H, d1 = nj + 2 * H;
@@ -119,7 +118,6 @@ namespace {
                 make_store<double>(d0, d1, nk, H, utens_f));
         };
         auto s0 = make_set(), s1 = make_set();
-        constexpr int Tag = std::is_same<Backend, st::b200<>>::value ? 0 : 1;
         const double dtr = 3. / 20.;
         auto call = [&](auto &f) {
             st::run(user::vert_adv_spec<double, Tag>(), backend, grid, std::get<0>(f), std::get<1>(f), std::get<2>(f),
@@ -128,6 +126,8 @@ namespace {
         double t = time_us([&](int s) { s == 0 ? call(s0) : call(s1); }, SETS);
         report("vertical_advection_dycore", name, t, 1. * ni * nj * nk, 48);
     }
+    template <int BI, int BJ, int KB>
+    using fused_t = st::b200<gtb200::default_stream, gtb200::fused_when_possible, gtb200::block_geometry<BI, BJ, KB>>;
 } // namespace
 
 int main(int argc, char **argv) {
@@ -135,10 +135,22 @@ int main(int argc, char **argv) {
               nk = argc > 3 ? std::atoi(argv[3]) : 80;
     try {
         std::printf("# %dx%dx%d fp64, CUDA events around 200 runs, rotating field sets\n", ni, nj, nk);
-        hori_diff("stencil::gpu<>", st::gpu<>(), ni, nj, nk);
-        hori_diff("stencil::b200<>", st::b200<>(), ni, nj, nk);
-        vert_adv("stencil::gpu<>", st::gpu<>(), ni, nj, nk);
-        vert_adv("stencil::b200<>", st::b200<>(), ni, nj, nk);
+        // tag 0 functors are bound to the named kernels, tag 1 functors are not: generic paths of the same tag
+        using staged_t = st::b200<gtb200::default_stream, gtb200::stage_by_stage>;
+        hori_diff<1>("stencil::gpu<>", st::gpu<>(), ni, nj, nk);
+        hori_diff<0>("stencil::b200<> named", st::b200<>(), ni, nj, nk);
+        hori_diff<1>("b200 fused 32x8x8", st::b200<>(), ni, nj, nk);
+        hori_diff<1>("b200 fused 64x4x8", fused_t<64, 4, 8>(), ni, nj, nk);
+        hori_diff<1>("b200 fused 32x16x4", fused_t<32, 16, 4>(), ni, nj, nk);
+        hori_diff<1>("b200 fused 64x8x2", fused_t<64, 8, 2>(), ni, nj, nk);
+        hori_diff<1>("b200 stage by stage", staged_t(), ni, nj, nk);
+        vert_adv<1>("stencil::gpu<>", st::gpu<>(), ni, nj, nk);
+        vert_adv<0>("stencil::b200<> named", st::b200<>(), ni, nj, nk);
+        vert_adv<1>("b200 fused 32x8", st::b200<>(), ni, nj, nk);
+        vert_adv<1>("b200 fused 32x4", fused_t<32, 4, 8>(), ni, nj, nk);
+        vert_adv<1>("b200 fused 32x2", fused_t<32, 2, 8>(), ni, nj, nk);
+        vert_adv<1>("b200 fused 64x1", fused_t<64, 1, 8>(), ni, nj, nk);
+        vert_adv<1>("b200 stage by stage", staged_t(), ni, nj, nk);
     } catch (std::exception const &e) {
         std::printf("EXCEPTION: %s\n", e.what());
         return 2;
