@@ -86,9 +86,9 @@ namespace gtb200 {
     struct stage_by_stage {};
 #ifdef __CUDACC__
     /// IJ block and levels per CTA of the fused generic path (third template argument of stencil::b200).
-    template <int BI, int BJ, int KB>
-    using block_geometry = ::gridtools::stencil::b200_backend::fused::geometry<BI, BJ, KB>;
-    using default_geometry = block_geometry<32, 8, 8>;
+    template <int BI, int BJ, int KB, int SweepUnroll = 2, bool ChainSweeps = true>
+    using block_geometry = ::gridtools::stencil::b200_backend::fused::geometry<BI, BJ, KB, SweepUnroll, ChainSweeps>;
+    using default_geometry = ::gridtools::stencil::b200_backend::fused::geometry<>;
 #else
     struct default_geometry {};
 #endif

@@ -21,10 +21,11 @@
  *       part of the sweep itself and are checked at run time against the k bounds of the field: on the first level
  *       of the sweep the whole window is filled, afterwards the entry that slides in; every level flushes the entry
  *       that slides out, the last level the whole window.  Same values in the same places, no spec surgery.
- *   a7  temporaries that are neither ij- nor k-cached live in device memory (whole domain).  A spec whose non-cached
- *       temporaries are read at IJ offsets would need CTA-private blocked copies (gpu/tmp_storage_sid.hpp:54-69);
- *       such specs -- and sweeps with IJ extents, and k caches in parallel multi-stages -- are not `fusable` and take
- *       the stage-by-stage path of b200.hpp instead.
+ *   a7  temporaries that are neither ij- nor k-cached live in device memory: one whole-domain array when they are only
+ *       read at IJ offset zero, CTA-private halo-extended blocks when they are read at IJ offsets
+ *       (gpu/tmp_storage_sid.hpp:54-69), so that no CTA reads what another one writes.
+ *   Not `fusable` (they take the stage-by-stage path of b200.hpp): sweeps with IJ extents and k caches in parallel
+ *   multi-stages.  Consecutive forward / backward multi-stages share ONE launch (body_chain).
  *
  * Everything here is written against a `Cta` policy (block / thread indices, barrier, shared-memory base): `cuda_cta`
  * is the product; tests/cpp/emulated_cta.hpp runs the very same body on the host, one OpenMP team per CTA, to pin
@@ -65,9 +66,16 @@ namespace gridtools {
         namespace b200_backend {
             namespace fused {
                 // ---------------------------------------------------------------- geometry
-                template <int_t BI = 32, int_t BJ = 8, int_t KB = 8>
+                // IJ block of a CTA, levels per CTA of a parallel multi-stage, unroll factor of the level loop of a sweep.
+                // Defaults from profiles/r01_fused_generic.txt (256x256x80 fp64): hori_diff 32x8x8 53.0 us, 64x4x8
+                // 61.5, 32x16x8 51.2, 80 levels per CTA 96.2; vert_adv unroll 1 / 2 / 4: 167.9 / 115.6 / 143.8 us.
+                // ChainSweeps: consecutive forward / backward multi-stages in one launch (body_chain) -- what one of them
+                // writes is then read with coherent loads by the next -- or one launch each, every field a multi-stage
+                // only reads on the read-only path.
+                template <int_t BI = 32, int_t BJ = 8, int_t KB = 8, int_t SweepUnroll = 2, bool ChainSweeps = true>
                 struct geometry {
-                    static constexpr int_t bi = BI, bj = BJ, kb = KB;
+                    static constexpr int_t bi = BI, bj = BJ, kb = KB, sweep_unroll = SweepUnroll;
+                    static constexpr bool chain_sweeps = ChainSweeps;
                 };
 
                 template <class Extent>
@@ -103,13 +111,8 @@ namespace gridtools {
                         ? !meta::any_of<is_k_cached, typename Mss::plh_map_t>::value
                         : !has_ij_extent<typename Mss::extent_t>::value>;
 
-                template <class Info>
-                using tmp_is_fusable =
-                    std::bool_constant<!needs_memory<Info>::value || !has_ij_extent<typename Info::extent_t>::value>;
-
                 template <class Spec, class Msses = be_api::make_fused_view<Spec>>
-                using fusable = std::bool_constant<meta::all_of<mss_is_fusable, meta::rename<meta::list, Msses>>::value &&
-                                                   meta::all_of<tmp_is_fusable, typename Msses::tmp_plh_map_t>::value>;
+                using fusable = meta::all_of<mss_is_fusable, meta::rename<meta::list, Msses>>;
 
                 // ---------------------------------------------------------------- shared-memory tiles (ij caches)
                 template <class T, class Cta>
@@ -207,15 +210,26 @@ namespace gridtools {
                 };
 
                 // ---------------------------------------------------------------- per-thread body of one multi-stage
-                template <class Cta, class Mss, class Geo, class Holder, class Strides, class KSizes, class Bounds>
+                // `Volatile`: placeholders written somewhere in the same launch (see body_chain), never read-only loaded
+                template <class Cta,
+                    class Mss,
+                    class Geo,
+                    class Volatile,
+                    class Holder,
+                    class Strides,
+                    class KSizes,
+                    class Bounds>
                 struct mss_body {
+                    using cta_t = Cta;
                     using extent_t = typename Mss::extent_t;
                     using plh_map_t = typename Mss::plh_map_t;
                     using k_cached_t = meta::filter<is_k_cached, plh_map_t>;
                     using io_cached_t = meta::filter<is_io_cached, plh_map_t>;
                     using step_t = typename Mss::k_step_t;
-                    using deref_t = read_only_deref<
-                        meta::transform<be_api::get_key, meta::filter<be_api::get_is_const, plh_map_t>>>;
+                    template <class Info>
+                    using is_read_only = std::bool_constant<Info::is_const_t::value &&
+                                                            !meta::st_contains<Volatile, typename Info::plh_t>::value>;
+                    using deref_t = read_only_deref<meta::transform<be_api::get_key, meta::filter<is_read_only, plh_map_t>>>;
 
                     static constexpr bool parallel = be_api::is_parallel<typename Mss::execution_t>::value;
                     static constexpr int_t imin = extent_t::iminus::value, jmin = extent_t::jminus::value;
@@ -360,6 +374,7 @@ namespace gridtools {
                         int_t n = 0, k_pos = m_k_first;
                         tuple_util::host_device::for_each(
                             [&](int_t size, auto info) GT_FORCE_INLINE_LAMBDA {
+#pragma unroll(Geo::sweep_unroll)
                                 for (int_t k = 0; k < size; ++k) {
                                     if (on)
                                         sync_caches<true>(windows, mixed.secondary(), k_pos, n == 0);
@@ -378,6 +393,76 @@ namespace gridtools {
                     }
                 };
 
+                // ---------------------------------------------------------------- consecutive sweeps in one launch
+                // Forward / backward multi-stages that follow each other are column-local on both sides (no IJ extents,
+                // one thread per column), so they run back to back inside one kernel: what the first leaves in device
+                // memory (flushed k caches, plain temporaries) is read again by the thread that wrote it.  This is the
+                // case the reference fuses with launch_or_fuse (gpu/entry_point.hpp:97-124); vertical advection and the
+                // Thomas solve become one launch.
+                template <class... Bodies>
+                struct body_chain {
+                    using first_t = meta::first<body_chain>;
+                    using cta_t = typename first_t::cta_t;
+                    static constexpr bool parallel = false;
+                    static constexpr int_t threads = first_t::threads;
+                    static_assert(std::conjunction<std::bool_constant<Bodies::threads == threads>...>::value &&
+                                      !std::disjunction<std::bool_constant<Bodies::parallel>...>::value,
+                        GT_INTERNAL_ERROR);
+                    tuple<Bodies...> m_bodies;
+
+                    GT_FUNCTION void operator()() const {
+                        tuple_util::host_device::for_each(
+                            [](auto const &body) GT_FORCE_INLINE_LAMBDA {
+                                body();
+                                cta_t::sync(); // the next multi-stage may reuse the shared-memory tiles
+                            },
+                            m_bodies);
+                    }
+                };
+
+                template <class... Bodies, class Body>
+                body_chain<Bodies..., Body> chained(body_chain<Bodies...> chain, Body body) {
+                    return {tuple_util::push_back(std::move(chain.m_bodies), std::move(body))};
+                }
+                template <class First, class Body, std::enable_if_t<!meta::is_instantiation_of<body_chain, First>::value, int> = 0>
+                body_chain<First, Body> chained(First first, Body body) {
+                    return {tuple<First, Body>{std::move(first), std::move(body)}};
+                }
+
+                template <class Body>
+                struct pending {
+                    Body m_body;
+                    int_t m_nbi, m_nbj, m_nbk, m_smem;
+
+                    template <class Launcher>
+                    void flush(Launcher &launcher) && {
+                        if (m_nbi > 0 && m_nbj > 0 && m_nbk > 0)
+                            launcher.launch(m_body, m_nbi, m_nbj, m_nbk, Body::threads, m_smem);
+                    }
+                    template <bool Chain, class Launcher, class Other>
+                    auto then(Launcher &launcher, pending<Other> next) && {
+                        if constexpr (Chain && !Body::parallel && !Other::parallel) {
+                            auto chain = chained(std::move(m_body), std::move(next.m_body));
+                            return pending<decltype(chain)>{std::move(chain),
+                                m_nbi,
+                                m_nbj,
+                                m_nbk > next.m_nbk ? m_nbk : next.m_nbk,
+                                m_smem > next.m_smem ? m_smem : next.m_smem};
+                        } else {
+                            std::move(*this).flush(launcher);
+                            return next;
+                        }
+                    }
+                };
+                struct nothing_pending {
+                    template <class Launcher>
+                    void flush(Launcher &) && {}
+                    template <bool Chain, class Launcher, class Next>
+                    Next then(Launcher &, Next next) && {
+                        return next;
+                    }
+                };
+
                 // ---------------------------------------------------------------- host side: one multi-stage
                 template <class Plh, class DataStores>
                 k_bounds field_k_bounds(DataStores const &data_stores) {
@@ -386,8 +471,8 @@ namespace gridtools {
                         int_t(sid::get_upper_bound<dim::k>(sid::get_upper_bounds(store)))};
                 }
 
-                template <class Launcher, class Geo, class Mss, class Grid, class DataStores>
-                void launch_mss(Launcher &launcher, Mss, Grid const &grid, DataStores &data_stores) {
+                template <class Launcher, class Geo, class Volatile, class Mss, class Grid, class DataStores>
+                auto prepare_mss(Mss, Grid const &grid, DataStores &data_stores) {
                     using cta_t = typename Launcher::cta_t;
                     using plh_map_t = typename Mss::plh_map_t;
                     using io_cached_t = meta::filter<is_io_cached, plh_map_t>;
@@ -436,23 +521,91 @@ namespace gridtools {
                     int_t k_total = 0;
                     tuple_util::for_each([&](int_t n) { k_total += n; }, k_sizes);
                     const int_t ni = grid.i_size(), nj = grid.j_size();
-                    if (ni <= 0 || nj <= 0 || k_total <= 0)
-                        return;
-
                     using body_t = mss_body<cta_t,
                         Mss,
                         Geo,
+                        meta::if_<be_api::is_parallel<typename Mss::execution_t>, meta::list<>, Volatile>,
                         decltype(sid::get_origin(composite) + offset),
                         decltype(strides),
                         decltype(k_sizes),
                         decltype(bounds)>;
-                    body_t body{sid::get_origin(composite) + offset, strides, k_sizes, bounds, ni, nj, k_first};
-                    launcher.launch(body,
-                        (ni + Geo::bi - 1) / Geo::bi,
-                        (nj + Geo::bj - 1) / Geo::bj,
-                        body_t::parallel ? (k_total + Geo::kb - 1) / Geo::kb : 1,
-                        body_t::threads,
-                        smem_bytes);
+                    const int_t nbk = body_t::parallel ? (k_total + Geo::kb - 1) / Geo::kb : (k_total > 0 ? 1 : 0);
+                    return pending<body_t>{
+                        body_t{sid::get_origin(composite) + offset, strides, k_sizes, bounds, ni, nj, k_first},
+                        ni > 0 ? (ni + Geo::bi - 1) / Geo::bi : 0,
+                        nj > 0 ? (nj + Geo::bj - 1) / Geo::bj : 0,
+                        nbk,
+                        smem_bytes};
+                }
+
+                template <class Launcher, class Geo, class Volatile, class Grid, class DataStores, class Pending>
+                void launch_msses(Launcher &launcher, meta::list<>, Grid const &, DataStores &, Pending pending) {
+                    std::move(pending).flush(launcher);
+                }
+                template <class Launcher,
+                    class Geo,
+                    class Volatile,
+                    class Mss,
+                    class... Msses,
+                    class Grid,
+                    class DataStores,
+                    class Pending>
+                void launch_msses(Launcher &launcher,
+                    meta::list<Mss, Msses...>,
+                    Grid const &grid,
+                    DataStores &data_stores,
+                    Pending pending) {
+                    launch_msses<Launcher, Geo, Volatile>(launcher,
+                        meta::list<Msses...>(),
+                        grid,
+                        data_stores,
+                        std::move(pending).template then<Geo::chain_sweeps>(
+                            launcher, prepare_mss<Launcher, Geo, Volatile>(Mss(), grid, data_stores)));
+                }
+
+                // placeholders some sweep of the spec writes: sweeps may share a launch (body_chain), and what one of
+                // them writes must not be read through the non-coherent path by the next
+                template <class Mss>
+                using written_plhs = meta::transform<be_api::get_plh,
+                    meta::filter<meta::not_<be_api::get_is_const>::apply, typename Mss::plh_map_t>>;
+                template <class Mss>
+                using is_sweep = std::bool_constant<!be_api::is_parallel<typename Mss::execution_t>::value>;
+                template <class Msses>
+                using written_in_sweeps = meta::dedup<meta::rename<meta::concat,
+                    meta::push_front<meta::transform<written_plhs, meta::filter<is_sweep, meta::rename<meta::list, Msses>>>,
+                        meta::list<>>>>;
+
+                // ---------------------------------------------------------------- temporaries in device memory
+                // read at offset zero only: one array over the whole domain, i fastest like the fields
+                template <class Geo, class T, class Extent, class Grid, class Interval, class Allocator>
+                auto make_temporary(std::false_type, Extent extent, Grid const &grid, Interval interval, Allocator &alloc) {
+                    auto offsets = hymap::keys<dim::k>::make_values(-grid.k_start(interval) - extent.minus(dim::k()));
+                    // first key = stride 1 (stride_util::make_strides_from_sizes)
+                    auto sizes = hymap::keys<dim::i, dim::j, dim::k>::make_values(
+                        grid.i_size(), grid.j_size(), grid.k_size(interval, extent));
+                    using kind_t = meta::list<Extent, behind<void>>;
+                    return sid::block(
+                        sid::shift_sid_origin(sid::make_contiguous<T, ptrdiff_t, kind_t>(alloc, sizes), offsets),
+                        hymap::keys<dim::i, dim::j>::make_values(
+                            integral_constant<int_t, Geo::bi>(), integral_constant<int_t, Geo::bj>()));
+                }
+                // read at IJ offsets: every CTA owns a halo-extended copy of its block (the stages that write it run
+                // on the extended tile), so no CTA ever reads what another one writes -- the layout idea of the
+                // reference's gpu/tmp_storage_sid.hpp:54-69 with the block index outermost but k
+                template <class Geo, class T, class Extent, class Grid, class Interval, class Allocator>
+                auto make_temporary(std::true_type, Extent extent, Grid const &grid, Interval interval, Allocator &alloc) {
+                    auto offsets = hymap::keys<dim::i, dim::j, dim::k>::make_values(-extent.minus(dim::i()),
+                        -extent.minus(dim::j()),
+                        -grid.k_start(interval) - extent.minus(dim::k()));
+                    auto sizes = hymap::
+                        keys<dim::i, dim::j, sid::blocked_dim<dim::i>, sid::blocked_dim<dim::j>, dim::k>::make_values(
+                            extent.extend(dim::i(), integral_constant<int_t, Geo::bi>()),
+                            extent.extend(dim::j(), integral_constant<int_t, Geo::bj>()),
+                            (grid.i_size() + Geo::bi - 1) / Geo::bi,
+                            (grid.j_size() + Geo::bj - 1) / Geo::bj,
+                            grid.k_size(interval, extent));
+                    using kind_t = meta::list<Extent, behind<Geo>>;
+                    return sid::shift_sid_origin(sid::make_contiguous<T, ptrdiff_t, kind_t>(alloc, sizes), offsets);
                 }
 
                 // ---------------------------------------------------------------- host side: the whole spec
@@ -465,27 +618,21 @@ namespace gridtools {
                         meta::filter<needs_memory, typename msses_t::tmp_plh_map_t>>;
                     auto alloc = launcher.allocator();
                     auto temporaries = be_api::make_data_stores(tmp_plh_map_t(), [&](auto info) {
-                        auto extent = info.extent();
-                        auto interval = msses_t::interval();
-                        auto offsets = hymap::keys<dim::i, dim::j, dim::k>::make_values(-extent.minus(dim::i()),
-                            -extent.minus(dim::j()),
-                            -grid.k_start(interval) - extent.minus(dim::k()));
-                        // first key = stride 1 (stride_util::make_strides_from_sizes): i fastest, like the fields
-                        auto sizes = hymap::keys<dim::i, dim::j, dim::k>::make_values(
-                            grid.i_size(extent), grid.j_size(extent), grid.k_size(interval, extent));
-                        using stride_kind = meta::list<decltype(extent), behind<void>>;
-                        return sid::shift_sid_origin(
-                            sid::make_contiguous<decltype(info.data()), ptrdiff_t, stride_kind>(alloc, sizes), offsets);
+                        using extent_t = decltype(info.extent());
+                        return make_temporary<Geo, decltype(info.data())>(
+                            has_ij_extent<extent_t>(), extent_t(), grid, msses_t::interval(), alloc);
                     });
-                    auto blocked = tuple_util::transform(
+                    auto fields = tuple_util::transform(
                         [](auto &&store) {
                             return sid::block(std::forward<decltype(store)>(store),
                                 hymap::keys<dim::i, dim::j>::make_values(
                                     integral_constant<int_t, Geo::bi>(), integral_constant<int_t, Geo::bj>()));
                         },
-                        hymap::concat(std::move(external), std::move(temporaries)));
-                    for_each<meta::rename<meta::list, msses_t>>(
-                        [&](auto mss) { launch_mss<Launcher, Geo>(launcher, mss, grid, blocked); });
+                        std::move(external));
+                    auto data_stores = hymap::concat(std::move(fields), std::move(temporaries));
+                    using volatile_t = meta::if_c<Geo::chain_sweeps, written_in_sweeps<msses_t>, meta::list<>>;
+                    launch_msses<Launcher, Geo, volatile_t>(
+                        launcher, meta::rename<meta::list, msses_t>(), grid, data_stores, nothing_pending());
                 }
 
 #ifdef __CUDACC__

@@ -370,8 +370,9 @@ namespace cases {
             eval(out()) = eval(out()) + eval(a());
         }
     };
-    template <class T, class Traits, class Backend>
-    auto mixed(Traits, Backend backend, int ni, int nj, int nk0, int nk1) {
+    // CacheG = false_type: `g` is a plain temporary read at IJ offsets (CTA-private blocks in the fused path)
+    template <class T, class CacheG, class Traits, class Backend>
+    auto mixed_spec(CacheG, Traits, Backend backend, int ni, int nj, int nk0, int nk1) {
         constexpr int H = 2;
         const int d0 = ni + 2 * H, d1 = nj + 2 * H, nk = nk0 + nk1;
         auto hh = ij_halos(d0, d1, H);
@@ -382,6 +383,13 @@ namespace cases {
         st::run(
             [](auto in, auto out) {
                 GT_DECLARE_TMP(T, g, s);
+                if constexpr (!CacheG::value)
+                    return st::multi_pass(st::execute_parallel()
+                                              .stage(grad_f(), g, in)
+                                              .stage(smooth_f(), s, g)
+                                              .stage(combine_f(), out, s, in),
+                        st::execute_parallel().stage(add_f(), out, s));
+                else
                 return st::multi_pass(st::execute_parallel()
                                           .ij_cached(g)
                                           .stage(grad_f(), g, in)
@@ -391,5 +399,13 @@ namespace cases {
             },
             backend, grid, in, out);
         return out;
+    }
+    template <class T, class Traits, class Backend>
+    auto mixed(Traits tr, Backend backend, int ni, int nj, int nk0, int nk1) {
+        return mixed_spec<T>(std::true_type(), tr, backend, ni, nj, nk0, nk1);
+    }
+    template <class T, class Traits, class Backend>
+    auto mixed_plain(Traits tr, Backend backend, int ni, int nj, int nk0, int nk1) {
+        return mixed_spec<T>(std::false_type(), tr, backend, ni, nj, nk0, nk1);
     }
 } // namespace cases

@@ -25,6 +25,7 @@ namespace {
 
     template <class Geo>
     struct run {
+        static constexpr long sweep_launches = Geo::chain_sweeps ? 1 : 2;
         using be_t = emulated::backend<Geo>;
         using ref_t = st::cpu_ifirst<>;
         // cpu_kfirst storage has i-stride 1 like storage::gpu
@@ -64,13 +65,13 @@ namespace {
             }
             {
                 auto got = cases::vert_adv<double>(tr, be_t(), ni, nj, nk + 4);
-                expect_launches("vert_adv launches", 2);
+                expect_launches("vert_adv launches", sweep_launches); // forward and backward sweeps chained
                 auto ref = cases::vert_adv<double>(tr, ref_t(), ni, nj, nk + 4);
                 cases::same(name("vert_adv f64", ni, nj, nk + 4).c_str(), got, ref, ni + 6, nj + 6, nk + 4, 1e-12, g_failed);
             }
             {
                 auto got = cases::tridiagonal(tr, be_t(), ni, nj, 6);
-                expect_launches("tridiagonal launches", 2);
+                expect_launches("tridiagonal launches", sweep_launches);
                 auto ref = cases::tridiagonal(tr, ref_t(), ni, nj, 6);
                 cases::same(name("tridiagonal", ni, nj, 6).c_str(), got, ref, ni, nj, 6, 1e-13, g_failed);
             }
@@ -106,6 +107,13 @@ namespace {
                 cases::same(name("mixed tiles + plain temporaries, 2 intervals", ni, nj, nk + 2).c_str(), got, ref,
                     ni + 4, nj + 4, nk + 2, 1e-13, g_failed);
             }
+            {
+                auto got = cases::mixed_plain<double>(tr, be_t(), ni, nj, 2, nk);
+                expect_launches("mixed (no caches) launches", 2);
+                auto ref = cases::mixed_plain<double>(tr, ref_t(), ni, nj, 2, nk);
+                cases::same(name("temporary read at IJ offsets, not cached", ni, nj, nk + 2).c_str(), got, ref, ni + 4,
+                    nj + 4, nk + 2, 1e-13, g_failed);
+            }
         }
     };
 } // namespace
@@ -117,6 +125,8 @@ int main() {
     run<fused::geometry<8, 4, 3>>{"[8x4x3 blocks]"}.all(1, 1, 2);
     // the default geometry on a domain of a few blocks
     run<fused::geometry<>>{"[32x8x8 blocks]"}.all(37, 11, 10);
+    // sweeps in separate launches
+    run<fused::geometry<8, 4, 3, 2, false>>{"[8x4x3 blocks, unchained]"}.all(19, 9, 7);
     std::printf(g_failed ? "FAILED (%d)\n" : "ALL PASSED\n", g_failed);
     return g_failed ? 1 : 0;
 }

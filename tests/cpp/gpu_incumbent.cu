@@ -126,8 +126,9 @@ namespace {
         double t = time_us([&](int s) { s == 0 ? call(s0) : call(s1); }, SETS);
         report("vertical_advection_dycore", name, t, 1. * ni * nj * nk, 48);
     }
-    template <int BI, int BJ, int KB>
-    using fused_t = st::b200<gtb200::default_stream, gtb200::fused_when_possible, gtb200::block_geometry<BI, BJ, KB>>;
+    template <int BI, int BJ, int KB, int U = 1, bool Chain = true>
+    using fused_t =
+        st::b200<gtb200::default_stream, gtb200::fused_when_possible, gtb200::block_geometry<BI, BJ, KB, U, Chain>>;
 } // namespace
 
 int main(int argc, char **argv) {
@@ -137,20 +138,26 @@ int main(int argc, char **argv) {
         std::printf("# %dx%dx%d fp64, CUDA events around 200 runs, rotating field sets\n", ni, nj, nk);
         // tag 0 functors are bound to the named kernels, tag 1 functors are not: generic paths of the same tag
         using staged_t = st::b200<gtb200::default_stream, gtb200::stage_by_stage>;
+#ifndef FUSED_SWEEP
         hori_diff<1>("stencil::gpu<>", st::gpu<>(), ni, nj, nk);
         hori_diff<0>("stencil::b200<> named", st::b200<>(), ni, nj, nk);
-        hori_diff<1>("b200 fused 32x8x8", st::b200<>(), ni, nj, nk);
-        hori_diff<1>("b200 fused 64x4x8", fused_t<64, 4, 8>(), ni, nj, nk);
-        hori_diff<1>("b200 fused 32x16x4", fused_t<32, 16, 4>(), ni, nj, nk);
-        hori_diff<1>("b200 fused 64x8x2", fused_t<64, 8, 2>(), ni, nj, nk);
-        hori_diff<1>("b200 stage by stage", staged_t(), ni, nj, nk);
+        hori_diff<1>("stencil::b200<> fused", st::b200<>(), ni, nj, nk);
+        hori_diff<1>("stencil::b200<> staged", staged_t(), ni, nj, nk);
         vert_adv<1>("stencil::gpu<>", st::gpu<>(), ni, nj, nk);
         vert_adv<0>("stencil::b200<> named", st::b200<>(), ni, nj, nk);
-        vert_adv<1>("b200 fused 32x8", st::b200<>(), ni, nj, nk);
-        vert_adv<1>("b200 fused 32x4", fused_t<32, 4, 8>(), ni, nj, nk);
-        vert_adv<1>("b200 fused 32x2", fused_t<32, 2, 8>(), ni, nj, nk);
-        vert_adv<1>("b200 fused 64x1", fused_t<64, 1, 8>(), ni, nj, nk);
-        vert_adv<1>("b200 stage by stage", staged_t(), ni, nj, nk);
+        vert_adv<1>("stencil::b200<> fused", st::b200<>(), ni, nj, nk);
+        vert_adv<1>("stencil::b200<> staged", staged_t(), ni, nj, nk);
+#else
+        // block geometries / sweep unroll factors of the fused generic path (make -C tests/cpp fused_timing)
+        hori_diff<1>("fused 32x8x8", fused_t<32, 8, 8>(), ni, nj, nk);
+        hori_diff<1>("fused 64x8x4", fused_t<64, 8, 4>(), ni, nj, nk);
+        vert_adv<1>("fused chained unroll 2", fused_t<32, 8, 8, 2, true>(), ni, nj, nk);
+        vert_adv<1>("fused chained unroll 3", fused_t<32, 8, 8, 3, true>(), ni, nj, nk);
+        vert_adv<1>("fused 2 launches unroll 1", fused_t<32, 8, 8, 1, false>(), ni, nj, nk);
+        vert_adv<1>("fused 2 launches unroll 2", fused_t<32, 8, 8, 2, false>(), ni, nj, nk);
+        vert_adv<1>("fused 2 launches unroll 3", fused_t<32, 8, 8, 3, false>(), ni, nj, nk);
+        vert_adv<1>("fused 2 launches unroll 4", fused_t<32, 8, 8, 4, false>(), ni, nj, nk);
+#endif
     } catch (std::exception const &e) {
         std::printf("EXCEPTION: %s\n", e.what());
         return 2;

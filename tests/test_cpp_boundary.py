@@ -50,7 +50,36 @@ def test_b200_tag_through_gridtools_frontend():
     print(r.stdout)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
     assert "ALL PASSED" in r.stdout
-    assert r.stdout.count(" ok ") >= 17 + 4 * 14
+    assert r.stdout.count(" ok ") >= 17 + 5 * 15
+
+
+SELECT_TU = r"""
+#include <cstring>
+#include <gridtools/stencil/cartesian.hpp>
+#include <gtb200/stencil/b200_select.hpp>
+namespace st = gridtools::stencil;
+using tag_t = st::b200<>;
+using staged_t = st::b200<gtb200::default_stream, gtb200::stage_by_stage>;
+static_assert(std::is_same<decltype(backend_storage_traits(tag_t())), gridtools::storage::gpu>::value, "");
+static_assert(std::is_same<decltype(backend_timer_impl(staged_t())), gridtools::timer_cuda>::value, "");
+static_assert(!decltype(backend_supports_icosahedral(tag_t()))::value, "");
+static_assert(decltype(backend_supports_vertical_stencils(tag_t()))::value, "");
+int main() { return std::strcmp(backend_name(tag_t()), "b200"); }
+"""
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference headers only exist in the build container")
+def test_harness_traits_of_the_tag(tmp_path):
+    """What tests/include/stencil_select.hpp:129-231 asks of a backend tag (storage traits, timer, name, capability
+    probes) is found by ADL on stencil::b200 (include/gtb200/stencil/b200_select.hpp)."""
+    src = tmp_path / "sel.cpp"
+    src.write_text(SELECT_TU)
+    exe = tmp_path / "sel"
+    cmd = ["/usr/bin/g++", "-std=c++17", "-I" + REF, "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include",
+           str(src), "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert subprocess.run([str(exe)]).returncode == 0
 
 
 EMU_BIN = os.path.join(ROOT, "tests", "_build", "fused_emulation")
@@ -67,7 +96,7 @@ def test_fused_generic_path_on_emulated_ctas():
     r = subprocess.run([EMU_BIN], capture_output=True, text=True, timeout=900, env=env)
     print(r.stdout)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
-    assert "ALL PASSED" in r.stdout and r.stdout.count(" ok ") >= 52
+    assert "ALL PASSED" in r.stdout and r.stdout.count(" ok ") >= 70
 
 
 # ------------------------------------------------------------------------------------------------ gcl (C++ class)
