@@ -323,10 +323,22 @@ namespace gridtools {
                             sid::get_stride_element<behind_key<Info>, dim::k>(m_strides),
                             integral_constant<int_t, W>());
                         auto &win = host_device::at_key<typename Info::key_t>(windows);
-                        if constexpr (Fill)
-                            win.ptr()[W] = *mem;
-                        else
+                        if constexpr (Fill) {
+                            // a field that is only filled from (never flushed to, not written elsewhere in this
+                            // launch) is read-only here: same non-coherent path as read_only_deref
+                            using value_t = std::remove_cv_t<std::remove_reference_t<decltype(*mem)>>;
+                            constexpr bool read_only = !has_flush<Info>::value && std::is_arithmetic<value_t>::value &&
+                                                       !meta::st_contains<Volatile, typename Info::plh_t>::value;
+#ifdef __CUDA_ARCH__
+                            if constexpr (read_only)
+                                win.ptr()[W] = __ldg(&*mem);
+                            else
+#endif
+                                win.ptr()[W] = *mem;
+                            (void)read_only;
+                        } else {
                             *mem = win.ptr()[W];
+                        }
                     }
 
                     template <bool Fill, class Info, int_t From, int_t To, class Windows, class Ptr>
