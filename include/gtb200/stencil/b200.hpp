@@ -86,8 +86,9 @@ namespace gtb200 {
     struct stage_by_stage {};
 #ifdef __CUDACC__
     /// IJ block and levels per CTA of the fused generic path (third template argument of stencil::b200).
-    template <int BI, int BJ, int KB, int SweepUnroll = 2, bool ChainSweeps = true>
-    using block_geometry = ::gridtools::stencil::b200_backend::fused::geometry<BI, BJ, KB, SweepUnroll, ChainSweeps>;
+    template <int BI, int BJ, int KB, int SweepUnroll = 3, bool ChainSweeps = true, int Prefetch = 4, bool PrefetchL1 = true>
+    using block_geometry =
+        ::gridtools::stencil::b200_backend::fused::geometry<BI, BJ, KB, SweepUnroll, ChainSweeps, Prefetch, PrefetchL1>;
     using default_geometry = ::gridtools::stencil::b200_backend::fused::geometry<>;
 #else
     struct default_geometry {};

@@ -24,8 +24,10 @@
  *   a7  temporaries that are neither ij- nor k-cached live in device memory: one whole-domain array when they are only
  *       read at IJ offset zero, CTA-private halo-extended blocks when they are read at IJ offsets
  *       (gpu/tmp_storage_sid.hpp:54-69), so that no CTA reads what another one writes.
- *   Not `fusable` (they take the stage-by-stage path of b200.hpp): sweeps with IJ extents and k caches in parallel
- *   multi-stages.  Consecutive forward / backward multi-stages share ONE launch (body_chain).
+ *   Not `fusable` (it takes the stage-by-stage path of b200.hpp): k caches inside a parallel multi-stage.  Sweeps
+ *   with IJ extents work like the others (the halo threads sweep their columns with their own windows; a cache is
+ *   filled / flushed on the columns inside its placeholder's IJ extent).  Consecutive column-local forward / backward
+ *   multi-stages share ONE launch (body_chain).
  *
  * Everything here is written against a `Cta` policy (block / thread indices, barrier, shared-memory base): `cuda_cta`
  * is the product; tests/cpp/emulated_cta.hpp runs the very same body on the host, one OpenMP team per CTA, to pin
@@ -68,14 +70,26 @@ namespace gridtools {
                 // ---------------------------------------------------------------- geometry
                 // IJ block of a CTA, levels per CTA of a parallel multi-stage, unroll factor of the level loop of a sweep.
                 // Defaults from profiles/r01_fused_generic.txt (256x256x80 fp64): hori_diff 32x8x8 53.0 us, 64x4x8
-                // 61.5, 32x16x8 51.2, 80 levels per CTA 96.2; vert_adv unroll 1 / 2 / 4: 167.9 / 115.6 / 143.8 us.
+                // 61.5, 32x16x8 51.2, 80 levels per CTA 96.2; vert_adv chained, unroll 1 / 2 / 3: 168 / 130-151 / 128-132 us,
+                // unroll 3 with prefetch 2 L1 / 4 L1 / 4 L2 / 8 L2: 108.8 / 111.9 / 112.1 / 156.0 us, sweeps in separate
+                // launches 164-190 us.
                 // ChainSweeps: consecutive forward / backward multi-stages in one launch (body_chain) -- what one of them
                 // writes is then read with coherent loads by the next -- or one launch each, every field a multi-stage
                 // only reads on the read-only path.
-                template <int_t BI = 32, int_t BJ = 8, int_t KB = 8, int_t SweepUnroll = 2, bool ChainSweeps = true>
+                // Prefetch > 0: a sweep asks for the lines of level k + Prefetch of every field it only reads (and of the
+                // fields behind filled k caches) while it works on level k -- into L1 (PrefetchL1) or L2.  A sweep has one
+                // thread per column, far fewer than an SM can hold, so it is bound by the latency of one level's loads;
+                // the prefetch turns that into a bandwidth problem without touching the user functors.
+                template <int_t BI = 32,
+                    int_t BJ = 8,
+                    int_t KB = 8,
+                    int_t SweepUnroll = 3,
+                    bool ChainSweeps = true,
+                    int_t Prefetch = 4,
+                    bool PrefetchL1 = true>
                 struct geometry {
-                    static constexpr int_t bi = BI, bj = BJ, kb = KB, sweep_unroll = SweepUnroll;
-                    static constexpr bool chain_sweeps = ChainSweeps;
+                    static constexpr int_t bi = BI, bj = BJ, kb = KB, sweep_unroll = SweepUnroll, prefetch = Prefetch;
+                    static constexpr bool chain_sweeps = ChainSweeps, prefetch_l1 = PrefetchL1;
                 };
 
                 template <class Extent>
@@ -105,11 +119,10 @@ namespace gridtools {
                 struct behind {};
 
                 // ---------------------------------------------------------------- can a spec take the fused path?
+                // the one shape that is not taken: k caches inside a parallel multi-stage (levels are spread over CTAs)
                 template <class Mss>
-                using mss_is_fusable = std::bool_constant<
-                    be_api::is_parallel<typename Mss::execution_t>::value
-                        ? !meta::any_of<is_k_cached, typename Mss::plh_map_t>::value
-                        : !has_ij_extent<typename Mss::extent_t>::value>;
+                using mss_is_fusable = std::bool_constant<!be_api::is_parallel<typename Mss::execution_t>::value ||
+                                                          !meta::any_of<is_k_cached, typename Mss::plh_map_t>::value>;
 
                 template <class Spec, class Msses = be_api::make_fused_view<Spec>>
                 using fusable = meta::all_of<mss_is_fusable, meta::rename<meta::list, Msses>>;
@@ -205,6 +218,20 @@ namespace gridtools {
                     }
                 };
 
+                template <bool L1, class T>
+                GT_FUNCTION void prefetch_line(T const *ptr) {
+#ifdef __CUDA_ARCH__
+                    if (L1)
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+                    else
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+#else
+                    (void)ptr;
+#endif
+                }
+                template <bool L1, class Other>
+                GT_FUNCTION void prefetch_line(Other const &) {} // not a pointer to memory (global_parameter, ...)
+
                 struct k_bounds {
                     int_t lo, hi; // valid levels of the field behind a cache, relative to the grid's k origin
                 };
@@ -232,6 +259,8 @@ namespace gridtools {
                     using deref_t = read_only_deref<meta::transform<be_api::get_key, meta::filter<is_read_only, plh_map_t>>>;
 
                     static constexpr bool parallel = be_api::is_parallel<typename Mss::execution_t>::value;
+                    // column-local sweeps may share a launch with their neighbours (body_chain)
+                    static constexpr bool chainable = !parallel && !has_ij_extent<extent_t>::value;
                     static constexpr int_t imin = extent_t::iminus::value, jmin = extent_t::jminus::value;
                     static constexpr int_t width = Geo::bi - imin + extent_t::iplus::value;
                     static constexpr int_t height = Geo::bj - jmin + extent_t::jplus::value;
@@ -350,7 +379,8 @@ namespace gridtools {
 
                     // `whole`: first level of the sweep for fills, last level for flushes
                     template <bool Fill, class Windows, class Ptr>
-                    GT_FUNCTION void sync_caches(Windows &windows, Ptr const &ptr, int_t k_pos, bool whole) const {
+                    GT_FUNCTION void sync_caches(
+                        Windows &windows, Ptr const &ptr, point const &p, int_t k_pos, bool whole) const {
                         // the entry that enters (fill) or leaves (flush) the window at every step of the sweep
                         constexpr bool at_plus = (step_t::value > 0) == Fill;
                         tuple_util::host_device::for_each(
@@ -358,6 +388,9 @@ namespace gridtools {
                                 using info_t = decltype(info);
                                 using win_t = window_of<info_t>;
                                 if constexpr (Fill ? has_fill<info_t>::value : has_flush<info_t>::value) {
+                                    // only the columns on which the stages use this placeholder (its IJ extent)
+                                    if (!active(p, to_horizontal_extent<typename info_t::extent_t>()))
+                                        return;
                                     if (whole)
                                         sync_range<Fill, info_t, win_t::minus, win_t::plus>(windows, ptr, k_pos, b);
                                     else
@@ -369,7 +402,35 @@ namespace gridtools {
                             m_bounds);
                     }
 
-                    // forward / backward multi-stage: one column per thread, k caches in registers
+                    // what a sweep reads from memory level by level: plain fields it does not write, fields behind fills
+                    template <class Info>
+                    using is_streamed_in = std::bool_constant<(is_plain<Info>::value && Info::is_const_t::value) ||
+                                                              (is_k_cached<Info>::value && has_fill<Info>::value)>;
+                    template <class Info>
+                    using memory_key = meta::if_<is_plain<Info>, typename Info::key_t, behind<typename Info::plh_t>>;
+
+                    template <class Ptr>
+                    GT_FUNCTION void prefetch_ahead(Ptr const &ptr, point const &p, int_t levels_left) const {
+                        if constexpr (Geo::prefetch > 0) {
+                            if (levels_left <= Geo::prefetch)
+                                return; // level k + Prefetch is not part of this sweep
+                            host_device::for_each<meta::filter<is_streamed_in, plh_map_t>>([&](auto info)
+                                                                                            GT_FORCE_INLINE_LAMBDA {
+                                using info_t = decltype(info);
+                                using key_t = memory_key<info_t>;
+                                if (!active(p, to_horizontal_extent<typename info_t::extent_t>()))
+                                    return;
+                                auto mem = host_device::at_key<key_t>(ptr);
+                                sid::shift(mem,
+                                    sid::get_stride_element<key_t, dim::k>(m_strides),
+                                    integral_constant<int_t, Geo::prefetch * step_t::value>());
+                                prefetch_line<Geo::prefetch_l1>(mem);
+                            });
+                        }
+                    }
+
+                    // forward / backward multi-stage: one column per thread -- the threads of the halo points sweep their
+                    // columns too, with their own windows -- k caches in registers
                     template <class Ptr>
                     GT_FUNCTION void run(std::false_type, Ptr &ptr, point const &p) const {
                         using keys_t = meta::transform<be_api::get_key, k_cached_t>;
@@ -379,7 +440,6 @@ namespace gridtools {
                             tuple_util::host_device::transform(
                                 [](auto &w) GT_FORCE_INLINE_LAMBDA { return w.ptr(); }, windows),
                             std::move(ptr));
-                        const bool on = active(p, extent<>());
                         int_t total = 0;
                         tuple_util::host_device::for_each(
                             [&](int_t size) GT_FORCE_INLINE_LAMBDA { total += size; }, m_k_sizes);
@@ -388,11 +448,10 @@ namespace gridtools {
                             [&](int_t size, auto info) GT_FORCE_INLINE_LAMBDA {
 #pragma unroll(Geo::sweep_unroll)
                                 for (int_t k = 0; k < size; ++k) {
-                                    if (on)
-                                        sync_caches<true>(windows, mixed.secondary(), k_pos, n == 0);
+                                    prefetch_ahead(mixed.secondary(), p, total - n);
+                                    sync_caches<true>(windows, mixed.secondary(), p, k_pos, n == 0);
                                     exec_cells(info, mixed, p);
-                                    if (on)
-                                        sync_caches<false>(windows, mixed.secondary(), k_pos, n == total - 1);
+                                    sync_caches<false>(windows, mixed.secondary(), p, k_pos, n == total - 1);
                                     tuple_util::host_device::for_each(
                                         [](auto &w) GT_FORCE_INLINE_LAMBDA { w.slide(step_t()); }, windows);
                                     info.inc_k(mixed.secondary(), m_strides);
@@ -415,10 +474,10 @@ namespace gridtools {
                 struct body_chain {
                     using first_t = meta::first<body_chain>;
                     using cta_t = typename first_t::cta_t;
-                    static constexpr bool parallel = false;
+                    static constexpr bool parallel = false, chainable = true;
                     static constexpr int_t threads = first_t::threads;
                     static_assert(std::conjunction<std::bool_constant<Bodies::threads == threads>...>::value &&
-                                      !std::disjunction<std::bool_constant<Bodies::parallel>...>::value,
+                                      std::conjunction<std::bool_constant<Bodies::chainable>...>::value,
                         GT_INTERNAL_ERROR);
                     tuple<Bodies...> m_bodies;
 
@@ -453,7 +512,7 @@ namespace gridtools {
                     }
                     template <bool Chain, class Launcher, class Other>
                     auto then(Launcher &launcher, pending<Other> next) && {
-                        if constexpr (Chain && !Body::parallel && !Other::parallel) {
+                        if constexpr (Chain && Body::chainable && Other::chainable) {
                             auto chain = chained(std::move(m_body), std::move(next.m_body));
                             return pending<decltype(chain)>{std::move(chain),
                                 m_nbi,

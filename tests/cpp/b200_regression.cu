@@ -297,6 +297,8 @@ namespace {
             cases::kcache_local(host, ref_be, ni, nj, nk), ni, nj, nk, 1e-14, g_failed);
         cases::same(name("mixed tiles + plain temporaries").c_str(), cases::mixed<double>(dev, be, ni, nj, 2, nk),
             cases::mixed<double>(host, ref_be, ni, nj, 2, nk), ni + 4, nj + 4, nk + 2, 1e-12, g_failed);
+        cases::same(name("forward sweep with IJ extents").c_str(), cases::sweep_with_extents(dev, be, ni, nj, nk),
+            cases::sweep_with_extents(host, ref_be, ni, nj, nk), ni + 6, nj + 6, nk, 1e-12, g_failed);
         cases::same(name("temporary read at IJ offsets, not cached").c_str(),
             cases::mixed_plain<double>(dev, be, ni, nj, 2, nk), cases::mixed_plain<double>(host, ref_be, ni, nj, 2, nk),
             ni + 4, nj + 4, nk + 2, 1e-12, g_failed);
@@ -335,8 +337,13 @@ int main() {
         test_generic_cases<staged_t>("staged", 70, 19, 13);
         // sweeps in separate launches (every read-only field on the ld.global.nc path), three levels unrolled
         using unchained_t = st::b200<gtb200::default_stream, gtb200::fused_when_possible,
-            gtb200::block_geometry<32, 8, 8, 3, false>>;
+            gtb200::block_geometry<32, 8, 8, 3, false, 0, false>>;
         test_generic_cases<unchained_t>("fused, sweeps unchained", 70, 19, 13);
+        // software prefetch in the sweeps (default: 4 levels ahead into L1): off, 8 levels ahead into L2
+        test_generic_cases<st::b200<gtb200::default_stream, gtb200::fused_when_possible,
+            gtb200::block_geometry<32, 8, 8, 3, true, 0, false>>>("fused, no prefetch", 70, 19, 13);
+        test_generic_cases<st::b200<gtb200::default_stream, gtb200::fused_when_possible,
+            gtb200::block_geometry<32, 8, 8, 2, true, 8, false>>>("fused, prefetch 8 L2", 70, 19, 13);
     } catch (std::exception const &e) {
         std::printf("EXCEPTION: %s\n", e.what());
         return 2;

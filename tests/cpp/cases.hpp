@@ -400,6 +400,67 @@ namespace cases {
             backend, grid, in, out);
         return out;
     }
+    // ------------------------------------------------------------------ sweeps with IJ extents
+    // forward sweep: an ij-cached difference read at j offsets feeds a local k cache; the result is flushed through
+    // a second k cache into a temporary that the following parallel multi-stage reads at i offsets
+    struct diff_i_f {
+        using a = inout_accessor<0>;
+        using in = in_accessor<1, extent<-1, 1, 0, 0>>;
+        using param_list = make_param_list<a, in>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval) {
+            eval(a()) = eval(in(1, 0)) - eval(in(-1, 0));
+        }
+    };
+    struct accumulate_f {
+        using acc = inout_accessor<0, extent<0, 0, 0, 0, -1, 0>>;
+        using c = inout_accessor<1, extent<0, 0, 0, 0, -1, 0>>;
+        using a = in_accessor<2, extent<0, 0, -1, 1>>;
+        using param_list = make_param_list<acc, c, a>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval, kc_full_t::first_level) {
+            eval(acc()) = eval(a(0, 1)) + eval(a(0, -1));
+            eval(c()) = eval(acc());
+        }
+        template <class E>
+        GT_FUNCTION static void apply(E eval, kc_full_t::modify<1, 0>) {
+            eval(acc()) = 0.5 * eval(acc(0, 0, -1)) + eval(a(0, 1)) + eval(a(0, -1));
+            eval(c()) = eval(c(0, 0, -1)) + eval(acc());
+        }
+    };
+    struct spread_f {
+        using out = inout_accessor<0>;
+        using c = in_accessor<1, extent<-1, 1, 0, 0>>;
+        using param_list = make_param_list<out, c>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval) {
+            eval(out()) = eval(c(-1, 0)) + 2 * eval(c()) + eval(c(1, 0));
+        }
+    };
+    template <class Traits, class Backend>
+    auto sweep_with_extents(Traits, Backend backend, int ni, int nj, int nk) {
+        constexpr int H = 3;
+        const int d0 = ni + 2 * H, d1 = nj + 2 * H;
+        auto hh = ij_halos(d0, d1, H);
+        auto grid = st::make_grid(hh.first, hh.second, kc_axis_t(nk));
+        auto in = make_store<Traits, double>(
+            d0, d1, nk, H, [](int i, int j, int k) { return std::sin(0.3 * i + 0.1 * k) + std::cos(0.2 * j) * (1 + 0.1 * k); });
+        auto out = make_store<Traits, double>(d0, d1, nk, H, [](int, int, int) { return -3.; });
+        st::run(
+            [](auto in, auto out) {
+                GT_DECLARE_TMP(double, a, acc, c);
+                return st::multi_pass(st::execute_forward()
+                                          .ij_cached(a)
+                                          .k_cached(acc)
+                                          .k_cached(st::cache_io_policy::flush(), c)
+                                          .stage(diff_i_f(), a, in)
+                                          .stage(accumulate_f(), acc, c, a),
+                    st::execute_parallel().stage(spread_f(), out, c));
+            },
+            backend, grid, in, out);
+        return out;
+    }
+
     template <class T, class Traits, class Backend>
     auto mixed(Traits tr, Backend backend, int ni, int nj, int nk0, int nk1) {
         return mixed_spec<T>(std::true_type(), tr, backend, ni, nj, nk0, nk1);

@@ -108,6 +108,13 @@ namespace {
                     ni + 4, nj + 4, nk + 2, 1e-13, g_failed);
             }
             {
+                auto got = cases::sweep_with_extents(tr, be_t(), ni, nj, nk);
+                expect_launches("sweep with IJ extents launches", 2);
+                auto ref = cases::sweep_with_extents(tr, ref_t(), ni, nj, nk);
+                cases::same(name("forward sweep with IJ extents, flushed to a blocked temporary", ni, nj, nk).c_str(), got,
+                    ref, ni + 6, nj + 6, nk, 1e-13, g_failed);
+            }
+            {
                 auto got = cases::mixed_plain<double>(tr, be_t(), ni, nj, 2, nk);
                 expect_launches("mixed (no caches) launches", 2);
                 auto ref = cases::mixed_plain<double>(tr, ref_t(), ni, nj, 2, nk);
@@ -125,6 +132,8 @@ int main() {
     run<fused::geometry<8, 4, 3>>{"[8x4x3 blocks]"}.all(1, 1, 2);
     // the default geometry on a domain of a few blocks
     run<fused::geometry<>>{"[32x8x8 blocks]"}.all(37, 11, 10);
+    // prefetch ahead (a no-op on the host, but the address arithmetic is instantiated)
+    run<fused::geometry<8, 4, 3, 2, true, 4, true>>{"[8x4x3 blocks, prefetch]"}.all(19, 9, 7);
     // sweeps in separate launches
     run<fused::geometry<8, 4, 3, 2, false>>{"[8x4x3 blocks, unchained]"}.all(19, 9, 7);
     std::printf(g_failed ? "FAILED (%d)\n" : "ALL PASSED\n", g_failed);
