@@ -297,6 +297,12 @@ namespace {
             cases::kcache_local(host, ref_be, ni, nj, nk), ni, nj, nk, 1e-14, g_failed);
         cases::same(name("mixed tiles + plain temporaries").c_str(), cases::mixed<double>(dev, be, ni, nj, 2, nk),
             cases::mixed<double>(host, ref_be, ni, nj, 2, nk), ni + 4, nj + 4, nk + 2, 1e-12, g_failed);
+        {
+            int bad = cases::prepare_tracers(dev, be, ni, nj, nk, 5);
+            std::printf("%-58s %s (%d of 5 tracers differ)\n", name("expandable_run<2>, 5 tracers").c_str(),
+                bad ? "FAILED" : "ok", bad);
+            g_failed += bad != 0;
+        }
         cases::same(name("forward sweep with IJ extents").c_str(), cases::sweep_with_extents(dev, be, ni, nj, nk),
             cases::sweep_with_extents(host, ref_be, ni, nj, nk), ni + 6, nj + 6, nk, 1e-12, g_failed);
         cases::same(name("temporary read at IJ offsets, not cached").c_str(),

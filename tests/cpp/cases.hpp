@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <functional>
 #include <string>
+#include <vector>
 
 #include <gridtools/stencil/cartesian.hpp>
 #include <gridtools/stencil/global_parameter.hpp>
@@ -400,6 +401,47 @@ namespace cases {
             backend, grid, in, out);
         return out;
     }
+    // ------------------------------------------------------------------ expandable_run
+    // advection_pdbott_prepare_tracers.cpp:23-52: vectors of stores expanded two at a time by the frontend; the backend
+    // sees one spec with two stages (and a second one with the odd tracer left over)
+    struct scale_f {
+        using data = inout_accessor<0>;
+        using data_nnow = in_accessor<1>;
+        using rho = in_accessor<2>;
+        using param_list = make_param_list<data, data_nnow, rho>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval) {
+            eval(data()) = eval(rho()) * eval(data_nnow());
+        }
+    };
+    // returns the number of tracers that differ from rho * in (bit-exact: one multiplication)
+    template <class Traits, class Backend>
+    int prepare_tracers(Traits, Backend backend, int ni, int nj, int nk, int tracers) {
+        auto hh = ij_halos(ni, nj, 0);
+        auto grid = st::make_grid(hh.first, hh.second, st::axis<1>(nk));
+        using store_t = decltype(make_store<Traits, double>(ni, nj, nk, 0, fun_t()));
+        std::vector<store_t> in, out;
+        for (int t = 0; t < tracers; ++t) {
+            out.push_back(make_store<Traits, double>(ni, nj, nk, 0, [](int, int, int) { return -1.; }));
+            in.push_back(make_store<Traits, double>(ni, nj, nk, 0, [t](int i, int j, int k) { return t + 0.1 * i + 0.01 * j + k; }));
+        }
+        auto rho = make_store<Traits, double const>(ni, nj, nk, 0, [](int i, int, int k) { return 1.1 + 0.001 * (i + k); });
+        st::expandable_run<2>(
+            [](auto out, auto in, auto rho) { return st::execute_parallel().stage(scale_f(), out, in, rho); }, backend,
+            grid, out, in, rho);
+        int bad = 0;
+        for (int t = 0; t < tracers; ++t) {
+            auto o = out[t]->const_host_view();
+            bool ok = true;
+            for (int k = 0; k < nk; ++k)
+                for (int j = 0; j < nj; ++j)
+                    for (int i = 0; i < ni; ++i)
+                        ok = ok && o(i, j, k) == (1.1 + 0.001 * (i + k)) * (t + 0.1 * i + 0.01 * j + k);
+            bad += !ok;
+        }
+        return bad;
+    }
+
     // ------------------------------------------------------------------ sweeps with IJ extents
     // forward sweep: an ij-cached difference read at j offsets feeds a local k cache; the result is flushed through
     // a second k cache into a temporary that the following parallel multi-stage reads at i offsets

@@ -108,6 +108,12 @@ namespace {
                     ni + 4, nj + 4, nk + 2, 1e-13, g_failed);
             }
             {
+                int bad = cases::prepare_tracers(tr, be_t(), ni, nj, nk, 5);
+                std::printf("%-58s %s (%d of 5 tracers differ)\n", name("expandable_run<2>, 5 tracers", ni, nj, nk).c_str(),
+                    bad ? "FAILED" : "ok", bad);
+                g_failed += bad != 0;
+            }
+            {
                 auto got = cases::sweep_with_extents(tr, be_t(), ni, nj, nk);
                 expect_launches("sweep with IJ extents launches", 2);
                 auto ref = cases::sweep_with_extents(tr, ref_t(), ni, nj, nk);
