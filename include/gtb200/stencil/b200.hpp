@@ -17,8 +17,8 @@
  *     hand-written sm_100a kernel of libgtb200.so through the C ABI of include/gtb200.h (TMA-staged fused
  *     horizontal diffusion, TMA-streamed forward/backward vertical advection, ...).  The fields passed to `run`
  *     must be in the order of the corresponding C-ABI function, which is the order the reference's own specs use
- *     (horizontal_diffusion.cpp:98-106, vertical_advection_dycore.cpp:140-149, tridiagonal.cpp:83-97,
- *     copy_stencil.cpp:42-47).  User functors are compile-time types a shared library cannot see, hence the one-line
+ *     (horizontal_diffusion.cpp:98-106, horizontal_diffusion_fused.cpp:86-95, vertical_advection_dycore.cpp:140-149,
+ *     tridiagonal.cpp:83-97, copy_stencil.cpp:42-47).  User functors are compile-time types a shared library cannot see, hence the one-line
  *     registration next to the functor definitions.
  *
  *  2. GENERIC PATHS (need nvcc: the user functors are instantiated inside a __global__ template in the user's
@@ -71,7 +71,7 @@
 namespace gtb200 {
 
     /// Kernels of libgtb200.so a whole spec can be bound to.
-    enum class kernel { none, copy, hori_diff, simple_hori_diff, vert_adv, tridiagonal };
+    enum class kernel { none, copy, hori_diff, hori_diff_fused, simple_hori_diff, vert_adv, tridiagonal };
 
     /// Primary template: a spec made of these user functors (in stage order, duplicates removed) has no named kernel.
     template <class FunctorList>
@@ -174,6 +174,22 @@ namespace gridtools {
                 auto in = as_field(tuple_util::get<0>(ds)), coeff = as_field(tuple_util::get<1>(ds)),
                      out = as_field(tuple_util::get<2>(ds));
                 using T = element_of<std::decay_t<decltype(tuple_util::get<2>(ds))>>;
+                static_assert(std::is_same<T, double>::value || std::is_same<T, float>::value, "float or double");
+                int st = std::is_same<T, double>::value
+                             ? gtb_hori_diff_f64(&in, &coeff, &out, grid.i_size(), grid.j_size(), grid.k_size(), stream)
+                             : gtb_hori_diff_f32(&in, &coeff, &out, grid.i_size(), grid.j_size(), grid.k_size(), stream);
+                gtb200::check(st, "gtb_hori_diff");
+            }
+
+            // horizontal_diffusion_fused.cpp:86-95 : run_single_stage(out_function(), backend, grid, out, in, coeff) -- the
+            // same stencil written as one stage that evaluates lap / flx / fly through call<>; same kernel, other
+            // argument order
+            template <class Grid, class DataStores>
+            void run_named(kernel_c<kernel::hori_diff_fused>, Grid const &grid, DataStores &ds, void *stream) {
+                static_assert(tuple_util::size<DataStores>::value == 3, "hori_diff_fused takes (out, in, coeff)");
+                auto out = as_field(tuple_util::get<0>(ds)), in = as_field(tuple_util::get<1>(ds)),
+                     coeff = as_field(tuple_util::get<2>(ds));
+                using T = element_of<std::decay_t<decltype(tuple_util::get<0>(ds))>>;
                 static_assert(std::is_same<T, double>::value || std::is_same<T, float>::value, "float or double");
                 int st = std::is_same<T, double>::value
                              ? gtb_hori_diff_f64(&in, &coeff, &out, grid.i_size(), grid.j_size(), grid.k_size(), stream)

@@ -82,6 +82,25 @@ namespace cases {
         return out;
     }
 
+    // horizontal_diffusion_fused.cpp:86-95: one stage, lap / flx / fly evaluated through call<>; must give what the
+    // four-stage spec gives
+    template <class T, int Tag = 1, class Traits, class Backend>
+    auto hori_diff_fused(Traits, Backend backend, int ni, int nj, int nk) {
+        constexpr int H = 2;
+        const int d0 = ni + 2 * H, d1 = nj + 2 * H;
+        fun_t in_f = [=](int i, int j, int k) {
+            double x = 1. * i / d0, y = 1. * j / d1;
+            return 5. + 8 * (2. + std::cos(M_PI * (x + 1.5 * y)) + std::sin(2 * M_PI * (x + 1.5 * y))) / 4. + 0.02 * k;
+        };
+        auto hh = ij_halos(d0, d1, H);
+        auto grid = st::make_grid(hh.first, hh.second, st::axis<1>(nk));
+        auto in = make_store<Traits, T const>(d0, d1, nk, H, in_f);
+        auto co = make_store<Traits, T const>(d0, d1, nk, H, [](int i, int j, int) { return 0.025 + 1e-4 * ((i + j) % 5); });
+        auto out = make_store<Traits, T>(d0, d1, nk, H, [](int, int, int) { return -1.; });
+        st::run_single_stage(user::fused_out_f<Tag>(), backend, grid, out, in, co);
+        return out;
+    }
+
     template <class T, class Traits, class Backend>
     auto simple_hori_diff(Traits, Backend backend, int ni, int nj, int nk) {
         constexpr int H = 2;

@@ -86,6 +86,49 @@ namespace user {
         };
     }
 
+    // ---- the same stencil as ONE stage, intermediate results through call<> (horizontal_diffusion_fused.cpp:23-84)
+    template <int Tag>
+    struct fused_flx_f {
+        using out = inout_accessor<0>;
+        using in = in_accessor<1, extent<-1, 2, -1, 1>>;
+        using param_list = make_param_list<out, in>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval) {
+            auto hi = call<lap_f<Tag>>::with(eval, in(1, 0));
+            auto lo = call<lap_f<Tag>>::with(eval, in(0, 0));
+            auto flx = hi - lo;
+            eval(out()) = flx * (eval(in(1, 0)) - eval(in(0, 0))) > 0 ? 0 : flx;
+        }
+    };
+    template <int Tag>
+    struct fused_fly_f {
+        using out = inout_accessor<0>;
+        using in = in_accessor<1, extent<-1, 1, -1, 2>>;
+        using param_list = make_param_list<out, in>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval) {
+            auto hi = call<lap_f<Tag>>::with(eval, in(0, 1));
+            auto lo = call<lap_f<Tag>>::with(eval, in(0, 0));
+            auto fly = hi - lo;
+            eval(out()) = fly * (eval(in(0, 1)) - eval(in(0, 0))) > 0 ? 0 : fly;
+        }
+    };
+    template <int Tag>
+    struct fused_out_f {
+        using out = inout_accessor<0>;
+        using in = in_accessor<1, extent<-2, 2, -2, 2>>;
+        using coeff = in_accessor<2>;
+        using param_list = make_param_list<out, in, coeff>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval) {
+            auto flx_hi = call<fused_flx_f<Tag>>::with(eval, in(0, 0));
+            auto flx_lo = call<fused_flx_f<Tag>>::with(eval, in(-1, 0));
+            auto fly_hi = call<fused_fly_f<Tag>>::with(eval, in(0, 0));
+            auto fly_lo = call<fused_fly_f<Tag>>::with(eval, in(0, -1));
+            eval(out()) = eval(in()) - eval(coeff()) * (flx_hi - flx_lo + fly_hi - fly_lo);
+        }
+    };
+
     // ---- simple horizontal diffusion (simple_hori_diff.cpp:25-61): j-only coefficient fields
     template <int Tag>
     struct wlap_f {

@@ -53,6 +53,14 @@ namespace {
                 cases::same(name("hori_diff f64", ni, nj, nk).c_str(), got, ref, ni + 4, nj + 4, nk, 1e-13, g_failed);
             }
             {
+                // the one-stage call<> formulation on the emulated CTAs against the four-stage spec on cpu_ifirst
+                auto got = cases::hori_diff_fused<double>(tr, be_t(), ni, nj, nk);
+                expect_launches("hori_diff_fused launches", 1);
+                auto ref = cases::hori_diff<double>(tr, ref_t(), ni, nj, nk);
+                cases::same(name("hori_diff as one stage with call<> f64", ni, nj, nk).c_str(), got, ref, ni + 4, nj + 4,
+                    nk, 1e-13, g_failed);
+            }
+            {
                 auto got = cases::hori_diff<float>(tr, be_t(), ni, nj, 3);
                 auto ref = cases::hori_diff<float>(tr, ref_t(), ni, nj, 3);
                 cases::same(name("hori_diff f32", ni, nj, 3).c_str(), got, ref, ni + 4, nj + 4, 3, 1e-5, g_failed);
