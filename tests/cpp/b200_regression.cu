@@ -1,7 +1,7 @@
 // b200_regression.cu -- the stencil::b200 backend tag driven through GridTools' own frontend (stencil::run /
 // run_single_stage, storage::builder, make_grid), compared in the same process with the reference's cpu_ifirst
 // backend on the same inputs.  Tag 0 functors are registered to the named sm_100a kernels, tag 1 functors are not and
-// exercise the generic path.  Built here against /root/reference/include; the binary travels to the GPU box.
+// exercise the generic paths (more of those in b200_generic.cu).  Built here against /root/reference/include; the binary travels to the GPU box.
 //
 //   b200_regression            -> prints one line per case and "ALL PASSED" / "FAILED"; exit code 0 / 1
 #include <cmath>
@@ -24,7 +24,6 @@
 #include <gtb200/boundaries/boundary.hpp>
 #include <gtb200/stencil/b200.hpp>
 
-#include "cases.hpp"
 #include "functors.hpp"
 
 GTB200_REGISTER_SPEC(gtb200::kernel::copy, user::copy_f<0>);
@@ -255,60 +254,6 @@ namespace {
         verify(name.c_str(), out, ones, ni, nj, nk, 0, 1e-14); // tridiagonal.cpp:97
     }
 
-    // Every case of cases.hpp through one of the generic paths of the tag, against cpu_ifirst (whole storages: the
-    // halo must come back untouched).  `Backend` = st::b200<> (fused where fusable: all of these are) or
-    // st::b200<default_stream, stage_by_stage>.
-    template <class Backend>
-    void test_generic_cases(std::string label, int ni, int nj, int nk) {
-        gt::storage::gpu dev;
-        gt::storage::cpu_ifirst host;
-        st::cpu_ifirst<> ref_be;
-        Backend be;
-        auto fwd = [] { return st::execute_forward(); };
-        auto bwd = [] { return st::execute_backward(); };
-        auto name = [&](const char *what) {
-            return label + " " + what + " " + std::to_string(ni) + "x" + std::to_string(nj) + "x" + std::to_string(nk);
-        };
-        cases::same(name("hori_diff f64").c_str(), cases::hori_diff<double>(dev, be, ni, nj, nk),
-            cases::hori_diff<double>(host, ref_be, ni, nj, nk), ni + 4, nj + 4, nk, 1e-12, g_failed);
-        cases::same(name("hori_diff f32").c_str(), cases::hori_diff<float>(dev, be, ni, nj, nk),
-            cases::hori_diff<float>(host, ref_be, ni, nj, nk), ni + 4, nj + 4, nk, 1e-5, g_failed);
-        cases::same(name("simple_hori_diff f64").c_str(), cases::simple_hori_diff<double>(dev, be, ni, nj, nk),
-            cases::simple_hori_diff<double>(host, ref_be, ni, nj, nk), ni + 4, nj + 4, nk, 1e-12, g_failed);
-        cases::same(name("vert_adv f64").c_str(), cases::vert_adv<double>(dev, be, ni, nj, nk),
-            cases::vert_adv<double>(host, ref_be, ni, nj, nk), ni + 6, nj + 6, nk, 1e-12, g_failed);
-        cases::same(name("vert_adv f32").c_str(), cases::vert_adv<float>(dev, be, ni, nj, nk),
-            cases::vert_adv<float>(host, ref_be, ni, nj, nk), ni + 6, nj + 6, nk, 1e-4, g_failed);
-        cases::same(name("tridiagonal").c_str(), cases::tridiagonal(dev, be, ni, nj, 6),
-            cases::tridiagonal(host, ref_be, ni, nj, 6), ni, nj, 6, 1e-12, g_failed);
-        cases::same(name("k-cache fill forward").c_str(), cases::kcache_fill(fwd, dev, be, ni, nj, nk),
-            cases::kcache_fill(fwd, host, ref_be, ni, nj, nk), ni, nj, nk, 0, g_failed);
-        cases::same(name("k-cache fill backward").c_str(), cases::kcache_fill(bwd, dev, be, ni, nj, nk),
-            cases::kcache_fill(bwd, host, ref_be, ni, nj, nk), ni, nj, nk, 0, g_failed);
-        for (bool forward : {true, false}) {
-            cases::same(name(forward ? "k-cache flush forward" : "k-cache flush backward").c_str(),
-                cases::kcache_flush(forward, dev, be, ni, nj, nk), cases::kcache_flush(forward, host, ref_be, ni, nj, nk),
-                ni, nj, nk, 0, g_failed);
-            cases::same(name(forward ? "k-cache fill+flush forward" : "k-cache fill+flush backward").c_str(),
-                cases::kcache_fill_and_flush(forward, dev, be, ni, nj, nk),
-                cases::kcache_fill_and_flush(forward, host, ref_be, ni, nj, nk), ni, nj, nk, 0, g_failed);
-        }
-        cases::same(name("k-cache local, two stages").c_str(), cases::kcache_local(dev, be, ni, nj, nk),
-            cases::kcache_local(host, ref_be, ni, nj, nk), ni, nj, nk, 1e-14, g_failed);
-        cases::same(name("mixed tiles + plain temporaries").c_str(), cases::mixed<double>(dev, be, ni, nj, 2, nk),
-            cases::mixed<double>(host, ref_be, ni, nj, 2, nk), ni + 4, nj + 4, nk + 2, 1e-12, g_failed);
-        {
-            int bad = cases::prepare_tracers(dev, be, ni, nj, nk, 5);
-            std::printf("%-58s %s (%d of 5 tracers differ)\n", name("expandable_run<2>, 5 tracers").c_str(),
-                bad ? "FAILED" : "ok", bad);
-            g_failed += bad != 0;
-        }
-        cases::same(name("forward sweep with IJ extents").c_str(), cases::sweep_with_extents(dev, be, ni, nj, nk),
-            cases::sweep_with_extents(host, ref_be, ni, nj, nk), ni + 6, nj + 6, nk, 1e-12, g_failed);
-        cases::same(name("temporary read at IJ offsets, not cached").c_str(),
-            cases::mixed_plain<double>(dev, be, ni, nj, 2, nk), cases::mixed_plain<double>(host, ref_be, ni, nj, 2, nk),
-            ni + 4, nj + 4, nk + 2, 1e-12, g_failed);
-    }
 } // namespace
 
 int main() {
@@ -336,20 +281,6 @@ int main() {
         test_tridiagonal<0>(12, 33, 6);
         test_tridiagonal<0>(23, 11, 6);
         test_tridiagonal<1>(23, 11, 6);
-        using staged_t = st::b200<gtb200::default_stream, gtb200::stage_by_stage>;
-        test_generic_cases<st::b200<>>("fused", 70, 19, 13);   // partial tiles in i and j, partial k block
-        test_generic_cases<st::b200<>>("fused", 1, 1, 2);
-        test_generic_cases<st::b200<>>("fused", 128, 64, 80);
-        test_generic_cases<staged_t>("staged", 70, 19, 13);
-        // sweeps in separate launches (every read-only field on the ld.global.nc path), three levels unrolled
-        using unchained_t = st::b200<gtb200::default_stream, gtb200::fused_when_possible,
-            gtb200::block_geometry<32, 8, 8, 3, false, 0, false>>;
-        test_generic_cases<unchained_t>("fused, sweeps unchained", 70, 19, 13);
-        // software prefetch in the sweeps (default: 4 levels ahead into L1): off, 8 levels ahead into L2
-        test_generic_cases<st::b200<gtb200::default_stream, gtb200::fused_when_possible,
-            gtb200::block_geometry<32, 8, 8, 3, true, 0, false>>>("fused, no prefetch", 70, 19, 13);
-        test_generic_cases<st::b200<gtb200::default_stream, gtb200::fused_when_possible,
-            gtb200::block_geometry<32, 8, 8, 2, true, 8, false>>>("fused, prefetch 8 L2", 70, 19, 13);
     } catch (std::exception const &e) {
         std::printf("EXCEPTION: %s\n", e.what());
         return 2;
