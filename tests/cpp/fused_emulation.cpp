@@ -146,6 +146,9 @@ int main() {
     run<fused::geometry<8, 4, 3>>{"[8x4x3 blocks]"}.all(1, 1, 2);
     // the default geometry on a domain of a few blocks
     run<fused::geometry<>>{"[32x8x8 blocks]"}.all(37, 11, 10);
+    // extremes: one level per CTA with tiny blocks; all levels in one CTA with a wide block
+    run<fused::geometry<4, 2, 1>>{"[4x2x1 blocks]"}.all(9, 5, 4);
+    run<fused::geometry<64, 4, 80>>{"[64x4x80 blocks]"}.all(70, 6, 5);
     // prefetch ahead (a no-op on the host, but the address arithmetic is instantiated)
     run<fused::geometry<8, 4, 3, 2, true, 4, true>>{"[8x4x3 blocks, prefetch]"}.all(19, 9, 7);
     // sweeps in separate launches

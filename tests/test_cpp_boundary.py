@@ -110,15 +110,15 @@ EMU_BIN = os.path.join(ROOT, "tests", "_build", "fused_emulation")
 def test_fused_generic_path_on_emulated_ctas():
     """tests/_build/fused_emulation (g++ only): the per-thread body of the fused generic path -- thread-to-point mapping,
     shared-memory tiles, register windows with fill / flush, k blocking -- run by emulated CTAs (one OpenMP team per
-    CTA, `omp barrier` for `__syncthreads`) and compared with the reference's cpu_ifirst backend on 13 specs, four
-    block geometries / domain sizes; also one launch per multi-stage."""
+    CTA, `omp barrier` for `__syncthreads`) and compared with the reference's cpu_ifirst backend on 17 specs, eight
+    block geometries / domain sizes / options; also one launch per multi-stage."""
     if not os.path.exists(EMU_BIN):
         pytest.skip("tests/_build/fused_emulation not built (make -C tests/cpp in the build container)")
     env = dict(os.environ, OMP_WAIT_POLICY="passive")
     r = subprocess.run([EMU_BIN], capture_output=True, text=True, timeout=900, env=env)
     print(r.stdout)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
-    assert "ALL PASSED" in r.stdout and r.stdout.count(" ok ") >= 102
+    assert "ALL PASSED" in r.stdout and r.stdout.count(" ok ") >= 136
 
 
 # ------------------------------------------------------------------------------------------------ gcl (C++ class)
