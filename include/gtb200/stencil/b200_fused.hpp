@@ -48,6 +48,7 @@
 #include <gridtools/common/tuple_util.hpp>
 #include <gridtools/meta.hpp>
 #include <gridtools/sid/allocator.hpp>
+#include <gridtools/sid/as_const.hpp>
 #include <gridtools/sid/block.hpp>
 #include <gridtools/sid/composite.hpp>
 #include <gridtools/sid/concept.hpp>

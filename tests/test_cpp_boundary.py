@@ -104,6 +104,55 @@ def test_harness_traits_of_the_tag(tmp_path):
     assert subprocess.run([str(exe)]).returncode == 0
 
 
+FUSABLE_TU = r"""
+#include <cstdio>
+#include <gtb200/stencil/b200_fused.hpp>   // first: the header must be self-sufficient
+#include <gridtools/stencil/cartesian.hpp>
+#include <gridtools/storage/builder.hpp>
+#include <gridtools/storage/cpu_kfirst.hpp>
+#include <gridtools/storage/sid.hpp>
+#include "cases.hpp"
+namespace st = gridtools::stencil;
+namespace gt = gridtools;
+struct probe {
+    static bool &fusable() { static bool v; return v; }
+    template <class Spec, class Grid, class DataStores>
+    friend void gridtools_backend_entry_point(probe, Spec, Grid const &, DataStores) {
+        fusable() = st::b200_backend::fused::fusable<Spec>::value;
+    }
+};
+int main() {
+    auto h = gt::halo_descriptor(0, 0, 0, 3, 4);
+    auto grid = st::make_grid(h, h, cases::kc_axis_t(4));
+    auto mk = [] { return gt::storage::builder<gt::storage::cpu_kfirst>.type<double>().dimensions(4, 4, 4).build(); };
+    st::run([](auto in, auto out) { GT_DECLARE_TMP(double, acc);
+        return st::execute_parallel().k_cached(acc).stage(cases::carry_f(), in, acc).stage(cases::emit_f(), acc, out); },
+        probe(), grid, mk(), mk());
+    bool parallel_with_k_cache = probe::fusable();
+    st::run([](auto in, auto out) { GT_DECLARE_TMP(double, acc);
+        return st::execute_forward().k_cached(acc).stage(cases::carry_f(), in, acc).stage(cases::emit_f(), acc, out); },
+        probe(), grid, mk(), mk());
+    bool sweep_with_k_cache = probe::fusable();
+    std::printf("%d %d\n", parallel_with_k_cache, sweep_with_k_cache);
+    return !(!parallel_with_k_cache && sweep_with_k_cache);
+}
+"""
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference headers only exist in the build container")
+def test_fusable_predicate_and_header_self_sufficiency(tmp_path):
+    """b200_fused.hpp compiles on its own as host code; the one shape the fused path declines (k caches inside a
+    parallel multi-stage) is reported by fused::fusable, a sweep with a k cache is taken."""
+    src = tmp_path / "fusable.cpp"
+    src.write_text(FUSABLE_TU)
+    exe = tmp_path / "fusable"
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O0", "-I" + REF, "-I" + os.path.join(ROOT, "include"),
+           "-I" + os.path.join(ROOT, "tests", "cpp"), str(src), "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert subprocess.run([str(exe)]).returncode == 0
+
+
 EMU_BIN = os.path.join(ROOT, "tests", "_build", "fused_emulation")
 
 
