@@ -15,7 +15,9 @@
 #include <vector>
 
 #include <gridtools/stencil/cartesian.hpp>
+#include <gridtools/sid/rename_dimensions.hpp>
 #include <gridtools/stencil/global_parameter.hpp>
+#include <gridtools/stencil/positional.hpp>
 #include <gridtools/storage/builder.hpp>
 #include <gridtools/storage/sid.hpp>
 
@@ -63,6 +65,8 @@ namespace cases {
             ++failed;
         return bad == 0;
     }
+
+    inline double ramp(int i, int j, int k) { return 1 + i + 0.5 * j + 0.25 * k * k; }
 
     // ------------------------------------------------------------------ specs of functors.hpp
     template <class T, class Traits, class Backend>
@@ -171,8 +175,6 @@ namespace cases {
     // ------------------------------------------------------------------ k-cache patterns
     using kc_axis_t = st::axis<1, st::axis_config::offset_limit<3>>;
     using kc_full_t = kc_axis_t::full_interval;
-
-    inline double ramp(int i, int j, int k) { return 1 + i + 0.5 * j + 0.25 * k * k; }
 
     // out(k) = in(k-1) + in(k) + in(k+1), clipped at both ends: a filled window [-1, 1]
     struct shifted_sum_f {
@@ -420,6 +422,99 @@ namespace cases {
             backend, grid, in, out);
         return out;
     }
+    // ------------------------------------------------------------------ other data stores the frontend hands to a backend
+    // positional_stencil.cpp:20-43: out = i + j + k from positional<dim> "fields" (no memory behind them)
+    struct position_sum_f {
+        using out = inout_accessor<0>;
+        using i_pos = in_accessor<1>;
+        using j_pos = in_accessor<2>;
+        using k_pos = in_accessor<3>;
+        using param_list = make_param_list<out, i_pos, j_pos, k_pos>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval) {
+            eval(out()) = eval(i_pos()) + 100 * eval(j_pos()) + 10000 * eval(k_pos());
+        }
+    };
+    template <class Traits, class Backend>
+    auto positional_sum(Traits, Backend backend, int ni, int nj, int nk) {
+        constexpr int H = 1;
+        const int d0 = ni + 2 * H, d1 = nj + 2 * H;
+        auto hh = ij_halos(d0, d1, H);
+        auto grid = st::make_grid(hh.first, hh.second, st::axis<1>(nk));
+        auto out = make_store<Traits, double>(d0, d1, nk, H, [](int, int, int) { return -1.; });
+        st::run_single_stage(position_sum_f(), backend, grid, out, st::positional<st::dim::i>(),
+            st::positional<st::dim::j>(), st::positional<st::dim::k>());
+        return out;
+    }
+
+    // parallel_multistage_fusion.cpp:26-67: a temporary written by one parallel multi-stage and read one level up by the
+    // next -- the two must not be fused into one launch
+    using pf_axis_t = st::axis<1>;
+    struct fill_level_f {
+        using out = inout_accessor<0>;
+        using k_pos = in_accessor<1>;
+        using param_list = make_param_list<out, k_pos>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval) {
+            eval(out()) = 3 + eval(k_pos());
+        }
+    };
+    struct copy_from_above_f {
+        using in = in_accessor<0, extent<0, 0, 0, 0, 0, 1>>;
+        using out = inout_accessor<1>;
+        using param_list = make_param_list<in, out>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval, pf_axis_t::full_interval::modify<0, -1>) {
+            eval(out()) = eval(in(0, 0, 1));
+        }
+        template <class E>
+        GT_FUNCTION static void apply(E eval, pf_axis_t::full_interval::last_level) {
+            eval(out()) = eval(in());
+        }
+    };
+    template <class Traits, class Backend>
+    auto parallel_multistage(Traits, Backend backend, int ni, int nj, int nk) {
+        auto hh = ij_halos(ni, nj, 0);
+        auto grid = st::make_grid(hh.first, hh.second, pf_axis_t(nk));
+        auto out = make_store<Traits, double>(ni, nj, nk, 0, [](int, int, int) { return -1.; });
+        st::run(
+            [](auto out, auto k_pos) {
+                GT_DECLARE_TMP(double, tmp);
+                return st::multi_pass(st::execute_parallel().stage(fill_level_f(), tmp, k_pos),
+                    st::execute_parallel().stage(copy_from_above_f(), tmp, out));
+            },
+            backend, grid, out, st::positional<st::dim::k>());
+        return out;
+    }
+
+    // whole_axis_access.cpp:24-58: the k dimension of a field renamed to a fourth dimension, so that a stage can walk
+    // the whole column: out(k) = sum of in over the levels below k
+    struct sum_below_f {
+        using out = inout_accessor<0>;
+        using in = in_accessor<1, extent<>, 4>;
+        using k_pos = in_accessor<2>;
+        using param_list = make_param_list<out, in, k_pos>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval) {
+            auto k = eval(k_pos());
+            std::decay_t<decltype(eval(out()))> res = 0;
+            for (int kk = 0; kk < k; ++kk)
+                res += eval(in(0, 0, 0, kk));
+            eval(out()) = res;
+        }
+    };
+    template <class Traits, class Backend>
+    auto whole_axis(Traits, Backend backend, int ni, int nj, int nk) {
+        using namespace gt::literals;
+        auto hh = ij_halos(ni, nj, 0);
+        auto grid = st::make_grid(hh.first, hh.second, st::axis<1>(nk));
+        auto in = make_store<Traits, double>(ni, nj, nk, 0, ramp);
+        auto out = make_store<Traits, double>(ni, nj, nk, 0, [](int, int, int) { return -1.; });
+        st::run_single_stage(sum_below_f(), backend, grid, out,
+            gt::sid::rename_dimensions<st::dim::k, decltype(3_c)>(in), st::positional<st::dim::k>());
+        return out;
+    }
+
     // ------------------------------------------------------------------ expandable_run
     // advection_pdbott_prepare_tracers.cpp:23-52: vectors of stores expanded two at a time by the frontend; the backend
     // sees one spec with two stages (and a second one with the odd tracer left over)

@@ -116,6 +116,24 @@ namespace {
                     ni + 4, nj + 4, nk + 2, 1e-13, g_failed);
             }
             {
+                auto got = cases::positional_sum(tr, be_t(), ni, nj, nk);
+                auto ref = cases::positional_sum(tr, ref_t(), ni, nj, nk);
+                cases::same(name("positional<i,j,k>", ni, nj, nk).c_str(), got, ref, ni + 2, nj + 2, nk, 0, g_failed);
+            }
+            {
+                auto got = cases::parallel_multistage(tr, be_t(), ni, nj, nk);
+                expect_launches("parallel multistage launches", 2);
+                auto ref = cases::parallel_multistage(tr, ref_t(), ni, nj, nk);
+                cases::same(name("two parallel multi-stages, temporary read at k+1", ni, nj, nk).c_str(), got, ref, ni,
+                    nj, nk, 0, g_failed);
+            }
+            {
+                auto got = cases::whole_axis(tr, be_t(), ni, nj, nk);
+                auto ref = cases::whole_axis(tr, ref_t(), ni, nj, nk);
+                cases::same(name("whole axis through a renamed k dimension", ni, nj, nk).c_str(), got, ref, ni, nj, nk, 0,
+                    g_failed);
+            }
+            {
                 int bad = cases::prepare_tracers(tr, be_t(), ni, nj, nk, 5);
                 std::printf("%-58s %s (%d of 5 tracers differ)\n", name("expandable_run<2>, 5 tracers", ni, nj, nk).c_str(),
                     bad ? "FAILED" : "ok", bad);
