@@ -157,7 +157,31 @@ namespace {
     };
 } // namespace
 
+// c_array_copy.cpp:22-46: plain C arrays are SIDs too (compile-time strides, k fastest)
+void c_arrays() {
+    int out[7][5][3];
+    decltype(out) in;
+    int n = 0;
+    for (auto &&vvv : in)
+        for (auto &&vv : vvv)
+            for (auto &&v : vv)
+                v = n++;
+    for (auto &&vvv : out)
+        for (auto &&vv : vvv)
+            for (auto &&v : vv)
+                v = -1;
+    st::run_single_stage(user::copy_f<1>(), emulated::backend<fused::geometry<4, 2, 2>>(), st::make_grid(7, 5, 3), in, out);
+    int bad = 0;
+    for (int i = 0; i < 7; ++i)
+        for (int j = 0; j < 5; ++j)
+            for (int k = 0; k < 3; ++k)
+                bad += out[i][j][k] != in[i][j][k];
+    std::printf("%-58s %s (mismatches %d)\n", "copy between C arrays 7x5x3 [4x2x2 blocks]", bad ? "FAILED" : "ok", bad);
+    g_failed += bad != 0;
+}
+
 int main() {
+    c_arrays();
     // small blocks: many CTAs, partial tiles in i and j, partial k blocks
     run<fused::geometry<8, 4, 3>>{"[8x4x3 blocks]"}.all(19, 9, 7);
     run<fused::geometry<8, 4, 3>>{"[8x4x3 blocks]"}.all(8, 4, 3);
