@@ -86,9 +86,16 @@ namespace gtb200 {
     struct stage_by_stage {};
 #ifdef __CUDACC__
     /// IJ block and levels per CTA of the fused generic path (third template argument of stencil::b200).
-    template <int BI, int BJ, int KB, int SweepUnroll = 3, bool ChainSweeps = true, int Prefetch = 4, bool PrefetchL1 = true>
-    using block_geometry =
-        ::gridtools::stencil::b200_backend::fused::geometry<BI, BJ, KB, SweepUnroll, ChainSweeps, Prefetch, PrefetchL1>;
+    template <int BI,
+        int BJ,
+        int KB,
+        int SweepUnroll = 3,
+        bool ChainSweeps = true,
+        int Prefetch = 4,
+        bool PrefetchL1 = true,
+        int ParallelPrefetch = 0>
+    using block_geometry = ::gridtools::stencil::b200_backend::fused::
+        geometry<BI, BJ, KB, SweepUnroll, ChainSweeps, Prefetch, PrefetchL1, ParallelPrefetch>;
     using default_geometry = ::gridtools::stencil::b200_backend::fused::geometry<>;
 #else
     struct default_geometry {};

@@ -87,10 +87,14 @@ namespace gridtools {
                     int_t SweepUnroll = 3,
                     bool ChainSweeps = true,
                     int_t Prefetch = 4,
-                    bool PrefetchL1 = true>
+                    bool PrefetchL1 = true,
+                    int_t ParallelPrefetch = 0>
                 struct geometry {
                     static constexpr int_t bi = BI, bj = BJ, kb = KB, sweep_unroll = SweepUnroll, prefetch = Prefetch;
                     static constexpr bool chain_sweeps = ChainSweeps, prefetch_l1 = PrefetchL1;
+                    // the same inside the KB levels a CTA of a parallel multi-stage walks (every thread asks for its
+                    // own point of the halo-extended tile; not measured yet, hence off)
+                    static constexpr int_t parallel_prefetch = ParallelPrefetch;
                 };
 
                 template <class Extent>
@@ -330,6 +334,7 @@ namespace gridtools {
                                 }
                                 sid::shift(ptr, sid::get_stride<dim::k>(m_strides), lo);
                                 for (int_t k = lo; k < hi; ++k) {
+                                    prefetch_ahead<Geo::parallel_prefetch>(ptr, p, hi - k);
                                     exec_cells(info, ptr, p);
                                     info.inc_k(ptr, m_strides);
                                 }
@@ -410,11 +415,11 @@ namespace gridtools {
                     template <class Info>
                     using memory_key = meta::if_<is_plain<Info>, typename Info::key_t, behind<typename Info::plh_t>>;
 
-                    template <class Ptr>
+                    template <int_t Distance, class Ptr>
                     GT_FUNCTION void prefetch_ahead(Ptr const &ptr, point const &p, int_t levels_left) const {
-                        if constexpr (Geo::prefetch > 0) {
-                            if (levels_left <= Geo::prefetch)
-                                return; // level k + Prefetch is not part of this sweep
+                        if constexpr (Distance > 0) {
+                            if (levels_left <= Distance)
+                                return; // level k + Distance is not part of this sweep / of this CTA's levels
                             host_device::for_each<meta::filter<is_streamed_in, plh_map_t>>([&](auto info)
                                                                                             GT_FORCE_INLINE_LAMBDA {
                                 using info_t = decltype(info);
@@ -424,7 +429,7 @@ namespace gridtools {
                                 auto mem = host_device::at_key<key_t>(ptr);
                                 sid::shift(mem,
                                     sid::get_stride_element<key_t, dim::k>(m_strides),
-                                    integral_constant<int_t, Geo::prefetch * step_t::value>());
+                                    integral_constant<int_t, Distance * step_t::value>());
                                 prefetch_line<Geo::prefetch_l1>(mem);
                             });
                         }
@@ -449,7 +454,7 @@ namespace gridtools {
                             [&](int_t size, auto info) GT_FORCE_INLINE_LAMBDA {
 #pragma unroll(Geo::sweep_unroll)
                                 for (int_t k = 0; k < size; ++k) {
-                                    prefetch_ahead(mixed.secondary(), p, total - n);
+                                    prefetch_ahead<Geo::prefetch>(mixed.secondary(), p, total - n);
                                     sync_caches<true>(windows, mixed.secondary(), p, k_pos, n == 0);
                                     exec_cells(info, mixed, p);
                                     sync_caches<false>(windows, mixed.secondary(), p, k_pos, n == total - 1);

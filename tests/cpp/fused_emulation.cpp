@@ -192,7 +192,7 @@ int main() {
     run<fused::geometry<4, 2, 1>>{"[4x2x1 blocks]"}.all(9, 5, 4);
     run<fused::geometry<64, 4, 80>>{"[64x4x80 blocks]"}.all(70, 6, 5);
     // prefetch ahead (a no-op on the host, but the address arithmetic is instantiated)
-    run<fused::geometry<8, 4, 3, 2, true, 4, true>>{"[8x4x3 blocks, prefetch]"}.all(19, 9, 7);
+    run<fused::geometry<8, 4, 3, 2, true, 4, true, 1>>{"[8x4x3 blocks, prefetch]"}.all(19, 9, 7);
     // sweeps in separate launches
     run<fused::geometry<8, 4, 3, 2, false>>{"[8x4x3 blocks, unchained]"}.all(19, 9, 7);
     std::printf(g_failed ? "FAILED (%d)\n" : "ALL PASSED\n", g_failed);
