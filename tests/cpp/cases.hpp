@@ -515,6 +515,59 @@ namespace cases {
         return out;
     }
 
+    // ------------------------------------------------------------------ several element types in one spec
+    // (test_multi_types.cpp): a float tile and a double tile side by side in shared memory, an int field, a double output
+    struct to_float_f {
+        using t = inout_accessor<0>;
+        using in = in_accessor<1, extent<-1, 1, 0, 0>>;
+        using param_list = make_param_list<t, in>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval) {
+            eval(t()) = float(eval(in(1, 0)) - eval(in(-1, 0)));
+        }
+    };
+    struct widen_f {
+        using d = inout_accessor<0>;
+        using t = in_accessor<1, extent<0, 0, -1, 1>>;
+        using n = in_accessor<2>;
+        using param_list = make_param_list<d, t, n>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval) {
+            eval(d()) = double(eval(t(0, 1))) + double(eval(t(0, -1))) + eval(n());
+        }
+    };
+    struct gather_f {
+        using out = inout_accessor<0>;
+        using d = in_accessor<1, extent<-1, 1, 0, 0>>;
+        using param_list = make_param_list<out, d>;
+        template <class E>
+        GT_FUNCTION static void apply(E eval) {
+            eval(out()) = eval(d(-1, 0)) + eval(d(1, 0));
+        }
+    };
+    template <class Traits, class Backend>
+    auto multi_types(Traits, Backend backend, int ni, int nj, int nk) {
+        constexpr int H = 3;
+        const int d0 = ni + 2 * H, d1 = nj + 2 * H;
+        auto hh = ij_halos(d0, d1, H);
+        auto grid = st::make_grid(hh.first, hh.second, st::axis<1>(nk));
+        auto in = make_store<Traits, double>(d0, d1, nk, H, [](int i, int j, int k) { return 0.5 * i * i + j + 0.25 * k; });
+        auto n = make_store<Traits, int>(d0, d1, nk, H, [](int i, int j, int k) { return i + 2 * j + 3 * k; });
+        auto out = make_store<Traits, double>(d0, d1, nk, H, [](int, int, int) { return -3.; });
+        st::run(
+            [](auto in, auto n, auto out) {
+                GT_DECLARE_TMP(float, t);
+                GT_DECLARE_TMP(double, d);
+                return st::execute_parallel()
+                    .ij_cached(t, d)
+                    .stage(to_float_f(), t, in)
+                    .stage(widen_f(), d, t, n)
+                    .stage(gather_f(), out, d);
+            },
+            backend, grid, in, n, out);
+        return out;
+    }
+
     // ------------------------------------------------------------------ expandable_run
     // advection_pdbott_prepare_tracers.cpp:23-52: vectors of stores expanded two at a time by the frontend; the backend
     // sees one spec with two stages (and a second one with the odd tracer left over)

@@ -134,6 +134,13 @@ namespace {
                     g_failed);
             }
             {
+                auto got = cases::multi_types(tr, be_t(), ni, nj, nk);
+                expect_launches("multi types launches", 1);
+                auto ref = cases::multi_types(tr, ref_t(), ni, nj, nk);
+                cases::same(name("float and double tiles, int field", ni, nj, nk).c_str(), got, ref, ni + 6, nj + 6, nk,
+                    0, g_failed);
+            }
+            {
                 int bad = cases::prepare_tracers(tr, be_t(), ni, nj, nk, 5);
                 std::printf("%-58s %s (%d of 5 tracers differ)\n", name("expandable_run<2>, 5 tracers", ni, nj, nk).c_str(),
                     bad ? "FAILED" : "ok", bad);

@@ -167,7 +167,7 @@ def test_fused_generic_path_on_emulated_ctas():
     r = subprocess.run([EMU_BIN], capture_output=True, text=True, timeout=900, env=env)
     print(r.stdout)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
-    assert "ALL PASSED" in r.stdout and r.stdout.count(" ok ") >= 161
+    assert "ALL PASSED" in r.stdout and r.stdout.count(" ok ") >= 169
 
 
 # ------------------------------------------------------------------------------------------------ gcl (C++ class)
