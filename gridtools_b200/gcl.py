@@ -242,10 +242,21 @@ class halo_exchange_dynamic_ut:
 
     def _export(self):
         L = _lib.lib()
-        desc = (_lib.HaloDesc * 3)(*[_lib.HaloDesc(*h) for h in self.plan.halos])
+        # elements wider than 8 bytes (the reference's own test exchanges array<int, 4>) travel as `f` consecutive
+        # 8- (or 4-) byte words: the unit-stride dimension is scaled by f, the byte order of a message is unchanged
+        es, f = self.dtype.itemsize, 1
+        if es not in (4, 8):
+            word = 8 if es % 8 == 0 else 4
+            if es % word:
+                raise ValueError("element size %d is not a multiple of 4 bytes" % es)
+            es, f = word, es // word
+        halos = list(self.plan.halos)
+        m, p, b, e, t = halos[0]
+        halos[0] = (m * f, p * f, b * f, e * f + f - 1, t * f)
+        desc = (_lib.HaloDesc * 3)(*[_lib.HaloDesc(*h) for h in halos])
         nbr = (C.c_int * 27)(*self.plan.neighbour)
         h = C.c_void_p()
-        _lib.check(L.gtb_halo_create(desc, nbr, self.grid.rank, self.max_fields, self.dtype.itemsize, C.byref(h)))
+        _lib.check(L.gtb_halo_create(desc, nbr, self.grid.rank, self.max_fields, es, C.byref(h)))
         self._h = h
         buf = C.create_string_buffer(_lib.HALO_BLOB_BYTES)
         _lib.check(L.gtb_halo_export(self._h, buf))

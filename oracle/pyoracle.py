@@ -150,6 +150,35 @@ def halo_exchange_all(h, dims, periodic, fields, elem_size):
                                      ptrs, n_fields, elem_size), "gto_halo_exchange_all")
 
 
+def ref_gcl_exchange(halos, proc_dims, periodic, fields, layout=(2, 1, 0), proc_layout=(0, 1, 2), use_vector=True,
+                     generic=False, split_phase=False):
+    """The REFERENCE's own gcl (oracle/ref_gcl.cpp over oracle/mpi_shim/mpi.h, threads as ranks): one pack / exchange /
+    unpack of gcl::halo_exchange_dynamic_ut<layout_map<*layout>, layout_map<*proc_layout>, T, gcl::cpu> or, with
+    generic=True, gcl::halo_exchange_generic<layout_map<*proc_layout>, gcl::cpu> with one field_on_the_fly per field.
+
+    layout: the reference's T_layout_map values (GridTools convention: the dimension with value 2 has unit stride);
+    halos: (minus, plus, begin, end, total) per USER dimension -- three for dynamic_ut, n_fields x three for generic;
+    periodic: USER dimension order; fields: list over ranks (row-major Cartesian ranks) of lists of C-contiguous numpy
+    arrays addressed as storage memory (modified in place); element size 4, 8 or 16 bytes."""
+    n_fields = len(fields[0])
+    flat = [f for r in fields for f in r]
+    assert all(f.flags.c_contiguous for f in flat)
+    esz = flat[0].dtype.itemsize
+    hs = [int(x) for h in halos for x in (h if np.isscalar(h[0]) else [y for t in h for y in t])]
+    assert len(hs) == (15 * n_fields if generic else 15), len(hs)
+    ptrs = (C.c_void_p * len(flat))(*[f.ctypes.data for f in flat])
+    i3 = lambda v: (C.c_int * 3)(*[int(x) for x in v])
+    _chk(ref().gtref_gcl_exchange(i3(layout), i3(proc_layout), i3(proc_dims), i3(periodic), (C.c_int * len(hs))(*hs),
+                                  esz, n_fields, ptrs, int(use_vector), int(generic), int(split_phase)),
+         "gtref_gcl_exchange")
+
+
+def ref_gcl_proc(proc_dims, periodic, rank, di, dj, dk):
+    """MPI_3D_process_grid_t<3>::proc(di, dj, dk) of `rank` (proc_grids_3D.hpp:179-211), periodic in grid order."""
+    i3 = lambda v: (C.c_int * 3)(*[int(x) for x in v])
+    return ref().gtref_gcl_proc(i3(proc_dims), i3(periodic), rank, di, dj, dk)
+
+
 def boundary_apply(h, mask, kind, value, fields):
     """boundaries/apply.hpp:44-56; fields: numpy arrays [d2, d1, d0] (modified in place); mask: 27 ints or None."""
     ptrs = (C.c_void_p * len(fields))(*[f.ctypes.data for f in fields])

@@ -93,8 +93,27 @@ def boundary(name):
     np.savez_compressed(os.path.join(HERE, name), **out)
 
 
+def halo(name, proc_dims, periodic, layout=(2, 1, 0), n_fields=2):
+    """One pack / exchange / unpack of the reference's gcl::halo_exchange_dynamic_ut<layout, <0,1,2>, double, cpu>
+    (run with threads as ranks through oracle/mpi_shim/mpi.h) on random boxes; halos in USER dimension order."""
+    h = [(2, 3, 2, 9, 14), (1, 2, 1, 6, 10), (0, 1, 0, 4, 6)]
+    order = np.argsort(layout)
+    shape = tuple(h[d][4] for d in order)
+    n = proc_dims[0] * proc_dims[1] * proc_dims[2]
+    rng = np.random.default_rng(7)
+    start = rng.standard_normal((n, n_fields) + shape)
+    res = [[start[r, f].copy() for f in range(n_fields)] for r in range(n)]
+    o.ref_gcl_exchange(h, proc_dims, periodic, res, layout=layout)
+    np.savez_compressed(os.path.join(HERE, name), halos=np.array(h), proc_dims=np.array(proc_dims),
+                        periodic=np.array(periodic), layout=np.array(layout), n_fields=n_fields, start=start,
+                        result=np.array(res))
+
+
 if __name__ == "__main__":
     o.build(ref=True)
+    halo("halo_2x2x1_p101.npz", (2, 2, 1), (1, 0, 1))
+    halo("halo_2x4x1_p000.npz", (2, 4, 1), (0, 0, 0))
+    halo("halo_1x2x2_p010_l021.npz", (1, 2, 2), (0, 1, 0), layout=(0, 2, 1))
     hori_diff(12, 33, 6, "hori_diff_12x33x6.npz")     # test_environment sizes 12x33 (k shortened)
     hori_diff(70, 19, 3, "hori_diff_70x19x3.npz")     # crosses a 64-wide tile boundary
     vert_adv(13, 7, 61, "vert_adv_13x7x61.npz")       # 61 levels like the 12x33x61 environment

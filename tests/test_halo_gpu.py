@@ -241,3 +241,103 @@ def test_generic_exchange_two_field_shapes(gt, oracle):
         assert np.array_equal(dev[r][1][0].cpu().numpy(), eb[r][0]), r
     for hg in hgs:
         hg.close()
+
+
+# ---------------------------------------------------------------------- pinned on the reference's own gcl
+LAYOUTS = [(0, 1, 2), (0, 2, 1), (1, 0, 2), (1, 2, 0), (2, 0, 1), (2, 1, 0)]  # T_layout_map, 2 = unit stride
+
+
+def _exchange_layout(gt, user_halos, proc_dims, per_user, layout_gt, proc_layout, start, use_vector):
+    """The CUDA exchange for in-process ranks with a data layout / process layout; `start` = [rank][field] host
+    arrays in storage order.  Returns the exchanged copies."""
+    inc = tuple(2 - v for v in layout_gt)
+    per_grid = [0, 0, 0]
+    for d in range(3):
+        per_grid[proc_layout[d]] = per_user[d]
+    n = proc_dims[0] * proc_dims[1] * proc_dims[2]
+    hes, dev = [], []
+    for r in range(n):
+        grid = gt.gcl.ProcGrid(proc_dims, per_grid, r)
+        he = gt.gcl.halo_exchange_dynamic_ut(per_user, grid, start[r][0].dtype, layout=inc, proc_layout=proc_layout,
+                                             comm=None, transport="p2p")
+        for d in range(3):
+            he.add_halo(d, *user_halos[d])
+        he.setup(len(start[r]))
+        hes.append(he)
+        dev.append([gt.torch.from_numpy(a.view(np.uint8).copy()).cuda() for a in start[r]])
+    gt.gcl.connect_local(hes)
+    for he, d in zip(hes, dev):
+        ptrs = [t.data_ptr() for t in d]
+        he.pack(ptrs) if use_vector else he.pack(*ptrs)
+    for he, d in zip(hes, dev):
+        ptrs = [t.data_ptr() for t in d]
+        he.exchange()
+        he.unpack(ptrs) if use_vector else he.unpack(*ptrs)
+    gt.torch.cuda.synchronize()
+    for he in hes:
+        assert he.check() == 0
+        he.close()
+    return [[t.cpu().numpy().view(a.dtype).reshape(a.shape) for t, a in zip(d, s)] for d, s in zip(dev, start)]
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_all_layouts_interfaces_periodicities_equal_reference_gcl(gt, oracle, layout):
+    """The sweep of tests/regression/gcl/test_halo_exchange_3D.cpp:150-172,195-208: 6 layouts x {vector, variadic} x
+    2^3 periodicities, 16-byte elements (array<int, 4>) and doubles; the expectation is the REFERENCE's gcl run by
+    oracle/_ref/libgtref.so (threads as ranks over oracle/mpi_shim/mpi.h)."""
+    import itertools
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/libgtref.so missing")
+    rng = np.random.default_rng(17)
+    user_halos = [(2, 3, 2, 24, 28), (4, 4, 4, 15, 20), (3, 3, 3, 9, 13)]  # spec 2 of the reference test, padded in i
+    order = np.argsort(layout)
+    shape = tuple(user_halos[d][4] for d in order)
+    for proc_dims in [(2, 1, 2), (2, 2, 1)]:
+        n = proc_dims[0] * proc_dims[1] * proc_dims[2]
+        for per in itertools.product((1, 0), repeat=3):
+            for use_vector, dtype in ((True, "V16"), (False, np.float64)):
+                if dtype == "V16":
+                    start = [[rng.integers(0, 1 << 30, shape + (4,)).astype(np.int32).view("V16").reshape(shape)
+                              for _ in range(3)] for _ in range(n)]
+                else:
+                    start = [[rng.standard_normal(shape) for _ in range(3)] for _ in range(n)]
+                want = [[a.copy() for a in r] for r in start]
+                oracle.ref_gcl_exchange(user_halos, proc_dims, per, want, layout=layout, use_vector=use_vector)
+                got = _exchange_layout(gt, user_halos, proc_dims, per, layout, (0, 1, 2), start, use_vector)
+                for r in range(n):
+                    for f in range(3):
+                        assert got[r][f].tobytes() == want[r][f].tobytes(), (proc_dims, per, dtype, r, f)
+
+
+@pytest.mark.parametrize("proc_layout", [(1, 0, 2), (2, 1, 0)])
+def test_process_layouts_equal_reference_gcl(gt, oracle, proc_layout):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/libgtref.so missing")
+    rng = np.random.default_rng(19)
+    user_halos = [(2, 3, 2, 9, 14), (1, 2, 1, 6, 10), (0, 1, 0, 4, 6)]
+    for layout in [(2, 1, 0), (0, 1, 2), (1, 2, 0)]:
+        order = np.argsort(layout)
+        shape = tuple(user_halos[d][4] for d in order)
+        for proc_dims, per in [((2, 2, 1), (1, 0, 1)), ((1, 2, 2), (0, 1, 0)), ((3, 1, 2), (1, 1, 1))]:
+            n = proc_dims[0] * proc_dims[1] * proc_dims[2]
+            start = [[rng.standard_normal(shape).astype(np.float32) for _ in range(2)] for _ in range(n)]
+            want = [[a.copy() for a in r] for r in start]
+            oracle.ref_gcl_exchange(user_halos, proc_dims, per, want, layout=layout, proc_layout=proc_layout)
+            got = _exchange_layout(gt, user_halos, proc_dims, per, layout, proc_layout, start, True)
+            for r in range(n):
+                for f in range(2):
+                    assert got[r][f].tobytes() == want[r][f].tobytes(), (layout, proc_dims, per, r, f)
+
+
+@pytest.mark.parametrize("name", ["halo_2x2x1_p101", "halo_2x4x1_p000", "halo_1x2x2_p010_l021"])
+def test_golden_halo_vectors_on_the_device(gt, golden, name):
+    """tests/golden/halo_*.npz: written by make_golden.py from the reference's gcl."""
+    g = golden(name + ".npz")
+    halos, dims, per = [tuple(int(x) for x in h) for h in g["halos"]], tuple(g["proc_dims"]), tuple(g["periodic"])
+    layout, n_fields = tuple(int(x) for x in g["layout"]), int(g["n_fields"])
+    n = dims[0] * dims[1] * dims[2]
+    start = [[g["start"][r, f].copy() for f in range(n_fields)] for r in range(n)]
+    got = _exchange_layout(gt, halos, dims, per, layout, (0, 1, 2), start, True)
+    for r in range(n):
+        for f in range(n_fields):
+            assert np.array_equal(got[r][f], g["result"][r, f]), (r, f)
