@@ -195,8 +195,8 @@ def time_reference(stencil, steps, warmup):
             o.ref_run(o.HORI_DIFF, backend, [inp, coeff], [res], NI, NJ, NK, nrep=warmup, flush=True)
             times = o.ref_run(o.HORI_DIFF, backend, [inp, coeff], [res], NI, NJ, NK, nrep=steps, flush=True)
         if best is None or statistics.median(times) < statistics.median(best[1]):
-            best = (backend, times)
-    return best[0], best[1], o.ref_num_threads()
+            best = (backend, times, res)
+    return best[0], best[1], o.ref_num_threads(), best[2]
 
 
 def reference_arm(args):
@@ -204,7 +204,7 @@ def reference_arm(args):
     if rank != 0:
         return
     steps = min(args.steps, 50)  # bounded sample: each step is one full 256x256x80 application (~5-15 ms)
-    backend, times, cores = time_reference(args.stencil, steps, min(args.warmup, 5))
+    backend, times, cores, _ = time_reference(args.stencil, steps, min(args.warmup, 5))
     sec = statistics.median(times)
     mpts = NI * NJ * NK / sec / 1e6
     sample = "%d timed applications of %s %dx%dx%d fp64 on stencil::%s, cache flush before each, median" % (
@@ -272,7 +272,10 @@ def b200_arm(args):
     # ---- fields: two rotating sets per rank
     global NI, NJ
     dims = gcl.ProcGrid.dims_create(world)
-    grid = gcl.ProcGrid(dims, (False, False, False), rank)
+    # GTB_PERIODIC=1 (diagnosis): periodic process grid, every rank has all 8 IJ neighbours (itself where a dimension
+    # has one rank) -- the exchange load of an interior rank of a large grid on as few as 2 GPUs
+    periodic = (True, True, False) if os.environ.get("GTB_PERIODIC") == "1" else (False, False, False)
+    grid = gcl.ProcGrid(dims, periodic, rank)
     name = args.stencil
     H = HALO[name]
     np_dtype = np.float64 if args.dtype == "f64" else np.float32
@@ -286,7 +289,7 @@ def b200_arm(args):
     n_fields = 5 if name == "vert_adv" else 3
     set_bytes = n_fields * (NI + 2 * H + 16) * (NJ + 2 * H) * NK * itemsize
     # enough rotating sets that no step finds its inputs in the 126 MB L2; one set when a set alone is far larger
-    n_sets = 1 if set_bytes > (1 << 30) else (2 if name == "vert_adv" else 3)
+    n_sets = 1 if set_bytes > (1 << 30) else 4  # >= 4 independent field sets
     n_sets = int(os.environ.get("GTB_NSETS", n_sets))
     on_device = NI * NJ * NK > 32 * 2**20
     sets = []
@@ -311,8 +314,7 @@ def b200_arm(args):
     # ---- halo exchange object (N > 1): the field with an IJ extent (wcon resp. in), one per set
     he = None
     if world > 1:
-        he = gcl.halo_exchange_dynamic_ut((False, False, False), grid, np_dtype, comm=gcl.TorchComm(),
-                                          transport="p2p")
+        he = gcl.halo_exchange_dynamic_ut(periodic, grid, np_dtype, comm=gcl.TorchComm(), transport="p2p")
         f0 = sets[0][0]
         p0, d1, d2 = f0.padded_lengths
         he.add_halo(0, H, H, H, H + NI - 1, p0)
@@ -341,17 +343,22 @@ def b200_arm(args):
     # stream).  exchange(s+1) touches field set (s+1) % n_sets, last read by stencil(s+1-n_sets): event dependency.
     # The whole loop is recorded once as a gtb_seq (include/gtb200.h) and issued natively: three launches and four
     # stream/event operations per 27-60 us step are more than per-call ctypes marshalling leaves room for.
-    total_steps = max(args.warmup, 3) + args.steps
+    # Timed region at N > 1: the ranks leave a host barrier hundreds of microseconds apart, and a rank that starts early
+    # waits for its neighbours' first halos, so timing from the first launch after the barrier charges that start skew
+    # to the steps (round 1: 9-12 us per step at --steps 20).  The K timed steps are therefore issued in the SAME
+    # native call as LEAD un-timed lead-in steps; the start mark is recorded in the compute stream after the last
+    # lead-in stencil, when the exchange has put the ranks in lock-step, the end mark after the last timed stencil.
+    LEAD = 3 if he is not None else 0
     n_warm = max(args.warmup, 3)
+    total_steps = n_warm + LEAD + args.steps
     seq, step_ops = None, []
     gated = False
+    first_timed_op = [0]
 
     def build_sequence(use_gates):
         """The loop of total_steps steps as one gtb_seq.  use_gates: the two orderings between the streams (stencil
         after unpack, unpack after the stencil that last read the halos) are waits ON THE DEVICE (gtb_stencil_gate /
-        gtb_halo_gate) instead of stream events.  Measured (profiles/README.md): 2 us per step cheaper for vert_adv on one
-        GPU that is its own neighbour, no gain between two real GPUs (57.9 against 56.6-56.8 us), 3 us dearer for
-        hori_diff -- so stream events stay the default and GTB_GATES=1 selects the gates."""
+        gtb_halo_gate) instead of stream events (GTB_GATES=1)."""
         sq, ops = stencil.Sequence(), []
         M = n_sets + 2  # event slots: exchange done = s % M, stencil done = M + s % M
         done = torch.zeros(1, dtype=torch.int64, device="cuda") if use_gates else None
@@ -370,6 +377,9 @@ def b200_arm(args):
 
         for s in range(total_steps):
             first = len(sq)
+            if s == n_warm + LEAD:
+                sq.mark(0, comp_h)
+                first_timed_op[0] = first
             if s == 0:
                 add_exchange(0)
             if s + 1 < total_steps:
@@ -385,12 +395,18 @@ def b200_arm(args):
             if not use_gates:
                 sq.record(M + s % M, comp_h)
             ops.append((first, len(sq) - first))
+        sq.mark(1, comp_h)
+        ops[-1] = (ops[-1][0], ops[-1][1] + 1)
         sq.keep = done
         return sq, ops
 
     if he is not None:
         _lib.set_option("reserve_sms", int(os.environ.get("GTB_RESERVE_SMS", RESERVE_SMS)))  # left to the exchange
         _lib.set_option("halo.fused", int(os.environ.get("GTB_HALO_FUSED", HALO_FUSED)))
+        if "GTB_PDL" in os.environ:
+            _lib.set_option("pdl", int(os.environ["GTB_PDL"]))
+        if "GTB_HALO_MAX_BLOCKS" in os.environ:
+            _lib.set_option("halo.max_blocks", int(os.environ["GTB_HALO_MAX_BLOCKS"]))
         gated = name == "vert_adv" and itemsize == 8 and os.environ.get("GTB_GATES", "0") == "1"  # opt-in, see docstring
         seq, step_ops = build_sequence(gated)
 
@@ -444,20 +460,20 @@ def b200_arm(args):
         torch.cuda.synchronize()
         per_step = [ev[s].elapsed_time(ev[s + 1]) for s in range(len(ev) - 1)]
     else:  # one native call issues the K timed steps; the compute stream's events bracket them
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        seq.run(step_ops[n_warm][0], sum(c for _, c in step_ops[n_warm:]))
-        ev1.record()
+        seq.run(step_ops[n_warm][0], sum(c for _, c in step_ops[n_warm:]))  # LEAD lead-in steps, mark, K steps, mark
         barrier()
-        total_ms = ev0.elapsed_time(ev1)
-        launches = _lib.launch_count() - launches0
+        total_ms = seq.elapsed_ms(0, 1)
+        launches = (_lib.launch_count() - launches0) * args.steps // (args.steps + LEAD)
         per_step = [total_ms / args.steps]
         if he.check() != 0:
             raise SystemExit("bench.py: a halo wait timed out in the timed region")
+    rank_ms = [total_ms / args.steps]
     if world > 1:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        rank_ms = [float(x.item()) / args.steps for x in allt]
+        total_ms = max(float(x.item()) for x in allt)
     ms_per_step = total_ms / args.steps
     pts = NI * NJ * NK
     value = n_gpus * pts / (ms_per_step * 1e-3) / 1e6
@@ -512,6 +528,10 @@ def b200_arm(args):
                        sum(f.nbytes_host for f in sets[0][:5 if name == "vert_adv" else 2]) // 2**20, n_sets),
                    "vs_baseline_ref": "reference stencil::gpu on P100, BASELINE.md section 1"},
         "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
+        "rank_ms_per_step": rank_ms,
+        "timing": ("marks in the compute stream of every rank after %d lead-in steps issued in the same native call "
+                   "(ranks in lock-step), max over ranks" % LEAD) if seq is not None else
+        "one CUDA event pair around the K back-to-back steps",
         "step_ms_median": statistics.median(per_step), "step_ms_p90": sorted(per_step)[int(0.9 * len(per_step))],
         "step_ms_max": max(per_step), "step_ms_note": "second pass with an event after every step (+~2.4 us per step)"
         if seq is None else "timed region / steps",
@@ -527,17 +547,35 @@ def b200_arm(args):
             e["value"] = n_gpus * pts / (e["ms_per_step"] * 1e-3) / 1e6
         line["e2e"] = e
     if rank == 0 and extras and world == 1:
-        try:
-            backend, times, cores = time_reference(name, 20, 2)
-            sec = statistics.median(times)
-            line["cpu_baseline"] = {
-                "value": pts / sec / 1e6, "unit": "Mpts/s", "cores": cores, "kind": "reference",
-                "sample": "20 timed applications of %s %dx%dx%d fp64 on the reference's stencil::%s (best of "
-                          "cpu_ifirst/cpu_kfirst), cache flush before each, median" % (name, NI, NJ, NK, backend)}
-        except Exception as e:  # the checker library is not part of the product
-            line["cpu_baseline"] = {"value": None, "unit": "Mpts/s", "cores": 0, "kind": "reference",
-                                    "sample": "unavailable: %s" % e}
-        line["also"] = secondary(torch, stencil, storage, "hori_diff" if name == "vert_adv" else "vert_adv", peak)
+        other = "hori_diff" if name == "vert_adv" else "vert_adv"
+        # both halves of the metric in the kept line: the other stencil, same hygiene (>= 4 rotating sets, K launches
+        # back to back between one pair of events)
+        roofline[other] = secondary(torch, stencil, storage, other, peak, args.steps, max(args.warmup, 3))
+        roofline[name] = {k: roofline[k] for k in ("achieved", "frac", "traffic", "kernel", "launch_ms")}
+        line["parity_checked"], line["max_rel_err"], line["parity"] = False, None, {}
+        for st_name in (name, other):
+            try:
+                backend, times, cores, want = time_reference(st_name, 20 if st_name == name else 3, 2)
+                if st_name == name:
+                    sec = statistics.median(times)
+                    line["cpu_baseline"] = {
+                        "value": pts / sec / 1e6, "unit": "Mpts/s", "cores": cores, "kind": "reference",
+                        "sample": "20 timed applications of %s %dx%dx%d fp64 on the reference's stencil::%s (best of "
+                                  "cpu_ifirst/cpu_kfirst), cache flush before each, median" % (name, NI, NJ, NK, backend)}
+                # correctness inside the benchmarked configuration: one fresh application of the benchmarked call at the
+                # benchmarked size against the reference's own CPU backend (oracle/_ref/libgtref.so as the checker)
+                line["parity"][st_name] = parity(torch, stencil, storage, st_name, want)
+            except Exception as e:  # the checker library is not part of the product
+                if st_name == name:
+                    line["cpu_baseline"] = {"value": None, "unit": "Mpts/s", "cores": 0, "kind": "reference",
+                                            "sample": "unavailable: %s" % e}
+                line["parity"][st_name] = {"checked": False, "why": str(e)}
+        errs = [v.get("max_rel_err") for v in line["parity"].values() if v.get("checked")]
+        if len(errs) == 2:
+            line["parity_checked"], line["max_rel_err"] = True, max(errs)
+            line["parity_tolerance"] = 1e-12
+            if max(errs) > 1e-12:
+                raise SystemExit("bench.py: result differs from the reference by %g (> 1e-12)" % max(errs))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -625,42 +663,65 @@ def e2e(torch, stencil, storage, name, sets, dtr, args, n_gpus):
             "timed_by": "host wall clock around %d steps, device synchronised on both sides" % steps}
 
 
-def secondary(torch, stencil, storage, name, peak):
-    """The other stencil of the metric, kernel-only, same hygiene (reported beside the headline)."""
+def secondary(torch, stencil, storage, name, peak, steps, warmup):
+    """The other stencil of the metric, kernel-only, same hygiene as the headline: 4 rotating field sets (> L2 each
+    round), W warm-up launches, K launches back to back between ONE pair of events."""
     H = HALO[name]
     sets = []
     if name == "hori_diff":
-        for _ in range(3):
+        for _ in range(4):
             inp, coeff = repo_hori_diff(NI, NJ, NK)
             sets.append([storage.from_numpy(inp, (H, H, 0)), storage.from_numpy(coeff, (H, H, 0)),
                          storage.from_numpy(np.zeros_like(inp), (H, H, 0))])
-        run = lambda st: stencil.horizontal_diffusion(*st)  # noqa: E731
+        plans = [stencil.plan("horizontal_diffusion", *st) for st in sets]
     else:
-        for _ in range(2):
+        for _ in range(4):
             arrs, dtr = repo_vert_adv(NI, NJ, NK)
             sets.append([storage.from_numpy(a, (H, H, 0)) for a in arrs])
-        run = lambda st: stencil.vertical_advection_dycore(*st, 0.15)  # noqa: E731
+        plans = [stencil.plan("vertical_advection_dycore", *st, dtr_stage=0.15) for st in sets]
     for st in sets:
         for f in st:
             f.const_target_tensor()
-    for s in range(10):
-        run(sets[s % len(sets)])
+    h = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for s in range(warmup):
+        plans[s % 4](h)
     torch.cuda.synchronize()
-    evs = []
-    for s in range(100):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        run(sets[s % len(sets)])
-        b.record()
-        evs.append((a, b))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for s in range(steps):
+        plans[s % 4](h)
+    b.record()
     torch.cuda.synchronize()
-    ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
+    ms = a.elapsed_time(b) / steps
     pts = NI * NJ * NK
     gbs = ALGO_BYTES[name] * pts / (ms * 1e-3) / 1e9
     return {"metric": "Mpts/s %s %dx%dx%d fp64" % (name, NI, NJ, NK), "value": pts / (ms * 1e-3) / 1e6,
-            "unit": "Mpts/s", "kernel_ms": ms, "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak,
-                                                            "unit": "GB/s", "frac": gbs / peak,
-                                                            "traffic": traffic_from_profile(name)}}
+            "unit": "Mpts/s", "launch_ms": ms, "achieved": gbs, "peak": peak, "frac": gbs / peak,
+            "traffic": traffic_from_profile(name), "kernel": "va_pair_kernel" if name == "vert_adv" else "hd_tma_kernel",
+            "steps": steps, "sets": 4}
+
+
+def parity(torch, stencil, storage, name, want):
+    """One application of the benchmarked call on fresh fields of the benchmarked size, compared with the reference's
+    CPU backend result `want` (relative error as tests/include/verifier.hpp:26-52 defines it)."""
+    H = HALO[name]
+    if name == "vert_adv":
+        arrs, dtr = repo_vert_adv(NI, NJ, NK)
+        st = [storage.from_numpy(a, (H, H, 0)) for a in arrs]
+        stencil.vertical_advection_dycore(*st, dtr)
+        out = st[0]
+    else:
+        inp, coeff = repo_hori_diff(NI, NJ, NK)
+        st = [storage.from_numpy(inp, (H, H, 0)), storage.from_numpy(coeff, (H, H, 0)),
+              storage.from_numpy(np.zeros_like(inp), (H, H, 0))]
+        stencil.horizontal_diffusion(*st)
+        out = st[2]
+    torch.cuda.synchronize()
+    got = out.to_numpy()[:, H:-H, H:-H]
+    ref = want[:, H:-H, H:-H]
+    den = np.maximum(np.maximum(np.abs(got), np.abs(ref)), 1e-300)
+    err = float(np.max(np.abs(got - ref) / den))
+    return {"checked": True, "max_rel_err": err, "points": int(got.size), "against": "reference cpu backend (libgtref)"}
 
 
 if __name__ == "__main__":

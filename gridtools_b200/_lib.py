@@ -97,6 +97,8 @@ _SIG = {
     "gtb_seq_add_record": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "gtb_seq_add_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "gtb_seq_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "gtb_seq_add_mark": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "gtb_seq_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
 }
 
 _lib = None

@@ -49,7 +49,7 @@ namespace gtb {
         int halo_max_blocks = 0; // > 0: grid size cap of the halo transfer kernels (0: one block per SM)
         int halo_vec = 1;       // 16-byte vector transfers where the halo regions allow it
         int halo_fused = 0;     // gtb_halo_exchange as ONE launch (pack, signal, wait, unpack); 0: two launches
-        int pdl = 1;            // programmatic dependent launch of the vertical advection kernel (prologue under the previous kernel's tail)
+        int pdl = 1;            // programmatic dependent launch of the vertical advection kernel (prologue under the previous kernel's tail): 0 off, 1 unless SMs are reserved, 2 always
         int reserve_sms = 0;    // SMs the persistent stencil grids leave free (for a halo exchange that runs beside them)
     };
     options &opts();
@@ -115,7 +115,7 @@ namespace gtb {
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         // not next to a concurrent exchange: the early CTAs of the NEXT launch would settle on the reserved SMs
-        attr[0].val.programmaticStreamSerializationAllowed = opts().pdl && opts().reserve_sms == 0 ? 1 : 0;
+        attr[0].val.programmaticStreamSerializationAllowed = opts().pdl == 2 || (opts().pdl == 1 && opts().reserve_sms == 0) ? 1 : 0;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);

@@ -15,7 +15,7 @@
 using namespace gtb;
 
 namespace {
-    enum op_kind { OP_HD64, OP_HD32, OP_VA64, OP_VA32, OP_TRACERS, OP_HALO, OP_RECORD, OP_WAIT, OP_SGATE, OP_HGATE };
+    enum op_kind { OP_HD64, OP_HD32, OP_VA64, OP_VA32, OP_TRACERS, OP_HALO, OP_RECORD, OP_WAIT, OP_SGATE, OP_HGATE, OP_MARK };
 
     struct op {
         op_kind kind;
@@ -36,6 +36,7 @@ namespace {
 struct gtb_seq {
     std::vector<op> ops;
     std::vector<cudaEvent_t> events;
+    std::vector<cudaEvent_t> marks; // timing-enabled events (gtb_seq_add_mark)
 };
 
 namespace {
@@ -65,6 +66,8 @@ GTB_API int gtb_seq_destroy(gtb_seq *s) {
     if (!s)
         return GTB_OK;
     for (cudaEvent_t e : s->events)
+        cudaEventDestroy(e);
+    for (cudaEvent_t e : s->marks)
         cudaEventDestroy(e);
     delete s;
     return GTB_OK;
@@ -178,6 +181,30 @@ GTB_API int gtb_seq_add_wait(gtb_seq *s, void *stream, int event) {
     return GTB_OK;
 }
 
+GTB_API int gtb_seq_add_mark(gtb_seq *s, int mark, void *stream) {
+    if (!s || mark < 0 || mark > 4096)
+        return fail(GTB_ERR_ARG, "gtb_seq_add_mark: bad argument");
+    while ((int)s->marks.size() <= mark) {
+        cudaEvent_t e;
+        GTB_CUDA(cudaEventCreate(&e));
+        s->marks.push_back(e);
+    }
+    op o{};
+    o.kind = OP_MARK;
+    o.event = mark;
+    o.stream = stream;
+    s->ops.push_back(o);
+    return GTB_OK;
+}
+
+GTB_API int gtb_seq_elapsed_ms(gtb_seq *s, int mark_a, int mark_b, float *ms) {
+    if (!s || !ms || mark_a < 0 || mark_b < 0 || mark_a >= (int)s->marks.size() || mark_b >= (int)s->marks.size())
+        return fail(GTB_ERR_ARG, "gtb_seq_elapsed_ms: bad argument");
+    GTB_CUDA(cudaEventSynchronize(s->marks[mark_b]));
+    GTB_CUDA(cudaEventElapsedTime(ms, s->marks[mark_a], s->marks[mark_b]));
+    return GTB_OK;
+}
+
 GTB_API int gtb_seq_run(gtb_seq *s, int first, int count) {
     if (!s || first < 0 || count < 0 || (size_t)first + (size_t)count > s->ops.size())
         return fail(GTB_ERR_ARG, "gtb_seq_run: slice out of range");
@@ -216,6 +243,9 @@ GTB_API int gtb_seq_run(gtb_seq *s, int first, int count) {
             break;
         case OP_WAIT:
             GTB_CUDA(cudaStreamWaitEvent(as_stream(o.stream), s->events[o.event], 0));
+            break;
+        case OP_MARK:
+            GTB_CUDA(cudaEventRecord(s->marks[o.event], as_stream(o.stream)));
             break;
         }
         if (st)

@@ -1648,7 +1648,7 @@ namespace {
     }
 
     // ------------------------------------------------------------------ paired-warp TMEM variant (va.variant = 7)
-    // What the debug knobs of variant 5 show (tools_va_dbg.py, profiles/README.md): with ALL arithmetic removed the
+    // What the debug knobs of variant 5 show (tools/va_dbg.py, profiles/README.md): with ALL arithmetic removed the
     // kernel still takes 58 of its 60 us -- 37 us for streaming the forward inputs, 9 us for the backward sweeps'
     // u_pos re-reads and 11 us for their output stores.  The sweeps are bound by the order in which one warp walks
     // through its memory operations, not by fp64 latency: while a warp sweeps back it streams nothing, and variant 6

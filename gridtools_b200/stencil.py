@@ -231,6 +231,15 @@ class Sequence:
     def wait(self, stream, event):
         _lib.check(_lib.lib().gtb_seq_add_wait(self._h, stream, int(event)))
 
+    def mark(self, mark, stream=None):
+        """Timing mark (gtb_seq_add_mark): recorded in `stream` when the sequence reaches this point."""
+        _lib.check(_lib.lib().gtb_seq_add_mark(self._h, int(mark), stream))
+
+    def elapsed_ms(self, mark_a, mark_b):
+        ms = C.c_float()
+        _lib.check(_lib.lib().gtb_seq_elapsed_ms(self._h, int(mark_a), int(mark_b), C.byref(ms)))
+        return float(ms.value)
+
     def run(self, first=0, count=None):
         n = len(self) - first if count is None else count
         _lib.check(_lib.lib().gtb_seq_run(self._h, int(first), int(n)))

@@ -272,6 +272,11 @@ int gtb_seq_add_stencil_gate(gtb_seq *s, const void *wait_flag, uint64_t wait_va
 int gtb_seq_add_halo_gate(gtb_seq *s, gtb_halo *h, const void *counter, uint64_t value);
 int gtb_seq_add_record(gtb_seq *s, int event, void *stream);
 int gtb_seq_add_wait(gtb_seq *s, void *stream, int event);
+/* Timing marks: a mark is a timing-enabled event recorded in `stream` when the sequence reaches it, so that a region
+ * in the MIDDLE of one gtb_seq_run() slice can be timed on the device (ranks of a multi-GPU loop are in lock-step
+ * there, which they are not at the first operation after a host barrier).  gtb_seq_elapsed_ms waits for mark_b. */
+int gtb_seq_add_mark(gtb_seq *s, int mark, void *stream);
+int gtb_seq_elapsed_ms(gtb_seq *s, int mark_a, int mark_b, float *ms);
 /* Issues operations [first, first + count) of the sequence. */
 int gtb_seq_run(gtb_seq *s, int first, int count);
 

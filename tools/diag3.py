@@ -5,7 +5,7 @@ import torch
 sys.path.insert(0, ".")
 import bench
 from gridtools_b200 import _lib, stencil, storage
-from tools_tune import timeit
+from tune import timeit
 torch.cuda.set_device(0)
 _lib.check(_lib.lib().gtb_init(0))
 sets = []

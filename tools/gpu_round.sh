@@ -13,15 +13,15 @@ if [ "$STEP" = all ] || [ "$STEP" = test ]; then
   grep -E "passed|failed|exit" gpurun_out/pytest_gpu.log | tail -8
 fi
 if [ "$STEP" = sanitize ]; then
-  timeout 900 compute-sanitizer --tool memcheck python tools_sanitize.py > gpurun_out/sanitize.log 2>&1
+  timeout 900 compute-sanitizer --tool memcheck python tools/sanitize.py > gpurun_out/sanitize.log 2>&1
   tail -15 gpurun_out/sanitize.log
 fi
 if [ "$STEP" = tuneva ]; then
-  timeout 600 python tools_tune.py va > gpurun_out/tune_va.txt 2>&1
+  timeout 600 python tools/tune.py va > gpurun_out/tune_va.txt 2>&1
   head -12 gpurun_out/tune_va.txt
 fi
 if [ "$STEP" = all ] || [ "$STEP" = tune ]; then
-  timeout 600 python tools_tune.py > gpurun_out/tune.txt 2>&1
+  timeout 600 python tools/tune.py > gpurun_out/tune.txt 2>&1
   tail -3 gpurun_out/tune.txt
 fi
 if [ "$STEP" = all ] || [ "$STEP" = bench ]; then

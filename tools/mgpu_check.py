@@ -3,7 +3,7 @@
 of the neighbouring rank's cell, or -1 at a non-periodic border (:106-123).  Runs both transports.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
-        tools_mgpu_check.py
+        tools/mgpu_check.py
 """
 import os
 import sys

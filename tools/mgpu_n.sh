@@ -3,7 +3,7 @@
 N=${1:-4}
 mkdir -p gpurun_out
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
-    tools_mgpu_check.py > gpurun_out/mgpu_check_$N.log 2>&1
+    tools/mgpu_check.py > gpurun_out/mgpu_check_$N.log 2>&1
 echo "mgpu_check exit $?"; grep "MGPU\|mismatch\|Error" gpurun_out/mgpu_check_$N.log | tail -4
 for st in vert_adv hori_diff; do
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \

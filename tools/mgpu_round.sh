@@ -4,7 +4,7 @@ N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/topo.txt 2>&1
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
-    tools_mgpu_check.py > gpurun_out/mgpu_check_$N.log 2>&1
+    tools/mgpu_check.py > gpurun_out/mgpu_check_$N.log 2>&1
 echo "mgpu_check exit $?"; tail -4 gpurun_out/mgpu_check_$N.log
 timeout 300 python bench.py --gpus 1 --steps 200 --warmup 20 --no-extras > gpurun_out/scale_va_1.json 2>> gpurun_out/scale.err
 for n in 2 4 8; do

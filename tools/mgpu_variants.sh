@@ -1,0 +1,43 @@
+#!/bin/bash
+# Exchange/overlap variants of the weak-scaling bench on N GPUs (gpurun --gpus N): one short bench run per variant.
+# GTB_PERIODIC=1 gives every rank all 8 IJ neighbours, the exchange load of an interior rank of a large process grid.
+N=${1:-2}
+STEPS=${2:-100}
+OUT=gpurun_out/variants_$N.txt
+mkdir -p gpurun_out
+: > $OUT
+run() { # name stencil env...
+  local name=$1 st=$2; shift 2
+  local line
+  line=$(env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
+      --master-port 29531 bench.py --gpus $N --steps $STEPS --warmup 10 --stencil $st --no-extras 2>> gpurun_out/variants.err | tail -1)
+  python3 - "$name" "$st" "$line" >> $OUT <<'PY'
+import json, sys
+name, st, line = sys.argv[1:4]
+try:
+    d = json.loads(line)
+    print("%-34s %-9s %7.2f us/step  ranks %s" % (name, st, d["ms_per_step"] * 1e3,
+          " ".join("%.1f" % (x * 1e3) for x in d["rank_ms_per_step"])))
+except Exception as e:
+    print("%-34s %-9s FAILED %s %r" % (name, st, e, line[:200]))
+PY
+  tail -1 $OUT
+}
+for st in vert_adv hori_diff; do
+  timeout 300 python bench.py --gpus 1 --steps $STEPS --warmup 10 --stencil $st --no-extras 2>> gpurun_out/variants.err | tail -1 | \
+    python3 -c "import json,sys; d=json.loads(sys.stdin.read()); print('%-34s %-9s %7.2f us/step' % ('N=1', '$st', d['ms_per_step']*1e3))" | tee -a $OUT
+  run "plain(nonperiodic)"              $st GTB_X=0
+  run "periodic default(r4,b148)"       $st GTB_PERIODIC=1
+  run "periodic r4 b32"                 $st GTB_PERIODIC=1 GTB_HALO_MAX_BLOCKS=32
+  run "periodic r4 b32 pdl2"            $st GTB_PERIODIC=1 GTB_HALO_MAX_BLOCKS=32 GTB_PDL=2
+  run "periodic r0 pdl2 b148"           $st GTB_PERIODIC=1 GTB_RESERVE_SMS=0 GTB_PDL=2
+  run "periodic r0 pdl2 b32"            $st GTB_PERIODIC=1 GTB_RESERVE_SMS=0 GTB_PDL=2 GTB_HALO_MAX_BLOCKS=32
+  run "periodic r2 b16"                 $st GTB_PERIODIC=1 GTB_RESERVE_SMS=2 GTB_HALO_MAX_BLOCKS=16
+  run "periodic r4 b32 fused"           $st GTB_PERIODIC=1 GTB_HALO_MAX_BLOCKS=32 GTB_HALO_FUSED=1
+  run "periodic r8 b64"                 $st GTB_PERIODIC=1 GTB_RESERVE_SMS=8 GTB_HALO_MAX_BLOCKS=64
+  if [ $st = vert_adv ]; then
+    run "periodic r4 b32 gates"         $st GTB_PERIODIC=1 GTB_HALO_MAX_BLOCKS=32 GTB_GATES=1
+    run "periodic r4 b32 gates pdl2"    $st GTB_PERIODIC=1 GTB_HALO_MAX_BLOCKS=32 GTB_GATES=1 GTB_PDL=2
+  fi
+done
+cat $OUT

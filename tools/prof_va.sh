@@ -1,6 +1,6 @@
 #!/bin/bash
 # ncu full capture of the vertical advection kernel (one GPU); output in gpurun_out/prof_va.ncu-rep
-# usage: tools_prof_va.sh [variant] [unroll] [stages] [nk]
+# usage: tools/prof_va.sh [variant] [unroll] [stages] [nk]
 mkdir -p gpurun_out
 cat > /tmp/prof_va.py <<PY
 import sys

@@ -1,6 +1,6 @@
 #!/bin/bash
 # ncu full capture of a vertical advection variant in STEADY STATE (no cache flush between launches, 2 rotating
-# field sets): usage tools_prof_va2.sh <variant> <tag> [extra va.option=value ...]
+# field sets): usage tools/prof_va2.sh <variant> <tag> [extra va.option=value ...]
 mkdir -p gpurun_out
 V=${1:-5}; TAG=${2:-va$V}; shift; shift
 cat > /tmp/prof_va2.py <<PY

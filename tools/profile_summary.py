@@ -1,6 +1,6 @@
 """Condenses gpurun_out/prof_{va,hd}.ncu-rep (ncu --set full captures) into the tracked summaries under profiles/.
 
-    python tools_profile_summary.py r01        # -> profiles/r01_va_ncu.txt, r01_hd_ncu.txt, traffic.json, ...
+    python tools/profile_summary.py r01        # -> profiles/r01_va_ncu.txt, r01_hd_ncu.txt, traffic.json, ...
 """
 import csv
 import io
@@ -59,7 +59,7 @@ def main():
         if not os.path.exists(rep):
             continue
         hdr, units, rows = raw(rep)
-        lines = ["# ncu --set full --clock-control none, kernel regex %s_ (tools_gpu_round.sh ncu); one column per captured launch" % name]
+        lines = ["# ncu --set full --clock-control none, kernel regex %s_ (tools/gpu_round.sh ncu); one column per captured launch" % name]
         ik = hdr.index("Kernel Name")
         lines.append("kernel: " + rows[0][ik])
         vals = {}

@@ -1,6 +1,6 @@
 """Sweeps the kernel variants on the GPU box and prints a table (used to pick the defaults in csrc/*.cu).
 
-    python tools_tune.py > gpurun_out/tune.txt
+    python tools/tune.py > gpurun_out/tune.txt
 """
 import itertools
 import statistics
