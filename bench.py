@@ -388,10 +388,14 @@ def b200_arm(args):
                 sq.stencil_gate(flag, e0 + s, done.data_ptr())
             else:
                 sq.wait(comp_h, s % M)
+            if timeline is not None and s < timeline.shape[0]:
+                sq.stamp(timeline[s, 0:1].data_ptr(), comp_h)
             if name == "vert_adv":
                 sq.vertical_advection_dycore(*sets[s % n_sets], dtr, stream=comp_h)
             else:
                 sq.horizontal_diffusion(*sets[s % n_sets], stream=comp_h)
+            if timeline is not None and s < timeline.shape[0]:
+                sq.stamp(timeline[s, 1:2].data_ptr(), comp_h)
             if not use_gates:
                 sq.record(M + s % M, comp_h)
             ops.append((first, len(sq) - first))
@@ -400,6 +404,14 @@ def b200_arm(args):
         sq.keep = done
         return sq, ops
 
+    # GTB_TIMELINE=1 (diagnosis, distorts the timing slightly): %globaltimer stamps around every stencil launch and
+    # inside the transfer kernels; rank 0 prints the steps of the timed region to stderr
+    timeline = halo_trace = None
+    if he is not None and os.environ.get("GTB_TIMELINE") == "1":
+        timeline = torch.zeros((total_steps, 2), dtype=torch.int64, device="cuda")
+        halo_trace = torch.zeros((256, 8), dtype=torch.int64, device="cuda")
+        _lib.check(_lib.lib().gtb_halo_set_trace(he._h, C.c_void_p(halo_trace.data_ptr())))
+        epoch0 = he.epoch()
     if he is not None:
         _lib.set_option("reserve_sms", int(os.environ.get("GTB_RESERVE_SMS", RESERVE_SMS)))  # left to the exchange
         _lib.set_option("halo.fused", int(os.environ.get("GTB_HALO_FUSED", HALO_FUSED)))
@@ -467,6 +479,18 @@ def b200_arm(args):
         per_step = [total_ms / args.steps]
         if he.check() != 0:
             raise SystemExit("bench.py: a halo wait timed out in the timed region")
+    if timeline is not None and rank == 0:
+        tl, ht = timeline.cpu().numpy(), halo_trace.cpu().numpy()
+        s0 = n_warm + LEAD + 2
+        t0 = int(tl[s0, 0])
+        sys.stderr.write("timeline (us, relative to the start of stencil %d); exchange e feeds stencil e\n" % s0)
+        sys.stderr.write("%5s %9s %9s | %9s %9s | %9s %9s %9s\n" % ("step", "st.start", "st.end", "pk.start", "pk.end",
+                                                                    "up.start", "up.flags", "up.end"))
+        for st in range(s0, min(s0 + 8, total_steps)):
+            row = ht[(epoch0 + st) % 256]
+            rel = lambda v: (int(v) - t0) / 1e3  # noqa: E731
+            sys.stderr.write("%5d %9.1f %9.1f | %9.1f %9.1f | %9.1f %9.1f %9.1f\n" % (
+                st, rel(tl[st, 0]), rel(tl[st, 1]), rel(row[0]), rel(row[1]), rel(row[2]), rel(row[3]), rel(row[4])))
     rank_ms = [total_ms / args.steps]
     if world > 1:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)

@@ -28,6 +28,12 @@ class HaloDesc(C.Structure):
     _fields_ = [("minus", C.c_int), ("plus", C.c_int), ("begin", C.c_int), ("end", C.c_int), ("total", C.c_int)]
 
 
+class HaloField(C.Structure):
+    """gtb_halo_field: a field with its own three halo descriptors (field_on_the_fly)."""
+
+    _fields_ = [("ptr", C.c_void_p), ("desc", HaloDesc * 3)]
+
+
 class GtbError(RuntimeError):
     def __init__(self, status, message):
         super().__init__("libgtb200 status %d: %s" % (status, message))
@@ -76,6 +82,10 @@ _SIG = {
     "gtb_halo_exchange": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
     "gtb_halo_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "gtb_halo_next_epoch": (C.c_int, [C.c_void_p]),
+    "gtb_halo_set_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gtb_stamp": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gtb_halo_generic_pack_send": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "gtb_halo_generic_wait_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "gtb_boundary_apply": (C.c_int, [C.POINTER(HaloDesc), C.POINTER(C.c_int), C.c_int, C.c_double, C.POINTER(C.c_void_p),
                                      C.c_int, C.c_int, C.c_void_p]),
     "gtb_halo_set_boundary": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
@@ -97,6 +107,7 @@ _SIG = {
     "gtb_seq_add_record": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "gtb_seq_add_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "gtb_seq_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "gtb_seq_add_stamp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "gtb_seq_add_mark": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "gtb_seq_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
 }

@@ -141,6 +141,11 @@ namespace gtb {
 namespace gtb {
     namespace ptx {
 #ifdef __CUDACC__
+        __device__ __forceinline__ unsigned long long globaltimer() {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            return t;
+        }
         __device__ __forceinline__ uint32_t smem_addr(const void *p) {
             return static_cast<uint32_t>(__cvta_generic_to_shared(p));
         }

@@ -23,6 +23,10 @@
 
 #include <unistd.h>
 
+#include <map>
+#include <mutex>
+#include <vector>
+
 using namespace gtb;
 
 namespace {
@@ -78,6 +82,7 @@ struct gtb_halo {
     uint64_t epoch; // starts at 1
     int *d_error;   // device flag set by a wait that timed out
     unsigned *d_counters; // block counter of the fused pack + signal launch
+    unsigned long long *trace; // diagnosis (gtb_halo_set_trace): [epoch % 256][8] globaltimer stamps
 };
 
 namespace {
@@ -102,6 +107,7 @@ namespace {
         unsigned long long *gate_timeouts;
         unsigned long long *unpacked;   // unpack: the last block stores the epoch here when every block is done
         unsigned *counter2;             // block counter of that, zero between launches
+        unsigned long long *trace;      // diagnosis: row of 8 globaltimer stamps of this epoch, or nullptr
     };
 
     constexpr int kMaxSeg = 26;
@@ -178,8 +184,11 @@ namespace {
             while (ch >= t.chunk_start[s + 1])
                 ++s;
             if (WAIT && t.flag[s] && !((waited >> s) & 1u)) {
-                if (threadIdx.x == 0)
+                if (threadIdx.x == 0) {
                     wait_flag(t.flag[s], sy.epoch, sy.error, sy.timeout_cycles, t.dir[s]);
+                    if (sy.trace)
+                        atomicMax(sy.trace + 3, ptx::globaltimer());
+                }
                 __syncthreads();
                 waited |= 1u << s;
             }
@@ -239,6 +248,8 @@ namespace {
     template <class E, bool PACK>
     __global__ void __launch_bounds__(kThreads) xfer_kernel(const __grid_constant__ xfer_args a) {
         __shared__ int s_last;
+        if (a.sync.trace && threadIdx.x == 0 && blockIdx.x == 0)
+            a.sync.trace[PACK ? 0 : 2] = ptx::globaltimer();
         if (!PACK && a.sync.gate) { // a stencil launch on another stream may still be reading the halos
             if (threadIdx.x == 0)
                 ptx::gate_wait(a.sync.gate, a.sync.gate_value, a.sync.gate_timeouts);
@@ -250,6 +261,8 @@ namespace {
             move_chunks<E, PACK, false>(a.t, a.fields, a.s1, a.s2, a.sync, a.fill_bits);
         if (PACK && a.sync.mode == 1)
             signal_peers(a.t, a.sync, &s_last);
+        if (a.sync.trace && threadIdx.x == 0)
+            atomicMax(a.sync.trace + (PACK ? 1 : 4), ptx::globaltimer());
         if (!PACK && a.sync.unpacked) { // publish "halos of epoch e are in place" for device-side gates
             __threadfence();
             __syncthreads();
@@ -369,6 +382,7 @@ namespace {
         sy.gate_timeouts = nullptr;
         sy.unpacked = nullptr;
         sy.counter2 = h->d_counters + 1;
+        sy.trace = h->trace ? h->trace + (h->epoch % 256) * 8 : nullptr;
     }
 
     // Blocks of a transfer launch: at most one small block per SM (option halo.max_blocks overrides).  The first of
@@ -528,6 +542,7 @@ GTB_API int gtb_halo_create(const gtb_halo_desc desc[3], const int neighbour_ran
     h->gate_counter = nullptr;
     h->gate_value = 0;
     h->d_unpacked = nullptr;
+    h->trace = nullptr;
     h->bc_bits = 0;
     h->send_total = h->recv_total = 0;
     for (int e2 = -1; e2 <= 1; ++e2)
@@ -592,6 +607,10 @@ GTB_API int gtb_halo_create(const gtb_halo_desc desc[3], const int neighbour_ran
     return GTB_OK;
 }
 
+namespace {
+    void free_generic_tables(const gtb_halo *h);
+}
+
 GTB_API int gtb_halo_destroy(gtb_halo *h) {
     if (!h)
         return GTB_OK;
@@ -604,6 +623,7 @@ GTB_API int gtb_halo_destroy(gtb_halo *h) {
             if (!shared)
                 cudaIpcCloseMemHandle(h->opened[n]);
         }
+    free_generic_tables(h);
     cudaFree(h->send_arena);
     cudaFree(h->arena);
     cudaFree(h->d_error);
@@ -851,12 +871,256 @@ GTB_API int gtb_halo_exchange(gtb_halo *h, void *const *fields, int n_fields, vo
     return gtb_halo_next_epoch(h);
 }
 
+// ------------------------------------------------------------------------------------------- generic exchange
+// halo_exchange_generic (gcl/halo_exchange.hpp:335-513): every field has its own halo descriptors.  The reference
+// concatenates the fields into one message per neighbour (descriptor_generic_manual.hpp:370-796) with per-field
+// kernels; here the (direction, field) pieces of ALL fields form one flat segment list in device memory that one
+// launch walks -- one launch packs and pushes everything, one launch waits and unpacks everything.
+namespace {
+    struct gseg {
+        int lo[3], len[3];
+        int dir;          // direction number 0..26
+        int chunk_start;  // first chunk of this segment in the flat chunk list
+        int64_t count;    // words
+        int64_t s1, s2;   // word strides of storage dimensions 1 and 2 of this field
+        char *fld;        // storage element (0,0,0) of the field
+        char *buf;        // where this piece lives in the message of its direction
+    };
+
+    struct gx_args {
+        const gseg *segs;
+        int n_seg, n_chunks;
+        uint64_t *flag[27]; // pack: flags to raise at the neighbours; unpack: own flags to wait for
+        sync_args sync;
+    };
+
+    template <class E, bool PACK>
+    __global__ void __launch_bounds__(kThreads) generic_xfer_kernel(const __grid_constant__ gx_args a) {
+        __shared__ int s_last;
+        if (a.sync.trace && threadIdx.x == 0 && blockIdx.x == 0)
+            a.sync.trace[PACK ? 0 : 2] = ptx::globaltimer();
+        unsigned waited = 0; // directions whose flag this block has acquired
+        int s = 0;
+        for (int ch = blockIdx.x; ch < a.n_chunks; ch += gridDim.x) {
+            while (s + 1 < a.n_seg && ch >= a.segs[s + 1].chunk_start)
+                ++s;
+            const gseg g = a.segs[s];
+            if (!PACK && a.flag[g.dir] && !((waited >> g.dir) & 1u)) {
+                if (threadIdx.x == 0)
+                    wait_flag(a.flag[g.dir], a.sync.epoch, a.sync.error, a.sync.timeout_cycles, g.dir);
+                __syncthreads();
+                waited |= 1u << g.dir;
+            }
+            const int64_t base = (int64_t)(ch - g.chunk_start) * kChunk + threadIdx.x;
+            E *buf = reinterpret_cast<E *>(g.buf);
+            E *fld = reinterpret_cast<E *>(g.fld);
+            int64_t idx[kItems];
+            E v[kItems];
+#pragma unroll
+            for (int it = 0; it < kItems; ++it) {
+                const int64_t e = base + (int64_t)it * kThreads;
+                if (e < g.count) {
+                    const int64_t q = e / g.len[0];
+                    const int i0 = (int)(e - q * g.len[0]);
+                    const int64_t q2 = q / g.len[1];
+                    const int i1 = (int)(q - q2 * g.len[1]);
+                    idx[it] = (g.lo[0] + i0) + (g.lo[1] + i1) * g.s1 + (g.lo[2] + q2) * g.s2;
+                    v[it] = PACK ? fld[idx[it]] : buf[e];
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < kItems; ++it) {
+                const int64_t e = base + (int64_t)it * kThreads;
+                if (e < g.count) {
+                    if (PACK)
+                        buf[e] = v[it];
+                    else
+                        fld[idx[it]] = v[it];
+                }
+            }
+        }
+        if (PACK) { // the last block raises the neighbours' flags once every block's stores are visible system-wide
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const unsigned done = atomicAdd(a.sync.counter, 1u) + 1u;
+                s_last = done == gridDim.x;
+                if (s_last)
+                    *a.sync.counter = 0;
+            }
+            __syncthreads();
+            if (s_last && threadIdx.x < 27 && a.flag[threadIdx.x]) {
+                __threadfence_system();
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.flag[threadIdx.x]), "l"(a.sync.epoch) : "memory");
+            }
+        }
+        if (a.sync.trace && threadIdx.x == 0)
+            atomicMax(a.sync.trace + (PACK ? 1 : 4), ptx::globaltimer());
+    }
+
+    // Device copies of segment lists, keyed by the bytes that determine them: a time loop that exchanges the same
+    // fields every step builds and uploads its four tables (pack / unpack x epoch parity) once.
+    struct gtable {
+        std::vector<char> key;
+        gseg *dev;
+        int n_seg, n_chunks;
+    };
+    std::mutex g_gtable_mutex;
+    std::map<const gtb_halo *, std::vector<gtable>> g_gtables;
+
+    template <bool PACK>
+    int run_generic(gtb_halo *h, const gtb_halo_field *fields, int n_fields, cudaStream_t stream, const char *who) {
+        if (!h || (!fields && n_fields))
+            return fail(GTB_ERR_ARG, "%s: null argument", who);
+        if (!h->connected)
+            return fail(GTB_ERR_STATE, "%s: gtb_halo_connect has not been called", who);
+        if (n_fields < 0)
+            return fail(GTB_ERR_ARG, "%s: negative field count", who);
+        const int parity = (int)(h->epoch & 1);
+        std::vector<char> key(sizeof(int) * 2 + sizeof(gtb_halo_field) * (size_t)n_fields);
+        const int tag[2] = {PACK ? 1 : 0, parity};
+        memcpy(key.data(), tag, sizeof(tag));
+        if (n_fields)
+            memcpy(key.data() + sizeof(tag), fields, sizeof(gtb_halo_field) * (size_t)n_fields);
+        gtable *tab = nullptr;
+        {
+            std::lock_guard<std::mutex> lock(g_gtable_mutex);
+            std::vector<gtable> &tabs = g_gtables[h];
+            for (gtable &t : tabs)
+                if (t.key == key)
+                    tab = &t;
+            if (!tab) {
+                std::vector<gseg> segs;
+                int chunks = 0;
+                for (int n = 0; n < 27; ++n) {
+                    if (n == 13 || h->nbr[n] < 0)
+                        continue;
+                    const int e[3] = {n % 3 - 1, (n / 3) % 3 - 1, n / 9 - 1};
+                    char *base = PACK ? (h->send[n].count ? peer_slot(h, n, h->epoch) : nullptr)
+                                      : (h->recv[n].count ? recv_slot(h, n, h->epoch) : nullptr);
+                    const int64_t capacity = (PACK ? h->send[n].count : h->recv[n].count) * h->max_fields * h->es;
+                    int64_t offset = 0;
+                    for (int f = 0; f < n_fields; ++f) {
+                        const gtb_halo_desc *d = fields[f].desc;
+                        gseg g;
+                        g.count = 1;
+                        for (int x = 0; x < 3; ++x) {
+                            if (d[x].minus < 0 || d[x].plus < 0 || d[x].begin < d[x].minus || d[x].end < d[x].begin ||
+                                d[x].end + d[x].plus >= d[x].total)
+                                return fail(GTB_ERR_ARG, "%s: inconsistent halo descriptor of field %d, dimension %d", who, f, x);
+                            g.lo[x] = PACK ? lo_inside(d[x], e[x]) : lo_outside(d[x], e[x]);
+                            g.len[x] = (PACK ? hi_inside(d[x], e[x]) : hi_outside(d[x], e[x])) - g.lo[x] + 1;
+                            g.count *= g.len[x] > 0 ? g.len[x] : 0;
+                        }
+                        if (g.count == 0)
+                            continue;
+                        if (!fields[f].ptr)
+                            return fail(GTB_ERR_ARG, "%s: field %d is null", who, f);
+                        if (!base || offset + g.count * h->es > capacity)
+                            return fail(GTB_ERR_ARG,
+                                "%s: the message for direction %d does not fit the buffers sized by the halo example at "
+                                "setup (%lld bytes)", who, n, (long long)capacity);
+                        g.dir = n;
+                        g.chunk_start = chunks;
+                        g.s1 = d[0].total;
+                        g.s2 = (int64_t)d[0].total * d[1].total;
+                        g.fld = static_cast<char *>(fields[f].ptr);
+                        g.buf = base + offset;
+                        offset += g.count * h->es;
+                        chunks += (int)((g.count + kChunk - 1) / kChunk);
+                        segs.push_back(g);
+                    }
+                }
+                gtable t;
+                t.key = key;
+                t.dev = nullptr;
+                t.n_seg = (int)segs.size();
+                t.n_chunks = chunks;
+                if (!segs.empty()) {
+                    GTB_CUDA(cudaMalloc(&t.dev, segs.size() * sizeof(gseg)));
+                    GTB_CUDA(cudaMemcpy(t.dev, segs.data(), segs.size() * sizeof(gseg), cudaMemcpyHostToDevice));
+                }
+                if (tabs.size() >= 64) { // bounded: a program that keeps changing its field lists recycles the oldest
+                    cudaStreamSynchronize(stream);
+                    cudaFree(tabs.front().dev);
+                    tabs.erase(tabs.begin());
+                }
+                tabs.push_back(std::move(t));
+                tab = &tabs.back();
+            }
+        }
+        gx_args a;
+        a.segs = tab->dev;
+        a.n_seg = tab->n_seg;
+        a.n_chunks = tab->n_chunks;
+        bool any_flag = false;
+        for (int n = 0; n < 27; ++n) {
+            a.flag[n] = nullptr;
+            if (n == 13 || h->nbr[n] < 0)
+                continue;
+            if (PACK && h->send[n].count && h->peer_arena[n])
+                a.flag[n] = reinterpret_cast<uint64_t *>(h->peer_arena[n]) + (h->epoch & 1) * 32 + (26 - n);
+            else if (!PACK && h->recv[n].count)
+                a.flag[n] = reinterpret_cast<uint64_t *>(h->arena) + (h->epoch & 1) * 32 + n;
+            any_flag = any_flag || a.flag[n];
+        }
+        if (!any_flag && a.n_chunks == 0)
+            return GTB_OK;
+        fill_sync(a.sync, h, PACK ? 1 : 2);
+        const int grid = xfer_grid(a.n_chunks);
+        if (h->es == 8)
+            generic_xfer_kernel<uint64_t, PACK><<<grid, kThreads, 0, stream>>>(a);
+        else
+            generic_xfer_kernel<uint32_t, PACK><<<grid, kThreads, 0, stream>>>(a);
+        count_launch();
+        return check_launch(who);
+    }
+} // namespace
+
+namespace {
+    void free_generic_tables(const gtb_halo *h) {
+        std::lock_guard<std::mutex> lock(g_gtable_mutex);
+        auto it = g_gtables.find(h);
+        if (it == g_gtables.end())
+            return;
+        for (gtable &t : it->second)
+            cudaFree(t.dev);
+        g_gtables.erase(it);
+    }
+} // namespace
+
+GTB_API int gtb_halo_generic_pack_send(gtb_halo *h, const gtb_halo_field *fields, int n_fields, void *stream) {
+    return run_generic<true>(h, fields, n_fields, as_stream(stream), "gtb_halo_generic_pack_send");
+}
+
+GTB_API int gtb_halo_generic_wait_unpack(gtb_halo *h, const gtb_halo_field *fields, int n_fields, void *stream) {
+    return run_generic<false>(h, fields, n_fields, as_stream(stream), "gtb_halo_generic_wait_unpack");
+}
+
 GTB_API int gtb_halo_error(gtb_halo *h, int *code) {
     if (!h || !code)
         return fail(GTB_ERR_ARG, "gtb_halo_error: null argument");
     GTB_CUDA(cudaDeviceSynchronize());
     GTB_CUDA(cudaMemcpy(code, h->d_error, sizeof(int), cudaMemcpyDeviceToHost));
     return GTB_OK;
+}
+
+GTB_API int gtb_halo_set_trace(gtb_halo *h, void *device_u64_256x8) {
+    if (!h)
+        return fail(GTB_ERR_ARG, "gtb_halo_set_trace: null handle");
+    h->trace = static_cast<unsigned long long *>(device_u64_256x8);
+    return GTB_OK;
+}
+
+namespace {
+    __global__ void stamp_kernel(unsigned long long *dst) { *dst = ptx::globaltimer(); }
+} // namespace
+
+GTB_API int gtb_stamp(void *device_u64, void *stream) {
+    if (!device_u64)
+        return fail(GTB_ERR_ARG, "gtb_stamp: null pointer");
+    stamp_kernel<<<1, 1, 0, as_stream(stream)>>>(static_cast<unsigned long long *>(device_u64));
+    return check_launch("stamp");
 }
 
 GTB_API int gtb_halo_next_epoch(gtb_halo *h) {

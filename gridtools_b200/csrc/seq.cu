@@ -15,7 +15,7 @@
 using namespace gtb;
 
 namespace {
-    enum op_kind { OP_HD64, OP_HD32, OP_VA64, OP_VA32, OP_TRACERS, OP_HALO, OP_RECORD, OP_WAIT, OP_SGATE, OP_HGATE, OP_MARK };
+    enum op_kind { OP_HD64, OP_HD32, OP_VA64, OP_VA32, OP_TRACERS, OP_HALO, OP_RECORD, OP_WAIT, OP_SGATE, OP_HGATE, OP_MARK, OP_STAMP };
 
     struct op {
         op_kind kind;
@@ -197,6 +197,17 @@ GTB_API int gtb_seq_add_mark(gtb_seq *s, int mark, void *stream) {
     return GTB_OK;
 }
 
+GTB_API int gtb_seq_add_stamp(gtb_seq *s, void *device_u64, void *stream) {
+    if (!s || !device_u64)
+        return fail(GTB_ERR_ARG, "gtb_seq_add_stamp: bad argument");
+    op o{};
+    o.kind = OP_STAMP;
+    o.gate_post = device_u64;
+    o.stream = stream;
+    s->ops.push_back(o);
+    return GTB_OK;
+}
+
 GTB_API int gtb_seq_elapsed_ms(gtb_seq *s, int mark_a, int mark_b, float *ms) {
     if (!s || !ms || mark_a < 0 || mark_b < 0 || mark_a >= (int)s->marks.size() || mark_b >= (int)s->marks.size())
         return fail(GTB_ERR_ARG, "gtb_seq_elapsed_ms: bad argument");
@@ -243,6 +254,9 @@ GTB_API int gtb_seq_run(gtb_seq *s, int first, int count) {
             break;
         case OP_WAIT:
             GTB_CUDA(cudaStreamWaitEvent(as_stream(o.stream), s->events[o.event], 0));
+            break;
+        case OP_STAMP:
+            st = gtb_stamp(o.gate_post, o.stream);
             break;
         case OP_MARK:
             GTB_CUDA(cudaEventRecord(s->marks[o.event], as_stream(o.stream)));

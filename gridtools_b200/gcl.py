@@ -97,9 +97,11 @@ class HaloPlan:
             if n == 13:
                 continue
             es = dir_of(n)  # storage-order direction
-            off = [0, 0, 0]
-            for d in range(3):
-                off[proc_layout[d]] = es[layout[d]]
+            # process dimension I moves with the storage direction of user dimension proc_layout[I]: the reference's
+            # nth<layout_transform<reversed data layout, proc layout>, I>(ii, jj, kk) (gcl/halo_exchange.hpp:169,
+            # high_level/descriptors.hpp:497-499) -- checked against the reference itself for the two proc layouts
+            # that are not their own inverse (tests/test_gcl_reference.py)
+            off = [es[layout[proc_layout[i]]] for i in range(3)]
             self.neighbour[n] = grid.proc(*off)
 
     # common/halo_descriptor.hpp:90-201
@@ -245,8 +247,9 @@ class halo_exchange_dynamic_ut:
         # elements wider than 8 bytes (the reference's own test exchanges array<int, 4>) travel as `f` consecutive
         # 8- (or 4-) byte words: the unit-stride dimension is scaled by f, the byte order of a message is unchanged
         es, f = self.dtype.itemsize, 1
-        if es not in (4, 8):
-            word = 8 if es % 8 == 0 else 4
+        forced = getattr(self, "_word", None)  # halo_exchange_generic builds its messages from 4-byte words
+        if es not in (4, 8) or (forced and forced != es):
+            word = forced or (8 if es % 8 == 0 else 4)
             if es % word:
                 raise ValueError("element size %d is not a multiple of 4 bytes" % es)
             es, f = word, es // word
@@ -449,103 +452,166 @@ class field_on_the_fly:
 
 
 class halo_exchange_generic:
-    """gcl::halo_exchange_generic<ProcLayout, Arch> (gcl/halo_exchange.hpp:334-470): every field brings its own halo
+    """gcl::halo_exchange_generic<ProcLayout, Arch> (gcl/halo_exchange.hpp:334-513): every field brings its own halo
     descriptors, so fields of different sizes, halo widths and element types travel in one pack / exchange / unpack.
 
         hg = halo_exchange_generic(periodicity, grid, comm=TorchComm())
-        hg.setup(max_fields)
+        hg.setup(max_fields, halo_example, typesize)          # field_on_the_fly (or three descriptors), bytes
         hg.pack(field_on_the_fly(a, halos_a), field_on_the_fly(b, halos_b)); hg.exchange(); hg.unpack(...)
 
-    The reference concatenates all fields into one message per neighbour (descriptor_generic_manual.hpp:370-796).  Here
-    the fields are grouped by (halo descriptors, element type); every group is one halo_exchange_dynamic_ut of this
-    package -- created at the first pack() that shows the group, which is a collective call like setup() itself, so
-    all ranks must present the same groups in the same order (they do in an SPMD program: message sizes have to agree
-    in the reference as well).  A pack() is one fused pack + NVLink store launch per group, an unpack() one wait +
-    scatter launch per group."""
+    Like the reference (descriptor_generic_manual.hpp:370-796) all fields of a pack() are concatenated into ONE message
+    per neighbour: one launch packs every field for every neighbour and stores it in the neighbours' receive buffers,
+    one launch waits for the arrival flags and unpacks (gtb_halo_generic_pack_send / _wait_unpack).  The buffers are
+    sized by setup(): max_fields fields of the example's halo regions with `typesize`-byte elements
+    (hndlr_generic::setup, gcl/halo_exchange.hpp:389-393).  Without an example the enclosing descriptor of the fields
+    of the first prepare() / pack() is used -- a collective call like setup() itself."""
 
-    def __init__(self, periodicity, grid: ProcGrid, comm=None, transport="p2p", proc_layout=(0, 1, 2), codec=None):
+    def __init__(self, periodicity, grid: ProcGrid, comm=None, transport="p2p", proc_layout=(0, 1, 2), codec=None,
+                 layout=(0, 1, 2)):
         self.periodicity, self.grid, self.comm, self.transport = tuple(periodicity), grid, comm, transport
-        self.proc_layout, self.codec = tuple(proc_layout), codec
+        self.proc_layout, self.codec, self.layout = tuple(proc_layout), codec, tuple(layout)
         self.max_fields = None
-        self._groups = {}   # signature -> halo_exchange_dynamic_ut
-        self._order = []    # signatures in creation order
-        self._last = []     # [(exchanger, [fields])] of the current pack
-        self.pending = []   # exchangers created by prepare() that still need connect_local (in-process ranks)
+        self._example = None
+        self._he = None     # the device object (p2p) / None (host transport: one plan per field)
+        self.pending = []   # [exchange object] until connect_local_generic connected it (in-process ranks)
+        self._last = []
 
     def setup(self, max_fields, halo_example=None, typesize=8):
-        """setup(max_fields_n, halo_example, typesize) (:389-393); the example and type size of the reference size its
-        buffers, here every group sizes its own."""
         self.max_fields = int(max_fields)
+        if halo_example is not None:
+            halos = halo_example.halos if isinstance(halo_example, field_on_the_fly) else halo_example
+            self._example = (tuple(tuple(int(x) for x in h) for h in halos), int(typesize))
 
-    def _exchanger(self, fotf):
-        sig = fotf.signature()
-        he = self._groups.get(sig)
-        if he is None:
-            if self.max_fields is None:
-                raise RuntimeError("pack() called before setup()")
-            he = halo_exchange_dynamic_ut(self.periodicity, self.grid, fotf.dtype, proc_layout=self.proc_layout,
-                                          comm=self.comm, transport=self.transport, codec=self.codec)
+    @staticmethod
+    def _words(fotf):
+        es = fotf.dtype.itemsize
+        if es % 4:
+            raise ValueError("element size %d is not a multiple of 4 bytes" % es)
+        return es // 4
+
+    def _plan(self, fotf):
+        return HaloPlan(fotf.halos, self.grid, self.layout, self.proc_layout)
+
+    def _create(self, fields):
+        if self.max_fields is None:
+            raise RuntimeError("pack() called before setup()")
+        if self._example is None:  # enclosing descriptor (the maximum per dimension, test_halo_exchange_3D.cpp:224-236)
+            enc, typesize = [], max(f.dtype.itemsize for f in fields)
             for d in range(3):
-                he.add_halo(d, *fotf.halos[d])
-            he.setup(self.max_fields)
-            if self.comm is None and self.transport != "host":
-                self.pending.append(he)
-            self._groups[sig] = he
-            self._order.append(sig)
-        return he
+                m = max(f.halos[d][0] for f in fields)
+                p = max(f.halos[d][1] for f in fields)
+                n = max(f.halos[d][3] - f.halos[d][2] + 1 for f in fields)
+                enc.append((m, p, m, m + n - 1, m + n + p))
+            self._example = (tuple(enc), typesize)
+        halos, typesize = self._example
+        he = halo_exchange_dynamic_ut(self.periodicity, self.grid, np.dtype("V%d" % typesize) if typesize not in (4, 8)
+                                      else (np.float32 if typesize == 4 else np.float64), layout=self.layout,
+                                      proc_layout=self.proc_layout, comm=self.comm, transport="p2p")
+        for d in range(3):
+            he.add_halo(d, *halos[d])
+        he._word = 4  # generic messages are built from 4-byte words
+        he.setup(self.max_fields)
+        if self.comm is None:
+            self.pending.append(he)
+        self._he = he
 
     def prepare(self, *fields):
-        """Creates the exchange objects for the groups these fields form (collective).  Only needed when several ranks
-        live in one process (comm=None): call it on every rank, then connect_local_generic([...])."""
-        for f in fields:
-            self._exchanger(f)
+        """Creates the device object (collective).  Only needed when several ranks live in one process (comm=None):
+        call it on every rank, then connect_local_generic([...])."""
+        if self.transport != "host" and self._he is None:
+            self._create(self._fields(fields))
 
-    def _grouped(self, fields):
+    @staticmethod
+    def _fields(fields):
         if len(fields) == 1 and isinstance(fields[0], (list, tuple)):
             fields = fields[0]  # pack(std::vector<field_on_the_fly>) overload (:421-424)
-        by_sig = {}
-        for f in fields:
-            self._exchanger(f)
-            by_sig.setdefault(f.signature(), []).append(f.field)
-        return [(self._groups[sig], by_sig[sig]) for sig in self._order if sig in by_sig]
+        return list(fields)
+
+    def _marshal(self, fields):
+        arr = (_lib.HaloField * max(1, len(fields)))()
+        for a, f in zip(arr, fields):
+            plan = self._plan(f)
+            w = self._words(f)
+            a.ptr = f.field.raw_ptr() if hasattr(f.field, "raw_ptr") else int(f.field)
+            for d in range(3):
+                m, p, b, e, t = plan.halos[d]
+                k = w if d == 0 else 1
+                a.desc[d] = _lib.HaloDesc(m * k, p * k, b * k, e * k + k - 1, t * k)
+        return arr
 
     def pack(self, *fields):
-        self._last = self._grouped(fields)
-        for he, fs in self._last:
-            he.pack(fs)
+        fields = self._fields(fields)
+        if self.transport == "host":
+            self._last = [(self._plan(f), f) for f in fields]
+            self._packed = {}
+            for i, (plan, f) in enumerate(self._last):
+                for n in range(27):
+                    if plan.send_count(n):
+                        self._packed[(n, i)] = self.codec.pack(plan, n, [f.field])
+            return
+        if self._he is None:
+            self._create(fields)
+        arr = self._marshal(fields)
+        _lib.check(_lib.lib().gtb_halo_generic_pack_send(self._he._h, arr, len(fields), self._he._stream()))
 
     def exchange(self):
-        for he, _ in self._last:
-            he.exchange()
+        self.start_exchange()
+        self.wait()
 
     def start_exchange(self):
-        for he, _ in self._last:
-            he.start_exchange()
+        if self.transport != "host":
+            return  # the messages left with pack()
+        import torch
+        sends, recvs, self._received = [], [], {}
+        for i, (plan, f) in enumerate(self._last):
+            for n in range(27):
+                peer = plan.neighbour[n]
+                if n == 13 or peer < 0:
+                    continue
+                if plan.recv_count(n):
+                    t = torch.empty(plan.recv_count(n), dtype=torch.from_numpy(np.zeros(1, f.dtype)).dtype)
+                    self._received[(n, i)] = t
+                    if peer == self.grid.rank:
+                        t.copy_(torch.from_numpy(np.ascontiguousarray(self._packed[(26 - n, i)])))
+                    else:
+                        recvs.append((peer, (26 - n) * 1000 + i, t))
+                if plan.send_count(n) and peer != self.grid.rank:
+                    sends.append((peer, n * 1000 + i, torch.from_numpy(np.ascontiguousarray(self._packed[(n, i)]))))
+        sends.sort(key=lambda x: x[1])
+        recvs.sort(key=lambda x: x[1])
+        if sends or recvs:
+            self.comm.exchange(sends, recvs)
 
     def wait(self):
-        for he, _ in self._last:
-            he.wait()
+        pass
 
     def unpack(self, *fields):
-        for he, fs in self._grouped(fields):
-            he.unpack(fs)
+        fields = self._fields(fields)
+        if self.transport == "host":
+            for i, f in enumerate(fields):
+                plan = self._plan(f)
+                for n in range(27):
+                    if plan.recv_count(n):
+                        self.codec.unpack(plan, n, [f.field], self._received[(n, i)].numpy())
+            return
+        arr = self._marshal(fields)
+        _lib.check(_lib.lib().gtb_halo_generic_wait_unpack(self._he._h, arr, len(fields), self._he._stream()))
+        _lib.check(_lib.lib().gtb_halo_next_epoch(self._he._h))
 
     def check(self):
-        return max([he.check() for he in self._groups.values()] + [0])
+        return self._he.check() if self._he is not None else 0
 
     def close(self):
-        for he in self._groups.values():
-            he.close()
-        self._groups.clear()
+        if self._he is not None:
+            self._he.close()
+            self._he = None
 
 
 def connect_local_generic(exchangers):
-    """In-process ranks of halo_exchange_generic objects: connects the groups created by prepare(), group by group."""
-    n = len(exchangers[0].pending)
-    if any(len(hg.pending) != n for hg in exchangers):
-        raise RuntimeError("the ranks prepared different numbers of groups")
-    for g in range(n):
-        connect_local([hg.pending[g] for hg in exchangers])
+    """In-process ranks of halo_exchange_generic objects: connects the device objects created by prepare()."""
+    if any(len(hg.pending) != 1 for hg in exchangers):
+        raise RuntimeError("every rank must have called prepare() exactly once")
+    connect_local([hg.pending[0] for hg in exchangers])
     for hg in exchangers:
         hg.pending = []
 

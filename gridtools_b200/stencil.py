@@ -235,6 +235,10 @@ class Sequence:
         """Timing mark (gtb_seq_add_mark): recorded in `stream` when the sequence reaches this point."""
         _lib.check(_lib.lib().gtb_seq_add_mark(self._h, int(mark), stream))
 
+    def stamp(self, device_u64, stream=None):
+        """Diagnosis: a one-thread kernel stores %globaltimer at `device_u64` when the sequence reaches this point."""
+        _lib.check(_lib.lib().gtb_seq_add_stamp(self._h, device_u64, stream))
+
     def elapsed_ms(self, mark_a, mark_b):
         ms = C.c_float()
         _lib.check(_lib.lib().gtb_seq_elapsed_ms(self._h, int(mark_a), int(mark_b), C.byref(ms)))

@@ -195,9 +195,27 @@ int gtb_halo_wait_unpack(gtb_halo *h, void *const *fields, int n_fields, void *s
  * pack() / exchange() / unpack() sequence of halo_exchange_dynamic_ut (gcl/halo_exchange.hpp:250-304) for hosts that do
  * not need the phases separately. */
 int gtb_halo_exchange(gtb_halo *h, void *const *fields, int n_fields, void *stream);
+/* halo_exchange_generic (gcl/halo_exchange.hpp:335-513, high_level/descriptor_generic_manual.hpp:370-796): every field
+ * brings ITS OWN halo descriptors (field_on_the_fly, high_level/field_on_the_fly.hpp:27-95).  The handle is created
+ * from the "halo example" (gtb_halo_create with the enclosing descriptors, max_fields and the word size: buffers hold
+ * max_fields fields of the example's regions, like hndlr_generic::setup :389-393).  All fields of a call travel in ONE
+ * message per neighbour (fields concatenated in argument order), packed by one launch and unpacked by one launch.
+ * desc[] is in increasing-stride order and in units of the handle's elem_size words (an element of k words scales
+ * the descriptor of dimension 0 by k).  GTB_ERR_ARG if a message would not fit the buffers. */
+typedef struct {
+    void *ptr; /* storage element (0,0,0), halo included */
+    gtb_halo_desc desc[3];
+} gtb_halo_field;
+int gtb_halo_generic_pack_send(gtb_halo *h, const gtb_halo_field *fields, int n_fields, void *stream);
+int gtb_halo_generic_wait_unpack(gtb_halo *h, const gtb_halo_field *fields, int n_fields, void *stream);
 /* Synchronises the device and reports whether a wait timed out: *code = 0 if not, else 1 + direction that never
  * arrived.  (Halo_Exchange_3D has no error path: a lost MPI peer hangs in MPI_Wait.) */
 int gtb_halo_error(gtb_halo *h, int *code);
+/* Diagnosis: with a device buffer of 256 x 8 uint64 set, the transfer kernels of epoch e stamp %globaltimer (ns) into
+ * row e % 256: [0] pack starts, [1] pack ends (flags raised), [2] unpack starts, [3] last arrival flag acquired,
+ * [4] unpack ends.  NULL switches it off.  gtb_stamp enqueues a one-thread kernel that stores %globaltimer. */
+int gtb_halo_set_trace(gtb_halo *h, void *device_u64_256x8);
+int gtb_stamp(void *device_u64, void *stream);
 /* Advances the epoch after unpack (double-buffered arenas: a neighbour may already send epoch e+1 while this rank
  * still unpacks epoch e). */
 int gtb_halo_next_epoch(gtb_halo *h);
@@ -277,6 +295,8 @@ int gtb_seq_add_wait(gtb_seq *s, void *stream, int event);
  * there, which they are not at the first operation after a host barrier).  gtb_seq_elapsed_ms waits for mark_b. */
 int gtb_seq_add_mark(gtb_seq *s, int mark, void *stream);
 int gtb_seq_elapsed_ms(gtb_seq *s, int mark_a, int mark_b, float *ms);
+/* diagnosis: gtb_stamp(device_u64, stream) when the sequence reaches this point */
+int gtb_seq_add_stamp(gtb_seq *s, void *device_u64, void *stream);
 /* Issues operations [first, first + count) of the sequence. */
 int gtb_seq_run(gtb_seq *s, int first, int count);
 

@@ -211,9 +211,9 @@ namespace gtb200 {
                 int nbr[27];
                 for (int n = 0; n < 27; ++n) {
                     const int es[3] = {n % 3 - 1, (n / 3) % 3 - 1, n / 9 - 1}; // offsets in storage order
-                    int off[3] = {0, 0, 0};
-                    for (int d = 0; d < 3; ++d)
-                        off[ProcLayout::at(d)] = es[storage_dim(d)];
+                    int off[3]; // process dimension i moves with user dimension ProcLayout::at(i) (descriptors.hpp:497-499)
+                    for (int i = 0; i < 3; ++i)
+                        off[i] = es[storage_dim(ProcLayout::at(i))];
                     nbr[n] = n == 13 ? -1 : m_grid.proc(off[0], off[1], off[2]);
                 }
                 check(gtb_halo_create(m_desc, nbr, m_grid.rank(), max_fields_n, (int)sizeof(T), &m_h), "gtb_halo_create");

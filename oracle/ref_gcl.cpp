@@ -143,6 +143,10 @@ namespace {
             return by_type<Layout, gt::layout_map<1, 0, 2>>(j);
         if (is(2, 1, 0))
             return by_type<Layout, gt::layout_map<2, 1, 0>>(j);
+        if (is(1, 2, 0)) // not an involution: user dimension d -> process dimension P[d] differs from its inverse
+            return by_type<Layout, gt::layout_map<1, 2, 0>>(j);
+        if (is(2, 0, 1))
+            return by_type<Layout, gt::layout_map<2, 0, 1>>(j);
         return 3;
     }
 

@@ -219,7 +219,7 @@ def plan_exchange(halos_user, proc_dims, periodic_user, fields, layout_gt, proc_
                     p.unpack_numpy(n, [fields[r][f]], msgs[(p.neighbour[n], 26 - n, f)])
 
 
-@pytest.mark.parametrize("proc_layout", [(0, 1, 2), (1, 0, 2), (2, 1, 0)])
+@pytest.mark.parametrize("proc_layout", [(0, 1, 2), (1, 0, 2), (2, 1, 0), (1, 2, 0), (2, 0, 1)])
 @pytest.mark.parametrize("layout", LAYOUTS)
 def test_host_plan_equals_reference_gcl_for_every_layout(ref, layout, proc_layout):
     rng = np.random.default_rng(11)

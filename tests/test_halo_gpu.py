@@ -309,7 +309,7 @@ def test_all_layouts_interfaces_periodicities_equal_reference_gcl(gt, oracle, la
                         assert got[r][f].tobytes() == want[r][f].tobytes(), (proc_dims, per, dtype, r, f)
 
 
-@pytest.mark.parametrize("proc_layout", [(1, 0, 2), (2, 1, 0)])
+@pytest.mark.parametrize("proc_layout", [(1, 0, 2), (2, 1, 0), (1, 2, 0)])
 def test_process_layouts_equal_reference_gcl(gt, oracle, proc_layout):
     if not oracle.have_ref():
         pytest.skip("oracle/_ref/libgtref.so missing")
@@ -341,3 +341,45 @@ def test_golden_halo_vectors_on_the_device(gt, golden, name):
     for r in range(n):
         for f in range(n_fields):
             assert np.array_equal(got[r][f], g["result"][r, f]), (r, f)
+
+
+@pytest.mark.parametrize("layout", [(2, 1, 0), (0, 1, 2), (1, 2, 0)])
+def test_generic_one_message_per_neighbour_equals_reference_generic(gt, oracle, layout):
+    """gcl::halo_exchange_generic + field_on_the_fly (test_halo_exchange_3D.cpp:241-266): three fields with their own
+    halo descriptors in ONE pack launch and ONE unpack launch; expectation = the reference's halo_exchange_generic."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/libgtref.so missing")
+    rng = np.random.default_rng(23)
+    hs = [[(0, 1, 0, 8, 10), (2, 3, 2, 8, 12), (2, 1, 2, 7, 9)], [(1, 1, 1, 9, 11), (2, 2, 2, 8, 11), (0, 0, 0, 5, 6)],
+          [(0, 1, 0, 8, 10), (2, 3, 2, 8, 12), (0, 1, 0, 5, 7)]]
+    inc = tuple(2 - v for v in layout)
+    order = np.argsort(layout)
+    for proc_dims, per in [((2, 2, 1), (1, 0, 1)), ((1, 2, 2), (0, 1, 0)), ((2, 1, 1), (0, 0, 0))]:
+        n = proc_dims[0] * proc_dims[1] * proc_dims[2]
+        start = [[rng.standard_normal(tuple(hs[f][d][4] for d in order)) for f in range(3)] for _ in range(n)]
+        want = [[a.copy() for a in r] for r in start]
+        oracle.ref_gcl_exchange(hs, proc_dims, per, want, layout=layout, generic=True)
+        hgs, dev, fotf = [], [], []
+        for r in range(n):
+            grid = gt.gcl.ProcGrid(proc_dims, per, r)
+            hg = gt.gcl.halo_exchange_generic(per, grid, comm=None, transport="p2p", layout=inc)
+            hg.setup(3)
+            d = [gt.torch.from_numpy(a.copy()).cuda() for a in start[r]]
+            fo = [gt.gcl.field_on_the_fly(d[f].data_ptr(), hs[f], np.float64) for f in range(3)]
+            hg.prepare(*fo)
+            hgs.append(hg), dev.append(d), fotf.append(fo)
+        gt.gcl.connect_local_generic(hgs)
+        launches0 = gt.lib.launch_count()
+        for hg, fo in zip(hgs, fotf):
+            hg.pack(*fo)
+        for hg, fo in zip(hgs, fotf):
+            hg.exchange()
+            hg.unpack(fo)
+        gt.torch.cuda.synchronize()
+        assert gt.lib.launch_count() - launches0 <= 2 * n  # one pack and one unpack launch per rank
+        for r in range(n):
+            assert hgs[r].check() == 0
+            for f in range(3):
+                assert np.array_equal(dev[r][f].cpu().numpy(), want[r][f]), (proc_dims, per, r, f)
+        for hg in hgs:
+            hg.close()
