@@ -365,15 +365,40 @@ def b200_arm(args):
         flag, e0 = (he.unpacked_flag(), he.epoch()) if use_gates else (None, 0)
         torch.cuda.synchronize()
 
+        nodeps = os.environ.get("GTB_NODEPS") == "1"  # diagnosis ONLY: no ordering between the streams (invalid run)
+
         def add_exchange(t):
-            if t - n_sets >= 0:
+            if t - n_sets >= 0 and not nodeps:
                 if use_gates:
                     sq.halo_gate(he, done.data_ptr(), t - n_sets + 1)
                 else:
                     sq.wait(comm_h, M + (t - n_sets) % M)
             sq.halo_exchange(he, [sets[t % n_sets][exch_index]], comm_h)
-            if not use_gates:
+            if not use_gates and not nodeps:
                 sq.record(t % M, comm_h)
+
+        if attached:  # ONE launch per step: the stencil of step s carries the exchange of step s + 1 in extra CTAs
+            sq.halo_exchange(he, [sets[0][exch_index]], comp_h)
+            for s in range(total_steps):
+                first = len(sq)
+                if s == n_warm + LEAD:
+                    sq.mark(0, comp_h)
+                if timeline is not None and s < timeline.shape[0]:
+                    sq.stamp(timeline[s, 0:1].data_ptr(), comp_h)
+                if s + 1 < total_steps:
+                    sq.halo_attach(he, [sets[(s + 1) % n_sets][exch_index]], comm_ctas)
+                if name == "vert_adv":
+                    sq.vertical_advection_dycore(*sets[s % n_sets], dtr, stream=comp_h)
+                else:
+                    sq.horizontal_diffusion(*sets[s % n_sets], stream=comp_h)
+                if timeline is not None and s < timeline.shape[0]:
+                    sq.stamp(timeline[s, 1:2].data_ptr(), comp_h)
+                ops.append((first, len(sq) - first))
+            ops[0] = (0, ops[0][0] + ops[0][1])
+            sq.mark(1, comp_h)
+            ops[-1] = (ops[-1][0], ops[-1][1] + 1)
+            sq.keep = done
+            return sq, ops
 
         for s in range(total_steps):
             first = len(sq)
@@ -386,7 +411,7 @@ def b200_arm(args):
                 add_exchange(s + 1)
             if use_gates:
                 sq.stencil_gate(flag, e0 + s, done.data_ptr())
-            else:
+            elif not nodeps:
                 sq.wait(comp_h, s % M)
             if timeline is not None and s < timeline.shape[0]:
                 sq.stamp(timeline[s, 0:1].data_ptr(), comp_h)
@@ -396,7 +421,7 @@ def b200_arm(args):
                 sq.horizontal_diffusion(*sets[s % n_sets], stream=comp_h)
             if timeline is not None and s < timeline.shape[0]:
                 sq.stamp(timeline[s, 1:2].data_ptr(), comp_h)
-            if not use_gates:
+            if not use_gates and not nodeps:
                 sq.record(M + s % M, comp_h)
             ops.append((first, len(sq) - first))
         sq.mark(1, comp_h)
@@ -412,7 +437,17 @@ def b200_arm(args):
         halo_trace = torch.zeros((256, 8), dtype=torch.int64, device="cuda")
         _lib.check(_lib.lib().gtb_halo_set_trace(he._h, C.c_void_p(halo_trace.data_ptr())))
         epoch0 = he.epoch()
-    if he is not None:
+    # N > 1, default: the exchange is ATTACHED to the stencil launch (gtb_halo_attach): a few extra CTAs of the stencil
+    # kernel's own grid pack, push over NVLink, wait and unpack while the others compute -- one launch per step, one
+    # stream, no events.  GTB_ATTACHED=0 selects the round-1 choreography (exchange kernels on a second stream).
+    attached = he is not None and os.environ.get("GTB_ATTACHED", "1") == "1"
+    comm_ctas = int(os.environ.get("GTB_COMM_CTAS", 4 if name == "vert_adv" else 8))
+    if attached:
+        _lib.set_option("reserve_sms", 0)
+        if "GTB_PDL" in os.environ:
+            _lib.set_option("pdl", int(os.environ["GTB_PDL"]))
+        seq, step_ops = build_sequence(False)
+    elif he is not None:
         _lib.set_option("reserve_sms", int(os.environ.get("GTB_RESERVE_SMS", RESERVE_SMS)))  # left to the exchange
         _lib.set_option("halo.fused", int(os.environ.get("GTB_HALO_FUSED", HALO_FUSED)))
         if "GTB_PDL" in os.environ:
@@ -543,11 +578,14 @@ def b200_arm(args):
             name, NI, NJ, NK, "fp64" if itemsize == 8 else "fp32",
             " (BASELINE.json configs[1] family)" if default_size else
             " (%s scaling of a %dx%dx%d global domain)" % (args.scaling, global_ni, global_nj, NK)),
-                   "decomposition": "%dx%dx1 IJ process grid, halo exchange of %s every step over NVLink (fused pack + peer "
-                                    "stores, device-side flags), overlapped with the previous step's stencil on a "
-                                    "high-priority stream, ordered by %s; %d SMs reserved for it; loop issued as one recorded gtb_seq" % (
-                       dims[0], dims[1], "wcon" if name == "vert_adv" else "in",
-                       "device-side gates" if gated else "stream events", RESERVE_SMS) if world > 1 else "single GPU",
+                   "decomposition": ("%dx%dx1 IJ process grid, halo exchange of %s every step over NVLink (peer stores, "
+                                     "device-side flags), " % (dims[0], dims[1], "wcon" if name == "vert_adv" else "in") +
+                                     ("ATTACHED to the stencil launch: %d communication CTAs of the stencil kernel's own grid "
+                                      "exchange the next step's field while the other CTAs compute (one launch per step)" % comm_ctas
+                                      if attached else
+                                      "overlapped with the previous step's stencil on a high-priority stream, ordered by %s; %d SMs "
+                                      "reserved for it" % ("device-side gates" if gated else "stream events", RESERVE_SMS)) +
+                                     "; loop issued as one recorded gtb_seq") if world > 1 else "single GPU",
                    "l2": "inputs of one step (%d MB) exceed L2 and %d field set(s) are rotated" % (
                        sum(f.nbytes_host for f in sets[0][:5 if name == "vert_adv" else 2]) // 2**20, n_sets),
                    "vs_baseline_ref": "reference stencil::gpu on P100, BASELINE.md section 1"},

@@ -82,6 +82,9 @@ _SIG = {
     "gtb_halo_exchange": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
     "gtb_halo_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "gtb_halo_next_epoch": (C.c_int, [C.c_void_p]),
+    "gtb_halo_poll_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "gtb_halo_attach": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int]),
+    "gtb_seq_add_halo_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int]),
     "gtb_halo_set_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gtb_stamp": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gtb_halo_generic_pack_send": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
@@ -107,6 +110,10 @@ _SIG = {
     "gtb_seq_add_record": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "gtb_seq_add_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "gtb_seq_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "gtb_stream_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "gtb_stream_destroy": (C.c_int, [C.c_void_p]),
+    "gtb_stream_after_default": (C.c_int, [C.c_void_p]),
+    "gtb_stream_synchronize": (C.c_int, [C.c_void_p]),
     "gtb_seq_add_stamp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "gtb_seq_add_mark": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "gtb_seq_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),

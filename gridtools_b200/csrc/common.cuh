@@ -48,6 +48,7 @@ namespace gtb {
         int l2_persist_mb = -1; // L2 set-aside for the k-cache slabs in MB: -1 auto (slab size), 0 off
         int halo_max_blocks = 0; // > 0: grid size cap of the halo transfer kernels (0: one block per SM)
         int halo_vec = 1;       // 16-byte vector transfers where the halo regions allow it
+        int halo_timeout_ms = 60000; // device-side waits for a neighbour's message give up after this long; 0: never
         int halo_fused = 0;     // gtb_halo_exchange as ONE launch (pack, signal, wait, unpack); 0: two launches
         int pdl = 1;            // programmatic dependent launch of the vertical advection kernel (prologue under the previous kernel's tail): 0 off, 1 unless SMs are reserved, 2 always
         int reserve_sms = 0;    // SMs the persistent stencil grids leave free (for a halo exchange that runs beside them)
@@ -105,8 +106,8 @@ namespace gtb {
     // Launch with the programmatic-stream-serialization attribute (option "pdl"): the kernel must call ptx::pdl_wait()
     // before it reads or writes anything an earlier kernel of the stream may have touched.
     template <class... KArgs, class... Args>
-    inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-        Args &&...args) {
+    inline cudaError_t launch_pdl_if(bool allowed, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+        cudaStream_t stream, Args &&...args) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = grid;
         cfg.blockDim = block;
@@ -114,11 +115,18 @@ namespace gtb {
         cfg.stream = stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        // not next to a concurrent exchange: the early CTAs of the NEXT launch would settle on the reserved SMs
-        attr[0].val.programmaticStreamSerializationAllowed = opts().pdl == 2 || (opts().pdl == 1 && opts().reserve_sms == 0) ? 1 : 0;
+        attr[0].val.programmaticStreamSerializationAllowed = allowed ? 1 : 0;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+    }
+    // option "pdl": 0 off, 1 unless SMs are reserved for an exchange on another stream (the early CTAs of the NEXT
+    // launch would settle exactly on the reserved SMs), 2 always
+    inline bool pdl_allowed() { return opts().pdl == 2 || (opts().pdl == 1 && opts().reserve_sms == 0); }
+    template <class... KArgs, class... Args>
+    inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+        Args &&...args) {
+        return launch_pdl_if(pdl_allowed(), kernel, grid, block, smem, stream, std::forward<Args>(args)...);
     }
 
     // TMA descriptor encoder, resolved from the driver at run time (no link-time dependency on libcuda).

@@ -20,6 +20,7 @@
 // Index ranges follow common/halo_descriptor.hpp:90-201 (loop_{low,high}_bound_{inside,outside}, s_length,
 // r_length); message layout is field-major, dimension 0 fastest (gcl/high_level/descriptors.hpp:61-91).
 #include "common.cuh"
+#include "halo_device.cuh"
 
 #include <unistd.h>
 
@@ -28,21 +29,14 @@
 #include <vector>
 
 using namespace gtb;
+using namespace gtb::halo_dev;
 
 namespace {
 
-    constexpr int kMaxFields = 16; // per launch; more fields are handled by looping launches
-    constexpr int kThreads = 256;
-    constexpr int kItems = 8;
+    constexpr int kBlocksPerSm = 5; // transfer kernels: register budget 64K / (5 * 256) = 51 per thread
     constexpr uint64_t kMagic = 0x6774623230306831ull; // "gtb200h1"
     constexpr int64_t kFlagBytes = 2 * 32 * 8;         // flags[parity][direction], uint64 epoch numbers
     constexpr int64_t kAlign = 256;
-
-    struct region {
-        int lo[3];
-        int len[3];
-        int64_t count; // 0: no such neighbour
-    };
 
     struct blob {
         uint64_t magic;
@@ -80,7 +74,8 @@ struct gtb_halo {
     void *opened[27];
     bool connected;
     uint64_t epoch; // starts at 1
-    int *d_error;   // device flag set by a wait that timed out
+    int *d_error;   // set by a wait that timed out: the device address of ...
+    int *h_error;   // ... this word of mapped, pinned host memory (readable without synchronising)
     unsigned *d_counters; // block counter of the fused pack + signal launch
     unsigned long long *trace; // diagnosis (gtb_halo_set_trace): [epoch % 256][8] globaltimer stamps
 };
@@ -93,41 +88,6 @@ namespace {
     int lo_outside(const gtb_halo_desc &h, int e) { return e == 0 ? h.begin : (e == 1 ? h.end + 1 : h.begin - h.minus); }
     int hi_outside(const gtb_halo_desc &h, int e) { return e == 0 ? h.end : (e == 1 ? h.end + h.plus : h.begin - 1); }
 
-    // Fused synchronisation of a transfer launch.  mode 1 (pack towards peers): the last block of the launch raises
-    // the neighbours' flags once every block has made its stores visible system-wide.  mode 2 (unpack): a block
-    // acquires the flag of a direction before it touches that direction's message.
-    struct sync_args {
-        uint64_t epoch;
-        unsigned *counter; // zero between launches
-        int *error;
-        long long timeout_cycles;
-        int mode; // 0 none, 1 signal after pack, 2 wait before unpack
-        const unsigned long long *gate; // unpack: wait for *gate >= gate_value before scattering (stencil still reads the halos)
-        unsigned long long gate_value;
-        unsigned long long *gate_timeouts;
-        unsigned long long *unpacked;   // unpack: the last block stores the epoch here when every block is done
-        unsigned *counter2;             // block counter of that, zero between launches
-        unsigned long long *trace;      // diagnosis: row of 8 globaltimer stamps of this epoch, or nullptr
-    };
-
-    constexpr int kMaxSeg = 26;
-    constexpr int kChunk = kThreads * kItems; // elements a block moves per step
-
-    // One launch moves every field of every active direction ("segment").  The work is a flat list of chunks of
-    // kChunk elements, segment-major then field-major, that a SMALL grid walks with a grid stride: the exchange has
-    // to run beside a persistent stencil kernel that owns the SMs, so it must not flood the CTA scheduler -- the first
-    // version launched 27 x n_fields x ceil(count / 1024) blocks, most of them empty, which filled every thread slot
-    // of the chip ahead of the lower-priority stencil launch and serialised the two (profiles/README.md).
-    struct seg_table {
-        int n_seg;
-        int dir[kMaxSeg];             // direction number (0..26) of segment s: reported by a wait that times out
-        region r[kMaxSeg];
-        char *buf[kMaxSeg];           // message buffer per segment (local or NVLink-mapped)
-        uint64_t *flag[kMaxSeg];      // flag to raise (pack) or to wait for (unpack); nullptr: none
-        int chunks_per_field[kMaxSeg];
-        int chunk_start[kMaxSeg + 1]; // prefix sum of chunks_per_field * n_fields
-    };
-
     struct xfer_args {
         seg_table t;
         char *fields[kMaxFields];
@@ -137,102 +97,52 @@ namespace {
         sync_args sync;
     };
 
-    struct exchange_args { // pack + signal + wait + unpack in one launch
-        seg_table snd, rcv;
-        char *fields[kMaxFields];
-        int64_t s1, s2;
-        int n_fields;
-        uint64_t fill_bits;
-        sync_args sync;
-    };
-
-    __device__ __forceinline__ void wait_flag(const uint64_t *flag, uint64_t epoch, int *error, long long timeout, int n) {
-        if (*reinterpret_cast<volatile int *>(error))
-            return; // an earlier wait already timed out: do not stall every following exchange as well
-        const long long t0 = clock64();
-        for (;;) {
-            uint64_t v;
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
-            if (v >= epoch)
-                break;
-            if (clock64() - t0 > timeout) {
-                atomicExch(error, 1 + n);
-                break;
-            }
-            __nanosleep(100);
-        }
-    }
-
-    template <class E>
-    __device__ __forceinline__ E make_fill(uint64_t bits) {
-        return (E)bits;
-    }
-    template <>
-    __device__ __forceinline__ uint4 make_fill<uint4>(uint64_t bits) { // bits = the element pattern repeated to 64 bits
-        return make_uint4((unsigned)bits, (unsigned)(bits >> 32), (unsigned)bits, (unsigned)(bits >> 32));
-    }
-
     // The chunks of one segment table, walked with a grid stride.  PACK: field -> buffer; else buffer -> field.
     // WAIT: acquire a segment's flag before its first chunk.
     template <class E, bool PACK, bool WAIT>
     __device__ __forceinline__ void move_chunks(const seg_table &t, char *const *fields, int64_t s1, int64_t s2,
         const sync_args &sy, uint64_t fill_bits = 0) {
         const int total = t.chunk_start[t.n_seg];
-        unsigned waited = 0; // segments whose flag this block has acquired (block-uniform)
+        unsigned waited = 0, failed = 0; // segments whose flag this block has acquired / given up on (block-uniform)
+        __shared__ int s_ok;
         int s = 0;
         for (int ch = blockIdx.x; ch < total; ch += gridDim.x) {
             while (ch >= t.chunk_start[s + 1])
                 ++s;
             if (WAIT && t.flag[s] && !((waited >> s) & 1u)) {
                 if (threadIdx.x == 0) {
-                    wait_flag(t.flag[s], sy.epoch, sy.error, sy.timeout_cycles, t.dir[s]);
+                    s_ok = wait_flag(t.flag[s], sy.epoch, sy.error, sy.timeout_cycles, t.dir[s]);
                     if (sy.trace)
                         atomicMax(sy.trace + 3, ptx::globaltimer());
                 }
                 __syncthreads();
                 waited |= 1u << s;
+                if (!s_ok)
+                    failed |= 1u << s;
+                __syncthreads();
             }
+            if (WAIT && ((failed >> s) & 1u))
+                continue; // the message never arrived: the halo keeps its old values, the error word is set
             const region &r = t.r[s];
             const int local = ch - t.chunk_start[s];
             const int f = local / t.chunks_per_field[s];
-            const int64_t base = (int64_t)(local - f * t.chunks_per_field[s]) * kChunk + threadIdx.x;
+            const uint32_t first = (uint32_t)(local - f * t.chunks_per_field[s]) * (uint32_t)kChunk;
             const bool fill = !PACK && t.buf[s] == nullptr; // border segment: boundary value instead of a message
             E *buf = reinterpret_cast<E *>(t.buf[s]) + (int64_t)f * r.count;
-            E *fld = reinterpret_cast<E *>(fields[f]);
-            const int l0 = r.len[0], l1 = r.len[1];
-            int64_t idx[kItems];
-            E v[kItems];
-#pragma unroll
-            for (int it = 0; it < kItems; ++it) {
-                int64_t e = base + (int64_t)it * kThreads;
-                if (e < r.count) {
-                    int64_t q = e / l0;
-                    int i0 = (int)(e - q * l0);
-                    int64_t q2 = q / l1;
-                    int i1 = (int)(q - q2 * l1);
-                    idx[it] = (r.lo[0] + i0) + (r.lo[1] + i1) * s1 + (r.lo[2] + q2) * s2;
-                    v[it] = PACK ? fld[idx[it]] : (fill ? make_fill<E>(fill_bits) : buf[e]);
-                }
-            }
-#pragma unroll
-            for (int it = 0; it < kItems; ++it) {
-                int64_t e = base + (int64_t)it * kThreads;
-                if (e < r.count) {
-                    if (PACK)
-                        buf[e] = v[it];
-                    else
-                        fld[idx[it]] = v[it];
-                }
-            }
+            move_chunk<E, PACK>(r.lo[0], r.lo[1], r.lo[2], r.len[0], r.len[1], s1, s2, (uint32_t)r.count, first,
+                reinterpret_cast<E *>(fields[f]), buf, fill, fill_bits);
         }
     }
 
     // After the pack: the last block of the launch raises the neighbours' flags once every block has made its
     // stores visible system-wide.
     __device__ __forceinline__ void signal_peers(const seg_table &t, const sync_args &sy, int *s_last) {
-        __threadfence_system(); // this thread's payload stores are visible to the peers before the block is counted
+        // The block's payload stores are ordered before the barrier, the ONE system-scope fence of thread 0 after it
+        // is cumulative over them (the pattern of a cooperative-groups grid sync).  Every thread fencing at system
+        // scope -- 5 000 MEMBAR.SYS per pack -- slowed the stencil kernel that runs beside the exchange.
         __syncthreads();
         if (threadIdx.x == 0) {
+            __threadfence_system();
             const unsigned done = atomicAdd(sy.counter, 1u) + 1u;
             *s_last = done == gridDim.x;
             if (*s_last)
@@ -246,7 +156,7 @@ namespace {
     }
 
     template <class E, bool PACK>
-    __global__ void __launch_bounds__(kThreads) xfer_kernel(const __grid_constant__ xfer_args a) {
+    __global__ void __launch_bounds__(kThreads, kBlocksPerSm) xfer_kernel(const __grid_constant__ xfer_args a) {
         __shared__ int s_last;
         if (a.sync.trace && threadIdx.x == 0 && blockIdx.x == 0)
             a.sync.trace[PACK ? 0 : 2] = ptx::globaltimer();
@@ -264,8 +174,9 @@ namespace {
         if (a.sync.trace && threadIdx.x == 0)
             atomicMax(a.sync.trace + (PACK ? 1 : 4), ptx::globaltimer());
         if (!PACK && a.sync.unpacked) { // publish "halos of epoch e are in place" for device-side gates
-            __threadfence();
             __syncthreads();
+            if (threadIdx.x == 0)
+                __threadfence();
             if (threadIdx.x == 0 && atomicAdd(a.sync.counter2, 1u) + 1u == gridDim.x) {
                 *a.sync.counter2 = 0;
                 __threadfence();
@@ -279,7 +190,7 @@ namespace {
     // resident when it starts to wait; a block that waits only depends on the PEERS' pack phases, never on a block of
     // its own launch that has not started (those only delay the peers' flags until the scheduler places them).
     template <class E>
-    __global__ void __launch_bounds__(kThreads) exchange_kernel(const __grid_constant__ exchange_args a) {
+    __global__ void __launch_bounds__(kThreads, kBlocksPerSm) exchange_kernel(const __grid_constant__ exchange_args a) {
         __shared__ int s_last;
         move_chunks<E, true, false>(a.snd, a.fields, a.s1, a.s2, a.sync);
         signal_peers(a.snd, a.sync, &s_last);
@@ -332,11 +243,17 @@ namespace {
 
     int64_t align_up(int64_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 
-    constexpr long long kTimeoutCycles = 6000000000ll; // ~3 s at 2 GHz: a lost neighbour must not hang the GPU
+    // Clock cycles a device-side wait for a neighbour's message may take (option halo.timeout_ms, default 60 s; 0: wait
+    // for ever like MPI_Wait).  Long, because a neighbour that is merely late -- load imbalance, I/O, a first-call
+    // JIT, a debugger -- is not an error; finite by default, because a GPU that spins for ever cannot be recovered.
+    long long timeout_cycles() {
+        const long long ms = opts().halo_timeout_ms;
+        return ms <= 0 ? 0 : ms * 2000000ll; // ~2 GHz
+    }
 
     // Segment table of the active directions.  sync_mode 1: flags to raise at the neighbours; 2: own flags to wait for.
     void fill_table(seg_table &t, const gtb_halo *h, bool pack, char *const bufs[27], int nf, int64_t field_offset,
-        int sync_mode) {
+        int sync_mode, int chunk = kChunk) {
         const region *regs = pack ? h->send : h->recv;
         t.n_seg = 0;
         t.chunk_start[0] = 0;
@@ -354,7 +271,7 @@ namespace {
                 else if (sync_mode == 2)
                     t.flag[sg] = reinterpret_cast<uint64_t *>(h->arena) + (h->epoch & 1) * 32 + n;
             }
-            t.chunks_per_field[sg] = (int)((regs[n].count + kChunk - 1) / kChunk);
+            t.chunks_per_field[sg] = (int)((regs[n].count + chunk - 1) / chunk);
             t.chunk_start[sg + 1] = t.chunk_start[sg] + t.chunks_per_field[sg] * nf;
         }
         if (!pack && h->bc_kind == GTB_BC_VALUE) // distributed_boundaries.hpp: value condition where there is no neighbour
@@ -366,7 +283,7 @@ namespace {
                 t.r[sg] = h->border[n];
                 t.buf[sg] = nullptr;
                 t.flag[sg] = nullptr;
-                t.chunks_per_field[sg] = (int)((h->border[n].count + kChunk - 1) / kChunk);
+                t.chunks_per_field[sg] = (int)((h->border[n].count + chunk - 1) / chunk);
                 t.chunk_start[sg + 1] = t.chunk_start[sg] + t.chunks_per_field[sg] * nf;
             }
     }
@@ -376,7 +293,7 @@ namespace {
         sy.epoch = h->epoch;
         sy.counter = h->d_counters;
         sy.error = h->d_error;
-        sy.timeout_cycles = kTimeoutCycles;
+        sy.timeout_cycles = timeout_cycles();
         sy.gate = nullptr;
         sy.gate_value = 0;
         sy.gate_timeouts = nullptr;
@@ -385,12 +302,16 @@ namespace {
         sy.trace = h->trace ? h->trace + (h->epoch % 256) * 8 : nullptr;
     }
 
-    // Blocks of a transfer launch: at most one small block per SM (option halo.max_blocks overrides).  The first of
-    // them start at once on the SMs a persistent stencil kernel leaves free (reserve_sms), the rest as its CTAs retire;
-    // capping the grid at what the reserved SMs hold makes an 8-neighbour exchange 7 us slower (r01_overlap_schemes.txt).
+    // Blocks of a transfer launch.  Beside a persistent stencil kernel (reserve_sms > 0) the grid is what the reserved
+    // SMs hold at once (kBlocksPerSm each): every block is resident from the start and the launch does not have to
+    // wait for stencil CTAs to retire (the device timeline of round 2, profiles/r02_exchange_timeline.txt, showed the
+    // tail blocks of a one-block-per-SM grid doing exactly that).  Standing alone: one block per SM.  Option
+    // halo.max_blocks overrides both.
     int xfer_grid(int chunks) {
         device_state *dv = dev();
         int cap = dv ? dv->sm_count : 128;
+        if (opts().reserve_sms > 0)
+            cap = opts().reserve_sms * kBlocksPerSm;
         if (opts().halo_max_blocks > 0)
             cap = opts().halo_max_blocks;
         return chunks < 1 ? 1 : (chunks > cap ? cap : chunks);
@@ -577,12 +498,17 @@ GTB_API int gtb_halo_create(const gtb_halo_desc desc[3], const int neighbour_ran
     h->send_arena = nullptr;
     h->arena = nullptr;
     h->d_error = nullptr;
+    h->h_error = nullptr;
     h->d_counters = nullptr;
     cudaError_t e = cudaMalloc(&h->send_arena, (size_t)(h->send_total + kAlign));
     if (e == cudaSuccess)
         e = cudaMalloc(&h->arena, (size_t)h->arena_bytes);
     if (e == cudaSuccess)
-        e = cudaMalloc(&h->d_error, sizeof(int));
+        e = cudaHostAlloc(&h->h_error, sizeof(int), cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+        *h->h_error = 0;
+        e = cudaHostGetDevicePointer(&h->d_error, h->h_error, 0);
+    }
     if (e == cudaSuccess)
         e = cudaMalloc(&h->d_counters, 32 * sizeof(unsigned));
     if (e == cudaSuccess)
@@ -594,11 +520,9 @@ GTB_API int gtb_halo_create(const gtb_halo_desc desc[3], const int neighbour_ran
     if (e == cudaSuccess)
         e = cudaMemset(h->arena, 0, (size_t)h->arena_bytes);
     if (e == cudaSuccess)
-        e = cudaMemset(h->d_error, 0, sizeof(int));
-    if (e == cudaSuccess)
         e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
-        cudaFree(h->send_arena), cudaFree(h->arena), cudaFree(h->d_error), cudaFree(h->d_counters), cudaFree(h->d_unpacked);
+        cudaFree(h->send_arena), cudaFree(h->arena), cudaFreeHost(h->h_error), cudaFree(h->d_counters), cudaFree(h->d_unpacked);
         delete h;
         cuda_fail(e, "gtb_halo_create: buffer allocation");
         return GTB_ERR_ALLOC;
@@ -626,7 +550,7 @@ GTB_API int gtb_halo_destroy(gtb_halo *h) {
     free_generic_tables(h);
     cudaFree(h->send_arena);
     cudaFree(h->arena);
-    cudaFree(h->d_error);
+    cudaFreeHost(h->h_error);
     cudaFree(h->d_counters);
     cudaFree(h->d_unpacked);
     delete h;
@@ -793,7 +717,7 @@ GTB_API int gtb_halo_wait(gtb_halo *h, void *stream) {
         return GTB_OK;
     w.epoch = h->epoch;
     w.error = h->d_error;
-    w.timeout_cycles = kTimeoutCycles;
+    w.timeout_cycles = timeout_cycles();
     wait_kernel<<<1, 32, 0, as_stream(stream)>>>(w);
     count_launch();
     return check_launch("halo wait");
@@ -895,11 +819,11 @@ namespace {
     };
 
     template <class E, bool PACK>
-    __global__ void __launch_bounds__(kThreads) generic_xfer_kernel(const __grid_constant__ gx_args a) {
+    __global__ void __launch_bounds__(kThreads, kBlocksPerSm) generic_xfer_kernel(const __grid_constant__ gx_args a) {
         __shared__ int s_last;
         if (a.sync.trace && threadIdx.x == 0 && blockIdx.x == 0)
             a.sync.trace[PACK ? 0 : 2] = ptx::globaltimer();
-        unsigned waited = 0; // directions whose flag this block has acquired
+        unsigned waited = 0, failed = 0; // directions whose flag this block has acquired / given up on
         int s = 0;
         for (int ch = blockIdx.x; ch < a.n_chunks; ch += gridDim.x) {
             while (s + 1 < a.n_seg && ch >= a.segs[s + 1].chunk_start)
@@ -907,42 +831,23 @@ namespace {
             const gseg g = a.segs[s];
             if (!PACK && a.flag[g.dir] && !((waited >> g.dir) & 1u)) {
                 if (threadIdx.x == 0)
-                    wait_flag(a.flag[g.dir], a.sync.epoch, a.sync.error, a.sync.timeout_cycles, g.dir);
+                    s_last = wait_flag(a.flag[g.dir], a.sync.epoch, a.sync.error, a.sync.timeout_cycles, g.dir);
                 __syncthreads();
                 waited |= 1u << g.dir;
+                if (!s_last)
+                    failed |= 1u << g.dir;
+                __syncthreads();
             }
-            const int64_t base = (int64_t)(ch - g.chunk_start) * kChunk + threadIdx.x;
-            E *buf = reinterpret_cast<E *>(g.buf);
-            E *fld = reinterpret_cast<E *>(g.fld);
-            int64_t idx[kItems];
-            E v[kItems];
-#pragma unroll
-            for (int it = 0; it < kItems; ++it) {
-                const int64_t e = base + (int64_t)it * kThreads;
-                if (e < g.count) {
-                    const int64_t q = e / g.len[0];
-                    const int i0 = (int)(e - q * g.len[0]);
-                    const int64_t q2 = q / g.len[1];
-                    const int i1 = (int)(q - q2 * g.len[1]);
-                    idx[it] = (g.lo[0] + i0) + (g.lo[1] + i1) * g.s1 + (g.lo[2] + q2) * g.s2;
-                    v[it] = PACK ? fld[idx[it]] : buf[e];
-                }
-            }
-#pragma unroll
-            for (int it = 0; it < kItems; ++it) {
-                const int64_t e = base + (int64_t)it * kThreads;
-                if (e < g.count) {
-                    if (PACK)
-                        buf[e] = v[it];
-                    else
-                        fld[idx[it]] = v[it];
-                }
-            }
+            if (!PACK && ((failed >> g.dir) & 1u))
+                continue;
+            move_chunk<E, PACK>(g.lo[0], g.lo[1], g.lo[2], g.len[0], g.len[1], g.s1, g.s2, (uint32_t)g.count,
+                (uint32_t)(ch - g.chunk_start) * (uint32_t)kChunk, reinterpret_cast<E *>(g.fld),
+                reinterpret_cast<E *>(g.buf), false, 0);
         }
         if (PACK) { // the last block raises the neighbours' flags once every block's stores are visible system-wide
-            __threadfence_system();
             __syncthreads();
             if (threadIdx.x == 0) {
+                __threadfence_system(); // cumulative over the block's stores (see signal_peers)
                 const unsigned done = atomicAdd(a.sync.counter, 1u) + 1u;
                 s_last = done == gridDim.x;
                 if (s_last)
@@ -1097,11 +1002,90 @@ GTB_API int gtb_halo_generic_wait_unpack(gtb_halo *h, const gtb_halo_field *fiel
     return run_generic<false>(h, fields, n_fields, as_stream(stream), "gtb_halo_generic_wait_unpack");
 }
 
+// ------------------------------------------------------------------------------------------- attached exchange
+// gtb_halo_attach arms the NEXT stencil launch of this host thread: the launch gets n_ctas extra CTAs that run the
+// whole exchange (halo_device.cuh: comm_cta) beside the CTAs that compute.  One launch per time step, no second
+// stream, no events -- the stream order of the launches is the only ordering there is: the exchange is complete when
+// the launch is, and it may touch nothing the stencil of the same launch reads or writes.
+namespace {
+    struct attached_state {
+        gtb_halo *h = nullptr;
+        std::vector<void *> fields;
+        int n_cta = 0;
+    };
+    thread_local attached_state t_attached;
+} // namespace
+
+GTB_API int gtb_halo_attach(gtb_halo *h, void *const *fields, int n_fields, int n_ctas) {
+    int st = check_fields(h, fields, n_fields, "gtb_halo_attach");
+    if (st)
+        return st;
+    if (!h->connected)
+        return fail(GTB_ERR_STATE, "gtb_halo_attach: gtb_halo_connect has not been called");
+    if (n_fields < 1 || n_fields > kMaxFields)
+        return fail(GTB_ERR_ARG, "gtb_halo_attach: 1 .. %d fields per attached exchange", kMaxFields);
+    if (n_ctas < 1 || n_ctas > 32)
+        return fail(GTB_ERR_ARG, "gtb_halo_attach: 1 .. 32 communication CTAs");
+    t_attached.h = h;
+    t_attached.fields.assign(fields, fields + n_fields);
+    t_attached.n_cta = n_ctas;
+    return GTB_OK;
+}
+
+namespace gtb {
+    // An attached exchange the stencil launch could not carry (a kernel variant without communication CTAs): run it as
+    // two launches of its own on the same stream -- the contract of gtb_halo_attach still holds.
+    int flush_attached(void *stream) {
+        if (!t_attached.h)
+            return GTB_OK;
+        gtb_halo *h = t_attached.h;
+        t_attached.h = nullptr;
+        return gtb_halo_exchange(h, t_attached.fields.data(), (int)t_attached.fields.size(), stream);
+    }
+
+    int take_attached(halo_dev::attached_args &out, int cta_threads) {
+        out.n_cta = 0;
+        if (!t_attached.h)
+            return GTB_OK;
+        gtb_halo *h = t_attached.h;
+        t_attached.h = nullptr; // one-shot
+        const int nf = (int)t_attached.fields.size();
+        char *sbufs[27], *rbufs[27];
+        for (int n = 0; n < 27; ++n) {
+            sbufs[n] = h->send[n].count ? peer_slot(h, n, h->epoch) : nullptr;
+            rbufs[n] = h->recv[n].count ? recv_slot(h, n, h->epoch) : nullptr;
+        }
+        exchange_args &a = out.x;
+        const int chunk = kAttachedItems * cta_threads;
+        fill_table(a.snd, h, true, sbufs, nf, 0, 1, chunk);
+        fill_table(a.rcv, h, false, rbufs, nf, 0, 2, chunk);
+        fill_sync(a.sync, h, 1);
+        a.fill_bits = h->bc_bits;
+        a.s1 = h->d[0].total;
+        a.s2 = (int64_t)h->d[0].total * h->d[1].total;
+        for (int f = 0; f < nf; ++f)
+            a.fields[f] = static_cast<char *>(t_attached.fields[f]);
+        a.n_fields = nf;
+        out.es = h->es;
+        out.chunk = chunk;
+        out.n_cta = t_attached.n_cta;
+        h->epoch += 1; // the launch that takes these arguments completes the exchange
+        return GTB_OK;
+    }
+} // namespace gtb
+
 GTB_API int gtb_halo_error(gtb_halo *h, int *code) {
     if (!h || !code)
         return fail(GTB_ERR_ARG, "gtb_halo_error: null argument");
     GTB_CUDA(cudaDeviceSynchronize());
-    GTB_CUDA(cudaMemcpy(code, h->d_error, sizeof(int), cudaMemcpyDeviceToHost));
+    *code = *reinterpret_cast<volatile int *>(h->h_error);
+    return GTB_OK;
+}
+
+GTB_API int gtb_halo_poll_error(gtb_halo *h, int *code) {
+    if (!h || !code)
+        return fail(GTB_ERR_ARG, "gtb_halo_poll_error: null argument");
+    *code = *reinterpret_cast<volatile int *>(h->h_error);
     return GTB_OK;
 }
 

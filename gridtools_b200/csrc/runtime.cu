@@ -177,6 +177,7 @@ namespace {
             {"reserve_sms", &o.reserve_sms},
             {"pdl", &o.pdl},
             {"halo.fused", &o.halo_fused},
+            {"halo.timeout_ms", &o.halo_timeout_ms},
             {"halo.vec", &o.halo_vec},
             {"halo.max_blocks", &o.halo_max_blocks},
             {"copy.vec", &o.copy_vec}};
@@ -236,6 +237,47 @@ GTB_API int gtb_release_scratch(void) {
 }
 
 GTB_API int64_t gtb_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------------ streams for hosts
+// Host bindings that do not want to include the CUDA runtime (the gcl handler of include/gtb200/gcl/b200.hpp) get
+// their private stream here.  gtb_stream_create gives a NON-BLOCKING stream: work on it is not ordered against the
+// legacy default stream implicitly, gtb_stream_after_default() orders it explicitly after everything issued to the
+// legacy default stream so far (what a kernel launched on a blocking stream would get for free).
+GTB_API int gtb_stream_create(void **stream, int high_priority) {
+    if (!stream)
+        return fail(GTB_ERR_ARG, "gtb_stream_create: null argument");
+    if (!dev())
+        return GTB_ERR_CUDA;
+    int lo = 0, hi = 0;
+    GTB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    cudaStream_t s;
+    GTB_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high_priority ? hi : lo));
+    *stream = s;
+    return GTB_OK;
+}
+
+GTB_API int gtb_stream_destroy(void *stream) {
+    if (stream)
+        GTB_CUDA(cudaStreamDestroy(as_stream(stream)));
+    return GTB_OK;
+}
+
+GTB_API int gtb_stream_after_default(void *stream) {
+    cudaEvent_t e;
+    GTB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaError_t st = cudaEventRecord(e, cudaStreamLegacy);
+    if (st == cudaSuccess)
+        st = cudaStreamWaitEvent(as_stream(stream), e, 0);
+    cudaEventDestroy(e); // released when the record has completed
+    if (st != cudaSuccess)
+        return cuda_fail(st, "gtb_stream_after_default");
+    return GTB_OK;
+}
+
+GTB_API int gtb_stream_synchronize(void *stream) {
+    GTB_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    return GTB_OK;
+}
 
 // ------------------------------------------------------------------------------------------------ stencil gates
 namespace gtb {

@@ -208,9 +208,21 @@ typedef struct {
 } gtb_halo_field;
 int gtb_halo_generic_pack_send(gtb_halo *h, const gtb_halo_field *fields, int n_fields, void *stream);
 int gtb_halo_generic_wait_unpack(gtb_halo *h, const gtb_halo_field *fields, int n_fields, void *stream);
-/* Synchronises the device and reports whether a wait timed out: *code = 0 if not, else 1 + direction that never
- * arrived.  (Halo_Exchange_3D has no error path: a lost MPI peer hangs in MPI_Wait.) */
+/* ATTACHED exchange: arms the NEXT stencil launch of this host thread (gtb_hori_diff_*, gtb_vert_adv_* on their default
+ * TMA kernels) with a complete exchange of `fields` -- pack, NVLink stores, flags, wait, unpack and the epoch advance of
+ * gtb_halo_exchange -- run by n_ctas extra CTAs of that launch beside the CTAs that compute.  A time step becomes ONE
+ * launch: no communication stream, no events, and programmatic dependent launch keeps working between steps.  The
+ * exchange is complete when the launch is; it must not touch what the stencil of the same launch reads or writes
+ * (exchange the fields of the NEXT step).  This is the compute + collective fusion for loops of the shape
+ * pack / exchange / unpack; run (tests/regression/gcl/copy_stencil_parallel.cpp:126-145). */
+int gtb_halo_attach(gtb_halo *h, void *const *fields, int n_fields, int n_ctas);
+/* Device-side waits for a neighbour's message give up after option "halo.timeout_ms" (default 60 000; 0 = wait for
+ * ever, like the MPI_Wait of Halo_Exchange_3D).  A wait that gave up does NOT unpack that message (the halo keeps its
+ * old values) and stores 1 + direction in an error word in mapped host memory; every later wait of the object fails
+ * at once.  gtb_halo_error synchronises the device first, gtb_halo_poll_error just reads the word (cheap enough for
+ * every time step); *code = 0 if all is well. */
 int gtb_halo_error(gtb_halo *h, int *code);
+int gtb_halo_poll_error(gtb_halo *h, int *code);
 /* Diagnosis: with a device buffer of 256 x 8 uint64 set, the transfer kernels of epoch e stamp %globaltimer (ns) into
  * row e % 256: [0] pack starts, [1] pack ends (flags raised), [2] unpack starts, [3] last arrival flag acquired,
  * [4] unpack ends.  NULL switches it off.  gtb_stamp enqueues a one-thread kernel that stores %globaltimer. */
@@ -263,6 +275,16 @@ int gtb_stencil_gate(const void *wait_flag, uint64_t wait_value, void *post_coun
 int gtb_halo_gate(gtb_halo *h, const void *counter, uint64_t value);
 int gtb_gate_timeouts(int64_t *count);
 
+/* ------------------------------------------------------------------------------------------------- streams
+ * For host bindings that do not include the CUDA runtime themselves.  gtb_stream_create returns a NON-BLOCKING
+ * cudaStream_t (optionally of the highest priority, for exchanges that run beside a stencil); gtb_stream_after_default
+ * makes the work issued to it from now on wait for everything issued to the legacy default stream so far;
+ * gtb_stream_synchronize blocks the host until the stream is idle. */
+int gtb_stream_create(void **stream, int high_priority);
+int gtb_stream_destroy(void *stream);
+int gtb_stream_after_default(void *stream);
+int gtb_stream_synchronize(void *stream);
+
 /* ------------------------------------------------------------------------------------- recorded call sequences
  * The reference's user programs drive their time loop from C++ (tests/regression/gcl/copy_stencil_parallel.cpp:126-145:
  * he.pack / he.exchange / he.unpack followed by run(spec, backend, grid, fields...)), a microsecond or two of host
@@ -285,6 +307,8 @@ int gtb_seq_add_vert_adv(gtb_seq *s, int elem_size, const gtb_field *utens_stage
 int gtb_seq_add_prepare_tracers(gtb_seq *s, const gtb_field *out, const gtb_field *in, int n_tracers,
     const gtb_field *rho, int ni, int nj, int nk, void *stream);
 int gtb_seq_add_halo_exchange(gtb_seq *s, gtb_halo *h, void *const *fields, int n_fields, void *stream);
+/* gtb_halo_attach for the stencil operation recorded NEXT */
+int gtb_seq_add_halo_attach(gtb_seq *s, gtb_halo *h, void *const *fields, int n_fields, int n_ctas);
 /* gtb_stencil_gate / gtb_halo_gate for the operation recorded NEXT (armed when the sequence reaches them) */
 int gtb_seq_add_stencil_gate(gtb_seq *s, const void *wait_flag, uint64_t wait_value, void *post_counter);
 int gtb_seq_add_halo_gate(gtb_seq *s, gtb_halo *h, const void *counter, uint64_t value);

@@ -24,6 +24,12 @@
  * and its split-phase parts have nothing left to do (no MPI_Isend / MPI_Irecv / MPI_Wait, no cudaDeviceSynchronize).
  * Ranks must share one NVLink/NVSwitch box (one process per GPU, or threads of one process).
  *
+ * Synchronisation: by default pack() and unpack() behave like the reference's GPU handler, which ends both with
+ * cudaDeviceSynchronize (descriptors_manual_gpu.hpp:400,431,486,514): the kernels run on a private non-blocking stream
+ * ordered after the legacy default stream, and unpack() returns when the halos are in place.  set_stream(s) switches
+ * to fully asynchronous operation on the caller's stream (no host synchronisation at all; the caller orders the
+ * stream against its stencils), which is what overlaps an exchange with computation.
+ *
  * Element types of any size that is a multiple of 4 bytes travel as 4- or 8-byte words (the reference's own test
  * exchanges array<int, 4>).  Failures of the C ABI are thrown as std::runtime_error.
  */
@@ -52,6 +58,38 @@ namespace gridtools {
                 if (status != GTB_OK)
                     throw std::runtime_error(std::string(what) + ": " + gtb_last_error());
             }
+
+            /// default: a private non-blocking stream, ordered after the legacy default stream at pack(), host-synchronised
+            /// at the end of unpack() (the reference's blocking semantics); a user stream: nothing of that
+            class stream_policy {
+                void *m_own = nullptr, *m_user = nullptr;
+
+              public:
+                stream_policy() = default;
+                stream_policy(stream_policy const &) = delete;
+                ~stream_policy() {
+                    if (m_own)
+                        gtb_stream_destroy(m_own);
+                }
+                void set(void *user) { m_user = user; }
+                void *get() {
+                    if (m_user)
+                        return m_user;
+                    if (!m_own)
+                        check(gtb_stream_create(&m_own, 1), "gtb_stream_create");
+                    return m_own;
+                }
+                void *before_pack() {
+                    void *s = get();
+                    if (!m_user)
+                        check(gtb_stream_after_default(s), "gtb_stream_after_default");
+                    return s;
+                }
+                void after_unpack() {
+                    if (!m_user)
+                        check(gtb_stream_synchronize(m_own), "gtb_stream_synchronize");
+                }
+            };
 
             /// words a T is moved as, and how many of them
             template <class T>
@@ -107,7 +145,7 @@ namespace gridtools {
             using words = b200_impl_::words<DataType>;
 
             gtb_halo *m_h = nullptr;
-            void *m_stream = nullptr;
+            b200_impl_::stream_policy m_stream;
 
             hndlr_dynamic_ut(hndlr_dynamic_ut const &) = delete;
             hndlr_dynamic_ut(hndlr_dynamic_ut &&) = delete;
@@ -115,13 +153,14 @@ namespace gridtools {
             void do_pack(void *const *fields, int n) {
                 if (!m_h)
                     throw std::logic_error("gcl::b200: pack() before setup()");
-                b200_impl_::check(gtb_halo_pack_send(m_h, fields, n, m_stream), "gtb_halo_pack_send");
+                b200_impl_::check(gtb_halo_pack_send(m_h, fields, n, m_stream.before_pack()), "gtb_halo_pack_send");
             }
             void do_unpack(void *const *fields, int n) {
                 if (!m_h)
                     throw std::logic_error("gcl::b200: unpack() before setup()");
-                b200_impl_::check(gtb_halo_wait_unpack(m_h, fields, n, m_stream), "gtb_halo_wait_unpack");
+                b200_impl_::check(gtb_halo_wait_unpack(m_h, fields, n, m_stream.get()), "gtb_halo_wait_unpack");
                 b200_impl_::check(gtb_halo_next_epoch(m_h), "gtb_halo_next_epoch");
+                m_stream.after_unpack();
             }
 
           public:
@@ -153,8 +192,8 @@ namespace gridtools {
                 m_h = b200_impl_::create_and_connect(this->comm(), desc, nbr, max_fields_n, words::size);
             }
 
-            /// kernels are enqueued on this cudaStream_t (default: the legacy default stream, like the reference)
-            void set_stream(void *cuda_stream) { m_stream = cuda_stream; }
+            /// asynchronous operation on the caller's cudaStream_t (see the header comment); nullptr = the default again
+            void set_stream(void *cuda_stream) { m_stream.set(cuda_stream); }
 
             template <typename... FIELDS>
             void pack(const FIELDS *..._fields) {
@@ -196,7 +235,7 @@ namespace gridtools {
         template <typename HaloExch, typename proc_layout_abs>
         class hndlr_generic<HaloExch, proc_layout_abs, b200> : public descriptor_base<HaloExch> {
             gtb_halo *m_h = nullptr;
-            void *m_stream = nullptr;
+            mutable b200_impl_::stream_policy m_stream;
             int m_max_fields = 0;
 
             hndlr_generic(hndlr_generic const &) = delete;
@@ -216,15 +255,16 @@ namespace gridtools {
             void do_pack(std::vector<gtb_halo_field> const &fs) const {
                 if (!m_h)
                     throw std::logic_error("gcl::b200: pack() before setup()");
-                b200_impl_::check(gtb_halo_generic_pack_send(m_h, fs.data(), (int)fs.size(), m_stream),
+                b200_impl_::check(gtb_halo_generic_pack_send(m_h, fs.data(), (int)fs.size(), m_stream.before_pack()),
                     "gtb_halo_generic_pack_send");
             }
             void do_unpack(std::vector<gtb_halo_field> const &fs) const {
                 if (!m_h)
                     throw std::logic_error("gcl::b200: unpack() before setup()");
-                b200_impl_::check(gtb_halo_generic_wait_unpack(m_h, fs.data(), (int)fs.size(), m_stream),
+                b200_impl_::check(gtb_halo_generic_wait_unpack(m_h, fs.data(), (int)fs.size(), m_stream.get()),
                     "gtb_halo_generic_wait_unpack");
                 b200_impl_::check(gtb_halo_next_epoch(m_h), "gtb_halo_next_epoch");
+                m_stream.after_unpack();
             }
 
           public:
@@ -258,7 +298,7 @@ namespace gridtools {
                 m_max_fields = max_fields_n;
             }
 
-            void set_stream(void *cuda_stream) { m_stream = cuda_stream; }
+            void set_stream(void *cuda_stream) { m_stream.set(cuda_stream); }
 
             template <typename... FIELDS>
             void pack(const FIELDS &..._fields) const {

@@ -391,7 +391,7 @@ namespace gridtools {
                 template <class Spec, class Grid, class DataStores>
                 static void generic(std::true_type /*fused*/, Spec spec, Grid const &grid, DataStores &data_stores) {
                     fused::cuda_launcher launcher{static_cast<cudaStream_t>(StreamGetter()())};
-                    fused::run<Geometry>(launcher, spec, grid, std::move(data_stores));
+                    fused::run_fused_spec<Geometry>(launcher, spec, grid, std::move(data_stores));
                 }
                 template <class Spec, class Grid, class DataStores>
                 static void generic(std::false_type, Spec spec, Grid const &grid, DataStores &data_stores) {

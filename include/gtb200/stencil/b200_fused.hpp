@@ -686,8 +686,10 @@ namespace gridtools {
                 }
 
                 // ---------------------------------------------------------------- host side: the whole spec
+                // (not called `run`: the tag's geometry argument makes this namespace an associated one of every b200<> tag,
+                // and an unqualified run(spec, backend, grid, ...) with an lvalue spec would pick an overload named run here)
                 template <class Geo = geometry<>, class Launcher, class Spec, class Grid, class DataStores>
-                void run(Launcher &launcher, Spec, Grid const &grid, DataStores external) {
+                void run_fused_spec(Launcher &launcher, Spec, Grid const &grid, DataStores external) {
                     using msses_t = be_api::make_fused_view<Spec>;
                     static_assert(fusable<Spec>::value, "stencil::b200: spec cannot take the fused path");
                     // device memory behind the temporaries that are not (purely) cached

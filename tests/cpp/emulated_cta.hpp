@@ -70,7 +70,7 @@ namespace emulated {
         template <class Spec, class Grid, class DataStores>
         friend void gridtools_backend_entry_point(backend, Spec spec, Grid const &grid, DataStores data_stores) {
             launcher l;
-            gridtools::stencil::b200_backend::fused::run<Geo>(l, spec, grid, std::move(data_stores));
+            gridtools::stencil::b200_backend::fused::run_fused_spec<Geo>(l, spec, grid, std::move(data_stores));
             last_launches() = l.launches;
         }
         static long &last_launches() {

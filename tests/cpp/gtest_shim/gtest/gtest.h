@@ -45,7 +45,7 @@ namespace testing {
         using ParamType = T;
         static const T &GetParam() { return *param_ptr(); }
         static const T *&param_ptr() {
-            static const T *p = nullptr;
+            static const T *p = nullptr; // shared by the rank threads of the MPI stand-in: see state_t::between_tests
             return p;
         }
     };
@@ -105,6 +105,9 @@ namespace testing {
             std::atomic<int> failures{0};
             std::mutex print;
             bool quiet = false;
+            // called before every test; the MPI stand-in puts a barrier here, so that all rank threads are in the
+            // same test (the parameter pointer of TEST_P is one static per suite, like in googletest)
+            std::function<void()> between_tests;
         };
         inline state_t &state() {
             static state_t s;
@@ -412,6 +415,8 @@ namespace testing {
                 std::cout << "[ RUN      ] " << full << std::endl;
             }
             internal::current_failures() = 0;
+            if (s.between_tests)
+                s.between_tests();
             if (t.before)
                 t.before();
             {

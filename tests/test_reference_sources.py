@@ -1,0 +1,60 @@
+"""The reference's OWN test sources, compiled unchanged where they lie under /root/reference/tests (tests/cpp/Makefile,
+target reference_sources) with two stand-ins for what this image lacks: tests/cpp/gtest_shim (googletest) and
+oracle/mpi_shim (MPI, threads as ranks), plus the one block a maintainer adds to tests/include/{stencil,gcl}_select.hpp
+(tests/cpp/select/).  The binaries are built in the build container and travel to the GPU box.
+
+  gcl_reference_cpu    tests/regression/gcl/test_halo_exchange_3D.cpp on the reference's gcl::cpu: proves the stand-ins
+  gcl_reference_b200   the same source with gcl_arch_t = gridtools::gcl::b200 (only the arch tag differs)
+  regression_b200      tests/regression/*.cpp (18 sources) + tests/src/regression_main.cpp with
+                       stencil_backend_t = gridtools::stencil::b200<>, no registration lines: the generic fused path
+"""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "tests", "_build")
+
+
+def run(name, *args, timeout=900):
+    exe = os.path.join(BUILD, name)
+    if not os.path.exists(exe):
+        pytest.skip("tests/_build/%s not built (make -C tests/cpp reference_sources in the build container)" % name)
+    r = subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True, timeout=timeout)
+    tail = r.stdout[-6000:] + r.stderr[-2000:]
+    return r.returncode, r.stdout, tail
+
+
+def test_reference_gcl_test_passes_on_its_own_cpu_arch_through_the_shims():
+    """halo_exchange_3D_all + halo_exchange_3D_generic (6 layouts x vector/variadic x 2^3 periodicities, 6 parameter
+    sets) on gcl::cpu with 2 thread-ranks: the unmodified reference passes its own test on gtest_shim + mpi_shim."""
+    rc, out, tail = run("gcl_reference_cpu", 2)
+    assert rc == 0 and "ALL PASSED" in out, tail
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ranks", [2, 4])
+def test_reference_gcl_test_passes_on_the_b200_arch(ranks):
+    """The same unmodified source with gcl_arch_t = gridtools::gcl::b200: reference class templates, reference ctor
+    (periodicity, MPI_Comm), device storages; rank threads share the visible GPUs."""
+    rc, out, tail = run("gcl_reference_b200", ranks)
+    assert rc == 0 and "ALL PASSED" in out, tail
+
+
+@pytest.mark.gpu
+def test_reference_regression_sources_pass_on_the_b200_backend():
+    """tests/regression/*.cpp through stencil::b200<> at the harness' inlined domain sizes (12x33x61, 23x11x43),
+    float and double, verified by the reference's own verifier against its own analytic repositories."""
+    rc, out, tail = run("regression_b200")
+    assert rc == 0 and "[  FAILED  ]" not in out, tail
+    assert "tests ran" in out and int(out.split("[==========] ")[-1].split(" tests ran")[0]) >= 40, tail
+
+
+@pytest.mark.gpu
+def test_reference_perftests_mode_on_the_b200_backend():
+    """`perftests 256 256 80 3` (tests/src/regression_main.cpp:27-60): the command-line sized cases, timed by the
+    harness' own timer_cuda, results verified."""
+    rc, out, tail = run("regression_b200", 256, 256, 80, 3)
+    assert rc == 0 and "[  FAILED  ]" not in out, tail
+    assert '"outputs"' in out and "horizontal_diffusion" in out and "vertical_advection_dycore" in out, tail
