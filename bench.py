@@ -40,6 +40,7 @@ P100_MPTS = {"vert_adv": 5117.0, "hori_diff": 10300.0}  # BASELINE.md section 1:
 HALO = {"vert_adv": 3, "hori_diff": 2}
 HALO_FUSED = 0   # N > 1: gtb_halo_exchange as one launch (pack, signal, wait, unpack)
 RESERVE_SMS = 4  # N > 1: SMs the persistent stencil grids leave free for the concurrent halo exchange kernels
+HALO_DMA = 1     # N > 1: the NVLink leg of the exchange on the copy engines (option halo.dma)
 
 
 def parse():
@@ -377,29 +378,6 @@ def b200_arm(args):
             if not use_gates and not nodeps:
                 sq.record(t % M, comm_h)
 
-        if attached:  # ONE launch per step: the stencil of step s carries the exchange of step s + 1 in extra CTAs
-            sq.halo_exchange(he, [sets[0][exch_index]], comp_h)
-            for s in range(total_steps):
-                first = len(sq)
-                if s == n_warm + LEAD:
-                    sq.mark(0, comp_h)
-                if timeline is not None and s < timeline.shape[0]:
-                    sq.stamp(timeline[s, 0:1].data_ptr(), comp_h)
-                if s + 1 < total_steps:
-                    sq.halo_attach(he, [sets[(s + 1) % n_sets][exch_index]], comm_ctas)
-                if name == "vert_adv":
-                    sq.vertical_advection_dycore(*sets[s % n_sets], dtr, stream=comp_h)
-                else:
-                    sq.horizontal_diffusion(*sets[s % n_sets], stream=comp_h)
-                if timeline is not None and s < timeline.shape[0]:
-                    sq.stamp(timeline[s, 1:2].data_ptr(), comp_h)
-                ops.append((first, len(sq) - first))
-            ops[0] = (0, ops[0][0] + ops[0][1])
-            sq.mark(1, comp_h)
-            ops[-1] = (ops[-1][0], ops[-1][1] + 1)
-            sq.keep = done
-            return sq, ops
-
         for s in range(total_steps):
             first = len(sq)
             if s == n_warm + LEAD:
@@ -432,23 +410,17 @@ def b200_arm(args):
     # GTB_TIMELINE=1 (diagnosis, distorts the timing slightly): %globaltimer stamps around every stencil launch and
     # inside the transfer kernels; rank 0 prints the steps of the timed region to stderr
     timeline = halo_trace = None
+    reserve_sms, halo_dma = 0, 0
     if he is not None and os.environ.get("GTB_TIMELINE") == "1":
         timeline = torch.zeros((total_steps, 2), dtype=torch.int64, device="cuda")
         halo_trace = torch.zeros((256, 8), dtype=torch.int64, device="cuda")
         _lib.check(_lib.lib().gtb_halo_set_trace(he._h, C.c_void_p(halo_trace.data_ptr())))
         epoch0 = he.epoch()
-    # N > 1, default: the exchange is ATTACHED to the stencil launch (gtb_halo_attach): a few extra CTAs of the stencil
-    # kernel's own grid pack, push over NVLink, wait and unpack while the others compute -- one launch per step, one
-    # stream, no events.  GTB_ATTACHED=0 selects the round-1 choreography (exchange kernels on a second stream).
-    attached = he is not None and os.environ.get("GTB_ATTACHED", "1") == "1"
-    comm_ctas = int(os.environ.get("GTB_COMM_CTAS", 4 if name == "vert_adv" else 8))
-    if attached:
-        _lib.set_option("reserve_sms", 0)
-        if "GTB_PDL" in os.environ:
-            _lib.set_option("pdl", int(os.environ["GTB_PDL"]))
-        seq, step_ops = build_sequence(False)
-    elif he is not None:
-        _lib.set_option("reserve_sms", int(os.environ.get("GTB_RESERVE_SMS", RESERVE_SMS)))  # left to the exchange
+    if he is not None:
+        reserve_sms = int(os.environ.get("GTB_RESERVE_SMS", RESERVE_SMS))
+        halo_dma = int(os.environ.get("GTB_HALO_DMA", HALO_DMA))
+        _lib.set_option("reserve_sms", reserve_sms)  # left to the exchange
+        _lib.set_option("halo.dma", halo_dma)
         _lib.set_option("halo.fused", int(os.environ.get("GTB_HALO_FUSED", HALO_FUSED)))
         if "GTB_PDL" in os.environ:
             _lib.set_option("pdl", int(os.environ["GTB_PDL"]))
@@ -519,13 +491,14 @@ def b200_arm(args):
         s0 = n_warm + LEAD + 2
         t0 = int(tl[s0, 0])
         sys.stderr.write("timeline (us, relative to the start of stencil %d); exchange e feeds stencil e\n" % s0)
-        sys.stderr.write("%5s %9s %9s | %9s %9s | %9s %9s %9s\n" % ("step", "st.start", "st.end", "pk.start", "pk.end",
-                                                                    "up.start", "up.flags", "up.end"))
+        sys.stderr.write("%5s %9s %9s | %9s %9s %9s | %9s %9s %9s\n" % ("step", "st.start", "st.end", "pk.start", "pk.end",
+                                                                        "signal", "up.start", "up.flags", "up.end"))
         for st in range(s0, min(s0 + 8, total_steps)):
             row = ht[(epoch0 + st) % 256]
             rel = lambda v: (int(v) - t0) / 1e3  # noqa: E731
-            sys.stderr.write("%5d %9.1f %9.1f | %9.1f %9.1f | %9.1f %9.1f %9.1f\n" % (
-                st, rel(tl[st, 0]), rel(tl[st, 1]), rel(row[0]), rel(row[1]), rel(row[2]), rel(row[3]), rel(row[4])))
+            sys.stderr.write("%5d %9.1f %9.1f | %9.1f %9.1f %9.1f | %9.1f %9.1f %9.1f\n" % (
+                st, rel(tl[st, 0]), rel(tl[st, 1]), rel(row[0]), rel(row[1]), rel(row[5]) if row[5] else float("nan"),
+                rel(row[2]), rel(row[3]) if row[3] else float("nan"), rel(row[4])))
     rank_ms = [total_ms / args.steps]
     if world > 1:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
@@ -578,14 +551,14 @@ def b200_arm(args):
             name, NI, NJ, NK, "fp64" if itemsize == 8 else "fp32",
             " (BASELINE.json configs[1] family)" if default_size else
             " (%s scaling of a %dx%dx%d global domain)" % (args.scaling, global_ni, global_nj, NK)),
-                   "decomposition": ("%dx%dx1 IJ process grid, halo exchange of %s every step over NVLink (peer stores, "
-                                     "device-side flags), " % (dims[0], dims[1], "wcon" if name == "vert_adv" else "in") +
-                                     ("ATTACHED to the stencil launch: %d communication CTAs of the stencil kernel's own grid "
-                                      "exchange the next step's field while the other CTAs compute (one launch per step)" % comm_ctas
-                                      if attached else
-                                      "overlapped with the previous step's stencil on a high-priority stream, ordered by %s; %d SMs "
-                                      "reserved for it" % ("device-side gates" if gated else "stream events", RESERVE_SMS)) +
-                                     "; loop issued as one recorded gtb_seq") if world > 1 else "single GPU",
+                   "decomposition": ("%dx%dx1 IJ process grid, halo exchange of %s every step over NVLink: local pack kernel, "
+                                     "%s, device-side arrival flags, local unpack kernel; on a high-priority stream beside "
+                                     "the previous step's stencil, ordered by %s; %d SMs reserved for the pack / unpack "
+                                     "kernels; loop issued as one recorded gtb_seq" % (
+                                         dims[0], dims[1], "wcon" if name == "vert_adv" else "in",
+                                         "copy-engine (DMA) transfers into the neighbours' receive buffers" if halo_dma else
+                                         "peer stores from the pack kernel", "device-side gates" if gated else "stream events",
+                                         reserve_sms)) if world > 1 else "single GPU",
                    "l2": "inputs of one step (%d MB) exceed L2 and %d field set(s) are rotated" % (
                        sum(f.nbytes_host for f in sets[0][:5 if name == "vert_adv" else 2]) // 2**20, n_sets),
                    "vs_baseline_ref": "reference stencil::gpu on P100, BASELINE.md section 1"},

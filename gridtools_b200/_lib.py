@@ -83,8 +83,6 @@ _SIG = {
     "gtb_halo_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "gtb_halo_next_epoch": (C.c_int, [C.c_void_p]),
     "gtb_halo_poll_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
-    "gtb_halo_attach": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int]),
-    "gtb_seq_add_halo_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int]),
     "gtb_halo_set_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gtb_stamp": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gtb_halo_generic_pack_send": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),

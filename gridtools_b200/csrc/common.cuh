@@ -49,6 +49,7 @@ namespace gtb {
         int halo_max_blocks = 0; // > 0: grid size cap of the halo transfer kernels (0: one block per SM)
         int halo_vec = 1;       // 16-byte vector transfers where the halo regions allow it
         int halo_timeout_ms = 60000; // device-side waits for a neighbour's message give up after this long; 0: never
+        int halo_dma = 0;       // gtb_halo_exchange / gtb_halo_send: the NVLink leg as copy-engine transfers of the packed messages
         int halo_fused = 0;     // gtb_halo_exchange as ONE launch (pack, signal, wait, unpack); 0: two launches
         int pdl = 1;            // programmatic dependent launch of the vertical advection kernel (prologue under the previous kernel's tail): 0 off, 1 unless SMs are reserved, 2 always
         int reserve_sms = 0;    // SMs the persistent stencil grids leave free (for a halo exchange that runs beside them)
@@ -68,10 +69,10 @@ namespace gtb {
     // Lazily initialised state of the current device; nullptr + error set if there is no usable device.
     device_state *dev();
 
-    // Cached scratch (temporaries): one growing slab per device, reused by every call on that device.  Stencil
-    // calls on different streams that both need scratch must not overlap (same rule as the reference's
-    // thread-local cached allocator).
-    void *scratch(size_t bytes);
+    // Cached scratch (temporaries, the counterpart of the reference's sid::device::cached_allocator): one growing slab
+    // per (device, stream).  Launches on one stream are ordered and share their slab; launches on different streams
+    // may overlap, so every stream has its own (gtb_release_scratch frees them all).
+    void *scratch(size_t bytes, cudaStream_t stream);
     int set_l2_persist(int64_t bytes);
 
     // Device-side ordering of a stencil launch against a halo exchange that runs beside it on another stream

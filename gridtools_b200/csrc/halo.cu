@@ -216,10 +216,13 @@ namespace {
     struct signal_args {
         uint64_t *flag[27]; // neighbour's flag word for the message coming from this rank (nullptr: none)
         uint64_t epoch;
+        unsigned long long *trace; // diagnosis: [5] = flags raised
     };
 
     __global__ void signal_kernel(const __grid_constant__ signal_args a) {
         const int n = threadIdx.x;
+        if (a.trace && n == 0)
+            a.trace[5] = ptx::globaltimer();
         if (n < 27 && a.flag[n]) {
             __threadfence_system(); // order the payload stores of the previous kernels before the flag
             asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.flag[n]), "l"(a.epoch) : "memory");
@@ -424,6 +427,7 @@ namespace {
         if (!any)
             return GTB_OK;
         s.epoch = h->epoch;
+        s.trace = h->trace ? h->trace + (h->epoch % 256) * 8 : nullptr;
         signal_kernel<<<1, 32, 0, stream>>>(s);
         count_launch();
         return check_launch("halo signal");
@@ -672,6 +676,17 @@ GTB_API int gtb_halo_send(gtb_halo *h, int n_fields, void *stream) {
         return fail(GTB_ERR_STATE, "gtb_halo_send: gtb_halo_connect has not been called");
     if (n_fields < 0 || n_fields > h->max_fields)
         return fail(GTB_ERR_ARG, "gtb_halo_send: n_fields %d exceeds max_fields %d", n_fields, h->max_fields);
+    if (opts().halo_dma) {
+        // The NVLink leg on the COPY ENGINES: one asynchronous peer copy per neighbour from the packed send buffer into
+        // the neighbour's receive buffer.  An SM sustains only ~10 GB/s of peer stores (profiles/r02_exchange_timeline.txt:
+        // the 2 MB of an 8-neighbour exchange took 33 us on the four SMs a persistent stencil can spare), the copy
+        // engines move them at link speed without touching an SM.  The flags follow in stream order.
+        for (int n = 0; n < 27; ++n)
+            if (h->send[n].count)
+                GTB_CUDA(cudaMemcpyAsync(peer_slot(h, n, h->epoch), h->send_arena + h->send_off[n],
+                    (size_t)(h->send[n].count * n_fields * h->es), cudaMemcpyDefault, as_stream(stream)));
+        return signal(h, as_stream(stream));
+    }
     push_args a;
     int64_t max_bytes = 0;
     for (int n = 0; n < 27; ++n) {
@@ -786,7 +801,13 @@ GTB_API int gtb_halo_exchange(gtb_halo *h, void *const *fields, int n_fields, vo
             return st;
         return gtb_halo_next_epoch(h);
     }
-    st = gtb_halo_pack_send(h, fields, n_fields, stream);
+    if (opts().halo_dma) { // pack locally, copy engines over NVLink, flags (option halo.dma, see gtb_halo_send)
+        st = gtb_halo_pack(h, fields, n_fields, stream);
+        if (!st)
+            st = gtb_halo_send(h, n_fields, stream);
+    } else {
+        st = gtb_halo_pack_send(h, fields, n_fields, stream);
+    }
     if (st)
         return st;
     st = gtb_halo_wait_unpack(h, fields, n_fields, stream);
@@ -1001,78 +1022,6 @@ GTB_API int gtb_halo_generic_pack_send(gtb_halo *h, const gtb_halo_field *fields
 GTB_API int gtb_halo_generic_wait_unpack(gtb_halo *h, const gtb_halo_field *fields, int n_fields, void *stream) {
     return run_generic<false>(h, fields, n_fields, as_stream(stream), "gtb_halo_generic_wait_unpack");
 }
-
-// ------------------------------------------------------------------------------------------- attached exchange
-// gtb_halo_attach arms the NEXT stencil launch of this host thread: the launch gets n_ctas extra CTAs that run the
-// whole exchange (halo_device.cuh: comm_cta) beside the CTAs that compute.  One launch per time step, no second
-// stream, no events -- the stream order of the launches is the only ordering there is: the exchange is complete when
-// the launch is, and it may touch nothing the stencil of the same launch reads or writes.
-namespace {
-    struct attached_state {
-        gtb_halo *h = nullptr;
-        std::vector<void *> fields;
-        int n_cta = 0;
-    };
-    thread_local attached_state t_attached;
-} // namespace
-
-GTB_API int gtb_halo_attach(gtb_halo *h, void *const *fields, int n_fields, int n_ctas) {
-    int st = check_fields(h, fields, n_fields, "gtb_halo_attach");
-    if (st)
-        return st;
-    if (!h->connected)
-        return fail(GTB_ERR_STATE, "gtb_halo_attach: gtb_halo_connect has not been called");
-    if (n_fields < 1 || n_fields > kMaxFields)
-        return fail(GTB_ERR_ARG, "gtb_halo_attach: 1 .. %d fields per attached exchange", kMaxFields);
-    if (n_ctas < 1 || n_ctas > 32)
-        return fail(GTB_ERR_ARG, "gtb_halo_attach: 1 .. 32 communication CTAs");
-    t_attached.h = h;
-    t_attached.fields.assign(fields, fields + n_fields);
-    t_attached.n_cta = n_ctas;
-    return GTB_OK;
-}
-
-namespace gtb {
-    // An attached exchange the stencil launch could not carry (a kernel variant without communication CTAs): run it as
-    // two launches of its own on the same stream -- the contract of gtb_halo_attach still holds.
-    int flush_attached(void *stream) {
-        if (!t_attached.h)
-            return GTB_OK;
-        gtb_halo *h = t_attached.h;
-        t_attached.h = nullptr;
-        return gtb_halo_exchange(h, t_attached.fields.data(), (int)t_attached.fields.size(), stream);
-    }
-
-    int take_attached(halo_dev::attached_args &out, int cta_threads) {
-        out.n_cta = 0;
-        if (!t_attached.h)
-            return GTB_OK;
-        gtb_halo *h = t_attached.h;
-        t_attached.h = nullptr; // one-shot
-        const int nf = (int)t_attached.fields.size();
-        char *sbufs[27], *rbufs[27];
-        for (int n = 0; n < 27; ++n) {
-            sbufs[n] = h->send[n].count ? peer_slot(h, n, h->epoch) : nullptr;
-            rbufs[n] = h->recv[n].count ? recv_slot(h, n, h->epoch) : nullptr;
-        }
-        exchange_args &a = out.x;
-        const int chunk = kAttachedItems * cta_threads;
-        fill_table(a.snd, h, true, sbufs, nf, 0, 1, chunk);
-        fill_table(a.rcv, h, false, rbufs, nf, 0, 2, chunk);
-        fill_sync(a.sync, h, 1);
-        a.fill_bits = h->bc_bits;
-        a.s1 = h->d[0].total;
-        a.s2 = (int64_t)h->d[0].total * h->d[1].total;
-        for (int f = 0; f < nf; ++f)
-            a.fields[f] = static_cast<char *>(t_attached.fields[f]);
-        a.n_fields = nf;
-        out.es = h->es;
-        out.chunk = chunk;
-        out.n_cta = t_attached.n_cta;
-        h->epoch += 1; // the launch that takes these arguments completes the exchange
-        return GTB_OK;
-    }
-} // namespace gtb
 
 GTB_API int gtb_halo_error(gtb_halo *h, int *code) {
     if (!h || !code)

@@ -1,7 +1,5 @@
-// halo_device.cuh -- device side of the halo exchange that more than one translation unit needs: the transfer kernels
-// of halo.cu and the COMMUNICATION CTAs that a stencil launch can carry (gtb_halo_attach, include/gtb200.h): a few
-// extra CTAs of the stencil kernel's own grid run a complete exchange (pack -> NVLink stores -> flags -> wait ->
-// unpack) beside the CTAs that compute, so that a time step is ONE launch with no stream events around it.
+// halo_device.cuh -- device side of the halo exchange: message geometry, arrival flags and the chunk mover of the
+// transfer kernels of halo.cu.
 #pragma once
 
 #include "common.cuh"
@@ -12,7 +10,6 @@ namespace gtb {
     constexpr int kMaxFields = 16; // per launch; more fields are handled by looping launches
     constexpr int kThreads = 256;  // block size of the stand-alone transfer kernels
     constexpr int kItems = 8;
-    constexpr int kAttachedItems = 16; // elements per thread and chunk of an attached exchange: chunk = 16 x CTA size
 
     struct region {
         int lo[3];
@@ -72,14 +69,16 @@ namespace gtb {
     // waits fail at once instead of stalling every following exchange for the whole timeout as well.
     __device__ __forceinline__ bool wait_flag(const uint64_t *flag, uint64_t epoch, int *error, long long timeout, int n) {
         const long long t0 = clock64();
-        for (;;) {
+        for (unsigned spins = 0;; ++spins) {
             uint64_t v; // poll relaxed, acquire once at the end
             asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
             if (v >= epoch) {
                 asm volatile("fence.acq_rel.sys;" ::: "memory");
                 return true;
             }
-            if (timeout > 0 && (clock64() - t0 > timeout || *reinterpret_cast<volatile int *>(error))) {
+            // the error word lives in HOST memory (a read crosses PCIe): look at it once in a while only
+            if (timeout > 0 && (spins & 0xfffu) == 0xfffu &&
+                (clock64() - t0 > timeout || *reinterpret_cast<volatile int *>(error))) {
                 if (!*reinterpret_cast<volatile int *>(error)) {
                     *reinterpret_cast<volatile int *>(error) = 1 + n;
                     __threadfence_system();
@@ -108,11 +107,11 @@ namespace gtb {
     template <class E, bool PACK, int THREADS = kThreads, int ITEMS = kItems>
     __device__ __forceinline__ void move_chunk(const int lo0, const int lo1, const int lo2, const int l0, const int l1,
         const int64_t s1, const int64_t s2, const uint32_t count, const uint32_t first, E *__restrict__ fld,
-        E *__restrict__ buf, const bool fill, const uint64_t fill_bits) {
+        E *__restrict__ buf, const bool fill, const uint64_t fill_bits, const int tid = threadIdx.x) {
         constexpr int kBatch = sizeof(E) >= 16 && ITEMS > 4 ? ITEMS / 2 : ITEMS;
         const uint32_t c = (uint32_t)THREADS / (uint32_t)l0;
         const int d0 = (int)((uint32_t)THREADS - c * (uint32_t)l0), d1 = (int)(c % (uint32_t)l1), d2 = (int)(c / (uint32_t)l1);
-        uint32_t e = first + threadIdx.x;
+        uint32_t e = first + (uint32_t)tid;
         const uint32_t q = e / (uint32_t)l0, q2 = q / (uint32_t)l1;
         int i0 = (int)(e - q * (uint32_t)l0), i1 = (int)(q - q2 * (uint32_t)l1), i2 = (int)q2;
         auto index = [&]() { return (int64_t)(lo0 + i0) + (int64_t)(lo1 + i1) * s1 + (int64_t)(lo2 + i2) * s2; };
@@ -160,99 +159,6 @@ namespace gtb {
     }
 
 
-    // ------------------------------------------------------------------------------------------ communication CTAs
-    // What CTA `cta` of `n_cta` communication CTAs does inside a stencil launch: its share of the pack chunks, the
-    // hand-shake (the last CTA to finish raises the neighbours' flags), its share of the unpack chunks behind the
-    // arrival flags.  A communication CTA only ever waits for communication CTAs of the NEIGHBOURS' launches, never
-    // for a CTA of its own launch, and the launchers put these CTAs first in the grid so that they are resident
-    // before any stencil CTA.  Chunks are 16 elements per thread: 16 loads in flight per thread (the exchange is
-    // latency-bound on the few SMs it gets).
-    struct attached_args {
-        exchange_args x;
-        int n_cta;  // 0: no exchange attached to this launch
-        int es;     // bytes per element the tables are expressed in: 4, 8 or 16
-        int chunk;  // elements per chunk the tables were built with (16 x block size of the carrying kernel)
-    };
-
-    template <class E, bool PACK, int THREADS>
-    __device__ __forceinline__ void comm_move(const seg_table &t, char *const *fields, int64_t s1, int64_t s2,
-        const sync_args &sy, uint64_t fill_bits, int cta, int n_cta, int *s_ok) {
-        constexpr int ITEMS = kAttachedItems;
-        constexpr int kAttachedChunk = THREADS * ITEMS;
-        const int total = t.chunk_start[t.n_seg];
-        unsigned waited = 0, failed = 0;
-        int s = 0;
-        for (int ch = cta; ch < total; ch += n_cta) {
-            while (ch >= t.chunk_start[s + 1])
-                ++s;
-            if (!PACK && t.flag[s] && !((waited >> s) & 1u)) {
-                if (threadIdx.x == 0)
-                    *s_ok = wait_flag(t.flag[s], sy.epoch, sy.error, sy.timeout_cycles, t.dir[s]);
-                __syncthreads();
-                waited |= 1u << s;
-                if (!*s_ok)
-                    failed |= 1u << s;
-                __syncthreads();
-            }
-            if ((failed >> s) & 1u)
-                continue; // the message never arrived: leave the halo alone, the error flag is set
-            const region &r = t.r[s];
-            const int local = ch - t.chunk_start[s];
-            const int f = local / t.chunks_per_field[s];
-            const uint32_t first = (uint32_t)(local - f * t.chunks_per_field[s]) * (uint32_t)kAttachedChunk;
-            const bool fill = !PACK && t.buf[s] == nullptr;
-            E *buf = reinterpret_cast<E *>(t.buf[s]) + (int64_t)f * r.count;
-            move_chunk<E, PACK, THREADS, ITEMS>(r.lo[0], r.lo[1], r.lo[2], r.len[0], r.len[1], s1, s2, (uint32_t)r.count,
-                first, reinterpret_cast<E *>(fields[f]), buf, fill, fill_bits);
-        }
-    }
-
-    template <class E, int THREADS>
-    __device__ __forceinline__ void comm_cta_typed(const exchange_args &a, int cta, int n_cta, int *s_int) {
-        if (a.sync.trace && threadIdx.x == 0 && cta == 0)
-            a.sync.trace[0] = ptx::globaltimer();
-        comm_move<E, true, THREADS>(a.snd, a.fields, a.s1, a.s2, a.sync, 0, cta, n_cta, s_int);
-        __syncthreads(); // this CTA's payload stores, then ONE cumulative system-scope fence
-        if (threadIdx.x == 0) {
-            __threadfence_system();
-            const unsigned done = atomicAdd(a.sync.counter, 1u) + 1u;
-            *s_int = done == (unsigned)n_cta;
-            if (*s_int)
-                *a.sync.counter = 0;
-        }
-        __syncthreads();
-        if (*s_int && threadIdx.x < a.snd.n_seg && a.snd.flag[threadIdx.x]) {
-            __threadfence_system();
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.snd.flag[threadIdx.x]), "l"(a.sync.epoch) : "memory");
-        }
-        __syncthreads();
-        if (a.sync.trace && threadIdx.x == 0) {
-            atomicMax(a.sync.trace + 1, ptx::globaltimer());
-            if (cta == 0)
-                a.sync.trace[2] = ptx::globaltimer();
-        }
-        comm_move<E, false, THREADS>(a.rcv, a.fields, a.s1, a.s2, a.sync, a.fill_bits, cta, n_cta, s_int);
-        if (a.sync.trace && threadIdx.x == 0)
-            atomicMax(a.sync.trace + 4, ptx::globaltimer());
-    }
-
-    // s_int: one int of shared memory
-    template <int THREADS>
-    __device__ __forceinline__ void comm_cta(const attached_args &a, int cta, int *s_int) {
-        if (a.es == 8)
-            comm_cta_typed<uint64_t, THREADS>(a.x, cta, a.n_cta, s_int);
-        else if (a.es == 4)
-            comm_cta_typed<uint32_t, THREADS>(a.x, cta, a.n_cta, s_int);
-        else
-            comm_cta_typed<uint4, THREADS>(a.x, cta, a.n_cta, s_int);
-    }
-
     } // namespace halo_dev
 
-    // host side (halo.cu): the exchange armed by gtb_halo_attach for the next stencil launch of this thread, if any.
-    // Fills `out` (n_cta = 0 when nothing is attached) and advances the epoch of the halo object.
-    // cta_threads: block size of the kernel that will carry it (the chunk tables depend on it).
-    int take_attached(halo_dev::attached_args &out, int cta_threads);
-    // called after every stencil launch: an attached exchange that was not taken runs as launches of its own
-    int flush_attached(void *stream);
 } // namespace gtb

@@ -21,7 +21,6 @@
 // Arithmetic follows the functor bodies operation by operation (no FMA contraction: the file is compiled with
 // -fmad=false), so results are bit-identical to oracle/gt_oracle.c compiled with -ffp-contract=off.
 #include "common.cuh"
-#include "halo_device.cuh"
 #include "tma.cuh"
 
 using namespace gtb;
@@ -256,16 +255,8 @@ namespace {
     // ------------------------------------------------ TMA variant with a block barrier per item (hd.variant = 2)
     template <class T, int STAGES, bool SIMPLE = false>
     __global__ void __launch_bounds__(THREADS, 2) hd_tma_kernel(const __grid_constant__ CUtensorMap map_in,
-        const __grid_constant__ CUtensorMap map_co, const hd_params<T> p,
-        const __grid_constant__ halo_dev::attached_args xa) {
+        const __grid_constant__ CUtensorMap map_co, const hd_params<T> p) {
         using L = layout<T>;
-        // the first xa.n_cta CTAs of the grid run the halo exchange attached to this launch (gtb_halo_attach)
-        if ((int)blockIdx.x < xa.n_cta) {
-            __shared__ int s_comm;
-            halo_dev::comm_cta<THREADS>(xa, (int)blockIdx.x, &s_comm);
-            return;
-        }
-        const int bid = (int)blockIdx.x - xa.n_cta, nblk = (int)gridDim.x - xa.n_cta; // the CTAs that compute
         extern __shared__ __align__(128) unsigned char smem[];
         uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * L::stage_bytes);
         const int tid = threadIdx.x;
@@ -284,7 +275,7 @@ namespace {
         }
         __syncthreads();
         item_iter it, ahead;
-        it.start(p, bid);
+        it.start(p, (int)blockIdx.x);
         ahead = it;
         if (tid == 0) {
             for (int s = 0; s < STAGES && ahead.k < p.nk; ++s, ahead.next(p))
@@ -305,7 +296,7 @@ namespace {
         if (p.gate.post) { // tell whoever waits for this launch (the unpack of a later exchange) that it is done
             __threadfence();
             __syncthreads();
-            if (tid == 0 && atomicAdd(p.gate.cta_done, 1) == nblk - 1) {
+            if (tid == 0 && atomicAdd(p.gate.cta_done, 1) == (int)gridDim.x - 1) {
                 *p.gate.cta_done = 0;
                 __threadfence();
                 atomicAdd(p.gate.post, 1ULL);
@@ -392,16 +383,7 @@ namespace {
         const int64_t items = (int64_t)p.tiles_i * p.tiles_j * p.nk;
         if (items >= (int64_t)1 << 31)
             return fail(GTB_ERR_ARG, "gtb_hori_diff: domain too large (%lld tile-levels)", (long long)items);
-        halo_dev::attached_args xa; // a halo exchange carried by this launch (gtb_halo_attach), n_cta = 0 if none
-        xa.n_cta = 0;
         int grid = stencil_sms(d) * ctas_per_sm;
-        if (variant == 0 || variant == 2) {
-            int st = take_attached(xa, THREADS);
-            if (st)
-                return st;
-            if (xa.n_cta > 0 && grid + xa.n_cta > d->sm_count * ctas_per_sm) // all CTAs of the grid resident at once
-                grid = d->sm_count * ctas_per_sm - xa.n_cta;
-        }
         if (grid > items)
             grid = (int)items;
         p.step_i = grid % p.tiles_i;
@@ -423,7 +405,7 @@ namespace {
                     return st;
                 // (no programmatic dependent launch here: with two CTAs per SM the early CTAs of the next launch take
                 // slots from the running one -- 24.6 -> 29.8 us measured)
-                kernel<<<grid + xa.n_cta, THREADS, smem, stream>>>(map_in, map_co, p, xa);
+                kernel<<<grid, THREADS, smem, stream>>>(map_in, map_co, p);
                 count_launch();
                 return check_launch("hd_tma_kernel");
             }
@@ -503,14 +485,12 @@ namespace {
 
 GTB_API int gtb_hori_diff_f64(const gtb_field *in, const gtb_field *coeff, const gtb_field *out, int ni, int nj,
     int nk, void *stream) {
-    int st = hori_diff<double>(in, coeff, out, ni, nj, nk, stream);
-    return st ? st : flush_attached(stream); // an attached exchange the launched variant could not carry
+    return hori_diff<double>(in, coeff, out, ni, nj, nk, stream);
 }
 
 GTB_API int gtb_hori_diff_f32(const gtb_field *in, const gtb_field *coeff, const gtb_field *out, int ni, int nj,
     int nk, void *stream) {
-    int st = hori_diff<float>(in, coeff, out, ni, nj, nk, stream);
-    return st ? st : flush_attached(stream);
+    return hori_diff<float>(in, coeff, out, ni, nj, nk, stream);
 }
 
 // ------------------------------------------------------------------------------------ simple_hori_diff.cpp:25-61
@@ -628,9 +608,7 @@ namespace {
                 int st = prepare_kernel(kernel, smem);
                 if (st)
                     return st;
-                halo_dev::attached_args none; // (simple_hori_diff launches carry no exchange)
-                none.n_cta = 0;
-                kernel<<<grid, THREADS, smem, as_stream(stream)>>>(map_in, map_co, q, none);
+                kernel<<<grid, THREADS, smem, as_stream(stream)>>>(map_in, map_co, q);
                 count_launch();
                 return check_launch("hd_tma_kernel (simple_hori_diff)");
             }

@@ -1,6 +1,8 @@
 // runtime.cu -- error state, options, device state, cached scratch and the TMA descriptor encoder of libgtb200.
 #include "common.cuh"
 
+#include <map>
+
 #include <mutex>
 #include <string>
 
@@ -14,7 +16,10 @@ namespace gtb {
         struct slab {
             void *ptr = nullptr;
             size_t bytes = 0;
-        } g_scratch[max_devices];
+        };
+        // one slab per (device, stream): launches on one stream run in order and may share a slab, launches on
+        // different streams (or from different host threads on different streams) may overlap and must not
+        std::map<std::pair<int, cudaStream_t>, slab> g_scratch;
         options g_opts;
     } // namespace
 
@@ -74,12 +79,12 @@ namespace gtb {
         return &s;
     }
 
-    void *scratch(size_t bytes) {
+    void *scratch(size_t bytes, cudaStream_t stream) {
         device_state *s = dev();
         if (!s)
             return nullptr;
         std::lock_guard<std::mutex> lock(g_mutex);
-        slab &sl = g_scratch[s->device];
+        slab &sl = g_scratch[{s->device, stream}];
         if (sl.bytes >= bytes && sl.ptr)
             return sl.ptr;
         if (sl.ptr) {
@@ -177,6 +182,7 @@ namespace {
             {"reserve_sms", &o.reserve_sms},
             {"pdl", &o.pdl},
             {"halo.fused", &o.halo_fused},
+            {"halo.dma", &o.halo_dma},
             {"halo.timeout_ms", &o.halo_timeout_ms},
             {"halo.vec", &o.halo_vec},
             {"halo.max_blocks", &o.halo_max_blocks},
@@ -227,11 +233,13 @@ GTB_API int gtb_release_scratch(void) {
     if (!s)
         return GTB_ERR_CUDA;
     std::lock_guard<std::mutex> lock(g_mutex);
-    slab &sl = g_scratch[s->device];
-    if (sl.ptr) {
-        cudaDeviceSynchronize();
-        cudaFree(sl.ptr);
-        sl = slab{};
+    cudaDeviceSynchronize();
+    for (auto it = g_scratch.begin(); it != g_scratch.end();) {
+        if (it->first.first == s->device) {
+            cudaFree(it->second.ptr);
+            it = g_scratch.erase(it);
+        } else
+            ++it;
     }
     return GTB_OK;
 }

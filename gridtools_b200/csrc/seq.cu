@@ -15,7 +15,7 @@
 using namespace gtb;
 
 namespace {
-    enum op_kind { OP_HD64, OP_HD32, OP_VA64, OP_VA32, OP_TRACERS, OP_HALO, OP_RECORD, OP_WAIT, OP_SGATE, OP_HGATE, OP_MARK, OP_STAMP, OP_ATTACH };
+    enum op_kind { OP_HD64, OP_HD32, OP_VA64, OP_VA32, OP_TRACERS, OP_HALO, OP_RECORD, OP_WAIT, OP_SGATE, OP_HGATE, OP_MARK, OP_STAMP };
 
     struct op {
         op_kind kind;
@@ -126,18 +126,6 @@ GTB_API int gtb_seq_add_halo_exchange(gtb_seq *s, gtb_halo *h, void *const *fiel
     o.halo = h;
     o.ptrs.assign(fields, fields + n_fields);
     o.stream = stream;
-    s->ops.push_back(o);
-    return GTB_OK;
-}
-
-GTB_API int gtb_seq_add_halo_attach(gtb_seq *s, gtb_halo *h, void *const *fields, int n_fields, int n_ctas) {
-    if (!s || !h || !fields || n_fields < 1)
-        return fail(GTB_ERR_ARG, "gtb_seq_add_halo_attach: bad argument");
-    op o{};
-    o.kind = OP_ATTACH;
-    o.halo = h;
-    o.ptrs.assign(fields, fields + n_fields);
-    o.event = n_ctas;
     s->ops.push_back(o);
     return GTB_OK;
 }
@@ -266,9 +254,6 @@ GTB_API int gtb_seq_run(gtb_seq *s, int first, int count) {
             break;
         case OP_WAIT:
             GTB_CUDA(cudaStreamWaitEvent(as_stream(o.stream), s->events[o.event], 0));
-            break;
-        case OP_ATTACH:
-            st = gtb_halo_attach(o.halo, o.ptrs.data(), (int)o.ptrs.size(), o.event);
             break;
         case OP_STAMP:
             st = gtb_stamp(o.gate_post, o.stream);

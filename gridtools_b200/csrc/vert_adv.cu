@@ -23,7 +23,6 @@
 // Arithmetic follows the functor bodies operation by operation (-fmad=false, IEEE division), so results are
 // bit-identical to oracle/gt_oracle.c compiled with -ffp-contract=off.
 #include "common.cuh"
-#include "halo_device.cuh"
 #include "tma.cuh"
 
 #include <mutex>
@@ -1680,17 +1679,7 @@ namespace {
     }
 
     template <class T, int KC>
-    __global__ void __launch_bounds__(512, 1) va_pair_kernel(const __grid_constant__ va_maps maps, const va_params<T> p,
-        const __grid_constant__ halo_dev::attached_args xa) {
-        // the first xa.n_cta CTAs of the grid run the halo exchange attached to this launch (gtb_halo_attach)
-        if ((int)blockIdx.x < xa.n_cta) {
-            __shared__ int s_comm;
-            ptx::pdl_launch_dependents();
-            ptx::pdl_wait(); // what is packed may have been written by the previous launch of the stream
-            halo_dev::comm_cta<512>(xa, (int)blockIdx.x, &s_comm);
-            return;
-        }
-        const int bid = (int)blockIdx.x - xa.n_cta, nblk = (int)gridDim.x - xa.n_cta; // the CTAs that compute
+    __global__ void __launch_bounds__(512, 1) va_pair_kernel(const __grid_constant__ va_maps maps, const va_params<T> p) {
         using L = va_tma_layout<T>;
         using CFG = va_tmem_cfg<T>;
         constexpr int es = L::es;
@@ -1750,7 +1739,7 @@ namespace {
         const int nk = p.nk;
         const T dtr = p.dtr;
         const uint64_t pol_keep = ptx::policy_evict_last(), pol_stream = ptx::policy_evict_first();
-        const int total = nblk * PAIRS;
+        const int total = gridDim.x * PAIRS;
         const int nchunks = (nk + KC - 1) / KC;
         const int c_tail = (nk - 1) / KC;   // first forward chunk that needs per-level checks (holds level nk-1)
         const int c_split = p.k_split / KC; // physical chunks [0, c_split) live in TMEM, the rest in the slab
@@ -1760,7 +1749,7 @@ namespace {
         // diagnosis only (va.debug & 128): globaltimer stamps per pair -- [0] start, F warp pass p: [1 + 4p] begin,
         // [2 + 4p] end; B warp pass p: [3 + 4p] begin, [4 + 4p] end
         long long *const trace = (p.debug & 128) && lane == 0 && !idle
-                                     ? p.trace + (size_t)(bid * 8 + pw) * 32
+                                     ? p.trace + (size_t)(blockIdx.x * 8 + pw) * 32
                                      : nullptr;
         auto stamp = [&](int e) {
             if (trace && e < 32)
@@ -1796,7 +1785,7 @@ namespace {
                     issue_f(i0, j, c);
                 u0 = i0 + lane < p.ni ? __ldg(p.u_stage.ptr + i0 + lane + (int64_t)j * p.u_stage.sj) : T(0);
             };
-            int item = pw * nblk + bid;
+            int item = pw * gridDim.x + blockIdx.x;
             T u0 = T(0);
             if (item < p.items)
                 prime(item, u0);
@@ -2017,7 +2006,7 @@ namespace {
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
-            if (atomicAdd(p.tickets + 1, 1) == nblk - 1) { // every F warp has drawn its last ticket
+            if (atomicAdd(p.tickets + 1, 1) == (int)gridDim.x - 1) { // every F warp has drawn its last ticket
                 p.tickets[0] = 0;
                 p.tickets[1] = 0;
                 __threadfence();
@@ -2463,16 +2452,10 @@ namespace {
         p.trace = reinterpret_cast<long long *>(reinterpret_cast<char *>(va_ticket_base()) + 256);
         if (!p.tickets)
             return GTB_ERR_ALLOC;
-        halo_dev::attached_args xa; // a halo exchange carried by this launch (gtb_halo_attach), n_cta = 0 if none
-        int st = take_attached(xa, 512);
-        if (st)
-            return st;
         int grid = o.va_ctas_per_sm < 0 ? -o.va_ctas_per_sm : stencil_sms(d);
-        if (xa.n_cta > 0 && grid > d->sm_count - xa.n_cta) // one CTA per SM: the communication CTAs get their own SMs
-            grid = d->sm_count - xa.n_cta;
         if ((int64_t)grid * pairs > strips)
             grid = (int)((strips + pairs - 1) / pairs);
-        st = set_l2_persist(0);
+        int st = set_l2_persist(0);
         if (st)
             return st;
         auto kernel = va_pair_kernel<T, KC>;
@@ -2482,9 +2465,7 @@ namespace {
             GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             done_dev = d->device;
         }
-        // a launch that carries its exchange has no other stream to stay clear of: dependent launch whenever enabled
-        GTB_CUDA(launch_pdl_if(xa.n_cta > 0 ? opts().pdl != 0 : pdl_allowed(), kernel, dim3(grid + xa.n_cta), dim3(512),
-            (size_t)smem, stream, maps, p, xa));
+        GTB_CUDA(launch_pdl(kernel, dim3(grid), dim3(512), (size_t)smem, stream, maps, p));
         count_launch();
         return check_launch("va_pair_kernel");
     }
@@ -2571,7 +2552,7 @@ namespace {
             p.slots = (int64_t)grid * 32;
             slab_elems = (int64_t)ns * p.nk * p.slots;
         }
-        p.scratch = static_cast<T *>(scratch((size_t)slab_elems * sizeof(T)));
+        p.scratch = static_cast<T *>(scratch((size_t)slab_elems * sizeof(T), stream));
         if (!p.scratch)
             return GTB_ERR_ALLOC;
         p.persistent = 1;
@@ -2686,7 +2667,7 @@ namespace {
         if (mode == 2)
             return dispatch_flags<T, true>(p, o.va_hints != 0, save_upos, unroll, threads, (int)smem_need, grid, s);
         p.slots = p.persistent ? (int64_t)grid * threads : (int64_t)ni * nj;
-        p.scratch = static_cast<T *>(scratch((size_t)ns * nk * p.slots * sizeof(T)));
+        p.scratch = static_cast<T *>(scratch((size_t)ns * nk * p.slots * sizeof(T), s));
         if (!p.scratch)
             return GTB_ERR_ALLOC;
         return dispatch_flags<T, false>(p, o.va_hints != 0, save_upos, unroll, threads, 0, grid, s);
@@ -2696,14 +2677,12 @@ namespace {
 
 GTB_API int gtb_vert_adv_f64(const gtb_field *utens_stage, const gtb_field *u_stage, const gtb_field *wcon,
     const gtb_field *u_pos, const gtb_field *utens, double dtr_stage, int ni, int nj, int nk, void *stream) {
-    int st = vert_adv<double>(utens_stage, u_stage, wcon, u_pos, utens, dtr_stage, ni, nj, nk, stream);
-    return st ? st : flush_attached(stream); // an attached exchange the launched variant could not carry
+    return vert_adv<double>(utens_stage, u_stage, wcon, u_pos, utens, dtr_stage, ni, nj, nk, stream);
 }
 
 GTB_API int gtb_vert_adv_f32(const gtb_field *utens_stage, const gtb_field *u_stage, const gtb_field *wcon,
     const gtb_field *u_pos, const gtb_field *utens, float dtr_stage, int ni, int nj, int nk, void *stream) {
-    int st = vert_adv<float>(utens_stage, u_stage, wcon, u_pos, utens, dtr_stage, ni, nj, nk, stream);
-    return st ? st : flush_attached(stream);
+    return vert_adv<float>(utens_stage, u_stage, wcon, u_pos, utens, dtr_stage, ni, nj, nk, stream);
 }
 
 GTB_API int gtb_tridiagonal_f64(const gtb_field *inf, const gtb_field *diag, const gtb_field *sup, const gtb_field *rhs,

@@ -216,12 +216,6 @@ class Sequence:
         _lib.check(_lib.lib().gtb_seq_add_halo_exchange(self._h, he._h, arr, n, stream))
         self._keep.append((he, fields))
 
-    def halo_attach(self, he, fields, n_ctas=4):
-        """The stencil recorded NEXT carries a complete exchange of `fields` in n_ctas extra CTAs (gtb_halo_attach)."""
-        arr, n = he._ptrs(list(fields))
-        _lib.check(_lib.lib().gtb_seq_add_halo_attach(self._h, he._h, arr, n, int(n_ctas)))
-        self._keep.append((he, fields))
-
     def stencil_gate(self, wait_flag=None, wait_value=0, post_counter=None):
         """Device-side gate for the stencil recorded next (gtb_stencil_gate): wait until *wait_flag >= wait_value, add 1
         to *post_counter when done.  Pointers are raw device addresses (ints) or None."""

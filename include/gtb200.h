@@ -208,14 +208,6 @@ typedef struct {
 } gtb_halo_field;
 int gtb_halo_generic_pack_send(gtb_halo *h, const gtb_halo_field *fields, int n_fields, void *stream);
 int gtb_halo_generic_wait_unpack(gtb_halo *h, const gtb_halo_field *fields, int n_fields, void *stream);
-/* ATTACHED exchange: arms the NEXT stencil launch of this host thread (gtb_hori_diff_*, gtb_vert_adv_* on their default
- * TMA kernels) with a complete exchange of `fields` -- pack, NVLink stores, flags, wait, unpack and the epoch advance of
- * gtb_halo_exchange -- run by n_ctas extra CTAs of that launch beside the CTAs that compute.  A time step becomes ONE
- * launch: no communication stream, no events, and programmatic dependent launch keeps working between steps.  The
- * exchange is complete when the launch is; it must not touch what the stencil of the same launch reads or writes
- * (exchange the fields of the NEXT step).  This is the compute + collective fusion for loops of the shape
- * pack / exchange / unpack; run (tests/regression/gcl/copy_stencil_parallel.cpp:126-145). */
-int gtb_halo_attach(gtb_halo *h, void *const *fields, int n_fields, int n_ctas);
 /* Device-side waits for a neighbour's message give up after option "halo.timeout_ms" (default 60 000; 0 = wait for
  * ever, like the MPI_Wait of Halo_Exchange_3D).  A wait that gave up does NOT unpack that message (the halo keeps its
  * old values) and stores 1 + direction in an error word in mapped host memory; every later wait of the object fails
@@ -307,8 +299,6 @@ int gtb_seq_add_vert_adv(gtb_seq *s, int elem_size, const gtb_field *utens_stage
 int gtb_seq_add_prepare_tracers(gtb_seq *s, const gtb_field *out, const gtb_field *in, int n_tracers,
     const gtb_field *rho, int ni, int nj, int nk, void *stream);
 int gtb_seq_add_halo_exchange(gtb_seq *s, gtb_halo *h, void *const *fields, int n_fields, void *stream);
-/* gtb_halo_attach for the stencil operation recorded NEXT */
-int gtb_seq_add_halo_attach(gtb_seq *s, gtb_halo *h, void *const *fields, int n_fields, int n_ctas);
 /* gtb_stencil_gate / gtb_halo_gate for the operation recorded NEXT (armed when the sequence reaches them) */
 int gtb_seq_add_stencil_gate(gtb_seq *s, const void *wait_flag, uint64_t wait_value, void *post_counter);
 int gtb_seq_add_halo_gate(gtb_seq *s, gtb_halo *h, const void *counter, uint64_t value);

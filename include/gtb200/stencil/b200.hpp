@@ -40,6 +40,8 @@
  */
 #pragma once
 
+#include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
@@ -64,6 +66,7 @@
 #endif
 
 #include "../../gtb200.h"
+#include "b200_shapes.hpp"
 #ifdef __CUDACC__
 #include "b200_fused.hpp"
 #endif
@@ -71,7 +74,7 @@
 namespace gtb200 {
 
     /// Kernels of libgtb200.so a whole spec can be bound to.
-    enum class kernel { none, copy, hori_diff, hori_diff_fused, simple_hori_diff, vert_adv, tridiagonal };
+    enum class kernel { none, copy, hori_diff, hori_diff_fused, simple_hori_diff, vert_adv, tridiagonal, prepare_tracers };
 
     /// Primary template: a spec made of these user functors (in stage order, duplicates removed) has no named kernel.
     template <class FunctorList>
@@ -251,6 +254,9 @@ namespace gridtools {
             template <class Grid, class DataStores>
             void run_named(kernel_c<kernel::tridiagonal>, Grid const &grid, DataStores &ds, void *stream) {
                 static_assert(tuple_util::size<DataStores>::value == 5, "tridiagonal takes (inf, diag, sup, rhs, out)");
+                using T = element_of<std::decay_t<decltype(tuple_util::get<4>(ds))>>;
+                static_assert(std::is_same<T, double>::value,
+                    "gtb_tridiagonal_f64 is the only Thomas kernel (float specs take the generic path, see has_kernel)");
                 gtb_field f[5] = {as_field(tuple_util::get<0>(ds)),
                     as_field(tuple_util::get<1>(ds)),
                     as_field(tuple_util::get<2>(ds)),
@@ -260,6 +266,64 @@ namespace gridtools {
                                   &f[0], &f[1], &f[2], &f[3], &f[4], grid.i_size(), grid.j_size(), grid.k_size(), stream),
                     "gtb_tridiagonal_f64");
             }
+
+            // advection_pdbott_prepare_tracers.cpp:45-52 : one chunk of expandable_run<Factor>: (out_0..out_F-1, in_0..in_F-1, rho)
+            template <class Grid, class DataStores>
+            void run_named(kernel_c<kernel::prepare_tracers>, Grid const &grid, DataStores &ds, void *stream) {
+                constexpr size_t F = (tuple_util::size<DataStores>::value - 1) / 2;
+                gtb_field out[F], in[F], rho;
+                size_t n = 0;
+                tuple_util::for_each(
+                    [&](auto &store) {
+                        gtb_field f = as_field(store);
+                        if (n < F)
+                            out[n] = f;
+                        else if (n < 2 * F)
+                            in[n - F] = f;
+                        else
+                            rho = f;
+                        ++n;
+                    },
+                    ds);
+                gtb200::check(gtb_prepare_tracers_f64(
+                                  out, in, (int)F, &rho, grid.i_size(), grid.j_size(), grid.k_size(), stream),
+                    "gtb_prepare_tracers_f64");
+            }
+
+            // ---------------------------------------------------------------- is the binding valid for THIS spec?
+            constexpr shape::id shape_of(kernel k) {
+                return k == kernel::copy               ? shape::id::copy
+                       : k == kernel::hori_diff        ? shape::id::hori_diff
+                       : k == kernel::hori_diff_fused  ? shape::id::hori_diff_fused
+                       : k == kernel::simple_hori_diff ? shape::id::simple_hori_diff
+                       : k == kernel::vert_adv         ? shape::id::vert_adv
+                       : k == kernel::tridiagonal      ? shape::id::tridiagonal
+                       : k == kernel::prepare_tracers  ? shape::id::prepare_tracers
+                                                       : shape::id::none;
+            }
+            // element types the kernel exists for
+            template <kernel K, class T>
+            using has_kernel = std::integral_constant<bool,
+                K == kernel::copy ? (sizeof(T) == 4 || sizeof(T) == 8)
+                : (K == kernel::tridiagonal || K == kernel::prepare_tracers)
+                    ? std::is_same<T, double>::value
+                    : (std::is_same<T, double>::value || std::is_same<T, float>::value)>;
+
+            /// A spec runs on a named kernel iff its functor list is registered (GTB200_REGISTER_SPEC), the kernel exists
+            /// for its element type, AND the spec is exactly the reference spec that kernel implements (b200_shapes.hpp):
+            /// same wiring of placeholders to stage arguments, caches, intervals, extents and run() argument order.
+            template <class Spec, class Grid, class DataStores>
+            struct named_kernel_of {
+                static constexpr kernel registered = ::gtb200::named_spec<spec_functors<Spec>>::value;
+                using first_store_t = std::decay_t<decltype(tuple_util::get<0>(std::declval<DataStores &>()))>;
+                using T = element_of<first_store_t>;
+                template <kernel K>
+                static constexpr bool usable() {
+                    return has_kernel<K, T>::value &&
+                           shape::matches<shape_of(K), spec_functors<Spec>, T, Spec, Grid, DataStores>::value;
+                }
+                static constexpr kernel value = registered != kernel::none && usable<registered>() ? registered : kernel::none;
+            };
 
 #ifdef __CUDACC__
             // ---------------------------------------------------------------- generic path (stage by stage)
@@ -343,7 +407,7 @@ namespace gridtools {
             void run_generic(Spec, Grid const &grid, DataStores external, void *stream) {
                 using stages_t = be_api::make_split_view<Spec>;
                 using tmp_plh_map_t = be_api::remove_caches_from_plh_map<typename stages_t::tmp_plh_map_t>;
-                auto alloc = sid::device::cached_allocator(&cuda_util::cuda_malloc<char[]>);
+                auto alloc = fused::cuda_launcher{static_cast<cudaStream_t>(stream)}.allocator(); // per-stream free lists
                 // temporaries: whole (extent-extended) domain in device memory, origin at the first compute point
                 auto temporaries = be_api::make_data_stores(tmp_plh_map_t(), [&](auto info) {
                     auto extent = info.extent();
@@ -371,7 +435,7 @@ namespace gridtools {
             struct b200 {
                 template <class Spec, class Grid, class DataStores>
                 static void dispatch(std::true_type /*named*/, Spec, Grid const &grid, DataStores &data_stores) {
-                    run_named(kernel_c<::gtb200::named_spec<spec_functors<Spec>>::value>(), grid, data_stores,
+                    run_named(kernel_c<named_kernel_of<Spec, Grid, DataStores>::value>(), grid, data_stores,
                         StreamGetter()());
                 }
                 template <class Spec, class Grid, class DataStores>
@@ -382,8 +446,9 @@ namespace gridtools {
                     b200::generic(std::integral_constant<bool, fuse>(), spec, grid, data_stores);
 #else
                     static_assert(sizeof(Spec) == 0,
-                        "stencil::b200: this spec is not bound to a named kernel (GTB200_REGISTER_SPEC); the generic "
-                        "path instantiates the user functors in a CUDA kernel and needs this file to be compiled by nvcc");
+                        "stencil::b200: this spec is not bound to a named kernel (no GTB200_REGISTER_SPEC for its functors, "
+                        "or it does not have the shape of the reference spec the kernel implements, b200_shapes.hpp); the "
+                        "generic path instantiates the user functors in a CUDA kernel and needs nvcc");
 #endif
                 }
 
@@ -401,7 +466,16 @@ namespace gridtools {
 
                 template <class Spec, class Grid, class DataStores>
                 friend void gridtools_backend_entry_point(b200, Spec spec, Grid const &grid, DataStores data_stores) {
-                    constexpr bool named = ::gtb200::named_spec<spec_functors<Spec>>::value != ::gtb200::kernel::none;
+                    constexpr bool named = named_kernel_of<Spec, Grid, DataStores>::value != ::gtb200::kernel::none;
+                    // GTB200_TRACE_DISPATCH=1: one line per spec instantiation telling which path it takes
+                    static const bool traced = [] {
+                        if (std::getenv("GTB200_TRACE_DISPATCH"))
+                            std::fprintf(stderr, "stencil::b200: spec -> %s (kernel id %d, registered id %d)\n",
+                                named ? "named kernel" : "generic path", (int)named_kernel_of<Spec, Grid, DataStores>::value,
+                                (int)named_kernel_of<Spec, Grid, DataStores>::registered);
+                        return true;
+                    }();
+                    (void)traced;
                     b200::dispatch(std::integral_constant<bool, named>(), spec, grid, data_stores);
                 }
             };

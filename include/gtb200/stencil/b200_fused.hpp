@@ -36,7 +36,10 @@
 #pragma once
 
 #include <limits>
+#include <map>
+#include <memory>
 #include <type_traits>
+#include <vector>
 #include <utility>
 
 #include <gridtools/common/for_each.hpp>
@@ -769,7 +772,43 @@ namespace gridtools {
                     using cta_t = cuda_cta;
                     cudaStream_t m_stream;
 
-                    static auto allocator() { return sid::device::cached_allocator(&cuda_util::cuda_malloc<char[]>); }
+                    // Device memory for the temporaries, recycled like the reference's sid::device::cached_allocator
+                    // (sid/allocator.hpp:65-95: thread-local free lists by size) -- but the free lists are per STREAM:
+                    // a block is handed back as soon as run() returns, while the kernels that use it may still be in
+                    // flight.  On the same stream the next user is ordered behind them; a launch on another stream
+                    // (b200<stream_getter>) is not, so it must not get that block.
+                    struct stream_cached_malloc {
+                        cudaStream_t m_stream;
+                        struct cache_t {
+                            std::map<std::pair<cudaStream_t, size_t>, std::vector<char *>> free;
+                            ~cache_t() {
+                                for (auto &kv : free)
+                                    for (char *p : kv.second)
+                                        cudaFree(p);
+                            }
+                        };
+                        static cache_t &cache() {
+                            static thread_local cache_t c;
+                            return c;
+                        }
+                        struct deleter_f {
+                            cudaStream_t m_stream;
+                            size_t m_size;
+                            void operator()(char *p) const { cache().free[{m_stream, m_size}].push_back(p); }
+                        };
+                        std::unique_ptr<char[], deleter_f> operator()(size_t size) const {
+                            auto &list = cache().free[{m_stream, size}];
+                            char *p = nullptr;
+                            if (list.empty()) {
+                                GT_CUDA_CHECK(cudaMalloc(&p, size));
+                            } else {
+                                p = list.back();
+                                list.pop_back();
+                            }
+                            return std::unique_ptr<char[], deleter_f>(p, deleter_f{m_stream, size});
+                        }
+                    };
+                    auto allocator() const { return sid::device::allocator(stream_cached_malloc{m_stream}); }
 
                     template <class Body>
                     void launch(Body const &body, int_t nbi, int_t nbj, int_t nbk, int_t threads, int_t smem) const {

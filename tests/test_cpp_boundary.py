@@ -104,6 +104,85 @@ def test_harness_traits_of_the_tag(tmp_path):
     assert subprocess.run([str(exe)]).returncode == 0
 
 
+SHAPE_TU = r"""
+#include <gridtools/stencil/cartesian.hpp>
+#include <gridtools/stencil/global_parameter.hpp>
+#include <gridtools/storage/builder.hpp>
+#include <gridtools/storage/cpu_ifirst.hpp>
+#include <gridtools/storage/sid.hpp>
+#include <gtb200/stencil/b200.hpp>
+#include "functors.hpp"
+GTB200_REGISTER_SPEC(gtb200::kernel::copy, user::copy_f<0>);
+GTB200_REGISTER_SPEC(gtb200::kernel::hori_diff, user::lap_f<0>, user::flx_f<0>, user::fly_f<0>, user::out_f<0>);
+GTB200_REGISTER_SPEC(gtb200::kernel::simple_hori_diff, user::wlap_f<0>, user::divflux_f<0>);
+GTB200_REGISTER_SPEC(gtb200::kernel::vert_adv, user::va_forward_f<0>, user::va_backward_f<0>);
+GTB200_REGISTER_SPEC(gtb200::kernel::tridiagonal, user::td_forward_f<0>, user::td_backward_f<0>);
+namespace gt = gridtools; namespace st = gridtools::stencil; using gtb200::kernel;
+// a backend tag that only asks: which named kernel would stencil::b200 bind this spec to?
+template <kernel Expected>
+struct probe {
+    template <class Spec, class Grid, class DataStores>
+    friend void gridtools_backend_entry_point(probe, Spec, Grid const &, DataStores) {
+        static_assert(st::b200_backend::named_kernel_of<Spec, Grid, DataStores>::value == Expected, "binding");
+    }
+};
+template <class T>
+auto mk() { return gt::storage::builder<gt::storage::cpu_ifirst>.template type<T>().dimensions(20, 20, 8).halos(3, 3, 0).build(); }
+void checks() {
+    auto h = gt::halo_descriptor(3, 3, 3, 16, 20);
+    auto grid = st::make_grid(h, h, st::axis<1>(8));
+    // the reference shapes bind ...
+    st::run(user::hori_diff_spec<double, 0>(), probe<kernel::hori_diff>(), grid, mk<double>(), mk<double>(), mk<double>());
+    st::run(user::hori_diff_spec<float, 0>(), probe<kernel::hori_diff>(), grid, mk<float>(), mk<float>(), mk<float>());
+    st::run_single_stage(user::copy_f<0>(), probe<kernel::copy>(), grid, mk<double>(), mk<double>());
+    st::run(user::tridiagonal_spec<0>(), probe<kernel::tridiagonal>(), grid, mk<double>(), mk<double>(), mk<double>(), mk<double>(), mk<double>());
+    auto vgrid = st::make_grid(h, h, user::va_axis_t(8));
+    st::run(user::vert_adv_spec<double, 0>(), probe<kernel::vert_adv>(), vgrid, mk<double>(), mk<double>(), mk<double>(),
+        mk<double>(), mk<double>(), st::global_parameter(0.15));
+    // ... the Thomas solve in float does not (there is only gtb_tridiagonal_f64) ...
+    st::run(user::tridiagonal_spec<0>(), probe<kernel::none>(), grid, mk<float>(), mk<float>(), mk<float>(), mk<float>(), mk<float>());
+    // ... nor do the same functors with another wiring: in and coeff swapped in the last stage,
+    st::run([](auto in, auto coeff, auto out) {
+            GT_DECLARE_TMP(double, lap, flx, fly);
+            return st::execute_parallel().ij_cached(lap, flx, fly).stage(user::lap_f<0>(), lap, in)
+                .stage(user::flx_f<0>(), flx, in, lap).stage(user::fly_f<0>(), fly, in, lap)
+                .stage(user::out_f<0>(), out, coeff, flx, fly, in); },
+        probe<kernel::none>(), grid, mk<double>(), mk<double>(), mk<double>());
+    // another order of the run() arguments,
+    st::run([](auto out, auto in, auto coeff) {
+            GT_DECLARE_TMP(double, lap, flx, fly);
+            return st::execute_parallel().ij_cached(lap, flx, fly).stage(user::lap_f<0>(), lap, in)
+                .stage(user::flx_f<0>(), flx, in, lap).stage(user::fly_f<0>(), fly, in, lap)
+                .stage(user::out_f<0>(), out, in, flx, fly, coeff); },
+        probe<kernel::none>(), grid, mk<double>(), mk<double>(), mk<double>());
+    // temporaries that are not ij-cached,
+    st::run([](auto in, auto coeff, auto out) {
+            GT_DECLARE_TMP(double, lap, flx, fly);
+            return st::execute_parallel().stage(user::lap_f<0>(), lap, in)
+                .stage(user::flx_f<0>(), flx, in, lap).stage(user::fly_f<0>(), fly, in, lap)
+                .stage(user::out_f<0>(), out, in, flx, fly, coeff); },
+        probe<kernel::none>(), grid, mk<double>(), mk<double>(), mk<double>());
+    // or a copy functor used twice.
+    st::run([](auto a, auto b) { return st::execute_parallel().stage(user::copy_f<0>(), a, b).stage(user::copy_f<0>(), b, a); },
+        probe<kernel::none>(), grid, mk<double>(), mk<double>());
+}
+"""
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference headers only exist in the build container")
+def test_named_binding_needs_the_reference_shape(tmp_path):
+    """GTB200_REGISTER_SPEC alone does not bind: the spec must be type-identical (temporaries renumbered) to the
+    reference spec the kernel implements, built by the reference's own frontend (b200_shapes.hpp).  Same functors with
+    swapped wiring, another run() argument order, without the caches, or an element type the kernel does not exist
+    for fall through to the generic path."""
+    src = tmp_path / "shape.cpp"
+    src.write_text(SHAPE_TU)
+    cmd = ["/usr/bin/g++", "-std=c++17", "-fsyntax-only", "-I" + REF, "-I" + os.path.join(ROOT, "include"),
+           "-I" + os.path.join(ROOT, "tests", "cpp"), str(src)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
+
+
 FUSABLE_TU = r"""
 #include <cstdio>
 #include <gtb200/stencil/b200_fused.hpp>   // first: the header must be self-sufficient

@@ -383,71 +383,3 @@ def test_generic_one_message_per_neighbour_equals_reference_generic(gt, oracle, 
                 assert np.array_equal(dev[r][f].cpu().numpy(), want[r][f]), (proc_dims, per, r, f)
         for hg in hgs:
             hg.close()
-
-
-@pytest.mark.parametrize("stencil_name", ["hori_diff", "vert_adv"])
-def test_attached_exchange_rides_in_the_stencil_launch(gt, oracle, stencil_name):
-    """gtb_halo_attach: the next stencil launch carries a complete exchange in extra CTAs of its own grid.  A periodic
-    rank that is its own neighbour in i and j: every step is ONE launch that computes on field set A while its
-    communication CTAs refresh the halos of field set B; results = exchange oracle, then stencil oracle."""
-    import ctypes as C
-    from gridtools_b200 import stencil
-    from oracle import pyoracle as o
-    torch = gt.torch
-    H = 2 if stencil_name == "hori_diff" else 3
-    ni, nj, nk = 96, 40, 12
-    per = (True, True, False)
-    grid = gt.gcl.ProcGrid((1, 1, 1), per, 0)
-    rng = np.random.default_rng(31)
-    shape = (nk, nj + 2 * H, ni + 2 * H)
-    n_in = 2 if stencil_name == "hori_diff" else 5
-    exch = 0 if stencil_name == "hori_diff" else 2
-    boxes = [[rng.uniform(1, 2, shape) * (1e-4 if (stencil_name == "vert_adv" and f in (2, 4)) else 1.0)
-              for f in range(n_in)] for _ in range(2)]
-    sets = [[gt.storage.from_numpy(b, (H, H, 0)) for b in bs] for bs in boxes]
-    outs = [gt.storage.from_numpy(np.zeros(shape), (H, H, 0)) for _ in range(2)]
-    he = gt.gcl.halo_exchange_dynamic_ut(per, grid, np.float64, comm=None, transport="p2p")
-    p0 = sets[0][0].padded_lengths[0]
-    he.add_halo(0, H, H, H, H + ni - 1, p0)
-    he.add_halo(1, H, H, H, H + nj - 1, nj + 2 * H)
-    he.add_halo(2, 0, 0, 0, nk - 1, nk)
-    he.setup(1)
-    he._connect([he.blob])
-    for st in sets:
-        for f in st:
-            f.const_target_tensor()
-    launches0 = gt.lib.launch_count()
-
-    def run(s):
-        if stencil_name == "hori_diff":
-            stencil.horizontal_diffusion(sets[s][0], sets[s][1], outs[s])
-        else:
-            stencil.vertical_advection_dycore(*sets[s], 0.15)
-
-    def attach(s):
-        arr = (C.c_void_p * 1)(sets[s][exch].raw_ptr())
-        gt.lib.check(gt.lib.lib().gtb_halo_attach(he._h, arr, 1, 2))
-
-    he.pack([sets[0][exch].raw_ptr()]); he.exchange(); he.unpack([sets[0][exch].raw_ptr()])  # halos of set 0
-    attach(1)   # launch 0: stencil on set 0, exchange of set 1
-    run(0)
-    run(1)      # launch 1: stencil on set 1 (its halos came with launch 0), nothing attached
-    torch.cuda.synchronize()
-    assert he.check() == 0
-    assert gt.lib.launch_count() - launches0 == 4  # pack, unpack, two stencil launches: the attached exchange is no launch
-    hal = [(H, H, H, H + ni - 1, ni + 2 * H), (H, H, H, H + nj - 1, nj + 2 * H), (0, 0, 0, nk - 1, nk)]
-    inner = (slice(None), slice(H, -H), slice(H, -H))
-    for s in range(2):
-        want_in = [b.copy() for b in boxes[s]]
-        o.halo_exchange_all(hal, (1, 1, 1), per, [[want_in[exch]]], 8)
-        sets[s][exch]._host_stale = True
-        assert np.array_equal(sets[s][exch].to_numpy(), want_in[exch]), "halos of set %d" % s
-        if stencil_name == "hori_diff":
-            want = o.hori_diff(want_in[0], want_in[1])
-            outs[s]._host_stale = True
-            assert np.array_equal(outs[s].to_numpy()[inner], want[inner]), s
-        else:
-            want = o.vert_adv(*want_in, 0.15)
-            sets[s][0]._host_stale = True
-            assert np.array_equal(sets[s][0].to_numpy()[inner], want[inner]), s
-    he.close()

@@ -58,3 +58,23 @@ def test_reference_perftests_mode_on_the_b200_backend():
     rc, out, tail = run("regression_b200", 256, 256, 80, 3)
     assert rc == 0 and "[  FAILED  ]" not in out, tail
     assert '"outputs"' in out and "horizontal_diffusion" in out and "vertical_advection_dycore" in out, tail
+
+
+@pytest.mark.gpu
+def test_reference_regression_sources_bind_to_the_named_kernels():
+    """regression_b200_named = the same unchanged sources with tests/cpp/register_reference_specs.hpp force-included
+    (the GTB200_REGISTER_SPEC lines): every registered spec passes the shape check of b200_shapes.hpp and runs on its
+    hand-written kernel, results verified by the reference's verifier."""
+    exe = os.path.join(BUILD, "regression_b200_named")
+    if not os.path.exists(exe):
+        pytest.skip("tests/_build/regression_b200_named not built")
+    env = dict(os.environ, GTB200_TRACE_DISPATCH="1")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900, env=env)
+    tail = r.stdout[-5000:] + r.stderr[-3000:]
+    assert r.returncode == 0 and "[  FAILED  ]" not in r.stdout, tail
+    named = [l for l in r.stderr.splitlines() if "-> named kernel" in l]
+    generic = [l for l in r.stderr.splitlines() if "-> generic path" in l]
+    # copy, hori_diff, hori_diff_fused, simple_hori_diff, vert_adv (float + double each), tridiagonal (double),
+    # prepare_tracers chunks of 2 and 1 (double; float has no kernel: generic)
+    kinds = {l.split("kernel id ")[1].split(",")[0] for l in named}
+    assert kinds >= {"1", "2", "3", "4", "5", "6", "7"}, (sorted(kinds), generic, tail)

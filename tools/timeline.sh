@@ -18,6 +18,7 @@ for l in sys.stdin:
         print(l.rstrip())" >> $OUT
 }
 for st in vert_adv hori_diff; do
-  run "periodic attached" $st GTB_PERIODIC=1
+  run "periodic dma r4" $st GTB_PERIODIC=1
+  run "periodic nodma r4" $st GTB_PERIODIC=1 GTB_HALO_DMA=0
 done
 cat $OUT
