@@ -39,8 +39,10 @@ ALGO_BYTES = {"vert_adv": 48, "hori_diff": 24}  # per interior point, fp64 (SURV
 P100_MPTS = {"vert_adv": 5117.0, "hori_diff": 10300.0}  # reference stencil::gpu on P100
 HALO = {"vert_adv": 3, "hori_diff": 2}
 HALO_FUSED = 0   # N > 1: gtb_halo_exchange as one launch (pack, signal, wait, unpack)
-RESERVE_SMS = 4  # N > 1: SMs the persistent stencil grids leave free for the concurrent halo exchange kernels
-HALO_DMA = 1     # N > 1: the NVLink leg of the exchange on the copy engines (option halo.dma)
+RESERVE_SMS = {"vert_adv": 6, "hori_diff": 8}  # N > 1: SMs the persistent stencil grids leave to the concurrent exchange kernels
+# (profiles/r02_exchange_variants.txt: an SM pushes only ~10 GB/s over NVLink, the exchange must end inside a step)
+HALO_DMA = 0     # N > 1: 1 = the NVLink leg of the exchange on the copy engines (option halo.dma; measured slower:
+                 # eight in-stream peer copies cost ~6.5 us each, profiles/r02_exchange_timeline.txt)
 
 
 def parse():
@@ -417,7 +419,7 @@ def b200_arm(args):
         _lib.check(_lib.lib().gtb_halo_set_trace(he._h, C.c_void_p(halo_trace.data_ptr())))
         epoch0 = he.epoch()
     if he is not None:
-        reserve_sms = int(os.environ.get("GTB_RESERVE_SMS", RESERVE_SMS))
+        reserve_sms = int(os.environ.get("GTB_RESERVE_SMS", RESERVE_SMS[name]))
         halo_dma = int(os.environ.get("GTB_HALO_DMA", HALO_DMA))
         _lib.set_option("reserve_sms", reserve_sms)  # left to the exchange
         _lib.set_option("halo.dma", halo_dma)

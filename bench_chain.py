@@ -87,7 +87,7 @@ def main():
     comp_h = C.c_void_p(comp.cuda_stream)
     comm_h = comp_h if args.no_overlap else C.c_void_p(comm.cuda_stream)
     if world > 1 and not args.no_overlap:
-        _lib.set_option("reserve_sms", bench.RESERVE_SMS)
+        _lib.set_option("reserve_sms", bench.RESERVE_SMS["vert_adv"])
     seq = stencil.Sequence()
     total = args.warmup + args.steps
     ops = []
@@ -151,7 +151,7 @@ def main():
             "config": {"workload": "chain %dx%dx%d per GPU, %dx%d process grid" % (ni, nj, nk, dims[0], dims[1]),
                        "overlap": "none (exchanges on the compute stream)" if args.no_overlap or world == 1 else
                        "exchange(in) beside vert_adv, exchange(wcon) beside prepare_tracers, %d SMs reserved" %
-                       bench.RESERVE_SMS},
+                       bench.RESERVE_SMS["vert_adv"]},
             "roofline": {"bound": "hbm", "achieved": algo / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": algo / (ms_step * 1e-3) / 1e9 / peak, "peak_source": src,
                          "algorithmic_bytes_per_step": algo},

@@ -108,6 +108,12 @@ _SIG = {
     "gtb_seq_add_record": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "gtb_seq_add_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "gtb_seq_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "gtb_tensor_map_3d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                          C.POINTER(C.c_int)]),
+    "gtb_device_malloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
+    "gtb_device_free": (C.c_int, [C.c_void_p]),
+    "gtb_staged_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "gtb_staged_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "gtb_stream_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     "gtb_stream_destroy": (C.c_int, [C.c_void_p]),
     "gtb_stream_after_default": (C.c_int, [C.c_void_p]),

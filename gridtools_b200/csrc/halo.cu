@@ -105,6 +105,10 @@ namespace {
         const int total = t.chunk_start[t.n_seg];
         unsigned waited = 0, failed = 0; // segments whose flag this block has acquired / given up on (block-uniform)
         __shared__ int s_ok;
+        if (WAIT && blockIdx.x == 0 && threadIdx.x == 0) // segments without elements: flags only (see fill_table)
+            for (int f = 0; f < t.n_seg; ++f)
+                if (t.flag[f] && t.chunk_start[f + 1] == t.chunk_start[f])
+                    wait_flag(t.flag[f], sy.epoch, sy.error, sy.timeout_cycles, t.dir[f]);
         int s = 0;
         for (int ch = blockIdx.x; ch < total; ch += gridDim.x) {
             while (ch >= t.chunk_start[s + 1])
@@ -261,12 +265,19 @@ namespace {
         t.n_seg = 0;
         t.chunk_start[0] = 0;
         for (int n = 0; n < 27; ++n) {
-            if (n == 13 || !bufs[n] || regs[n].count == 0)
+            if (n == 13)
+                continue;
+            // A direction that carries payload only the OTHER way (asymmetric halos: minus = 1, plus = 0) still
+            // exchanges flags both ways -- a segment without elements: seeing a neighbour's epoch e + 1 is what proves
+            // that it has unpacked epoch e and its double-buffered slot may be overwritten (MPI needs no such thing).
+            const bool flag_only = sync_mode != 0 && h->nbr[n] >= 0 && regs[n].count == 0 &&
+                                   (pack ? h->recv[n].count : h->send[n].count) != 0;
+            if (!flag_only && (!bufs[n] || regs[n].count == 0))
                 continue;
             const int sg = t.n_seg++;
             t.dir[sg] = n;
             t.r[sg] = regs[n];
-            t.buf[sg] = bufs[n] + field_offset * regs[n].count * h->es;
+            t.buf[sg] = flag_only ? nullptr : bufs[n] + field_offset * regs[n].count * h->es;
             t.flag[sg] = nullptr;
             if (h->nbr[n] >= 0) {
                 if (sync_mode == 1) // the neighbour sees this rank in direction 26 - n
@@ -418,7 +429,7 @@ namespace {
         bool any = false;
         for (int n = 0; n < 27; ++n) {
             s.flag[n] = nullptr;
-            if (n != 13 && h->nbr[n] >= 0 && h->peer_arena[n]) {
+            if (n != 13 && h->nbr[n] >= 0 && h->peer_arena[n] && (h->send[n].count || h->recv[n].count)) {
                 // the neighbour sees this rank in direction 26 - n
                 s.flag[n] = reinterpret_cast<uint64_t *>(h->peer_arena[n]) + (h->epoch & 1) * 32 + (26 - n);
                 any = true;
@@ -723,7 +734,7 @@ GTB_API int gtb_halo_wait(gtb_halo *h, void *stream) {
     bool any = false;
     for (int n = 0; n < 27; ++n) {
         w.flag[n] = nullptr;
-        if (h->recv[n].count) {
+        if (n != 13 && h->nbr[n] >= 0 && (h->recv[n].count || h->send[n].count)) { // flags travel both ways
             w.flag[n] = reinterpret_cast<const uint64_t *>(h->arena) + (h->epoch & 1) * 32 + n;
             any = true;
         }
@@ -845,6 +856,14 @@ namespace {
         if (a.sync.trace && threadIdx.x == 0 && blockIdx.x == 0)
             a.sync.trace[PACK ? 0 : 2] = ptx::globaltimer();
         unsigned waited = 0, failed = 0; // directions whose flag this block has acquired / given up on
+        if (!PACK && blockIdx.x == 0 && threadIdx.x == 0) { // directions without a segment of their own: flags only
+            unsigned with_seg = 0;
+            for (int f = 0; f < a.n_seg; ++f)
+                with_seg |= 1u << a.segs[f].dir;
+            for (int n = 0; n < 27; ++n)
+                if (a.flag[n] && !((with_seg >> n) & 1u))
+                    wait_flag(a.flag[n], a.sync.epoch, a.sync.error, a.sync.timeout_cycles, n);
+        }
         int s = 0;
         for (int ch = blockIdx.x; ch < a.n_chunks; ch += gridDim.x) {
             while (s + 1 < a.n_seg && ch >= a.segs[s + 1].chunk_start)
@@ -984,9 +1003,10 @@ namespace {
             a.flag[n] = nullptr;
             if (n == 13 || h->nbr[n] < 0)
                 continue;
-            if (PACK && h->send[n].count && h->peer_arena[n])
+            const bool active = h->send[n].count || h->recv[n].count; // flags travel both ways (see fill_table)
+            if (PACK && active && h->peer_arena[n])
                 a.flag[n] = reinterpret_cast<uint64_t *>(h->peer_arena[n]) + (h->epoch & 1) * 32 + (26 - n);
-            else if (!PACK && h->recv[n].count)
+            else if (!PACK && active)
                 a.flag[n] = reinterpret_cast<uint64_t *>(h->arena) + (h->epoch & 1) * 32 + n;
             any_flag = any_flag || a.flag[n];
         }

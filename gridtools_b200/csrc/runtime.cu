@@ -1,6 +1,10 @@
 // runtime.cu -- error state, options, device state, cached scratch and the TMA descriptor encoder of libgtb200.
 #include "common.cuh"
 
+#include <thread>
+
+#include <cstring>
+
 #include <map>
 
 #include <mutex>
@@ -285,6 +289,175 @@ GTB_API int gtb_stream_after_default(void *stream) {
 GTB_API int gtb_stream_synchronize(void *stream) {
     GTB_CUDA(cudaStreamSynchronize(as_stream(stream)));
     return GTB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ tensor maps
+// For kernels that are compiled in the USER's translation unit (the generic fused path of stencil::b200 instantiates
+// the user's functors there): a TMA descriptor of a 3-d box over an i-contiguous field, encoded here so that the
+// header needs neither libcuda nor the driver entry point query.  GTB_ERR_LAYOUT when the field is not
+// TMA-addressable (base or strides not multiples of 16 bytes, box row not a multiple of 16 bytes, box too large).
+GTB_API int gtb_tensor_map_3d(void *map128, const void *base, int elem_size, const int64_t dims[3],
+    const int64_t strides_bytes[2], const int box[3]) {
+    if (!map128 || !base || !dims || !strides_bytes || !box)
+        return fail(GTB_ERR_ARG, "gtb_tensor_map_3d: null argument");
+    if (!dev())
+        return GTB_ERR_CUDA;
+    auto enc = tensor_map_encoder();
+    if (!enc)
+        return fail(GTB_ERR_CUDA, "gtb_tensor_map_3d: cuTensorMapEncodeTiled not available");
+    CUtensorMapDataType dt;
+    if (elem_size == 8)
+        dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+    else if (elem_size == 4)
+        dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    else
+        return fail(GTB_ERR_LAYOUT, "gtb_tensor_map_3d: element size %d", elem_size);
+    if (reinterpret_cast<uintptr_t>(base) % 16 || strides_bytes[0] % 16 || strides_bytes[1] % 16 ||
+        strides_bytes[0] <= 0 || strides_bytes[1] <= 0 || (box[0] * (int64_t)elem_size) % 16 || box[0] > 256 ||
+        box[1] > 256 || box[2] > 256 || box[0] < 1 || box[1] < 1 || box[2] < 1 || dims[0] < 1 || dims[1] < 1 ||
+        dims[2] < 1)
+        return fail(GTB_ERR_LAYOUT, "gtb_tensor_map_3d: field is not TMA-addressable");
+    cuuint64_t d[3] = {(cuuint64_t)dims[0], (cuuint64_t)dims[1], (cuuint64_t)dims[2]};
+    cuuint64_t st[2] = {(cuuint64_t)strides_bytes[0], (cuuint64_t)strides_bytes[1]};
+    cuuint32_t bx[3] = {(cuuint32_t)box[0], (cuuint32_t)box[1], (cuuint32_t)box[2]};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(static_cast<CUtensorMap *>(map128), dt, 3, const_cast<void *>(base), d, st, bx, estr,
+        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(GTB_ERR_LAYOUT, "gtb_tensor_map_3d: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return GTB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ staged copies
+// Whole-allocation transfers between PAGEABLE host memory and the device, for storage traits (include/gtb200/storage/
+// b200.hpp): the host mirror of a GridTools data_store is a plain new[] array that the traits never see allocated or
+// freed (storage/data_store.hpp:101-104), so it cannot be pinned in place.  A plain cudaMemcpy from pageable memory
+// (storage/gpu.hpp:86-99) lets the driver stage through its own small pinned buffers at the speed of ONE host thread;
+// here the chunks are staged by several host threads into a ring of pinned buffers and sent by asynchronous copies that
+// overlap the staging of the next chunk.  Stream-ordered on `stream` (nullptr = legacy default stream, like the reference).
+namespace {
+    constexpr size_t kStageChunk = 8u << 20;
+    constexpr int kStageSlots = 3, kStageThreads = 4;
+    struct stage_ring {
+        char *slot[kStageSlots] = {};
+        cudaEvent_t done[kStageSlots] = {};
+        int device = -1;
+        ~stage_ring() {
+            for (int i = 0; i < kStageSlots; ++i)
+                if (slot[i]) {
+                    cudaFreeHost(slot[i]);
+                    cudaEventDestroy(done[i]);
+                }
+        }
+    };
+    stage_ring *ring() {
+        static thread_local stage_ring r;
+        device_state *d = dev();
+        if (!d)
+            return nullptr;
+        if (!r.slot[0]) {
+            for (int i = 0; i < kStageSlots; ++i) {
+                if (cudaHostAlloc(&r.slot[i], kStageChunk, cudaHostAllocDefault) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&r.done[i], cudaEventDisableTiming) != cudaSuccess) {
+                    cuda_fail(cudaGetLastError(), "staged copy: pinned ring");
+                    return nullptr;
+                }
+            }
+            r.device = d->device;
+        }
+        return &r;
+    }
+    void parallel_copy(char *dst, const char *src, size_t n) {
+        if (n < (1u << 20)) {
+            std::memcpy(dst, src, n);
+            return;
+        }
+        std::thread th[kStageThreads - 1];
+        const size_t part = (n / kStageThreads + 63) & ~size_t(63);
+        for (int t = 0; t < kStageThreads - 1; ++t) {
+            const size_t off = (size_t)(t + 1) * part;
+            if (off < n)
+                th[t] = std::thread([=] { std::memcpy(dst + off, src + off, off + part < n ? part : n - off); });
+        }
+        std::memcpy(dst, src, part < n ? part : n);
+        for (auto &t : th)
+            if (t.joinable())
+                t.join();
+    }
+} // namespace
+
+GTB_API int gtb_device_malloc(void **out, int64_t bytes) {
+    if (!out || bytes < 0)
+        return fail(GTB_ERR_ARG, "gtb_device_malloc: bad argument");
+    if (!dev())
+        return GTB_ERR_CUDA;
+    *out = nullptr;
+    if (bytes == 0)
+        return GTB_OK;
+    cudaError_t e = cudaMalloc(out, (size_t)bytes);
+    if (e != cudaSuccess) {
+        cuda_fail(e, "gtb_device_malloc");
+        return GTB_ERR_ALLOC;
+    }
+    return GTB_OK;
+}
+
+GTB_API int gtb_device_free(void *p) {
+    if (p)
+        cudaFree(p);
+    return GTB_OK;
+}
+
+GTB_API int gtb_staged_upload(void *device_dst, const void *host_src, int64_t bytes, void *stream) {
+    if (bytes < 0 || (bytes && (!device_dst || !host_src)))
+        return fail(GTB_ERR_ARG, "gtb_staged_upload: bad argument");
+    stage_ring *r = ring();
+    if (!r)
+        return GTB_ERR_CUDA;
+    cudaStream_t s = stream ? as_stream(stream) : cudaStreamLegacy;
+    int i = 0;
+    for (int64_t off = 0; off < bytes; off += (int64_t)kStageChunk, i = (i + 1) % kStageSlots) {
+        const size_t n = (size_t)(bytes - off < (int64_t)kStageChunk ? bytes - off : (int64_t)kStageChunk);
+        GTB_CUDA(cudaEventSynchronize(r->done[i])); // the copy that last used this slot has drained it
+        parallel_copy(r->slot[i], static_cast<const char *>(host_src) + off, n);
+        GTB_CUDA(cudaMemcpyAsync(static_cast<char *>(device_dst) + off, r->slot[i], n, cudaMemcpyHostToDevice, s));
+        GTB_CUDA(cudaEventRecord(r->done[i], s));
+    }
+    return GTB_OK; // host_src may be modified again; the device copy is complete in stream order
+}
+
+GTB_API int gtb_staged_download(void *host_dst, const void *device_src, int64_t bytes, void *stream) {
+    if (bytes < 0 || (bytes && (!host_dst || !device_src)))
+        return fail(GTB_ERR_ARG, "gtb_staged_download: bad argument");
+    stage_ring *r = ring();
+    if (!r)
+        return GTB_ERR_CUDA;
+    cudaStream_t s = stream ? as_stream(stream) : cudaStreamLegacy;
+    const int64_t n_chunks = (bytes + (int64_t)kStageChunk - 1) / (int64_t)kStageChunk;
+    auto size_of = [&](int64_t c) {
+        const int64_t off = c * (int64_t)kStageChunk;
+        return (size_t)(bytes - off < (int64_t)kStageChunk ? bytes - off : (int64_t)kStageChunk);
+    };
+    auto issue = [&](int64_t c) -> int {
+        const int i = (int)(c % kStageSlots);
+        GTB_CUDA(cudaMemcpyAsync(r->slot[i], static_cast<const char *>(device_src) + c * (int64_t)kStageChunk, size_of(c),
+            cudaMemcpyDeviceToHost, s));
+        GTB_CUDA(cudaEventRecord(r->done[i], s));
+        return GTB_OK;
+    };
+    for (int64_t c = 0; c < n_chunks && c < kStageSlots - 1; ++c) // prime the ring
+        if (int st = issue(c))
+            return st;
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        if (c + kStageSlots - 1 < n_chunks)
+            if (int st = issue(c + kStageSlots - 1))
+                return st;
+        const int i = (int)(c % kStageSlots);
+        GTB_CUDA(cudaEventSynchronize(r->done[i]));
+        parallel_copy(static_cast<char *>(host_dst) + c * (int64_t)kStageChunk, r->slot[i], size_of(c));
+    }
+    return GTB_OK; // host_dst is complete
 }
 
 // ------------------------------------------------------------------------------------------------ stencil gates

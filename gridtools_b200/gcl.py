@@ -293,6 +293,11 @@ class halo_exchange_dynamic_ut:
             return
         arr, n = self._ptrs(fields)
         self._nf = n
+        lost = C.c_int()  # a device-side wait of an earlier exchange that gave up (halo.timeout_ms): host memory read
+        _lib.check(_lib.lib().gtb_halo_poll_error(self._h, C.byref(lost)))
+        if lost.value:
+            raise RuntimeError("halo exchange: the message from direction %d never arrived; the halos of that "
+                               "exchange are stale" % (lost.value - 1))
         fn = _lib.lib().gtb_halo_pack_send if self.transport == "p2p" else _lib.lib().gtb_halo_pack
         _lib.check(fn(self._h, arr, n, self._stream()))
 

@@ -267,6 +267,26 @@ int gtb_stencil_gate(const void *wait_flag, uint64_t wait_value, void *post_coun
 int gtb_halo_gate(gtb_halo *h, const void *counter, uint64_t value);
 int gtb_gate_timeouts(int64_t *count);
 
+/* ------------------------------------------------------------------------------------------ tensor maps
+ * A TMA descriptor (CUtensorMap, 128 bytes, 64-byte aligned) of a 3-d box over an i-contiguous field, for kernels that
+ * are compiled in the user's translation unit (the generic fused path of include/gtb200/stencil/b200_fused.hpp stages
+ * read-only fields through shared memory with it).  dims: extents of the tensor from `base`; strides_bytes: j and k;
+ * box: elements per dimension.  GTB_ERR_LAYOUT when the field is not TMA-addressable. */
+int gtb_tensor_map_3d(void *map128, const void *base, int elem_size, const int64_t dims[3],
+    const int64_t strides_bytes[2], const int box[3]);
+
+/* ------------------------------------------------------------------------------------------ staged copies
+ * Whole-allocation transfers between PAGEABLE host memory and the device for storage traits (the host mirror of a
+ * GridTools data_store is a new[] array the traits cannot pin, storage/data_store.hpp:101-104): chunks are staged by
+ * several host threads through a ring of pinned buffers and overlap with the asynchronous copies, instead of the single
+ * blocking cudaMemcpy of storage/gpu.hpp:86-99.  Stream-ordered on `stream` (NULL = legacy default stream).  Upload:
+ * returns when host_src may be reused; download: returns when host_dst is complete. */
+/* device memory for host bindings that do not include the CUDA runtime (storage traits) */
+int gtb_device_malloc(void **out, int64_t bytes);
+int gtb_device_free(void *p);
+int gtb_staged_upload(void *device_dst, const void *host_src, int64_t bytes, void *stream);
+int gtb_staged_download(void *host_dst, const void *device_src, int64_t bytes, void *stream);
+
 /* ------------------------------------------------------------------------------------------------- streams
  * For host bindings that do not include the CUDA runtime themselves.  gtb_stream_create returns a NON-BLOCKING
  * cudaStream_t (optionally of the highest priority, for exchanges that run beside a stencil); gtb_stream_after_default

@@ -59,6 +59,16 @@ namespace gridtools {
                     throw std::runtime_error(std::string(what) + ": " + gtb_last_error());
             }
 
+            /// A device-side wait that gave up (option halo.timeout_ms) left its halo untouched and set the object's
+            /// error word; the reference would hang in MPI_Wait.  Cheap (a host memory read): called in every pack / unpack.
+            inline void throw_if_lost(gtb_halo *h) {
+                int code = 0;
+                check(gtb_halo_poll_error(h, &code), "gtb_halo_poll_error");
+                if (code)
+                    throw std::runtime_error("gcl::b200: the message from direction " + std::to_string(code - 1) +
+                                             " never arrived (halo.timeout_ms); the halos of that exchange are stale");
+            }
+
             /// default: a private non-blocking stream, ordered after the legacy default stream at pack(), host-synchronised
             /// at the end of unpack() (the reference's blocking semantics); a user stream: nothing of that
             class stream_policy {
@@ -85,9 +95,11 @@ namespace gridtools {
                         check(gtb_stream_after_default(s), "gtb_stream_after_default");
                     return s;
                 }
-                void after_unpack() {
+                /// true if the host waited for the unpack (default mode): its outcome is known now
+                bool after_unpack() {
                     if (!m_user)
                         check(gtb_stream_synchronize(m_own), "gtb_stream_synchronize");
+                    return !m_user;
                 }
             };
 
@@ -153,6 +165,7 @@ namespace gridtools {
             void do_pack(void *const *fields, int n) {
                 if (!m_h)
                     throw std::logic_error("gcl::b200: pack() before setup()");
+                b200_impl_::throw_if_lost(m_h);
                 b200_impl_::check(gtb_halo_pack_send(m_h, fields, n, m_stream.before_pack()), "gtb_halo_pack_send");
             }
             void do_unpack(void *const *fields, int n) {
@@ -160,7 +173,8 @@ namespace gridtools {
                     throw std::logic_error("gcl::b200: unpack() before setup()");
                 b200_impl_::check(gtb_halo_wait_unpack(m_h, fields, n, m_stream.get()), "gtb_halo_wait_unpack");
                 b200_impl_::check(gtb_halo_next_epoch(m_h), "gtb_halo_next_epoch");
-                m_stream.after_unpack();
+                if (m_stream.after_unpack())
+                    b200_impl_::throw_if_lost(m_h);
             }
 
           public:
@@ -255,6 +269,7 @@ namespace gridtools {
             void do_pack(std::vector<gtb_halo_field> const &fs) const {
                 if (!m_h)
                     throw std::logic_error("gcl::b200: pack() before setup()");
+                b200_impl_::throw_if_lost(m_h);
                 b200_impl_::check(gtb_halo_generic_pack_send(m_h, fs.data(), (int)fs.size(), m_stream.before_pack()),
                     "gtb_halo_generic_pack_send");
             }
@@ -264,7 +279,8 @@ namespace gridtools {
                 b200_impl_::check(gtb_halo_generic_wait_unpack(m_h, fs.data(), (int)fs.size(), m_stream.get()),
                     "gtb_halo_generic_wait_unpack");
                 b200_impl_::check(gtb_halo_next_epoch(m_h), "gtb_halo_next_epoch");
-                m_stream.after_unpack();
+                if (m_stream.after_unpack())
+                    b200_impl_::throw_if_lost(m_h);
             }
 
           public:

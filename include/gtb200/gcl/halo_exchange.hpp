@@ -229,6 +229,11 @@ namespace gtb200 {
 
             /// pack(fields) (:250,:269): gather + NVLink push + signal, one launch.
             void pack(std::vector<T *> const &fields) {
+                int lost = 0; // a wait of an earlier exchange that gave up (halo.timeout_ms): a host memory read
+                check(gtb_halo_poll_error(m_h, &lost), "gtb_halo_poll_error");
+                if (lost)
+                    throw std::runtime_error("gtb200::gcl: the message from direction " + std::to_string(lost - 1) +
+                                             " never arrived; the halos of that exchange are stale");
                 check(gtb_halo_pack_send(m_h, ptrs(fields), (int)fields.size(), m_stream), "gtb_halo_pack_send");
             }
             template <class... Fields>

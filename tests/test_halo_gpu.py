@@ -383,3 +383,51 @@ def test_generic_one_message_per_neighbour_equals_reference_generic(gt, oracle, 
                 assert np.array_equal(dev[r][f].cpu().numpy(), want[r][f]), (proc_dims, per, r, f)
         for hg in hgs:
             hg.close()
+
+
+@pytest.mark.parametrize("dma", [0, 1])
+def test_asymmetric_halos_many_epochs(gt, oracle, dma):
+    """minus = 1, plus = 0 in i on a non-periodic 3 x 1 x 1 grid: every rank sends towards +i but receives nothing from
+    there.  The double-buffered receive slots rely on flags travelling BOTH ways (a segment without payload), five
+    epochs with new data each; also through the copy-engine transport (halo.dma)."""
+    import ctypes as C
+    halos = [(1, 0, 1, 24, 32), (0, 0, 0, 9, 10), (0, 0, 0, 3, 4)]
+    dims, periodic, n = (3, 1, 1), (0, 0, 0), 3
+    gt.lib.set_option("halo.dma", dma)
+    try:
+        hes, host, dev = [], [], []
+        rng = np.random.default_rng(41)
+        for r in range(n):
+            grid = gt.gcl.ProcGrid(dims, periodic, r)
+            he = gt.gcl.halo_exchange_dynamic_ut(periodic, grid, np.float64, comm=None, transport="p2p")
+            for d in range(3):
+                he.add_halo(d, *halos[d])
+            he.setup(2)
+            hes.append(he)
+            host.append([rng.standard_normal(he.plan.storage_shape()) for _ in range(2)])
+            dev.append([gt.torch.from_numpy(a.copy()).cuda() for a in host[-1]])
+        gt.gcl.connect_local(hes)
+        stream = C.c_void_p(gt.torch.cuda.current_stream().cuda_stream)
+        L = gt.lib.lib()
+        for epoch in range(5):
+            for r in range(n):  # new interior data every epoch
+                for f in range(2):
+                    host[r][f] += epoch + 1
+                    dev[r][f] += epoch + 1
+            for he, d in zip(hes, dev):
+                arr = (C.c_void_p * 2)(*[t.data_ptr() for t in d])
+                gt.lib.check(L.gtb_halo_pack(he._h, arr, 2, stream) if dma else L.gtb_halo_pack_send(he._h, arr, 2, stream))
+                if dma:
+                    gt.lib.check(L.gtb_halo_send(he._h, 2, stream))
+            for he, d in zip(hes, dev):
+                he.unpack([t.data_ptr() for t in d])
+            oracle.halo_exchange_all(halos, dims, periodic, host, 8)
+        gt.torch.cuda.synchronize()
+        for r in range(n):
+            assert hes[r].check() == 0
+            for f in range(2):
+                assert np.array_equal(dev[r][f].cpu().numpy(), host[r][f]), (r, f)
+        for he in hes:
+            he.close()
+    finally:
+        gt.lib.set_option("halo.dma", 0)

@@ -26,15 +26,14 @@ PY
 for st in vert_adv hori_diff; do
   timeout 300 python bench.py --gpus 1 --steps $STEPS --warmup 10 --stencil $st --no-extras 2>> gpurun_out/variants.err | tail -1 | \
     python3 -c "import json,sys; d=json.loads(sys.stdin.read()); print('%-34s %-9s %7.2f us/step' % ('N=1', '$st', d['ms_per_step']*1e3))" | tee -a $OUT
-  run "plain dma r4"                    $st GTB_X=0
-  run "periodic dma r4"                 $st GTB_PERIODIC=1
-  run "periodic dma r2"                 $st GTB_PERIODIC=1 GTB_RESERVE_SMS=2
-  run "periodic dma r8"                 $st GTB_PERIODIC=1 GTB_RESERVE_SMS=8
-  run "periodic nodma r4"               $st GTB_PERIODIC=1 GTB_HALO_DMA=0
-  run "periodic nodma r8"               $st GTB_PERIODIC=1 GTB_HALO_DMA=0 GTB_RESERVE_SMS=8
+  run "plain r6"                        $st GTB_RESERVE_SMS=6
+  run "periodic r6"                     $st GTB_PERIODIC=1 GTB_RESERVE_SMS=6
+  run "periodic r8"                     $st GTB_PERIODIC=1 GTB_RESERVE_SMS=8
+  run "periodic r12"                    $st GTB_PERIODIC=1 GTB_RESERVE_SMS=12
   if [ $st = vert_adv ]; then
-    run "periodic dma r4 gates pdl2"    $st GTB_PERIODIC=1 GTB_GATES=1 GTB_PDL=2
-    run "periodic dma r2 gates pdl2"    $st GTB_PERIODIC=1 GTB_GATES=1 GTB_PDL=2 GTB_RESERVE_SMS=2
+    run "periodic r6 gates pdl2"        $st GTB_PERIODIC=1 GTB_GATES=1 GTB_PDL=2 GTB_RESERVE_SMS=6
+    run "periodic r8 gates pdl2"        $st GTB_PERIODIC=1 GTB_GATES=1 GTB_PDL=2 GTB_RESERVE_SMS=8
+    run "plain r6 gates pdl2"           $st GTB_GATES=1 GTB_PDL=2 GTB_RESERVE_SMS=6
   fi
 done
 cat $OUT
