@@ -481,7 +481,16 @@ def b200_arm(args):
         torch.cuda.synchronize()
         per_step = [ev[s].elapsed_time(ev[s + 1]) for s in range(len(ev) - 1)]
     else:  # one native call issues the K timed steps; the compute stream's events bracket them
-        seq.run(step_ops[n_warm][0], sum(c for _, c in step_ops[n_warm:]))  # LEAD lead-in steps, mark, K steps, mark
+        # LEAD lead-in steps; a rendezvous of ALL ranks on the device (the exchanges couple only neighbours, and with
+        # n_sets rotating field sets a rank may run n_sets - 1 steps ahead of its neighbours: a rank that is ahead when it
+        # passes its start mark would be charged that head start, 8 GPUs: +10 us per step at --steps 20); then the start
+        # mark, the K timed steps and the end mark.  Both native calls are issued before the device has worked off the
+        # first, so the compute stream never runs dry.
+        lead_ops = sum(c for _, c in step_ops[n_warm:n_warm + LEAD])
+        seq.run(step_ops[n_warm][0], lead_ops)
+        rendezvous = torch.zeros(1, device="cuda")
+        dist.all_reduce(rendezvous)  # enqueued on the compute stream: every rank's timed region starts at the same time
+        seq.run(step_ops[n_warm][0] + lead_ops, sum(c for _, c in step_ops[n_warm + LEAD:]))
         barrier()
         total_ms = seq.elapsed_ms(0, 1)
         launches = (_lib.launch_count() - launches0) * args.steps // (args.steps + LEAD)
@@ -566,8 +575,9 @@ def b200_arm(args):
                    "vs_baseline_ref": "reference stencil::gpu on P100, BASELINE.md section 1"},
         "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
         "rank_ms_per_step": rank_ms,
-        "timing": ("marks in the compute stream of every rank after %d lead-in steps issued in the same native call "
-                   "(ranks in lock-step), max over ranks" % LEAD) if seq is not None else
+        "timing": ("marks in the compute stream of every rank: %d lead-in steps, an all-reduce on the compute stream (all "
+                   "ranks start the timed region together), start mark, K steps, end mark; max over ranks" % LEAD)
+        if seq is not None else
         "one CUDA event pair around the K back-to-back steps",
         "step_ms_median": statistics.median(per_step), "step_ms_p90": sorted(per_step)[int(0.9 * len(per_step))],
         "step_ms_max": max(per_step), "step_ms_note": "second pass with an event after every step (+~2.4 us per step)"

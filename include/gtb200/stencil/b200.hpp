@@ -96,9 +96,10 @@ namespace gtb200 {
         bool ChainSweeps = true,
         int Prefetch = 4,
         bool PrefetchL1 = true,
-        int ParallelPrefetch = 0>
+        int ParallelPrefetch = 0,
+        bool StageReadOnly = true>
     using block_geometry = ::gridtools::stencil::b200_backend::fused::
-        geometry<BI, BJ, KB, SweepUnroll, ChainSweeps, Prefetch, PrefetchL1, ParallelPrefetch>;
+        geometry<BI, BJ, KB, SweepUnroll, ChainSweeps, Prefetch, PrefetchL1, ParallelPrefetch, StageReadOnly>;
     using default_geometry = ::gridtools::stencil::b200_backend::fused::geometry<>;
 #else
     struct default_geometry {};

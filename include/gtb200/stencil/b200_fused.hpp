@@ -67,10 +67,46 @@
 #include <gridtools/common/cuda_util.hpp>
 #endif
 
+#include "../../gtb200.h"
+
 namespace gridtools {
     namespace stencil {
         namespace b200_backend {
             namespace fused {
+#ifdef __CUDACC__
+                // ---------------------------------------------------------------- TMA (cp.async.bulk.tensor) helpers
+                namespace tma {
+                    __device__ __forceinline__ uint32_t smem_addr(const void *p) {
+                        return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+                    }
+                    __device__ __forceinline__ void mbar_init(uint64_t *bar) {
+                        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)) : "memory");
+                        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                    }
+                    __device__ __forceinline__ void expect_tx(uint64_t *bar, uint32_t bytes) {
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+                                     : "memory");
+                    }
+                    __device__ __forceinline__ void load_3d(void *dst, const void *map, uint64_t *bar, int c0, int c1, int c2) {
+                        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+                                     "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_addr(dst)),
+                                     "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_addr(bar)), "r"(c0), "r"(c1), "r"(c2)
+                                     : "memory");
+                    }
+                    __device__ __forceinline__ void wait(uint64_t *bar) { // phase 0: the barrier is used once per CTA
+                        asm volatile("{\n"
+                                     ".reg .pred p;\n"
+                                     "WAIT_LOOP:\n"
+                                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+                                     "@p bra WAIT_DONE;\n"
+                                     "bra WAIT_LOOP;\n"
+                                     "WAIT_DONE:\n"
+                                     "}" ::"r"(smem_addr(bar))
+                                     : "memory");
+                    }
+                } // namespace tma
+#endif
+
                 // ---------------------------------------------------------------- geometry
                 // IJ block of a CTA, levels per CTA of a parallel multi-stage, unroll factor of the level loop of a sweep.
                 // Defaults from profiles/r01_fused_generic.txt (256x256x80 fp64): hori_diff 32x8x8 53.0 us, 64x4x8
@@ -91,10 +127,15 @@ namespace gridtools {
                     bool ChainSweeps = true,
                     int_t Prefetch = 4,
                     bool PrefetchL1 = true,
-                    int_t ParallelPrefetch = 0>
+                    int_t ParallelPrefetch = 0,
+                    bool StageReadOnly = true>
                 struct geometry {
                     static constexpr int_t bi = BI, bj = BJ, kb = KB, sweep_unroll = SweepUnroll, prefetch = Prefetch;
                     static constexpr bool chain_sweeps = ChainSweeps, prefetch_l1 = PrefetchL1;
+                    // parallel multi-stages: the fields they only read (no k offsets) are STAGED -- one TMA box over the
+                    // halo-extended IJ tile and the KB levels of the CTA lands in shared memory before the stages run, so
+                    // that every stage argument with an IJ extent is a shared-memory read (see staged tiles below)
+                    static constexpr bool stage_read_only = StageReadOnly;
                     // the same inside the KB levels a CTA of a parallel multi-stage walks (every thread asks for its
                     // own point of the halo-extended tile; not measured yet, hence off)
                     static constexpr int_t parallel_prefetch = ParallelPrefetch;
@@ -166,6 +207,82 @@ namespace gridtools {
                         .template set<sid::property::ptr_diff, int_t>()
                         .template set<sid::property::strides_kind, tile_kind<integral_constant<int_t, w>>>();
                 }
+
+                // ---------------------------------------------------------------- staged tiles (read-only fields)
+                // The reference's GPU backend reads a field with an IJ extent through global loads at every access
+                // (horizontal diffusion: 10 loads of `in` per point and level, behind each block barrier, SURVEY.md
+                // section 8 row a4) and so did this path: a CTA walks its KB levels as a chain of barrier -> loads from
+                // L1/L2 -> barrier, bound by their latency (52.9 us for horizontal diffusion at 256x256x80, 0.36 of the
+                // roofline).  Staging: every plain field a parallel multi-stage only reads, without k offsets, gets a
+                // shared-memory tile (BI + i-extent rounded up to 16 bytes) x (BJ + j-extent) x KB, filled ONCE per CTA
+                // by one `cp.async.bulk.tensor.3d` (TMA) issued by thread 0 -- out-of-domain points come back as zeros
+                // -- or, where the field is not TMA-addressable (and on the emulated CTAs of the tests), by a cooperative
+                // copy.  The stages then see a SID whose strides are the tile's: nothing else changes for them.
+                template <class T, class Cta, class Geo>
+                struct staged_holder {
+                    int_t m_bytes;   // start of the tile in the CTA's dynamic shared memory (128-byte aligned)
+                    int_t m_elems;   // offset of the addressed element, including what the host shifted in k
+                    int_t m_kstride; // elements per level of the tile
+                    int_t m_k_first; // levels the host has already shifted by
+                    GT_FUNCTION T const *operator()() const {
+                        return reinterpret_cast<T const *>(Cta::smem() + m_bytes) +
+                               (m_elems - (m_k_first + Cta::block_k() * Geo::kb) * m_kstride);
+                    }
+                    friend GT_FUNCTION staged_holder operator+(staged_holder h, int_t d) {
+                        h.m_elems += d;
+                        return h;
+                    }
+                };
+
+                template <class T, class Geo, class Extent>
+                struct staged_shape {
+                    static constexpr int_t row = 16 / int_t(sizeof(T)) > 0 ? 16 / int_t(sizeof(T)) : 1;
+                    static constexpr int_t used_w = Geo::bi - Extent::iminus::value + Extent::iplus::value;
+                    static constexpr int_t w = (used_w + row - 1) / row * row; // box rows are multiples of 16 bytes
+                    static constexpr int_t h = Geo::bj - Extent::jminus::value + Extent::jplus::value;
+                    static constexpr int_t bytes = int_t(sizeof(T)) * w * h * Geo::kb;
+                };
+
+                template <class T, class Cta, class Geo, class Extent>
+                auto make_staged_tile(int_t start, int_t k_first) {
+                    using shape_t = staged_shape<T, Geo, Extent>;
+                    return sid::synthetic()
+                        .template set<sid::property::origin>(staged_holder<T, Cta, Geo>{
+                            start, -Extent::iminus::value - Extent::jminus::value * shape_t::w, shape_t::w * shape_t::h, k_first})
+                        .template set<sid::property::strides>(hymap::keys<dim::i, dim::j, dim::k>::make_values(
+                            integral_constant<int_t, 1>(),
+                            integral_constant<int_t, shape_t::w>(),
+                            integral_constant<int_t, shape_t::w * shape_t::h>()))
+                        .template set<sid::property::ptr_diff, int_t>()
+                        .template set<sid::property::strides_kind,
+                            tile_kind<meta::list<integral_constant<int_t, shape_t::w>, integral_constant<int_t, shape_t::h>>>>();
+                }
+
+                /// where a staged tile comes from: filled in by prepare_mss, read by the CTA that fills the tile
+                template <class T>
+                struct staged_src {
+                    alignas(64) unsigned char m_map[128]; // CUtensorMap over the extended compute domain (if m_tma)
+                    T const *m_origin;                    // element (0, 0, first level of the multi-stage)
+                    ptrdiff_t m_sj, m_sk;
+                    int_t m_start;                        // of the tile in shared memory
+                    int_t m_tma;
+                };
+
+                template <class T>
+                struct is_staged_type : std::bool_constant<std::is_same<T, double>::value || std::is_same<T, float>::value> {};
+
+                // a raw pointer to T with i (unit), j and k strides behind the placeholder?
+                template <class Sid, class = void>
+                struct is_stageable_sid : std::false_type {};
+                template <class Sid>
+                struct is_stageable_sid<Sid,
+                    std::enable_if_t<std::is_pointer<sid::ptr_type<Sid>>::value &&
+                                     has_key<sid::strides_type<Sid>, dim::i>::value &&
+                                     has_key<sid::strides_type<Sid>, dim::j>::value &&
+                                     has_key<sid::strides_type<Sid>, dim::k>::value>>
+                    : std::bool_constant<std::is_same<std::decay_t<decltype(sid::get_stride<dim::i>(
+                                                          std::declval<sid::strides_type<Sid> const &>()))>,
+                          integral_constant<int_t, 1>>::value> {};
 
                 // ---------------------------------------------------------------- register windows (k caches)
                 template <class T, int_t Minus, int_t Plus>
@@ -253,7 +370,9 @@ namespace gridtools {
                     class Holder,
                     class Strides,
                     class KSizes,
-                    class Bounds>
+                    class Bounds,
+                    class StagedInfos = meta::list<>, // plh_infos of the staged fields ...
+                    class StagedSrcs = tuple<>>       // ... and a staged_src for each of them
                 struct mss_body {
                     using cta_t = Cta;
                     using extent_t = typename Mss::extent_t;
@@ -261,9 +380,11 @@ namespace gridtools {
                     using k_cached_t = meta::filter<is_k_cached, plh_map_t>;
                     using io_cached_t = meta::filter<is_io_cached, plh_map_t>;
                     using step_t = typename Mss::k_step_t;
+                    // (staged fields are shared-memory pointers: never through ld.global.nc)
                     template <class Info>
                     using is_read_only = std::bool_constant<Info::is_const_t::value &&
-                                                            !meta::st_contains<Volatile, typename Info::plh_t>::value>;
+                                                            !meta::st_contains<Volatile, typename Info::plh_t>::value &&
+                                                            !meta::st_contains<StagedInfos, Info>::value>;
                     using deref_t = read_only_deref<meta::transform<be_api::get_key, meta::filter<is_read_only, plh_map_t>>>;
 
                     static constexpr bool parallel = be_api::is_parallel<typename Mss::execution_t>::value;
@@ -281,6 +402,8 @@ namespace gridtools {
                     Bounds m_bounds;   // k_bounds per filled / flushed cache (order of io_cached_t)
                     int_t m_ni, m_nj;  // compute domain
                     int_t m_k_first;   // level of the first step of the sweep
+                    StagedSrcs m_staged; // sources of the staged tiles
+                    int_t m_bar;         // shared-memory offset of the mbarrier the TMA loads complete on
 
                     struct point {
                         int_t ti, tj, gi, gj;
@@ -315,7 +438,73 @@ namespace gridtools {
                         sid::shift(ptr, sid::get_stride<sid::blocked_dim<dim::j>>(m_strides), Cta::block_j());
                         sid::shift(ptr, sid::get_stride<dim::i>(m_strides), p.ti);
                         sid::shift(ptr, sid::get_stride<dim::j>(m_strides), p.tj);
+                        if constexpr (meta::length<StagedInfos>::value != 0)
+                            fill_staged(tid);
                         run(std::bool_constant<parallel>(), ptr, p);
+                    }
+
+                    // Fills the staged tiles of this CTA: levels [block_k * KB, block_k * KB + KB) of the halo-extended
+                    // IJ tile of every staged field.  TMA where the field is addressable (one elected thread, completion
+                    // on an mbarrier), a cooperative copy otherwise; points outside the extended compute domain are zeros.
+                    GT_FUNCTION void fill_staged(int_t tid) const {
+                        int_t k_total = 0;
+                        tuple_util::host_device::for_each([&](int_t size) GT_FORCE_INLINE_LAMBDA { k_total += size; }, m_k_sizes);
+                        const int_t k0 = Cta::block_k() * Geo::kb, i0 = Cta::block_i() * Geo::bi, j0 = Cta::block_j() * Geo::bj;
+#ifdef __CUDA_ARCH__
+                        uint64_t *bar = reinterpret_cast<uint64_t *>(Cta::smem() + m_bar);
+                        uint32_t tx_bytes = 0;
+                        if (tid == 0) {
+                            tma::mbar_init(bar);
+                            tuple_util::host_device::for_each(
+                                [&](auto info, auto const &src) GT_FORCE_INLINE_LAMBDA {
+                                    using info_t = decltype(info);
+                                    using shape_t = staged_shape<std::remove_const_t<typename info_t::data_t>, Geo,
+                                        to_horizontal_extent<typename info_t::extent_t>>;
+                                    if (src.m_tma)
+                                        tx_bytes += shape_t::bytes;
+                                },
+                                meta::rename<tuple, StagedInfos>(),
+                                m_staged);
+                            if (tx_bytes) {
+                                tma::expect_tx(bar, tx_bytes);
+                                tuple_util::host_device::for_each(
+                                    [&](auto, auto const &src) GT_FORCE_INLINE_LAMBDA {
+                                        if (src.m_tma)
+                                            tma::load_3d(Cta::smem() + src.m_start, src.m_map, bar, i0, j0, k0);
+                                    },
+                                    meta::rename<tuple, StagedInfos>(),
+                                    m_staged);
+                            }
+                        }
+#endif
+                        tuple_util::host_device::for_each(
+                            [&](auto info, auto const &src) GT_FORCE_INLINE_LAMBDA {
+                                using info_t = decltype(info);
+                                using T = std::remove_const_t<typename info_t::data_t>;
+                                using ext_t = to_horizontal_extent<typename info_t::extent_t>;
+                                using shape_t = staged_shape<T, Geo, ext_t>;
+                                if (src.m_tma)
+                                    return;
+                                T *tile = reinterpret_cast<T *>(Cta::smem() + src.m_start);
+                                for (int_t idx = tid; idx < shape_t::w * shape_t::h * Geo::kb; idx += threads) {
+                                    const int_t x = idx % shape_t::w, r = idx / shape_t::w, y = r % shape_t::h, z = r / shape_t::h;
+                                    const int_t gi = i0 + ext_t::iminus::value + x, gj = j0 + ext_t::jminus::value + y,
+                                                gk = k0 + z;
+                                    const bool inside = x < shape_t::used_w && gi < m_ni + ext_t::iplus::value &&
+                                                        gj < m_nj + ext_t::jplus::value && gk < k_total;
+                                    tile[idx] = inside ? src.m_origin[gi + gj * src.m_sj + gk * src.m_sk] : T(0);
+                                }
+                            },
+                            meta::rename<tuple, StagedInfos>(),
+                            m_staged);
+                        Cta::sync(); // the cooperative copies, and the mbarrier initialisation, are visible to every thread
+#ifdef __CUDA_ARCH__
+                        bool any_tma = false;
+                        tuple_util::host_device::for_each(
+                            [&](auto const &src) GT_FORCE_INLINE_LAMBDA { any_tma = any_tma || src.m_tma; }, m_staged);
+                        if (any_tma)
+                            tma::wait(bar);
+#endif
                     }
 
                     // parallel multi-stage: this CTA takes levels [kb * KB, kb * KB + KB) of the multi-stage's interval
@@ -551,12 +740,35 @@ namespace gridtools {
                         int_t(sid::get_upper_bound<dim::k>(sid::get_upper_bounds(store)))};
                 }
 
+                // which placeholders of a multi-stage are staged (see staged tiles above)
+                template <class Mss, class Geo, class DataStores>
+                struct staged_in {
+                    template <class Info, class Plh = typename Info::plh_t>
+                    using store_t = std::decay_t<decltype(at_key<Plh>(std::declval<DataStores &>()))>;
+                    template <class Info>
+                    using apply = std::bool_constant<Geo::stage_read_only &&
+                        be_api::is_parallel<typename Mss::execution_t>::value && is_plain<Info>::value &&
+                        Info::is_const_t::value && !Info::is_tmp_t::value && Info::extent_t::kminus::value == 0 &&
+                        Info::extent_t::kplus::value == 0 && is_staged_type<std::remove_const_t<typename Info::data_t>>::value &&
+                        is_stageable_sid<store_t<Info>>::value>;
+                };
+                template <class Mss, class Grid>
+                int_t k_total_of(Mss, Grid const &grid) {
+                    int_t n = 0;
+                    tuple_util::for_each([&](int_t size) { n += size; }, be_api::make_k_sizes(Mss::interval_infos(), grid));
+                    return n;
+                }
+
                 template <class Launcher, class Geo, class Volatile, class Mss, class Grid, class DataStores>
                 auto prepare_mss(Mss, Grid const &grid, DataStores &data_stores) {
                     using cta_t = typename Launcher::cta_t;
                     using plh_map_t = typename Mss::plh_map_t;
                     using io_cached_t = meta::filter<is_io_cached, plh_map_t>;
                     int_t smem_bytes = 0;
+                    const int_t k_first = grid.k_start(Mss::interval(), Mss::execution());
+                    // plain fields a parallel multi-stage only reads, without k offsets: staged through shared memory
+                    using staged_t = meta::filter<staged_in<Mss, Geo, DataStores>::template apply, plh_map_t>;
+                    int_t staged_starts[meta::length<staged_t>::value + 1] = {}, staged_count = 0;
 
                     // fields, shared-memory tiles and window stubs under the keys the stages look them up with ...
                     auto members = tuple_util::transform(
@@ -572,10 +784,53 @@ namespace gridtools {
                                 return make_window_stub<std::remove_const_t<typename decltype(info)::data_t>>();
                             },
                             [&](meta::list<>, auto info) {
-                                return sid::add_const(info.is_const(), at_key<decltype(info.plh())>(data_stores));
+                                using info_t = decltype(info);
+                                if constexpr (meta::st_contains<staged_t, info_t>::value) {
+                                    using shape_t = staged_shape<std::remove_const_t<typename info_t::data_t>, Geo,
+                                        to_horizontal_extent<typename info_t::extent_t>>;
+                                    const int_t start = (smem_bytes + 127) / 128 * 128;
+                                    smem_bytes = start + shape_t::bytes;
+                                    staged_starts[staged_count++] = start; // (transform visits the placeholders in order)
+                                    return make_staged_tile<std::remove_const_t<typename info_t::data_t>, cta_t, Geo,
+                                        to_horizontal_extent<typename info_t::extent_t>>(start, k_first);
+                                } else {
+                                    return sid::add_const(info.is_const(), at_key<decltype(info.plh())>(data_stores));
+                                }
                             }),
                         meta::rename<tuple, meta::transform<be_api::get_caches, plh_map_t>>(),
                         meta::rename<tuple, plh_map_t>());
+                    // where the staged tiles come from (same walk through the shared memory as above)
+                    int_t staged_walk = 0;
+                    auto staged_srcs = tuple_util::transform(
+                        [&](auto info) {
+                            using info_t = decltype(info);
+                            using T = std::remove_const_t<typename info_t::data_t>;
+                            using ext_t = to_horizontal_extent<typename info_t::extent_t>;
+                            using shape_t = staged_shape<T, Geo, ext_t>;
+                            auto &store = at_key<decltype(info.plh())>(data_stores);
+                            auto store_strides = sid::get_strides(store);
+                            staged_src<T> src{};
+                            src.m_sj = sid::get_stride<dim::j>(store_strides);
+                            src.m_sk = sid::get_stride<dim::k>(store_strides);
+                            src.m_origin = sid::get_origin(store)() + ptrdiff_t(k_first) * src.m_sk;
+                            src.m_start = staged_starts[staged_walk++];
+                            // the tensor is the extended compute domain over the levels of this multi-stage: what
+                            // lies outside reads as zero, like in the cooperative copy
+                            const int64_t dims[3] = {grid.i_size() - ext_t::iminus::value + ext_t::iplus::value,
+                                grid.j_size() - ext_t::jminus::value + ext_t::jplus::value,
+                                k_total_of(Mss(), grid)};
+                            const int64_t byte_strides[2] = {int64_t(src.m_sj) * int64_t(sizeof(T)), int64_t(src.m_sk) * int64_t(sizeof(T))};
+                            const int box[3] = {shape_t::w, shape_t::h, Geo::kb};
+                            src.m_tma = dims[0] > 0 && dims[1] > 0 && dims[2] > 0 &&
+                                        Launcher::tensor_map(src.m_map,
+                                            src.m_origin + ext_t::iminus::value + ptrdiff_t(ext_t::jminus::value) * src.m_sj,
+                                            int(sizeof(T)), dims, byte_strides, box);
+                            return src;
+                        },
+                        meta::rename<tuple, staged_t>());
+                    const int_t bar_off = (smem_bytes + 7) / 8 * 8;
+                    if (meta::length<staged_t>::value != 0)
+                        smem_bytes = bar_off + 8;
                     // ... plus the fields behind filled / flushed k caches
                     auto behinds = tuple_util::transform(
                         [&](auto info) {
@@ -595,7 +850,6 @@ namespace gridtools {
 
                     auto strides = sid::get_strides(composite);
                     sid::ptr_diff_type<decltype(composite)> offset{};
-                    const int_t k_first = grid.k_start(Mss::interval(), Mss::execution());
                     sid::shift(offset, sid::get_stride<dim::k>(strides), k_first);
                     auto k_sizes = be_api::make_k_sizes(Mss::interval_infos(), grid);
                     int_t k_total = 0;
@@ -608,10 +862,12 @@ namespace gridtools {
                         decltype(sid::get_origin(composite) + offset),
                         decltype(strides),
                         decltype(k_sizes),
-                        decltype(bounds)>;
+                        decltype(bounds),
+                        staged_t,
+                        decltype(staged_srcs)>;
                     const int_t nbk = body_t::parallel ? (k_total + Geo::kb - 1) / Geo::kb : (k_total > 0 ? 1 : 0);
                     return pending<body_t>{
-                        body_t{sid::get_origin(composite) + offset, strides, k_sizes, bounds, ni, nj, k_first},
+                        body_t{sid::get_origin(composite) + offset, strides, k_sizes, bounds, ni, nj, k_first, staged_srcs, bar_off},
                         ni > 0 ? (ni + Geo::bi - 1) / Geo::bi : 0,
                         nj > 0 ? (nj + Geo::bj - 1) / Geo::bj : 0,
                         nbk,
@@ -764,13 +1020,19 @@ namespace gridtools {
                 };
 
                 template <class Body>
-                __global__ void __launch_bounds__(Body::threads) mss_kernel(Body body) {
+                __global__ void __launch_bounds__(Body::threads) mss_kernel(const __grid_constant__ Body body) {
                     body();
                 }
 
                 struct cuda_launcher {
                     using cta_t = cuda_cta;
                     cudaStream_t m_stream;
+
+                    /// TMA descriptor of a 3-d box (libgtb200 encodes it); false if the field is not TMA-addressable
+                    static bool tensor_map(void *map, const void *base, int elem_size, const int64_t dims[3],
+                        const int64_t strides_bytes[2], const int box[3]) {
+                        return gtb_tensor_map_3d(map, base, elem_size, dims, strides_bytes, box) == GTB_OK;
+                    }
 
                     // Device memory for the temporaries, recycled like the reference's sid::device::cached_allocator
                     // (sid/allocator.hpp:65-95: thread-local free lists by size) -- but the free lists are per STREAM:

@@ -41,6 +41,15 @@ namespace emulated {
         long launches = 0, syncs_possible = 0;
 
         static auto allocator() { return gridtools::sid::cached_allocator(&std::make_unique<char[]>); }
+        // no TMA on the host: the staged tiles are filled by the cooperative copy
+        static bool tensor_map(void *, const void *, int, const int64_t *, const int64_t *, const int *) {
+            ++staged_fields();
+            return false;
+        }
+        static long &staged_fields() { // how many fields have been staged through emulated shared memory so far
+            static long n = 0;
+            return n;
+        }
 
         template <class Body>
         void launch(Body const &body, int_t nbi, int_t nbj, int_t nbk, int_t threads, int_t smem) {

@@ -28,8 +28,9 @@ namespace {
         static constexpr long sweep_launches = Geo::chain_sweeps ? 1 : 2;
         using be_t = emulated::backend<Geo>;
         using ref_t = st::cpu_ifirst<>;
-        // cpu_kfirst storage has i-stride 1 like storage::gpu
-        using traits_t = gt::storage::cpu_kfirst;
+        // cpu_ifirst storage: i has the compile-time stride 1 of storage::gpu (what the staging of read-only fields
+        // through shared memory needs, and padded rows)
+        using traits_t = gt::storage::cpu_ifirst;
         std::string m_geo;
 
         void expect_launches(const char *what, long n) {
@@ -202,6 +203,9 @@ int main() {
     run<fused::geometry<8, 4, 3, 2, true, 4, true, 1>>{"[8x4x3 blocks, prefetch]"}.all(19, 9, 7);
     // sweeps in separate launches
     run<fused::geometry<8, 4, 3, 2, false>>{"[8x4x3 blocks, unchained]"}.all(19, 9, 7);
+    std::printf("fields staged through (emulated) shared memory: %ld\n", emulated::launcher::staged_fields());
+    if (emulated::launcher::staged_fields() == 0)
+        ++g_failed; // the staging of read-only fields of parallel multi-stages must be exercised here
     std::printf(g_failed ? "FAILED (%d)\n" : "ALL PASSED\n", g_failed);
     return g_failed ? 1 : 0;
 }

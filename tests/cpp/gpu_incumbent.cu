@@ -126,9 +126,9 @@ namespace {
         double t = time_us([&](int s) { s == 0 ? call(s0) : call(s1); }, SETS);
         report("vertical_advection_dycore", name, t, 1. * ni * nj * nk, 48);
     }
-    template <int BI, int BJ, int KB, int U = 1, bool Chain = true, int P = 0, bool L1 = false, int PP = 0>
+    template <int BI, int BJ, int KB, int U = 1, bool Chain = true, int P = 0, bool L1 = false, int PP = 0, bool Stage = true>
     using fused_t = st::b200<gtb200::default_stream, gtb200::fused_when_possible,
-        gtb200::block_geometry<BI, BJ, KB, U, Chain, P, L1, PP>>;
+        gtb200::block_geometry<BI, BJ, KB, U, Chain, P, L1, PP, Stage>>;
 } // namespace
 
 int main(int argc, char **argv) {
@@ -149,11 +149,13 @@ int main(int argc, char **argv) {
         vert_adv<1>("stencil::b200<> staged", staged_t(), ni, nj, nk);
 #else
         // block geometries / sweep unroll factors of the fused generic path (make -C tests/cpp fused_timing)
-        hori_diff<1>("fused 32x8x8", fused_t<32, 8, 8>(), ni, nj, nk);
-        hori_diff<1>("fused 32x8x8 prefetch 1", fused_t<32, 8, 8, 3, true, 4, true, 1>(), ni, nj, nk);
-        hori_diff<1>("fused 32x8x8 prefetch 2", fused_t<32, 8, 8, 3, true, 4, true, 2>(), ni, nj, nk);
-        hori_diff<1>("fused 32x8x16 prefetch 2", fused_t<32, 8, 16, 3, true, 4, true, 2>(), ni, nj, nk);
-        hori_diff<1>("fused 64x8x8 prefetch 1", fused_t<64, 8, 8, 3, true, 4, true, 1>(), ni, nj, nk);
+        hori_diff<1>("fused 32x8x8 TMA-staged", fused_t<32, 8, 8>(), ni, nj, nk);
+        hori_diff<1>("fused 32x8x8 not staged", fused_t<32, 8, 8, 3, true, 4, true, 0, false>(), ni, nj, nk);
+        hori_diff<1>("fused 32x8x4 TMA-staged", fused_t<32, 8, 4>(), ni, nj, nk);
+        hori_diff<1>("fused 32x8x16 TMA-staged", fused_t<32, 8, 16>(), ni, nj, nk);
+        hori_diff<1>("fused 64x8x8 TMA-staged", fused_t<64, 8, 8>(), ni, nj, nk);
+        hori_diff<1>("fused 32x16x8 TMA-staged", fused_t<32, 16, 8>(), ni, nj, nk);
+        hori_diff<1>("fused 64x4x8 TMA-staged", fused_t<64, 4, 8>(), ni, nj, nk);
         vert_adv<1>("fused unroll 3 prefetch 4 L1", fused_t<32, 8, 8, 3, true, 4, true>(), ni, nj, nk);
         vert_adv<1>("fused unroll 3 prefetch 2 L1", fused_t<32, 8, 8, 3, true, 2, true>(), ni, nj, nk);
         vert_adv<1>("fused unroll 3 prefetch 3 L1", fused_t<32, 8, 8, 3, true, 3, true>(), ni, nj, nk);

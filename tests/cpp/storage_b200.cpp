@@ -13,7 +13,8 @@
 
 namespace gt = gridtools;
 namespace st = gridtools::stencil;
-using namespace st::cartesian;
+using namespace gridtools::stencil;
+using namespace gridtools::stencil::cartesian;
 
 struct copy_functor {
     using in = in_accessor<0>;
