@@ -16,7 +16,7 @@
 //    three block-wide barriers of the reference and leaves exactly one __syncthreads per item (ring hand-over);
 //  * `out` is stored straight from registers, 256 B (fp64) per warp instruction.
 // A second variant stages the same tiles with cp.async (LDGSTS) element by element; it is used when the layout
-// does not satisfy TMA's 16-byte stride/alignment rules, and serves as an A/B baseline ("hd.variant" option: 1 cp.async, 2 TMA + block barrier, 3 TMA warp specialised = default).
+// does not satisfy TMA's 16-byte stride/alignment rules, and serves as an A/B baseline ("hd.variant" option: 0 auto, 1 cp.async, 2 TMA + block barrier).
 //
 // Arithmetic follows the functor bodies operation by operation (no FMA contraction: the file is compiled with
 // -fmad=false), so results are bit-identical to oracle/gt_oracle.c compiled with -ffp-contract=off.
@@ -201,57 +201,6 @@ namespace {
         ptx::tma_load_3d(base + L::in_alloc, map_co, bar, it.i0(), it.j0(), it.k);
     }
 
-    // ------------------------------------------------ TMA variant, warp specialised (hd.variant = 3, the default)
-    // WARPS compute warps + 1 producer warp.  full[s]: TMA landed stage s.  empty[s]: all compute warps have read it.
-    // No block-wide barrier in the loop: compute warps drift apart and keep the fp64 pipe and the LSU busy while
-    // other warps wait for data.
-    template <class T, int STAGES>
-    __global__ void __launch_bounds__(THREADS + 32, 2) hd_tma_ws_kernel(const __grid_constant__ CUtensorMap map_in,
-        const __grid_constant__ CUtensorMap map_co, const hd_params<T> p) {
-        using L = layout<T>;
-        extern __shared__ __align__(128) unsigned char smem[];
-        uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * L::stage_bytes);
-        uint64_t *empty = full + STAGES;
-        const int tid = threadIdx.x;
-        const int warp = tid >> 5, lane = tid & 31;
-        if (tid == 0) {
-            ptx::prefetch_tensormap(&map_in);
-            ptx::prefetch_tensormap(&map_co);
-#pragma unroll
-            for (int s = 0; s < STAGES; ++s) {
-                ptx::mbar_init(&full[s], 1);
-                ptx::mbar_init(&empty[s], WARPS);
-            }
-            ptx::fence_barrier_init();
-        }
-        __syncthreads();
-        item_iter it;
-        it.start(p, (int)blockIdx.x);
-        if (warp == WARPS) {
-            if (lane == 0) {
-                for (int n = 0; it.k < p.nk; ++n, it.next(p)) {
-                    const int s = n % STAGES;
-                    if (n >= STAGES)
-                        ptx::mbar_wait(&empty[s], (uint32_t)((n / STAGES - 1) & 1));
-                    tma_issue<T>(&map_in, &map_co, smem + s * L::stage_bytes, &full[s], it);
-                }
-            }
-            return;
-        }
-        const int tx = tid % BI, ty = tid / BI;
-        for (int n = 0; it.k < p.nk; ++n, it.next(p)) {
-            const int s = n % STAGES;
-            ptx::mbar_wait(&full[s], (uint32_t)((n / STAGES) & 1));
-            const unsigned char *base = smem + s * L::stage_bytes;
-            compute_item<T>(p, reinterpret_cast<const T *>(base), reinterpret_cast<const T *>(base + L::in_alloc), it,
-                tx, ty, [&] {
-                    __syncwarp();
-                    if (lane == 0)
-                        ptx::mbar_arrive(&empty[s]);
-                });
-        }
-    }
-
     // ------------------------------------------------ TMA variant with a block barrier per item (hd.variant = 2)
     template <class T, int STAGES, bool SIMPLE = false>
     __global__ void __launch_bounds__(THREADS, 2) hd_tma_kernel(const __grid_constant__ CUtensorMap map_in,
@@ -393,12 +342,15 @@ namespace {
         const bool gated = p.gate.wait_flag || p.gate.post;
         if (gated && p.gate.post && !p.gate.cta_done)
             return GTB_ERR_ALLOC;
+        if (variant == 3)
+            return fail(GTB_ERR_ARG, "gtb_hori_diff: hd.variant=3 (warp-specialised producer) was removed: it measured "
+                                     "slower than the block-barrier pipeline (27.9 against 24.6 us); use 0, 1 or 2");
         if (variant != 1) {
             CUtensorMap map_in, map_co;
             bool ok = make_map<T>(&map_in, p.in, p.in_sj, p.in_sk, L::lead, 2, (int64_t)L::lead + p.ni + 2, p.nj + 4,
                           p.nk, L::in_w, IN_H) &&
                       make_map<T>(&map_co, p.coeff, p.co_sj, p.co_sk, 0, 0, p.ni, p.nj, p.nk, BI, BJ);
-            if (ok && variant != 3) { // auto picks the block-barrier pipeline: it measured 3 % faster at 256x256x80
+            if (ok) {
                 auto kernel = hd_tma_kernel<T, STAGES>;
                 int st = prepare_kernel(kernel, smem);
                 if (st)
@@ -412,15 +364,6 @@ namespace {
             if (gated)
                 return fail(GTB_ERR_ARG, "gtb_hori_diff: a gate (gtb_stencil_gate) needs the default TMA kernel "
                                          "(hd.variant 0 or 2, TMA-addressable layout)");
-            if (ok) {
-                auto kernel = hd_tma_ws_kernel<T, STAGES>;
-                int st = prepare_kernel(kernel, smem);
-                if (st)
-                    return st;
-                kernel<<<grid, THREADS + 32, smem, stream>>>(map_in, map_co, p);
-                count_launch();
-                return check_launch("hd_tma_ws_kernel");
-            }
             if (variant != 0)
                 return fail(GTB_ERR_LAYOUT,
                     "gtb_hori_diff: hd.variant=%d (TMA) needs 16-byte aligned origins and stride_j/stride_k that "

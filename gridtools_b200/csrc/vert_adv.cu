@@ -359,147 +359,6 @@ namespace {
         CUtensorMap us, up, ut, un, wc;
     };
 
-    template <class T, int KC, int S, int WARPS, int NS>
-    __global__ void __launch_bounds__(WARPS * 32) va_tma_kernel(const __grid_constant__ va_maps maps,
-        const va_params<T> p) {
-        using L = va_tma_layout<T>;
-        constexpr int stage_bytes = L::template stage_bytes<KC>();
-        extern __shared__ __align__(128) unsigned char smem_all[];
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        unsigned char *ring = smem_all + warp * (S * stage_bytes);
-        uint64_t *full = reinterpret_cast<uint64_t *>(smem_all + WARPS * S * stage_bytes) + warp * S;
-        if (lane == 0) {
-#pragma unroll
-            for (int s = 0; s < S; ++s)
-                ptx::mbar_init(&full[s], 1);
-            ptx::fence_barrier_init();
-            if (threadIdx.x == 0) {
-                ptx::prefetch_tensormap(&maps.us);
-                ptx::prefetch_tensormap(&maps.up);
-                ptx::prefetch_tensormap(&maps.ut);
-                ptx::prefetch_tensormap(&maps.un);
-                ptx::prefetch_tensormap(&maps.wc);
-            }
-        }
-        __syncwarp();
-        const int nk = p.nk;
-        const T dtr = p.dtr;
-        const uint64_t pol_keep = ptx::policy_evict_last();
-        const int gw = blockIdx.x * WARPS + warp, total = gridDim.x * WARPS;
-        T *slab = p.scratch + (int64_t)gw * 32 + lane; // [k][NS][slots]
-        const int64_t sstride = p.slots;
-        const int nchunks = (nk + KC - 1) / KC;
-        uint32_t n_issued = 0, n_waited = 0; // ring uses so far (stage = n % S, parity = (n / S) & 1)
-
-        for (int item = gw; item < p.items; item += total) {
-            const int ti = item % p.tiles_i, j = item / p.tiles_i;
-            const int i0 = ti * 32, i = i0 + lane;
-            const bool active = i < p.ni;
-            // Whole warp: lane 0 arms the barrier, then lanes 0..4 issue the five box loads with ONE predicated
-            // instruction (a TMA issue costs ~150 cycles of the issuing thread; five in a row by one lane made the
-            // ring refill as expensive as the forward math of the chunk).
-            auto issue = [&](int c) {
-                const int s = n_issued % S;
-                if (lane == 0)
-                    ptx::mbar_expect_tx(&full[s], KC * (4 * 32 + L::ww) * L::es);
-                __syncwarp();
-                if (lane < 5)
-                    ptx::tma_load_3d(ring + s * stage_bytes + lane * (KC * 32 * L::es), &maps.us + lane, &full[s], i0, j,
-                        c * KC + (lane >= 3 ? 1 : 0)); // u_stage and wcon are read one level up
-            };
-            // prologue: S-1 chunks in flight
-            for (int c = 0; c < S - 1 && c < nchunks; ++c) {
-                issue(c);
-                ++n_issued;
-            }
-            va_state<T> st;
-            st.u_k = active ? __ldg(p.u_stage.ptr + i + (int64_t)j * p.u_stage.sj) : T(0);
-            st.u_km1 = st.wsum_k = st.cc_prev = st.dc_prev = st.up_last = T(0);
-            for (int c = 0; c < nchunks; ++c) {
-                if (c + S - 1 < nchunks) { // refill the stage consumed in the previous iteration
-                    issue(c + S - 1);
-                    ++n_issued;
-                }
-                const int s = n_waited % S;
-                ptx::mbar_wait(&full[s], (n_waited / S) & 1);
-                ++n_waited;
-                const T *sd = reinterpret_cast<const T *>(ring + s * stage_bytes);
-                const T *wc = sd + 4 * KC * 32;
-#pragma unroll
-                for (int u = 0; u < KC; ++u) {
-                    const int k = c * KC + u;
-                    if (k < nk) {
-                        T us = sd[u * 32 + lane], up = sd[(KC + u) * 32 + lane], ut = sd[(2 * KC + u) * 32 + lane];
-                        T un = sd[(3 * KC + u) * 32 + lane];
-                        T w0 = wc[u * L::ww + lane], w1 = wc[u * L::ww + lane + 1];
-                        T cc, dc;
-                        if (p.debug & 2) {
-                            cc = us + un + w0 + w1;
-                            dc = up + ut;
-                            st.dc_prev = dc;
-                        } else {
-                            va_forward_level<T>(k, nk, dtr, us, un, w0, w1, up, ut, st, cc, dc);
-                        }
-                        if (k < nk - 1 && !(p.debug & 4)) {
-                            T *q = slab + (int64_t)k * NS * sstride;
-                            ptx::st_hint(q, cc, pol_keep);
-                            ptx::st_hint(q + sstride, dc, pol_keep);
-                            if constexpr (NS == 3)
-                                ptx::st_hint(q + 2 * sstride, up, pol_keep);
-                        }
-                    }
-                }
-                __syncwarp(); // all lanes are done with stage s before lane 0 refills it
-            }
-            // ---------------------------------------------------------------- backward sweep (u_backward_function)
-            T *us_p = p.utens_stage.ptr + i + (int64_t)j * p.utens_stage.sj;
-            const T *up_p = p.u_pos.ptr + (active ? i : 0) + (int64_t)j * p.u_pos.sj;
-            const int64_t us_sk = p.utens_stage.sk, up_sk = p.u_pos.sk;
-            T data = st.dc_prev;
-            if (active)
-                us_p[(int64_t)(nk - 1) * us_sk] = dtr * (data - st.up_last);
-            constexpr int BU = 8;
-            struct back_level {
-                T cc, dc, up;
-            };
-            auto load_back = [&](int k, back_level &v) {
-                if (k >= 0) {
-                    const T *q = slab + (int64_t)k * NS * sstride;
-                    v.cc = ptx::ld_hint(q, pol_keep);
-                    v.dc = ptx::ld_hint(q + sstride, pol_keep);
-                    if constexpr (NS == 3)
-                        v.up = ptx::ld_hint(q + 2 * sstride, pol_keep);
-                    else
-                        v.up = __ldg(up_p + k * up_sk);
-                }
-            };
-            back_level bcur[BU];
-            if (p.debug & 1)
-                continue;
-#pragma unroll
-            for (int u = 0; u < BU; ++u)
-                load_back(nk - 2 - u, bcur[u]);
-            for (int k0 = nk - 2; k0 >= 0; k0 -= BU) {
-                back_level bnxt[BU];
-#pragma unroll
-                for (int u = 0; u < BU; ++u)
-                    load_back(k0 - BU - u, bnxt[u]);
-#pragma unroll
-                for (int u = 0; u < BU; ++u) {
-                    const int k = k0 - u;
-                    if (k >= 0) { // body :111-116
-                        data = bcur[u].dc - bcur[u].cc * data;
-                        if (active)
-                            us_p[(int64_t)k * us_sk] = dtr * (data - bcur[u].up);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < BU; ++u)
-                    bcur[u] = bnxt[u];
-            }
-        }
-    }
-
     // ------------------------------------------------------------------ streaming variant (va.variant = 3, default)
     // Same decomposition as variant 2 (one warp = one 32-column strip, persistent over the strips, the warp is its
     // own TMA producer), rebuilt around what the profile of variant 2 showed (profiles/README.md):
@@ -695,303 +554,10 @@ namespace {
         }
     }
 
-    // ------------------------------------------------------------------ resident variant (va.variant = 4, default)
-    // The L2 slab of variants 2 and 3 is not free: every byte written to and read back from it crosses the L2 slices,
-    // and the L2 slices of this chip move ~8 TB/s in total, HBM misses included (measured: 504 MB of L2 traffic in
-    // 62 us for variant 3, whatever the prefetch depth or the number of warps).  With ccol/dcol/u_pos in L2 the sweep
-    // moves 96 B per point through L2 against 48 B from HBM and is L2-bound at ~60 us.  Here ccol and dcol never
-    // leave the SM:
-    //  * the last RMAX levels of a column live in REGISTERS (statically indexed arrays, forward and backward sweeps
-    //    over that range are fully unrolled): at 7 warps per SM a thread may own 255 registers, and the register file
-    //    (256 KB per SM) is the largest on-chip memory there is;
-    //  * the levels below (k < k_split = nk - 1 - RMAX rounded up to a chunk) live in a per-warp SHARED-MEMORY slab
-    //    [k][ccol, dcol][32 lanes] (conflict free);
-    //  * u_pos, needed again by the backward sweep, is re-read through a small second TMA ring; the forward loads of
-    //    u_pos carry an L2 evict_last hint and everything else evict_first, so the second read is an L2 hit.
-    // L2 traffic drops to 56 B per point, HBM traffic stays at the compulsory 48 B.  A strip whose shared-memory slab
-    // would not leave room for 7 warps per SM (large nk) is run by variant 3 instead.
-    // Statically indexed access to the register-resident k-cache: chunk number -> KC array elements, through a switch
-    // (a jump table in SASS) so that the arrays never get a dynamic index and stay in registers.
-    template <class T, int KC, int NCR>
-    struct reg_tier {
-        template <int C>
-        static __device__ __forceinline__ void put_case(T *rc, T *rd, const T *ccv, const T *dcv) {
-            asm volatile("" ::: "memory"); // keeps the case a real branch target (the compiler would otherwise turn the
-                                           // switch into one select per array element and case)
-#pragma unroll
-            for (int u = 0; u < KC; ++u) {
-                rc[C * KC + u] = ccv[u];
-                rd[C * KC + u] = dcv[u];
-            }
-        }
-        template <int C>
-        static __device__ __forceinline__ void get_case(const T *rc, const T *rd, T *ccv, T *dcv) {
-            asm volatile("" ::: "memory");
-#pragma unroll
-            for (int u = 0; u < KC; ++u) {
-                ccv[u] = rc[C * KC + u];
-                dcv[u] = rd[C * KC + u];
-            }
-        }
-#define GTB_RT_CASES(F)                                                                                               \
-    F(0) F(1) F(2) F(3) F(4) F(5) F(6) F(7) F(8) F(9) F(10) F(11) F(12) F(13) F(14) F(15) F(16) F(17) F(18) F(19) F(20)   \
-        F(21) F(22) F(23) F(24) F(25) F(26) F(27) F(28) F(29) F(30) F(31) F(32) F(33) F(34) F(35) F(36) F(37) F(38) F(39) \
-            F(40) F(41)
-        static_assert(NCR <= 42, "extend GTB_RT_CASES");
-        static __device__ __forceinline__ void put(int c, T *rc, T *rd, const T *ccv, const T *dcv) {
-            switch (c) {
-#define GTB_RT_PUT(C)                          \
-    case C:                                    \
-        if constexpr (C < NCR)                 \
-            put_case<C>(rc, rd, ccv, dcv);     \
-        break;
-                GTB_RT_CASES(GTB_RT_PUT)
-#undef GTB_RT_PUT
-            default:
-                break;
-            }
-        }
-        static __device__ __forceinline__ void get(int c, const T *rc, const T *rd, T *ccv, T *dcv) {
-#pragma unroll
-            for (int u = 0; u < KC; ++u)
-                ccv[u] = dcv[u] = T(0);
-            switch (c) {
-#define GTB_RT_GET(C)                          \
-    case C:                                    \
-        if constexpr (C < NCR)                 \
-            get_case<C>(rc, rd, ccv, dcv);     \
-        break;
-                GTB_RT_CASES(GTB_RT_GET)
-#undef GTB_RT_GET
-            default:
-                break;
-            }
-        }
-#undef GTB_RT_CASES
-    };
-
+    // bytes of one stage of the backward sweep's u_pos ring (paired-warp kernel)
     template <class T, int KC>
     constexpr int va_bstage_bytes() {
         return (KC * 32 * (int)sizeof(T) + 127) / 128 * 128;
-    }
-
-    template <class T, int KC, int S, int SB, int RMAX>
-    __global__ void __launch_bounds__(32) va_resident_kernel(const __grid_constant__ va_maps maps, const va_params<T> p) {
-        using L = va_tma_layout<T>;
-        constexpr int es = L::es;
-        constexpr int fstage = L::template stage_bytes<KC>();
-        constexpr int bstage = va_bstage_bytes<T, KC>();
-        constexpr uint32_t ftx = KC * (4 * 32 + L::ww) * es;
-        constexpr uint32_t btx = KC * 32 * es;
-        constexpr int NCR = (RMAX + KC - 1) / KC + 1; // chunks of the register tier (+1: the chunk of level nk-1)
-        extern __shared__ __align__(128) unsigned char smem_all[];
-        unsigned char *fring = smem_all;
-        unsigned char *bring = smem_all + S * fstage;
-        uint64_t *ffull = reinterpret_cast<uint64_t *>(smem_all + S * fstage + SB * bstage);
-        uint64_t *bfull = ffull + S;
-        const int lane = threadIdx.x;
-        T *const ss = reinterpret_cast<T *>(smem_all + S * fstage + SB * bstage + 128) + lane; // [k][2][32]
-        if (lane == 0) {
-#pragma unroll
-            for (int s = 0; s < S; ++s)
-                ptx::mbar_init(&ffull[s], 1);
-#pragma unroll
-            for (int s = 0; s < SB; ++s)
-                ptx::mbar_init(&bfull[s], 1);
-            ptx::fence_barrier_init();
-            ptx::prefetch_tensormap(&maps.us);
-            ptx::prefetch_tensormap(&maps.up);
-            ptx::prefetch_tensormap(&maps.ut);
-            ptx::prefetch_tensormap(&maps.un);
-            ptx::prefetch_tensormap(&maps.wc);
-        }
-        __syncwarp();
-        const int nk = p.nk;
-        const T dtr = p.dtr;
-        const uint64_t pol_keep = ptx::policy_evict_last(), pol_stream = ptx::policy_evict_first();
-        const int gw = blockIdx.x, total = gridDim.x;
-        const int nchunks = (nk + KC - 1) / KC;
-        const int k_split = p.k_split, c_split = k_split / KC;
-        const int cb_top = (nk - 2) / KC; // backward chunk that holds level nk-2
-        int f_issue = 0, f_wait = 0, b_issue = 0, b_wait = 0; // ring stages: producer fills next / consumer waits for next
-        uint32_t f_phase = 0, b_phase = 0;                    // parity of the consumer's current trip around each ring
-
-        auto issue_f = [&](int i0, int j, int c) {
-            const int s = f_issue;
-            f_issue = f_issue + 1 == S ? 0 : f_issue + 1;
-            if (ptx::elect_one()) {
-                unsigned char *st = fring + s * fstage;
-                uint64_t *bar = &ffull[s];
-                ptx::mbar_expect_tx(bar, ftx);
-                ptx::tma_load_3d_hint(st, &maps.us, bar, i0, j, c * KC, pol_stream);
-                ptx::tma_load_3d_hint(st + KC * 32 * es, &maps.up, bar, i0, j, c * KC, pol_keep); // read again below
-                ptx::tma_load_3d_hint(st + 2 * KC * 32 * es, &maps.ut, bar, i0, j, c * KC, pol_stream);
-                ptx::tma_load_3d_hint(st + 3 * KC * 32 * es, &maps.un, bar, i0, j, c * KC + 1, pol_stream);
-                ptx::tma_load_3d_hint(st + 4 * KC * 32 * es, &maps.wc, bar, i0, j, c * KC + 1, pol_stream);
-            }
-        };
-        auto issue_b = [&](int i0, int j, int cb) {
-            const int s = b_issue;
-            b_issue = b_issue + 1 == SB ? 0 : b_issue + 1;
-            if (ptx::elect_one()) {
-                ptx::mbar_expect_tx(&bfull[s], btx);
-                ptx::tma_load_3d_hint(bring + s * bstage, &maps.up, &bfull[s], i0, j, cb * KC, pol_stream);
-            }
-        };
-        auto prime = [&](int item, T &u0) { // first S-1 forward chunks of a strip + u_stage(k = 0)
-            const int ti = item % p.tiles_i, j = item / p.tiles_i;
-            const int i0 = ti * 32;
-            for (int c = 0; c < S - 1 && c < nchunks; ++c)
-                issue_f(i0, j, c);
-            u0 = i0 + lane < p.ni ? __ldg(p.u_stage.ptr + i0 + lane + (int64_t)j * p.u_stage.sj) : T(0);
-        };
-        struct lvl {
-            T us, un, w0, w1, up, ut;
-        };
-        auto read_level = [&](const T *sd, int u) {
-            lvl v;
-            v.us = sd[u * 32 + lane], v.up = sd[(KC + u) * 32 + lane], v.ut = sd[(2 * KC + u) * 32 + lane];
-            v.un = sd[(3 * KC + u) * 32 + lane];
-            const T *wc = sd + 4 * KC * 32;
-            v.w0 = wc[u * L::ww + lane], v.w1 = wc[u * L::ww + lane + 1];
-            return v;
-        };
-
-        int item = gw;
-        T u0 = T(0);
-        if (item < p.items)
-            prime(item, u0);
-        for (; item < p.items; item += total) {
-            const int ti = item % p.tiles_i, j = item / p.tiles_i;
-            const int i0 = ti * 32, i = i0 + lane;
-            const bool active = i < p.ni;
-            va_state<T> st;
-            st.u_k = u0;
-            st.u_km1 = st.wsum_k = st.cc_prev = st.dc_prev = st.up_last = T(0);
-            T rc[NCR * KC], rd[NCR * KC]; // ccol / dcol of levels k_split .. (statically indexed: registers)
-            auto next_stage = [&](int c) { // refill the stage consumed in the previous iteration, wait for chunk c
-                if (c + S - 1 < nchunks)
-                    issue_f(i0, j, c + S - 1);
-                const int s = f_wait;
-                ptx::mbar_wait(&ffull[s], f_phase);
-                if (++f_wait == S) {
-                    f_wait = 0;
-                    f_phase ^= 1;
-                }
-                return reinterpret_cast<const T *>(fring + s * fstage);
-            };
-            // ------------------------------------------------ forward sweep, shared-memory tier (all body levels but k = 0)
-            for (int c = 0; c < c_split; ++c) {
-                const T *sd = next_stage(c);
-                T *q = ss + (int64_t)c * (KC * 2 * 32);
-#pragma unroll
-                for (int u = 0; u < KC; ++u) {
-                    lvl v = read_level(sd, u);
-                    T cc, dc;
-                    if (u == 0 && c == 0)
-                        va_forward_level<T>(0, 3, dtr, v.us, v.un, v.w0, v.w1, v.up, v.ut, st, cc, dc); // first, folded
-                    else
-                        va_forward_level<T>(1, 3, dtr, v.us, v.un, v.w0, v.w1, v.up, v.ut, st, cc, dc); // body, folded
-                    q[(u * 2) * 32] = cc;
-                    q[(u * 2 + 1) * 32] = dc;
-                }
-                __syncwarp(); // all lanes are done with the stage before lane 0 refills it
-            }
-            // ------------------------------------------------ forward sweep, register tier
-            // The chunk loop is NOT unrolled (48 unrolled levels overflow the instruction cache: the first version
-            // of this kernel stalled 1.5 cycles per issue on instruction fetch); a chunk's KC results are moved
-            // into the register arrays by a switch on the chunk number, whose cases index them statically.
-            const T *sd_last = nullptr;
-            for (int c = c_split; c < nchunks; ++c) {
-                const T *sd = next_stage(c);
-                sd_last = sd;
-                T ccv[KC], dcv[KC];
-                if (c != 0 && c < (nk - 1) / KC) {
-                    va_forward_body_chunk<T, KC>(
-                        dtr, st,
-                        [&](int u, T &us, T &un, T &w0, T &w1, T &up, T &ut) {
-                            lvl v = read_level(sd, u);
-                            us = v.us, un = v.un, w0 = v.w0, w1 = v.w1, up = v.up, ut = v.ut;
-                        },
-                        [&](int u, T cc, T dc, T) {
-                            ccv[u] = cc;
-                            dcv[u] = dc;
-                        });
-                } else {
-#pragma unroll
-                    for (int u = 0; u < KC; ++u) {
-                        const int k = c * KC + u;
-                        ccv[u] = dcv[u] = T(0);
-                        if (k < nk - 1) {
-                            lvl v = read_level(sd, u);
-                            if (k == 0)
-                                va_forward_level<T>(0, 3, dtr, v.us, v.un, v.w0, v.w1, v.up, v.ut, st, ccv[u], dcv[u]);
-                            else
-                                va_forward_level<T>(1, 3, dtr, v.us, v.un, v.w0, v.w1, v.up, v.ut, st, ccv[u], dcv[u]);
-                        }
-                    }
-                }
-                reg_tier<T, KC, NCR>::put(c - c_split, rc, rd, ccv, dcv);
-                if (c != nchunks - 1)
-                    __syncwarp(); // the stage of the last chunk is read once more below
-            }
-            // ------------------------------------------------ last level (:70-83) from the stage of the last chunk
-            {
-                const int u = nk - 1 - (nchunks - 1) * KC;
-                T us = sd_last[u * 32 + lane], up = sd_last[(KC + u) * 32 + lane], ut = sd_last[(2 * KC + u) * 32 + lane];
-                T cc, dc;
-                va_forward_level<T>(2, 3, dtr, us, T(0), T(0), T(0), up, ut, st, cc, dc); // last, folded
-                __syncwarp();
-            }
-            // ------------------------------------------------ backward sweep (u_backward_function)
-            for (int n = 0; n < SB - 1 && cb_top - n >= 0; ++n)
-                issue_b(i0, j, cb_top - n);
-            if (item + total < p.items) // HBM keeps streaming while this warp sweeps back
-                prime(item + total, u0);
-            const int64_t us_sk = p.utens_stage.sk;
-            T *o = p.utens_stage.ptr + i + (int64_t)j * p.utens_stage.sj + (int64_t)(nk - 1) * us_sk;
-            T data = st.dc_prev; // last_level :118-121
-            if (active)
-                *o = dtr * (data - st.up_last);
-            auto next_bstage = [&](int cb) {
-                if (cb - (SB - 1) >= 0)
-                    issue_b(i0, j, cb - (SB - 1));
-                const int s = b_wait;
-                ptx::mbar_wait(&bfull[s], b_phase);
-                if (++b_wait == SB) {
-                    b_wait = 0;
-                    b_phase ^= 1;
-                }
-                return reinterpret_cast<const T *>(bring + s * bstage) + lane;
-            };
-            for (int cb = cb_top; cb >= c_split; --cb) { // register tier
-                const T *sb = next_bstage(cb);
-                T ccv[KC], dcv[KC];
-                reg_tier<T, KC, NCR>::get(cb - c_split, rc, rd, ccv, dcv);
-#pragma unroll
-                for (int u = KC - 1; u >= 0; --u) { // body :111-116
-                    if (cb * KC + u <= nk - 2) {
-                        data = dcv[u] - ccv[u] * data;
-                        o -= us_sk;
-                        if (active)
-                            *o = dtr * (data - sb[u * 32]);
-                    }
-                }
-                __syncwarp();
-            }
-            for (int cb = c_split - 1; cb >= 0; --cb) { // shared-memory tier
-                const T *sb = next_bstage(cb);
-                const T *q = ss + (int64_t)cb * (KC * 2 * 32);
-#pragma unroll
-                for (int u = KC - 1; u >= 0; --u) {
-                    data = q[(u * 2 + 1) * 32] - q[(u * 2) * 32] * data;
-                    o -= us_sk;
-                    if (active)
-                        *o = dtr * (data - sb[u * 32]);
-                }
-                __syncwarp();
-            }
-        }
     }
 
     // ------------------------------------------------------------------ TMEM variant (va.variant = 5)
@@ -1108,11 +674,6 @@ namespace {
     };
 
     // shared memory: [warps][stages][fstage] | [warps][slab_bytes] | [warps][stages] mbarriers | TMEM base address
-    template <class T, int KC>
-    int va_tmem_smem(int warps, int stages, int slab_bytes) {
-        return warps * (stages * va_tma_layout<T>::template stage_bytes<KC>() + slab_bytes + stages * 8) + 16;
-    }
-
     __device__ __forceinline__ uint64_t globaltimer_ns() {
         uint64_t t;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -1122,531 +683,6 @@ namespace {
     // Strips are handed out dynamically: the first one is the warp's own number, the following ones come from a
     // ticket counter (one atomic per strip), so warps that start late (stagger) or run on a slower SM take fewer.
     // The last warp to finish resets the counters for the next launch on the stream.
-    template <class T, int KC, int NBC>
-    __global__ void __launch_bounds__(256, 1) va_tmem_kernel(const __grid_constant__ va_maps maps, const va_params<T> p) {
-        using L = va_tma_layout<T>;
-        using CFG = va_tmem_cfg<T>;
-        constexpr int es = L::es;
-        constexpr int fstage = L::template stage_bytes<KC>();
-        constexpr uint32_t ftx = KC * (4 * 32 + L::ww) * es;
-        constexpr int CPL = CFG::cpl;
-        constexpr int NW = KC * CPL; // 32-bit words of a chunk
-        extern __shared__ __align__(128) unsigned char smem_all[];
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, WARPS = blockDim.x >> 5;
-        const int S = p.stages;
-        const int slab_bytes = (int)p.slots; // per warp, multiple of 128
-        unsigned char *fring = smem_all + warp * (S * fstage);
-        T *const ss = reinterpret_cast<T *>(smem_all + WARPS * (S * fstage) + warp * slab_bytes) + lane; // [k][2][32]
-        uint64_t *ffull = reinterpret_cast<uint64_t *>(smem_all + WARPS * (S * fstage + slab_bytes)) + warp * S;
-        uint32_t *tslot = reinterpret_cast<uint32_t *>(smem_all + WARPS * (S * fstage + slab_bytes + S * 8));
-        if (lane == 0) {
-            for (int s = 0; s < S; ++s)
-                ptx::mbar_init(&ffull[s], 1);
-            ptx::fence_barrier_init();
-            if (warp == 0) {
-                ptx::prefetch_tensormap(&maps.us);
-                ptx::prefetch_tensormap(&maps.up);
-                ptx::prefetch_tensormap(&maps.ut);
-                ptx::prefetch_tensormap(&maps.un);
-                ptx::prefetch_tensormap(&maps.wc);
-            }
-        }
-        if (warp == 0)
-            tm::alloc(tslot, 512);
-        tm::fence_before();
-        __syncthreads();
-        tm::fence_after();
-        const uint32_t tbase = *tslot;
-        // this warp's window: lane quarter warp % 4, column half warp / 4
-        const uint32_t tw = tbase + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 256);
-
-        const int nk = p.nk;
-        const T dtr = p.dtr;
-        const int dbg = p.debug; // diagnosis only (va.debug): 1 skip backward, 8 skip output stores
-        const uint64_t pol_keep = ptx::policy_evict_last(), pol_stream = ptx::policy_evict_first();
-        const int gw = warp * gridDim.x + blockIdx.x, total = gridDim.x * WARPS;
-        const int nchunks = (nk + KC - 1) / KC;
-        const int c_tail = (nk - 1) / KC; // first forward chunk that needs per-level checks (holds level nk-1)
-        const int k_split = p.k_split, c_split = k_split / KC; // chunks [0, c_split) live in TMEM, the rest in the slab
-        const int cb_top = (nk - 2) / KC; // backward chunk that holds level nk-2
-        int f_issue = 0, f_wait = 0;
-        uint32_t f_phase = 0;
-
-        auto issue_f = [&](int i0, int j, int c) {
-            const int s = f_issue;
-            f_issue = f_issue + 1 == S ? 0 : f_issue + 1;
-            if (ptx::elect_one()) {
-                unsigned char *st = fring + s * fstage;
-                uint64_t *bar = &ffull[s];
-                ptx::mbar_expect_tx(bar, ftx);
-                ptx::tma_load_3d_hint(st, &maps.us, bar, i0, j, c * KC, pol_stream);
-                ptx::tma_load_3d_hint(st + KC * 32 * es, &maps.up, bar, i0, j, c * KC, pol_keep); // read again below
-                ptx::tma_load_3d_hint(st + 2 * KC * 32 * es, &maps.ut, bar, i0, j, c * KC, pol_stream);
-                ptx::tma_load_3d_hint(st + 3 * KC * 32 * es, &maps.un, bar, i0, j, c * KC + 1, pol_stream);
-                ptx::tma_load_3d_hint(st + 4 * KC * 32 * es, &maps.wc, bar, i0, j, c * KC + 1, pol_stream);
-            }
-        };
-        auto prime = [&](int item, T &u0) { // first S-1 forward chunks of a strip + u_stage(k = 0)
-            const int ti = item % p.tiles_i, j = item / p.tiles_i;
-            const int i0 = ti * 32;
-            for (int c = 0; c < S - 1 && c < nchunks; ++c)
-                issue_f(i0, j, c);
-            u0 = i0 + lane < p.ni ? __ldg(p.u_stage.ptr + i0 + lane + (int64_t)j * p.u_stage.sj) : T(0);
-        };
-        auto next_ticket = [&]() {
-            int t = 0;
-            if (lane == 0)
-                t = atomicAdd(p.tickets, 1);
-            return total + __shfl_sync(0xffffffffu, t, 0);
-        };
-        // chunk c of the k-cache: one TMEM store / load, or the shared-memory slab above the TMEM capacity
-        auto put_chunk = [&](int c, const T *ccv, const T *dcv) {
-            if (c < c_split) {
-                uint32_t w[NW];
-#pragma unroll
-                for (int u = 0; u < KC; ++u)
-                    tm::pack<T>(ccv[u], dcv[u], w + u * CPL);
-                tm::st<NW>(tw + (uint32_t)(c * NW), w);
-            } else {
-                T *q = ss + (c * KC - k_split) * 64;
-#pragma unroll
-                for (int u = 0; u < KC; ++u) {
-                    if (c * KC + u < nk - 1) {
-                        q[u * 64] = ccv[u];
-                        q[u * 64 + 32] = dcv[u];
-                    }
-                }
-            }
-        };
-        auto get_chunk = [&](int c, T *ccv, T *dcv) {
-            if (c < c_split) {
-                uint32_t w[NW];
-                tm::ld<NW>(tw + (uint32_t)(c * NW), w);
-                tm::wait_ld();
-#pragma unroll
-                for (int u = 0; u < KC; ++u)
-                    tm::unpack<T>(w + u * CPL, ccv[u], dcv[u]);
-            } else {
-                const T *q = ss + (c * KC - k_split) * 64;
-#pragma unroll
-                for (int u = 0; u < KC; ++u) {
-                    if (c * KC + u < nk - 1) {
-                        ccv[u] = q[u * 64];
-                        dcv[u] = q[u * 64 + 32];
-                    }
-                }
-            }
-        };
-
-        int item = gw;
-        T u0 = T(0);
-        if (item < p.items)
-            prime(item, u0);
-        if (p.stagger_ns > 0 && warp > 0) { // the ring is already filling; de-phase this warp's sweeps
-            const uint64_t until = globaltimer_ns() + (uint64_t)warp * (uint64_t)p.stagger_ns;
-            while (globaltimer_ns() < until)
-                __nanosleep(256);
-        }
-        while (item < p.items) {
-            const int ti = item % p.tiles_i, j = item / p.tiles_i;
-            const int i0 = ti * 32, i = i0 + lane;
-            const bool active = i < p.ni;
-            va_state<T> st;
-            st.u_k = u0;
-            st.u_km1 = st.wsum_k = st.cc_prev = st.dc_prev = st.up_last = T(0);
-            // ---------------------------------------------------------------- forward sweep (u_forward_function)
-            for (int c = 0; c < nchunks; ++c) {
-                if (c + S - 1 < nchunks) // refill the stage consumed in the previous iteration
-                    issue_f(i0, j, c + S - 1);
-                const int s = f_wait;
-                ptx::mbar_wait(&ffull[s], f_phase);
-                if (++f_wait == S) {
-                    f_wait = 0;
-                    f_phase ^= 1;
-                }
-                const T *sd = reinterpret_cast<const T *>(fring + s * fstage);
-                const T *wc = sd + 4 * KC * 32;
-                T ccv[KC], dcv[KC];
-                if (dbg & 2) { // diagnosis: traffic pattern without the forward arithmetic
-#pragma unroll
-                    for (int u = 0; u < KC; ++u) {
-                        ccv[u] = sd[u * 32 + lane] + sd[(KC + u) * 32 + lane] + wc[u * L::ww + lane + 1];
-                        dcv[u] = sd[(2 * KC + u) * 32 + lane] + sd[(3 * KC + u) * 32 + lane];
-                        st.dc_prev = dcv[u];
-                    }
-                } else if (c != 0 && c < c_tail) {
-                    va_forward_body_chunk<T, KC>(
-                        dtr, st,
-                        [&](int u, T &us, T &un, T &w0, T &w1, T &up, T &ut) {
-                            us = sd[u * 32 + lane], up = sd[(KC + u) * 32 + lane], ut = sd[(2 * KC + u) * 32 + lane];
-                            un = sd[(3 * KC + u) * 32 + lane];
-                            w0 = wc[u * L::ww + lane], w1 = wc[u * L::ww + lane + 1];
-                        },
-                        [&](int u, T cc, T dc, T) {
-                            ccv[u] = cc;
-                            dcv[u] = dc;
-                        });
-                } else {
-#pragma unroll
-                    for (int u = 0; u < KC; ++u) {
-                        const int k = c * KC + u;
-                        ccv[u] = dcv[u] = T(0);
-                        if (k < nk) {
-                            T us = sd[u * 32 + lane], up = sd[(KC + u) * 32 + lane], ut = sd[(2 * KC + u) * 32 + lane];
-                            T un = sd[(3 * KC + u) * 32 + lane];
-                            T w0 = wc[u * L::ww + lane], w1 = wc[u * L::ww + lane + 1];
-                            va_forward_level<T>(k, nk, dtr, us, un, w0, w1, up, ut, st, ccv[u], dcv[u]);
-                        }
-                    }
-                }
-                if (c <= cb_top)
-                    put_chunk(c, ccv, dcv);
-                __syncwarp(); // all lanes are done with stage s before lane 0 refills it
-            }
-            const int next = next_ticket();
-            // ---------------------------------------------------------------- backward sweep (u_backward_function)
-            if (dbg & 1) {
-                if (next < p.items)
-                    prime(next, u0);
-                if (active)
-                    p.utens_stage.ptr[i + (int64_t)j * p.utens_stage.sj] = st.dc_prev;
-                item = next;
-                continue;
-            }
-            const int64_t us_sk = p.utens_stage.sk, up_sk = p.u_pos.sk;
-            T *o = p.utens_stage.ptr + i + (int64_t)j * p.utens_stage.sj + (int64_t)(nk - 1) * us_sk;
-            const T *upp = p.u_pos.ptr + (active ? i : 0) + (int64_t)j * p.u_pos.sj;
-            // u_pos(k) of NBC chunks in flight (register ring, statically indexed): L2 hits, last use
-            T bu[NBC][KC];
-            auto load_upos = [&](int b, int cb) {
-                if (cb >= 0) {
-#pragma unroll
-                    for (int u = 0; u < KC; ++u)
-                        if (cb * KC + u <= nk - 2)
-                            bu[b][u] = ptx::ld_hint(upp + (int64_t)(cb * KC + u) * up_sk, pol_stream);
-                }
-            };
-#pragma unroll
-            for (int b = 0; b < NBC; ++b)
-                load_upos(b, cb_top - b);
-            if (next < p.items) // HBM keeps streaming while this warp sweeps back
-                prime(next, u0);
-            tm::wait_st(); // the forward sweep's TMEM stores have landed
-            T data = st.dc_prev; // last_level :118-121
-            if (active)
-                *o = dtr * (data - st.up_last);
-            for (int cb0 = cb_top; cb0 >= 0; cb0 -= NBC) {
-#pragma unroll
-                for (int b = 0; b < NBC; ++b) {
-                    const int cb = cb0 - b;
-                    if (cb >= 0) {
-                        T ccv[KC], dcv[KC];
-                        get_chunk(cb, ccv, dcv);
-#pragma unroll
-                        for (int u = KC - 1; u >= 0; --u) { // body :111-116
-                            if (cb * KC + u <= nk - 2) {
-                                if (dbg & 16) // diagnosis: no dependent chain in the backward sweep
-                                    data = dcv[u] - ccv[u];
-                                else
-                                    data = dcv[u] - ccv[u] * data;
-                                o -= us_sk;
-                                if (active && !(dbg & 8))
-                                    *o = dtr * (data - bu[b][u]);
-                            }
-                        }
-                        load_upos(b, cb - NBC);
-                    }
-                }
-            }
-            item = next;
-        }
-        if (lane == 0 && atomicAdd(p.tickets + 1, 1) == total - 1) { // every warp has drawn its last ticket
-            p.tickets[0] = 0;
-            p.tickets[1] = 0;
-            __threadfence();
-        }
-        tm::fence_before();
-        __syncthreads();
-        if (warp == 0)
-            tm::dealloc(tbase, 512);
-    }
-
-    // ------------------------------------------------------------------ fused-sweep TMEM variant (va.variant = 6)
-    // Variant 5 still runs the two sweeps of a strip one after the other, and every warp of the chip does so in
-    // lock-step: HBM is read for ~20 us, then nearly idle for ~5-10 us while the backward sweeps drain, twice per
-    // launch.  Both sweeps are latency-bound chains of dependent fp64 operations (forward ~10 per level through the
-    // reciprocal, backward 2 per level), so a warp can run them SIDE BY SIDE at no cost in issue slots: here the
-    // backward sweep of strip n is executed inside the forward loop of the warp's next strip n+1, chunk for chunk.
-    //  * One k-cache window serves both strips: at step c the backward sweep reads chunk cb_top-c of strip n out of
-    //    a physical slot, then the forward sweep of strip n+1 stores its chunk c into the slot just freed.  The
-    //    layout therefore alternates between natural and mirrored chunk order from strip to strip.
-    //  * u_pos(k) for the backward sweep arrives through a second small TMA ring (L2 hits: the forward load left the
-    //    lines evict_last), so the loop body needs no statically indexed register ring and is not unrolled.
-    //  * The TMA ring of the forward sweep never drains between strips; the output stores of strip n spread over the
-    //    whole forward sweep of strip n+1 instead of arriving as one burst.
-    // Only the first forward sweep and the last backward sweep of a warp run alone.
-    template <class T, int KC>
-    int va_fused_smem(int warps, int stages, int bstages, int slab_bytes) {
-        return warps * (stages * va_tma_layout<T>::template stage_bytes<KC>() + bstages * va_bstage_bytes<T, KC>() +
-                           slab_bytes + (stages + bstages) * 8) + 16;
-    }
-
-    template <class T, int KC>
-    __global__ void __launch_bounds__(256, 1) va_fused_kernel(const __grid_constant__ va_maps maps, const va_params<T> p) {
-        using L = va_tma_layout<T>;
-        using CFG = va_tmem_cfg<T>;
-        constexpr int es = L::es;
-        constexpr int fstage = L::template stage_bytes<KC>();
-        constexpr int bstage = va_bstage_bytes<T, KC>();
-        constexpr uint32_t ftx = KC * (4 * 32 + L::ww) * es;
-        constexpr uint32_t btx = KC * 32 * es;
-        constexpr int CPL = CFG::cpl;
-        constexpr int NW = KC * CPL; // 32-bit words of a chunk
-        extern __shared__ __align__(128) unsigned char smem_all[];
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, WARPS = blockDim.x >> 5;
-        const int S = p.stages, SB = p.bstages;
-        const int slab_bytes = (int)p.slots; // per warp, multiple of 128
-        const int per_warp = S * fstage + SB * bstage + slab_bytes;
-        unsigned char *fring = smem_all + warp * per_warp;
-        unsigned char *bring = fring + S * fstage;
-        T *const ss = reinterpret_cast<T *>(bring + SB * bstage) + lane; // [chunk][level][2][32]
-        uint64_t *ffull = reinterpret_cast<uint64_t *>(smem_all + WARPS * per_warp) + warp * (S + SB);
-        uint64_t *bfull = ffull + S;
-        uint32_t *tslot = reinterpret_cast<uint32_t *>(smem_all + WARPS * (per_warp + (S + SB) * 8));
-        if (lane == 0) {
-            for (int s = 0; s < S + SB; ++s)
-                ptx::mbar_init(&ffull[s], 1);
-            ptx::fence_barrier_init();
-            if (warp == 0) {
-                ptx::prefetch_tensormap(&maps.us);
-                ptx::prefetch_tensormap(&maps.up);
-                ptx::prefetch_tensormap(&maps.ut);
-                ptx::prefetch_tensormap(&maps.un);
-                ptx::prefetch_tensormap(&maps.wc);
-            }
-        }
-        if (warp == 0)
-            tm::alloc(tslot, 512);
-        tm::fence_before();
-        __syncthreads();
-        tm::fence_after();
-        const uint32_t tbase = *tslot;
-        const uint32_t tw = tbase + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 256);
-
-        const int nk = p.nk;
-        const T dtr = p.dtr;
-        const uint64_t pol_keep = ptx::policy_evict_last(), pol_stream = ptx::policy_evict_first();
-        const int gw = warp * gridDim.x + blockIdx.x, total = gridDim.x * WARPS;
-        const int nchunks = (nk + KC - 1) / KC;
-        const int c_tail = (nk - 1) / KC; // first forward chunk that needs per-level checks (holds level nk-1)
-        const int c_split = p.k_split / KC; // physical chunks [0, c_split) live in TMEM, the rest in the slab
-        const int cb_top = (nk - 2) / KC;   // last stored chunk (holds level nk-2)
-        const int64_t us_sk = p.utens_stage.sk;
-        int f_issue = 0, f_wait = 0, b_issue = 0, b_wait = 0;
-        uint32_t f_phase = 0, b_phase = 0;
-
-        auto issue_f = [&](int i0, int j, int c) {
-            const int s = f_issue;
-            f_issue = f_issue + 1 == S ? 0 : f_issue + 1;
-            if (ptx::elect_one()) {
-                unsigned char *st = fring + s * fstage;
-                uint64_t *bar = &ffull[s];
-                ptx::mbar_expect_tx(bar, ftx);
-                ptx::tma_load_3d_hint(st, &maps.us, bar, i0, j, c * KC, pol_stream);
-                ptx::tma_load_3d_hint(st + KC * 32 * es, &maps.up, bar, i0, j, c * KC, pol_keep); // read again by issue_b
-                ptx::tma_load_3d_hint(st + 2 * KC * 32 * es, &maps.ut, bar, i0, j, c * KC, pol_stream);
-                ptx::tma_load_3d_hint(st + 3 * KC * 32 * es, &maps.un, bar, i0, j, c * KC + 1, pol_stream);
-                ptx::tma_load_3d_hint(st + 4 * KC * 32 * es, &maps.wc, bar, i0, j, c * KC + 1, pol_stream);
-            }
-        };
-        auto issue_b = [&](int i0, int j, int cb) {
-            const int s = b_issue;
-            b_issue = b_issue + 1 == SB ? 0 : b_issue + 1;
-            if (ptx::elect_one()) {
-                ptx::mbar_expect_tx(&bfull[s], btx);
-                ptx::tma_load_3d_hint(bring + s * bstage, &maps.up, &bfull[s], i0, j, cb * KC, pol_stream);
-            }
-        };
-        auto prime = [&](int item, T &u0) { // first S-1 forward chunks of a strip + u_stage(k = 0)
-            const int ti = item % p.tiles_i, j = item / p.tiles_i;
-            const int i0 = ti * 32;
-            for (int c = 0; c < S - 1 && c < nchunks; ++c)
-                issue_f(i0, j, c);
-            u0 = i0 + lane < p.ni ? __ldg(p.u_stage.ptr + i0 + lane + (int64_t)j * p.u_stage.sj) : T(0);
-        };
-        auto next_ticket = [&]() {
-            int t = 0;
-            if (lane == 0)
-                t = atomicAdd(p.tickets, 1);
-            return total + __shfl_sync(0xffffffffu, t, 0);
-        };
-        // physical chunk slot `ph` of the k-cache window; `c` is the logical chunk (for the level bound)
-        auto put_chunk = [&](int ph, int c, const T *ccv, const T *dcv) {
-            if (ph < c_split) {
-                uint32_t w[NW];
-#pragma unroll
-                for (int u = 0; u < KC; ++u)
-                    tm::pack<T>(ccv[u], dcv[u], w + u * CPL);
-                tm::st<NW>(tw + (uint32_t)(ph * NW), w);
-            } else {
-                T *q = ss + (ph - c_split) * (KC * 64);
-#pragma unroll
-                for (int u = 0; u < KC; ++u) {
-                    if (c * KC + u < nk - 1) {
-                        q[u * 64] = ccv[u];
-                        q[u * 64 + 32] = dcv[u];
-                    }
-                }
-            }
-        };
-        auto get_chunk = [&](int ph, int c, T *ccv, T *dcv) {
-            if (ph < c_split) {
-                uint32_t w[NW];
-                tm::ld<NW>(tw + (uint32_t)(ph * NW), w);
-                tm::wait_ld();
-#pragma unroll
-                for (int u = 0; u < KC; ++u)
-                    tm::unpack<T>(w + u * CPL, ccv[u], dcv[u]);
-            } else {
-                const T *q = ss + (ph - c_split) * (KC * 64);
-#pragma unroll
-                for (int u = 0; u < KC; ++u) {
-                    ccv[u] = dcv[u] = T(0);
-                    if (c * KC + u < nk - 1) {
-                        ccv[u] = q[u * 64];
-                        dcv[u] = q[u * 64 + 32];
-                    }
-                }
-            }
-        };
-
-        int item = gw;
-        T u0 = T(0);
-        if (item < p.items)
-            prime(item, u0);
-        // backward state of the previous strip of this warp
-        bool have_prev = false;
-        int b_i0 = 0, b_j = 0;
-        bool b_active = false;
-        T data = T(0);
-        T *o = nullptr;
-        int mirrored = 0; // chunk order in which the strip whose forward sweep runs now stores its k-cache
-
-        while (item < p.items || have_prev) {
-            const bool do_f = item < p.items;
-            int i0 = 0, j = 0;
-            if (do_f) {
-                const int ti = item % p.tiles_i;
-                j = item / p.tiles_i;
-                i0 = ti * 32;
-            }
-            va_state<T> st;
-            st.u_k = u0;
-            st.u_km1 = st.wsum_k = st.cc_prev = st.dc_prev = st.up_last = T(0);
-            const int nsteps = do_f ? nchunks : cb_top + 1;
-            for (int c = 0; c < nsteps; ++c) {
-                const bool do_b = have_prev && c <= cb_top;
-                const int ph = mirrored ? cb_top - c : c; // slot the backward sweep frees and the forward sweep fills
-                const int cb = cb_top - c;                // logical chunk of the backward sweep
-                // ---------------- backward: chunk cb of the previous strip out of the k-cache
-                T bcc[KC], bdc[KC];
-                const T *sb = nullptr;
-                if (do_b) {
-                    if (cb - (SB - 1) >= 0)
-                        issue_b(b_i0, b_j, cb - (SB - 1));
-                    get_chunk(ph, cb, bcc, bdc);
-                }
-                // ---------------- forward: chunk c of the current strip
-                T ccv[KC], dcv[KC];
-                if (do_f) {
-                    if (c + S - 1 < nchunks) // refill the stage consumed in the previous iteration
-                        issue_f(i0, j, c + S - 1);
-                    const int s = f_wait;
-                    ptx::mbar_wait(&ffull[s], f_phase);
-                    if (++f_wait == S) {
-                        f_wait = 0;
-                        f_phase ^= 1;
-                    }
-                    const T *sd = reinterpret_cast<const T *>(fring + s * fstage);
-                    const T *wc = sd + 4 * KC * 32;
-                    if (c != 0 && c < c_tail) {
-                        va_forward_body_chunk<T, KC>(
-                            dtr, st,
-                            [&](int u, T &us, T &un, T &w0, T &w1, T &up, T &ut) {
-                                us = sd[u * 32 + lane], up = sd[(KC + u) * 32 + lane], ut = sd[(2 * KC + u) * 32 + lane];
-                                un = sd[(3 * KC + u) * 32 + lane];
-                                w0 = wc[u * L::ww + lane], w1 = wc[u * L::ww + lane + 1];
-                            },
-                            [&](int u, T cc, T dc, T) {
-                                ccv[u] = cc;
-                                dcv[u] = dc;
-                            });
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < KC; ++u) {
-                            const int k = c * KC + u;
-                            ccv[u] = dcv[u] = T(0);
-                            if (k < nk) {
-                                T us = sd[u * 32 + lane], up = sd[(KC + u) * 32 + lane], ut = sd[(2 * KC + u) * 32 + lane];
-                                T un = sd[(3 * KC + u) * 32 + lane];
-                                T w0 = wc[u * L::ww + lane], w1 = wc[u * L::ww + lane + 1];
-                                va_forward_level<T>(k, nk, dtr, us, un, w0, w1, up, ut, st, ccv[u], dcv[u]);
-                            }
-                        }
-                    }
-                }
-                // ---------------- backward: levels of chunk cb, top down (u_backward_function body :111-116)
-                if (do_b) {
-                    const int s = b_wait;
-                    ptx::mbar_wait(&bfull[s], b_phase);
-                    if (++b_wait == SB) {
-                        b_wait = 0;
-                        b_phase ^= 1;
-                    }
-                    sb = reinterpret_cast<const T *>(bring + s * bstage) + lane;
-#pragma unroll
-                    for (int u = KC - 1; u >= 0; --u) {
-                        if (cb * KC + u <= nk - 2) {
-                            data = bdc[u] - bcc[u] * data;
-                            o -= us_sk;
-                            if (b_active)
-                                *o = dtr * (data - sb[u * 32]);
-                        }
-                    }
-                }
-                if (do_f && c <= cb_top)
-                    put_chunk(ph, c, ccv, dcv);
-                __syncwarp(); // all lanes are done with the ring stages before one lane refills them
-            }
-            have_prev = false;
-            if (do_f) { // this strip's backward sweep runs inside the next pass
-                have_prev = true;
-                b_i0 = i0, b_j = j;
-                b_active = i0 + lane < p.ni;
-                o = p.utens_stage.ptr + (b_active ? i0 + lane : 0) + (int64_t)j * p.utens_stage.sj + (int64_t)(nk - 1) * us_sk;
-                data = st.dc_prev; // last_level :118-121
-                if (b_active)
-                    *o = dtr * (data - st.up_last);
-                for (int n = 0; n < SB - 1 && cb_top - n >= 0; ++n)
-                    issue_b(i0, j, cb_top - n);
-                item = next_ticket();
-                if (item < p.items)
-                    prime(item, u0);
-                tm::wait_st(); // this strip's TMEM stores have landed before the next pass reads them
-                mirrored ^= 1;
-            }
-        }
-        if (lane == 0 && atomicAdd(p.tickets + 1, 1) == total - 1) { // every warp has drawn its last ticket
-            p.tickets[0] = 0;
-            p.tickets[1] = 0;
-            __threadfence();
-        }
-        tm::fence_before();
-        __syncthreads();
-        if (warp == 0)
-            tm::dealloc(tbase, 512);
-    }
-
     // ------------------------------------------------------------------ paired-warp TMEM variant (va.variant = 7)
     // What the debug knobs of variant 5 show (tools/va_dbg.py, profiles/README.md): with ALL arithmetic removed the
     // kernel still takes 58 of its 60 us -- 37 us for streaming the forward inputs, 9 us for the backward sweeps'
@@ -2166,22 +1202,6 @@ namespace {
                          : dispatch_unroll<T, SMEM, false, false>(p, unroll, threads, smem, grid, stream);
     }
 
-    template <class T, int KC, int S, int WARPS, int NS>
-    int launch_va_tma(const va_maps &maps, const va_params<T> &p, int grid, cudaStream_t stream) {
-        using L = va_tma_layout<T>;
-        auto kernel = va_tma_kernel<T, KC, S, WARPS, NS>;
-        const int smem = WARPS * (S * L::template stage_bytes<KC>() + S * 8);
-        static thread_local int done_dev = -1;
-        if (done_dev != dev()->device) {
-            GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            done_dev = dev()->device;
-        }
-        kernel<<<grid, WARPS * 32, smem, stream>>>(maps, p);
-        count_launch();
-        return check_launch("va_tma_kernel");
-    }
-
     template <class T, int KC, int S, int NB, int NS>
     int launch_va_stream(const va_maps &maps, const va_params<T> &p, int grid, cudaStream_t stream) {
         auto kernel = va_stream_kernel<T, KC, S, NB, NS>;
@@ -2227,63 +1247,6 @@ namespace {
         }
     }
 
-    template <class T>
-    struct va_resident_cfg { // levels of ccol/dcol a thread keeps in registers
-        static constexpr int rmax = sizeof(T) == 8 ? 48 : 80;
-    };
-
-    template <class T, int KC, int S, int SB>
-    int va_resident_smem(int k_split) {
-        return S * va_tma_layout<T>::template stage_bytes<KC>() + SB * va_bstage_bytes<T, KC>() + 128 +
-               k_split * 2 * 32 * (int)sizeof(T);
-    }
-
-    template <class T, int KC, int S, int SB>
-    int launch_va_resident(const va_maps &maps, const va_params<T> &p, int grid, cudaStream_t stream) {
-        auto kernel = va_resident_kernel<T, KC, S, SB, va_resident_cfg<T>::rmax>;
-        const int smem = va_resident_smem<T, KC, S, SB>(p.k_split);
-        static thread_local int done_dev = -1;
-        if (done_dev != dev()->device) {
-            GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev()->max_smem_optin));
-            GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            done_dev = dev()->device;
-        }
-        kernel<<<grid, 32, smem, stream>>>(maps, p);
-        count_launch();
-        return check_launch("va_resident_kernel");
-    }
-
-    // Resident variant: kc/stages pick the ring shape; returns -1 if the shared-memory slab does not leave room for
-    // `wps` warps per SM (the caller then uses the L2-slab variant 3 unless variant 4 was requested explicitly).
-    template <class T>
-    int vert_adv_resident(va_params<T> &p, const options &o, device_state *d, const va_maps &maps, int kc, int wps,
-        int grid, bool forced, cudaStream_t stream) {
-        constexpr int rmax = va_resident_cfg<T>::rmax;
-        int k_split = p.nk - 1 - rmax;
-        k_split = k_split <= 0 ? 0 : ceil_div(k_split, kc) * kc;
-        p.k_split = k_split;
-        int smem;
-        const int stages = o.va_stages;
-        if (kc == 2)
-            smem = stages == 4 ? va_resident_smem<T, 2, 4, 3>(k_split) : va_resident_smem<T, 2, 5, 3>(k_split);
-        else
-            smem = stages == 2 ? va_resident_smem<T, 4, 2, 2>(k_split)
-                               : (stages == 4 ? va_resident_smem<T, 4, 4, 4>(k_split) : va_resident_smem<T, 4, 3, 2>(k_split));
-        if (smem > d->max_smem_optin)
-            return -1;
-        if (!forced && (int64_t)wps * (smem + 1024) > (int64_t)228 * 1024)
-            return -1;
-        int st = set_l2_persist(0);
-        if (st)
-            return st;
-        if (kc == 2)
-            return stages == 4 ? launch_va_resident<T, 2, 4, 3>(maps, p, grid, stream)
-                               : launch_va_resident<T, 2, 5, 3>(maps, p, grid, stream);
-        return stages == 2 ? launch_va_resident<T, 4, 2, 2>(maps, p, grid, stream)
-                           : (stages == 4 ? launch_va_resident<T, 4, 4, 4>(maps, p, grid, stream)
-                                          : launch_va_resident<T, 4, 3, 2>(maps, p, grid, stream));
-    }
-
     constexpr int kTraceEvents = 32, kTraceSlots = 2048;
     constexpr size_t kTraceBytes = (size_t)kTraceSlots * kTraceEvents * sizeof(long long);
 
@@ -2318,106 +1281,6 @@ namespace {
     // va.threads (re-used) = start stagger between the warps of a CTA in units of 100 ns.  Returns -1 when the
     // shared-memory slab for the levels above the TMEM capacity does not fit (tall columns): the caller then uses
     // variant 3.
-    template <class T>
-    int vert_adv_tmem(va_params<T> &p, const options &o, device_state *d, const va_maps &maps, cudaStream_t stream) {
-        constexpr int KC = 4;
-        const int warps = o.va_ctas_per_sm >= 4 && o.va_ctas_per_sm <= 8 ? o.va_ctas_per_sm : 8;
-        const int levels = va_tmem_cfg<T>::levels(warps);
-        const int cb_top = (p.nk - 2) / KC;
-        int k_split = (cb_top + 1) * KC;
-        if (k_split > levels)
-            k_split = levels;
-        p.k_split = k_split;
-        const int slab_levels = p.nk - 1 - k_split > 0 ? p.nk - 1 - k_split : 0;
-        const int slab_bytes = (slab_levels * 64 * (int)sizeof(T) + 127) / 128 * 128;
-        p.slots = slab_bytes;
-        p.scratch = nullptr;
-        p.persistent = 1;
-        int stages = o.va_stages >= 2 && o.va_stages <= 16 ? o.va_stages : 0;
-        if (stages == 0)
-            for (stages = 8; stages > 2 && va_tmem_smem<T, KC>(warps, stages, slab_bytes) > d->max_smem_optin;)
-                --stages;
-        const int smem = va_tmem_smem<T, KC>(warps, stages, slab_bytes);
-        if (smem > d->max_smem_optin)
-            return -1;
-        p.stages = stages;
-        p.stagger_ns = o.va_stagger > 0 ? o.va_stagger * 100 : 0;
-        p.tickets = va_ticket_counters();
-        p.trace = reinterpret_cast<long long *>(reinterpret_cast<char *>(va_ticket_base()) + 256);
-        if (!p.tickets)
-            return GTB_ERR_ALLOC;
-        const int64_t strips = (int64_t)p.tiles_i * p.nj;
-        int grid = o.va_ctas_per_sm < 0 ? -o.va_ctas_per_sm : stencil_sms(d);
-        if ((int64_t)grid * warps > strips)
-            grid = (int)((strips + warps - 1) / warps);
-        int st = set_l2_persist(0);
-        if (st)
-            return st;
-        auto kernel = va_tmem_kernel<T, KC, 8>;
-        static thread_local int done_dev = -1;
-        if (done_dev != d->device) {
-            GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->max_smem_optin));
-            GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            done_dev = d->device;
-        }
-        kernel<<<grid, warps * 32, smem, stream>>>(maps, p);
-        count_launch();
-        return check_launch("va_tmem_kernel");
-    }
-
-    // Fused-sweep TMEM variant (va.variant = 6): same knobs as variant 5 (va.ctas_per_sm = warps per CTA, va.stages =
-    // forward ring depth), va.unroll = depth of the backward u_pos ring (default 4).
-    template <class T>
-    int vert_adv_fused(va_params<T> &p, const options &o, device_state *d, const va_maps &maps, cudaStream_t stream) {
-        constexpr int KC = 4;
-        const int warps = o.va_ctas_per_sm >= 4 && o.va_ctas_per_sm <= 8 ? o.va_ctas_per_sm : 8;
-        const int levels = va_tmem_cfg<T>::levels(warps);
-        const int cb_top = (p.nk - 2) / KC;
-        int k_split = (cb_top + 1) * KC;
-        if (k_split > levels)
-            k_split = levels;
-        p.k_split = k_split;
-        const int slab_bytes = (cb_top + 1 - k_split / KC) * KC * 64 * (int)sizeof(T);
-        p.slots = slab_bytes;
-        p.scratch = nullptr;
-        p.persistent = 1;
-        const int bstages = o.va_unroll >= 2 && o.va_unroll <= 8 ? o.va_unroll : 4;
-        int stages = o.va_stages >= 2 && o.va_stages <= 16 ? o.va_stages : 0;
-        if (stages == 0)
-            for (stages = 6; stages > 2 && va_fused_smem<T, KC>(warps, stages, bstages, slab_bytes) > d->max_smem_optin;)
-                --stages;
-        const int smem = va_fused_smem<T, KC>(warps, stages, bstages, slab_bytes);
-        if (smem > d->max_smem_optin)
-            return -1;
-        p.stages = stages;
-        p.bstages = bstages;
-        p.stagger_ns = 0;
-        p.tickets = va_ticket_counters();
-        p.trace = reinterpret_cast<long long *>(reinterpret_cast<char *>(va_ticket_base()) + 256);
-        if (!p.tickets)
-            return GTB_ERR_ALLOC;
-        const int64_t strips = (int64_t)p.tiles_i * p.nj;
-        int grid = o.va_ctas_per_sm < 0 ? -o.va_ctas_per_sm : stencil_sms(d);
-        if ((int64_t)grid * warps > strips)
-            grid = (int)((strips + warps - 1) / warps);
-        int st = set_l2_persist(0);
-        if (st)
-            return st;
-        auto kernel = va_fused_kernel<T, KC>;
-        static thread_local int done_dev = -1;
-        if (done_dev != d->device) {
-            GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->max_smem_optin));
-            GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            done_dev = d->device;
-        }
-        kernel<<<grid, warps * 32, smem, stream>>>(maps, p);
-        count_launch();
-        return check_launch("va_fused_kernel");
-    }
-
-    // Paired-warp TMEM variant (va.variant = 7): va.ctas_per_sm = F/B warp pairs in use per CTA (1..8, 0 = auto;
-    // < 0: an absolute number of CTAs, tests), va.stages = forward ring depth, va.unroll = depth of the
-    // (no further knobs).
     template <class T>
     int vert_adv_pair(va_params<T> &p, const options &o, device_state *d, const va_maps &maps, cudaStream_t stream) {
         constexpr int KC = 4;
@@ -2488,35 +1351,34 @@ namespace {
 
     // Persistent one-warp CTAs over the 32-column strips.  va.variant 2: per-warp TMA ring + per-thread slab loads;
     // 3 (and auto): two-ring streaming kernel.  va.ctas_per_sm > 0: warps per SM, < 0: absolute grid size (tests).
+    // The TMA kernels: va.variant 0 (auto) = the paired-warp TMEM kernel for fp64 (fastest measured, profiles/README.md)
+    // and, for fp32 -- where a strip moves half the bytes and the sweep is latency-bound -- and for columns too tall
+    // for TMEM + shared memory, the one-warp streaming kernel with its L2 slab (variant 3).  Variants 2, 4, 5 and 6 of
+    // round 1 (first TMA version, register-resident k cache, one-warp TMEM, fused-sweep TMEM) were the measured-slower
+    // steps towards variant 7 and have been removed.
     template <class T>
     int vert_adv_tma(va_params<T> &p, const options &o, device_state *d, cudaStream_t stream, bool *done) {
         *done = false;
-        const bool stream_variant = o.va_variant != 2;
-        const bool resident = o.va_variant == 4; // (auto = variant 3: measured fastest, see profiles/README.md)
-        // auto: the paired-warp TMEM kernel for fp64 (fastest measured, profiles/README.md); for fp32, where a strip moves
-        // half the bytes and the sweep is latency-bound, the one-warp streaming kernel with its L2 slab
-        const int tm_variant = o.va_variant == 0 ? (sizeof(T) == 8 ? 7 : 0) : o.va_variant;
-        const bool tmem = tm_variant >= 5 && tm_variant <= 7;
-        int kc = o.va_unroll == 8 && !tmem ? 8 : (o.va_unroll == 2 && !stream_variant ? 2 : 4);
-        if (resident && !tmem) // auto: 2-level stages for fp64 (shared memory is what limits the warps per SM), 4 for fp32
-            kc = o.va_unroll == 2 ? 2 : (o.va_unroll == 4 ? 4 : (sizeof(T) == 8 ? 2 : 4));
+        if (o.va_variant == 2 || (o.va_variant >= 4 && o.va_variant <= 6))
+            return fail(GTB_ERR_ARG, "gtb_vert_adv: va.variant=%d was removed (use 0 = auto, 1 = LDG fallback, 3 = "
+                                     "streaming warps with an L2 slab, 7 = paired warps with the k cache in TMEM)", o.va_variant);
+        const int tm_variant = o.va_variant == 0 ? (sizeof(T) == 8 ? 7 : 3) : o.va_variant;
+        const int kc = 4; // levels per TMA stage
         p.kc = kc;
         p.debug = o.va_debug;
         va_maps maps;
         if (!make_va_maps<T>(maps, p))
             return GTB_OK; // not addressable: the caller falls back to the register-prefetch kernel
-        const int wps = o.va_ctas_per_sm > 0 ? o.va_ctas_per_sm : 7; // warps per SM
+        const int wps = o.va_ctas_per_sm > 0 ? o.va_ctas_per_sm : 7; // warps per SM (variant 3)
         const int64_t strips = (int64_t)p.tiles_i * p.nj;
         p.items = (int)strips;
         int grid = o.va_ctas_per_sm < 0 ? -o.va_ctas_per_sm : wps * stencil_sms(d);
         if (grid > strips)
             grid = (int)strips;
-        if (!tmem && (p.gate.wait_flag || p.gate.post))
+        if (tm_variant != 7 && (p.gate.wait_flag || p.gate.post))
             return fail(GTB_ERR_ARG, "gtb_vert_adv: a gate needs the paired-warp kernel");
-        if (tmem) {
-            int st = tm_variant == 7 ? vert_adv_pair<T>(p, o, d, maps, stream)
-                                     : (tm_variant == 6 ? vert_adv_fused<T>(p, o, d, maps, stream)
-                                                        : vert_adv_tmem<T>(p, o, d, maps, stream));
+        if (tm_variant == 7) {
+            int st = vert_adv_pair<T>(p, o, d, maps, stream);
             if (st >= 0) {
                 *done = true;
                 return st;
@@ -2524,34 +1386,10 @@ namespace {
             if (p.gate.wait_flag || p.gate.post)
                 return fail(GTB_ERR_ARG, "gtb_vert_adv: a gate needs the paired-warp kernel, which cannot hold nk = %d levels", p.nk);
         }
-        if (resident) {
-            p.scratch = nullptr;
-            p.slots = 0;
-            p.persistent = 1;
-            int st = vert_adv_resident<T>(p, o, d, maps, kc, wps, grid, o.va_variant == 4, stream);
-            if (st >= 0) {
-                *done = true;
-                return st;
-            }
-            if (o.va_variant == 4)
-                return fail(GTB_ERR_ARG, "gtb_vert_adv: va.variant=4 needs more shared memory than an SM has for nk=%d", p.nk);
-            if (kc != 4) { // variant 3 streams 4-level stages
-                kc = 4;
-                p.kc = kc;
-                if (!make_va_maps<T>(maps, p))
-                    return GTB_OK;
-            }
-        }
         const bool save_upos = o.va_save_upos != 2;
         const int ns = save_upos ? 3 : 2;
-        int64_t slab_elems; // whole scratch
-        if (stream_variant) {
-            p.slots = (int64_t)p.nk * ns * 32; // one contiguous slab per warp
-            slab_elems = p.slots * grid;
-        } else {
-            p.slots = (int64_t)grid * 32;
-            slab_elems = (int64_t)ns * p.nk * p.slots;
-        }
+        p.slots = (int64_t)p.nk * ns * 32; // one contiguous slab per warp
+        const int64_t slab_elems = p.slots * grid;
         p.scratch = static_cast<T *>(scratch((size_t)slab_elems * sizeof(T), stream));
         if (!p.scratch)
             return GTB_ERR_ALLOC;
@@ -2563,28 +1401,8 @@ namespace {
             if (st)
                 return st;
         }
-        if (stream_variant)
-            return save_upos ? dispatch_va_stream<T, 3>(maps, p, kc, o.va_stages, o.va_threads / 32, grid, stream)
-                             : dispatch_va_stream<T, 2>(maps, p, kc, o.va_stages, o.va_threads / 32, grid, stream);
-        if (save_upos) {
-            switch (kc) {
-            case 2:
-                return launch_va_tma<T, 2, 6, 1, 3>(maps, p, grid, stream);
-            case 8:
-                return launch_va_tma<T, 8, 3, 1, 3>(maps, p, grid, stream);
-            default:
-                return o.va_stages == 6 ? launch_va_tma<T, 4, 6, 1, 3>(maps, p, grid, stream)
-                                        : launch_va_tma<T, 4, 4, 1, 3>(maps, p, grid, stream);
-            }
-        }
-        switch (kc) {
-        case 2:
-            return launch_va_tma<T, 2, 6, 1, 2>(maps, p, grid, stream);
-        case 8:
-            return launch_va_tma<T, 8, 3, 1, 2>(maps, p, grid, stream);
-        default:
-            return launch_va_tma<T, 4, 4, 1, 2>(maps, p, grid, stream);
-        }
+        return save_upos ? dispatch_va_stream<T, 3>(maps, p, kc, o.va_stages, o.va_threads / 32, grid, stream)
+                         : dispatch_va_stream<T, 2>(maps, p, kc, o.va_stages, o.va_threads / 32, grid, stream);
     }
 
     template <class T>

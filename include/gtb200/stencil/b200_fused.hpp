@@ -122,7 +122,7 @@ namespace gridtools {
                 // the prefetch turns that into a bandwidth problem without touching the user functors.
                 template <int_t BI = 32,
                     int_t BJ = 8,
-                    int_t KB = 8,
+                    int_t KB = 4, // (r02_fused_timing.txt: horizontal diffusion 46.8 us with 4 levels per CTA, 49.2 with 8, 61.6 with 16)
                     int_t SweepUnroll = 3,
                     bool ChainSweeps = true,
                     int_t Prefetch = 4,
@@ -271,12 +271,18 @@ namespace gridtools {
                 template <class T>
                 struct is_staged_type : std::bool_constant<std::is_same<T, double>::value || std::is_same<T, float>::value> {};
 
-                // a raw pointer to T with i (unit), j and k strides behind the placeholder?
+                // a raw pointer to T with i (unit), j and k strides -- and no further dimension -- behind the placeholder?
+                template <class Key>
+                using is_ijk_key = std::bool_constant<std::is_same<Key, dim::i>::value || std::is_same<Key, dim::j>::value ||
+                                                      std::is_same<Key, dim::k>::value ||
+                                                      std::is_same<Key, sid::blocked_dim<dim::i>>::value ||
+                                                      std::is_same<Key, sid::blocked_dim<dim::j>>::value>;
                 template <class Sid, class = void>
                 struct is_stageable_sid : std::false_type {};
                 template <class Sid>
                 struct is_stageable_sid<Sid,
                     std::enable_if_t<std::is_pointer<sid::ptr_type<Sid>>::value &&
+                                     meta::all_of<is_ijk_key, get_keys<sid::strides_type<Sid>>>::value &&
                                      has_key<sid::strides_type<Sid>, dim::i>::value &&
                                      has_key<sid::strides_type<Sid>, dim::j>::value &&
                                      has_key<sid::strides_type<Sid>, dim::k>::value>>

@@ -47,6 +47,6 @@ if [ "$STEP" = generic ]; then
   timeout 120 tests/_build/b200_generic > gpurun_out/b200_generic.txt 2>&1; tail -n 1 gpurun_out/b200_generic.txt
   timeout 120 tests/_build/gpu_incumbent > gpurun_out/incumbent.txt 2>&1; cat gpurun_out/incumbent.txt
   timeout 120 tests/_build/fused_timing > gpurun_out/fused_timing.txt 2>&1; cat gpurun_out/fused_timing.txt
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:mss_kernel -s 6 -c 2 -f -o gpurun_out/prof_fused \
-      tests/_build/gpu_incumbent > gpurun_out/ncu_fused.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:mss_kernel -s 20 -c 2 -f -o gpurun_out/prof_fused \
+      tests/_build/fused_timing > gpurun_out/ncu_fused.log 2>&1
 fi
