@@ -47,12 +47,10 @@
 #include <gridtools/gcl/halo_exchange.hpp>
 
 #include "../../gtb200.h"
+#include "arch.hpp"
 
 namespace gridtools {
     namespace gcl {
-        /// Indicates that the data lives on a B200 and is exchanged by libgtb200 (next to gcl::cpu and gcl::gpu).
-        struct b200 {};
-
         namespace b200_impl_ {
             inline void check(int status, const char *what) {
                 if (status != GTB_OK)

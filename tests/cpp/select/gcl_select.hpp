@@ -14,6 +14,7 @@
 #define GT_TIMER_CUDA
 #endif
 #include <gridtools/gcl/halo_exchange.hpp>
+#include <gtb200/boundaries/b200.hpp>
 #include <gtb200/gcl/b200.hpp>
 namespace {
     using gcl_arch_t = gridtools::gcl::b200;

@@ -5,8 +5,9 @@ oracle/mpi_shim (MPI, threads as ranks), plus the one block a maintainer adds to
 
   gcl_reference_cpu    tests/regression/gcl/test_halo_exchange_3D.cpp on the reference's gcl::cpu: proves the stand-ins
   gcl_reference_b200   the same source with gcl_arch_t = gridtools::gcl::b200 (only the arch tag differs)
-  regression_b200      tests/regression/*.cpp (18 sources) + tests/src/regression_main.cpp with
+  regression_b200      tests/regression/*.cpp (19 sources) + tests/src/regression_main.cpp with
                        stencil_backend_t = gridtools::stencil::b200<>, no registration lines: the generic fused path
+                       (incl. boundary_conditions.cpp with gcl_arch_t = gridtools::gcl::b200)
 """
 import os
 import subprocess
@@ -78,3 +79,13 @@ def test_reference_regression_sources_bind_to_the_named_kernels():
     # prepare_tracers chunks of 2 and 1 (double; float has no kernel: generic)
     kinds = {l.split("kernel id ")[1].split(",")[0] for l in named}
     assert kinds >= {"1", "2", "3", "4", "5", "6", "7"}, (sorted(kinds), generic, tail)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ranks", [1, 4])
+def test_reference_boundary_unit_tests_pass_on_the_b200_arch(ranks):
+    """tests/unit_tests/boundaries/test_boundary_conditions.cpp and test_distributed_boundaries.cpp, unchanged, with
+    gcl_arch_t = gridtools::gcl::b200: user boundary functors (gtb200/boundaries/b200.hpp) and the reference's own
+    distributed_boundaries<comm_traits<storage, gcl::b200, timer>> over the b200 halo exchange."""
+    rc, out, tail = run("boundaries_reference_b200", ranks)
+    assert rc == 0 and "ALL PASSED" in out, tail
