@@ -1,8 +1,10 @@
 #!/bin/bash
 # Scaling round at exactly N ranks (gpurun --gpus N): stamp check of the exchange, the weak-scaling bench lines of both
 # stencils (as the driver runs them and with more steps), and BASELINE.json configs 4-5 (4096^2 strong / weak, chain).
-N=${1:-8}
+# The first argument may be a list ("2 4" on a 4-GPU box).
+MODE=${2:-full}
 mkdir -p gpurun_out
+for N in ${1:-8}; do
 run() { # tag, script, args...
   local tag=$1; shift
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
@@ -23,9 +25,10 @@ echo "mgpu_check exit $?"; grep "MGPU\|mismatch\|Error" gpurun_out/mgpu_check_$N
 run r02_scale_vert_adv_${N}          bench.py --gpus $N --steps 200 --warmup 20 --no-extras
 run r02_scale_vert_adv_${N}_steps20  bench.py --gpus $N --steps 20 --warmup 3
 run r02_scale_hori_diff_${N}         bench.py --gpus $N --steps 200 --warmup 20 --stencil hori_diff --no-extras
-if [ "${2:-full}" = full ]; then
+if [ "$MODE" = full ]; then
   run r02_hd4096_strong_${N}         bench.py --gpus $N --steps 20 --warmup 3 --stencil hori_diff --ni 4096 --nj 4096 --scaling strong --no-extras
   run r02_hd4096_weak_${N}           bench.py --gpus $N --steps 10 --warmup 3 --stencil hori_diff --ni 4096 --nj 4096 --scaling weak --no-extras
   run r02_chain_1024_${N}            bench_chain.py --steps 20 --warmup 3
 fi
 tail -3 gpurun_out/scale_$N.err
+done
