@@ -41,6 +41,7 @@ HALO = {"vert_adv": 3, "hori_diff": 2}
 HALO_FUSED = 0   # N > 1: gtb_halo_exchange as one launch (pack, signal, wait, unpack)
 RESERVE_SMS = {"vert_adv": 6, "hori_diff": 8}  # N > 1: SMs the persistent stencil grids leave to the concurrent exchange kernels
 # (profiles/r02_exchange_variants.txt: an SM pushes only ~10 GB/s over NVLink, the exchange must end inside a step)
+EXCHANGES_IN_FLIGHT = 1  # N > 1: pattern objects (and streams) that take the per-step exchanges in turn
 HALO_DMA = 0     # N > 1: 1 = the NVLink leg of the exchange on the copy engines (option halo.dma; measured slower:
                  # eight in-stream peer copies cost ~6.5 us each, profiles/r02_exchange_timeline.txt)
 
@@ -324,6 +325,21 @@ def b200_arm(args):
         he.add_halo(1, H, H, H, H + NJ - 1, d1)
         he.add_halo(2, 0, 0, 0, NK - 1, d2)
         he.setup(1)
+    # Exchanges in flight (N > 1): an exchange is a latency chain (pack, NVLink, the neighbours' flags, unpack) of about
+    # the length of a hori_diff step, and the exchanges of ONE pattern object are ordered.  PIPE pattern objects (own
+    # receive arenas and flags) on PIPE streams take the steps in turn, so the pack of step s+2 does not wait for the
+    # flags of step s+1 -- what an application does that exchanges several fields through several patterns.
+    pipe = int(os.environ.get("GTB_PIPE", EXCHANGES_IN_FLIGHT)) if he is not None else 1
+    if os.environ.get("GTB_TIMELINE") == "1" or os.environ.get("GTB_GATES", "0") == "1":
+        pipe = 1
+    hes = [he]
+    for _ in range(1, pipe):
+        h2 = gcl.halo_exchange_dynamic_ut(periodic, grid, np_dtype, comm=gcl.TorchComm(), transport="p2p")
+        h2.add_halo(0, H, H, H, H + NI - 1, p0)
+        h2.add_halo(1, H, H, H, H + NJ - 1, d1)
+        h2.add_halo(2, 0, 0, 0, NK - 1, d2)
+        h2.setup(1)
+        hes.append(h2)
 
     exch_index = 2 if name == "vert_adv" else 0
 
@@ -333,6 +349,8 @@ def b200_arm(args):
     comm = torch.cuda.Stream(priority=-1) if he is not None else None
     comp_h = C.c_void_p(comp.cuda_stream)
     comm_h = C.c_void_p(comm.cuda_stream) if comm is not None else None
+    comms = [comm] + [torch.cuda.Stream(priority=-1) for _ in range(1, pipe)]
+    comm_hs = [C.c_void_p(c.cuda_stream) if c is not None else None for c in comms]
     if name == "vert_adv":
         stencil_plans = [stencil.plan("vertical_advection_dycore", *st, dtr_stage=dtr) for st in sets]
     else:
@@ -375,10 +393,10 @@ def b200_arm(args):
                 if use_gates:
                     sq.halo_gate(he, done.data_ptr(), t - n_sets + 1)
                 else:
-                    sq.wait(comm_h, M + (t - n_sets) % M)
-            sq.halo_exchange(he, [sets[t % n_sets][exch_index]], comm_h)
+                    sq.wait(comm_hs[t % pipe], M + (t - n_sets) % M)
+            sq.halo_exchange(hes[t % pipe], [sets[t % n_sets][exch_index]], comm_hs[t % pipe])
             if not use_gates and not nodeps:
-                sq.record(t % M, comm_h)
+                sq.record(t % M, comm_hs[t % pipe])
 
         for s in range(total_steps):
             first = len(sq)
@@ -446,7 +464,7 @@ def b200_arm(args):
     for s in range(n_warm):
         step(s)
     barrier()
-    if he is not None and he.check() != 0:
+    if he is not None and any(h.check() != 0 for h in hes):
         raise SystemExit("bench.py: a halo wait timed out during warm-up")
     if gated:  # a device-side wait that gave up means the choreography is broken on this box: use stream events
         t = torch.tensor([_lib.gate_timeouts()], device="cuda", dtype=torch.int64)
@@ -495,7 +513,7 @@ def b200_arm(args):
         total_ms = seq.elapsed_ms(0, 1)
         launches = (_lib.launch_count() - launches0) * args.steps // (args.steps + LEAD)
         per_step = [total_ms / args.steps]
-        if he.check() != 0:
+        if any(h.check() != 0 for h in hes):
             raise SystemExit("bench.py: a halo wait timed out in the timed region")
     if timeline is not None and rank == 0:
         tl, ht = timeline.cpu().numpy(), halo_trace.cpu().numpy()
@@ -565,11 +583,11 @@ def b200_arm(args):
                    "decomposition": ("%dx%dx1 IJ process grid, halo exchange of %s every step over NVLink: local pack kernel, "
                                      "%s, device-side arrival flags, local unpack kernel; on a high-priority stream beside "
                                      "the previous step's stencil, ordered by %s; %d SMs reserved for the pack / unpack "
-                                     "kernels; loop issued as one recorded gtb_seq" % (
+                                     "kernels; %d pattern object(s) take the steps in turn; loop issued as one recorded gtb_seq" % (
                                          dims[0], dims[1], "wcon" if name == "vert_adv" else "in",
                                          "copy-engine (DMA) transfers into the neighbours' receive buffers" if halo_dma else
                                          "peer stores from the pack kernel", "device-side gates" if gated else "stream events",
-                                         reserve_sms)) if world > 1 else "single GPU",
+                                         reserve_sms, pipe)) if world > 1 else "single GPU",
                    "l2": "inputs of one step (%d MB) exceed L2 and %d field set(s) are rotated" % (
                        sum(f.nbytes_host for f in sets[0][:5 if name == "vert_adv" else 2]) // 2**20, n_sets),
                    "vs_baseline_ref": "reference stencil::gpu on P100, BASELINE.md section 1"},

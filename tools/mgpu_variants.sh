@@ -23,17 +23,17 @@ except Exception as e:
 PY
   tail -1 $OUT
 }
-for st in vert_adv hori_diff; do
-  timeout 300 python bench.py --gpus 1 --steps $STEPS --warmup 10 --stencil $st --no-extras 2>> gpurun_out/variants.err | tail -1 | \
-    python3 -c "import json,sys; d=json.loads(sys.stdin.read()); print('%-34s %-9s %7.2f us/step' % ('N=1', '$st', d['ms_per_step']*1e3))" | tee -a $OUT
-  run "plain r6"                        $st GTB_RESERVE_SMS=6
-  run "periodic r6"                     $st GTB_PERIODIC=1 GTB_RESERVE_SMS=6
-  run "periodic r8"                     $st GTB_PERIODIC=1 GTB_RESERVE_SMS=8
-  run "periodic r12"                    $st GTB_PERIODIC=1 GTB_RESERVE_SMS=12
-  if [ $st = vert_adv ]; then
-    run "periodic r6 gates pdl2"        $st GTB_PERIODIC=1 GTB_GATES=1 GTB_PDL=2 GTB_RESERVE_SMS=6
-    run "periodic r8 gates pdl2"        $st GTB_PERIODIC=1 GTB_GATES=1 GTB_PDL=2 GTB_RESERVE_SMS=8
-    run "plain r6 gates pdl2"           $st GTB_GATES=1 GTB_PDL=2 GTB_RESERVE_SMS=6
-  fi
-done
+n1() {
+  timeout 300 python bench.py --gpus 1 --steps $STEPS --warmup 10 --stencil $1 --no-extras 2>> gpurun_out/variants.err | tail -1 | \
+    python3 -c "import json,sys; d=json.loads(sys.stdin.read()); print('%-34s %-9s %7.2f us/step' % ('N=1', '$1', d['ms_per_step']*1e3))" | tee -a $OUT
+}
+# round 2, last sweep: pattern objects taking the steps in turn (GTB_PIPE) against one object
+n1 hori_diff
+run "plain r8 pipe 1"                 hori_diff GTB_RESERVE_SMS=8 GTB_PIPE=1
+run "plain r8 pipe 2"                 hori_diff GTB_RESERVE_SMS=8 GTB_PIPE=2
+run "periodic r8 pipe 1"              hori_diff GTB_PERIODIC=1 GTB_RESERVE_SMS=8 GTB_PIPE=1
+run "periodic r8 pipe 2"              hori_diff GTB_PERIODIC=1 GTB_RESERVE_SMS=8 GTB_PIPE=2
+run "periodic r8 pipe 3"              hori_diff GTB_PERIODIC=1 GTB_RESERVE_SMS=8 GTB_PIPE=3
+run "periodic r12 pipe 2"             hori_diff GTB_PERIODIC=1 GTB_RESERVE_SMS=12 GTB_PIPE=2
+run "periodic r6 pipe 2"              vert_adv GTB_PERIODIC=1 GTB_RESERVE_SMS=6 GTB_PIPE=2
 cat $OUT
