@@ -43,6 +43,7 @@ namespace gtb {
         int va_save_upos = 0; // u_pos(k) kept next to ccol/dcol instead of re-read in the backward sweep: 0 auto, 1 on, 2 off
         int va_debug = 0;     // diagnosis only, see va_params::debug
         int va_stages = 0;    // TMA ring depth (0 auto)
+        int va_bldg = 0;      // paired-warp kernel: u_pos of the backward sweep 0 auto, 1 register loads (LDG), 2 TMA ring
         int va_stagger = 0;   // TMEM variant: start stagger between the warps of a CTA, in units of 100 ns
         int copy_vec = 1;     // vectorised copy on/off
         int l2_persist_mb = -1; // L2 set-aside for the k-cache slabs in MB: -1 auto (slab size), 0 off

@@ -183,6 +183,7 @@ namespace {
             {"va.debug", &o.va_debug},
             {"va.stages", &o.va_stages},
             {"va.stagger", &o.va_stagger},
+            {"va.bldg", &o.va_bldg},
             {"reserve_sms", &o.reserve_sms},
             {"pdl", &o.pdl},
             {"halo.fused", &o.halo_fused},

@@ -714,7 +714,124 @@ namespace {
         asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
     }
 
+    // Backward sweep of one strip with u_pos read straight into registers (va_pair_kernel<..., BLDG = true>): see there.
+    template <int N>
+    struct va_words {
+        uint32_t v[N];
+    };
+    template <class T, int N>
+    struct va_vals {
+        T v[N];
+    };
     template <class T, int KC>
+    __device__ __forceinline__ void va_pair_backward_ldg(const va_params<T> &p, int lane, int i0, int j, int cb_top,
+        int c_split, int mirrored, int more, uint32_t tw, T *ss, volatile int *ctl, T data, T up_last, int &done,
+        uint64_t pol_stream) {
+        using CFG = va_tmem_cfg<T>;
+        constexpr int CPL = CFG::cpl;
+        constexpr int NW = KC * CPL;
+        const int nk = p.nk;
+        const T dtr = p.dtr;
+        const bool active = i0 + lane < p.ni;
+        const int64_t us_sk = p.utens_stage.sk;
+        // `upq` walks down the column one chunk per load; only the top chunk can hold levels past nk-2 (never used:
+        // clamped to its first level).  (Walking level by level with one pointer, or loads without the L2 hint, are
+        // slower: profiles/r02_va_timeline.txt.)
+        const int64_t up_sk = p.u_pos.sk;
+        const T *upq = p.u_pos.ptr + (active ? i0 + lane : 0) + (int64_t)j * p.u_pos.sj + (int64_t)(cb_top * KC) * up_sk;
+        int up_left = cb_top + 1; // chunks not loaded yet
+        auto load_up = [&](va_vals<T, KC> &up, auto top) {
+            if (up_left <= 0)
+                return;
+#pragma unroll
+            for (int u = 0; u < KC; ++u) {
+                const bool in = !decltype(top)::value || cb_top * KC + u <= nk - 2;
+                up.v[u] = ptx::ld_hint(in ? upq + u * up_sk : upq, pol_stream);
+            }
+            upq -= KC * up_sk;
+            --up_left;
+        };
+        va_vals<T, KC> up0, up1, up2, up3;
+        load_up(up0, std::true_type());
+        load_up(up1, std::false_type());
+        load_up(up2, std::false_type());
+        load_up(up3, std::false_type());
+        T *o = p.utens_stage.ptr + (active ? i0 + lane : 0) + (int64_t)j * p.utens_stage.sj + (int64_t)(nk - 1) * us_sk;
+        if (active) // last_level :118-121
+            *o = dtr * (data - up_last);
+        // {ccol, dcol} of a chunk live in one of two register sets (packed words, as they come out of TMEM): the set of
+        // chunk cb-1 is filled while the levels of chunk cb are computed from the other one.
+        va_words<NW> w0, w1;
+        auto fetch = [&](int cb, va_words<NW> &w) { // issue the loads of chunk cb
+            const int ph = mirrored ? cb_top - cb : cb; // where the strip stored its chunk cb
+            if (ph < c_split)
+                tm::ld<NW>(tw + (uint32_t)(ph * NW), w.v);
+            return ph;
+        };
+        auto land = [&](int cb, int ph, va_words<NW> &w) { // ... and wait for them
+            if (ph < c_split) {
+                tm::wait_ld();
+            } else {
+                const T *q = ss + (ph - c_split) * (KC * 64);
+#pragma unroll
+                for (int u = 0; u < KC; ++u) {
+                    T cc = T(0), dc = T(0);
+                    if (cb * KC + u < nk - 1) {
+                        cc = q[u * 64];
+                        dc = q[u * 64 + 32];
+                    }
+                    tm::pack<T>(cc, dc, w.v + u * CPL);
+                }
+            }
+            ++done;
+            if (more && ((done & 1) == 0 || cb == 0)) { // the slots read so far may be overwritten by the partner
+                tm::fence_before();
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0)
+                    ctl[0] = done;
+            }
+        };
+        auto sweep = [&](int cb, va_words<NW> &wc, va_words<NW> &wn, va_vals<T, KC> &up, auto checked) {
+            int ph_next = 0;
+            if (cb > 0)
+                ph_next = fetch(cb - 1, wn);
+#pragma unroll
+            for (int u = KC - 1; u >= 0; --u) { // levels of chunk cb, top down (body :111-116)
+                if (!decltype(checked)::value || cb * KC + u <= nk - 2) {
+                    T cc, dc;
+                    tm::unpack<T>(wc.v + u * CPL, cc, dc);
+                    data = dc - cc * data;
+                    o -= us_sk;
+                    if (active)
+                        *o = dtr * (data - up.v[u]);
+                }
+            }
+            load_up(up, std::false_type()); // this register set again four chunks further down
+            if (cb > 0)
+                land(cb - 1, ph_next, wn);
+        };
+        land(cb_top, fetch(cb_top, w0), w0);
+        sweep(cb_top, w0, w1, up0, std::true_type()); // the top chunk may hold fewer than KC levels
+        for (int cb = cb_top - 1; cb >= 0;) {
+            sweep(cb--, w1, w0, up1, std::false_type());
+            if (cb < 0)
+                break;
+            sweep(cb--, w0, w1, up2, std::false_type());
+            if (cb < 0)
+                break;
+            sweep(cb--, w1, w0, up3, std::false_type());
+            if (cb < 0)
+                break;
+            sweep(cb--, w0, w1, up0, std::false_type());
+        }
+    }
+
+    // BLDG: the B warp reads u_pos(k) with plain (L2-hinted) loads into registers, three chunks ahead, instead of through
+    // its own TMA ring: per chunk 4 LDGs replace the elected-lane TMA issue (28 instructions), the mbarrier wait and the
+    // shared-memory reads -- the backward sweep is bound by the length of its own instruction stream (ncu: `wait` and
+    // `branch_resolving` stalls, 160 instructions per 4-level chunk at one warp per scheduler), not by memory.
+    template <class T, int KC, bool BLDG>
     __global__ void __launch_bounds__(512, 1) va_pair_kernel(const __grid_constant__ va_maps maps, const va_params<T> p) {
         using L = va_tma_layout<T>;
         using CFG = va_tmem_cfg<T>;
@@ -821,7 +938,9 @@ namespace {
                     issue_f(i0, j, c);
                 u0 = i0 + lane < p.ni ? __ldg(p.u_stage.ptr + i0 + lane + (int64_t)j * p.u_stage.sj) : T(0);
             };
-            int item = pw * gridDim.x + blockIdx.x;
+            // first strips: the pairs of a CTA take neighbouring strips (va.debug & 256, experiment: the CTA then reads 2 KB
+            // contiguous rows per level and field at about the same time) or strips one grid apart
+            int item = (p.debug & 256) ? blockIdx.x * PAIRS + pw : pw * gridDim.x + blockIdx.x;
             T u0 = T(0);
             if (item < p.items)
                 prime(item, u0);
@@ -950,90 +1069,95 @@ namespace {
                 const int ti = item % p.tiles_i, j = item / p.tiles_i;
                 const int i0 = ti * 32;
                 const bool active = i0 + lane < p.ni;
-                auto issue_b = [&](int cb) { // u_pos of chunk cb: an L2 hit (the forward load left the lines evict_last)
-                    const int s = b_issue;
-                    b_issue = b_issue + 1 == SB ? 0 : b_issue + 1;
-                    if (ptx::elect_one()) {
-                        ptx::mbar_expect_tx(&bfull[s], btx);
-                        ptx::tma_load_3d_hint(bring + s * bstage, &maps.up, &bfull[s], i0, j, cb * KC, pol_stream);
-                    }
-                };
-                for (int n = 0; n < SB - 1 && cb_top - n >= 0; ++n)
-                    issue_b(cb_top - n);
-                T *o = p.utens_stage.ptr + (active ? i0 + lane : 0) + (int64_t)j * p.utens_stage.sj + (int64_t)(nk - 1) * us_sk;
-                if (active) // last_level :118-121
-                    *o = dtr * (data - up_last);
-                // The k-cache is read one chunk ahead of the arithmetic: the TMEM / shared-memory latency of chunk cb-1
-                // hides behind the four levels of chunk cb.  While the partner sweeps forward (`more`) it is told
-                // after every second chunk which slots are free; in the last, backward-only pass nobody listens.
-                T bcc[KC], bdc[KC];
-                uint32_t w[NW];
-                auto fetch = [&](int cb) { // issue the loads of chunk cb
-                    const int ph = mirrored ? cb_top - cb : cb; // where the strip stored its chunk cb
-                    if (ph < c_split)
-                        tm::ld<NW>(tw + (uint32_t)(ph * NW), w);
-                    return ph;
-                };
-                auto land = [&](int cb, int ph) { // ... and wait for them
-                    if (ph < c_split) {
-                        tm::wait_ld();
-#pragma unroll
-                        for (int u = 0; u < KC; ++u)
-                            tm::unpack<T>(w + u * CPL, bcc[u], bdc[u]);
-                    } else {
-                        const T *q = ss + (ph - c_split) * (KC * 64);
-#pragma unroll
-                        for (int u = 0; u < KC; ++u) {
-                            bcc[u] = bdc[u] = T(0);
-                            if (cb * KC + u < nk - 1) {
-                                bcc[u] = q[u * 64];
-                                bdc[u] = q[u * 64 + 32];
+                if constexpr (BLDG) {
+                    va_pair_backward_ldg<T, KC>(p, lane, i0, j, cb_top, c_split, mirrored, more, tw, ss, ctl, data, up_last,
+                        done, pol_stream);
+                } else {
+                    auto issue_b = [&](int cb) { // u_pos of chunk cb: an L2 hit (the forward load left the lines evict_last)
+                        const int s = b_issue;
+                        b_issue = b_issue + 1 == SB ? 0 : b_issue + 1;
+                        if (ptx::elect_one()) {
+                            ptx::mbar_expect_tx(&bfull[s], btx);
+                            ptx::tma_load_3d_hint(bring + s * bstage, &maps.up, &bfull[s], i0, j, cb * KC, pol_stream);
+                        }
+                    };
+                    for (int n = 0; n < SB - 1 && cb_top - n >= 0; ++n)
+                        issue_b(cb_top - n);
+                    T *o = p.utens_stage.ptr + (active ? i0 + lane : 0) + (int64_t)j * p.utens_stage.sj + (int64_t)(nk - 1) * us_sk;
+                    if (active) // last_level :118-121
+                        *o = dtr * (data - up_last);
+                    // The k-cache is read one chunk ahead of the arithmetic: the TMEM / shared-memory latency of chunk cb-1
+                    // hides behind the four levels of chunk cb.  While the partner sweeps forward (`more`) it is told
+                    // after every second chunk which slots are free; in the last, backward-only pass nobody listens.
+                    T bcc[KC], bdc[KC];
+                    uint32_t w[NW];
+                    auto fetch = [&](int cb) { // issue the loads of chunk cb
+                        const int ph = mirrored ? cb_top - cb : cb; // where the strip stored its chunk cb
+                        if (ph < c_split)
+                            tm::ld<NW>(tw + (uint32_t)(ph * NW), w);
+                        return ph;
+                    };
+                    auto land = [&](int cb, int ph) { // ... and wait for them
+                        if (ph < c_split) {
+                            tm::wait_ld();
+    #pragma unroll
+                            for (int u = 0; u < KC; ++u)
+                                tm::unpack<T>(w + u * CPL, bcc[u], bdc[u]);
+                        } else {
+                            const T *q = ss + (ph - c_split) * (KC * 64);
+    #pragma unroll
+                            for (int u = 0; u < KC; ++u) {
+                                bcc[u] = bdc[u] = T(0);
+                                if (cb * KC + u < nk - 1) {
+                                    bcc[u] = q[u * 64];
+                                    bdc[u] = q[u * 64 + 32];
+                                }
                             }
                         }
-                    }
-                    ++done;
-                    if (more && ((done & 1) == 0 || cb == 0)) { // the slots read so far may be overwritten by the partner
-                        tm::fence_before();
-                        __threadfence_block();
-                        __syncwarp();
-                        if (lane == 0)
-                            ctl[0] = done;
-                    }
-                };
-                auto sweep = [&](int cb, auto checked) { // levels of chunk cb, top down (body :111-116)
-                    T ccv[KC], dcv[KC];
-#pragma unroll
-                    for (int u = 0; u < KC; ++u)
-                        ccv[u] = bcc[u], dcv[u] = bdc[u];
-                    int ph_next = 0;
-                    if (cb > 0)
-                        ph_next = fetch(cb - 1);
-                    if (cb - (SB - 1) >= 0)
-                        issue_b(cb - (SB - 1));
-                    const int s = b_wait;
-                    ptx::mbar_wait(&bfull[s], b_phase);
-                    if (++b_wait == SB) {
-                        b_wait = 0;
-                        b_phase ^= 1;
-                    }
-                    const T *sb = reinterpret_cast<const T *>(bring + s * bstage) + lane;
-#pragma unroll
-                    for (int u = KC - 1; u >= 0; --u) {
-                        if (!decltype(checked)::value || cb * KC + u <= nk - 2) {
-                            data = dcv[u] - ccv[u] * data;
-                            o -= us_sk;
-                            if (active)
-                                *o = dtr * (data - sb[u * 32]);
+                        ++done;
+                        if (more && ((done & 1) == 0 || cb == 0)) { // the slots read so far may be overwritten by the partner
+                            tm::fence_before();
+                            __threadfence_block();
+                            __syncwarp();
+                            if (lane == 0)
+                                ctl[0] = done;
                         }
-                    }
-                    if (cb > 0)
-                        land(cb - 1, ph_next);
-                    __syncwarp(); // all lanes are done with the ring stage before one lane refills it
-                };
-                land(cb_top, fetch(cb_top));
-                sweep(cb_top, std::true_type()); // the top chunk may hold fewer than KC levels
-                for (int cb = cb_top - 1; cb >= 0; --cb)
-                    sweep(cb, std::false_type());
+                    };
+                    auto sweep = [&](int cb, auto checked) { // levels of chunk cb, top down (body :111-116)
+                        T ccv[KC], dcv[KC];
+    #pragma unroll
+                        for (int u = 0; u < KC; ++u)
+                            ccv[u] = bcc[u], dcv[u] = bdc[u];
+                        int ph_next = 0;
+                        if (cb > 0)
+                            ph_next = fetch(cb - 1);
+                        if (cb - (SB - 1) >= 0)
+                            issue_b(cb - (SB - 1));
+                        const int s = b_wait;
+                        ptx::mbar_wait(&bfull[s], b_phase);
+                        if (++b_wait == SB) {
+                            b_wait = 0;
+                            b_phase ^= 1;
+                        }
+                        const T *sb = reinterpret_cast<const T *>(bring + s * bstage) + lane;
+    #pragma unroll
+                        for (int u = KC - 1; u >= 0; --u) {
+                            if (!decltype(checked)::value || cb * KC + u <= nk - 2) {
+                                data = dcv[u] - ccv[u] * data;
+                                o -= us_sk;
+                                if (active)
+                                    *o = dtr * (data - sb[u * 32]);
+                            }
+                        }
+                        if (cb > 0)
+                            land(cb - 1, ph_next);
+                        __syncwarp(); // all lanes are done with the ring stage before one lane refills it
+                    };
+                    land(cb_top, fetch(cb_top));
+                    sweep(cb_top, std::true_type()); // the top chunk may hold fewer than KC levels
+                    for (int cb = cb_top - 1; cb >= 0; --cb)
+                        sweep(cb, std::false_type());
+                }
                 stamp(4 + 4 * pass);
                 if (!more)
                     break;
@@ -1321,12 +1445,13 @@ namespace {
         int st = set_l2_persist(0);
         if (st)
             return st;
-        auto kernel = va_pair_kernel<T, KC>;
-        static thread_local int done_dev = -1;
-        if (done_dev != d->device) {
+        const bool bldg = o.va_bldg != 2; // 0 auto / 1: u_pos of the backward sweep by register loads; 2: through a TMA ring
+        auto kernel = bldg ? va_pair_kernel<T, KC, true> : va_pair_kernel<T, KC, false>;
+        static thread_local int done_dev[2] = {-1, -1};
+        if (done_dev[bldg] != d->device) {
             GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->max_smem_optin));
             GTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            done_dev = d->device;
+            done_dev[bldg] = d->device;
         }
         GTB_CUDA(launch_pdl(kernel, dim3(grid), dim3(512), (size_t)smem, stream, maps, p));
         count_launch();

@@ -39,7 +39,7 @@ def gt():
 def reset_options(gt):
     yield
     for k in ("hd.variant", "hd.stages", "hd.ctas_per_sm", "va.variant", "va.threads", "va.unroll", "va.scratch", "va.stagger",
-              "va.ctas_per_sm", "va.save_upos", "va.stages"):
+              "va.ctas_per_sm", "va.save_upos", "va.stages", "va.bldg"):
         gt.lib.set_option(k, 0)
     gt.lib.set_option("va.hints", 1)
     gt.lib.set_option("copy.vec", 1)
@@ -228,6 +228,8 @@ def test_simple_hori_diff_random_bit_exact(gt, oracle, size, dtype):
 
 # ------------------------------------------------------------------------------------- vertical advection
 VA_CONFIGS = [dict(), dict(variant=7), dict(variant=7, ctas_per_sm=-1), dict(variant=7, ctas_per_sm=3, stages=2, unroll=2),
+              dict(variant=7, bldg=1), dict(variant=7, bldg=2), dict(variant=7, bldg=1, ctas_per_sm=-1),
+              dict(variant=7, bldg=1, ctas_per_sm=3, stages=2), dict(variant=7, bldg=1, ctas_per_sm=7, stages=3),
               dict(variant=7, ctas_per_sm=7, stages=3, unroll=4), dict(variant=3), dict(variant=3, ctas_per_sm=-2, unroll=8),
               dict(variant=3, ctas_per_sm=-1), dict(variant=3, stages=3, ctas_per_sm=-3), dict(variant=3, stages=6),
               dict(variant=3, ctas_per_sm=-2, save_upos=2), dict(variant=3, threads=32, ctas_per_sm=-1, save_upos=2),
@@ -278,10 +280,11 @@ def test_vert_adv_random_bit_exact(gt, oracle, size, alignment):
     arrs = [rng.uniform(5, 9, shape), rng.uniform(5, 9, shape), rng.uniform(-3e-4, 3e-4, shape),
             rng.uniform(5, 9, shape), rng.uniform(-1e-5, 1e-5, shape)]
     for cfg in (dict(), dict(variant=7), dict(variant=7, ctas_per_sm=-1, stages=2), dict(variant=3, ctas_per_sm=-3),
+                dict(variant=7, bldg=1), dict(variant=7, bldg=1, ctas_per_sm=-1, stages=2), dict(variant=7, bldg=2),
                 dict(variant=3, ctas_per_sm=-1, unroll=8), dict(variant=3, ctas_per_sm=-2, threads=32, save_upos=2),
                 dict(variant=3, threads=64, save_upos=2), dict(variant=1), dict(variant=1, scratch=2, threads=32),
                 dict(variant=1, ctas_per_sm=-2, threads=32)):
-        for k in ("variant", "threads", "unroll", "scratch", "ctas_per_sm", "save_upos", "stages", "stagger"):
+        for k in ("variant", "threads", "unroll", "scratch", "ctas_per_sm", "save_upos", "stages", "stagger", "bldg"):
             gt.lib.set_option("va." + k, 0)
         set_va(gt, cfg)
         try:
@@ -302,9 +305,12 @@ def test_vert_adv_full_size(gt, oracle):
     shape = (nk, nj + 6, ni + 6)
     arrs = [rng.uniform(5, 9, shape), rng.uniform(5, 9, shape), rng.uniform(-3e-4, 3e-4, shape),
             rng.uniform(5, 9, shape), rng.uniform(-1e-5, 1e-5, shape)]
-    out, _ = run_va(gt, arrs, 0.15)
     inner = (slice(None), slice(3, -3), slice(3, -3))
-    assert np.array_equal(out[inner], oracle.vert_adv(*arrs, 0.15)[inner])
+    want = oracle.vert_adv(*arrs, 0.15)[inner]
+    for bldg in (0, 1, 2):  # u_pos of the backward sweep: default, register loads, TMA ring
+        gt.lib.set_option("va.bldg", bldg)
+        out, _ = run_va(gt, arrs, 0.15)
+        assert np.array_equal(out[inner], want), bldg
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
@@ -320,8 +326,9 @@ def test_vert_adv_tall_columns(gt, oracle, nk, dtype):
             rng.uniform(-1e-5, 1e-5, shape).astype(dtype)]
     want = oracle.vert_adv(*arrs, 0.15)
     inner = (slice(None), slice(3, -3), slice(3, -3))
-    for cfg in (dict(), dict(variant=7), dict(variant=7, ctas_per_sm=-1), dict(variant=3), dict(variant=3, threads=32, stages=2, ctas_per_sm=-2)):
-        for k in ("variant", "unroll", "stages", "ctas_per_sm"):
+    for cfg in (dict(), dict(variant=7), dict(variant=7, ctas_per_sm=-1), dict(variant=7, bldg=1), dict(variant=7, bldg=1, ctas_per_sm=-1),
+                dict(variant=7, bldg=2), dict(variant=3), dict(variant=3, threads=32, stages=2, ctas_per_sm=-2)):
+        for k in ("variant", "unroll", "stages", "ctas_per_sm", "bldg"):
             gt.lib.set_option("va." + k, 0)
         set_va(gt, cfg)
         try:

@@ -54,14 +54,14 @@ def sass_mix(rep):
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     traffic = {}
-    for name, stencil in (("va", "vert_adv"), ("hd", "hori_diff")):
+    for name, stencil in (("va", "vert_adv"), ("hd", "hori_diff"), ("fused", None)):
         rep = "gpurun_out/prof_%s.ncu-rep" % name
         if not os.path.exists(rep):
             continue
         hdr, units, rows = raw(rep)
         lines = ["# ncu --set full --clock-control none, kernel regex %s_ (tools/gpu_round.sh ncu); one column per captured launch" % name]
         ik = hdr.index("Kernel Name")
-        lines.append("kernel: " + rows[0][ik])
+        lines.append("kernel: " + rows[0][ik][:400])
         vals = {}
         for i, h in enumerate(hdr):
             if h in KEYS:
@@ -70,8 +70,10 @@ def main():
         rd = [float(x) for x in vals["dram__bytes_read.sum"]]
         wr = [float(x) for x in vals["dram__bytes_write.sum"]]
         scale = 1e6 if units[hdr.index("dram__bytes_read.sum")] == "Mbyte" else 1.0
-        traffic[stencil] = int((sum(rd) / len(rd) + sum(wr) / len(wr)) * scale)
-        lines.append("dram traffic per launch (read + write, mean of the captured launches): %d bytes" % traffic[stencil])
+        per_launch = int((sum(rd) / len(rd) + sum(wr) / len(wr)) * scale)
+        if stencil is not None:
+            traffic[stencil] = per_launch
+        lines.append("dram traffic per launch (read + write, mean of the captured launches): %d bytes" % per_launch)
         mix = sass_mix(rep)
         tot = sum(v[0] for v in mix.values()) or 1
         lines.append("")

@@ -48,11 +48,12 @@ def main():
                     f.const_target_tensor()
             plans = [stencil.plan("vertical_advection_dycore", *st, dtr_stage=0.15) for st in sets]
             res = []
-            combos = [dict(variant=7, ctas_per_sm=p, stages=s, unroll=u) for p, s, u in
-                      itertools.product((6, 7, 8), (0, 3, 4, 5), (2, 3, 4))] if dtype == np.float64 else []
+            combos = [dict(variant=7, bldg=b, ctas_per_sm=p, stages=s, unroll=u) for b, p, s, u in
+                      itertools.product((1, 2), (6, 7, 8), (0, 3, 4, 5), (2, 3))] if dtype == np.float64 else \
+                     [dict(variant=7, bldg=b) for b in (1, 2)]
             combos += [dict(variant=3, ctas_per_sm=w, threads=32 * nb, stages=4) for w, nb in itertools.product((6, 7, 8), (1, 2, 4))]
             for cfg in combos:
-                for k in ("variant", "threads", "unroll", "ctas_per_sm", "stages"):
+                for k in ("variant", "threads", "unroll", "ctas_per_sm", "stages", "bldg"):
                     _lib.set_option("va." + k, cfg.get(k, 0))
                 try:
                     ms = timeit(plans)
@@ -64,7 +65,7 @@ def main():
                                                                   ms * 1e3, b / ms / 1e6)))
             for _, line in sorted(res):
                 print(line)
-            for k in ("variant", "threads", "unroll", "ctas_per_sm", "stages"):
+            for k in ("variant", "threads", "unroll", "ctas_per_sm", "stages", "bldg"):
                 _lib.set_option("va." + k, 0)
     if only in ("all", "hd"):
         for dtype, n in ((np.float64, 256), (np.float32, 256), (np.float64, 512), (np.float32, 512)):
