@@ -23,7 +23,7 @@ for a in sys.argv[1:]:
     k, v = a.split("=")
     if k == "debug":
         extra_debug = int(v)
-    _lib.set_option("va." + k, int(v))
+    _lib.set_option(k if k in ("pdl", "reserve_sms") else "va." + k, int(v))
 print("options:", " ".join(sys.argv[1:]))
 buf = np.zeros((2048, 32), np.int64)
 for s in range(6):
