@@ -31,10 +31,10 @@ namespace gtb {
 
     // ---------------------------------------------------------------- options
     struct options {
-        int hd_variant = 0;   // 0 auto, 1 cp.async staged, 2 TMA + block barrier, 3 TMA warp specialised
+        int hd_variant = 0;   // 0 auto, 1 cp.async staged, 2 TMA + block barrier
         int hd_stages = 0;    // 0 auto
         int hd_ctas_per_sm = 0;
-        int va_variant = 0;   // 0 auto, 1 register-prefetch LDG, 2 TMA-streamed persistent warps
+        int va_variant = 0;   // 0 auto, 1 first TMA version, 3 TMA + L2 slab (fp32 default), 7 paired warps + tensor memory (fp64 default)
         int va_threads = 0;   // threads per CTA (multiple of 32)
         int va_unroll = 0;    // k levels prefetched ahead
         int va_scratch = 0;   // 0 auto, 1 global (L2) scratch, 2 shared memory

@@ -7,18 +7,19 @@
 // by the backward sweep; no prefetching ("no unrolling", make_kernel_fun.hpp:62-64), so every level waits for its
 // own loads.
 //
-// What this file does instead (four kernels, "va.variant" option; 0 = auto = 3 when the layout is TMA-addressable,
-// else 1; measured numbers in profiles/README.md):
-//  1  va_kernel          one thread per column, loads software-pipelined UNROLL levels ahead through registers
-//                        (plain LDG, any alignment), ccol/dcol in shared memory or a column-interleaved global scratch;
-//  2  va_tma_kernel      first TMA version: persistent one-warp CTAs, per-warp TMA ring, per-thread slab loads;
-//  3  va_stream_kernel   the default: same decomposition as 2 with half the instructions per level, a contiguous
-//                        per-warp L2 slab and a 32-level register ring for the backward sweep;
-//  4  va_resident_kernel ccol/dcol never leave the SM: the upper 48 levels of a column in registers, the rest in
-//                        shared memory (no L2 slab at all; as fast as 3 at nk = 80, refused when nk is too tall).
+// What this file does instead ("va.variant" option; 0 = auto; measured numbers in profiles/README.md):
+//  7  va_pair_kernel     fp64 default: one 16-warp CTA per SM = 8 forward / backward warp pairs, ccol/dcol in TENSOR
+//                        MEMORY (one window per pair, levels past it in a shared-memory slab), forward inputs through a
+//                        per-warp TMA ring, backward sweep of strip n beside the forward sweep of strip n+1;
+//  3  va_stream_kernel   fp32 default and columns too tall for 7: persistent one-warp CTAs, per-warp TMA ring,
+//                        ccol/dcol/u_pos in a contiguous per-warp L2 slab, 32-level register ring for the backward sweep;
+//  1  va_tma_kernel      first TMA version (per-thread slab loads); kept as the reference point of the sweeps;
+//  0/- va_kernel         any alignment: one thread per column, loads software-pipelined UNROLL levels ahead through
+//                        registers (plain LDG), ccol/dcol in shared memory or a column-interleaved global scratch.
+// (Variants 2, 4, 5, 6 of round 1 -- measured slower -- were removed; their numbers are in profiles/r01_*.)
 // Common to all: a warp covers 32 consecutive i (256 B per fp64 row), the k_caches of the reference are registers
 // rotated by the sweep (u_stage(k-1,k,k+1), wcon(i,k)+wcon(i+1,k), ccol/dcol(k-1), data_col(k+1)), and the
-// temporaries ccol/dcol that the reference flushes to HBM stay in L2 (evict_last, persisting set-aside) or on the SM.
+// temporaries ccol/dcol that the reference flushes to HBM stay on the SM (7) or in L2 (3, evict_last).
 //
 // Arithmetic follows the functor bodies operation by operation (-fmad=false, IEEE division), so results are
 // bit-identical to oracle/gt_oracle.c compiled with -ffp-contract=off.
