@@ -217,10 +217,14 @@ namespace {
             for (int s = 0; s < STAGES; ++s)
                 ptx::mbar_init(&full[s], 1);
             ptx::fence_barrier_init();
-            if (p.gate.wait_flag) { // the halo of `in` is being unpacked by a kernel on another stream
-                ptx::gate_wait(p.gate.wait_flag, p.gate.wait_value, p.gate.timeouts);
-                ptx::fence_proxy_async_all(); // ... and is read through the async proxy (TMA) below
-            }
+        }
+        // launched with programmatic stream serialization (launch_pdl): everything above ran under the previous kernel's
+        // tail; nothing an earlier kernel of the stream may have touched is read or written before this wait
+        ptx::pdl_launch_dependents();
+        ptx::pdl_wait();
+        if (tid == 0 && p.gate.wait_flag) { // the halo of `in` is being unpacked by a kernel on another stream
+            ptx::gate_wait(p.gate.wait_flag, p.gate.wait_value, p.gate.timeouts);
+            ptx::fence_proxy_async_all(); // ... and is read through the async proxy (TMA) below
         }
         __syncthreads();
         item_iter it, ahead;
@@ -355,9 +359,11 @@ namespace {
                 int st = prepare_kernel(kernel, smem);
                 if (st)
                     return st;
-                // (no programmatic dependent launch here: with two CTAs per SM the early CTAs of the next launch take
-                // slots from the running one -- 24.6 -> 29.8 us measured)
-                kernel<<<grid, THREADS, smem, stream>>>(map_in, map_co, p);
+                // Programmatic dependent launch only with one CTA per SM: with two, the early CTAs of the next launch take
+                // the slots of the CTAs that finish first and the launch gets slower (stages 3: 24.6 -> 28.6 us); with
+                // one CTA per SM and 4-5 stages it is 24.2 us (profiles/r02_hd_pdl.txt).
+                GTB_CUDA(launch_pdl_if(pdl_allowed() && ctas_per_sm == 1, kernel, dim3(grid), dim3(THREADS), (size_t)smem, stream,
+                    map_in, map_co, p));
                 count_launch();
                 return check_launch("hd_tma_kernel");
             }
@@ -551,7 +557,8 @@ namespace {
                 int st = prepare_kernel(kernel, smem);
                 if (st)
                     return st;
-                kernel<<<grid, THREADS, smem, as_stream(stream)>>>(map_in, map_co, q);
+                GTB_CUDA(launch_pdl_if(false, kernel, dim3(grid), dim3(THREADS), (size_t)smem, as_stream(stream), map_in,
+                    map_co, q)); // two CTAs per SM: see hori_diff
                 count_launch();
                 return check_launch("hd_tma_kernel (simple_hori_diff)");
             }

@@ -5,6 +5,7 @@
 Timing: K launches back to back between one pair of events over four rotating field sets (what bench.py measures).
 """
 import itertools
+import os
 import sys
 
 import numpy as np
@@ -37,6 +38,9 @@ def main():
     only = sys.argv[1] if len(sys.argv) > 1 else "all"
     torch.cuda.set_device(0)
     _lib.check(_lib.lib().gtb_init(0))
+    if "GTB_PDL" in os.environ:  # programmatic dependent launch: 0 off, 1 on (default)
+        _lib.set_option("pdl", int(os.environ["GTB_PDL"]))
+        print("pdl =", os.environ["GTB_PDL"])
     if only in ("all", "va"):
         for dtype in (np.float64, np.float32):
             sets = []
