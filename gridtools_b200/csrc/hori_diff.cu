@@ -257,6 +257,67 @@ namespace {
         }
     }
 
+    // ------------------------------------------------ two tile pipelines in ONE CTA per SM (hd.variant = 4)
+    // The same pipeline as hd_tma_kernel, twice per CTA: threads [0, THREADS) and [THREADS, 2*THREADS) each own a TMA
+    // ring, mbarriers and a share of the item list, and meet on their own named barrier.  One CTA per SM is what
+    // programmatic dependent launch needs here (with two CTAs per SM the early CTAs of the next launch slow the
+    // running one down, profiles/r02_hd_pdl.txt): the prologue runs under the previous launch's tail.
+    template <class T, int STAGES>
+    __global__ void __launch_bounds__(2 * THREADS, 1) hd_tma2_kernel(const __grid_constant__ CUtensorMap map_in,
+        const __grid_constant__ CUtensorMap map_co, const hd_params<T> p) {
+        using L = layout<T>;
+        extern __shared__ __align__(128) unsigned char smem_all[];
+        const int sub = threadIdx.x / THREADS, tid = threadIdx.x % THREADS;
+        unsigned char *smem = smem_all + sub * (STAGES * L::stage_bytes);
+        uint64_t *full = reinterpret_cast<uint64_t *>(smem_all + 2 * STAGES * L::stage_bytes) + sub * STAGES;
+        const int tx = tid % BI, ty = tid / BI;
+        if (tid == 0) {
+            if (sub == 0) {
+                ptx::prefetch_tensormap(&map_in);
+                ptx::prefetch_tensormap(&map_co);
+            }
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s)
+                ptx::mbar_init(&full[s], 1);
+            ptx::fence_barrier_init();
+        }
+        ptx::pdl_launch_dependents();
+        ptx::pdl_wait(); // nothing an earlier kernel of the stream may have touched is read or written before this
+        if (threadIdx.x == 0 && p.gate.wait_flag) { // the halo of `in` is being unpacked by a kernel on another stream
+            ptx::gate_wait(p.gate.wait_flag, p.gate.wait_value, p.gate.timeouts);
+            ptx::fence_proxy_async_all();
+        }
+        __syncthreads();
+        item_iter it, ahead;
+        it.start(p, (int)blockIdx.x * 2 + sub);
+        ahead = it;
+        if (tid == 0) {
+            for (int s = 0; s < STAGES && ahead.k < p.nk; ++s, ahead.next(p))
+                tma_issue<T>(&map_in, &map_co, smem + s * L::stage_bytes, &full[s], ahead);
+        }
+        for (int n = 0; it.k < p.nk; ++n, it.next(p)) {
+            const int s = n % STAGES;
+            ptx::mbar_wait(&full[s], (uint32_t)((n / STAGES) & 1));
+            const unsigned char *base = smem + s * L::stage_bytes;
+            compute_item<T, false>(p, reinterpret_cast<const T *>(base), reinterpret_cast<const T *>(base + L::in_alloc), it,
+                tx, ty, [] {});
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + sub), "n"(THREADS) : "memory"); // this half is done with stage s
+            if (tid == 0 && ahead.k < p.nk) {
+                tma_issue<T>(&map_in, &map_co, smem + s * L::stage_bytes, &full[s], ahead);
+                ahead.next(p);
+            }
+        }
+        if (p.gate.post) {
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0 && atomicAdd(p.gate.cta_done, 1) == (int)gridDim.x - 1) {
+                *p.gate.cta_done = 0;
+                __threadfence();
+                atomicAdd(p.gate.post, 1ULL);
+            }
+        }
+    }
+
     // ------------------------------------------------ cp.async (LDGSTS) variant (hd.variant = 1, any alignment)
     template <class T, int STAGES>
     __global__ void __launch_bounds__(THREADS, 2) hd_cpasync_kernel(const hd_params<T> p) {
@@ -354,6 +415,27 @@ namespace {
             bool ok = make_map<T>(&map_in, p.in, p.in_sj, p.in_sk, L::lead, 2, (int64_t)L::lead + p.ni + 2, p.nj + 4,
                           p.nk, L::in_w, IN_H) &&
                       make_map<T>(&map_co, p.coeff, p.co_sj, p.co_sk, 0, 0, p.ni, p.nj, p.nk, BI, BJ);
+            // auto: short launches (<= 32 items per pipeline: 256^2 x 80 has 17) gain the launch gap (24.5 -> 23.3 us), long
+            // ones lose (512^2 x 80: 81 -> 89 us; the two-CTA kernel is at 95 % of the HBM peak there): profiles/r02_hd_pdl.txt
+            const bool two_in_one = variant == 4 || (variant == 0 && pdl_allowed() && opts().hd_ctas_per_sm == 0 &&
+                                                        items <= (int64_t)stencil_sms(d) * 2 * 32);
+            if (ok && two_in_one) { // two pipelines per CTA, one CTA per SM, programmatic dependent launch
+                int grid2 = stencil_sms(d);
+                if ((int64_t)grid2 * 2 > items)
+                    grid2 = (int)((items + 1) / 2);
+                const int lg = grid2 * 2;
+                p.step_i = lg % p.tiles_i;
+                p.step_j = (lg / p.tiles_i) % p.tiles_j;
+                p.step_k = (lg / p.tiles_i) / p.tiles_j;
+                const int smem2 = 2 * smem;
+                auto kernel = hd_tma2_kernel<T, STAGES>;
+                int st = prepare_kernel(kernel, smem2);
+                if (st)
+                    return st;
+                GTB_CUDA(launch_pdl(kernel, dim3(grid2), dim3(2 * THREADS), (size_t)smem2, stream, map_in, map_co, p));
+                count_launch();
+                return check_launch("hd_tma2_kernel");
+            }
             if (ok) {
                 auto kernel = hd_tma_kernel<T, STAGES>;
                 int st = prepare_kernel(kernel, smem);

@@ -88,7 +88,7 @@ def test_copy_scalar_path(gt, oracle):
 
 
 # ------------------------------------------------------------------------------------- horizontal diffusion
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 4])
 @pytest.mark.parametrize("name", ["hori_diff_12x33x6.npz", "hori_diff_70x19x3.npz"])
 def test_hori_diff_golden(gt, oracle, golden, name, variant):
     g = golden(name)
@@ -105,7 +105,7 @@ def test_hori_diff_golden(gt, oracle, golden, name, variant):
     assert np.all(out[halo_mask] == -7.0), "the kernel wrote outside the compute domain"
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("size,alignment", [((1, 1, 1), 128), ((5, 3, 2), 1), ((64, 16, 3), 128), ((65, 17, 2), 128),
                                             ((129, 47, 5), 1), ((200, 40, 7), 128), ((23, 11, 43), 128)])
@@ -119,7 +119,7 @@ def test_hori_diff_random_bit_exact(gt, oracle, variant, dtype, size, alignment)
         out = run_hd(gt, inp, coeff, alignment)
     except gt.lib.GtbError as e:
         # an explicitly requested TMA variant refuses layouts TMA cannot address (variant 0 falls back to cp.async)
-        assert variant == 2 and alignment == 1 and e.status == gt.lib.GTB_ERR_LAYOUT
+        assert variant in (2, 4) and alignment == 1 and e.status == gt.lib.GTB_ERR_LAYOUT
         pytest.skip("layout is not TMA addressable")
     inner = (slice(None), slice(2, -2), slice(2, -2))
     assert np.array_equal(out[inner], oracle.hori_diff(inp, coeff)[inner])
@@ -140,7 +140,7 @@ def test_hori_diff_pipeline_depths(gt, oracle, stages, ctas):
     coeff = rng.uniform(0, 0.05, inp.shape)
     ref = oracle.hori_diff(inp, coeff)
     inner = (slice(None), slice(2, -2), slice(2, -2))
-    for variant in (1, 2):
+    for variant in (1, 2, 4):
         gt.lib.set_option("hd.variant", variant)
         gt.lib.set_option("hd.stages", stages)
         gt.lib.set_option("hd.ctas_per_sm", ctas)
@@ -157,9 +157,12 @@ def test_hori_diff_full_size(gt, oracle):
         x, y = i / d0, j / d1  # horizontal_diffusion_repository.hpp:32-42
         inp = 5. + 8 * (2. + np.cos(np.pi * (x + 1.5 * y)) + np.sin(2 * np.pi * (x + 1.5 * y))) / 4. + 0. * k
         coeff = np.full_like(inp, 0.025)
-        out = run_hd(gt, inp, coeff)
         inner = (slice(None), slice(2, -2), slice(2, -2))
-        assert np.array_equal(out[inner], oracle.hori_diff(inp, coeff)[inner])
+        want = oracle.hori_diff(inp, coeff)[inner]
+        for variant in (0, 4):  # default; two pipelines in one CTA per SM
+            gt.lib.set_option("hd.variant", variant)
+            out = run_hd(gt, inp, coeff)
+            assert np.array_equal(out[inner], want), variant
 
 
 def test_hori_diff_linearity(gt):

@@ -82,8 +82,9 @@ def main():
                 for f in st:
                     f.const_target_tensor()
             plans = [stencil.plan("horizontal_diffusion", *st) for st in sets]
-            for stages, ctas in itertools.product((2, 3, 4, 5), (1, 2)):
-                for k, v in (("hd.variant", 2), ("hd.stages", stages), ("hd.ctas_per_sm", ctas)):
+            for stages, ctas in list(itertools.product((2, 3, 4, 5), (1, 2))) + [(2, 0), (3, 0), (4, 0), (5, 0)]:
+                # ctas = 0: two pipelines in one CTA per SM (hd.variant 4)
+                for k, v in (("hd.variant", 2 if ctas else 4), ("hd.stages", stages), ("hd.ctas_per_sm", ctas)):
                     _lib.set_option(k, v)
                 try:
                     ms = timeit(plans)
