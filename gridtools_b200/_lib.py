@@ -52,6 +52,7 @@ _SIG = {
     "gtb_get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
     "gtb_release_scratch": (C.c_int, []),
     "gtb_launch_count": (C.c_int64, []),
+    "gtb_last_kernel": (C.c_char_p, []),
     "gtb_copy_box_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p]),
     "gtb_debug_trace": (C.c_int, [C.c_void_p, C.c_int64]),
@@ -170,6 +171,11 @@ def gate_timeouts():
     n = C.c_int64()
     check(lib().gtb_gate_timeouts(C.byref(n)))
     return n.value
+
+
+def last_kernel():
+    """Name of the kernel this thread launched last (which variant the automatic choice took)."""
+    return lib().gtb_last_kernel().decode()
 
 
 def launch_count():

@@ -96,7 +96,9 @@ namespace gtb {
 
     inline cudaStream_t as_stream(void *s) { return static_cast<cudaStream_t>(s); }
 
+    const char *&last_kernel_name(); // per thread: what the last check_launch was called with (gtb_last_kernel)
     inline int check_launch(const char *what) {
+        last_kernel_name() = what;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess)
             return cuda_fail(e, what);

@@ -249,6 +249,15 @@ GTB_API int gtb_release_scratch(void) {
     return GTB_OK;
 }
 
+namespace gtb {
+    const char *&last_kernel_name() {
+        static thread_local const char *name = "";
+        return name;
+    }
+} // namespace gtb
+
+GTB_API const char *gtb_last_kernel(void) { return gtb::last_kernel_name(); }
+
 GTB_API int64_t gtb_launch_count(void) { return g_launches.load(); }
 
 // ------------------------------------------------------------------------------------------------ streams for hosts

@@ -82,6 +82,8 @@ int gtb_copy_box_async(void *device_origin, void *host_origin, int elem_size, in
     int nj, int nk, int to_device, void *stream);
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t gtb_launch_count(void);
+/* Name of the kernel the calling thread launched last ("" before the first): which variant the automatic choice took. */
+const char *gtb_last_kernel(void);
 
 /* --------------------------------------------------------------------------------- named stencil kernels
  * Each is the fused B200 kernel for one spec of the reference's regression/perf suite; together they are what
