@@ -97,9 +97,10 @@ namespace gtb200 {
         int Prefetch = 4,
         bool PrefetchL1 = true,
         int ParallelPrefetch = 0,
-        bool StageReadOnly = true>
+        bool StageReadOnly = true,
+        bool RegisterTiles = true>
     using block_geometry = ::gridtools::stencil::b200_backend::fused::
-        geometry<BI, BJ, KB, SweepUnroll, ChainSweeps, Prefetch, PrefetchL1, ParallelPrefetch, StageReadOnly>;
+        geometry<BI, BJ, KB, SweepUnroll, ChainSweeps, Prefetch, PrefetchL1, ParallelPrefetch, StageReadOnly, RegisterTiles>;
     using default_geometry = ::gridtools::stencil::b200_backend::fused::geometry<>;
 #else
     struct default_geometry {};

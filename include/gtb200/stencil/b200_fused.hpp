@@ -24,6 +24,11 @@
  *   a7  temporaries that are neither ij- nor k-cached live in device memory: one whole-domain array when they are only
  *       read at IJ offset zero, CTA-private halo-extended blocks when they are read at IJ offsets
  *       (gpu/tmp_storage_sid.hpp:54-69), so that no CTA reads what another one writes.
+ *   f4  horizontal multi-stages on REGISTER tiles (gpu_horizontal/entry_point.hpp:57-100, j_cache.hpp:31-52): a parallel
+ *       multi-stage whose temporaries are all ij caches does not use a3/a4 at all -- one thread per column and level
+ *       walks the rows of the block with the temporaries in per-thread register arrays that slide along j, the
+ *       stages evaluated redundantly over their column extent, inputs with IJ offsets read from TMA-staged
+ *       shared-memory tiles (hz_body; horizontal diffusion: 25 us against 47 us on shared-memory tiles).
  *   Not `fusable` (it takes the stage-by-stage path of b200.hpp): k caches inside a parallel multi-stage.  Sweeps
  *   with IJ extents work like the others (the halo threads sweep their columns with their own windows; a cache is
  *   filled / flushed on the columns inside its placeholder's IJ extent).  Consecutive column-local forward / backward
@@ -128,7 +133,8 @@ namespace gridtools {
                     int_t Prefetch = 4,
                     bool PrefetchL1 = true,
                     int_t ParallelPrefetch = 0,
-                    bool StageReadOnly = true>
+                    bool StageReadOnly = true,
+                    bool RegisterTiles = true>
                 struct geometry {
                     static constexpr int_t bi = BI, bj = BJ, kb = KB, sweep_unroll = SweepUnroll, prefetch = Prefetch;
                     static constexpr bool chain_sweeps = ChainSweeps, prefetch_l1 = PrefetchL1;
@@ -139,6 +145,10 @@ namespace gridtools {
                     // the same inside the KB levels a CTA of a parallel multi-stage walks (every thread asks for its
                     // own point of the halo-extended tile; not measured yet, hence off)
                     static constexpr int_t parallel_prefetch = ParallelPrefetch;
+                    // parallel multi-stages whose temporaries are all ij caches: one thread per column i and level, the
+                    // temporaries in per-thread REGISTER tiles that slide along j (no shared-memory tiles, no barriers
+                    // between the stages; see hz_body)
+                    static constexpr bool register_tiles = RegisterTiles;
                 };
 
                 template <class Extent>
@@ -328,6 +338,50 @@ namespace gridtools {
                         .template set<sid::property::strides_kind, window_kind>();
                 }
 
+                // ---------------------------------------------------------------- register tiles (ij caches, per thread)
+                // What the reference's gpu_horizontal backend does with its j caches (gpu_horizontal/j_cache.hpp:31-52,
+                // entry_point.hpp:57-100): a thread walks the rows of its block along j and keeps every temporary of the
+                // multi-stage in a small register array that covers the temporary's IJ extent around the thread's column
+                // and current row; the stages are evaluated for every column offset of their extent (redundantly, instead
+                // of reading a neighbour's result through shared memory) and the arrays slide by one row per step.
+                template <class T, class Extent>
+                struct rtile {
+                    static constexpr int_t iminus = Extent::iminus::value, jminus = Extent::jminus::value;
+                    static constexpr int_t iw = Extent::iplus::value - iminus + 1, jw = Extent::jplus::value - jminus + 1;
+                    T m_v[iw * jw];
+                    GT_FUNCTION T *ptr() { return m_v + (-iminus * jw - jminus); }
+                    GT_FUNCTION void slide() {
+#pragma unroll
+                        for (int_t i = 0; i < iw; ++i)
+#pragma unroll
+                            for (int_t j = 0; j + 1 < jw; ++j)
+                                m_v[i * jw + j] = m_v[i * jw + j + 1];
+                    }
+                };
+                template <class Info>
+                using rtile_of = rtile<std::remove_const_t<typename Info::data_t>, typename Info::extent_t>;
+
+                // what stands for such a temporary inside the composite: no memory, the strides of its register tile
+                template <class JWidth>
+                struct rtile_kind {};
+                template <class T, class Extent>
+                auto make_rtile_stub() {
+                    using jw_t = integral_constant<int_t, rtile<T, Extent>::jw>;
+                    return sid::synthetic()
+                        .template set<sid::property::origin>(null_holder<T>{})
+                        .template set<sid::property::strides>(
+                            hymap::keys<dim::i, dim::j>::make_values(jw_t(), integral_constant<int_t, 1>()))
+                        .template set<sid::property::ptr_diff, int_t>()
+                        .template set<sid::property::strides_kind, rtile_kind<jw_t>>();
+                }
+
+                // can a multi-stage run on register tiles?  parallel, every temporary it touches is an ij cache
+                template <class Info>
+                using is_rtile_compatible = std::bool_constant<is_ij_cached<Info>::value || (is_plain<Info>::value && !Info::is_tmp_t::value)>;
+                template <class Mss>
+                using mss_is_horizontal = std::bool_constant<be_api::is_parallel<typename Mss::execution_t>::value &&
+                                                             meta::all_of<is_rtile_compatible, typename Mss::plh_map_t>::value>;
+
                 // Fields a multi-stage only reads go through the read-only data path (ld.global.nc), which also lets the
                 // compiler move their loads across the stores of the sweep (the reference: gpu/entry_point.hpp:135-147).
                 // Window and tile pointers are pointers to non-const and never take this overload.
@@ -369,6 +423,70 @@ namespace gridtools {
 
                 // ---------------------------------------------------------------- per-thread body of one multi-stage
                 // `Volatile`: placeholders written somewhere in the same launch (see body_chain), never read-only loaded
+                // Fills the staged tiles of a CTA: levels [block_k * KB, block_k * KB + KB) of the halo-extended IJ tile of
+                // every staged field.  TMA where the field is addressable (one elected thread, completion on an
+                // mbarrier), a cooperative copy otherwise; points outside the extended compute domain are zeros.
+                template <class Cta, class Geo, class StagedInfos, int_t Threads, class StagedSrcs>
+                GT_FUNCTION void fill_staged_tiles(
+                    int_t tid, StagedSrcs const &staged, int_t k_total, int_t ni, int_t nj, int_t bar_off) {
+                    const int_t k0 = Cta::block_k() * Geo::kb, i0 = Cta::block_i() * Geo::bi, j0 = Cta::block_j() * Geo::bj;
+#ifdef __CUDA_ARCH__
+                    uint64_t *bar = reinterpret_cast<uint64_t *>(Cta::smem() + bar_off);
+                    uint32_t tx_bytes = 0;
+                    if (tid == 0) {
+                        tma::mbar_init(bar);
+                        tuple_util::host_device::for_each(
+                            [&](auto info, auto const &src) GT_FORCE_INLINE_LAMBDA {
+                                using info_t = decltype(info);
+                                using shape_t = staged_shape<std::remove_const_t<typename info_t::data_t>, Geo,
+                                    to_horizontal_extent<typename info_t::extent_t>>;
+                                if (src.m_tma)
+                                    tx_bytes += shape_t::bytes;
+                            },
+                            meta::rename<tuple, StagedInfos>(),
+                            staged);
+                        if (tx_bytes) {
+                            tma::expect_tx(bar, tx_bytes);
+                            tuple_util::host_device::for_each(
+                                [&](auto, auto const &src) GT_FORCE_INLINE_LAMBDA {
+                                    if (src.m_tma)
+                                        tma::load_3d(Cta::smem() + src.m_start, src.m_map, bar, i0, j0, k0);
+                                },
+                                meta::rename<tuple, StagedInfos>(),
+                                staged);
+                        }
+                    }
+#endif
+                    tuple_util::host_device::for_each(
+                        [&](auto info, auto const &src) GT_FORCE_INLINE_LAMBDA {
+                            using info_t = decltype(info);
+                            using T = std::remove_const_t<typename info_t::data_t>;
+                            using ext_t = to_horizontal_extent<typename info_t::extent_t>;
+                            using shape_t = staged_shape<T, Geo, ext_t>;
+                            if (src.m_tma)
+                                return;
+                            T *tile = reinterpret_cast<T *>(Cta::smem() + src.m_start);
+                            for (int_t idx = tid; idx < shape_t::w * shape_t::h * Geo::kb; idx += Threads) {
+                                const int_t x = idx % shape_t::w, r = idx / shape_t::w, y = r % shape_t::h, z = r / shape_t::h;
+                                const int_t gi = i0 + ext_t::iminus::value + x, gj = j0 + ext_t::jminus::value + y,
+                                            gk = k0 + z;
+                                const bool inside = x < shape_t::used_w && gi < ni + ext_t::iplus::value &&
+                                                    gj < nj + ext_t::jplus::value && gk < k_total;
+                                tile[idx] = inside ? src.m_origin[gi + gj * src.m_sj + gk * src.m_sk] : T(0);
+                            }
+                        },
+                        meta::rename<tuple, StagedInfos>(),
+                        staged);
+                    Cta::sync(); // the cooperative copies, and the mbarrier initialisation, are visible to every thread
+#ifdef __CUDA_ARCH__
+                    bool any_tma = false;
+                    tuple_util::host_device::for_each(
+                        [&](auto const &src) GT_FORCE_INLINE_LAMBDA { any_tma = any_tma || src.m_tma; }, staged);
+                    if (any_tma)
+                        tma::wait(bar);
+#endif
+                }
+
                 template <class Cta,
                     class Mss,
                     class Geo,
@@ -449,68 +567,10 @@ namespace gridtools {
                         run(std::bool_constant<parallel>(), ptr, p);
                     }
 
-                    // Fills the staged tiles of this CTA: levels [block_k * KB, block_k * KB + KB) of the halo-extended
-                    // IJ tile of every staged field.  TMA where the field is addressable (one elected thread, completion
-                    // on an mbarrier), a cooperative copy otherwise; points outside the extended compute domain are zeros.
                     GT_FUNCTION void fill_staged(int_t tid) const {
                         int_t k_total = 0;
                         tuple_util::host_device::for_each([&](int_t size) GT_FORCE_INLINE_LAMBDA { k_total += size; }, m_k_sizes);
-                        const int_t k0 = Cta::block_k() * Geo::kb, i0 = Cta::block_i() * Geo::bi, j0 = Cta::block_j() * Geo::bj;
-#ifdef __CUDA_ARCH__
-                        uint64_t *bar = reinterpret_cast<uint64_t *>(Cta::smem() + m_bar);
-                        uint32_t tx_bytes = 0;
-                        if (tid == 0) {
-                            tma::mbar_init(bar);
-                            tuple_util::host_device::for_each(
-                                [&](auto info, auto const &src) GT_FORCE_INLINE_LAMBDA {
-                                    using info_t = decltype(info);
-                                    using shape_t = staged_shape<std::remove_const_t<typename info_t::data_t>, Geo,
-                                        to_horizontal_extent<typename info_t::extent_t>>;
-                                    if (src.m_tma)
-                                        tx_bytes += shape_t::bytes;
-                                },
-                                meta::rename<tuple, StagedInfos>(),
-                                m_staged);
-                            if (tx_bytes) {
-                                tma::expect_tx(bar, tx_bytes);
-                                tuple_util::host_device::for_each(
-                                    [&](auto, auto const &src) GT_FORCE_INLINE_LAMBDA {
-                                        if (src.m_tma)
-                                            tma::load_3d(Cta::smem() + src.m_start, src.m_map, bar, i0, j0, k0);
-                                    },
-                                    meta::rename<tuple, StagedInfos>(),
-                                    m_staged);
-                            }
-                        }
-#endif
-                        tuple_util::host_device::for_each(
-                            [&](auto info, auto const &src) GT_FORCE_INLINE_LAMBDA {
-                                using info_t = decltype(info);
-                                using T = std::remove_const_t<typename info_t::data_t>;
-                                using ext_t = to_horizontal_extent<typename info_t::extent_t>;
-                                using shape_t = staged_shape<T, Geo, ext_t>;
-                                if (src.m_tma)
-                                    return;
-                                T *tile = reinterpret_cast<T *>(Cta::smem() + src.m_start);
-                                for (int_t idx = tid; idx < shape_t::w * shape_t::h * Geo::kb; idx += threads) {
-                                    const int_t x = idx % shape_t::w, r = idx / shape_t::w, y = r % shape_t::h, z = r / shape_t::h;
-                                    const int_t gi = i0 + ext_t::iminus::value + x, gj = j0 + ext_t::jminus::value + y,
-                                                gk = k0 + z;
-                                    const bool inside = x < shape_t::used_w && gi < m_ni + ext_t::iplus::value &&
-                                                        gj < m_nj + ext_t::jplus::value && gk < k_total;
-                                    tile[idx] = inside ? src.m_origin[gi + gj * src.m_sj + gk * src.m_sk] : T(0);
-                                }
-                            },
-                            meta::rename<tuple, StagedInfos>(),
-                            m_staged);
-                        Cta::sync(); // the cooperative copies, and the mbarrier initialisation, are visible to every thread
-#ifdef __CUDA_ARCH__
-                        bool any_tma = false;
-                        tuple_util::host_device::for_each(
-                            [&](auto const &src) GT_FORCE_INLINE_LAMBDA { any_tma = any_tma || src.m_tma; }, m_staged);
-                        if (any_tma)
-                            tma::wait(bar);
-#endif
+                        fill_staged_tiles<Cta, Geo, StagedInfos, threads>(tid, m_staged, k_total, m_ni, m_nj, m_bar);
                     }
 
                     // parallel multi-stage: this CTA takes levels [kb * KB, kb * KB + KB) of the multi-stage's interval
@@ -668,6 +728,120 @@ namespace gridtools {
                     }
                 };
 
+                // ---------------------------------------------------------------- parallel multi-stage on register tiles
+                // One thread per column i of the block and per level of the CTA's KB levels (BI x KB threads); the thread
+                // walks the BJ rows of the block, starting as many rows early as the temporaries need to be warm.  Fields
+                // read with IJ offsets come from the staged shared-memory tiles (TMA) like on the tile path; nothing is
+                // exchanged between threads, so there is no barrier after the tiles have landed.
+                template <class Cta,
+                    class Mss,
+                    class Geo,
+                    class Holder,
+                    class Strides,
+                    class KSizes,
+                    class StagedInfos = meta::list<>,
+                    class StagedSrcs = tuple<>>
+                struct hz_body {
+                    using cta_t = Cta;
+                    using register_tiles_t = void; // (how the tests tell this body from mss_body)
+                    using extent_t = typename Mss::extent_t;
+                    using plh_map_t = typename Mss::plh_map_t;
+                    using cached_t = meta::filter<is_ij_cached, plh_map_t>;
+                    template <class Info>
+                    using is_read_only =
+                        std::bool_constant<Info::is_const_t::value && !meta::st_contains<StagedInfos, Info>::value>;
+                    using deref_t = read_only_deref<meta::transform<be_api::get_key, meta::filter<is_read_only, plh_map_t>>>;
+
+                    static constexpr bool parallel = true, chainable = false;
+                    static constexpr int_t threads = (Geo::bi * Geo::kb + 31) / 32 * 32;
+                    static_assert(threads <= 1024, "stencil::b200 register-tile path: BI x KB exceeds one CTA");
+                    // first row of the walk, relative to the block: the stages run `jplus` rows ahead of their consumers
+                    static constexpr int_t j_start = extent_t::jminus::value - extent_t::jplus::value;
+
+                    Holder m_holder;
+                    Strides m_strides;
+                    KSizes m_k_sizes;
+                    int_t m_ni, m_nj;
+                    StagedSrcs m_staged;
+                    int_t m_bar;
+
+                    // one cell at column offsets [iminus, iplus] of its extent, `jplus` rows ahead of row j
+                    template <int_t J, class Cell, class Mixed>
+                    GT_FUNCTION void exec_cell(Cell cell, Mixed const &mixed, int_t rows) const {
+                        using ext_t = typename Cell::extent_t;
+                        constexpr int_t jj = J + ext_t::jplus::value; // the row this cell computes in step J
+                        if constexpr (jj >= ext_t::jminus::value) {
+                            if (jj < rows + ext_t::jplus::value) {
+#pragma unroll
+                                for (int_t di = ext_t::iminus::value; di <= ext_t::iplus::value; ++di) {
+                                    Mixed q = mixed;
+                                    tuple_util::host_device::for_each(
+                                        [di](auto &wp, auto info) GT_FORCE_INLINE_LAMBDA {
+                                            wp += di * rtile_of<decltype(info)>::jw + ext_t::jplus::value;
+                                        },
+                                        q.primary(),
+                                        meta::rename<tuple, cached_t>());
+                                    sid::shift(q.secondary(), sid::get_stride<dim::i>(m_strides), di);
+                                    sid::shift(q.secondary(), sid::get_stride<dim::j>(m_strides), typename ext_t::jplus());
+                                    cell.template operator()<deref_t>(q, m_strides);
+                                }
+                            }
+                        }
+                    }
+
+                    template <int_t J, class Info, class Tiles, class Mixed>
+                    GT_FUNCTION void walk(Info info, Tiles &tiles, Mixed &mixed, int_t rows) const {
+                        if constexpr (J < Geo::bj) {
+                            if (J < rows) {
+                                host_device::for_each<typename Info::cells_t>(
+                                    [&](auto cell) GT_FORCE_INLINE_LAMBDA { exec_cell<J>(cell, mixed, rows); });
+                                sid::shift(mixed.secondary(), sid::get_stride<dim::j>(m_strides), integral_constant<int_t, 1>());
+                                tuple_util::host_device::for_each([](auto &t) GT_FORCE_INLINE_LAMBDA { t.slide(); }, tiles);
+                                walk<J + 1>(info, tiles, mixed, rows);
+                            }
+                        }
+                    }
+
+                    GT_FUNCTION void operator()() const {
+                        const int_t tid = Cta::tid();
+                        int_t k_total = 0;
+                        tuple_util::host_device::for_each([&](int_t size) GT_FORCE_INLINE_LAMBDA { k_total += size; }, m_k_sizes);
+                        if constexpr (meta::length<StagedInfos>::value != 0)
+                            fill_staged_tiles<Cta, Geo, StagedInfos, threads>(tid, m_staged, k_total, m_ni, m_nj, m_bar);
+                        const int_t ti = tid % Geo::bi, level = Cta::block_k() * Geo::kb + tid / Geo::bi;
+                        const int_t gi = Cta::block_i() * Geo::bi + ti;
+                        int_t rows = m_nj - Cta::block_j() * Geo::bj; // rows of this block inside the compute domain
+                        if (rows > Geo::bj)
+                            rows = Geo::bj;
+                        if (tid >= Geo::bi * Geo::kb || gi >= m_ni || level >= k_total)
+                            return;
+                        auto ptr = m_holder();
+                        sid::shift(ptr, sid::get_stride<sid::blocked_dim<dim::i>>(m_strides), Cta::block_i());
+                        sid::shift(ptr, sid::get_stride<sid::blocked_dim<dim::j>>(m_strides), Cta::block_j());
+                        sid::shift(ptr, sid::get_stride<dim::i>(m_strides), ti);
+                        sid::shift(ptr, sid::get_stride<dim::j>(m_strides), integral_constant<int_t, j_start>());
+                        sid::shift(ptr, sid::get_stride<dim::k>(m_strides), level);
+                        int_t cur = 0;
+                        tuple_util::host_device::for_each(
+                            [&](int_t size, auto info) GT_FORCE_INLINE_LAMBDA {
+                                const bool mine = level >= cur && level < cur + size;
+                                cur += size;
+                                if (!mine)
+                                    return;
+                                using keys_t = meta::transform<be_api::get_key, cached_t>;
+                                using tiles_t = hymap::from_keys_values<keys_t, meta::transform<rtile_of, cached_t>>;
+                                tiles_t tiles;
+                                auto mixed = hymap::host_device::merge(
+                                    tuple_util::host_device::transform(
+                                        [](auto &t) GT_FORCE_INLINE_LAMBDA { return t.ptr(); }, tiles),
+                                    ptr);
+                                walk<j_start>(info, tiles, mixed, rows);
+                            },
+                            m_k_sizes,
+                            Mss::interval_infos());
+                    }
+                };
+
                 // ---------------------------------------------------------------- consecutive sweeps in one launch
                 // Forward / backward multi-stages that follow each other are column-local on both sides (no IJ extents,
                 // one thread per column), so they run back to back inside one kernel: what the first leaves in device
@@ -771,6 +945,7 @@ namespace gridtools {
                     using plh_map_t = typename Mss::plh_map_t;
                     using io_cached_t = meta::filter<is_io_cached, plh_map_t>;
                     int_t smem_bytes = 0;
+                    constexpr bool horizontal = Geo::register_tiles && mss_is_horizontal<Mss>::value;
                     const int_t k_first = grid.k_start(Mss::interval(), Mss::execution());
                     // plain fields a parallel multi-stage only reads, without k offsets: staged through shared memory
                     using staged_t = meta::filter<staged_in<Mss, Geo, DataStores>::template apply, plh_map_t>;
@@ -781,10 +956,11 @@ namespace gridtools {
                         overload(
                             [&](meta::list<cache_type::ij>, auto info) {
                                 using info_t = decltype(info);
-                                return make_tile<std::remove_const_t<typename info_t::data_t>,
-                                    cta_t,
-                                    Geo,
-                                    typename info_t::extent_t>(smem_bytes);
+                                using data_t = std::remove_const_t<typename info_t::data_t>;
+                                if constexpr (horizontal)
+                                    return make_rtile_stub<data_t, typename info_t::extent_t>();
+                                else
+                                    return make_tile<data_t, cta_t, Geo, typename info_t::extent_t>(smem_bytes);
                             },
                             [](meta::list<cache_type::k>, auto info) {
                                 return make_window_stub<std::remove_const_t<typename decltype(info)::data_t>>();
@@ -861,23 +1037,41 @@ namespace gridtools {
                     int_t k_total = 0;
                     tuple_util::for_each([&](int_t n) { k_total += n; }, k_sizes);
                     const int_t ni = grid.i_size(), nj = grid.j_size();
-                    using body_t = mss_body<cta_t,
-                        Mss,
-                        Geo,
-                        meta::if_<be_api::is_parallel<typename Mss::execution_t>, meta::list<>, Volatile>,
-                        decltype(sid::get_origin(composite) + offset),
-                        decltype(strides),
-                        decltype(k_sizes),
-                        decltype(bounds),
-                        staged_t,
-                        decltype(staged_srcs)>;
-                    const int_t nbk = body_t::parallel ? (k_total + Geo::kb - 1) / Geo::kb : (k_total > 0 ? 1 : 0);
-                    return pending<body_t>{
-                        body_t{sid::get_origin(composite) + offset, strides, k_sizes, bounds, ni, nj, k_first, staged_srcs, bar_off},
-                        ni > 0 ? (ni + Geo::bi - 1) / Geo::bi : 0,
-                        nj > 0 ? (nj + Geo::bj - 1) / Geo::bj : 0,
-                        nbk,
-                        smem_bytes};
+                    const int_t nbi = ni > 0 ? (ni + Geo::bi - 1) / Geo::bi : 0, nbj = nj > 0 ? (nj + Geo::bj - 1) / Geo::bj : 0;
+                    if constexpr (horizontal) {
+                        using body_t = hz_body<cta_t,
+                            Mss,
+                            Geo,
+                            decltype(sid::get_origin(composite) + offset),
+                            decltype(strides),
+                            decltype(k_sizes),
+                            staged_t,
+                            decltype(staged_srcs)>;
+                        return pending<body_t>{
+                            body_t{sid::get_origin(composite) + offset, strides, k_sizes, ni, nj, staged_srcs, bar_off},
+                            nbi,
+                            nbj,
+                            (k_total + Geo::kb - 1) / Geo::kb,
+                            smem_bytes};
+                    } else {
+                        using body_t = mss_body<cta_t,
+                            Mss,
+                            Geo,
+                            meta::if_<be_api::is_parallel<typename Mss::execution_t>, meta::list<>, Volatile>,
+                            decltype(sid::get_origin(composite) + offset),
+                            decltype(strides),
+                            decltype(k_sizes),
+                            decltype(bounds),
+                            staged_t,
+                            decltype(staged_srcs)>;
+                        const int_t nbk = body_t::parallel ? (k_total + Geo::kb - 1) / Geo::kb : (k_total > 0 ? 1 : 0);
+                        return pending<body_t>{
+                            body_t{sid::get_origin(composite) + offset, strides, k_sizes, bounds, ni, nj, k_first, staged_srcs, bar_off},
+                            nbi,
+                            nbj,
+                            nbk,
+                            smem_bytes};
+                    }
                 }
 
                 template <class Launcher, class Geo, class Volatile, class Grid, class DataStores, class Pending>

@@ -88,6 +88,19 @@ int main() {
         test_generic_cases<st::b200<>>("fused", 128, 64, 80);
         test_generic_cases<staged_t>("staged", 70, 19, 13);
         test_generic_cases<unchained_t>("fused, sweeps unchained", 70, 19, 13);
+        // parallel multi-stages whose temporaries are all ij caches on per-thread register tiles
+        using rtiles_t = st::b200<gtb200::default_stream, gtb200::fused_when_possible,
+            gtb200::block_geometry<32, 16, 4, 3, true, 4, true, 0, true, true>>;
+        using rtiles_plain_t = st::b200<gtb200::default_stream, gtb200::fused_when_possible,
+            gtb200::block_geometry<64, 8, 2, 3, true, 4, true, 0, false, true>>;
+        test_generic_cases<rtiles_t>("register tiles", 70, 19, 13);
+        test_generic_cases<rtiles_t>("register tiles", 128, 64, 80);
+        test_generic_cases<rtiles_plain_t>("register tiles, not staged", 70, 19, 13);
+        // ... and the shared-memory tile path for the same multi-stages
+        using tiles_t = st::b200<gtb200::default_stream, gtb200::fused_when_possible,
+            gtb200::block_geometry<32, 8, 4, 3, true, 4, true, 0, true, false>>;
+        test_generic_cases<tiles_t>("shared-memory tiles", 70, 19, 13);
+        test_generic_cases<tiles_t>("shared-memory tiles", 128, 64, 80);
     } catch (std::exception const &e) {
         std::printf("EXCEPTION: %s\n", e.what());
         return 2;

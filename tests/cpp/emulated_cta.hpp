@@ -51,9 +51,19 @@ namespace emulated {
             return n;
         }
 
+        static long &register_tile_launches() { // launches of multi-stages that ran on per-thread register tiles
+            static long n = 0;
+            return n;
+        }
+        template <class Body, class = void>
+        struct on_register_tiles : std::false_type {};
+        template <class Body>
+        struct on_register_tiles<Body, std::void_t<typename Body::register_tiles_t>> : std::true_type {};
+
         template <class Body>
         void launch(Body const &body, int_t nbi, int_t nbj, int_t nbk, int_t threads, int_t smem) {
             ++launches;
+            register_tile_launches() += on_register_tiles<Body>::value;
             std::vector<char> shared(smem + 16);
             omp_set_dynamic(0);
             for (int_t bk = 0; bk < nbk; ++bk)

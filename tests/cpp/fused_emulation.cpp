@@ -188,21 +188,41 @@ void c_arrays() {
     g_failed += bad != 0;
 }
 
+// shared-memory tiles for the ij caches (RegisterTiles = false) ...
+template <int BI = 32, int BJ = 8, int KB = 4, int U = 3, bool Chain = true, int P = 4, bool L1 = true, int PP = 0, bool Stage = true>
+using tiles = fused::geometry<BI, BJ, KB, U, Chain, P, L1, PP, Stage, false>;
+// ... or per-thread register tiles wherever a parallel multi-stage allows it (the default)
+template <int BI = 32, int BJ = 8, int KB = 4, bool Stage = true>
+using rtiles = fused::geometry<BI, BJ, KB, 3, true, 4, true, 0, Stage, true>;
+
 int main() {
+#ifndef GTB_ONLY_REGISTER_TILES
     c_arrays();
     // small blocks: many CTAs, partial tiles in i and j, partial k blocks
-    run<fused::geometry<8, 4, 3>>{"[8x4x3 blocks]"}.all(19, 9, 7);
-    run<fused::geometry<8, 4, 3>>{"[8x4x3 blocks]"}.all(8, 4, 3);
-    run<fused::geometry<8, 4, 3>>{"[8x4x3 blocks]"}.all(1, 1, 2);
-    // the default geometry on a domain of a few blocks
-    run<fused::geometry<>>{"[32x8x8 blocks]"}.all(37, 11, 10);
+    run<tiles<8, 4, 3>>{"[8x4x3 blocks]"}.all(19, 9, 7);
+    run<tiles<8, 4, 3>>{"[8x4x3 blocks]"}.all(8, 4, 3);
+    run<tiles<8, 4, 3>>{"[8x4x3 blocks]"}.all(1, 1, 2);
+    // the former default geometry on a domain of a few blocks
+    run<tiles<32, 8, 8>>{"[32x8x8 blocks]"}.all(37, 11, 10);
     // extremes: one level per CTA with tiny blocks; all levels in one CTA with a wide block
-    run<fused::geometry<4, 2, 1>>{"[4x2x1 blocks]"}.all(9, 5, 4);
-    run<fused::geometry<64, 4, 80>>{"[64x4x80 blocks]"}.all(70, 6, 5);
+    run<tiles<4, 2, 1>>{"[4x2x1 blocks]"}.all(9, 5, 4);
+    run<tiles<64, 4, 80>>{"[64x4x80 blocks]"}.all(70, 6, 5);
     // prefetch ahead (a no-op on the host, but the address arithmetic is instantiated)
-    run<fused::geometry<8, 4, 3, 2, true, 4, true, 1>>{"[8x4x3 blocks, prefetch]"}.all(19, 9, 7);
+    run<tiles<8, 4, 3, 2, true, 4, true, 1>>{"[8x4x3 blocks, prefetch]"}.all(19, 9, 7);
     // sweeps in separate launches
-    run<fused::geometry<8, 4, 3, 2, false>>{"[8x4x3 blocks, unchained]"}.all(19, 9, 7);
+    run<tiles<8, 4, 3, 2, false>>{"[8x4x3 blocks, unchained]"}.all(19, 9, 7);
+    const long before = emulated::launcher::register_tile_launches();
+    if (before != 0)
+        ++g_failed; // nothing above may have taken the register-tile path
+#endif
+    // parallel multi-stages whose temporaries are all ij caches on per-thread register tiles (the others as before)
+    run<rtiles<8, 4, 3>>{"[8x4x3 blocks, register tiles]"}.all(19, 9, 7);
+    run<rtiles<8, 4, 3>>{"[8x4x3 blocks, register tiles]"}.all(1, 1, 2);
+    run<fused::geometry<>>{"[default geometry]"}.all(37, 11, 10);
+    run<rtiles<4, 2, 1, false>>{"[4x2x1 blocks, register tiles, not staged]"}.all(9, 5, 4);
+    std::printf("launches on register tiles: %ld\n", emulated::launcher::register_tile_launches());
+    if (emulated::launcher::register_tile_launches() == 0)
+        ++g_failed; // horizontal diffusion and friends must take that path in the register-tile configurations
     std::printf("fields staged through (emulated) shared memory: %ld\n", emulated::launcher::staged_fields());
     if (emulated::launcher::staged_fields() == 0)
         ++g_failed; // the staging of read-only fields of parallel multi-stages must be exercised here

@@ -126,9 +126,12 @@ namespace {
         double t = time_us([&](int s) { s == 0 ? call(s0) : call(s1); }, SETS);
         report("vertical_advection_dycore", name, t, 1. * ni * nj * nk, 48);
     }
-    template <int BI, int BJ, int KB, int U = 1, bool Chain = true, int P = 0, bool L1 = false, int PP = 0, bool Stage = true>
+    template <int BI, int BJ, int KB, int U = 1, bool Chain = true, int P = 0, bool L1 = false, int PP = 0, bool Stage = true,
+        bool RegisterTiles = false>
     using fused_t = st::b200<gtb200::default_stream, gtb200::fused_when_possible,
-        gtb200::block_geometry<BI, BJ, KB, U, Chain, P, L1, PP, Stage>>;
+        gtb200::block_geometry<BI, BJ, KB, U, Chain, P, L1, PP, Stage, RegisterTiles>>;
+    template <int BI, int BJ, int KB, bool Stage = true>
+    using rtile_t = fused_t<BI, BJ, KB, 3, true, 4, true, 0, Stage, true>;
 } // namespace
 
 int main(int argc, char **argv) {
@@ -149,13 +152,19 @@ int main(int argc, char **argv) {
         vert_adv<1>("stencil::b200<> staged", staged_t(), ni, nj, nk);
 #else
         // block geometries / sweep unroll factors of the fused generic path (make -C tests/cpp fused_timing)
+        // register tiles: one thread per column and level, temporaries in registers sliding along j
+        hori_diff<1>("register tiles 32x8x4", rtile_t<32, 8, 4>(), ni, nj, nk);
+        hori_diff<1>("register tiles 32x16x4", rtile_t<32, 16, 4>(), ni, nj, nk);
+        hori_diff<1>("register tiles 64x16x4", rtile_t<64, 16, 4>(), ni, nj, nk);
+        hori_diff<1>("register tiles 64x8x4", rtile_t<64, 8, 4>(), ni, nj, nk);
+        hori_diff<1>("register tiles 32x16x8", rtile_t<32, 16, 8>(), ni, nj, nk);
+        hori_diff<1>("register tiles 64x16x2", rtile_t<64, 16, 2>(), ni, nj, nk);
+        hori_diff<1>("register tiles 32x16x4 not staged", rtile_t<32, 16, 4, false>(), ni, nj, nk);
+        hori_diff<1>("register tiles 128x16x2 not staged", rtile_t<128, 16, 2, false>(), ni, nj, nk);
         hori_diff<1>("fused 32x8x8 TMA-staged", fused_t<32, 8, 8>(), ni, nj, nk);
         hori_diff<1>("fused 32x8x8 not staged", fused_t<32, 8, 8, 3, true, 4, true, 0, false>(), ni, nj, nk);
         hori_diff<1>("fused 32x8x4 TMA-staged", fused_t<32, 8, 4>(), ni, nj, nk);
-        hori_diff<1>("fused 32x8x16 TMA-staged", fused_t<32, 8, 16>(), ni, nj, nk);
         hori_diff<1>("fused 64x8x8 TMA-staged", fused_t<64, 8, 8>(), ni, nj, nk);
-        hori_diff<1>("fused 32x16x8 TMA-staged", fused_t<32, 16, 8>(), ni, nj, nk);
-        hori_diff<1>("fused 64x4x8 TMA-staged", fused_t<64, 4, 8>(), ni, nj, nk);
         vert_adv<1>("fused unroll 3 prefetch 4 L1", fused_t<32, 8, 8, 3, true, 4, true>(), ni, nj, nk);
         vert_adv<1>("fused unroll 3 prefetch 2 L1", fused_t<32, 8, 8, 3, true, 2, true>(), ni, nj, nk);
         vert_adv<1>("fused unroll 3 prefetch 3 L1", fused_t<32, 8, 8, 3, true, 3, true>(), ni, nj, nk);
