@@ -945,7 +945,9 @@ namespace gridtools {
                     using plh_map_t = typename Mss::plh_map_t;
                     using io_cached_t = meta::filter<is_io_cached, plh_map_t>;
                     int_t smem_bytes = 0;
-                    constexpr bool horizontal = Geo::register_tiles && mss_is_horizontal<Mss>::value;
+                    // (a geometry with more than 1024 column-levels per CTA keeps the tile path)
+                    constexpr bool horizontal =
+                        Geo::register_tiles && mss_is_horizontal<Mss>::value && Geo::bi * Geo::kb <= 1024;
                     const int_t k_first = grid.k_start(Mss::interval(), Mss::execution());
                     // plain fields a parallel multi-stage only reads, without k offsets: staged through shared memory
                     using staged_t = meta::filter<staged_in<Mss, Geo, DataStores>::template apply, plh_map_t>;

@@ -198,6 +198,7 @@ using rtiles = fused::geometry<BI, BJ, KB, 3, true, 4, true, 0, Stage, true>;
 int main() {
 #ifndef GTB_ONLY_REGISTER_TILES
     c_arrays();
+    const long before = emulated::launcher::register_tile_launches();
     // small blocks: many CTAs, partial tiles in i and j, partial k blocks
     run<tiles<8, 4, 3>>{"[8x4x3 blocks]"}.all(19, 9, 7);
     run<tiles<8, 4, 3>>{"[8x4x3 blocks]"}.all(8, 4, 3);
@@ -211,9 +212,8 @@ int main() {
     run<tiles<8, 4, 3, 2, true, 4, true, 1>>{"[8x4x3 blocks, prefetch]"}.all(19, 9, 7);
     // sweeps in separate launches
     run<tiles<8, 4, 3, 2, false>>{"[8x4x3 blocks, unchained]"}.all(19, 9, 7);
-    const long before = emulated::launcher::register_tile_launches();
-    if (before != 0)
-        ++g_failed; // nothing above may have taken the register-tile path
+    if (emulated::launcher::register_tile_launches() != before)
+        ++g_failed; // none of the `tiles` configurations may have taken the register-tile path
 #endif
     // parallel multi-stages whose temporaries are all ij caches on per-thread register tiles (the others as before)
     run<rtiles<8, 4, 3>>{"[8x4x3 blocks, register tiles]"}.all(19, 9, 7);
