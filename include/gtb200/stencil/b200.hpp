@@ -98,9 +98,19 @@ namespace gtb200 {
         bool PrefetchL1 = true,
         int ParallelPrefetch = 0,
         bool StageReadOnly = true,
-        bool RegisterTiles = true>
-    using block_geometry = ::gridtools::stencil::b200_backend::fused::
-        geometry<BI, BJ, KB, SweepUnroll, ChainSweeps, Prefetch, PrefetchL1, ParallelPrefetch, StageReadOnly, RegisterTiles>;
+        bool RegisterTiles = true,
+        bool L2Hints = false>
+    using block_geometry = ::gridtools::stencil::b200_backend::fused::geometry<BI,
+        BJ,
+        KB,
+        SweepUnroll,
+        ChainSweeps,
+        Prefetch,
+        PrefetchL1,
+        ParallelPrefetch,
+        StageReadOnly,
+        RegisterTiles,
+        L2Hints>;
     using default_geometry = ::gridtools::stencil::b200_backend::fused::geometry<>;
 #else
     struct default_geometry {};

@@ -134,7 +134,8 @@ namespace gridtools {
                     bool PrefetchL1 = true,
                     int_t ParallelPrefetch = 0,
                     bool StageReadOnly = true,
-                    bool RegisterTiles = true>
+                    bool RegisterTiles = true,
+                    bool L2Hints = false>
                 struct geometry {
                     static constexpr int_t bi = BI, bj = BJ, kb = KB, sweep_unroll = SweepUnroll, prefetch = Prefetch;
                     static constexpr bool chain_sweeps = ChainSweeps, prefetch_l1 = PrefetchL1;
@@ -149,6 +150,11 @@ namespace gridtools {
                     // temporaries in per-thread REGISTER tiles that slide along j (no shared-memory tiles, no barriers
                     // between the stages; see hz_body)
                     static constexpr bool register_tiles = RegisterTiles;
+                    // forward / backward multi-stages: what a sweep flushes into a temporary is stored with L2 priority
+                    // `evict_last`, the temporaries and the fields a sweep only streams through are read `evict_first`,
+                    // so that flush -> fill pairs between chained sweeps (vertical advection: ccol, dcol, 84 MB at
+                    // 256x256x80) stay in the 126 MB L2 instead of going through HBM
+                    static constexpr bool l2_hints = L2Hints;
                 };
 
                 template <class Extent>
@@ -385,14 +391,83 @@ namespace gridtools {
                 // Fields a multi-stage only reads go through the read-only data path (ld.global.nc), which also lets the
                 // compiler move their loads across the stores of the sweep (the reference: gpu/entry_point.hpp:135-147).
                 // Window and tile pointers are pointers to non-const and never take this overload.
-                template <class ConstKeys>
+                // L2 eviction priorities for the accesses of a sweep (geometry::l2_hints); 4- and 8-byte elements
+                namespace l2 {
+                    template <class T>
+                    using hintable = std::bool_constant<std::is_arithmetic<T>::value && (sizeof(T) == 4 || sizeof(T) == 8)>;
+#ifdef __CUDA_ARCH__
+                    __device__ __forceinline__ uint64_t evict_first() {
+                        uint64_t p;
+                        asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+                        return p;
+                    }
+                    __device__ __forceinline__ uint64_t evict_last() {
+                        uint64_t p;
+                        asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+                        return p;
+                    }
+                    template <bool NonCoherent, class T>
+                    __device__ __forceinline__ T load_evict_first(T const *ptr) {
+                        const uint64_t pol = evict_first();
+                        T v;
+                        if constexpr (sizeof(T) == 8) {
+                            uint64_t r;
+                            if constexpr (NonCoherent)
+                                asm volatile("ld.global.nc.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(r) : "l"(ptr), "l"(pol));
+                            else
+                                asm volatile("ld.global.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(r) : "l"(ptr), "l"(pol) : "memory");
+                            memcpy(&v, &r, 8);
+                        } else {
+                            uint32_t r;
+                            if constexpr (NonCoherent)
+                                asm volatile("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(r) : "l"(ptr), "l"(pol));
+                            else
+                                asm volatile("ld.global.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(r) : "l"(ptr), "l"(pol) : "memory");
+                            memcpy(&v, &r, 4);
+                        }
+                        return v;
+                    }
+                    template <class T>
+                    __device__ __forceinline__ void store_evict_last(T *ptr, T v) {
+                        const uint64_t pol = evict_last();
+                        if constexpr (sizeof(T) == 8) {
+                            uint64_t r;
+                            memcpy(&r, &v, 8);
+                            asm volatile("st.global.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(ptr), "l"(r), "l"(pol) : "memory");
+                        } else {
+                            uint32_t r;
+                            memcpy(&r, &v, 4);
+                            asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(ptr), "r"(r), "l"(pol) : "memory");
+                        }
+                    }
+#endif
+                } // namespace l2
+
+                // `Stream`: read-only fields are read `evict_first` (they pass through a sweep once); `DeadAfterRead`: keys
+                // of temporaries an earlier sweep of the launch has written and this multi-stage only reads
+                template <class ConstKeys, bool Stream = false, class DeadAfterRead = meta::list<>>
                 struct read_only_deref {
                     template <class Key,
                         class T,
                         std::enable_if_t<meta::st_contains<ConstKeys, Key>::value && std::is_arithmetic<T>::value, int> = 0>
                     GT_FUNCTION T operator()(Key, T const *ptr) const {
 #ifdef __CUDA_ARCH__
-                        return __ldg(ptr);
+                        if constexpr (Stream && l2::hintable<T>::value)
+                            return l2::load_evict_first<true>(ptr);
+                        else
+                            return __ldg(ptr);
+#else
+                        return *ptr;
+#endif
+                    }
+                    template <class Key,
+                        class T,
+                        std::enable_if_t<!meta::st_contains<ConstKeys, Key>::value && meta::st_contains<DeadAfterRead, Key>::value &&
+                                             l2::hintable<T>::value,
+                            int> = 0>
+                    GT_FUNCTION T operator()(Key, T const *ptr) const {
+#ifdef __CUDA_ARCH__
+                        return l2::load_evict_first<false>(ptr);
 #else
                         return *ptr;
 #endif
@@ -421,8 +496,6 @@ namespace gridtools {
                     int_t lo, hi; // valid levels of the field behind a cache, relative to the grid's k origin
                 };
 
-                // ---------------------------------------------------------------- per-thread body of one multi-stage
-                // `Volatile`: placeholders written somewhere in the same launch (see body_chain), never read-only loaded
                 // Fills the staged tiles of a CTA: levels [block_k * KB, block_k * KB + KB) of the halo-extended IJ tile of
                 // every staged field.  TMA where the field is addressable (one elected thread, completion on an
                 // mbarrier), a cooperative copy otherwise; points outside the extended compute domain are zeros.
@@ -487,6 +560,8 @@ namespace gridtools {
 #endif
                 }
 
+                // ---------------------------------------------------------------- per-thread body of one multi-stage
+                // `Volatile`: placeholders written somewhere in the same launch (see body_chain), never read-only loaded
                 template <class Cta,
                     class Mss,
                     class Geo,
@@ -509,7 +584,17 @@ namespace gridtools {
                     using is_read_only = std::bool_constant<Info::is_const_t::value &&
                                                             !meta::st_contains<Volatile, typename Info::plh_t>::value &&
                                                             !meta::st_contains<StagedInfos, Info>::value>;
-                    using deref_t = read_only_deref<meta::transform<be_api::get_key, meta::filter<is_read_only, plh_map_t>>>;
+                    // temporaries an earlier sweep of this launch wrote and this multi-stage only reads, uncached
+                    template <class Info>
+                    using is_dead_after_read = std::bool_constant<Info::is_const_t::value && Info::is_tmp_t::value &&
+                                                                  is_plain<Info>::value &&
+                                                                  meta::st_contains<Volatile, typename Info::plh_t>::value>;
+                    static constexpr bool hints = Geo::l2_hints && !be_api::is_parallel<typename Mss::execution_t>::value;
+                    using deref_t = read_only_deref<meta::transform<be_api::get_key, meta::filter<is_read_only, plh_map_t>>,
+                        hints,
+                        meta::if_c<hints,
+                            meta::transform<be_api::get_key, meta::filter<is_dead_after_read, plh_map_t>>,
+                            meta::list<>>>;
 
                     static constexpr bool parallel = be_api::is_parallel<typename Mss::execution_t>::value;
                     // column-local sweeps may share a launch with their neighbours (body_chain)
@@ -623,14 +708,24 @@ namespace gridtools {
                             constexpr bool read_only = !has_flush<Info>::value && std::is_arithmetic<value_t>::value &&
                                                        !meta::st_contains<Volatile, typename Info::plh_t>::value;
 #ifdef __CUDA_ARCH__
-                            if constexpr (read_only)
+                            if constexpr (read_only && hints && l2::hintable<value_t>::value)
+                                win.ptr()[W] = l2::load_evict_first<true>(&*mem);
+                            else if constexpr (read_only)
                                 win.ptr()[W] = __ldg(&*mem);
                             else
 #endif
                                 win.ptr()[W] = *mem;
                             (void)read_only;
                         } else {
-                            *mem = win.ptr()[W];
+                            using value_t = std::remove_cv_t<std::remove_reference_t<decltype(*mem)>>;
+#ifdef __CUDA_ARCH__
+                            // what a sweep flushes into a temporary is read again by a later sweep: keep it in L2
+                            if constexpr (hints && Info::is_tmp_t::value && l2::hintable<value_t>::value)
+                                l2::store_evict_last(&*mem, value_t(win.ptr()[W]));
+                            else
+#endif
+                                *mem = win.ptr()[W];
+                            (void)sizeof(value_t);
                         }
                     }
 

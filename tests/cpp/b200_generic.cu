@@ -96,6 +96,10 @@ int main() {
         test_generic_cases<rtiles_t>("register tiles", 70, 19, 13);
         test_generic_cases<rtiles_t>("register tiles", 128, 64, 80);
         test_generic_cases<rtiles_plain_t>("register tiles, not staged", 70, 19, 13);
+        // sweeps with L2 eviction priorities on their flushes, fills and streamed fields
+        using hinted_t = st::b200<gtb200::default_stream, gtb200::fused_when_possible,
+            gtb200::block_geometry<32, 8, 4, 3, true, 4, true, 0, true, true, true>>;
+        test_generic_cases<hinted_t>("L2 hints", 70, 19, 13);
         // ... and the shared-memory tile path for the same multi-stages
         using tiles_t = st::b200<gtb200::default_stream, gtb200::fused_when_possible,
             gtb200::block_geometry<32, 8, 4, 3, true, 4, true, 0, true, false>>;

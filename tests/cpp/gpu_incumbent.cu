@@ -127,9 +127,9 @@ namespace {
         report("vertical_advection_dycore", name, t, 1. * ni * nj * nk, 48);
     }
     template <int BI, int BJ, int KB, int U = 1, bool Chain = true, int P = 0, bool L1 = false, int PP = 0, bool Stage = true,
-        bool RegisterTiles = false>
+        bool RegisterTiles = false, bool L2Hints = false>
     using fused_t = st::b200<gtb200::default_stream, gtb200::fused_when_possible,
-        gtb200::block_geometry<BI, BJ, KB, U, Chain, P, L1, PP, Stage, RegisterTiles>>;
+        gtb200::block_geometry<BI, BJ, KB, U, Chain, P, L1, PP, Stage, RegisterTiles, L2Hints>>;
     template <int BI, int BJ, int KB, bool Stage = true>
     using rtile_t = fused_t<BI, BJ, KB, 3, true, 4, true, 0, Stage, true>;
 } // namespace
@@ -157,14 +157,17 @@ int main(int argc, char **argv) {
         hori_diff<1>("register tiles 32x16x4", rtile_t<32, 16, 4>(), ni, nj, nk);
         hori_diff<1>("register tiles 64x16x4", rtile_t<64, 16, 4>(), ni, nj, nk);
         hori_diff<1>("register tiles 64x8x4", rtile_t<64, 8, 4>(), ni, nj, nk);
-        hori_diff<1>("register tiles 32x16x8", rtile_t<32, 16, 8>(), ni, nj, nk);
-        hori_diff<1>("register tiles 64x16x2", rtile_t<64, 16, 2>(), ni, nj, nk);
         hori_diff<1>("register tiles 32x16x4 not staged", rtile_t<32, 16, 4, false>(), ni, nj, nk);
         hori_diff<1>("register tiles 128x16x2 not staged", rtile_t<128, 16, 2, false>(), ni, nj, nk);
         hori_diff<1>("fused 32x8x8 TMA-staged", fused_t<32, 8, 8>(), ni, nj, nk);
         hori_diff<1>("fused 32x8x8 not staged", fused_t<32, 8, 8, 3, true, 4, true, 0, false>(), ni, nj, nk);
         hori_diff<1>("fused 32x8x4 TMA-staged", fused_t<32, 8, 4>(), ni, nj, nk);
         hori_diff<1>("fused 64x8x8 TMA-staged", fused_t<64, 8, 8>(), ni, nj, nk);
+        // sweeps with L2 eviction priorities: flushed temporaries evict_last, streamed fields and dead temporaries evict_first
+        vert_adv<1>("fused L2 hints, prefetch 2 L1", fused_t<32, 8, 8, 3, true, 2, true, 0, true, true, true>(), ni, nj, nk);
+        vert_adv<1>("fused L2 hints, prefetch 4 L1", fused_t<32, 8, 8, 3, true, 4, true, 0, true, true, true>(), ni, nj, nk);
+        vert_adv<1>("fused L2 hints, no prefetch", fused_t<32, 8, 8, 3, true, 0, true, 0, true, true, true>(), ni, nj, nk);
+        vert_adv<1>("fused L2 hints, prefetch 4 L2", fused_t<32, 8, 8, 3, true, 4, false, 0, true, true, true>(), ni, nj, nk);
         vert_adv<1>("fused unroll 3 prefetch 4 L1", fused_t<32, 8, 8, 3, true, 4, true>(), ni, nj, nk);
         vert_adv<1>("fused unroll 3 prefetch 2 L1", fused_t<32, 8, 8, 3, true, 2, true>(), ni, nj, nk);
         vert_adv<1>("fused unroll 3 prefetch 3 L1", fused_t<32, 8, 8, 3, true, 3, true>(), ni, nj, nk);
