@@ -165,6 +165,31 @@ def test_hori_diff_full_size(gt, oracle):
             assert np.array_equal(out[inner], want), variant
 
 
+def test_last_kernel_reports_the_automatic_choice(gt):
+    """gtb_last_kernel: a short launch takes the one-CTA two-pipeline kernel (programmatic dependent launch), an explicit
+    hd.variant 2 or SMs reserved for an exchange the two-CTA kernel; vertical advection fp64 the paired-warp kernel."""
+    rng = np.random.default_rng(3)
+    inp = rng.standard_normal((8, 36, 132))
+    coeff = rng.uniform(0, 0.05, inp.shape)
+    run_hd(gt, inp, coeff)
+    assert gt.lib.last_kernel().startswith("hd_tma2_kernel")
+    gt.lib.set_option("hd.variant", 2)
+    run_hd(gt, inp, coeff)
+    assert gt.lib.last_kernel().startswith("hd_tma_kernel")
+    gt.lib.set_option("hd.variant", 0)
+    gt.lib.set_option("reserve_sms", 8)
+    try:
+        run_hd(gt, inp, coeff)
+        assert gt.lib.last_kernel().startswith("hd_tma_kernel")
+    finally:
+        gt.lib.set_option("reserve_sms", 0)
+    shape = (20, 11, 70)
+    arrs = [rng.uniform(5, 9, shape), rng.uniform(5, 9, shape), rng.uniform(-3e-4, 3e-4, shape),
+            rng.uniform(5, 9, shape), rng.uniform(-1e-5, 1e-5, shape)]
+    run_va(gt, arrs, 0.15)
+    assert gt.lib.last_kernel().startswith("va_pair_kernel")
+
+
 def test_hori_diff_linearity(gt):
     """Size-independent property at 512x512x80 fp32 (configs[2]): scaling `in` by a power of two scales `out`
     exactly (the flux limiter only looks at signs)."""
