@@ -8,6 +8,9 @@ oracle/mpi_shim (MPI, threads as ranks), plus the one block a maintainer adds to
   regression_b200      tests/regression/*.cpp (19 sources) + tests/src/regression_main.cpp with
                        stencil_backend_t = gridtools::stencil::b200<>, no registration lines: the generic fused path
                        (incl. boundary_conditions.cpp with gcl_arch_t = gridtools::gcl::b200)
+  regression_emulated  the same 18 stencil sources with stencil_backend_t = emulated::backend<> (g++ only): the very bodies
+                       of the generic path -- register tiles, shared-memory tiles, register windows, chained sweeps -- run
+                       by emulated CTAs on the host, no GPU
 """
 import os
 import subprocess
@@ -32,6 +35,14 @@ def test_reference_gcl_test_passes_on_its_own_cpu_arch_through_the_shims():
     sets) on gcl::cpu with 2 thread-ranks: the unmodified reference passes its own test on gtest_shim + mpi_shim."""
     rc, out, tail = run("gcl_reference_cpu", 2)
     assert rc == 0 and "ALL PASSED" in out, tail
+
+
+def test_reference_regression_sources_pass_on_emulated_ctas():
+    """tests/regression/*.cpp, unchanged, through the generic path's per-thread bodies on emulated CTAs (cpu_ifirst
+    stores): float and double, both inlined domain sizes, verified by the reference's own verifier.  No GPU."""
+    rc, out, tail = run("regression_emulated", timeout=600)
+    assert rc == 0 and "[  FAILED  ]" not in out, tail
+    assert "tests ran" in out and int(out.split("[==========] ")[-1].split(" tests ran")[0]) >= 50, tail
 
 
 @pytest.mark.gpu
