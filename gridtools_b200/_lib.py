@@ -113,6 +113,8 @@ _SIG = {
                           C.POINTER(C.c_int)]),
     "gtb_device_malloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "gtb_device_free": (C.c_int, [C.c_void_p]),
+    "gtb_host_malloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
+    "gtb_host_free": (C.c_int, [C.c_void_p]),
     "gtb_staged_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "gtb_staged_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "gtb_stream_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),

@@ -397,6 +397,40 @@ namespace {
     }
 } // namespace
 
+namespace {
+    // page-locked host memory (gtb_host_malloc, cudaHostAlloc, cudaHostRegister)?
+    bool is_pinned_host(const void *p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return a.type == cudaMemoryTypeHost;
+    }
+} // namespace
+
+GTB_API int gtb_host_malloc(void **out, int64_t bytes) {
+    if (!out || bytes < 0)
+        return fail(GTB_ERR_ARG, "gtb_host_malloc: bad argument");
+    if (!dev())
+        return GTB_ERR_CUDA;
+    *out = nullptr;
+    if (bytes == 0)
+        return GTB_OK;
+    cudaError_t e = cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        cuda_fail(e, "gtb_host_malloc");
+        return GTB_ERR_ALLOC;
+    }
+    return GTB_OK;
+}
+
+GTB_API int gtb_host_free(void *p) {
+    if (p)
+        cudaFreeHost(p);
+    return GTB_OK;
+}
+
 GTB_API int gtb_device_malloc(void **out, int64_t bytes) {
     if (!out || bytes < 0)
         return fail(GTB_ERR_ARG, "gtb_device_malloc: bad argument");
@@ -422,10 +456,17 @@ GTB_API int gtb_device_free(void *p) {
 GTB_API int gtb_staged_upload(void *device_dst, const void *host_src, int64_t bytes, void *stream) {
     if (bytes < 0 || (bytes && (!device_dst || !host_src)))
         return fail(GTB_ERR_ARG, "gtb_staged_upload: bad argument");
+    if (!dev())
+        return GTB_ERR_CUDA;
+    cudaStream_t s = stream ? as_stream(stream) : cudaStreamLegacy;
+    if (bytes && is_pinned_host(host_src)) { // a pinned mirror (gtb_host_malloc): the copy engine reads it directly
+        GTB_CUDA(cudaMemcpyAsync(device_dst, host_src, (size_t)bytes, cudaMemcpyHostToDevice, s));
+        GTB_CUDA(cudaStreamSynchronize(s)); // host_src may be written again when this returns
+        return GTB_OK;
+    }
     stage_ring *r = ring();
     if (!r)
         return GTB_ERR_CUDA;
-    cudaStream_t s = stream ? as_stream(stream) : cudaStreamLegacy;
     int i = 0;
     for (int64_t off = 0; off < bytes; off += (int64_t)kStageChunk, i = (i + 1) % kStageSlots) {
         const size_t n = (size_t)(bytes - off < (int64_t)kStageChunk ? bytes - off : (int64_t)kStageChunk);
@@ -440,10 +481,17 @@ GTB_API int gtb_staged_upload(void *device_dst, const void *host_src, int64_t by
 GTB_API int gtb_staged_download(void *host_dst, const void *device_src, int64_t bytes, void *stream) {
     if (bytes < 0 || (bytes && (!host_dst || !device_src)))
         return fail(GTB_ERR_ARG, "gtb_staged_download: bad argument");
+    if (!dev())
+        return GTB_ERR_CUDA;
+    cudaStream_t s = stream ? as_stream(stream) : cudaStreamLegacy;
+    if (bytes && is_pinned_host(host_dst)) {
+        GTB_CUDA(cudaMemcpyAsync(host_dst, device_src, (size_t)bytes, cudaMemcpyDeviceToHost, s));
+        GTB_CUDA(cudaStreamSynchronize(s));
+        return GTB_OK;
+    }
     stage_ring *r = ring();
     if (!r)
         return GTB_ERR_CUDA;
-    cudaStream_t s = stream ? as_stream(stream) : cudaStreamLegacy;
     const int64_t n_chunks = (bytes + (int64_t)kStageChunk - 1) / (int64_t)kStageChunk;
     auto size_of = [&](int64_t c) {
         const int64_t off = c * (int64_t)kStageChunk;

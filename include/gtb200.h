@@ -286,6 +286,11 @@ int gtb_tensor_map_3d(void *map128, const void *base, int elem_size, const int64
 /* device memory for host bindings that do not include the CUDA runtime (storage traits) */
 int gtb_device_malloc(void **out, int64_t bytes);
 int gtb_device_free(void *p);
+/* Page-locked host memory: a host mirror allocated with it is copied by the copy engine directly (gtb_staged_* skip the
+ * staging ring for pinned memory, whoever pinned it).  The reference's data_store allocates its mirror itself
+ * (storage/data_store.hpp:101-104); patches/gridtools-host-mirror-through-traits.patch routes that through the traits. */
+int gtb_host_malloc(void **out, int64_t bytes);
+int gtb_host_free(void *p);
 int gtb_staged_upload(void *device_dst, const void *host_src, int64_t bytes, void *stream);
 int gtb_staged_download(void *host_dst, const void *device_src, int64_t bytes, void *stream);
 

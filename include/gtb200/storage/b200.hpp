@@ -17,8 +17,9 @@
  *
  * The host mirror itself cannot be pinned by a traits type: data_store allocates it with std::make_unique<T[]>
  * and frees it BEFORE the device holder (storage/data_store.hpp:101-104), so neither cudaHostAlloc nor
- * cudaHostRegister / cudaHostUnregister can be tied to its lifetime from here; INTEGRATION.md section 4 shows the
- * two-line data_store change that would allow it.
+ * cudaHostRegister / cudaHostUnregister can be tied to its lifetime from here.  patches/gridtools-host-mirror-through-
+ * traits.patch is the reference-side change that allows it: with it the mirror comes from
+ * storage_allocate_host below and the transfers skip the staging ring.
  *
  * Plain host code over the C ABI (no CUDA headers needed); link with -lgtb200.
  */
@@ -46,6 +47,9 @@ namespace gridtools {
             struct device_free {
                 void operator()(void *p) const { gtb_device_free(p); }
             };
+            struct host_free {
+                void operator()(void *p) const { gtb_host_free(p); }
+            };
         } // namespace b200_impl_
 
         struct b200 {
@@ -63,6 +67,16 @@ namespace gridtools {
                 void *p = nullptr;
                 b200_impl_::check(gtb_device_malloc(&p, (int64_t)(size * sizeof(T))), "gtb_device_malloc");
                 return std::unique_ptr<T[], b200_impl_::device_free>(static_cast<T *>(p));
+            }
+
+            // The host mirror, page-locked -- used by a data_store that allocates its mirror through the traits
+            // (patches/gridtools-host-mirror-through-traits.patch; the unpatched reference never asks).  The transfers
+            // below then go from / to the mirror directly.
+            template <class LazyType, class T = typename LazyType::type>
+            friend auto storage_allocate_host(b200, LazyType, size_t size) {
+                void *p = nullptr;
+                b200_impl_::check(gtb_host_malloc(&p, (int64_t)(size * sizeof(T))), "gtb_host_malloc");
+                return std::unique_ptr<T[], b200_impl_::host_free>(static_cast<T *>(p));
             }
 
             template <class T>
